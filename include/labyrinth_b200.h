@@ -1,0 +1,149 @@
+/* labyrinth_b200.h -- C ABI of the B200 BFS hot path (liblabyrinth_b200.so).
+ *
+ * The reference (agl-alexglopez/multithreading-with-mazes) has no FFI: its boundary for this path
+ * is a set of C++20-module free functions of type void(Maze::Maze&) kept in std::function tables
+ *   run_maze/run_maze.cc:97-124   "bfs-hunt" / "bfs-gather" / "bfs-corners"  -> Bfs::hunt/gather/corners
+ *   measure/measure.cc:96-101     "distance"                                 -> Distance::paint_distance_from_center
+ * include/labyrinth.hh re-creates those namespaces/names/signatures on top of THIS header, so the
+ * CLIs dispatch unchanged; INTEGRATION.md shows the binding a maintainer would add upstream.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success, a negative lab_status
+ *     otherwise, and lab_last_error() gives the message (the reference prints to stderr and
+ *     std::abort()s instead: solvers/solve_utilities.cc:200-202,247-251; the C++ mirror keeps that).
+ *   - squares: rows*cols uint16_t, dense row-major, exactly Maze::Maze's vector<Square>
+ *     (maze/maze.cc:127-144; sizeof(Square) == 2).  Bit layout: maze/maze.cc:39-55,170-173,
+ *     solvers/solve_utilities.cc:59-79, painters/rgb.cc:21-22.
+ *   - a lab_grid is a maze resident in one GPU's HBM together with the search workspace; it can be
+ *     solved/painted repeatedly without touching the host.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     LAB_ERR_CUDA.
+ */
+#ifndef LABYRINTH_B200_H
+#define LABYRINTH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAB_INF 0xFFFFFFFFu /* level of a wall / unreached square */
+
+typedef enum lab_status {
+    LAB_OK = 0,
+    LAB_ERR_ARG = -1,      /* bad pointer / size / coordinate                                  */
+    LAB_ERR_CUDA = -2,     /* CUDA runtime error (no device, out of memory, launch failure)    */
+    LAB_ERR_TIMEOUT = -3,  /* the persistent search kernel hit its deadline (LAB_BFS_BUDGET_MS) */
+    LAB_ERR_INTERNAL = -4, /* invariant broken inside the search (queue overflow)              */
+    LAB_ERR_PLACE = -5     /* no valid square for a start/finish (reference aborts here)       */
+} lab_status;
+
+/* Maze::Point, maze/maze.cc:116-119 */
+typedef struct lab_point {
+    int32_t row;
+    int32_t col;
+} lab_point;
+
+typedef struct lab_grid lab_grid;
+
+/* Device-side timing of the last search on a grid (CUDA events on the grid's stream), ms. */
+typedef struct lab_timing {
+    float h2d_ms;    /* lab_grid_upload / create-with-host-data            */
+    float setup_ms;  /* workspace reset (memsets)                          */
+    float pack_ms;   /* Square grid -> tile bit masks + border masks       */
+    float search_ms; /* the persistent tile-relaxation kernel              */
+    float post_ms;   /* measure / paint / path kernels                     */
+    float total_ms;  /* setup + pack + search + post                       */
+    float d2h_ms;    /* lab_grid_download / result copies                  */
+} lab_timing;
+
+/* Work counters of the last search (diagnostics; zero cost when unread). */
+typedef struct lab_stats {
+    uint64_t tiles;         /* tiles in the grid                                         */
+    uint64_t activations;   /* tile relaxation passes                                    */
+    uint64_t empty;         /* ... that found nothing to do                              */
+    uint64_t levels;        /* warp-level BFS steps summed over all passes               */
+    uint64_t settled;       /* square settle events (> visited squares if corrections)   */
+    uint64_t rechecks;      /* label-correcting look-ups                                 */
+    uint64_t resettles;     /* squares whose level was lowered after first being settled */
+    uint64_t queue_pushes;  /* tiles handed over through the global queue                */
+    uint64_t direct;        /* tiles the finishing warp walked into itself               */
+    uint32_t worker_warps;  /* warps of the persistent launch                            */
+    uint32_t error;         /* Control.error                                             */
+} lab_stats;
+
+/* ---- grid lifetime (replaces Maze::Maze construction, maze/maze.cc:349-354, for the GPU side) -- */
+/* host_squares may be NULL (grid zero-filled). rows, cols >= 3. */
+int lab_grid_create(int rows, int cols, const uint16_t *host_squares, lab_grid **out);
+/* Borrow device memory the caller owns (e.g. a torch tensor's data_ptr) as the Square array. */
+int lab_grid_create_on_device(int rows, int cols, void *device_squares, lab_grid **out);
+int lab_grid_upload(lab_grid *g, const uint16_t *host_squares);
+int lab_grid_download(lab_grid *g, uint16_t *host_squares);
+int lab_grid_destroy(lab_grid *g);
+/* All later work of this grid is enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream). */
+int lab_grid_set_stream(lab_grid *g, void *cuda_stream);
+void *lab_grid_device_squares(lab_grid *g);
+int lab_grid_rows(const lab_grid *g);
+int lab_grid_cols(const lab_grid *g);
+/* OR `bits` into / AND `mask` onto single squares of the device grid (start/finish placement,
+ * corner carving: bfs_threads.cc:248-251,424-433). */
+int lab_grid_or_bits(lab_grid *g, const lab_point *cells, const uint16_t *bits, int n);
+int lab_grid_and_bits(lab_grid *g, uint16_t mask);
+
+/* ---- Distance::paint_distance_from_center, BFS part (painters/distance.cc:129-153) ------------ */
+/* Levels from (sr, sc) over squares with path_bit set and measure bit clear; the start is expanded
+ * whatever its bits.  Side effect on the grid: Rgb::measure (bit 9) on every reached square.
+ *   dist_host   NULL or rows*cols uint32 (LAB_INF = no map entry); copied D2H when non-NULL
+ *   max_out     Distance_map::max (largest level);   settled_out  Distance_map::distances.size()
+ * The level field stays resident: lab_distance_device() returns it. */
+int lab_distance_map(lab_grid *g, int sr, int sc, uint32_t *dist_host, uint64_t *max_out,
+                     uint64_t *settled_out);
+/* The reference's start square for a rows x cols maze (distance.cc:131-134). */
+lab_point lab_distance_start(int rows, int cols);
+/* Device pointer to plane k's level field of the last search (rows*cols uint32), or NULL. */
+void *lab_levels_device(lab_grid *g, int plane);
+/* Use caller-owned device memory (rows*cols uint32) as plane k's level field from now on. */
+int lab_levels_bind(lab_grid *g, int plane, void *device_levels);
+
+/* ---- Bfs::hunt / gather / corners, thread part (solvers/bfs_threads.cc:35-85,144-185) --------- */
+/* The caller has placed start_bit / finish_bit (and carved the centre for corners) exactly as
+ * Bfs::hunt :245-251, Bfs::gather :335-344, Bfs::corners :422-433 do; lab_place_* below do it on a
+ * host copy with the reference's rules.  Canonical lock-step semantics.
+ * Paths: (row,col) pairs ordered like Bfs_monitor::thread_paths (finish side first, start last,
+ * finish excluded); path buffers are host memory and may be NULL; path_len is always written. */
+int lab_bfs_hunt(lab_grid *g, lab_point start, lab_point finish, int32_t *winner, lab_point *path,
+                 uint64_t path_cap, uint64_t *path_len);
+int lab_bfs_gather(lab_grid *g, lab_point start, const lab_point finishes[4], int32_t claimed_by[4],
+                   lab_point *const paths[4], uint64_t path_cap, uint64_t path_len[4]);
+int lab_bfs_corners(lab_grid *g, const lab_point starts[4], lab_point finish, int32_t *winner,
+                    lab_point *path, uint64_t path_cap, uint64_t *path_len);
+/* Number of squares that received at least one paint/cache bit in the last solver call. */
+uint64_t lab_last_painted(const lab_grid *g);
+
+int lab_last_timing(const lab_grid *g, lab_timing *out);
+int lab_last_stats(const lab_grid *g, lab_stats *out);
+const char *lab_last_error(void);
+
+/* ---- host-side helpers shared with the C++ mirror (no GPU needed) ----------------------------- */
+/* Sutil::is_valid_start_or_finish / find_nearest_square / pick_random_point / set_corner_starts
+ * (solvers/solve_utilities.cc:166-173,229-252,275-285,254-273) on a host copy of the squares.
+ * `seed` stands in for the value the reference draws from std::random_device. */
+int lab_pick_random_point(int rows, int cols, const uint16_t *squares, uint32_t seed, lab_point *out);
+int lab_set_corner_starts(int rows, int cols, const uint16_t *squares, lab_point out[4]);
+/* Placement part of each game on a host copy: sets start/finish bits (and carves the centre). */
+int lab_place_hunt(int rows, int cols, uint16_t *squares, uint32_t seed, lab_point *start, lab_point *finish);
+int lab_place_gather(int rows, int cols, uint16_t *squares, uint32_t seed, lab_point *start, lab_point finishes[4]);
+int lab_place_corners(int rows, int cols, uint16_t *squares, uint32_t seed, lab_point starts[4], lab_point *finish);
+/* Linear-time seeded builders (builders/{arena,grid,recursive_backtracker,kruskal,
+ * wilson_path_carver,mods}.cc): builder in arena|rdfs|grid|kruskal|wilson, mod in none|cross|x. */
+int lab_build_maze(const char *builder, const char *mod, int rows, int cols, uint32_t seed, uint16_t *squares);
+
+/* Library / device probe: fills a short description, returns the number of CUDA devices (0 = none). */
+int lab_device_info(char *buf, size_t buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LABYRINTH_B200_H */

@@ -1,0 +1,325 @@
+// post.cuh -- what happens to the BFS fields after (and just before) the tile search:
+// run initialisation, the Square-grid side effects of each entry point, and path extraction.
+//
+//   distance  painters/distance.cc:138,149     Rgb::measure (bit 9) on every reached square
+//   hunt      solvers/bfs_threads.cc:61,263-274 paint bits, winner's path repainted in one colour
+//   gather    solvers/bfs_threads.cc:158-164,355-364  paint+cache bits, claims, path.front() recolour
+//   corners   solvers/bfs_threads.cc:61          paint bits only (static game does not repaint)
+//
+// The racy parts of the reference are replaced by the canonical lock-step model of
+// SURVEY.md App. A.4 (restated on the CPU in oracle/restate.cc orc_canon_*): colour k paints
+// exactly the squares whose level in k's field is below the level at which k's game ends.
+#pragma once
+#include "engine.cuh"
+
+namespace lab {
+
+enum Game : int { GAME_DISTANCE = 0, GAME_HUNT = 1, GAME_GATHER = 2, GAME_CORNERS = 3 };
+
+struct Paint_rule {
+    uint32_t plane; // which BFS field
+    uint32_t below; // paint squares whose level is < below
+    uint32_t bits;  // Square bits to OR in
+    uint32_t pad;
+};
+
+// Per-run results, device resident; the host reads it once at the end.
+struct Result {
+    int32_t winner;             // hunt/corners: winning colour, -1 none
+    int32_t claimed_by[4];      // gather: colour that claims finish j, -1 unreachable
+    int32_t finish_of[4];       // gather: finish index colour k claims, -1 none
+    uint32_t game_level[4];     // level at which colour k's game ends (D_k), INF if never
+    unsigned long long path_len[4];
+    unsigned long long settled; // squares with a level (distance: map size)
+    unsigned long long max_level;
+    uint32_t n_rules;
+    uint32_t pad;
+    Paint_rule rule[4];
+};
+
+// Host-filled description of one search.
+struct Run_desc {
+    int game;
+    int nplanes;
+    int32_t src_r[MAX_PLANES], src_c[MAX_PLANES]; // -1: this band has no source for plane k
+    int n_targets;
+    int32_t tgt_plane[MAX_TARGETS], tgt_r[MAX_TARGETS], tgt_c[MAX_TARGETS];
+    uint32_t bound_mode;
+};
+
+// One thread.  Control and the queue were memset by the host (0 / 0xFF); this seeds the sources.
+LAB_DEV void init_run_body(Params p, Run_desc d, unsigned long long budget_ns) {
+    Control *ctl = p.ctl;
+    ctl->bound = INF;
+    ctl->bound_mode = d.bound_mode;
+    ctl->n_targets = static_cast<uint32_t>(d.n_targets);
+    for (int j = 0; j < d.n_targets; j++) {
+        ctl->target_plane[j] = static_cast<uint32_t>(d.tgt_plane[j]);
+        ctl->target_tile[j] = static_cast<uint32_t>((d.tgt_r[j] / TS) * p.g.tiles_x + d.tgt_c[j] / TS);
+        ctl->target_cell[j] = static_cast<unsigned long long>(d.tgt_r[j]) * p.g.cols + d.tgt_c[j];
+        ctl->target_val[j] = INF;
+    }
+    for (int k = 0; k < MAX_PLANES; k++) {
+        ctl->src_tile[k] = 0xFFFFFFFFu;
+        ctl->src_rc[k] = 0;
+    }
+    uint32_t pending = 0;
+    for (int k = 0; k < d.nplanes; k++) {
+        if (d.src_r[k] < 0) {
+            continue;
+        }
+        uint32_t const t = static_cast<uint32_t>((d.src_r[k] / TS) * p.g.tiles_x + d.src_c[k] / TS);
+        ctl->src_tile[k] = t;
+        ctl->src_rc[k] = static_cast<uint32_t>(((d.src_r[k] % TS) << 8) | (d.src_c[k] % TS));
+        p.plane[k].state[t] = ST_ACTIVE | ST_DIRTY;
+        p.queue[ctl->tail & p.qmask] = static_cast<uint32_t>(k) * static_cast<uint32_t>(p.g.ntiles) + t;
+        ctl->tail++;
+        pending++;
+    }
+    ctl->pending = pending;
+    ctl->done = pending == 0 ? 1u : 0u;
+    ctl->deadline_ns = lab_clock_ns() + budget_ns;
+}
+
+// Sources are passable whatever their Square says (the reference pushes its start unconditionally).
+// One thread, between pack and cross.
+LAB_DEV void force_sources_body(Geom g, uint64_t *path, Run_desc d) {
+    for (int k = 0; k < d.nplanes; k++) {
+        if (d.src_r[k] >= 0) {
+            source_force_passable(g, path, d.src_r[k], d.src_c[k]);
+        }
+    }
+}
+
+// distance epilogue: measure bit on every visited square + exact count of visited squares.
+// Same row/word item space as pack_body.
+LAB_DEV void measure_body(Geom g, uint16_t *grid, uint64_t const *visited, Result *res, long long gwarp,
+                          long long nwarps, int lane) {
+    long long const total = static_cast<long long>(g.rows) * g.tiles_x;
+    unsigned long long count = 0;
+    for (long long item = gwarp; item < total; item += nwarps) {
+        long long const r = item / g.tiles_x;
+        int const j = static_cast<int>(item % g.tiles_x);
+        uint64_t const v = visited[((r / TS) * g.tiles_x + j) * TS + (r % TS)];
+        if (v == 0) {
+            continue;
+        }
+        int const c0 = j * TS + lane;
+        int const c1 = c0 + 32;
+        if ((v >> lane) & 1) {
+            grid[r * g.cols + c0] |= SQ_MEASURE;
+        }
+        if ((v >> (lane + 32)) & 1) {
+            grid[r * g.cols + c1] |= SQ_MEASURE;
+        }
+        count += static_cast<unsigned long long>(lab_popc64(v));
+    }
+    if (lane == 0 && count) {
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&res->settled), static_cast<uint64_t>(count));
+    }
+}
+
+// exact maximum level (only needed when some square was settled more than once)
+// (res->max_level was zeroed by max_level_prepare_body when the exact pass is needed)
+LAB_DEV void max_level_body(Geom g, uint32_t const *dist, Control const *ctl, Result *res, long long gthread,
+                            long long nthreads) {
+    if (ctl->n_resettles == 0) {
+        return; // every square was settled once: the running maximum is already exact
+    }
+    long long const n = static_cast<long long>(g.rows) * g.cols;
+    uint32_t m = 0;
+    for (long long i = gthread; i < n; i += nthreads) {
+        uint32_t const d = dist[i];
+        if (d != INF && d > m) {
+            m = d;
+        }
+    }
+    m = lab_reduce_max(m);
+    if ((gthread & 31) == 0 && m) {
+        lab_atomic_max(reinterpret_cast<uint32_t *>(&res->max_level), m); // low word of the u64 (little endian)
+    }
+}
+
+LAB_DEV void max_level_prepare_body(Control const *ctl, Result *res) {
+    res->max_level = ctl->n_resettles == 0 ? ctl->max_level : 0ull;
+}
+
+// One thread: turn the targets' levels into the paint rules of the game (orc_canon_* in the oracle).
+LAB_DEV void resolve_body(Params p, Run_desc d, Result *res, int32_t const *finish_rc /* n_targets (r,c) */) {
+    Control const *ctl = p.ctl;
+    res->winner = -1;
+    res->n_rules = 0;
+    for (int k = 0; k < 4; k++) {
+        res->claimed_by[k] = -1;
+        res->finish_of[k] = -1;
+        res->game_level[k] = INF;
+        res->path_len[k] = 0;
+    }
+    if (d.game == GAME_DISTANCE) {
+        max_level_prepare_body(ctl, res);
+        return;
+    }
+    if (d.game == GAME_HUNT) {
+        uint32_t const T = ctl->target_val[0];
+        res->winner = T != INF ? 0 : -1;
+        res->game_level[0] = T;
+        res->n_rules = 1;
+        res->rule[0] = {0u, T, SQ_PAINT_MASK, 0u};
+        return;
+    }
+    if (d.game == GAME_CORNERS) {
+        uint32_t T = INF;
+        int w = -1;
+        for (int k = 0; k < 4; k++) {
+            if (ctl->target_val[k] < T) {
+                T = ctl->target_val[k];
+                w = k;
+            }
+        }
+        res->winner = w;
+        res->n_rules = 4;
+        for (int k = 0; k < 4; k++) {
+            res->game_level[k] = T;
+            res->rule[k] = {static_cast<uint32_t>(k), T, (1u << k) << SQ_PAINT_SHIFT, 0u};
+        }
+        return;
+    }
+    // gather: finishes sorted by (level, row, col); colour k claims the k-th
+    int order[4] = {0, 1, 2, 3};
+    for (int a = 1; a < 4; a++) {
+        for (int b = a; b > 0; b--) {
+            int const x = order[b - 1], y = order[b];
+            uint32_t const dx = ctl->target_val[x], dy = ctl->target_val[y];
+            bool less = dy < dx;
+            if (dy == dx) {
+                less = finish_rc[2 * y] < finish_rc[2 * x]
+                       || (finish_rc[2 * y] == finish_rc[2 * x] && finish_rc[2 * y + 1] < finish_rc[2 * x + 1]);
+            }
+            if (!less) {
+                break;
+            }
+            order[b - 1] = y;
+            order[b] = x;
+        }
+    }
+    res->n_rules = 4;
+    for (int k = 0; k < 4; k++) {
+        uint32_t const D = ctl->target_val[order[k]];
+        res->game_level[k] = D;
+        if (D != INF) {
+            res->claimed_by[order[k]] = k;
+            res->finish_of[k] = order[k];
+        }
+        res->rule[k] = {0u, D, ((1u << k) << SQ_PAINT_SHIFT) | ((1u << k) << SQ_CACHE_SHIFT), 0u};
+    }
+}
+
+// Elementwise: OR each rule's bits into the squares whose level in the rule's field is below the
+// rule's threshold; counts the squares that received any bit into res->settled.
+LAB_DEV void paint_body(Params p, uint16_t *grid, Result *res, long long gthread, long long nthreads) {
+    long long const n = static_cast<long long>(p.g.rows) * p.g.cols;
+    uint32_t const nr = res->n_rules;
+    Paint_rule r[4];
+    for (uint32_t k = 0; k < 4; k++) {
+        r[k] = res->rule[k < nr ? k : 0];
+    }
+    uint32_t painted = 0;
+    bool const same_plane = nr <= 1 || (r[0].plane == r[1].plane && r[0].plane == r[2].plane && r[0].plane == r[3].plane);
+    for (long long i = gthread; i < n; i += nthreads) {
+        uint32_t bits = 0;
+        if (same_plane) {
+            uint32_t const dv = p.plane[r[0].plane].dist[i];
+            for (uint32_t k = 0; k < nr; k++) {
+                bits |= dv < r[k].below ? r[k].bits : 0u;
+            }
+        } else {
+            for (uint32_t k = 0; k < nr; k++) {
+                bits |= p.plane[r[k].plane].dist[i] < r[k].below ? r[k].bits : 0u;
+            }
+        }
+        if (bits) {
+            grid[i] |= static_cast<uint16_t>(bits);
+            painted++;
+        }
+    }
+    painted = lab_reduce_add(painted);
+    if ((gthread & 31) == 0 && painted) {
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&res->settled), static_cast<uint64_t>(painted));
+    }
+}
+
+// Canonical shortest path (orc canonical_path): from the finish step to the FIRST neighbour in
+// N,E,S,W order whose level is one less.  One warp per path; lanes 0..3 read the 4 neighbours.
+// out (may be null) receives (row,col) pairs finish-side first, the start last.
+// If repaint_bits != 0 every path square gets its paint nibble replaced by repaint_bits (hunt).
+// Returns via res->path_len[slot].  `first_only` stops after the first step (gather's path.front()).
+LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int32_t *out,
+                       unsigned long long max_out, uint32_t repaint_bits, int first_only, Result *res, int slot,
+                       int lane) {
+    Geom const &g = p.g;
+    uint32_t const *dist = p.plane[plane].dist;
+    long long r = fr, c = fc;
+    uint32_t d = dist[r * g.cols + c];
+    unsigned long long n = 0;
+    if (d == INF) {
+        if (lane == 0) res->path_len[slot] = 0;
+        return;
+    }
+    int const dr[4] = {-1, 0, 1, 0};
+    int const dc[4] = {0, 1, 0, -1};
+    while (d > 0) {
+        bool hit = false;
+        if (lane < 4) {
+            long long const nr = r + dr[lane], nc = c + dc[lane];
+            if (nr >= 0 && nr < g.rows && nc >= 0 && nc < g.cols) {
+                hit = dist[nr * g.cols + nc] == d - 1;
+            }
+        }
+        uint32_t const m = lab_ballot(hit);
+        if (m == 0) {
+            break; // cannot happen on a converged field
+        }
+        int const k = lab_ffs64(m) - 1;
+        r += dr[k];
+        c += dc[k];
+        d--;
+        if (lane == 0) {
+            if (out && n < max_out) {
+                out[2 * n] = static_cast<int32_t>(r);
+                out[2 * n + 1] = static_cast<int32_t>(c);
+            }
+            if (repaint_bits) {
+                uint16_t const s = grid[r * g.cols + c];
+                grid[r * g.cols + c] = static_cast<uint16_t>((s & ~SQ_PAINT_MASK) | repaint_bits);
+            }
+        }
+        n++;
+        if (first_only) {
+            break;
+        }
+    }
+    if (lane == 0) {
+        res->path_len[slot] = first_only ? static_cast<unsigned long long>(dist[static_cast<long long>(fr) * g.cols + fc]) : n;
+    }
+}
+
+// gather fix-ups, one thread, after paint: the claims (bfs_threads.cc:158-161) and the
+// path.front() recolour in colour order (:355-364).  front_rc = first path square of colour k.
+LAB_DEV void gather_fixup_body(Geom g, uint16_t *grid, Result const *res, int32_t const *finish_rc,
+                               int32_t const *front_rc) {
+    for (int k = 0; k < 4; k++) {
+        int const j = res->finish_of[k];
+        if (j >= 0) {
+            grid[static_cast<long long>(finish_rc[2 * j]) * g.cols + finish_rc[2 * j + 1]]
+                |= static_cast<uint16_t>((1u << k) << SQ_CACHE_SHIFT);
+        }
+    }
+    for (int k = 0; k < 4; k++) {
+        if (res->finish_of[k] >= 0 && res->game_level[k] > 0 && front_rc[2 * k] >= 0) {
+            long long const i = static_cast<long long>(front_rc[2 * k]) * g.cols + front_rc[2 * k + 1];
+            grid[i] = static_cast<uint16_t>((grid[i] & ~SQ_PAINT_MASK) | ((1u << k) << SQ_PAINT_SHIFT));
+        }
+    }
+}
+
+} // namespace lab

@@ -1,0 +1,74 @@
+// simt.cuh -- the handful of warp / memory primitives the kernels use, behind one spelling.
+//
+// Device build (nvcc, sm_100a): each lab_* is the CUDA intrinsic.
+// Host build (tests/simt/): tests/simt/simt_host.hh is included INSTEAD of this file's device
+// half and implements the same names on a 32-fibre lock-step warp emulator, so the kernel
+// bodies in engine.cuh can be executed and checked against the oracle on a machine without a
+// GPU.  That emulator is test infrastructure; the product only ever runs the device half.
+#pragma once
+#include <cstdint>
+
+#if defined(LAB_SIMT_HOST)
+#include "simt_host.hh"
+#else
+
+#define LAB_DEV __device__ __forceinline__
+#define LAB_FULL 0xFFFFFFFFu
+
+LAB_DEV uint32_t lab_shfl_up(uint32_t v, int d) { return __shfl_up_sync(LAB_FULL, v, d); }
+LAB_DEV uint32_t lab_shfl_down(uint32_t v, int d) { return __shfl_down_sync(LAB_FULL, v, d); }
+LAB_DEV uint32_t lab_shfl(uint32_t v, int src) { return __shfl_sync(LAB_FULL, v, src); }
+LAB_DEV uint32_t lab_ballot(bool p) { return __ballot_sync(LAB_FULL, p); }
+LAB_DEV bool lab_any(bool p) { return __any_sync(LAB_FULL, p); }
+LAB_DEV uint32_t lab_reduce_min(uint32_t v) { return __reduce_min_sync(LAB_FULL, v); }
+LAB_DEV uint32_t lab_reduce_max(uint32_t v) { return __reduce_max_sync(LAB_FULL, v); }
+LAB_DEV uint32_t lab_reduce_or(uint32_t v) { return __reduce_or_sync(LAB_FULL, v); }
+LAB_DEV uint32_t lab_reduce_add(uint32_t v) { return __reduce_add_sync(LAB_FULL, v); }
+LAB_DEV void lab_syncwarp() { __syncwarp(); }
+
+LAB_DEV int lab_ffs64(uint64_t v) { return __ffsll(static_cast<long long>(v)); } // 1-based, 0 if none
+LAB_DEV int lab_popc64(uint64_t v) { return __popcll(v); }
+
+// loads that must observe other SMs' stores (L1 is not coherent inside a persistent kernel)
+LAB_DEV uint32_t lab_ld_cg(uint32_t const *p) { return __ldcg(p); }
+LAB_DEV uint64_t lab_ld_cg(uint64_t const *p) {
+    return static_cast<uint64_t>(__ldcg(reinterpret_cast<unsigned long long const *>(p)));
+}
+LAB_DEV uint32_t lab_ld_volatile(uint32_t const *p) { return *reinterpret_cast<uint32_t const volatile *>(p); }
+LAB_DEV uint64_t lab_ld_volatile(uint64_t const *p) { return *reinterpret_cast<uint64_t const volatile *>(p); }
+// read-only data (path masks): non-coherent path is fine
+LAB_DEV uint64_t lab_ld_ro(uint64_t const *p) {
+    return static_cast<uint64_t>(__ldg(reinterpret_cast<unsigned long long const *>(p)));
+}
+LAB_DEV uint32_t lab_ld_ro(uint32_t const *p) { return __ldg(p); }
+LAB_DEV uint16_t lab_ld_ro(uint16_t const *p) { return __ldg(p); }
+LAB_DEV void lab_st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
+LAB_DEV void lab_st_cg(uint64_t *p, uint64_t v) {
+    __stcg(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v));
+}
+LAB_DEV void lab_st_volatile(uint32_t *p, uint32_t v) { *reinterpret_cast<uint32_t volatile *>(p) = v; }
+
+LAB_DEV uint32_t lab_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+LAB_DEV uint64_t lab_atomic_add(uint64_t *p, uint64_t v) {
+    return static_cast<uint64_t>(atomicAdd(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v)));
+}
+LAB_DEV uint32_t lab_atomic_sub(uint32_t *p, uint32_t v) { return atomicSub(p, v); }
+LAB_DEV uint32_t lab_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
+LAB_DEV uint64_t lab_atomic_or(uint64_t *p, uint64_t v) {
+    return static_cast<uint64_t>(atomicOr(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v)));
+}
+LAB_DEV uint32_t lab_atomic_and(uint32_t *p, uint32_t v) { return atomicAnd(p, v); }
+LAB_DEV uint32_t lab_atomic_min(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
+LAB_DEV uint32_t lab_atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
+LAB_DEV uint32_t lab_atomic_cas(uint32_t *p, uint32_t expect, uint32_t v) { return atomicCAS(p, expect, v); }
+LAB_DEV uint32_t lab_atomic_exch(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
+
+LAB_DEV void lab_threadfence() { __threadfence(); }
+LAB_DEV void lab_nanosleep(unsigned ns) { __nanosleep(ns); }
+LAB_DEV uint64_t lab_clock_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+#endif // LAB_SIMT_HOST

@@ -1,0 +1,878 @@
+// lab.cu -- __global__ wrappers of the kernel bodies and the C ABI of include/labyrinth_b200.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a (see ../Makefile).  No torch, no CPU
+// fallback: every compute entry point needs a CUDA device and says so loudly otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/labyrinth_b200.h"
+#include "device/engine.cuh"
+#include "device/post.cuh"
+#include "host/builders.hh"
+#include "host/points.hh"
+
+using namespace lab;
+
+// ------------------------------------------------------------------------------------- kernels
+namespace {
+
+__device__ __forceinline__ long long gwarp_id() {
+    return (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+}
+__device__ __forceinline__ long long nwarps_total() { return (static_cast<long long>(gridDim.x) * blockDim.x) >> 5; }
+__device__ __forceinline__ int lane_id() { return static_cast<int>(threadIdx.x & 31); }
+
+__global__ void __launch_bounds__(256) k_pack(Geom g, uint16_t const *grid, uint64_t *path, uint16_t mask, uint16_t value) {
+    pack_body(g, grid, path, mask, value, gwarp_id(), nwarps_total(), lane_id());
+}
+
+__global__ void __launch_bounds__(256) k_cross(Geom g, uint64_t const *path, uint64_t *cross, uint64_t const *ghost_n,
+                                               uint64_t const *ghost_s) {
+    cross_body(g, path, cross, ghost_n, ghost_s, gwarp_id(), nwarps_total(), lane_id());
+}
+
+__global__ void k_force_sources(Geom g, uint64_t *path, Run_desc d) { force_sources_body(g, path, d); }
+
+__global__ void k_init_run(Params p, Run_desc d, unsigned long long budget_ns) { init_run_body(p, d, budget_ns); }
+
+// The persistent search kernel: every warp is a worker until the search is done.
+__global__ void __launch_bounds__(128) k_bfs_tiles(Params p) { bfs_worker_body(p, lane_id()); }
+
+__global__ void __launch_bounds__(256) k_measure(Geom g, uint16_t *grid, uint64_t const *visited, Result *res) {
+    measure_body(g, grid, visited, res, gwarp_id(), nwarps_total(), lane_id());
+}
+
+__global__ void k_resolve(Params p, Run_desc d, Result *res, int32_t const *finish_rc) {
+    resolve_body(p, d, res, finish_rc);
+}
+
+__global__ void __launch_bounds__(256) k_max_level(Geom g, uint32_t const *dist, Control const *ctl, Result *res) {
+    max_level_body(g, dist, ctl, res, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+                   static_cast<long long>(gridDim.x) * blockDim.x);
+}
+
+__global__ void __launch_bounds__(256) k_paint(Params p, uint16_t *grid, Result *res) {
+    paint_body(p, grid, res, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+               static_cast<long long>(gridDim.x) * blockDim.x);
+}
+
+// One warp per path (blockIdx.x = colour / slot).  The finish and the field are looked up from
+// the resolved result so that no host round trip sits between the search and the walk.
+__global__ void k_walk(Params p, int game, uint16_t *grid, Result *res, int32_t const *finish_rc, int32_t *out,
+                       unsigned long long out_stride, unsigned long long max_out, int first_only) {
+    int const slot = static_cast<int>(blockIdx.x);
+    int plane = 0, fj = 0;
+    uint32_t repaint = 0;
+    if (game == GAME_HUNT) {
+        if (res->winner < 0) {
+            if (lane_id() == 0) res->path_len[slot] = 0;
+            return;
+        }
+        repaint = (1u << res->winner) << SQ_PAINT_SHIFT;
+    } else if (game == GAME_CORNERS) {
+        if (res->winner < 0) {
+            if (lane_id() == 0) res->path_len[slot] = 0;
+            return;
+        }
+        plane = res->winner;
+    } else { // gather: colour `slot`
+        fj = res->finish_of[slot];
+        if (fj < 0) {
+            if (lane_id() == 0) {
+                res->path_len[slot] = 0;
+                if (out) {
+                    out[slot * out_stride * 2] = -1;
+                }
+            }
+            return;
+        }
+    }
+    walk_body(p, plane, finish_rc[2 * fj], finish_rc[2 * fj + 1], grid, out ? out + slot * out_stride * 2 : nullptr,
+              max_out, repaint, first_only, res, slot, lane_id());
+}
+
+__global__ void k_gather_fixup(Geom g, uint16_t *grid, Result const *res, int32_t const *finish_rc,
+                               int32_t const *front_rc) {
+    gather_fixup_body(g, grid, res, finish_rc, front_rc);
+}
+
+__global__ void k_or_bits(uint16_t *grid, long long cols, int32_t const *cells_rc, uint16_t const *bits, int n) {
+    for (int i = static_cast<int>(threadIdx.x); i < n; i += static_cast<int>(blockDim.x)) {
+        grid[static_cast<long long>(cells_rc[2 * i]) * cols + cells_rc[2 * i + 1]] |= bits[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_and_bits(uint16_t *grid, long long n, uint16_t mask) {
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        grid[i] &= mask;
+    }
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------ host side
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, char const *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t const e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                         \
+            return fail(LAB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                \
+    } while (0)
+
+enum Ev { EV_SETUP0, EV_PACK0, EV_SEARCH0, EV_POST0, EV_END, EV_COPY0, EV_COPY1, EV_COUNT };
+
+} // namespace
+
+struct lab_grid {
+    int device = 0;
+    Geom g{};
+    uint16_t *squares = nullptr;
+    bool owns_squares = false;
+    uint64_t *path = nullptr;
+    uint64_t *cross = nullptr;
+    Plane plane[MAX_PLANES]{};
+    bool owns_dist[MAX_PLANES]{};
+    int planes_alloc = 0;
+    Control *ctl = nullptr;
+    uint32_t *queue = nullptr;
+    uint32_t qcap = 0;
+    Result *res = nullptr;
+    int32_t *d_finish_rc = nullptr; // 4 (r,c)
+    int32_t *d_front_rc = nullptr;  // 4 (r,c)
+    int32_t *d_paths = nullptr;     // 4 * path_cap (r,c)
+    unsigned long long path_cap = 0;
+    int32_t *d_cells = nullptr; // scratch for or_bits
+    uint16_t *d_bits = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT]{};
+    int sm_count = 0;
+    int bfs_blocks = 0;
+    int bfs_threads = 128;
+    lab_timing timing{};
+    lab_stats stats{};
+    Result last{};
+    float h2d_ms = 0, d2h_ms = 0;
+};
+
+namespace {
+
+long long env_ll(char const *name, long long dflt) {
+    char const *v = std::getenv(name);
+    return v && *v ? std::atoll(v) : dflt;
+}
+
+int make_geom(int rows, int cols, Geom &g) {
+    if (rows < 3 || cols < 3 || static_cast<long long>(rows) * cols >= (1ll << 32)) {
+        return fail(LAB_ERR_ARG, "bad maze size %dx%d", rows, cols);
+    }
+    g.rows = rows;
+    g.cols = cols;
+    g.tiles_y = (rows + TS - 1) / TS;
+    g.tiles_x = (cols + TS - 1) / TS;
+    g.ntiles = g.tiles_y * g.tiles_x;
+    return LAB_OK;
+}
+
+int grid_common_init(lab_grid *h) {
+    CU(cudaGetDevice(&h->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    size_t const nt = static_cast<size_t>(h->g.ntiles);
+    CU(cudaMalloc(&h->path, nt * TS * sizeof(uint64_t)));
+    CU(cudaMalloc(&h->cross, nt * 4 * sizeof(uint64_t)));
+    CU(cudaMalloc(&h->ctl, sizeof(Control)));
+    CU(cudaMalloc(&h->res, sizeof(Result)));
+    CU(cudaMalloc(&h->d_finish_rc, 8 * sizeof(int32_t)));
+    CU(cudaMalloc(&h->d_front_rc, 8 * sizeof(int32_t)));
+    CU(cudaMalloc(&h->d_cells, 64 * sizeof(int32_t)));
+    CU(cudaMalloc(&h->d_bits, 32 * sizeof(uint16_t)));
+    for (auto &e : h->ev) {
+        CU(cudaEventCreate(&e));
+    }
+    // persistent launch: as many 4-warp blocks as stay resident
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bfs_tiles, h->bfs_threads, 0));
+    long long const want_warps_per_sm = env_ll("LAB_BFS_WARPS_PER_SM", 0);
+    if (want_warps_per_sm > 0) {
+        per_sm = std::max<int>(1, std::min<long long>(per_sm, want_warps_per_sm / (h->bfs_threads / 32)));
+    }
+    h->bfs_blocks = std::max(1, per_sm) * h->sm_count;
+    return LAB_OK;
+}
+
+int ensure_planes(lab_grid *h, int n) {
+    size_t const nt = static_cast<size_t>(h->g.ntiles);
+    size_t const cells = static_cast<size_t>(h->g.rows) * h->g.cols;
+    for (int k = h->planes_alloc; k < n; k++) {
+        Plane &p = h->plane[k];
+        CU(cudaMalloc(&p.visited, nt * TS * sizeof(uint64_t)));
+        CU(cudaMalloc(&p.edges, (nt + 2 * static_cast<size_t>(h->g.tiles_x)) * 4 * TS * sizeof(uint32_t)));
+        CU(cudaMalloc(&p.state, nt * sizeof(uint32_t)));
+        if (!p.dist) {
+            CU(cudaMalloc(&p.dist, cells * sizeof(uint32_t)));
+            h->owns_dist[k] = true;
+        }
+        h->planes_alloc = k + 1;
+    }
+    // queue: every (plane, tile) can be queued at most once at a time, plus one ticket per waiting warp
+    unsigned long long need = static_cast<unsigned long long>(n) * nt + static_cast<unsigned long long>(h->bfs_blocks) * (h->bfs_threads / 32) + 64;
+    uint32_t cap = 1024;
+    while (cap < need * 2) {
+        cap <<= 1;
+    }
+    if (cap > h->qcap) {
+        if (h->queue) {
+            CU(cudaFree(h->queue));
+        }
+        CU(cudaMalloc(&h->queue, static_cast<size_t>(cap) * sizeof(uint32_t)));
+        h->qcap = cap;
+    }
+    return LAB_OK;
+}
+
+Params make_params(lab_grid *h, int nplanes) {
+    Params p{};
+    p.g = h->g;
+    p.path = h->path;
+    p.cross = h->cross;
+    for (int k = 0; k < MAX_PLANES; k++) {
+        p.plane[k] = h->plane[k < nplanes ? k : 0];
+    }
+    p.nplanes = nplanes;
+    p.ctl = h->ctl;
+    p.queue = h->queue;
+    p.qmask = h->qcap - 1;
+    return p;
+}
+
+int blocks_for(lab_grid *h, long long warps_wanted, int threads) {
+    long long const per_block = threads / 32;
+    long long const cap = static_cast<long long>(h->sm_count) * (2048 / threads) * 4; // a few waves
+    long long b = (warps_wanted + per_block - 1) / per_block;
+    return static_cast<int>(std::max<long long>(1, std::min(b, cap)));
+}
+
+// Reset the workspace, pack the grid, run the persistent search.  Leaves EV_POST0 recorded.
+int run_search(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass_value) {
+    int rc = ensure_planes(h, d.nplanes);
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = h->stream;
+    Geom const &g = h->g;
+    size_t const nt = static_cast<size_t>(g.ntiles);
+    size_t const cells = static_cast<size_t>(g.rows) * g.cols;
+    Params p = make_params(h, d.nplanes);
+
+    CU(cudaEventRecord(h->ev[EV_SETUP0], s));
+    CU(cudaMemsetAsync(h->ctl, 0, sizeof(Control), s));
+    CU(cudaMemsetAsync(h->res, 0, sizeof(Result), s));
+    CU(cudaMemsetAsync(h->queue, 0xFF, static_cast<size_t>(h->qcap) * sizeof(uint32_t), s));
+    for (int k = 0; k < d.nplanes; k++) {
+        Plane &pl = h->plane[k];
+        CU(cudaMemsetAsync(pl.visited, 0, nt * TS * sizeof(uint64_t), s));
+        CU(cudaMemsetAsync(pl.edges, 0xFF, (nt + 2 * static_cast<size_t>(g.tiles_x)) * 4 * TS * sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(pl.state, 0, nt * sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(pl.dist, 0xFF, cells * sizeof(uint32_t), s));
+    }
+    CU(cudaEventRecord(h->ev[EV_PACK0], s));
+    long long const pack_items = static_cast<long long>(g.tiles_y) * TS * g.tiles_x;
+    k_pack<<<blocks_for(h, (pack_items + 3) / 4, 256), 256, 0, s>>>(g, h->squares, h->path, pass_mask, pass_value);
+    k_force_sources<<<1, 1, 0, s>>>(g, h->path, d);
+    k_cross<<<blocks_for(h, g.ntiles, 256), 256, 0, s>>>(g, h->path, h->cross, nullptr, nullptr);
+    unsigned long long const budget_ns = static_cast<unsigned long long>(env_ll("LAB_BFS_BUDGET_MS", 20000)) * 1000000ull;
+    k_init_run<<<1, 1, 0, s>>>(p, d, budget_ns);
+    CU(cudaEventRecord(h->ev[EV_SEARCH0], s));
+    k_bfs_tiles<<<h->bfs_blocks, h->bfs_threads, 0, s>>>(p);
+    CU(cudaEventRecord(h->ev[EV_POST0], s));
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+// After the post kernels: record the end, sync, read results/statistics/timings back.
+int finish_run(lab_grid *h) {
+    cudaStream_t s = h->stream;
+    CU(cudaEventRecord(h->ev[EV_END], s));
+    Control c{};
+    CU(cudaMemcpyAsync(&h->last, h->res, sizeof(Result), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&c, h->ctl, sizeof(Control), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    lab_timing &t = h->timing;
+    CU(cudaEventElapsedTime(&t.setup_ms, h->ev[EV_SETUP0], h->ev[EV_PACK0]));
+    CU(cudaEventElapsedTime(&t.pack_ms, h->ev[EV_PACK0], h->ev[EV_SEARCH0]));
+    CU(cudaEventElapsedTime(&t.search_ms, h->ev[EV_SEARCH0], h->ev[EV_POST0]));
+    CU(cudaEventElapsedTime(&t.post_ms, h->ev[EV_POST0], h->ev[EV_END]));
+    CU(cudaEventElapsedTime(&t.total_ms, h->ev[EV_SETUP0], h->ev[EV_END]));
+    t.h2d_ms = h->h2d_ms;
+    lab_stats &st = h->stats;
+    st.tiles = static_cast<uint64_t>(h->g.ntiles);
+    st.activations = c.n_activations;
+    st.empty = c.n_empty;
+    st.levels = c.n_levels;
+    st.settled = c.n_settled;
+    st.rechecks = c.n_rechecks;
+    st.resettles = c.n_resettles;
+    st.queue_pushes = c.n_pushes;
+    st.direct = c.n_direct;
+    st.worker_warps = static_cast<uint32_t>(h->bfs_blocks * (h->bfs_threads / 32));
+    st.error = c.error;
+    if (c.error == 1) {
+        return fail(LAB_ERR_TIMEOUT, "search kernel passed its deadline (LAB_BFS_BUDGET_MS); %llu tiles still active",
+                    static_cast<unsigned long long>(c.pending));
+    }
+    if (c.error) {
+        return fail(LAB_ERR_INTERNAL, "search kernel reported error %u", c.error);
+    }
+    if (c.pending != 0) {
+        return fail(LAB_ERR_INTERNAL, "search ended with %u tiles still active", c.pending);
+    }
+    return LAB_OK;
+}
+
+bool in_grid(lab_grid const *h, lab_point p) { return p.row >= 0 && p.row < h->g.rows && p.col >= 0 && p.col < h->g.cols; }
+
+int ensure_paths(lab_grid *h, unsigned long long cap) {
+    if (cap > h->path_cap) {
+        if (h->d_paths) {
+            CU(cudaFree(h->d_paths));
+            h->d_paths = nullptr;
+        }
+        CU(cudaMalloc(&h->d_paths, static_cast<size_t>(cap) * 4 * 2 * sizeof(int32_t)));
+        h->path_cap = cap;
+    }
+    return LAB_OK;
+}
+
+int grid_blocks(lab_grid *h) { return h->sm_count * 8; }
+
+} // namespace
+
+// ----------------------------------------------------------------------------------------- ABI
+extern "C" {
+
+const char *lab_last_error(void) { return g_error.c_str(); }
+
+int lab_device_info(char *buf, size_t buflen) {
+    int n = 0;
+    cudaError_t const e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        n = 0;
+        (void)cudaGetLastError();
+    }
+    if (buf && buflen) {
+        if (n > 0) {
+            cudaDeviceProp prop;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaGetDeviceProperties(&prop, dev);
+            snprintf(buf, buflen, "%s sm_%d%d, %d SMs, %.1f GB; liblabyrinth_b200 built for sm_100a", prop.name, prop.major,
+                     prop.minor, prop.multiProcessorCount, static_cast<double>(prop.totalGlobalMem) / 1e9);
+        } else {
+            snprintf(buf, buflen, "no CUDA device (%s); liblabyrinth_b200 has no CPU fallback", cudaGetErrorString(e));
+        }
+    }
+    return n;
+}
+
+int lab_grid_create(int rows, int cols, const uint16_t *host_squares, lab_grid **out) {
+    if (!out) {
+        return fail(LAB_ERR_ARG, "out is null");
+    }
+    *out = nullptr;
+    auto *h = new lab_grid();
+    int rc = make_geom(rows, cols, h->g);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+    size_t const bytes = static_cast<size_t>(rows) * cols * sizeof(uint16_t);
+    cudaError_t e = cudaMalloc(&h->squares, bytes);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(LAB_ERR_CUDA, "cudaMalloc(%zu) failed: %s -- liblabyrinth_b200 needs a CUDA device, there is no CPU fallback",
+                    bytes, cudaGetErrorString(e));
+    }
+    h->owns_squares = true;
+    rc = grid_common_init(h);
+    if (rc) {
+        lab_grid_destroy(h);
+        return rc;
+    }
+    if (host_squares) {
+        rc = lab_grid_upload(h, host_squares);
+    } else {
+        e = cudaMemset(h->squares, 0, bytes);
+        rc = e == cudaSuccess ? LAB_OK : fail(LAB_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    if (rc) {
+        lab_grid_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return LAB_OK;
+}
+
+int lab_grid_create_on_device(int rows, int cols, void *device_squares, lab_grid **out) {
+    if (!out || !device_squares) {
+        return fail(LAB_ERR_ARG, "null argument");
+    }
+    *out = nullptr;
+    auto *h = new lab_grid();
+    int rc = make_geom(rows, cols, h->g);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+    h->squares = static_cast<uint16_t *>(device_squares);
+    h->owns_squares = false;
+    rc = grid_common_init(h);
+    if (rc) {
+        lab_grid_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return LAB_OK;
+}
+
+int lab_grid_destroy(lab_grid *h) {
+    if (!h) {
+        return LAB_OK;
+    }
+    if (h->owns_squares) cudaFree(h->squares);
+    cudaFree(h->path);
+    cudaFree(h->cross);
+    for (int k = 0; k < MAX_PLANES; k++) {
+        cudaFree(h->plane[k].visited);
+        cudaFree(h->plane[k].edges);
+        cudaFree(h->plane[k].state);
+        if (h->owns_dist[k]) cudaFree(h->plane[k].dist);
+    }
+    cudaFree(h->ctl);
+    cudaFree(h->queue);
+    cudaFree(h->res);
+    cudaFree(h->d_finish_rc);
+    cudaFree(h->d_front_rc);
+    cudaFree(h->d_paths);
+    cudaFree(h->d_cells);
+    cudaFree(h->d_bits);
+    for (auto &e : h->ev) {
+        if (e) cudaEventDestroy(e);
+    }
+    delete h;
+    return LAB_OK;
+}
+
+int lab_grid_set_stream(lab_grid *h, void *cuda_stream) {
+    if (!h) {
+        return fail(LAB_ERR_ARG, "null grid");
+    }
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return LAB_OK;
+}
+
+void *lab_grid_device_squares(lab_grid *h) { return h ? h->squares : nullptr; }
+int lab_grid_rows(const lab_grid *h) { return h ? h->g.rows : 0; }
+int lab_grid_cols(const lab_grid *h) { return h ? h->g.cols : 0; }
+
+int lab_grid_upload(lab_grid *h, const uint16_t *host_squares) {
+    if (!h || !host_squares) {
+        return fail(LAB_ERR_ARG, "null argument");
+    }
+    size_t const bytes = static_cast<size_t>(h->g.rows) * h->g.cols * sizeof(uint16_t);
+    CU(cudaEventRecord(h->ev[EV_COPY0], h->stream));
+    CU(cudaMemcpyAsync(h->squares, host_squares, bytes, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaEventRecord(h->ev[EV_COPY1], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventElapsedTime(&h->h2d_ms, h->ev[EV_COPY0], h->ev[EV_COPY1]));
+    h->timing.h2d_ms = h->h2d_ms;
+    return LAB_OK;
+}
+
+int lab_grid_download(lab_grid *h, uint16_t *host_squares) {
+    if (!h || !host_squares) {
+        return fail(LAB_ERR_ARG, "null argument");
+    }
+    size_t const bytes = static_cast<size_t>(h->g.rows) * h->g.cols * sizeof(uint16_t);
+    CU(cudaEventRecord(h->ev[EV_COPY0], h->stream));
+    CU(cudaMemcpyAsync(host_squares, h->squares, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev[EV_COPY1], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventElapsedTime(&h->d2h_ms, h->ev[EV_COPY0], h->ev[EV_COPY1]));
+    h->timing.d2h_ms = h->d2h_ms;
+    return LAB_OK;
+}
+
+int lab_grid_or_bits(lab_grid *h, const lab_point *cells, const uint16_t *bits, int n) {
+    if (!h || !cells || !bits || n < 0 || n > 32) {
+        return fail(LAB_ERR_ARG, "bad or_bits arguments");
+    }
+    int32_t rc[64];
+    for (int i = 0; i < n; i++) {
+        if (!in_grid(h, cells[i])) {
+            return fail(LAB_ERR_ARG, "square (%d,%d) outside the maze", cells[i].row, cells[i].col);
+        }
+        rc[2 * i] = cells[i].row;
+        rc[2 * i + 1] = cells[i].col;
+    }
+    if (n == 0) {
+        return LAB_OK;
+    }
+    // stream-ordered staging copies from pageable memory complete before returning
+    CU(cudaMemcpyAsync(h->d_cells, rc, sizeof(int32_t) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_bits, bits, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, h->stream));
+    k_or_bits<<<1, 32, 0, h->stream>>>(h->squares, h->g.cols, h->d_cells, h->d_bits, n);
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+int lab_grid_and_bits(lab_grid *h, uint16_t mask) {
+    if (!h) {
+        return fail(LAB_ERR_ARG, "null grid");
+    }
+    k_and_bits<<<grid_blocks(h), 256, 0, h->stream>>>(h->squares, static_cast<long long>(h->g.rows) * h->g.cols, mask);
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+lab_point lab_distance_start(int rows, int cols) {
+    int const row_mid = rows / 2, col_mid = cols / 2;
+    return {row_mid + 1 - (row_mid % 2), col_mid + 1 - (col_mid % 2)}; // painters/distance.cc:131-134
+}
+
+void *lab_levels_device(lab_grid *h, int plane) {
+    return (h && plane >= 0 && plane < MAX_PLANES) ? h->plane[plane].dist : nullptr;
+}
+
+int lab_levels_bind(lab_grid *h, int plane, void *device_levels) {
+    if (!h || plane < 0 || plane >= MAX_PLANES || !device_levels) {
+        return fail(LAB_ERR_ARG, "bad levels_bind arguments");
+    }
+    if (h->owns_dist[plane] && h->plane[plane].dist) {
+        CU(cudaFree(h->plane[plane].dist));
+    }
+    h->plane[plane].dist = static_cast<uint32_t *>(device_levels);
+    h->owns_dist[plane] = false;
+    return LAB_OK;
+}
+
+int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t *max_out, uint64_t *settled_out) {
+    if (!h) {
+        return fail(LAB_ERR_ARG, "null grid");
+    }
+    if (!in_grid(h, {sr, sc})) {
+        return fail(LAB_ERR_ARG, "start (%d,%d) outside the maze", sr, sc);
+    }
+    Run_desc d{};
+    d.game = GAME_DISTANCE;
+    d.nplanes = 1;
+    for (int k = 0; k < MAX_PLANES; k++) {
+        d.src_r[k] = d.src_c[k] = -1;
+    }
+    d.src_r[0] = sr;
+    d.src_c[0] = sc;
+    d.n_targets = 0;
+    d.bound_mode = BOUND_NONE;
+    // passable <=> path_bit set and measure bit clear (distance.cc:145-148)
+    int rc = run_search(h, d, SQ_PATH | SQ_MEASURE, SQ_PATH);
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = h->stream;
+    Params p = make_params(h, 1);
+    k_resolve<<<1, 1, 0, s>>>(p, d, h->res, h->d_finish_rc);
+    k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
+    long long const items = static_cast<long long>(h->g.rows) * h->g.tiles_x;
+    k_measure<<<blocks_for(h, items, 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
+    CU(cudaGetLastError());
+    rc = finish_run(h);
+    if (rc) {
+        return rc;
+    }
+    if (max_out) *max_out = h->last.max_level;
+    if (settled_out) *settled_out = h->last.settled;
+    if (dist_host) {
+        size_t const bytes = static_cast<size_t>(h->g.rows) * h->g.cols * sizeof(uint32_t);
+        CU(cudaEventRecord(h->ev[EV_COPY0], s));
+        CU(cudaMemcpyAsync(dist_host, h->plane[0].dist, bytes, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(h->ev[EV_COPY1], s));
+        CU(cudaStreamSynchronize(s));
+        CU(cudaEventElapsedTime(&h->timing.d2h_ms, h->ev[EV_COPY0], h->ev[EV_COPY1]));
+    }
+    return LAB_OK;
+}
+
+static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finishes, int nfinish, bool want_paths,
+                         uint64_t path_cap) {
+    int32_t frc[8] = {0};
+    for (int i = 0; i < nfinish; i++) {
+        frc[2 * i] = finishes[i].row;
+        frc[2 * i + 1] = finishes[i].col;
+    }
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_finish_rc, frc, sizeof frc, cudaMemcpyHostToDevice, s));
+    int rc = run_search(h, d, SQ_PATH, SQ_PATH); // passable <=> path_bit (bfs_threads.cc:71-72)
+    if (rc) {
+        return rc;
+    }
+    Params p = make_params(h, d.nplanes);
+    k_resolve<<<1, 1, 0, s>>>(p, d, h->res, h->d_finish_rc);
+    k_paint<<<grid_blocks(h), 256, 0, s>>>(p, h->squares, h->res);
+    if (d.game == GAME_GATHER) {
+        CU(cudaMemsetAsync(h->d_front_rc, 0xFF, 8 * sizeof(int32_t), s));
+        k_walk<<<4, 32, 0, s>>>(p, d.game, h->squares, h->res, h->d_finish_rc, h->d_front_rc, 1, 1, 1);
+        k_gather_fixup<<<1, 1, 0, s>>>(h->g, h->squares, h->res, h->d_finish_rc, h->d_front_rc);
+        if (want_paths) {
+            rc = ensure_paths(h, path_cap);
+            if (rc) {
+                return rc;
+            }
+            k_walk<<<4, 32, 0, s>>>(p, d.game, h->squares, h->res, h->d_finish_rc, h->d_paths, h->path_cap, path_cap, 0);
+        }
+    } else {
+        // hunt repaints the winner's path (bfs_threads.cc:263-274), so it always walks;
+        // corners walks only when the caller wants the path (static corners never repaints)
+        if (d.game == GAME_HUNT || want_paths) {
+            if (want_paths) {
+                rc = ensure_paths(h, path_cap);
+                if (rc) {
+                    return rc;
+                }
+            }
+            k_walk<<<1, 32, 0, s>>>(p, d.game, h->squares, h->res, h->d_finish_rc, want_paths ? h->d_paths : nullptr,
+                                    h->path_cap, want_paths ? path_cap : 0, 0);
+        } else {
+            k_walk<<<1, 32, 0, s>>>(p, d.game, h->squares, h->res, h->d_finish_rc, nullptr, 0, 0, 1);
+        }
+    }
+    CU(cudaGetLastError());
+    return finish_run(h);
+}
+
+static int copy_path(lab_grid *h, int slot, lab_point *dst, uint64_t cap, uint64_t len) {
+    if (!dst || len == 0) {
+        return LAB_OK;
+    }
+    uint64_t const n = std::min<uint64_t>(cap, len);
+    static_assert(sizeof(lab_point) == 2 * sizeof(int32_t), "lab_point layout");
+    CU(cudaMemcpyAsync(dst, h->d_paths + static_cast<size_t>(slot) * h->path_cap * 2, n * sizeof(lab_point),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LAB_OK;
+}
+
+int lab_bfs_hunt(lab_grid *h, lab_point start, lab_point finish, int32_t *winner, lab_point *path, uint64_t path_cap,
+                 uint64_t *path_len) {
+    if (!h || !in_grid(h, start) || !in_grid(h, finish)) {
+        return fail(LAB_ERR_ARG, "bad hunt arguments");
+    }
+    Run_desc d{};
+    d.game = GAME_HUNT;
+    d.nplanes = 1;
+    for (int k = 0; k < MAX_PLANES; k++) {
+        d.src_r[k] = d.src_c[k] = -1;
+    }
+    d.src_r[0] = start.row;
+    d.src_c[0] = start.col;
+    d.n_targets = 1;
+    d.tgt_plane[0] = 0;
+    d.tgt_r[0] = finish.row;
+    d.tgt_c[0] = finish.col;
+    d.bound_mode = BOUND_MIN_ANY;
+    bool const want = path != nullptr && path_cap > 0;
+    int rc = solver_common(h, d, &finish, 1, want, path_cap);
+    if (rc) {
+        return rc;
+    }
+    if (winner) *winner = h->last.winner;
+    if (path_len) *path_len = h->last.path_len[0];
+    return want ? copy_path(h, 0, path, path_cap, h->last.path_len[0]) : LAB_OK;
+}
+
+int lab_bfs_gather(lab_grid *h, lab_point start, const lab_point finishes[4], int32_t claimed_by[4],
+                   lab_point *const paths[4], uint64_t path_cap, uint64_t path_len[4]) {
+    if (!h || !finishes || !in_grid(h, start)) {
+        return fail(LAB_ERR_ARG, "bad gather arguments");
+    }
+    Run_desc d{};
+    d.game = GAME_GATHER;
+    d.nplanes = 1;
+    for (int k = 0; k < MAX_PLANES; k++) {
+        d.src_r[k] = d.src_c[k] = -1;
+    }
+    d.src_r[0] = start.row;
+    d.src_c[0] = start.col;
+    d.n_targets = 4;
+    for (int j = 0; j < 4; j++) {
+        if (!in_grid(h, finishes[j])) {
+            return fail(LAB_ERR_ARG, "finish %d outside the maze", j);
+        }
+        d.tgt_plane[j] = 0;
+        d.tgt_r[j] = finishes[j].row;
+        d.tgt_c[j] = finishes[j].col;
+    }
+    d.bound_mode = BOUND_MAX_ALL;
+    bool const want = paths != nullptr && path_cap > 0;
+    int rc = solver_common(h, d, finishes, 4, want, path_cap);
+    if (rc) {
+        return rc;
+    }
+    for (int k = 0; k < 4; k++) {
+        if (claimed_by) claimed_by[k] = h->last.claimed_by[k];
+        if (path_len) path_len[k] = h->last.path_len[k];
+        if (want && paths[k]) {
+            rc = copy_path(h, k, paths[k], path_cap, h->last.path_len[k]);
+            if (rc) {
+                return rc;
+            }
+        }
+    }
+    return LAB_OK;
+}
+
+int lab_bfs_corners(lab_grid *h, const lab_point starts[4], lab_point finish, int32_t *winner, lab_point *path,
+                    uint64_t path_cap, uint64_t *path_len) {
+    if (!h || !starts || !in_grid(h, finish)) {
+        return fail(LAB_ERR_ARG, "bad corners arguments");
+    }
+    Run_desc d{};
+    d.game = GAME_CORNERS;
+    d.nplanes = 4;
+    d.n_targets = 4;
+    for (int k = 0; k < 4; k++) {
+        if (!in_grid(h, starts[k])) {
+            return fail(LAB_ERR_ARG, "start %d outside the maze", k);
+        }
+        d.src_r[k] = starts[k].row;
+        d.src_c[k] = starts[k].col;
+        d.tgt_plane[k] = k;
+        d.tgt_r[k] = finish.row;
+        d.tgt_c[k] = finish.col;
+    }
+    d.bound_mode = BOUND_MIN_ANY;
+    bool const want = path != nullptr && path_cap > 0;
+    int rc = solver_common(h, d, &finish, 1, want, path_cap);
+    if (rc) {
+        return rc;
+    }
+    if (winner) *winner = h->last.winner;
+    if (path_len) *path_len = h->last.path_len[0];
+    return want ? copy_path(h, 0, path, path_cap, h->last.path_len[0]) : LAB_OK;
+}
+
+uint64_t lab_last_painted(const lab_grid *h) { return h ? h->last.settled : 0; }
+
+int lab_last_timing(const lab_grid *h, lab_timing *out) {
+    if (!h || !out) {
+        return fail(LAB_ERR_ARG, "null argument");
+    }
+    *out = h->timing;
+    return LAB_OK;
+}
+
+int lab_last_stats(const lab_grid *h, lab_stats *out) {
+    if (!h || !out) {
+        return fail(LAB_ERR_ARG, "null argument");
+    }
+    *out = h->stats;
+    return LAB_OK;
+}
+
+// ---- host helpers ---------------------------------------------------------------------------
+int lab_pick_random_point(int rows, int cols, const uint16_t *squares, uint32_t seed, lab_point *out) {
+    if (!squares || !out || rows < 3 || cols < 3) {
+        return fail(LAB_ERR_ARG, "bad arguments");
+    }
+    host::Pt const p = host::pick_random_point(rows, cols, squares, seed);
+    *out = {p.row, p.col};
+    return p.row < 0 ? fail(LAB_ERR_PLACE, "could not place a point") : LAB_OK;
+}
+
+int lab_set_corner_starts(int rows, int cols, const uint16_t *squares, lab_point out[4]) {
+    if (!squares || !out || rows < 3 || cols < 3) {
+        return fail(LAB_ERR_ARG, "bad arguments");
+    }
+    host::Pt s[4];
+    host::set_corner_starts(rows, cols, squares, s);
+    int rc = LAB_OK;
+    for (int i = 0; i < 4; i++) {
+        out[i] = {s[i].row, s[i].col};
+        if (s[i].row < 0) rc = fail(LAB_ERR_PLACE, "could not place corner %d", i);
+    }
+    return rc;
+}
+
+int lab_place_hunt(int rows, int cols, uint16_t *squares, uint32_t seed, lab_point *start, lab_point *finish) {
+    if (!squares || !start || !finish || rows < 3 || cols < 3) {
+        return fail(LAB_ERR_ARG, "bad arguments");
+    }
+    host::Pt s, f;
+    if (!host::place_hunt(rows, cols, squares, seed, s, f)) {
+        return fail(LAB_ERR_PLACE, "could not place start/finish");
+    }
+    *start = {s.row, s.col};
+    *finish = {f.row, f.col};
+    return LAB_OK;
+}
+
+int lab_place_gather(int rows, int cols, uint16_t *squares, uint32_t seed, lab_point *start, lab_point finishes[4]) {
+    if (!squares || !start || !finishes || rows < 3 || cols < 3) {
+        return fail(LAB_ERR_ARG, "bad arguments");
+    }
+    host::Pt s, f[4];
+    if (!host::place_gather(rows, cols, squares, seed, s, f)) {
+        return fail(LAB_ERR_PLACE, "could not place start/finishes");
+    }
+    *start = {s.row, s.col};
+    for (int i = 0; i < 4; i++) {
+        finishes[i] = {f[i].row, f[i].col};
+    }
+    return LAB_OK;
+}
+
+int lab_place_corners(int rows, int cols, uint16_t *squares, uint32_t seed, lab_point starts[4], lab_point *finish) {
+    if (!squares || !starts || !finish || rows < 5 || cols < 5) {
+        return fail(LAB_ERR_ARG, "bad arguments");
+    }
+    host::Pt s[4], f;
+    if (!host::place_corners(rows, cols, squares, seed, s, f)) {
+        return fail(LAB_ERR_PLACE, "could not place corner starts");
+    }
+    for (int i = 0; i < 4; i++) {
+        starts[i] = {s[i].row, s[i].col};
+    }
+    *finish = {f.row, f.col};
+    return LAB_OK;
+}
+
+int lab_build_maze(const char *builder, const char *mod, int rows, int cols, uint32_t seed, uint16_t *squares) {
+    int const rc = host::build_maze(builder, mod, rows, cols, seed, squares);
+    if (rc == -1) return fail(LAB_ERR_ARG, "bad size %dx%d (odd, >= 7) or null pointer", rows, cols);
+    if (rc == -2) return fail(LAB_ERR_ARG, "unknown builder '%s'", builder ? builder : "(null)");
+    if (rc == -3) return fail(LAB_ERR_ARG, "unknown modification '%s'", mod ? mod : "(null)");
+    return LAB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,214 @@
+// emu.cc -- TEST INFRASTRUCTURE: runs the product's kernel BODIES (csrc/device/engine.cuh,
+// post.cuh) on the CPU warp emulator and exposes the same operations as the C ABI, so pytest can
+// compare them with the oracle without a GPU.  The orchestration mirrors csrc/lab.cu.
+#define LAB_SIMT_HOST 1
+#include "simt_host.hh"
+
+#include "../../multithreading-with-mazes_b200/csrc/device/engine.cuh"
+#include "../../multithreading-with-mazes_b200/csrc/device/post.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace lab;
+
+namespace {
+
+struct Workspace {
+    Geom g;
+    std::vector<uint16_t> *grid;
+    std::vector<uint64_t> path, cross;
+    std::vector<uint64_t> visited[MAX_PLANES];
+    std::vector<uint32_t> edges[MAX_PLANES], state[MAX_PLANES], dist[MAX_PLANES];
+    Control ctl;
+    std::vector<uint32_t> queue;
+    Result res;
+};
+
+Params make_params(Workspace &w, int nplanes) {
+    Params p{};
+    p.g = w.g;
+    p.path = w.path.data();
+    p.cross = w.cross.data();
+    for (int k = 0; k < MAX_PLANES; k++) {
+        int const kk = k < nplanes ? k : 0;
+        p.plane[k] = {w.visited[kk].data(), w.edges[kk].data(), w.state[kk].data(), w.dist[kk].data()};
+    }
+    p.nplanes = nplanes;
+    p.ctl = &w.ctl;
+    p.queue = w.queue.data();
+    p.qmask = static_cast<uint32_t>(w.queue.size() - 1);
+    return p;
+}
+
+int search(Workspace &w, uint16_t *grid, int rows, int cols, Run_desc const &d, uint16_t mask, uint16_t value,
+           int nwarps, unsigned sched_seed) {
+    Geom &g = w.g;
+    g.rows = rows;
+    g.cols = cols;
+    g.tiles_y = (rows + TS - 1) / TS;
+    g.tiles_x = (cols + TS - 1) / TS;
+    g.ntiles = g.tiles_y * g.tiles_x;
+    size_t const nt = static_cast<size_t>(g.ntiles), cells = static_cast<size_t>(rows) * cols;
+    w.path.assign(nt * TS, 0);
+    w.cross.assign(nt * 4, 0);
+    for (int k = 0; k < d.nplanes; k++) {
+        w.visited[k].assign(nt * TS, 0);
+        w.edges[k].assign((nt + 2 * static_cast<size_t>(g.tiles_x)) * 4 * TS, INF);
+        w.state[k].assign(nt, 0);
+        w.dist[k].assign(cells, INF);
+    }
+    std::memset(&w.ctl, 0, sizeof w.ctl);
+    std::memset(&w.res, 0, sizeof w.res);
+    size_t cap = 1024;
+    while (cap < 2 * (static_cast<size_t>(d.nplanes) * nt + static_cast<size_t>(nwarps) + 64)) cap <<= 1;
+    w.queue.assign(cap, Q_EMPTY);
+    Params p = make_params(w, d.nplanes);
+
+    simt::launch(nwarps, [&](int wid, int lane) { pack_body(g, grid, w.path.data(), mask, value, wid, nwarps, lane); });
+    force_sources_body(g, w.path.data(), d);
+    simt::launch(nwarps, [&](int wid, int lane) { cross_body(g, w.path.data(), w.cross.data(), nullptr, nullptr, wid, nwarps, lane); });
+    init_run_body(p, d, 60ull * 1000000000ull);
+    simt::launch(nwarps, [&](int, int lane) { bfs_worker_body(p, lane); }, sched_seed);
+    if (w.ctl.error) return -100 - static_cast<int>(w.ctl.error);
+    if (w.ctl.pending != 0) return -200;
+    return 0;
+}
+
+void fill_desc(Run_desc &d) {
+    std::memset(&d, 0, sizeof d);
+    for (int k = 0; k < MAX_PLANES; k++) d.src_r[k] = d.src_c[k] = -1;
+}
+
+void stats_out(Workspace const &w, uint64_t *st) {
+    if (!st) return;
+    st[0] = w.ctl.n_activations;
+    st[1] = w.ctl.n_empty;
+    st[2] = w.ctl.n_levels;
+    st[3] = w.ctl.n_settled;
+    st[4] = w.ctl.n_rechecks;
+    st[5] = w.ctl.n_resettles;
+    st[6] = w.ctl.n_pushes;
+    st[7] = w.ctl.n_direct;
+}
+
+} // namespace
+
+extern "C" {
+
+int emu_distance(int rows, int cols, uint16_t *grid, int sr, int sc, uint32_t *dist_out, uint64_t *max_out,
+                 uint64_t *settled_out, int nwarps, unsigned sched_seed, uint64_t *stats) {
+    Workspace w;
+    Run_desc d;
+    fill_desc(d);
+    d.game = GAME_DISTANCE;
+    d.nplanes = 1;
+    d.src_r[0] = sr;
+    d.src_c[0] = sc;
+    d.bound_mode = BOUND_NONE;
+    int rc = search(w, grid, rows, cols, d, SQ_PATH | SQ_MEASURE, SQ_PATH, nwarps, sched_seed);
+    if (rc) return rc;
+    Params p = make_params(w, 1);
+    int32_t frc[8] = {0};
+    resolve_body(p, d, &w.res, frc);
+    long long const nthreads = static_cast<long long>(nwarps) * 32;
+    simt::launch(nwarps, [&](int wid, int lane) {
+        max_level_body(w.g, w.dist[0].data(), &w.ctl, &w.res, static_cast<long long>(wid) * 32 + lane, nthreads);
+    });
+    simt::launch(nwarps, [&](int wid, int lane) { measure_body(w.g, grid, w.visited[0].data(), &w.res, wid, nwarps, lane); });
+    std::memcpy(dist_out, w.dist[0].data(), w.dist[0].size() * sizeof(uint32_t));
+    *max_out = w.res.max_level;
+    *settled_out = w.res.settled;
+    stats_out(w, stats);
+    return 0;
+}
+
+// game: 1 hunt, 2 gather, 3 corners.  starts: 4 (r,c) (hunt/gather use the first).  finishes: 4 (r,c)
+// (hunt/corners use the first).  paths_out: 4 * max_path (r,c).
+int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *starts, int32_t const *finishes,
+               int32_t *winner, int32_t *claimed_by, int32_t *paths_out, long long max_path, long long *path_len,
+               uint64_t *painted, int nwarps, unsigned sched_seed, uint64_t *stats) {
+    Workspace w;
+    Run_desc d;
+    fill_desc(d);
+    d.game = game;
+    int32_t frc[8] = {0};
+    if (game == GAME_HUNT) {
+        d.nplanes = 1;
+        d.src_r[0] = starts[0];
+        d.src_c[0] = starts[1];
+        d.n_targets = 1;
+        d.tgt_r[0] = finishes[0];
+        d.tgt_c[0] = finishes[1];
+        d.bound_mode = BOUND_MIN_ANY;
+        frc[0] = finishes[0];
+        frc[1] = finishes[1];
+    } else if (game == GAME_GATHER) {
+        d.nplanes = 1;
+        d.src_r[0] = starts[0];
+        d.src_c[0] = starts[1];
+        d.n_targets = 4;
+        for (int j = 0; j < 4; j++) {
+            d.tgt_r[j] = finishes[2 * j];
+            d.tgt_c[j] = finishes[2 * j + 1];
+            frc[2 * j] = finishes[2 * j];
+            frc[2 * j + 1] = finishes[2 * j + 1];
+        }
+        d.bound_mode = BOUND_MAX_ALL;
+    } else {
+        d.nplanes = 4;
+        d.n_targets = 4;
+        for (int k = 0; k < 4; k++) {
+            d.src_r[k] = starts[2 * k];
+            d.src_c[k] = starts[2 * k + 1];
+            d.tgt_plane[k] = k;
+            d.tgt_r[k] = finishes[0];
+            d.tgt_c[k] = finishes[1];
+        }
+        d.bound_mode = BOUND_MIN_ANY;
+        frc[0] = finishes[0];
+        frc[1] = finishes[1];
+    }
+    int rc = search(w, grid, rows, cols, d, SQ_PATH, SQ_PATH, nwarps, sched_seed);
+    if (rc) return rc;
+    Params p = make_params(w, d.nplanes);
+    resolve_body(p, d, &w.res, frc);
+    long long const nthreads = static_cast<long long>(nwarps) * 32;
+    simt::launch(nwarps, [&](int wid, int lane) { paint_body(p, grid, &w.res, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    int32_t front[8];
+    for (auto &x : front) x = -1;
+    auto walk = [&](int slot, int32_t *out, unsigned long long max_out, int first_only) {
+        int plane = 0, fj = 0;
+        uint32_t repaint = 0;
+        if (game == GAME_HUNT) {
+            if (w.res.winner < 0) return;
+            repaint = (1u << w.res.winner) << SQ_PAINT_SHIFT;
+        } else if (game == GAME_CORNERS) {
+            if (w.res.winner < 0) return;
+            plane = w.res.winner;
+        } else {
+            fj = w.res.finish_of[slot];
+            if (fj < 0) return;
+        }
+        simt::launch(1, [&](int, int lane) {
+            walk_body(p, plane, frc[2 * fj], frc[2 * fj + 1], grid, out, max_out, repaint, first_only, &w.res, slot, lane);
+        });
+    };
+    if (game == GAME_GATHER) {
+        for (int k = 0; k < 4; k++) walk(k, front + 2 * k, 1, 1);
+        gather_fixup_body(w.g, grid, &w.res, frc, front);
+        for (int k = 0; k < 4; k++) walk(k, paths_out + static_cast<size_t>(k) * max_path * 2, static_cast<unsigned long long>(max_path), 0);
+    } else {
+        walk(0, paths_out, static_cast<unsigned long long>(max_path), 0);
+    }
+    *winner = w.res.winner;
+    for (int k = 0; k < 4; k++) {
+        claimed_by[k] = w.res.claimed_by[k];
+        path_len[k] = static_cast<long long>(w.res.path_len[k]);
+    }
+    *painted = w.res.settled;
+    stats_out(w, stats);
+    return 0;
+}
+
+} // extern "C"
