@@ -72,6 +72,8 @@ typedef struct lab_stats {
     uint64_t direct;        /* tiles the finishing warp walked into itself               */
     uint32_t worker_warps;  /* warps of the persistent launch                            */
     uint32_t error;         /* Control.error                                             */
+    /* SM cycles summed over worker warps; non-zero only in the -DLAB_PROFILE build */
+    uint64_t cyc_load, cyc_loop, cyc_publish, cyc_idle;
 } lab_stats;
 
 /* ---- grid lifetime (replaces Maze::Maze construction, maze/maze.cc:349-354, for the GPU side) -- */

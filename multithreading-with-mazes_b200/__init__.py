@@ -19,7 +19,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblabyrinth_b200.so")
+LIB_PATH = os.environ.get("LAB_LIB") or os.path.join(HERE, "liblabyrinth_b200.so")
 INF = 0xFFFFFFFF
 
 # Square bits: maze/maze.cc:170-173, solvers/solve_utilities.cc:59-79, painters/rgb.cc:21-22
@@ -56,7 +56,8 @@ class Timing(Structure):
 
 class Stats(Structure):
     _fields_ = [(n, c_uint64) for n in ("tiles", "activations", "empty", "levels", "settled", "rechecks", "resettles",
-                                        "queue_pushes", "direct")] + [("worker_warps", c_uint32), ("error", c_uint32)]
+                                        "queue_pushes", "direct")] + [("worker_warps", c_uint32), ("error", c_uint32)] + [
+        (n, c_uint64) for n in ("cyc_load", "cyc_loop", "cyc_publish", "cyc_idle")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -89,6 +89,8 @@ struct Control {
     unsigned long long deadline_ns; // %globaltimer value after which the workers give up (error 1)
     // statistics
     unsigned long long n_activations, n_empty, n_levels, n_rechecks, n_resettles, n_settled, n_pushes, n_direct;
+    // SM cycles summed over warps (LAB_PROFILE builds only): loading a tile, the level loop, publishing, idle
+    unsigned long long cyc_load, cyc_loop, cyc_publish, cyc_idle;
 };
 
 struct Params {
@@ -101,6 +103,12 @@ struct Params {
     uint32_t *queue;
     uint32_t qmask; // capacity-1 (power of two > planes*ntiles + #warps)
 };
+
+#if defined(LAB_PROFILE)
+#define LAB_PROF(x) x
+#else
+#define LAB_PROF(x)
+#endif
 
 LAB_DEV uint64_t lab_shfl_up64(uint64_t v, int d) {
     uint32_t lo = lab_shfl_up(static_cast<uint32_t>(v), d);
@@ -217,16 +225,6 @@ LAB_DEV void queue_push(Params const &p, uint32_t item) {
     }
 }
 
-// Mark (plane, tile) dirty; returns true if THIS call made it active (caller must run or queue it).
-LAB_DEV bool tile_wake(Params const &p, int plane, long long t) {
-    uint32_t const old = lab_atomic_or(&p.plane[plane].state[t], ST_ACTIVE | ST_DIRTY);
-    if (old & ST_ACTIVE) {
-        return false;
-    }
-    lab_atomic_add(&p.ctl->pending, 1u);
-    return true;
-}
-
 // Seed one source square: forces it passable (the reference pushes its start without looking at
 // path_bit: bfs_threads.cc:41-43, distance.cc:135-138) and makes its tile active.  Call with one
 // thread, BEFORE cross_body.
@@ -237,51 +235,75 @@ LAB_DEV void source_force_passable(Geom g, uint64_t *path, int r, int c) {
 
 // ---------------------------------------------------------------------------------------------
 // One activation of one tile by one warp.
+//
+// A pass = one multi-source BFS over the tile from the SEEDS (border squares whose neighbour
+// across the border offers a better level, and the plane's source square), run level by level
+// in register bitboards.  The level loop does nothing but step: what was settled when is kept
+// BIT-SLICED (six 64-bit planes per row = a 6-bit level counter per square), so a batch of up
+// to 64 levels costs one shuffle + a few LOP3 per level on the critical path, and the levels are
+// written out afterwards square by square (emit_row).  Seeds are injected from bit-sliced planes
+// the same way.  Squares settled by an earlier activation are NOT blocked: the wave may run over
+// them and emit_row keeps the smaller level (atomicMin), which is what makes the relaxation
+// label-correcting without any per-level look-up.  On spanning-tree mazes a wave never meets
+// an already settled square, so nothing is ever written twice.
+
+constexpr int WINDOW = 64; // levels per batch
+
 struct Tile_ctx {
     uint32_t *dist_row0; // &dist[(row0 + 2*lane) * cols + col0]
     uint32_t *edges;     // this tile's [4][64]
     long long cols;
-    int lane;
 };
 
-LAB_DEV void settle_row(Tile_ctx const &tc, uint64_t bits, int which, int row_in_tile, uint32_t lvl) {
+struct Emit_acc {
+    uint32_t wake;      // Side bits: a neighbour can use what was just settled
+    uint32_t max_lvl;
+    uint32_t settled;
+    uint32_t resettled; // squares that already had a level
+};
+
+// One border square of this tile settled at `lvl`: record it in the edge array; wake the
+// neighbour if lvl + 1 beats what it holds across the border (f, 0 = border not crossable here).
+LAB_DEV void edge_update(uint32_t *e, uint32_t lvl, bool old, uint32_t f, int side, Emit_acc &acc) {
+    bool improved = true;
+    if (!old) {
+        *e = lvl;
+    } else {
+        improved = lab_atomic_min(e, lvl) > lvl;
+    }
+    if (improved && lvl + 1 < f) {
+        acc.wake |= 1u << side;
+    }
+}
+
+// Write out the squares of one row settled in the batch.  S = settled squares, Vold = squares that
+// had a level before this pass, B = their level relative to `base`, bit-sliced.
+LAB_DEV void emit_row(Tile_ctx const &tc, uint64_t S, uint64_t Vold, uint64_t const (&B)[6], uint32_t base, int which,
+                      int row_in_tile, uint32_t fW, uint32_t fE, uint32_t fNmax, uint32_t fSmax, Emit_acc &acc) {
     uint32_t *drow = tc.dist_row0 + which * tc.cols;
-    uint64_t w = bits;
-    while (w) {
-        int const c = lab_ffs64(w) - 1;
-        w &= w - 1;
-        drow[c] = lvl;
+    acc.settled += static_cast<uint32_t>(lab_popc64(S));
+    acc.resettled += static_cast<uint32_t>(lab_popc64(S & Vold));
+    while (S) {
+        int const c = lab_ffs64(S) - 1;
+        S &= S - 1;
+        uint32_t k = 0;
+#pragma unroll
+        for (int b = 0; b < 6; b++) {
+            k |= static_cast<uint32_t>((B[b] >> c) & 1ull) << b;
+        }
+        uint32_t const lvl = base + k;
+        bool const old = (Vold >> c) & 1ull;
+        if (!old) {
+            drow[c] = lvl;
+        } else {
+            lab_atomic_min(drow + c, lvl);
+        }
+        acc.max_lvl = lvl > acc.max_lvl ? lvl : acc.max_lvl;
+        if (c == 0) edge_update(tc.edges + SIDE_W * TS + row_in_tile, lvl, old, fW, SIDE_W, acc);
+        if (c == 63) edge_update(tc.edges + SIDE_E * TS + row_in_tile, lvl, old, fE, SIDE_E, acc);
+        if (row_in_tile == 0) edge_update(tc.edges + SIDE_N * TS + c, lvl, old, fNmax, SIDE_N, acc);
+        if (row_in_tile == TS - 1) edge_update(tc.edges + SIDE_S * TS + c, lvl, old, fSmax, SIDE_S, acc);
     }
-    if (bits & 1ull) {
-        tc.edges[SIDE_W * TS + row_in_tile] = lvl;
-    }
-    if (bits >> 63) {
-        tc.edges[SIDE_E * TS + row_in_tile] = lvl;
-    }
-}
-
-LAB_DEV void settle_edge_row(uint32_t *edge, uint64_t bits, uint32_t lvl) {
-    uint64_t w = bits;
-    while (w) {
-        int const c = lab_ffs64(w) - 1;
-        w &= w - 1;
-        edge[c] = lvl;
-    }
-}
-
-// Which neighbours could use the squares just settled at `lvl`?  (bit per Side)
-// A neighbour is woken only if lvl + 1 beats the level it already has across the border, which
-// also stops the wave echoing back into the tile it came from.
-LAB_DEV uint32_t wake_mask(uint64_t b0, uint64_t b1, uint32_t lvl, int lane, uint64_t XN, uint64_t XS,
-                           uint32_t fNmax, uint32_t fSmax, uint32_t fW0, uint32_t fW1, uint32_t fE0,
-                           uint32_t fE1) {
-    uint32_t const l1 = lvl + 1;
-    uint32_t m = 0;
-    m |= (lane == 0 && (b0 & XN) && l1 < fNmax) ? (1u << SIDE_N) : 0u;
-    m |= (lane == 31 && (b1 & XS) && l1 < fSmax) ? (1u << SIDE_S) : 0u;
-    m |= (((b0 & 1ull) && l1 < fW0) || ((b1 & 1ull) && l1 < fW1)) ? (1u << SIDE_W) : 0u;
-    m |= (((b0 >> 63) && l1 < fE0) || ((b1 >> 63) && l1 < fE1)) ? (1u << SIDE_E) : 0u;
-    return m;
 }
 
 // One border square: `seed` = facing level + 1 if that beats what this tile holds, else INF.
@@ -297,6 +319,8 @@ LAB_DEV void load_seed(bool crossing, uint32_t const *facing, uint32_t const *ow
         }
     }
 }
+
+LAB_DEV uint32_t seed_after(uint32_t s, uint32_t lvl) { return (s != INF && s > lvl) ? s : INF; }
 
 // returns the next item this warp should relax itself (ITEM_NONE if none)
 LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
@@ -324,30 +348,40 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
 
     Tile_ctx tc;
     tc.cols = g.cols;
-    tc.lane = lane;
     tc.edges = my_edges;
     tc.dist_row0 = pl.dist + (static_cast<long long>(ty) * TS + r0) * g.cols + static_cast<long long>(tx) * TS;
 
-    uint32_t st_levels = 0, st_rechecks = 0, st_resettles = 0, st_settled = 0;
-    uint32_t st_passes = 0, st_empty = 0;
-    uint32_t woke_total = 0; // sides on which a neighbour must look again (accumulated over reruns)
-    uint32_t max_lvl = 0;
+    // neighbour this lane looks after when waking (lanes 0..3 = Side)
+    long long nb = -1;
+    if (lane == SIDE_N) nb = ty > 0 ? t - g.tiles_x : -1;
+    if (lane == SIDE_S) nb = ty < g.tiles_y - 1 ? t + g.tiles_x : -1;
+    if (lane == SIDE_W) nb = tx > 0 ? t - 1 : -1;
+    if (lane == SIDE_E) nb = tx < g.tiles_x - 1 ? t + 1 : -1;
+    bool owned = false; // this lane's neighbour was made active by us and is ours to run or queue
+
+    uint32_t st_levels = 0, st_passes = 0, st_empty = 0;
+    Emit_acc acc{0u, 0u, 0u, 0u};
+    bool first_pass = true;
+    LAB_PROF(uint64_t pc_load = 0; uint64_t pc_loop = 0; uint64_t pc_pub = 0;)
 
     for (;;) { // rerun while a neighbour dirtied us during the pass
-        if (lane == 0) {
-            lab_atomic_and(&pl.state[t], ~ST_DIRTY);
+        LAB_PROF(uint64_t const pt0 = lab_cycles();)
+        if (!first_pass) {
+            // the tile arrives with DIRTY clear (see the wake protocol below); on a rerun it must be
+            // cleared BEFORE the edges are read again
+            if (lane == 0) {
+                lab_atomic_and(&pl.state[t], ~ST_DIRTY);
+            }
+            lab_threadfence();
+            lab_syncwarp();
         }
-        lab_threadfence();
-        lab_syncwarp();
+        first_pass = false;
 
-        uint64_t V0 = lab_ld_cg(pl.visited + t * TS + r0);
-        uint64_t V1 = lab_ld_cg(pl.visited + t * TS + r1);
-        uint64_t O0 = V0, O1 = V1; // settled by an EARLIER activation and not re-settled by this one
-        uint64_t const V0_in = V0, V1_in = V1;
+        uint64_t const V0 = lab_ld_cg(pl.visited + t * TS + r0);
+        uint64_t const V1 = lab_ld_cg(pl.visited + t * TS + r1);
 
         // ---- seeds: facing edge level + 1 where that beats what this tile has ------------------
         // N/S seeds: lane holds columns lane and lane+32.  W/E seeds: lane holds rows 2*lane, 2*lane+1.
-        // f* = the facing square's level where the border can be crossed, else 0 ("never worth waking").
         uint32_t sN0, sN1, sS0, sS1, sW0, sW1, sE0, sE1;
         uint32_t fN0, fN1, fS0, fS1, fW0, fW1, fE0, fE1;
         load_seed((XN >> lane) & 1, n_edges + SIDE_S * TS + lane, my_edges + SIDE_N * TS + lane, sN0, fN0);
@@ -358,10 +392,6 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
         load_seed((XW >> r1) & 1, w_edges + SIDE_E * TS + r1, my_edges + SIDE_W * TS + r1, sW1, fW1);
         load_seed((XE >> r0) & 1, e_edges + SIDE_W * TS + r0, my_edges + SIDE_E * TS + r0, sE0, fE0);
         load_seed((XE >> r1) & 1, e_edges + SIDE_W * TS + r1, my_edges + SIDE_E * TS + r1, sE1, fE1);
-        // a row-0 / row-63 square settled at level L can only help the tile above / below if
-        // L + 1 beats the WORST level over there (conservative: exact per-column test not needed)
-        uint32_t const fNmax = lab_reduce_max(fN0 > fN1 ? fN0 : fN1);
-        uint32_t const fSmax = lab_reduce_max(fS0 > fS1 ? fS0 : fS1);
         // The plane's source square, if it lies in this tile and is not settled yet, is a level-0 seed.
         uint64_t src0 = 0, src1 = 0;
         if (ctl->src_tile[plane] == static_cast<uint32_t>(t)) {
@@ -372,147 +402,159 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
         }
         uint32_t sSrc = (src0 | src1) ? 0u : INF;
 
-        uint32_t pending_min = lab_umin(lab_umin(lab_min3(sN0, sN1, sS0), lab_min3(sS1, sW0, sW1)),
-                                        lab_min3(sE0, sE1, sSrc));
+        uint32_t pending_min = lab_umin(lab_umin(lab_min3(sN0, sN1, sS0), lab_min3(sS1, sW0, sW1)), lab_min3(sE0, sE1, sSrc));
         pending_min = lab_reduce_min(pending_min);
         st_passes++;
+        LAB_PROF(uint64_t const pt1 = lab_cycles(); pc_load += pt1 - pt0;)
 
-        uint32_t chg = 0;
+        acc.wake = 0;
         if (pending_min == INF) {
             st_empty++;
         } else {
-            uint32_t lvl = pending_min;
+            // a row-0 / row-63 square settled at level L can only help the tile above / below if L + 1
+            // beats the WORST level over there (conservative; the exact per-column test is not needed)
+            uint32_t const fNmax = XN ? lab_reduce_max(fN0 > fN1 ? fN0 : fN1) : 0u;
+            uint32_t const fSmax = XS ? lab_reduce_max(fS0 > fS1 ? fS0 : fS1) : 0u;
+            bool const any_ns = lab_any((sN0 & sN1 & sS0 & sS1) != INF);
+            uint64_t A0 = P0, A1 = P1; // squares this pass may still settle
+            uint64_t Vn0 = V0, Vn1 = V1;
             uint64_t F0 = 0, F1 = 0;
+            uint32_t base = pending_min; // level of the first iteration of the batch
             uint32_t bound = lab_ld_volatile(&ctl->bound);
-            for (;;) {
-                // ---- inject the seeds whose level is `lvl` ---------------------------------------
-                if (lvl == pending_min) {
-                    uint64_t const nrow = lab_ballot64(sN0 == lvl, sN1 == lvl); // -> row 0  (lane 0, r0)
-                    uint64_t const srow = lab_ballot64(sS0 == lvl, sS1 == lvl); // -> row 63 (lane 31, r1)
-                    uint64_t i0 = (sW0 == lvl ? 1ull : 0ull) | (sE0 == lvl ? (1ull << 63) : 0ull);
-                    uint64_t i1 = (sW1 == lvl ? 1ull : 0ull) | (sE1 == lvl ? (1ull << 63) : 0ull);
-                    if (lane == 0) i0 |= nrow;
-                    if (lane == 31) i1 |= srow;
-                    if (sSrc == lvl) {
-                        i0 |= src0;
-                        i1 |= src1;
+            while (base <= bound) { // ---- one batch of up to WINDOW levels ------------------------
+                uint64_t B0[6] = {0, 0, 0, 0, 0, 0}, B1[6] = {0, 0, 0, 0, 0, 0};
+                uint64_t const A0s = A0, A1s = A1;
+                // seeds relative to the batch base (anything outside [0, 63] never matches)
+                uint32_t const rW0 = sW0 - base, rW1 = sW1 - base, rE0 = sE0 - base, rE1 = sE1 - base, rSrc = sSrc - base;
+                // N seeds land in row 0 (lane 0, r0), S seeds in row 63 (lane 31, r1): bit-sliced by ballots
+                uint64_t nsv = 0, nsp[6] = {0, 0, 0, 0, 0, 0};
+                if (any_ns) {
+                    uint32_t const rN0 = sN0 - base, rN1 = sN1 - base, rS0 = sS0 - base, rS1 = sS1 - base;
+                    bool const vN0 = rN0 < WINDOW, vN1 = rN1 < WINDOW, vS0 = rS0 < WINDOW, vS1 = rS1 < WINDOW;
+                    uint64_t const wn = lab_ballot64(vN0, vN1), ws = lab_ballot64(vS0, vS1);
+                    nsv = lane == 0 ? wn : (lane == 31 ? ws : 0ull);
+                    if (wn | ws) {
+#pragma unroll
+                        for (int b = 0; b < 6; b++) {
+                            uint64_t const pn = lab_ballot64(vN0 && ((rN0 >> b) & 1), vN1 && ((rN1 >> b) & 1));
+                            uint64_t const ps = lab_ballot64(vS0 && ((rS0 >> b) & 1), vS1 && ((rS1 >> b) & 1));
+                            nsp[b] = lane == 0 ? pn : (lane == 31 ? ps : 0ull);
+                        }
                     }
-                    // not if this activation already settled the square at a level <= lvl
-                    i0 &= ~(V0 & ~O0);
-                    i1 &= ~(V1 & ~O1);
-                    st_resettles += lab_popc64(i0 & O0) + lab_popc64(i1 & O1);
-                    V0 |= i0;
-                    V1 |= i1;
-                    O0 &= ~i0;
-                    O1 &= ~i1;
-                    F0 |= i0;
-                    F1 |= i1;
-                    if (i0 | i1) {
-                        settle_row(tc, i0, 0, r0, lvl);
-                        settle_row(tc, i1, 1, r1, lvl);
-                        if (lane == 0 && i0) settle_edge_row(my_edges + SIDE_N * TS, i0, lvl);
-                        if (lane == 31 && i1) settle_edge_row(my_edges + SIDE_S * TS, i1, lvl);
-                        st_settled += lab_popc64(i0) + lab_popc64(i1);
-                        if (lvl > max_lvl) max_lvl = lvl;
-                        chg |= wake_mask(i0, i1, lvl, lane, XN, XS, fNmax, fSmax, fW0, fW1, fE0, fE1);
+                }
+                int gi = 0; // groups of 8 levels completed
+                for (; gi < WINDOW / 8; gi++) {
+                    if (base + 8u * static_cast<uint32_t>(gi) > bound) {
+                        break;
                     }
-                    if (sN0 == lvl) sN0 = INF;
-                    if (sN1 == lvl) sN1 = INF;
-                    if (sS0 == lvl) sS0 = INF;
-                    if (sS1 == lvl) sS1 = INF;
-                    if (sW0 == lvl) sW0 = INF;
-                    if (sW1 == lvl) sW1 = INF;
-                    if (sE0 == lvl) sE0 = INF;
-                    if (sE1 == lvl) sE1 = INF;
-                    if (sSrc == lvl) sSrc = INF;
-                    pending_min = lab_umin(lab_umin(lab_min3(sN0, sN1, sS0), lab_min3(sS1, sW0, sW1)),
-                                           lab_min3(sE0, sE1, sSrc));
+                    // N/S seeds whose level is in this group: high 3 bits of their relative level == gi
+                    uint64_t gm = nsv;
+                    gm &= (gi & 1) ? nsp[3] : ~nsp[3];
+                    gm &= (gi & 2) ? nsp[4] : ~nsp[4];
+                    gm &= (gi & 4) ? nsp[5] : ~nsp[5];
+                    uint64_t G0 = 0, G1 = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        uint32_t const rel = 8u * static_cast<uint32_t>(gi) + static_cast<uint32_t>(j);
+                        // lanes 0 / 31 get their own row back from the out-of-range shuffle: harmless, it is
+                        // already OR-ed in below
+                        uint64_t const up = lab_shfl_up64(F1, 1);     // row 2*lane-1
+                        uint64_t const down = lab_shfl_down64(F0, 1); // row 2*lane+2
+                        uint64_t m = gm;
+                        m &= (j & 1) ? nsp[0] : ~nsp[0];
+                        m &= (j & 2) ? nsp[1] : ~nsp[1];
+                        m &= (j & 4) ? nsp[2] : ~nsp[2];
+                        uint64_t i0 = (rW0 == rel ? 1ull : 0ull) | (rE0 == rel ? (1ull << 63) : 0ull) | (rSrc == rel ? src0 : 0ull);
+                        uint64_t i1 = (rW1 == rel ? 1ull : 0ull) | (rE1 == rel ? (1ull << 63) : 0ull) | (rSrc == rel ? src1 : 0ull);
+                        i0 |= lane == 0 ? m : 0ull;
+                        i1 |= lane == 31 ? m : 0ull;
+                        uint64_t const N0 = ((F0 << 1) | (F0 >> 1) | F1 | up | i0) & A0;
+                        uint64_t const N1 = ((F1 << 1) | (F1 >> 1) | F0 | down | i1) & A1;
+                        A0 &= ~N0;
+                        A1 &= ~N1;
+                        if (j & 1) { B0[0] |= N0; B1[0] |= N1; }
+                        if (j & 2) { B0[1] |= N0; B1[1] |= N1; }
+                        if (j & 4) { B0[2] |= N0; B1[2] |= N1; }
+                        G0 |= N0;
+                        G1 |= N1;
+                        F0 = N0;
+                        F1 = N1;
+                    }
+                    if (gi & 1) { B0[3] |= G0; B1[3] |= G1; }
+                    if (gi & 2) { B0[4] |= G0; B1[4] |= G1; }
+                    if (gi & 4) { B0[5] |= G0; B1[5] |= G1; }
+                    st_levels += 8;
+                    if (!lab_any((F0 | F1) != 0)) {
+                        // nothing moving: skip to the group holding the next seed of this window, if any
+                        uint32_t const done_lvl = base + 8u * static_cast<uint32_t>(gi) + 7u;
+                        uint32_t nxt = lab_umin(lab_umin(lab_min3(seed_after(sN0, done_lvl), seed_after(sN1, done_lvl), seed_after(sS0, done_lvl)),
+                                                         lab_min3(seed_after(sS1, done_lvl), seed_after(sW0, done_lvl), seed_after(sW1, done_lvl))),
+                                                lab_min3(seed_after(sE0, done_lvl), seed_after(sE1, done_lvl), seed_after(sSrc, done_lvl)));
+                        nxt = lab_reduce_min(nxt);
+                        if (nxt == INF || nxt - base >= static_cast<uint32_t>(WINDOW) || nxt > bound) {
+                            gi++;
+                            break;
+                        }
+                        gi = static_cast<int>((nxt - base) / 8u) - 1; // the loop increment lands on its group
+                    }
+                }
+                // ---- write the batch out ---------------------------------------------------------
+                uint64_t const S0 = A0s & ~A0, S1 = A1s & ~A1;
+                if (S0 | S1) {
+                    emit_row(tc, S0, V0, B0, base, 0, r0, fW0, fE0, fNmax, fSmax, acc);
+                    emit_row(tc, S1, V1, B1, base, 1, r1, fW1, fE1, fNmax, fSmax, acc);
+                    Vn0 |= S0;
+                    Vn1 |= S1;
+                }
+                if (gi == 0) {
+                    break; // bound reached before anything ran
+                }
+                uint32_t const done_lvl = base + 8u * static_cast<uint32_t>(gi) - 1u;
+                sN0 = seed_after(sN0, done_lvl);
+                sN1 = seed_after(sN1, done_lvl);
+                sS0 = seed_after(sS0, done_lvl);
+                sS1 = seed_after(sS1, done_lvl);
+                sW0 = seed_after(sW0, done_lvl);
+                sW1 = seed_after(sW1, done_lvl);
+                sE0 = seed_after(sE0, done_lvl);
+                sE1 = seed_after(sE1, done_lvl);
+                sSrc = seed_after(sSrc, done_lvl);
+                bound = lab_ld_volatile(&ctl->bound);
+                if (lab_any((F0 | F1) != 0)) {
+                    base = done_lvl + 1; // the wave is still moving: next batch continues from it
+                } else {
+                    pending_min = lab_umin(lab_umin(lab_min3(sN0, sN1, sS0), lab_min3(sS1, sW0, sW1)), lab_min3(sE0, sE1, sSrc));
                     pending_min = lab_reduce_min(pending_min);
-                }
-                if (lvl >= bound) {
-                    break; // nothing at or beyond the bound needs expanding
-                }
-                // ---- one BFS level ----------------------------------------------------------------
-                uint64_t up = lab_shfl_up64(F1, 1);     // row 2*lane-1
-                uint64_t down = lab_shfl_down64(F0, 1); // row 2*lane+2
-                if (lane == 0) up = 0;
-                if (lane == 31) down = 0;
-                uint64_t const C0 = ((F0 << 1) | (F0 >> 1) | up | F1) & P0;
-                uint64_t const C1 = ((F1 << 1) | (F1 >> 1) | F0 | down) & P1;
-                uint64_t N0 = C0 & ~V0;
-                uint64_t N1 = C1 & ~V1;
-                uint64_t const R0 = C0 & O0;
-                uint64_t const R1 = C1 & O1;
-                uint32_t const nl = lvl + 1;
-                st_levels++;
-                if (lab_any((R0 | R1) != 0)) {
-                    // label-correcting slow path: the wave touches squares an earlier activation
-                    // settled; they are re-settled only if this wave is strictly better.
-                    uint64_t w = R0;
-                    uint32_t *d0 = tc.dist_row0;
-                    while (w) {
-                        int const c = lab_ffs64(w) - 1;
-                        w &= w - 1;
-                        st_rechecks++;
-                        if (lab_ld_cg(d0 + c) > nl) {
-                            N0 |= 1ull << c;
-                            O0 &= ~(1ull << c);
-                            st_resettles++;
-                        }
-                    }
-                    w = R1;
-                    uint32_t *d1 = tc.dist_row0 + tc.cols;
-                    while (w) {
-                        int const c = lab_ffs64(w) - 1;
-                        w &= w - 1;
-                        st_rechecks++;
-                        if (lab_ld_cg(d1 + c) > nl) {
-                            N1 |= 1ull << c;
-                            O1 &= ~(1ull << c);
-                            st_resettles++;
-                        }
-                    }
-                }
-                V0 |= N0;
-                V1 |= N1;
-                if (N0 | N1) {
-                    settle_row(tc, N0, 0, r0, nl);
-                    settle_row(tc, N1, 1, r1, nl);
-                    if (lane == 0 && N0) settle_edge_row(my_edges + SIDE_N * TS, N0, nl);
-                    if (lane == 31 && N1) settle_edge_row(my_edges + SIDE_S * TS, N1, nl);
-                    st_settled += lab_popc64(N0) + lab_popc64(N1);
-                    if (nl > max_lvl) max_lvl = nl;
-                    chg |= wake_mask(N0, N1, nl, lane, XN, XS, fNmax, fSmax, fW0, fW1, fE0, fE1);
-                }
-                F0 = N0;
-                F1 = N1;
-                lvl = nl;
-                if (!lab_any((F0 | F1) != 0)) {
                     if (pending_min == INF) {
                         break;
                     }
-                    lvl = pending_min; // nothing moving: jump to the next seed level
-                    bound = lab_ld_volatile(&ctl->bound);
-                    if (lvl >= bound) {
-                        break;
-                    }
+                    base = pending_min; // jump to the next seed level
                 }
             }
-            if ((V0 != V0_in) | (V1 != V1_in)) {
-                lab_st_cg(pl.visited + t * TS + r0, V0);
-                lab_st_cg(pl.visited + t * TS + r1, V1);
+            if ((Vn0 != V0) | (Vn1 != V1)) {
+                lab_st_cg(pl.visited + t * TS + r0, Vn0);
+                lab_st_cg(pl.visited + t * TS + r1, Vn1);
             }
         }
-        chg = lab_reduce_or(chg);
-        woke_total |= chg;
+        uint32_t const woke = lab_reduce_or(acc.wake);
+        bool const settled_any = lab_any(acc.settled != 0);
+        LAB_PROF(uint64_t const pt2 = lab_cycles(); pc_loop += pt2 - pt1;)
 
-        // ---- publish: everything above must be visible before any flag below -------------------
-        lab_threadfence();
+        // ---- publish ----------------------------------------------------------------------------
+        // wake protocol: a neighbour is taken with CAS(idle -> ACTIVE), i.e. it starts with DIRTY
+        // clear and needs no clearing round trip before it reads the edges; if it is already
+        // active it is marked DIRTY instead and whoever runs it goes round again.
+        bool const attempt = lane < 4 && ((woke >> lane) & 1u) && nb >= 0 && !owned;
+        uint32_t const n_attempt = static_cast<uint32_t>(lab_popc64(lab_ballot(attempt)));
+        if (lane == 0 && n_attempt) {
+            lab_atomic_add(&ctl->pending, n_attempt); // over-counts until the failures are taken back
+        }
+        lab_threadfence(); // levels, edges and visited bits above are visible before any flag below
         lab_syncwarp();
 
         // targets in this tile: refresh their values and the search bound
         uint32_t const ntg = ctl->n_targets;
-        if (ntg && lane == 0) {
+        if (ntg && lane == 0 && settled_any) {
             bool touched = false;
             for (uint32_t j = 0; j < ntg; j++) {
                 if (ctl->target_plane[j] == static_cast<uint32_t>(plane) && ctl->target_tile[j] == static_cast<uint32_t>(t)) {
@@ -539,74 +581,81 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
             }
         }
 
-        // try to go idle; if somebody dirtied us meanwhile, go round again
-        uint32_t again = 0;
-        if (lane == 0) {
-            uint32_t const old = lab_atomic_cas(&pl.state[t], ST_ACTIVE, 0u);
-            again = (old != ST_ACTIVE) ? 1u : 0u;
+        // one round trip: lanes 0..3 try to take their neighbour, lane 4 tries to let this tile go idle
+        uint32_t r = 0;
+        if (attempt) {
+            r = lab_atomic_cas(&pl.state[nb], 0u, ST_ACTIVE);
+        } else if (lane == 4) {
+            r = lab_atomic_cas(&pl.state[t], ST_ACTIVE, 0u);
         }
-        again = lab_shfl(again, 0);
+        bool failed = attempt && r != 0u;
+        if (attempt && !failed) {
+            owned = true;
+        }
+        if (lab_any(failed)) {
+            if (failed) { // already active over there: make sure it looks again
+                uint32_t const old = lab_atomic_or(&pl.state[nb], ST_ACTIVE | ST_DIRTY);
+                if (!(old & ST_ACTIVE)) {
+                    owned = true; // it went idle in between: ours after all (it will do one spurious rerun)
+                } else {
+                    lab_atomic_sub(&ctl->pending, 1u);
+                }
+            }
+        }
+        uint32_t const again = lab_shfl(r != ST_ACTIVE ? 1u : 0u, 4);
+        LAB_PROF(pc_pub += lab_cycles() - pt2;)
         if (!again) {
             break;
         }
     }
+    LAB_PROF(uint64_t const pt3 = lab_cycles();)
 
-    // ---- wake the neighbours whose facing edge changed; keep one for ourselves ------------------
+    // ---- hand the woken neighbours on: keep the first for ourselves, queue the rest --------------
+    uint32_t const own_mask = lab_ballot(owned);
     uint32_t next = ITEM_NONE;
-    if (lane == 0) {
-        uint32_t const base = static_cast<uint32_t>(plane) * static_cast<uint32_t>(g.ntiles);
-        long long nb[4];
-        nb[SIDE_N] = ty > 0 ? t - g.tiles_x : -1;
-        nb[SIDE_S] = ty < g.tiles_y - 1 ? t + g.tiles_x : -1;
-        nb[SIDE_W] = tx > 0 ? t - 1 : -1;
-        nb[SIDE_E] = tx < g.tiles_x - 1 ? t + 1 : -1;
-        unsigned pushes = 0, direct = 0;
-        for (int s = 0; s < 4; s++) {
-            if (((woke_total >> s) & 1u) && nb[s] >= 0 && tile_wake(p, plane, nb[s])) {
-                uint32_t const it = base + static_cast<uint32_t>(nb[s]);
-                if (next == ITEM_NONE) {
-                    next = it;
-                    direct++;
-                } else {
-                    queue_push(p, it);
-                    pushes++;
-                }
-            }
-        }
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_activations), static_cast<uint64_t>(st_passes));
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_empty), static_cast<uint64_t>(st_empty));
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_levels), static_cast<uint64_t>(st_levels));
-        if (pushes) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_pushes), static_cast<uint64_t>(pushes));
-        if (direct) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_direct), static_cast<uint64_t>(direct));
-        // this tile is idle now
-        uint32_t const left = lab_atomic_sub(&ctl->pending, 1u) - 1u;
-        if (left == 0u) {
-            lab_st_volatile(&ctl->done, 1u);
+    if (own_mask) {
+        int const first = lab_ffs64(own_mask) - 1;
+        uint32_t const base_item = static_cast<uint32_t>(plane) * static_cast<uint32_t>(g.ntiles);
+        uint32_t const mine = owned ? base_item + static_cast<uint32_t>(nb) : ITEM_NONE;
+        next = lab_shfl(mine, first);
+        if (owned && lane != first) {
+            queue_push(p, mine);
         }
     }
-    // per-lane statistics
+    if (lane == 0) {
+        unsigned const n_own = static_cast<unsigned>(lab_popc64(own_mask));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_activations), static_cast<uint64_t>(st_passes));
+        if (st_empty) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_empty), static_cast<uint64_t>(st_empty));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_levels), static_cast<uint64_t>(st_levels));
+        if (n_own > 1) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_pushes), static_cast<uint64_t>(n_own - 1));
+        if (n_own) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_direct), 1ull);
+        lab_atomic_sub(&ctl->pending, 1u); // this tile is idle now
+    }
     {
-        uint32_t const s_set = lab_reduce_add(static_cast<uint32_t>(st_settled));
-        uint32_t const s_rec = lab_reduce_add(static_cast<uint32_t>(st_rechecks));
-        uint32_t const s_res = lab_reduce_add(static_cast<uint32_t>(st_resettles));
-        uint32_t const s_max = lab_reduce_max(max_lvl);
+        uint32_t const s_set = lab_reduce_add(acc.settled);
+        uint32_t const s_res = lab_reduce_add(acc.resettled);
+        uint32_t const s_max = lab_reduce_max(acc.max_lvl);
         if (lane == 0) {
             if (s_set) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_settled), static_cast<uint64_t>(s_set));
-            if (s_rec) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_rechecks), static_cast<uint64_t>(s_rec));
             if (s_res) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_resettles), static_cast<uint64_t>(s_res));
             if (s_max) lab_atomic_max(&ctl->max_level, s_max);
         }
     }
-    next = lab_shfl(next, 0);
+    LAB_PROF(if (lane == 0) {
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_load), pc_load);
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_loop), pc_loop);
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_publish), pc_pub + (lab_cycles() - pt3));
+    })
     return next;
 }
 
-// The persistent worker: every warp of the launch runs this until the search is done.
+// The persistent worker: every warp of the launch runs this until no tile is active any more.
 LAB_DEV void bfs_worker_body(Params const &p, int lane) {
     Control *ctl = p.ctl;
     uint32_t item = ITEM_NONE;
     for (;;) {
         if (item == ITEM_NONE) {
+            LAB_PROF(uint64_t const pi0 = lab_cycles();)
             if (lane == 0) {
                 unsigned long long const h = lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->head), 1ull);
                 uint32_t *slot = &p.queue[h & p.qmask];
@@ -618,7 +667,8 @@ LAB_DEV void bfs_worker_body(Params const &p, int lane) {
                         lab_st_volatile(slot, Q_EMPTY);
                         break;
                     }
-                    if ((polls & 3u) == 0u && lab_ld_volatile(&ctl->done)) {
+                    // pending only ever OVER-counts the active tiles, so zero means the search is over
+                    if ((polls & 3u) == 0u && (lab_ld_volatile(&ctl->pending) == 0u || lab_ld_volatile(&ctl->done))) {
                         item = ITEM_EXIT;
                         break;
                     }
@@ -637,13 +687,11 @@ LAB_DEV void bfs_worker_body(Params const &p, int lane) {
             if (item == ITEM_EXIT) {
                 return;
             }
+            LAB_PROF(if (lane == 0) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_idle), lab_cycles() - pi0);)
         }
         item = relax_tile(p, item, lane);
-        // a direct hand-off still honours the deadline
         if (item != ITEM_NONE && lab_ld_volatile(&ctl->done)) {
-            // only possible after an error: drop the tile so the launch can end
-            if (lane == 0) lab_atomic_sub(&ctl->pending, 1u);
-            return;
+            return; // only after an error (deadline): give up, the host reports it
         }
     }
 }

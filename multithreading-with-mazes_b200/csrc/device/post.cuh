@@ -71,7 +71,7 @@ LAB_DEV void init_run_body(Params p, Run_desc d, unsigned long long budget_ns) {
         uint32_t const t = static_cast<uint32_t>((d.src_r[k] / TS) * p.g.tiles_x + d.src_c[k] / TS);
         ctl->src_tile[k] = t;
         ctl->src_rc[k] = static_cast<uint32_t>(((d.src_r[k] % TS) << 8) | (d.src_c[k] % TS));
-        p.plane[k].state[t] = ST_ACTIVE | ST_DIRTY;
+        p.plane[k].state[t] = ST_ACTIVE; // arrives like any woken tile: active, DIRTY clear
         p.queue[ctl->tail & p.qmask] = static_cast<uint32_t>(k) * static_cast<uint32_t>(p.g.ntiles) + t;
         ctl->tail++;
         pending++;

@@ -65,6 +65,7 @@ LAB_DEV uint32_t lab_atomic_exch(uint32_t *p, uint32_t v) { return atomicExch(p,
 
 LAB_DEV void lab_threadfence() { __threadfence(); }
 LAB_DEV void lab_nanosleep(unsigned ns) { __nanosleep(ns); }
+LAB_DEV uint64_t lab_cycles() { return static_cast<uint64_t>(clock64()); }
 LAB_DEV uint64_t lab_clock_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

@@ -339,6 +339,10 @@ int finish_run(lab_grid *h) {
     st.direct = c.n_direct;
     st.worker_warps = static_cast<uint32_t>(h->bfs_blocks * (h->bfs_threads / 32));
     st.error = c.error;
+    st.cyc_load = c.cyc_load;
+    st.cyc_loop = c.cyc_loop;
+    st.cyc_publish = c.cyc_publish;
+    st.cyc_idle = c.cyc_idle;
     if (c.error == 1) {
         return fail(LAB_ERR_TIMEOUT, "search kernel passed its deadline (LAB_BFS_BUDGET_MS); %llu tiles still active",
                     static_cast<unsigned long long>(c.pending));

@@ -241,6 +241,7 @@ LAB_DEV uint32_t lab_atomic_exch(uint32_t *p, uint32_t v) {
 }
 LAB_DEV void lab_threadfence() {}
 LAB_DEV void lab_nanosleep(unsigned) { simt::park(simt::RUNNABLE); }
+LAB_DEV uint64_t lab_cycles() { return 0; }
 LAB_DEV uint64_t lab_clock_ns() {
     return static_cast<uint64_t>(
         std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count());
