@@ -130,6 +130,16 @@ LAB_DEV uint64_t lab_ballot64(bool lo, bool hi) {
     uint32_t b = lab_ballot(hi);
     return (static_cast<uint64_t>(b) << 32) | a;
 }
+// A value other warps may be changing, read ONCE per warp: lane 0 loads, everybody gets its copy.
+// (32 separate loads could return different values and send lanes down different paths around
+// the *_sync primitives.)
+LAB_DEV uint32_t lab_ld_uniform(uint32_t const *p, int lane) {
+    uint32_t v = 0;
+    if (lane == 0) {
+        v = lab_ld_volatile(p);
+    }
+    return lab_shfl(v, 0);
+}
 LAB_DEV uint32_t lab_min3(uint32_t a, uint32_t b, uint32_t c) { return a < b ? (a < c ? a : c) : (b < c ? b : c); }
 LAB_DEV uint32_t lab_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
@@ -362,6 +372,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
     uint32_t st_levels = 0, st_passes = 0, st_empty = 0;
     Emit_acc acc{0u, 0u, 0u, 0u};
     bool first_pass = true;
+    uint32_t guard = 0; // belt and braces: a pass that cannot end must become an error, never a hang
     LAB_PROF(uint64_t pc_load = 0; uint64_t pc_loop = 0; uint64_t pc_pub = 0;)
 
     for (;;) { // rerun while a neighbour dirtied us during the pass
@@ -420,8 +431,14 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
             uint64_t Vn0 = V0, Vn1 = V1;
             uint64_t F0 = 0, F1 = 0;
             uint32_t base = pending_min; // level of the first iteration of the batch
-            uint32_t bound = lab_ld_volatile(&ctl->bound);
+            uint32_t bound = lab_ld_uniform(&ctl->bound, lane);
+            uint32_t batches = 0;
             while (base <= bound) { // ---- one batch of up to WINDOW levels ------------------------
+                if (++batches > (1u << 22)) {
+                    lab_atomic_max(&ctl->error, 4u);
+                    lab_st_volatile(&ctl->done, 1u);
+                    break;
+                }
                 uint64_t B0[6] = {0, 0, 0, 0, 0, 0}, B1[6] = {0, 0, 0, 0, 0, 0};
                 uint64_t const A0s = A0, A1s = A1;
                 // seeds relative to the batch base (anything outside [0, 63] never matches)
@@ -519,7 +536,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
                 sE0 = seed_after(sE0, done_lvl);
                 sE1 = seed_after(sE1, done_lvl);
                 sSrc = seed_after(sSrc, done_lvl);
-                bound = lab_ld_volatile(&ctl->bound);
+                bound = lab_ld_uniform(&ctl->bound, lane);
                 if (lab_any((F0 | F1) != 0)) {
                     base = done_lvl + 1; // the wave is still moving: next batch continues from it
                 } else {
@@ -602,9 +619,17 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
                 }
             }
         }
-        uint32_t const again = lab_shfl(r != ST_ACTIVE ? 1u : 0u, 4);
+        uint32_t const r4 = lab_shfl(r, 4); // what this tile's state word held when we tried to let go
+        bool const again = r4 != ST_ACTIVE;
         LAB_PROF(pc_pub += lab_cycles() - pt2;)
         if (!again) {
+            break;
+        }
+        if (++guard > 4096u || lab_ld_uniform(&ctl->done, lane)) {
+            if (lane == 0) {
+                lab_atomic_max(&ctl->error, 3u + (r4 << 8));
+                lab_st_volatile(&ctl->done, 1u);
+            }
             break;
         }
     }
@@ -690,7 +715,7 @@ LAB_DEV void bfs_worker_body(Params const &p, int lane) {
             LAB_PROF(if (lane == 0) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_idle), lab_cycles() - pi0);)
         }
         item = relax_tile(p, item, lane);
-        if (item != ITEM_NONE && lab_ld_volatile(&ctl->done)) {
+        if (item != ITEM_NONE && lab_ld_uniform(&ctl->done, lane)) {
             return; // only after an error (deadline): give up, the host reports it
         }
     }

@@ -141,6 +141,21 @@ int fail(int code, char const *fmt, ...) {
         }                                                                                                \
     } while (0)
 
+// LAB_TRACE=1: synchronise after every launch and say which one it was (debugging hangs/faults)
+bool trace_on() {
+    static int const on = std::getenv("LAB_TRACE") ? 1 : 0;
+    return on != 0;
+}
+#define TRACE(name, stream)                                                                              \
+    do {                                                                                                 \
+        if (trace_on()) {                                                                                \
+            fprintf(stderr, "[lab] %s ...", name);                                                       \
+            fflush(stderr);                                                                              \
+            cudaError_t const e_ = cudaStreamSynchronize(stream);                                        \
+            fprintf(stderr, " %s\n", cudaGetErrorString(e_));                                            \
+        }                                                                                                \
+    } while (0)
+
 enum Ev { EV_SETUP0, EV_PACK0, EV_SEARCH0, EV_POST0, EV_END, EV_COPY0, EV_COPY1, EV_COUNT };
 
 } // namespace
@@ -301,12 +316,17 @@ int run_search(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass
     CU(cudaEventRecord(h->ev[EV_PACK0], s));
     long long const pack_items = static_cast<long long>(g.tiles_y) * TS * g.tiles_x;
     k_pack<<<blocks_for(h, (pack_items + 3) / 4, 256), 256, 0, s>>>(g, h->squares, h->path, pass_mask, pass_value);
+    TRACE("k_pack", s);
     k_force_sources<<<1, 1, 0, s>>>(g, h->path, d);
+    TRACE("k_force_sources", s);
     k_cross<<<blocks_for(h, g.ntiles, 256), 256, 0, s>>>(g, h->path, h->cross, nullptr, nullptr);
+    TRACE("k_cross", s);
     unsigned long long const budget_ns = static_cast<unsigned long long>(env_ll("LAB_BFS_BUDGET_MS", 20000)) * 1000000ull;
     k_init_run<<<1, 1, 0, s>>>(p, d, budget_ns);
+    TRACE("k_init_run", s);
     CU(cudaEventRecord(h->ev[EV_SEARCH0], s));
     k_bfs_tiles<<<h->bfs_blocks, h->bfs_threads, 0, s>>>(p);
+    TRACE("k_bfs_tiles", s);
     CU(cudaEventRecord(h->ev[EV_POST0], s));
     CU(cudaGetLastError());
     return LAB_OK;
@@ -348,7 +368,7 @@ int finish_run(lab_grid *h) {
                     static_cast<unsigned long long>(c.pending));
     }
     if (c.error) {
-        return fail(LAB_ERR_INTERNAL, "search kernel reported error %u", c.error);
+        return fail(LAB_ERR_INTERNAL, "search kernel reported error %u (state word %u)", c.error & 0xFF, c.error >> 8);
     }
     if (c.pending != 0) {
         return fail(LAB_ERR_INTERNAL, "search ended with %u tiles still active", c.pending);
@@ -548,6 +568,7 @@ int lab_grid_or_bits(lab_grid *h, const lab_point *cells, const uint16_t *bits, 
     CU(cudaMemcpyAsync(h->d_cells, rc, sizeof(int32_t) * 2 * n, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_bits, bits, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, h->stream));
     k_or_bits<<<1, 32, 0, h->stream>>>(h->squares, h->g.cols, h->d_cells, h->d_bits, n);
+    TRACE("k_or_bits", h->stream);
     CU(cudaGetLastError());
     return LAB_OK;
 }
@@ -557,6 +578,7 @@ int lab_grid_and_bits(lab_grid *h, uint16_t mask) {
         return fail(LAB_ERR_ARG, "null grid");
     }
     k_and_bits<<<grid_blocks(h), 256, 0, h->stream>>>(h->squares, static_cast<long long>(h->g.rows) * h->g.cols, mask);
+    TRACE("k_and_bits", h->stream);
     CU(cudaGetLastError());
     return LAB_OK;
 }
@@ -607,9 +629,12 @@ int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t 
     cudaStream_t s = h->stream;
     Params p = make_params(h, 1);
     k_resolve<<<1, 1, 0, s>>>(p, d, h->res, h->d_finish_rc);
+    TRACE("k_resolve", s);
     k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
+    TRACE("k_max_level", s);
     long long const items = static_cast<long long>(h->g.rows) * h->g.tiles_x;
     k_measure<<<blocks_for(h, items, 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
+    TRACE("k_measure", s);
     CU(cudaGetLastError());
     rc = finish_run(h);
     if (rc) {
@@ -643,17 +668,22 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
     }
     Params p = make_params(h, d.nplanes);
     k_resolve<<<1, 1, 0, s>>>(p, d, h->res, h->d_finish_rc);
+    TRACE("k_resolve", s);
     k_paint<<<grid_blocks(h), 256, 0, s>>>(p, h->squares, h->res);
+    TRACE("k_paint", s);
     if (d.game == GAME_GATHER) {
         CU(cudaMemsetAsync(h->d_front_rc, 0xFF, 8 * sizeof(int32_t), s));
         k_walk<<<4, 32, 0, s>>>(p, d.game, h->squares, h->res, h->d_finish_rc, h->d_front_rc, 1, 1, 1);
+        TRACE("k_walk", s);
         k_gather_fixup<<<1, 1, 0, s>>>(h->g, h->squares, h->res, h->d_finish_rc, h->d_front_rc);
+        TRACE("k_gather_fixup", s);
         if (want_paths) {
             rc = ensure_paths(h, path_cap);
             if (rc) {
                 return rc;
             }
             k_walk<<<4, 32, 0, s>>>(p, d.game, h->squares, h->res, h->d_finish_rc, h->d_paths, h->path_cap, path_cap, 0);
+            TRACE("k_walk", s);
         }
     } else {
         // hunt repaints the winner's path (bfs_threads.cc:263-274), so it always walks;
@@ -667,8 +697,10 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
             }
             k_walk<<<1, 32, 0, s>>>(p, d.game, h->squares, h->res, h->d_finish_rc, want_paths ? h->d_paths : nullptr,
                                     h->path_cap, want_paths ? path_cap : 0, 0);
+            TRACE("k_walk", s);
         } else {
             k_walk<<<1, 32, 0, s>>>(p, d.game, h->squares, h->res, h->d_finish_rc, nullptr, 0, 0, 1);
+            TRACE("k_walk", s);
         }
     }
     CU(cudaGetLastError());

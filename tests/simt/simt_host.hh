@@ -41,6 +41,7 @@ struct Lane {
 struct Warp {
     Lane lanes[32];
     uint64_t xchg[2][32];
+    int site[32]; // source line of the primitive each lane is waiting in
     std::function<void(int)> body;
     int finished = 0;
 };
@@ -64,13 +65,25 @@ inline void park(Lane_state s) {
 }
 
 // all 32 lanes exchange one value; returns the buffer every lane can read after the barrier
+inline int g_site = 0; // set by the lab_* macros below just before the primitive runs
 inline uint64_t const *exchange(uint64_t v) {
     Lane *l = g_cur;
     unsigned const b = l->pc & 1u;
     l->pc++;
     l->warp->xchg[b][l->id] = v;
+    l->warp->site[l->id] = g_site;
     park(AT_BARRIER);
     return l->warp->xchg[b];
+}
+
+// seeded chaos: loads that observe other warps' stores sometimes let other warps run first, so
+// that two lanes of one warp can see different values -- as on the real machine
+inline std::mt19937 g_chaos(12345);
+inline unsigned g_chaos_on = 0;
+inline void maybe_yield() {
+    if (g_chaos_on && (g_chaos() & 7u) == 0u) {
+        park(RUNNABLE);
+    }
 }
 
 // run one scheduling round of a warp: every runnable lane runs until it parks
@@ -87,6 +100,13 @@ inline void run_round(Warp &w) {
         at += l.state == AT_BARRIER;
     }
     if (at == 32) {
+        for (int i = 1; i < 32; i++) {
+            if (w.site[i] != w.site[0]) {
+                std::fprintf(stderr, "simt: lanes 0 and %d of one warp sit in DIFFERENT primitives (lines %d and %d)\n", i,
+                             w.site[0], w.site[i]);
+                std::abort();
+            }
+        }
         for (auto &l : w.lanes) {
             l.state = RUNNABLE;
         }
@@ -119,6 +139,8 @@ inline void launch(int nwarps, std::function<void(int, int)> body, unsigned sche
         }
     }
     std::mt19937 rng(sched_seed);
+    g_chaos.seed(sched_seed * 7919u + 1u);
+    g_chaos_on = sched_seed;
     int live = nwarps;
     while (live > 0) {
         if (sched_seed == 0) {
@@ -138,6 +160,7 @@ inline void launch(int nwarps, std::function<void(int, int)> body, unsigned sche
         }
     }
     g_cur = nullptr;
+    g_chaos_on = 0;
 }
 
 } // namespace simt
@@ -193,8 +216,14 @@ LAB_DEV void lab_syncwarp() { (void)simt::exchange(0); }
 LAB_DEV int lab_ffs64(uint64_t v) { return v ? __builtin_ctzll(v) + 1 : 0; }
 LAB_DEV int lab_popc64(uint64_t v) { return __builtin_popcountll(v); }
 
-template <class T> LAB_DEV T lab_ld_cg(T const *p) { return *p; }
-template <class T> LAB_DEV T lab_ld_volatile(T const *p) { return *p; }
+template <class T> LAB_DEV T lab_ld_cg(T const *p) {
+    simt::maybe_yield();
+    return *p;
+}
+template <class T> LAB_DEV T lab_ld_volatile(T const *p) {
+    simt::maybe_yield();
+    return *p;
+}
 template <class T> LAB_DEV T lab_ld_ro(T const *p) { return *p; }
 template <class T> LAB_DEV void lab_st_cg(T *p, typename std::common_type<T>::type v) { *p = v; }
 LAB_DEV void lab_st_volatile(uint32_t *p, uint32_t v) { *p = v; }
@@ -246,3 +275,16 @@ LAB_DEV uint64_t lab_clock_ns() {
     return static_cast<uint64_t>(
         std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count());
 }
+
+// every warp-wide primitive records the source line it was called from; run_round() aborts if
+// the 32 lanes of a warp meet in primitives at different lines (divergent *_sync = deadlock on HW)
+#define lab_shfl_up(...) (simt::g_site = __LINE__, lab_shfl_up(__VA_ARGS__))
+#define lab_shfl_down(...) (simt::g_site = __LINE__, lab_shfl_down(__VA_ARGS__))
+#define lab_shfl(...) (simt::g_site = __LINE__, lab_shfl(__VA_ARGS__))
+#define lab_ballot(...) (simt::g_site = __LINE__, lab_ballot(__VA_ARGS__))
+#define lab_any(...) (simt::g_site = __LINE__, lab_any(__VA_ARGS__))
+#define lab_reduce_min(...) (simt::g_site = __LINE__, lab_reduce_min(__VA_ARGS__))
+#define lab_reduce_max(...) (simt::g_site = __LINE__, lab_reduce_max(__VA_ARGS__))
+#define lab_reduce_or(...) (simt::g_site = __LINE__, lab_reduce_or(__VA_ARGS__))
+#define lab_reduce_add(...) (simt::g_site = __LINE__, lab_reduce_add(__VA_ARGS__))
+#define lab_syncwarp() (simt::g_site = __LINE__, lab_syncwarp())
