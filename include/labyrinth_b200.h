@@ -73,7 +73,7 @@ typedef struct lab_stats {
     uint32_t worker_warps;  /* warps of the persistent launch                            */
     uint32_t error;         /* Control.error                                             */
     /* SM cycles summed over worker warps; non-zero only in the -DLAB_PROFILE build */
-    uint64_t cyc_load, cyc_loop, cyc_publish, cyc_idle;
+    uint64_t cyc_load, cyc_loop, cyc_publish, cyc_idle, cyc_step, cyc_emit, batches;
 } lab_stats;
 
 /* ---- grid lifetime (replaces Maze::Maze construction, maze/maze.cc:349-354, for the GPU side) -- */

@@ -90,7 +90,7 @@ struct Control {
     // statistics
     unsigned long long n_activations, n_empty, n_levels, n_rechecks, n_resettles, n_settled, n_pushes, n_direct;
     // SM cycles summed over warps (LAB_PROFILE builds only): loading a tile, the level loop, publishing, idle
-    unsigned long long cyc_load, cyc_loop, cyc_publish, cyc_idle;
+    unsigned long long cyc_load, cyc_loop, cyc_publish, cyc_idle, cyc_step, cyc_emit, n_batches;
 };
 
 struct Params {
@@ -259,9 +259,16 @@ LAB_DEV void source_force_passable(Geom g, uint64_t *path, int r, int c) {
 
 constexpr int WINDOW = 64; // levels per batch
 
+// Per-warp shared-memory stage for writing a batch out (see emit_batch): 8 words per tile row
+// {settled, level plane 0..5, visited-before}, stored word-major so that lane i's two rows are
+// one 16-byte store, followed by the facing levels of the W and E borders (uint32 per row).
+constexpr int STAGE_WORDS = 8;
+constexpr int STAGE_U64 = STAGE_WORDS * TS + TS; // 8*64 u64 + 2*64 u32
+constexpr int STAGE_BYTES = STAGE_U64 * 8;
+
 struct Tile_ctx {
-    uint32_t *dist_row0; // &dist[(row0 + 2*lane) * cols + col0]
-    uint32_t *edges;     // this tile's [4][64]
+    uint32_t *dist0; // &dist[row0 * cols + col0]
+    uint32_t *edges; // this tile's [4][64]
     long long cols;
 };
 
@@ -286,54 +293,149 @@ LAB_DEV void edge_update(uint32_t *e, uint32_t lvl, bool old, uint32_t f, int si
     }
 }
 
-// Write out the squares of one row settled in the batch.  S = settled squares, Vold = squares that
-// had a level before this pass, B = their level relative to `base`, bit-sliced.
-LAB_DEV void emit_row(Tile_ctx const &tc, uint64_t S, uint64_t Vold, uint64_t const (&B)[6], uint32_t base, int which,
-                      int row_in_tile, uint32_t fW, uint32_t fE, uint32_t fNmax, uint32_t fSmax, Emit_acc &acc) {
-    uint32_t *drow = tc.dist_row0 + which * tc.cols;
-    acc.settled += static_cast<uint32_t>(lab_popc64(S));
-    acc.resettled += static_cast<uint32_t>(lab_popc64(S & Vold));
-    while (S) {
-        int const c = lab_ffs64(S) - 1;
-        S &= S - 1;
-        uint32_t k = 0;
-#pragma unroll
-        for (int b = 0; b < 6; b++) {
-            k |= static_cast<uint32_t>((B[b] >> c) & 1ull) << b;
-        }
-        uint32_t const lvl = base + k;
-        bool const old = (Vold >> c) & 1ull;
-        if (!old) {
-            drow[c] = lvl;
-        } else {
-            lab_atomic_min(drow + c, lvl);
-        }
-        acc.max_lvl = lvl > acc.max_lvl ? lvl : acc.max_lvl;
-        if (c == 0) edge_update(tc.edges + SIDE_W * TS + row_in_tile, lvl, old, fW, SIDE_W, acc);
-        if (c == 63) edge_update(tc.edges + SIDE_E * TS + row_in_tile, lvl, old, fE, SIDE_E, acc);
-        if (row_in_tile == 0) edge_update(tc.edges + SIDE_N * TS + c, lvl, old, fNmax, SIDE_N, acc);
-        if (row_in_tile == TS - 1) edge_update(tc.edges + SIDE_S * TS + c, lvl, old, fSmax, SIDE_S, acc);
+// The state of one wave inside a tile: lane i holds rows 2i (suffix 0) and 2i+1 (suffix 1).
+struct Wave {
+    uint64_t A0, A1;       // squares this pass may still settle
+    uint64_t F0, F1;       // frontier: squares settled at the last level
+    uint64_t B0[6], B1[6]; // level of every square settled in this batch, relative to its base, bit-sliced
+};
+
+// Seeds of the current batch, relative to its base (anything outside [0, 63] never matches).
+struct Seeds {
+    uint32_t rW0, rW1, rE0, rE1, rSrc;
+    uint64_t src0, src1;
+    uint64_t nsv, nsp[6]; // N seeds -> row 0 (lane 0), S seeds -> row 63 (lane 31), bit-sliced
+};
+
+// Eight BFS levels.  INJECT = some seed's level falls into this group.
+// Critical path per level: shuffle -> LOP3 -> shuffle.  Everything else (planes, seeds) hangs off it.
+template <bool INJECT> LAB_DEV void step_group(Wave &w, Seeds const &sd, int gi, int lane, uint64_t P0, uint64_t P1) {
+    (void)P0;
+    (void)P1;
+    uint64_t gm = 0;
+    if (INJECT) {
+        gm = sd.nsv;
+        gm &= (gi & 1) ? sd.nsp[3] : ~sd.nsp[3];
+        gm &= (gi & 2) ? sd.nsp[4] : ~sd.nsp[4];
+        gm &= (gi & 4) ? sd.nsp[5] : ~sd.nsp[5];
     }
+    uint64_t G0 = 0, G1 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        // lanes 0 / 31 get their own row back from the out-of-range shuffle: harmless, that row is
+        // already OR-ed in below
+        uint64_t const up = lab_shfl_up64(w.F1, 1);     // row 2*lane-1
+        uint64_t const down = lab_shfl_down64(w.F0, 1); // row 2*lane+2
+        uint64_t i0 = 0, i1 = 0;
+        if (INJECT) {
+            uint32_t const rel = 8u * static_cast<uint32_t>(gi) + static_cast<uint32_t>(j);
+            uint64_t m = gm;
+            m &= (j & 1) ? sd.nsp[0] : ~sd.nsp[0];
+            m &= (j & 2) ? sd.nsp[1] : ~sd.nsp[1];
+            m &= (j & 4) ? sd.nsp[2] : ~sd.nsp[2];
+            i0 = (sd.rW0 == rel ? 1ull : 0ull) | (sd.rE0 == rel ? (1ull << 63) : 0ull) | (sd.rSrc == rel ? sd.src0 : 0ull);
+            i1 = (sd.rW1 == rel ? 1ull : 0ull) | (sd.rE1 == rel ? (1ull << 63) : 0ull) | (sd.rSrc == rel ? sd.src1 : 0ull);
+            i0 |= lane == 0 ? m : 0ull;
+            i1 |= lane == 31 ? m : 0ull;
+        }
+        uint64_t const N0 = ((w.F0 << 1) | (w.F0 >> 1) | w.F1 | up | i0) & w.A0;
+        uint64_t const N1 = ((w.F1 << 1) | (w.F1 >> 1) | w.F0 | down | i1) & w.A1;
+        w.A0 &= ~N0;
+        w.A1 &= ~N1;
+        if (j & 1) { w.B0[0] |= N0; w.B1[0] |= N1; }
+        if (j & 2) { w.B0[1] |= N0; w.B1[1] |= N1; }
+        if (j & 4) { w.B0[2] |= N0; w.B1[2] |= N1; }
+        G0 |= N0;
+        G1 |= N1;
+        w.F0 = N0;
+        w.F1 = N1;
+    }
+    if (gi & 1) { w.B0[3] |= G0; w.B1[3] |= G1; }
+    if (gi & 2) { w.B0[4] |= G0; w.B1[4] |= G1; }
+    if (gi & 4) { w.B0[5] |= G0; w.B1[5] |= G1; }
+}
+
+// Write a batch out, the whole warp working on one tile row at a time: lane l looks after
+// columns l and l+32 of the row, so the level stores of a row are coalesced and no lane is left
+// holding a long corridor alone.  S0/S1 = squares settled in the batch (rows 2*lane, 2*lane+1),
+// V0/V1 = squares that already had a level before this pass (they get atomicMin, not a store).
+LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint64_t S0, uint64_t S1, uint64_t V0,
+                        uint64_t V1, uint32_t base, int lane, uint32_t fNmax, uint32_t fSmax, Emit_acc &acc) {
+    uint32_t const even_rows = lab_ballot(S0 != 0); // bit i <-> row 2i
+    uint32_t const odd_rows = lab_ballot(S1 != 0);  // bit i <-> row 2i+1
+    if ((even_rows | odd_rows) == 0) {
+        return;
+    }
+    // stage[wd * 64 + row]
+    stage[0 * TS + 2 * lane] = S0;
+    stage[0 * TS + 2 * lane + 1] = S1;
+#pragma unroll
+    for (int b = 0; b < 6; b++) {
+        stage[(1 + b) * TS + 2 * lane] = w.B0[b];
+        stage[(1 + b) * TS + 2 * lane + 1] = w.B1[b];
+    }
+    stage[7 * TS + 2 * lane] = V0;
+    stage[7 * TS + 2 * lane + 1] = V1;
+    lab_syncwarp();
+    uint32_t const *fW = reinterpret_cast<uint32_t const *>(stage + STAGE_WORDS * TS);
+    uint32_t const *fE = fW + TS;
+    acc.settled += static_cast<uint32_t>(lab_popc64(S0) + lab_popc64(S1));
+    acc.resettled += static_cast<uint32_t>(lab_popc64(S0 & V0) + lab_popc64(S1 & V1));
+    for (int parity = 0; parity < 2; parity++) {
+        uint32_t rows = parity ? odd_rows : even_rows;
+        while (rows) {
+            int const r = 2 * (lab_ffs64(rows) - 1) + parity;
+            rows &= rows - 1;
+            uint64_t const S = stage[r];
+            uint64_t const Vold = stage[7 * TS + r];
+            uint32_t *drow = tc.dist0 + r * tc.cols;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                int const c = lane + 32 * half;
+                if ((S >> c) & 1ull) {
+                    uint32_t k = 0;
+#pragma unroll
+                    for (int b = 0; b < 6; b++) {
+                        k |= static_cast<uint32_t>((stage[(1 + b) * TS + r] >> c) & 1ull) << b;
+                    }
+                    uint32_t const lvl = base + k;
+                    bool const old = (Vold >> c) & 1ull;
+                    if (!old) {
+                        drow[c] = lvl;
+                    } else {
+                        lab_atomic_min(drow + c, lvl);
+                    }
+                    acc.max_lvl = lvl > acc.max_lvl ? lvl : acc.max_lvl;
+                    if (c == 0) edge_update(tc.edges + SIDE_W * TS + r, lvl, old, fW[r], SIDE_W, acc);
+                    if (c == TS - 1) edge_update(tc.edges + SIDE_E * TS + r, lvl, old, fE[r], SIDE_E, acc);
+                    if (r == 0) edge_update(tc.edges + SIDE_N * TS + c, lvl, old, fNmax, SIDE_N, acc);
+                    if (r == TS - 1) edge_update(tc.edges + SIDE_S * TS + c, lvl, old, fSmax, SIDE_S, acc);
+                }
+            }
+        }
+    }
+    lab_syncwarp(); // the stage is reused by the next batch
 }
 
 // One border square: `seed` = facing level + 1 if that beats what this tile holds, else INF.
-// `f` = the facing level (0 when the border cannot be crossed here).
-LAB_DEV void load_seed(bool crossing, uint32_t const *facing, uint32_t const *own, uint32_t &seed, uint32_t &f) {
+// f and o were loaded unconditionally; `crossing` says whether the border can be crossed here.
+LAB_DEV void make_seed(bool crossing, uint32_t &f, uint32_t o, uint32_t &seed) {
     seed = INF;
-    f = 0;
-    if (crossing) {
-        f = lab_ld_cg(facing);
-        uint32_t const o = lab_ld_cg(own);
-        if (f != INF && f + 1 < o) {
-            seed = f + 1;
-        }
+    if (!crossing) {
+        f = 0; // "never worth waking"
+    } else if (f != INF && f + 1 < o) {
+        seed = f + 1;
     }
 }
 
 LAB_DEV uint32_t seed_after(uint32_t s, uint32_t lvl) { return (s != INF && s > lvl) ? s : INF; }
+LAB_DEV uint32_t seed_group_bit(uint32_t s, uint32_t base) {
+    uint32_t const rel = s - base;
+    return rel < static_cast<uint32_t>(WINDOW) ? (1u << (rel >> 3)) : 0u;
+}
 
 // returns the next item this warp should relax itself (ITEM_NONE if none)
-LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
+LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *stage) {
     Geom const &g = p.g;
     int const plane = static_cast<int>(item / static_cast<uint32_t>(g.ntiles));
     long long const t = item % static_cast<uint32_t>(g.ntiles);
@@ -349,17 +451,19 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
     uint64_t const XS = lab_ld_ro(p.cross + t * 4 + SIDE_S);
     uint64_t const XW = lab_ld_ro(p.cross + t * 4 + SIDE_W);
     uint64_t const XE = lab_ld_ro(p.cross + t * 4 + SIDE_E);
-    // edges has one ghost tile-row above and below
+    // edges has one ghost tile-row above and below, so every neighbour pointer stays inside the
+    // allocation and the edge loads below can be issued unconditionally (one round trip)
     uint32_t *const my_edges = pl.edges + (t + g.tiles_x) * (4 * TS);
     uint32_t const *const n_edges = my_edges - static_cast<long long>(g.tiles_x) * (4 * TS);
     uint32_t const *const s_edges = my_edges + static_cast<long long>(g.tiles_x) * (4 * TS);
     uint32_t const *const w_edges = my_edges - 4 * TS;
     uint32_t const *const e_edges = my_edges + 4 * TS;
+    bool const bounded = ctl->bound_mode != BOUND_NONE;
 
     Tile_ctx tc;
     tc.cols = g.cols;
     tc.edges = my_edges;
-    tc.dist_row0 = pl.dist + (static_cast<long long>(ty) * TS + r0) * g.cols + static_cast<long long>(tx) * TS;
+    tc.dist0 = pl.dist + (static_cast<long long>(ty) * TS) * g.cols + static_cast<long long>(tx) * TS;
 
     // neighbour this lane looks after when waking (lanes 0..3 = Side)
     long long nb = -1;
@@ -373,7 +477,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
     Emit_acc acc{0u, 0u, 0u, 0u};
     bool first_pass = true;
     uint32_t guard = 0; // belt and braces: a pass that cannot end must become an error, never a hang
-    LAB_PROF(uint64_t pc_load = 0; uint64_t pc_loop = 0; uint64_t pc_pub = 0;)
+    LAB_PROF(uint64_t pc_load = 0; uint64_t pc_loop = 0; uint64_t pc_pub = 0; uint64_t pc_step = 0; uint64_t pc_emit = 0; uint64_t pn_batches = 0;)
 
     for (;;) { // rerun while a neighbour dirtied us during the pass
         LAB_PROF(uint64_t const pt0 = lab_cycles();)
@@ -393,25 +497,34 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
 
         // ---- seeds: facing edge level + 1 where that beats what this tile has ------------------
         // N/S seeds: lane holds columns lane and lane+32.  W/E seeds: lane holds rows 2*lane, 2*lane+1.
+        uint32_t fN0 = lab_ld_cg(n_edges + SIDE_S * TS + lane), fN1 = lab_ld_cg(n_edges + SIDE_S * TS + lane + 32);
+        uint32_t fS0 = lab_ld_cg(s_edges + SIDE_N * TS + lane), fS1 = lab_ld_cg(s_edges + SIDE_N * TS + lane + 32);
+        uint32_t fW0 = lab_ld_cg(w_edges + SIDE_E * TS + r0), fW1 = lab_ld_cg(w_edges + SIDE_E * TS + r1);
+        uint32_t fE0 = lab_ld_cg(e_edges + SIDE_W * TS + r0), fE1 = lab_ld_cg(e_edges + SIDE_W * TS + r1);
+        uint32_t const oN0 = lab_ld_cg(my_edges + SIDE_N * TS + lane), oN1 = lab_ld_cg(my_edges + SIDE_N * TS + lane + 32);
+        uint32_t const oS0 = lab_ld_cg(my_edges + SIDE_S * TS + lane), oS1 = lab_ld_cg(my_edges + SIDE_S * TS + lane + 32);
+        uint32_t const oW0 = lab_ld_cg(my_edges + SIDE_W * TS + r0), oW1 = lab_ld_cg(my_edges + SIDE_W * TS + r1);
+        uint32_t const oE0 = lab_ld_cg(my_edges + SIDE_E * TS + r0), oE1 = lab_ld_cg(my_edges + SIDE_E * TS + r1);
         uint32_t sN0, sN1, sS0, sS1, sW0, sW1, sE0, sE1;
-        uint32_t fN0, fN1, fS0, fS1, fW0, fW1, fE0, fE1;
-        load_seed((XN >> lane) & 1, n_edges + SIDE_S * TS + lane, my_edges + SIDE_N * TS + lane, sN0, fN0);
-        load_seed((XN >> (lane + 32)) & 1, n_edges + SIDE_S * TS + lane + 32, my_edges + SIDE_N * TS + lane + 32, sN1, fN1);
-        load_seed((XS >> lane) & 1, s_edges + SIDE_N * TS + lane, my_edges + SIDE_S * TS + lane, sS0, fS0);
-        load_seed((XS >> (lane + 32)) & 1, s_edges + SIDE_N * TS + lane + 32, my_edges + SIDE_S * TS + lane + 32, sS1, fS1);
-        load_seed((XW >> r0) & 1, w_edges + SIDE_E * TS + r0, my_edges + SIDE_W * TS + r0, sW0, fW0);
-        load_seed((XW >> r1) & 1, w_edges + SIDE_E * TS + r1, my_edges + SIDE_W * TS + r1, sW1, fW1);
-        load_seed((XE >> r0) & 1, e_edges + SIDE_W * TS + r0, my_edges + SIDE_E * TS + r0, sE0, fE0);
-        load_seed((XE >> r1) & 1, e_edges + SIDE_W * TS + r1, my_edges + SIDE_E * TS + r1, sE1, fE1);
+        make_seed((XN >> lane) & 1, fN0, oN0, sN0);
+        make_seed((XN >> (lane + 32)) & 1, fN1, oN1, sN1);
+        make_seed((XS >> lane) & 1, fS0, oS0, sS0);
+        make_seed((XS >> (lane + 32)) & 1, fS1, oS1, sS1);
+        make_seed((XW >> r0) & 1, fW0, oW0, sW0);
+        make_seed((XW >> r1) & 1, fW1, oW1, sW1);
+        make_seed((XE >> r0) & 1, fE0, oE0, sE0);
+        make_seed((XE >> r1) & 1, fE1, oE1, sE1);
         // The plane's source square, if it lies in this tile and is not settled yet, is a level-0 seed.
-        uint64_t src0 = 0, src1 = 0;
+        Seeds sd;
+        sd.src0 = 0;
+        sd.src1 = 0;
         if (ctl->src_tile[plane] == static_cast<uint32_t>(t)) {
             uint32_t const rc = ctl->src_rc[plane];
             int const sr = static_cast<int>(rc >> 8), sc = static_cast<int>(rc & 0xFF);
-            if (sr == r0 && !((V0 >> sc) & 1)) src0 = 1ull << sc;
-            if (sr == r1 && !((V1 >> sc) & 1)) src1 = 1ull << sc;
+            if (sr == r0 && !((V0 >> sc) & 1)) sd.src0 = 1ull << sc;
+            if (sr == r1 && !((V1 >> sc) & 1)) sd.src1 = 1ull << sc;
         }
-        uint32_t sSrc = (src0 | src1) ? 0u : INF;
+        uint32_t sSrc = (sd.src0 | sd.src1) ? 0u : INF;
 
         uint32_t pending_min = lab_umin(lab_umin(lab_min3(sN0, sN1, sS0), lab_min3(sS1, sW0, sW1)), lab_min3(sE0, sE1, sSrc));
         pending_min = lab_reduce_min(pending_min);
@@ -426,12 +539,23 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
             // beats the WORST level over there (conservative; the exact per-column test is not needed)
             uint32_t const fNmax = XN ? lab_reduce_max(fN0 > fN1 ? fN0 : fN1) : 0u;
             uint32_t const fSmax = XS ? lab_reduce_max(fS0 > fS1 ? fS0 : fS1) : 0u;
+            {   // W/E facing levels per row, for the lanes that will write columns 0 and 63 out
+                uint32_t *fW = reinterpret_cast<uint32_t *>(stage + STAGE_WORDS * TS);
+                uint32_t *fE = fW + TS;
+                fW[r0] = fW0;
+                fW[r1] = fW1;
+                fE[r0] = fE0;
+                fE[r1] = fE1;
+            }
             bool const any_ns = lab_any((sN0 & sN1 & sS0 & sS1) != INF);
-            uint64_t A0 = P0, A1 = P1; // squares this pass may still settle
+            Wave w;
+            w.A0 = P0;
+            w.A1 = P1;
+            w.F0 = 0;
+            w.F1 = 0;
             uint64_t Vn0 = V0, Vn1 = V1;
-            uint64_t F0 = 0, F1 = 0;
             uint32_t base = pending_min; // level of the first iteration of the batch
-            uint32_t bound = lab_ld_uniform(&ctl->bound, lane);
+            uint32_t bound = bounded ? lab_ld_uniform(&ctl->bound, lane) : INF;
             uint32_t batches = 0;
             while (base <= bound) { // ---- one batch of up to WINDOW levels ------------------------
                 if (++batches > (1u << 22)) {
@@ -439,90 +563,72 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
                     lab_st_volatile(&ctl->done, 1u);
                     break;
                 }
-                uint64_t B0[6] = {0, 0, 0, 0, 0, 0}, B1[6] = {0, 0, 0, 0, 0, 0};
-                uint64_t const A0s = A0, A1s = A1;
-                // seeds relative to the batch base (anything outside [0, 63] never matches)
-                uint32_t const rW0 = sW0 - base, rW1 = sW1 - base, rE0 = sE0 - base, rE1 = sE1 - base, rSrc = sSrc - base;
-                // N seeds land in row 0 (lane 0, r0), S seeds in row 63 (lane 31, r1): bit-sliced by ballots
-                uint64_t nsv = 0, nsp[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+                for (int b = 0; b < 6; b++) {
+                    w.B0[b] = 0;
+                    w.B1[b] = 0;
+                }
+                uint64_t const A0s = w.A0, A1s = w.A1;
+                sd.rW0 = sW0 - base;
+                sd.rW1 = sW1 - base;
+                sd.rE0 = sE0 - base;
+                sd.rE1 = sE1 - base;
+                sd.rSrc = sSrc - base;
+                // which groups of 8 levels of this window hold a seed (uniform 8-bit mask)
+                uint32_t grp = seed_group_bit(sW0, base) | seed_group_bit(sW1, base) | seed_group_bit(sE0, base)
+                               | seed_group_bit(sE1, base) | seed_group_bit(sSrc, base);
+                sd.nsv = 0;
+#pragma unroll
+                for (int b = 0; b < 6; b++) {
+                    sd.nsp[b] = 0;
+                }
                 if (any_ns) {
+                    // N seeds land in row 0 (lane 0, r0), S seeds in row 63 (lane 31, r1): bit-sliced by ballots
                     uint32_t const rN0 = sN0 - base, rN1 = sN1 - base, rS0 = sS0 - base, rS1 = sS1 - base;
                     bool const vN0 = rN0 < WINDOW, vN1 = rN1 < WINDOW, vS0 = rS0 < WINDOW, vS1 = rS1 < WINDOW;
                     uint64_t const wn = lab_ballot64(vN0, vN1), ws = lab_ballot64(vS0, vS1);
-                    nsv = lane == 0 ? wn : (lane == 31 ? ws : 0ull);
+                    sd.nsv = lane == 0 ? wn : (lane == 31 ? ws : 0ull);
                     if (wn | ws) {
+                        grp |= seed_group_bit(sN0, base) | seed_group_bit(sN1, base) | seed_group_bit(sS0, base)
+                               | seed_group_bit(sS1, base);
 #pragma unroll
                         for (int b = 0; b < 6; b++) {
                             uint64_t const pn = lab_ballot64(vN0 && ((rN0 >> b) & 1), vN1 && ((rN1 >> b) & 1));
                             uint64_t const ps = lab_ballot64(vS0 && ((rS0 >> b) & 1), vS1 && ((rS1 >> b) & 1));
-                            nsp[b] = lane == 0 ? pn : (lane == 31 ? ps : 0ull);
+                            sd.nsp[b] = lane == 0 ? pn : (lane == 31 ? ps : 0ull);
                         }
                     }
                 }
+                grp = lab_reduce_or(grp);
+                LAB_PROF(uint64_t const ps0 = lab_cycles(); pn_batches++;)
                 int gi = 0; // groups of 8 levels completed
                 for (; gi < WINDOW / 8; gi++) {
                     if (base + 8u * static_cast<uint32_t>(gi) > bound) {
                         break;
                     }
-                    // N/S seeds whose level is in this group: high 3 bits of their relative level == gi
-                    uint64_t gm = nsv;
-                    gm &= (gi & 1) ? nsp[3] : ~nsp[3];
-                    gm &= (gi & 2) ? nsp[4] : ~nsp[4];
-                    gm &= (gi & 4) ? nsp[5] : ~nsp[5];
-                    uint64_t G0 = 0, G1 = 0;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        uint32_t const rel = 8u * static_cast<uint32_t>(gi) + static_cast<uint32_t>(j);
-                        // lanes 0 / 31 get their own row back from the out-of-range shuffle: harmless, it is
-                        // already OR-ed in below
-                        uint64_t const up = lab_shfl_up64(F1, 1);     // row 2*lane-1
-                        uint64_t const down = lab_shfl_down64(F0, 1); // row 2*lane+2
-                        uint64_t m = gm;
-                        m &= (j & 1) ? nsp[0] : ~nsp[0];
-                        m &= (j & 2) ? nsp[1] : ~nsp[1];
-                        m &= (j & 4) ? nsp[2] : ~nsp[2];
-                        uint64_t i0 = (rW0 == rel ? 1ull : 0ull) | (rE0 == rel ? (1ull << 63) : 0ull) | (rSrc == rel ? src0 : 0ull);
-                        uint64_t i1 = (rW1 == rel ? 1ull : 0ull) | (rE1 == rel ? (1ull << 63) : 0ull) | (rSrc == rel ? src1 : 0ull);
-                        i0 |= lane == 0 ? m : 0ull;
-                        i1 |= lane == 31 ? m : 0ull;
-                        uint64_t const N0 = ((F0 << 1) | (F0 >> 1) | F1 | up | i0) & A0;
-                        uint64_t const N1 = ((F1 << 1) | (F1 >> 1) | F0 | down | i1) & A1;
-                        A0 &= ~N0;
-                        A1 &= ~N1;
-                        if (j & 1) { B0[0] |= N0; B1[0] |= N1; }
-                        if (j & 2) { B0[1] |= N0; B1[1] |= N1; }
-                        if (j & 4) { B0[2] |= N0; B1[2] |= N1; }
-                        G0 |= N0;
-                        G1 |= N1;
-                        F0 = N0;
-                        F1 = N1;
+                    if ((grp >> gi) & 1u) {
+                        step_group<true>(w, sd, gi, lane, P0, P1);
+                    } else {
+                        step_group<false>(w, sd, gi, lane, P0, P1);
                     }
-                    if (gi & 1) { B0[3] |= G0; B1[3] |= G1; }
-                    if (gi & 2) { B0[4] |= G0; B1[4] |= G1; }
-                    if (gi & 4) { B0[5] |= G0; B1[5] |= G1; }
                     st_levels += 8;
-                    if (!lab_any((F0 | F1) != 0)) {
-                        // nothing moving: skip to the group holding the next seed of this window, if any
-                        uint32_t const done_lvl = base + 8u * static_cast<uint32_t>(gi) + 7u;
-                        uint32_t nxt = lab_umin(lab_umin(lab_min3(seed_after(sN0, done_lvl), seed_after(sN1, done_lvl), seed_after(sS0, done_lvl)),
-                                                         lab_min3(seed_after(sS1, done_lvl), seed_after(sW0, done_lvl), seed_after(sW1, done_lvl))),
-                                                lab_min3(seed_after(sE0, done_lvl), seed_after(sE1, done_lvl), seed_after(sSrc, done_lvl)));
-                        nxt = lab_reduce_min(nxt);
-                        if (nxt == INF || nxt - base >= static_cast<uint32_t>(WINDOW) || nxt > bound) {
+                    if (!lab_any((w.F0 | w.F1) != 0)) {
+                        // nothing moving: skip to the next group of this window that holds a seed, if any
+                        uint32_t const later = grp & ~((2u << gi) - 1u);
+                        if (later == 0 || base + 8u * static_cast<uint32_t>(lab_ffs64(later) - 1) > bound) {
                             gi++;
                             break;
                         }
-                        gi = static_cast<int>((nxt - base) / 8u) - 1; // the loop increment lands on its group
+                        gi = lab_ffs64(later) - 2; // the loop increment lands on that group
                     }
                 }
                 // ---- write the batch out ---------------------------------------------------------
-                uint64_t const S0 = A0s & ~A0, S1 = A1s & ~A1;
-                if (S0 | S1) {
-                    emit_row(tc, S0, V0, B0, base, 0, r0, fW0, fE0, fNmax, fSmax, acc);
-                    emit_row(tc, S1, V1, B1, base, 1, r1, fW1, fE1, fNmax, fSmax, acc);
-                    Vn0 |= S0;
-                    Vn1 |= S1;
-                }
+                LAB_PROF(uint64_t const ps1 = lab_cycles(); pc_step += ps1 - ps0;)
+                uint64_t const S0 = A0s & ~w.A0, S1 = A1s & ~w.A1;
+                emit_batch(tc, stage, w, S0, S1, V0, V1, base, lane, fNmax, fSmax, acc);
+                Vn0 |= S0;
+                Vn1 |= S1;
+                LAB_PROF(pc_emit += lab_cycles() - ps1;)
                 if (gi == 0) {
                     break; // bound reached before anything ran
                 }
@@ -536,8 +642,10 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
                 sE0 = seed_after(sE0, done_lvl);
                 sE1 = seed_after(sE1, done_lvl);
                 sSrc = seed_after(sSrc, done_lvl);
-                bound = lab_ld_uniform(&ctl->bound, lane);
-                if (lab_any((F0 | F1) != 0)) {
+                if (bounded) {
+                    bound = lab_ld_uniform(&ctl->bound, lane);
+                }
+                if (lab_any((w.F0 | w.F1) != 0)) {
                     base = done_lvl + 1; // the wave is still moving: next batch continues from it
                 } else {
                     pending_min = lab_umin(lab_umin(lab_min3(sN0, sN1, sS0), lab_min3(sS1, sW0, sW1)), lab_min3(sE0, sE1, sSrc));
@@ -670,12 +778,16 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane) {
         lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_load), pc_load);
         lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_loop), pc_loop);
         lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_publish), pc_pub + (lab_cycles() - pt3));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_step), pc_step);
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_emit), pc_emit);
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_batches), pn_batches);
     })
     return next;
 }
 
 // The persistent worker: every warp of the launch runs this until no tile is active any more.
-LAB_DEV void bfs_worker_body(Params const &p, int lane) {
+// `stage` = this warp's STAGE_BYTES of shared memory.
+LAB_DEV void bfs_worker_body(Params const &p, int lane, uint64_t *stage) {
     Control *ctl = p.ctl;
     uint32_t item = ITEM_NONE;
     for (;;) {
@@ -714,7 +826,7 @@ LAB_DEV void bfs_worker_body(Params const &p, int lane) {
             }
             LAB_PROF(if (lane == 0) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_idle), lab_cycles() - pi0);)
         }
-        item = relax_tile(p, item, lane);
+        item = relax_tile(p, item, lane, stage);
         if (item != ITEM_NONE && lab_ld_uniform(&ctl->done, lane)) {
             return; // only after an error (deadline): give up, the host reports it
         }

@@ -43,7 +43,10 @@ __global__ void k_force_sources(Geom g, uint64_t *path, Run_desc d) { force_sour
 __global__ void k_init_run(Params p, Run_desc d, unsigned long long budget_ns) { init_run_body(p, d, budget_ns); }
 
 // The persistent search kernel: every warp is a worker until the search is done.
-__global__ void __launch_bounds__(128) k_bfs_tiles(Params p) { bfs_worker_body(p, lane_id()); }
+__global__ void __launch_bounds__(128) k_bfs_tiles(Params p) {
+    __shared__ __align__(16) uint64_t stage[4][STAGE_U64];
+    bfs_worker_body(p, lane_id(), stage[threadIdx.x >> 5]);
+}
 
 __global__ void __launch_bounds__(256) k_measure(Geom g, uint16_t *grid, uint64_t const *visited, Result *res) {
     measure_body(g, grid, visited, res, gwarp_id(), nwarps_total(), lane_id());
@@ -363,6 +366,9 @@ int finish_run(lab_grid *h) {
     st.cyc_loop = c.cyc_loop;
     st.cyc_publish = c.cyc_publish;
     st.cyc_idle = c.cyc_idle;
+    st.cyc_step = c.cyc_step;
+    st.cyc_emit = c.cyc_emit;
+    st.batches = c.n_batches;
     if (c.error == 1) {
         return fail(LAB_ERR_TIMEOUT, "search kernel passed its deadline (LAB_BFS_BUDGET_MS); %llu tiles still active",
                     static_cast<unsigned long long>(c.pending));

@@ -69,7 +69,8 @@ int search(Workspace &w, uint16_t *grid, int rows, int cols, Run_desc const &d, 
     force_sources_body(g, w.path.data(), d);
     simt::launch(nwarps, [&](int wid, int lane) { cross_body(g, w.path.data(), w.cross.data(), nullptr, nullptr, wid, nwarps, lane); });
     init_run_body(p, d, 60ull * 1000000000ull);
-    simt::launch(nwarps, [&](int, int lane) { bfs_worker_body(p, lane); }, sched_seed);
+    std::vector<uint64_t> stages(static_cast<size_t>(nwarps) * STAGE_U64);
+    simt::launch(nwarps, [&](int wid, int lane) { bfs_worker_body(p, lane, stages.data() + static_cast<size_t>(wid) * STAGE_U64); }, sched_seed);
     if (w.ctl.error) return -100 - static_cast<int>(w.ctl.error);
     if (w.ctl.pending != 0) return -200;
     return 0;

@@ -19,7 +19,9 @@ for a in cases:
         "case": a, "search_ms": round(t["search_ms"], 3), "max_level": r.max, "activations": s["activations"], "empty": s["empty"],
         "levels": s["levels"], "cyc_per_level": round(s["cyc_loop"] / max(1, s["levels"]), 1),
         "load_cyc_per_act": round(s["cyc_load"] / act), "publish_cyc_per_act": round(s["cyc_publish"] / act),
-        "loop_cyc_per_act": round(s["cyc_loop"] / act), "idle_Mcyc": round(s["cyc_idle"] / 1e6, 1),
+        "loop_cyc_per_act": round(s["cyc_loop"] / act), "step_cyc_per_level": round(s["cyc_step"] / max(1, s["levels"]), 1),
+        "emit_cyc_per_cell": round(s["cyc_emit"] / max(1, s["settled"]), 1), "emit_cyc_per_batch": round(s["cyc_emit"] / max(1, s["batches"])),
+        "step_cyc_per_batch": round(s["cyc_step"] / max(1, s["batches"])), "batches": s["batches"], "cells_per_batch": round(s["settled"] / max(1, s["batches"]), 1), "idle_Mcyc": round(s["cyc_idle"] / 1e6, 1),
         "busy_Mcyc": round((s["cyc_load"] + s["cyc_loop"] + s["cyc_publish"]) / 1e6, 1),
         "kernel_Mcyc_x_warps": round(t["search_ms"] * 1e-3 * 1.9e9 * s["worker_warps"] / 1e6, 1),
         "pushes": s["queue_pushes"], "direct": s["direct"]}))
