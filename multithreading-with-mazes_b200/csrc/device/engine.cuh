@@ -259,11 +259,11 @@ LAB_DEV void source_force_passable(Geom g, uint64_t *path, int r, int c) {
 
 constexpr int WINDOW = 64; // levels per batch
 
-// Per-warp shared-memory stage for writing a batch out (see emit_batch): 8 words per tile row
-// {settled, level plane 0..5, visited-before}, stored word-major so that lane i's two rows are
-// one 16-byte store, followed by the facing levels of the W and E borders (uint32 per row).
-constexpr int STAGE_WORDS = 8;
-constexpr int STAGE_U64 = STAGE_WORDS * TS + TS; // 8*64 u64 + 2*64 u32
+// Per-warp shared-memory stage for writing a batch out (see emit_batch).
+// layout (uint64 units): [0,6*64) level planes, [6*64,7*64) visited-before, [7*64,8*64) facing levels
+// of the W and E borders (2 x 64 uint32), then the cell list (4096 x uint16).
+constexpr int STAGE_FIXED_U64 = 8 * TS;
+constexpr int STAGE_U64 = STAGE_FIXED_U64 + (TS * TS * 2) / 8;
 constexpr int STAGE_BYTES = STAGE_U64 * 8;
 
 struct Tile_ctx {
@@ -355,64 +355,81 @@ template <bool INJECT> LAB_DEV void step_group(Wave &w, Seeds const &sd, int gi,
     if (gi & 4) { w.B0[5] |= G0; w.B1[5] |= G1; }
 }
 
-// Write a batch out, the whole warp working on one tile row at a time: lane l looks after
-// columns l and l+32 of the row, so the level stores of a row are coalesced and no lane is left
-// holding a long corridor alone.  S0/S1 = squares settled in the batch (rows 2*lane, 2*lane+1),
-// V0/V1 = squares that already had a level before this pass (they get atomicMin, not a store).
+// Write a batch out.  Two steps so that no lane is left holding a long corridor alone:
+//   1. every lane lists the squares settled in ITS two rows as (row << 6 | col) in the warp's
+//      shared-memory cell list (cheap serial loop: find bit, store a halfword), at the offset a
+//      warp-wide prefix sum of the per-lane counts gives it;
+//   2. the list is consumed 32 squares at a time, one square per lane: look the level up in the
+//      staged bit-sliced planes, store it (atomicMin if the square already had a level), and keep
+//      the tile's edge arrays / wake flags up to date for border squares.
+// S0/S1 = squares settled in the batch (rows 2*lane, 2*lane+1), V0/V1 = squares that already had a
+// level before this pass.
 LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint64_t S0, uint64_t S1, uint64_t V0,
                         uint64_t V1, uint32_t base, int lane, uint32_t fNmax, uint32_t fSmax, Emit_acc &acc) {
-    uint32_t const even_rows = lab_ballot(S0 != 0); // bit i <-> row 2i
-    uint32_t const odd_rows = lab_ballot(S1 != 0);  // bit i <-> row 2i+1
-    if ((even_rows | odd_rows) == 0) {
+    uint32_t const mine = static_cast<uint32_t>(lab_popc64(S0) + lab_popc64(S1));
+    // inclusive prefix sum over lanes
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t const v = lab_shfl_up(incl, d);
+        if (lane >= d) {
+            incl += v;
+        }
+    }
+    uint32_t const total = lab_shfl(incl, 31);
+    if (total == 0) {
         return;
     }
-    // stage[wd * 64 + row]
-    stage[0 * TS + 2 * lane] = S0;
-    stage[0 * TS + 2 * lane + 1] = S1;
+    // stage[wd * 64 + row]: level planes and visited-before, for step 2
 #pragma unroll
     for (int b = 0; b < 6; b++) {
-        stage[(1 + b) * TS + 2 * lane] = w.B0[b];
-        stage[(1 + b) * TS + 2 * lane + 1] = w.B1[b];
+        stage[b * TS + 2 * lane] = w.B0[b];
+        stage[b * TS + 2 * lane + 1] = w.B1[b];
     }
-    stage[7 * TS + 2 * lane] = V0;
-    stage[7 * TS + 2 * lane + 1] = V1;
-    lab_syncwarp();
-    uint32_t const *fW = reinterpret_cast<uint32_t const *>(stage + STAGE_WORDS * TS);
-    uint32_t const *fE = fW + TS;
-    acc.settled += static_cast<uint32_t>(lab_popc64(S0) + lab_popc64(S1));
-    acc.resettled += static_cast<uint32_t>(lab_popc64(S0 & V0) + lab_popc64(S1 & V1));
-    for (int parity = 0; parity < 2; parity++) {
-        uint32_t rows = parity ? odd_rows : even_rows;
-        while (rows) {
-            int const r = 2 * (lab_ffs64(rows) - 1) + parity;
-            rows &= rows - 1;
-            uint64_t const S = stage[r];
-            uint64_t const Vold = stage[7 * TS + r];
-            uint32_t *drow = tc.dist0 + r * tc.cols;
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                int const c = lane + 32 * half;
-                if ((S >> c) & 1ull) {
-                    uint32_t k = 0;
-#pragma unroll
-                    for (int b = 0; b < 6; b++) {
-                        k |= static_cast<uint32_t>((stage[(1 + b) * TS + r] >> c) & 1ull) << b;
-                    }
-                    uint32_t const lvl = base + k;
-                    bool const old = (Vold >> c) & 1ull;
-                    if (!old) {
-                        drow[c] = lvl;
-                    } else {
-                        lab_atomic_min(drow + c, lvl);
-                    }
-                    acc.max_lvl = lvl > acc.max_lvl ? lvl : acc.max_lvl;
-                    if (c == 0) edge_update(tc.edges + SIDE_W * TS + r, lvl, old, fW[r], SIDE_W, acc);
-                    if (c == TS - 1) edge_update(tc.edges + SIDE_E * TS + r, lvl, old, fE[r], SIDE_E, acc);
-                    if (r == 0) edge_update(tc.edges + SIDE_N * TS + c, lvl, old, fNmax, SIDE_N, acc);
-                    if (r == TS - 1) edge_update(tc.edges + SIDE_S * TS + c, lvl, old, fSmax, SIDE_S, acc);
-                }
-            }
+    stage[6 * TS + 2 * lane] = V0;
+    stage[6 * TS + 2 * lane + 1] = V1;
+    uint16_t *cells = reinterpret_cast<uint16_t *>(stage + STAGE_FIXED_U64);
+    {
+        uint32_t q = incl - mine;
+        uint64_t m = S0;
+        while (m) {
+            int const c = lab_ffs64(m) - 1;
+            m &= m - 1;
+            cells[q++] = static_cast<uint16_t>(((2 * lane) << 6) | c);
         }
+        m = S1;
+        while (m) {
+            int const c = lab_ffs64(m) - 1;
+            m &= m - 1;
+            cells[q++] = static_cast<uint16_t>(((2 * lane + 1) << 6) | c);
+        }
+    }
+    lab_syncwarp();
+    uint32_t const *fW = reinterpret_cast<uint32_t const *>(stage + 7 * TS);
+    uint32_t const *fE = fW + TS;
+    acc.settled += mine;
+    acc.resettled += static_cast<uint32_t>(lab_popc64(S0 & V0) + lab_popc64(S1 & V1));
+    for (uint32_t q = static_cast<uint32_t>(lane); q < total; q += 32) {
+        uint32_t const rc = cells[q];
+        int const r = static_cast<int>(rc >> 6), c = static_cast<int>(rc & 63u);
+        uint32_t k = 0;
+#pragma unroll
+        for (int b = 0; b < 6; b++) {
+            k |= static_cast<uint32_t>((stage[b * TS + r] >> c) & 1ull) << b;
+        }
+        uint32_t const lvl = base + k;
+        bool const old = (stage[6 * TS + r] >> c) & 1ull;
+        uint32_t *d = tc.dist0 + r * tc.cols + c;
+        if (!old) {
+            *d = lvl;
+        } else {
+            lab_atomic_min(d, lvl);
+        }
+        acc.max_lvl = lvl > acc.max_lvl ? lvl : acc.max_lvl;
+        if (c == 0) edge_update(tc.edges + SIDE_W * TS + r, lvl, old, fW[r], SIDE_W, acc);
+        if (c == TS - 1) edge_update(tc.edges + SIDE_E * TS + r, lvl, old, fE[r], SIDE_E, acc);
+        if (r == 0) edge_update(tc.edges + SIDE_N * TS + c, lvl, old, fNmax, SIDE_N, acc);
+        if (r == TS - 1) edge_update(tc.edges + SIDE_S * TS + c, lvl, old, fSmax, SIDE_S, acc);
     }
     lab_syncwarp(); // the stage is reused by the next batch
 }
@@ -540,7 +557,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
             uint32_t const fNmax = XN ? lab_reduce_max(fN0 > fN1 ? fN0 : fN1) : 0u;
             uint32_t const fSmax = XS ? lab_reduce_max(fS0 > fS1 ? fS0 : fS1) : 0u;
             {   // W/E facing levels per row, for the lanes that will write columns 0 and 63 out
-                uint32_t *fW = reinterpret_cast<uint32_t *>(stage + STAGE_WORDS * TS);
+                uint32_t *fW = reinterpret_cast<uint32_t *>(stage + 7 * TS);
                 uint32_t *fE = fW + TS;
                 fW[r0] = fW0;
                 fW[r1] = fW1;
