@@ -309,11 +309,10 @@ struct Seeds {
 
 // Eight BFS levels.  INJECT = some seed's level falls into this group.
 // Critical path per level: shuffle -> LOP3 -> shuffle.  Everything else (planes, seeds) hangs off it.
-template <bool INJECT> LAB_DEV void step_group(Wave &w, Seeds const &sd, int gi, int lane, uint64_t P0, uint64_t P1) {
-    (void)P0;
-    (void)P1;
+// NS = some of those seeds come through the north / south border (bit-sliced planes to match).
+template <bool INJECT, bool NS> LAB_DEV void step_group(Wave &w, Seeds const &sd, int gi, int lane) {
     uint64_t gm = 0;
-    if (INJECT) {
+    if (INJECT && NS) {
         gm = sd.nsv;
         gm &= (gi & 1) ? sd.nsp[3] : ~sd.nsp[3];
         gm &= (gi & 2) ? sd.nsp[4] : ~sd.nsp[4];
@@ -329,10 +328,13 @@ template <bool INJECT> LAB_DEV void step_group(Wave &w, Seeds const &sd, int gi,
         uint64_t i0 = 0, i1 = 0;
         if (INJECT) {
             uint32_t const rel = 8u * static_cast<uint32_t>(gi) + static_cast<uint32_t>(j);
-            uint64_t m = gm;
-            m &= (j & 1) ? sd.nsp[0] : ~sd.nsp[0];
-            m &= (j & 2) ? sd.nsp[1] : ~sd.nsp[1];
-            m &= (j & 4) ? sd.nsp[2] : ~sd.nsp[2];
+            uint64_t m = 0;
+            if (NS) {
+                m = gm;
+                m &= (j & 1) ? sd.nsp[0] : ~sd.nsp[0];
+                m &= (j & 2) ? sd.nsp[1] : ~sd.nsp[1];
+                m &= (j & 4) ? sd.nsp[2] : ~sd.nsp[2];
+            }
             i0 = (sd.rW0 == rel ? 1ull : 0ull) | (sd.rE0 == rel ? (1ull << 63) : 0ull) | (sd.rSrc == rel ? sd.src0 : 0ull);
             i1 = (sd.rW1 == rel ? 1ull : 0ull) | (sd.rE1 == rel ? (1ull << 63) : 0ull) | (sd.rSrc == rel ? sd.src1 : 0ull);
             i0 |= lane == 0 ? m : 0ull;
@@ -420,16 +422,21 @@ LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint
         uint32_t const lvl = base + k;
         bool const old = (stage[6 * TS + r] >> c) & 1ull;
         uint32_t *d = tc.dist0 + r * tc.cols + c;
-        if (!old) {
+        acc.max_lvl = lvl > acc.max_lvl ? lvl : acc.max_lvl;
+        bool const border = c == 0 || c == TS - 1 || r == 0 || r == TS - 1;
+        if (!old && !border) { // the common case: an interior square settled for the first time
             *d = lvl;
         } else {
-            lab_atomic_min(d, lvl);
+            if (!old) {
+                *d = lvl;
+            } else {
+                lab_atomic_min(d, lvl);
+            }
+            if (c == 0) edge_update(tc.edges + SIDE_W * TS + r, lvl, old, fW[r], SIDE_W, acc);
+            if (c == TS - 1) edge_update(tc.edges + SIDE_E * TS + r, lvl, old, fE[r], SIDE_E, acc);
+            if (r == 0) edge_update(tc.edges + SIDE_N * TS + c, lvl, old, fNmax, SIDE_N, acc);
+            if (r == TS - 1) edge_update(tc.edges + SIDE_S * TS + c, lvl, old, fSmax, SIDE_S, acc);
         }
-        acc.max_lvl = lvl > acc.max_lvl ? lvl : acc.max_lvl;
-        if (c == 0) edge_update(tc.edges + SIDE_W * TS + r, lvl, old, fW[r], SIDE_W, acc);
-        if (c == TS - 1) edge_update(tc.edges + SIDE_E * TS + r, lvl, old, fE[r], SIDE_E, acc);
-        if (r == 0) edge_update(tc.edges + SIDE_N * TS + c, lvl, old, fNmax, SIDE_N, acc);
-        if (r == TS - 1) edge_update(tc.edges + SIDE_S * TS + c, lvl, old, fSmax, SIDE_S, acc);
     }
     lab_syncwarp(); // the stage is reused by the next batch
 }
@@ -451,8 +458,72 @@ LAB_DEV uint32_t seed_group_bit(uint32_t s, uint32_t base) {
     return rel < static_cast<uint32_t>(WINDOW) ? (1u << (rel >> 3)) : 0u;
 }
 
+// Work counters a warp keeps in registers and adds to the Control block once, when it retires.
+struct Warp_stats {
+    uint32_t passes = 0, empty = 0, levels = 0, pushes = 0, direct = 0;
+    uint32_t settled = 0, resettled = 0, max_lvl = 0; // per lane
+    LAB_PROF(uint64_t c_load = 0; uint64_t c_loop = 0; uint64_t c_pub = 0; uint64_t c_step = 0; uint64_t c_emit = 0; uint64_t c_idle = 0; uint64_t batches = 0;)
+};
+
+LAB_DEV void flush_stats(Control *ctl, Warp_stats const &ws, int lane) {
+    uint32_t const s_set = lab_reduce_add(ws.settled);
+    uint32_t const s_res = lab_reduce_add(ws.resettled);
+    uint32_t const s_max = lab_reduce_max(ws.max_lvl);
+    if (lane == 0) {
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_activations), static_cast<uint64_t>(ws.passes));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_empty), static_cast<uint64_t>(ws.empty));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_levels), static_cast<uint64_t>(ws.levels));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_pushes), static_cast<uint64_t>(ws.pushes));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_direct), static_cast<uint64_t>(ws.direct));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_settled), static_cast<uint64_t>(s_set));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_resettles), static_cast<uint64_t>(s_res));
+        lab_atomic_max(&ctl->max_level, s_max);
+        LAB_PROF(lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_load), ws.c_load);
+                 lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_loop), ws.c_loop);
+                 lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_publish), ws.c_pub);
+                 lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_step), ws.c_step);
+                 lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_emit), ws.c_emit);
+                 lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_idle), ws.c_idle);
+                 lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_batches), ws.batches);)
+    }
+}
+
+// Wake the neighbours flagged in `woke` (Side bits; lane s < 4 looks after side s, its tile is nb).
+// A neighbour is taken with CAS(idle -> ACTIVE), so it starts with DIRTY clear and needs no clearing
+// round trip before it reads the edges; one that is already active is marked DIRTY instead and
+// whoever runs it goes round again.  Returns true in the lanes that now OWN their neighbour.
+LAB_DEV bool wake_neighbours(Plane const &pl, Control *ctl, uint32_t woke, int lane, long long nb, bool skip) {
+    bool const attempt = lane < 4 && ((woke >> lane) & 1u) && nb >= 0 && !skip;
+    uint32_t const n_attempt = static_cast<uint32_t>(lab_popc64(lab_ballot(attempt)));
+    if (n_attempt == 0) {
+        return false;
+    }
+    if (lane == 0) {
+        lab_atomic_add(&ctl->pending, n_attempt); // over-counts until the failures are taken back
+    }
+    lab_threadfence(); // the edge levels written so far are visible before any flag below
+    lab_syncwarp();
+    uint32_t r = 0;
+    if (attempt) {
+        r = lab_atomic_cas(&pl.state[nb], 0u, ST_ACTIVE);
+    }
+    bool const failed = attempt && r != 0u;
+    bool got = attempt && !failed;
+    if (lab_any(failed)) {
+        if (failed) {
+            uint32_t const old = lab_atomic_or(&pl.state[nb], ST_ACTIVE | ST_DIRTY);
+            if (!(old & ST_ACTIVE)) {
+                got = true; // it went idle in between: ours after all (it will do one spurious rerun)
+            } else {
+                lab_atomic_sub(&ctl->pending, 1u);
+            }
+        }
+    }
+    return got;
+}
+
 // returns the next item this warp should relax itself (ITEM_NONE if none)
-LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *stage) {
+LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *stage, Warp_stats &ws) {
     Geom const &g = p.g;
     int const plane = static_cast<int>(item / static_cast<uint32_t>(g.ntiles));
     long long const t = item % static_cast<uint32_t>(g.ntiles);
@@ -490,11 +561,9 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
     if (lane == SIDE_E) nb = tx < g.tiles_x - 1 ? t + 1 : -1;
     bool owned = false; // this lane's neighbour was made active by us and is ours to run or queue
 
-    uint32_t st_levels = 0, st_passes = 0, st_empty = 0;
     Emit_acc acc{0u, 0u, 0u, 0u};
     bool first_pass = true;
     uint32_t guard = 0; // belt and braces: a pass that cannot end must become an error, never a hang
-    LAB_PROF(uint64_t pc_load = 0; uint64_t pc_loop = 0; uint64_t pc_pub = 0; uint64_t pc_step = 0; uint64_t pc_emit = 0; uint64_t pn_batches = 0;)
 
     for (;;) { // rerun while a neighbour dirtied us during the pass
         LAB_PROF(uint64_t const pt0 = lab_cycles();)
@@ -545,12 +614,12 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
 
         uint32_t pending_min = lab_umin(lab_umin(lab_min3(sN0, sN1, sS0), lab_min3(sS1, sW0, sW1)), lab_min3(sE0, sE1, sSrc));
         pending_min = lab_reduce_min(pending_min);
-        st_passes++;
-        LAB_PROF(uint64_t const pt1 = lab_cycles(); pc_load += pt1 - pt0;)
+        ws.passes++;
+        LAB_PROF(uint64_t const pt1 = lab_cycles(); ws.c_load += pt1 - pt0;)
 
         acc.wake = 0;
         if (pending_min == INF) {
-            st_empty++;
+            ws.empty++;
         } else {
             // a row-0 / row-63 square settled at level L can only help the tile above / below if L + 1
             // beats the WORST level over there (conservative; the exact per-column test is not needed)
@@ -599,6 +668,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                 for (int b = 0; b < 6; b++) {
                     sd.nsp[b] = 0;
                 }
+                bool ns_window = false; // some N/S seed falls into this batch's window
                 if (any_ns) {
                     // N seeds land in row 0 (lane 0, r0), S seeds in row 63 (lane 31, r1): bit-sliced by ballots
                     uint32_t const rN0 = sN0 - base, rN1 = sN1 - base, rS0 = sS0 - base, rS1 = sS1 - base;
@@ -606,6 +676,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                     uint64_t const wn = lab_ballot64(vN0, vN1), ws = lab_ballot64(vS0, vS1);
                     sd.nsv = lane == 0 ? wn : (lane == 31 ? ws : 0ull);
                     if (wn | ws) {
+                        ns_window = true;
                         grp |= seed_group_bit(sN0, base) | seed_group_bit(sN1, base) | seed_group_bit(sS0, base)
                                | seed_group_bit(sS1, base);
 #pragma unroll
@@ -617,18 +688,20 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                     }
                 }
                 grp = lab_reduce_or(grp);
-                LAB_PROF(uint64_t const ps0 = lab_cycles(); pn_batches++;)
+                LAB_PROF(uint64_t const ps0 = lab_cycles(); ws.batches++;)
                 int gi = 0; // groups of 8 levels completed
                 for (; gi < WINDOW / 8; gi++) {
                     if (base + 8u * static_cast<uint32_t>(gi) > bound) {
                         break;
                     }
-                    if ((grp >> gi) & 1u) {
-                        step_group<true>(w, sd, gi, lane, P0, P1);
+                    if (!((grp >> gi) & 1u)) {
+                        step_group<false, false>(w, sd, gi, lane);
+                    } else if (ns_window) {
+                        step_group<true, true>(w, sd, gi, lane);
                     } else {
-                        step_group<false>(w, sd, gi, lane, P0, P1);
+                        step_group<true, false>(w, sd, gi, lane);
                     }
-                    st_levels += 8;
+                    ws.levels += 8;
                     if (!lab_any((w.F0 | w.F1) != 0)) {
                         // nothing moving: skip to the next group of this window that holds a seed, if any
                         uint32_t const later = grp & ~((2u << gi) - 1u);
@@ -640,12 +713,12 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                     }
                 }
                 // ---- write the batch out ---------------------------------------------------------
-                LAB_PROF(uint64_t const ps1 = lab_cycles(); pc_step += ps1 - ps0;)
+                LAB_PROF(uint64_t const ps1 = lab_cycles(); ws.c_step += ps1 - ps0;)
                 uint64_t const S0 = A0s & ~w.A0, S1 = A1s & ~w.A1;
                 emit_batch(tc, stage, w, S0, S1, V0, V1, base, lane, fNmax, fSmax, acc);
                 Vn0 |= S0;
                 Vn1 |= S1;
-                LAB_PROF(pc_emit += lab_cycles() - ps1;)
+                LAB_PROF(ws.c_emit += lab_cycles() - ps1;)
                 if (gi == 0) {
                     break; // bound reached before anything ran
                 }
@@ -672,6 +745,20 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                     }
                     base = pending_min; // jump to the next seed level
                 }
+                if (base > bound) {
+                    break;
+                }
+                // More batches to come here: let the neighbours this batch reached start NOW, on other
+                // warps, instead of at the end of the pass (their wave does not wait for our leftovers).
+                uint32_t const woke_now = lab_reduce_or(acc.wake);
+                if (woke_now) {
+                    acc.wake = 0;
+                    bool const got = wake_neighbours(pl, ctl, woke_now, lane, nb, owned);
+                    if (got) {
+                        queue_push(p, static_cast<uint32_t>(plane) * static_cast<uint32_t>(g.ntiles) + static_cast<uint32_t>(nb));
+                    }
+                    ws.pushes += static_cast<uint32_t>(lab_popc64(lab_ballot(got)));
+                }
             }
             if ((Vn0 != V0) | (Vn1 != V1)) {
                 lab_st_cg(pl.visited + t * TS + r0, Vn0);
@@ -680,7 +767,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
         }
         uint32_t const woke = lab_reduce_or(acc.wake);
         bool const settled_any = lab_any(acc.settled != 0);
-        LAB_PROF(uint64_t const pt2 = lab_cycles(); pc_loop += pt2 - pt1;)
+        LAB_PROF(uint64_t const pt2 = lab_cycles(); ws.c_loop += pt2 - pt1;)
 
         // ---- publish ----------------------------------------------------------------------------
         // wake protocol: a neighbour is taken with CAS(idle -> ACTIVE), i.e. it starts with DIRTY
@@ -746,7 +833,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
         }
         uint32_t const r4 = lab_shfl(r, 4); // what this tile's state word held when we tried to let go
         bool const again = r4 != ST_ACTIVE;
-        LAB_PROF(pc_pub += lab_cycles() - pt2;)
+        LAB_PROF(ws.c_pub += lab_cycles() - pt2;)
         if (!again) {
             break;
         }
@@ -772,33 +859,18 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
             queue_push(p, mine);
         }
     }
+    {
+        uint32_t const n_own = static_cast<uint32_t>(lab_popc64(own_mask));
+        ws.pushes += n_own > 1 ? n_own - 1 : 0;
+        ws.direct += n_own ? 1 : 0;
+        ws.settled += acc.settled;
+        ws.resettled += acc.resettled;
+        ws.max_lvl = acc.max_lvl > ws.max_lvl ? acc.max_lvl : ws.max_lvl;
+    }
     if (lane == 0) {
-        unsigned const n_own = static_cast<unsigned>(lab_popc64(own_mask));
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_activations), static_cast<uint64_t>(st_passes));
-        if (st_empty) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_empty), static_cast<uint64_t>(st_empty));
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_levels), static_cast<uint64_t>(st_levels));
-        if (n_own > 1) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_pushes), static_cast<uint64_t>(n_own - 1));
-        if (n_own) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_direct), 1ull);
         lab_atomic_sub(&ctl->pending, 1u); // this tile is idle now
     }
-    {
-        uint32_t const s_set = lab_reduce_add(acc.settled);
-        uint32_t const s_res = lab_reduce_add(acc.resettled);
-        uint32_t const s_max = lab_reduce_max(acc.max_lvl);
-        if (lane == 0) {
-            if (s_set) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_settled), static_cast<uint64_t>(s_set));
-            if (s_res) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_resettles), static_cast<uint64_t>(s_res));
-            if (s_max) lab_atomic_max(&ctl->max_level, s_max);
-        }
-    }
-    LAB_PROF(if (lane == 0) {
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_load), pc_load);
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_loop), pc_loop);
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_publish), pc_pub + (lab_cycles() - pt3));
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_step), pc_step);
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_emit), pc_emit);
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->n_batches), pn_batches);
-    })
+    LAB_PROF(ws.c_pub += lab_cycles() - pt3;)
     return next;
 }
 
@@ -807,6 +879,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
 LAB_DEV void bfs_worker_body(Params const &p, int lane, uint64_t *stage) {
     Control *ctl = p.ctl;
     uint32_t item = ITEM_NONE;
+    Warp_stats ws;
     for (;;) {
         if (item == ITEM_NONE) {
             LAB_PROF(uint64_t const pi0 = lab_cycles();)
@@ -833,21 +906,22 @@ LAB_DEV void bfs_worker_body(Params const &p, int lane, uint64_t *stage) {
                         break;
                     }
                     lab_nanosleep(backoff);
-                    if (backoff < 2048) backoff *= 2;
+                    if (backoff < 512) backoff *= 2;
                     polls++;
                 }
             }
             item = lab_shfl(item, 0);
+            LAB_PROF(ws.c_idle += lab_cycles() - pi0;)
             if (item == ITEM_EXIT) {
-                return;
+                break;
             }
-            LAB_PROF(if (lane == 0) lab_atomic_add(reinterpret_cast<uint64_t *>(&ctl->cyc_idle), lab_cycles() - pi0);)
         }
-        item = relax_tile(p, item, lane, stage);
+        item = relax_tile(p, item, lane, stage, ws);
         if (item != ITEM_NONE && lab_ld_uniform(&ctl->done, lane)) {
-            return; // only after an error (deadline): give up, the host reports it
+            break; // only after an error (deadline): give up, the host reports it
         }
     }
+    flush_stats(ctl, ws, lane);
 }
 
 } // namespace lab
