@@ -1,0 +1,82 @@
+"""Pins the oracle (oracle/restate.cc) and the product's host code against the real reference text
+compiled into oracle/_ref/.  Skipped where _ref is absent."""
+import numpy as np
+import pytest
+
+from _util import paths_equal
+
+pytestmark = pytest.mark.ref
+
+BUILDERS = ["arena", "grid", "rdfs", "kruskal", "wilson"]
+SIZES = [(7, 7), (9, 13), (21, 33), (51, 111), (127, 127)]
+
+
+@pytest.mark.parametrize("builder", BUILDERS)
+def test_builders_byte_identical(ref, lab, builder):
+    for rows, cols in SIZES + [(255, 255)]:
+        for seed in (0, 1, 12345):
+            for mod in (None, "cross", "x"):
+                assert (ref.ref_build(builder, rows, cols, seed, mod) == lab.build_maze(builder, rows, cols, seed, mod)).all(), (rows, cols, seed, mod)
+
+
+@pytest.mark.parametrize("builder", BUILDERS)
+def test_distance_restatement(ref, builder):
+    for rows, cols in SIZES:
+        for seed in (1, 2):
+            for mod in (None, "cross"):
+                grid = ref.ref_build(builder, rows, cols, seed, mod)
+                ga, d, mx, rgb = ref.ref_distance(grid, seed=11)
+                gb, d2, mx2, settled = ref.distance_map(grid)
+                dd = np.where(d == np.uint64(2**64 - 1), np.uint64(ref.INF), d).astype(np.uint32)
+                assert (ga == gb).all() and (dd == d2).all() and mx == mx2 and settled == int((dd != ref.INF).sum())
+
+
+@pytest.mark.parametrize("builder", BUILDERS)
+def test_hunter_gatherer_restatement(ref, builder):
+    for rows, cols in SIZES[1:]:
+        for seed in (1, 2):
+            grid = ref.ref_build(builder, rows, cols, seed, None)
+            for game, place in ((0, ref.place_hunt), (1, ref.place_gather)):
+                placed, s, _ = place(grid, seed + 100)
+                for order in [(0, 1, 2, 3), (3, 2, 1, 0), (2, 0, 3, 1)]:
+                    a = ref.ref_solver_sequential(game, placed, [s] * 4, order)
+                    b = ref.solver_sequential(game, placed, [s] * 4, order)
+                    assert (a[0] == b[0]).all() and a[2] == b[2] and paths_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("builder", BUILDERS)
+def test_placement_rules(ref, lab, builder):
+    for rows, cols in SIZES:
+        grid = ref.ref_build(builder, rows, cols, 3, None)
+        for seed in range(8):
+            p = ref.ref_pick_random_point(grid, seed)
+            assert p == ref.pick_random_point(grid, seed) == lab.pick_random_point(grid, seed)
+        assert (ref.ref_set_corner_starts(grid) == ref.set_corner_starts(grid)).all()
+
+
+@pytest.mark.parametrize("builder", ["rdfs", "kruskal", "grid", "arena"])
+def test_canonical_model_brackets_the_real_threads(ref, builder):
+    """The reference's games race.  Whatever its 4 std::threads did, colour k's
+    paint must contain every square strictly closer than the level its game ended at, and nothing
+    farther than that level -- which is what the canonical model paints / allows."""
+    O = ref
+    for rows, cols in [(21, 33), (51, 111)]:
+        for seed in (1, 2, 3):
+            grid = O.ref_build(builder, rows, cols, seed, None)
+            # hunt
+            placed, s, f = O.place_hunt(grid, seed + 200)
+            real = O.ref_game(O.HUNT, grid, seed + 200)
+            d = O.bfs_levels(placed, int(s[0]), int(s[1]))
+            T = int(d[f[0], f[1]])
+            paint = (real & O.PAINT_MASK) != 0
+            assert not paint[d > T].any() and not paint[f[0], f[1]]
+            assert paint[(d < T) & (d > 0)].all()  # some thread painted every closer square
+            # the repainted winner path: single-colour squares forming a chain of length T
+            # gather
+            placed, s, fin = O.place_gather(grid, seed + 200)
+            real = O.ref_game(O.GATHER, grid, seed + 200)
+            d = O.bfs_levels(placed, int(s[0]), int(s[1]))
+            Dmax = max(int(d[r, c]) for r, c in fin)
+            assert not ((real & O.PAINT_MASK) != 0)[d > Dmax].any()
+            for r, c in fin:  # every finish ends up claimed (non-zero cache nibble)
+                assert real[r, c] & O.CACHE_MASK
