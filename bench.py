@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- the BFS hot path on B200, measured as BASELINE.json asks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one maze: the whole search (workspace reset, pack,
+persistent tile-relaxation kernel, epilogue) for the workload named in ``config.workload``.
+Default workload = BASELINE.json configs[1]: Distance map from the centre of a 4095x4095 Kruskal
+perfect maze (seeded, built by the product's linear-time builder, byte-identical to the
+reference builder's output for that seed).
+
+  value      cells settled / second (G/s) with the maze already resident in HBM: K steps, each timed
+             with CUDA events on the launching stream (the Square grid is restored from a pristine
+             device copy and L2 is flushed between steps, outside the timed region), max over ranks.
+  e2e        the same metric through the host-facing call path: pinned host Squares -> H2D -> search
+             -> D2H of the Squares (and the level field for the distance map), copies timed.
+  roofline   HBM: algorithmic bytes per launch (8 B x rows x cols for the distance
+             map, 4 B x rows x cols for the solvers) / the search kernel's CUDA-event time, against
+             MEASURED_PEAKS.json's copy bandwidth.
+  cpu_baseline  the oracle's CPU restatement ("port", 1 thread) on the same maze, rank 0, N = 1.
+
+``--impl reference`` times the reference's own CPU implementation (oracle/_ref = the real
+reference text compiled here) on a bounded sample of the workload; see reference_arm().
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+import __graft_entry__ as graft  # noqa: E402
+
+SEED = 0xB2000000
+WORKLOADS = {
+    # name: (game, builder, n, mod, BASELINE config it stands for)
+    "c2-distance-kruskal-4095": ("distance", "kruskal", 4095, None, "configs[1]"),
+    "c3-gather-arena-16383": ("gather", "arena", 16383, None, "configs[2]"),
+    "c4-corners-grid-cross-4095": ("corners", "grid", 4095, "cross", "configs[3] at 4095 (host build time)"),
+    "h-distance-arena-32767": ("distance", "arena", 32767, None, "north_star headline size, open maze"),
+    "h-gather-arena-32767": ("gather", "arena", 32767, None, "north_star headline size, open maze"),
+    "distance-wilson-4095": ("distance", "wilson", 4095, None, "configs[4] builder at 4095"),
+    "distance-arena-16383": ("distance", "arena", 16383, None, "configs[2] maze, distance map"),
+}
+DEFAULT = "c2-distance-kruskal-4095"
+ALG_BYTES_PER_CELL = {"distance": 8.0, "gather": 4.0, "hunt": 4.0, "corners": 4.0}
+KERNELS_PER_STEP = {"distance": 8, "gather": 10, "hunt": 8, "corners": 8}  # my kernels launched per step
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.rows = []
+        self.proc = None
+        self.idx = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_case(lab, workload: str, seed_offset: int = 0):
+    game, builder, n, mod, _ = WORKLOADS[workload]
+    maze = lab.build_maze(builder, n, n, seed=SEED + 2 + seed_offset, mod=mod)
+    spec = {"game": game, "rows": n, "cols": n}
+    if game == "distance":
+        spec["start"] = lab.distance_start(n, n)
+    elif game == "gather":
+        maze, spec["start"], spec["finishes"] = lab.place_gather(maze, seed=SEED + 3 + seed_offset)
+    elif game == "hunt":
+        maze, spec["start"], spec["finish"] = lab.place_hunt(maze, seed=SEED + 3 + seed_offset)
+    elif game == "corners":
+        maze, spec["starts"], spec["finish"] = lab.place_corners(maze, seed=SEED + 3 + seed_offset)
+    return maze, spec
+
+
+def run_search(grid, spec):
+    """One pass of the hot path on a device-resident grid -> settled cells."""
+    game = spec["game"]
+    if game == "distance":
+        return grid.distance_map(spec["start"], want_dist=False).settled
+    if game == "gather":
+        return grid.gather(spec["start"], spec["finishes"], want_paths=False).painted
+    if game == "hunt":
+        return grid.hunt(spec["start"], spec["finish"], want_path=False).painted
+    return grid.corners(spec["starts"], spec["finish"], want_path=False).painted
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lab = graft.load_package()
+    workload = args.workload
+    game, builder, n, mod, stands_for = WORKLOADS[workload]
+
+    # ---- synthetic input: one seeded maze per rank (independent mazes: no data-path collective) ----
+    t0 = time.time()
+    maze, spec = make_case(lab, workload, seed_offset=rank)
+    build_s = time.time() - t0
+    rows, cols = maze.shape
+    cells = rows * cols
+    stream = torch.cuda.current_stream()
+    pristine = torch.from_numpy(maze.view(np.int16)).cuda()
+    work = torch.empty_like(pristine)
+    levels = [torch.empty((rows, cols), dtype=torch.int32, device="cuda") for _ in range(4 if game == "corners" else 1)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    grid = lab.Grid.from_device_ptr(rows, cols, work.data_ptr(), keepalive=work)
+    grid.set_stream(stream.cuda_stream)
+    for k, lv in enumerate(levels):
+        grid.bind_levels(k, lv.data_ptr())
+
+    def step(timed_events=None):
+        work.copy_(pristine)  # restore the Squares (the search marks them) -- outside the timed region
+        flush.fill_(1)        # and push the previous step's lines out of L2
+        if timed_events:
+            timed_events[0].record(stream)
+        settled = run_search(grid, spec)
+        if timed_events:
+            timed_events[1].record(stream)
+        return settled
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    settled = 0
+    t = {"setup_ms": 0.0, "pack_ms": 0.0, "search_ms": 0.0, "post_ms": 0.0, "total_ms": 0.0}
+    for e in evs:
+        settled += step(e)
+        for k in t:
+            t[k] += grid.timing()[k]
+    torch.cuda.synchronize()
+    step_ms = sum(a.elapsed_time(b) for a, b in evs)
+    stats = grid.stats()
+
+    # ---- end to end: pinned host buffers, copies inside the timed region ---------------------------
+    host_in = torch.from_numpy(maze.view(np.int16)).pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    host_lv = torch.empty((rows, cols), dtype=torch.int32).pin_memory() if game == "distance" else None
+    e2e_steps = max(1, min(args.steps, 5))
+    e_ms, e_settled = 0.0, 0
+    for i in range(e2e_steps + 1):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        grid.upload_ptr(host_in.data_ptr())
+        if game == "distance":
+            s = grid.distance_map(spec["start"], dist_host_ptr=host_lv.data_ptr()).settled
+        else:
+            s = run_search(grid, spec)
+        grid.download_ptr(host_out.data_ptr())
+        b.record(stream)
+        torch.cuda.synchronize()
+        if i > 0:  # first one warms the pinned paths
+            e_ms += a.elapsed_time(b)
+            e_settled += s
+    h2d = cells * 2
+    d2h = cells * 2 + (cells * 4 if game == "distance" else 0)
+
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- max over ranks, whole-job aggregate -------------------------------------------------------
+    vec = torch.tensor([step_ms, e_ms, t["search_ms"]], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(settled), float(e_settled)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    step_ms_max, e_ms_max, search_ms_max = (float(x) for x in vec.tolist())
+    settled_all, e_settled_all = (float(x) for x in tot.tolist())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    alg_bytes = ALG_BYTES_PER_CELL[game] * cells
+    search_ms_avg = t["search_ms"] / args.steps
+    achieved = alg_bytes / (search_ms_avg * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(workload)
+    out = {
+        "metric": "cells settled/sec (G/s) for BFS distance map & bfs-gather; % of HBM roofline",
+        "value": settled_all / (step_ms_max * 1e-3) / 1e9,
+        "unit": "Gcells/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": step_ms_max / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u16",
+        "data": "synthetic",
+        "config": {
+            "workload": workload, "stands_for": stands_for, "game": game, "builder": builder, "mod": mod, "rows": rows,
+            "cols": cols, "seed": SEED + 2, "cells_settled_per_step": settled // args.steps,
+            "parallelism": "1 maze per GPU (independent mazes, no data-path collective)" if world > 1 else "1 GPU",
+            "l2": "256 MB flush buffer written between timed steps", "maze_build_s_host": round(build_s, 2),
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "k_bfs_tiles", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": search_ms_avg,
+                     "kernel_share_of_step": t["search_ms"] / step_ms},
+        "e2e": {"value": e_settled_all / (e_ms_max * 1e-3) / 1e9, "unit": "Gcells/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e_ms_max / e2e_steps, "steps": e2e_steps},
+        "gpu_launches": KERNELS_PER_STEP[game] * args.steps,
+        "clocks": clocks,
+        "phases_ms_per_step": {k: v / args.steps for k, v in t.items()},
+        "search_stats_last_step": {k: stats[k] for k in ("tiles", "activations", "empty", "levels", "settled", "resettles",
+                                                         "queue_pushes", "direct", "worker_warps")},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_port_baseline(maze, spec, budget_s=args.cpu_budget)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def port_once(O, maze, spec) -> int:
+    """One run of the oracle's CPU restatement of the workload's game -> cells settled."""
+    game = spec["game"]
+    if game == "distance":
+        return O.distance_map(maze)[3]
+    if game == "gather":
+        g = O.canon_gather(maze, spec["start"], spec["finishes"])[0]
+        return int(((g & (O.PAINT_MASK | O.CACHE_MASK)) != 0).sum())
+    if game == "hunt":
+        g = O.canon_hunt(maze, spec["start"], spec["finish"])[0]
+        return int(((g & O.PAINT_MASK) != 0).sum())
+    g = O.canon_corners(maze, spec["starts"], spec["finish"])[0]
+    return int(((g & O.PAINT_MASK) != 0).sum())
+
+
+def cpu_port_baseline(maze, spec, budget_s: float):
+    """The oracle's CPU restatement (kind "port", one thread) on the same maze, for about budget_s."""
+    O = graft.load_oracle()
+    runs, settled, t0 = 0, 0, time.perf_counter()
+    while True:
+        settled = port_once(O, maze, spec)
+        runs += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or runs >= 50:
+            break
+    return {"value": settled * runs / el / 1e9, "unit": "Gcells/s", "cores": 1, "kind": "port",
+            "sample": f"the full workload maze, {runs} run(s) of oracle/restate.cc in {el:.1f} s", "host_cores_available": os.cpu_count()}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU code on the box's host cores.
+
+    oracle/_ref holds the REAL reference text (compiled in the authoring container, travels as a
+    prebuilt .so).  Its hash (maze/maze.cc:397-405) makes it super-linear, so a step is a bounded
+    sample: the same builder/seed/game at 511x511 (distance) or 383x383 (solvers), which takes
+    seconds.  Distance is single-threaded upstream; the solvers spawn the reference's fixed 4
+    std::threads (solvers/solve_utilities.cc:57) whatever the core count.  Without _ref the oracle
+    port runs the full workload instead."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lab = graft.load_package()
+    O = graft.load_oracle()
+    workload = args.workload
+    game, builder, n, mod, stands_for = WORKLOADS[workload]
+    use_ref = O.have_ref()
+    if use_ref:
+        sn = 511 if game == "distance" else 383
+        maze = lab.build_maze(builder, sn, sn, seed=SEED + 2, mod=mod)
+        kind, cores = "reference", (1 if game == "distance" else 4)
+        game_id = {"hunt": O.HUNT, "gather": O.GATHER, "corners": O.CORNERS}.get(game)
+
+        def one():
+            if game == "distance":
+                d = O.ref_distance(maze, seed=1)[1]
+                return int((d != np.uint64(2**64 - 1)).sum())
+            g = O.ref_game(game_id, maze, seed=SEED + 3)
+            return int(((g & O.PAINT_MASK) != 0).sum())
+        sample = f"{builder} {sn}x{sn} (same seed/game), real reference text (oracle/_ref), {cores} thread(s)"
+    else:
+        maze, spec = make_case(lab, workload)
+        sn, kind, cores = n, "port", 1
+
+        def one():
+            return port_once(O, maze, spec)
+        sample = "full workload, oracle port (oracle/_ref not built here)"
+    for _ in range(min(args.warmup, 1)):
+        one()
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    settled = 0
+    for _ in range(steps):
+        settled += one()
+    el = time.perf_counter() - t0
+    value = settled / el / 1e9
+    print(json.dumps({
+        "impl": "reference", "metric": "cells settled/sec (G/s) for BFS distance map & bfs-gather; % of HBM roofline",
+        "value": value, "unit": "Gcells/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+        "data": "synthetic", "config": {"workload": workload, "stands_for": stands_for, "game": game, "builder": builder, "mod": mod,
+                                        "rows": sn, "cols": sn, "note": "bounded sample of the workload; the reference is super-linear in maze size"},
+        "cpu_baseline": {"value": value, "unit": "Gcells/s", "cores": cores, "kind": kind, "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": value, "unit": "Gcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()
