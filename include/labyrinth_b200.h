@@ -124,6 +124,27 @@ int lab_bfs_corners(lab_grid *g, const lab_point starts[4], lab_point finish, in
 /* Number of squares that received at least one paint/cache bit in the last solver call. */
 uint64_t lab_last_painted(const lab_grid *g);
 
+/* ---- row bands: one lab_grid per GPU holds a band of rows of a taller maze --------------------- */
+/* A sharded distance map is a loop the caller drives (one process per GPU; the exchange is the
+ * caller's: NCCL send/recv of one row of levels per neighbour and a one-word all-reduce):
+ *     lab_band_begin          reset + pack this band (src = -1,-1 if the start is in another band)
+ *     lab_band_path_rows      passable flags (1 byte/column, lab_band_cols_padded columns) of the band's
+ *                             first and last row -> exchange once with the neighbours
+ *     lab_band_set_neighbour_paths   the neighbours' facing rows (NULL = no band there)
+ *     repeat { lab_band_relax; lab_band_export_edges; exchange; lab_band_import_edges -> activated;
+ *              all-reduce(activated) } until no rank activated a tile
+ *     lab_band_finish         measure bits, local max level and local count of settled squares
+ * All row buffers are DEVICE pointers (uint8 / uint32, lab_band_cols_padded entries).  A band with a
+ * neighbour below must have a multiple of 64 rows.  Levels are global BFS levels. */
+int lab_band_cols_padded(const lab_grid *g);
+int lab_band_begin(lab_grid *g, int src_r_local, int src_c);
+int lab_band_path_rows(lab_grid *g, void *top_dev, void *bottom_dev);
+int lab_band_set_neighbour_paths(lab_grid *g, const void *above_bottom_dev, const void *below_top_dev);
+int lab_band_relax(lab_grid *g);
+int lab_band_export_edges(lab_grid *g, void *top_levels_dev, void *bottom_levels_dev);
+int lab_band_import_edges(lab_grid *g, const void *above_bottom_levels_dev, const void *below_top_levels_dev, uint32_t *activated);
+int lab_band_finish(lab_grid *g, uint64_t *local_max, uint64_t *local_settled);
+
 int lab_last_timing(const lab_grid *g, lab_timing *out);
 int lab_last_stats(const lab_grid *g, lab_stats *out);
 const char *lab_last_error(void);

@@ -34,6 +34,8 @@ ABI_SYMBOLS = (
     "lab_bfs_hunt", "lab_bfs_gather", "lab_bfs_corners", "lab_last_painted", "lab_last_timing", "lab_last_stats",
     "lab_last_error", "lab_pick_random_point", "lab_set_corner_starts", "lab_place_hunt", "lab_place_gather",
     "lab_place_corners", "lab_build_maze", "lab_device_info",
+    "lab_band_cols_padded", "lab_band_begin", "lab_band_path_rows", "lab_band_set_neighbour_paths", "lab_band_relax",
+    "lab_band_export_edges", "lab_band_import_edges", "lab_band_finish",
 )
 
 
@@ -107,6 +109,14 @@ def lib():
         L.lab_place_corners.argtypes = [c_int, c_int, c_void_p, c_uint32, c_void_p, POINTER(Point)]
         L.lab_build_maze.argtypes = [c_char_p, c_char_p, c_int, c_int, c_uint32, c_void_p]
         L.lab_device_info.argtypes = [c_char_p, c_size_t]
+        L.lab_band_cols_padded.argtypes = [c_void_p]
+        L.lab_band_begin.argtypes = [c_void_p, c_int, c_int]
+        L.lab_band_path_rows.argtypes = [c_void_p, c_void_p, c_void_p]
+        L.lab_band_set_neighbour_paths.argtypes = [c_void_p, c_void_p, c_void_p]
+        L.lab_band_relax.argtypes = [c_void_p]
+        L.lab_band_export_edges.argtypes = [c_void_p, c_void_p, c_void_p]
+        L.lab_band_import_edges.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_uint32)]
+        L.lab_band_finish.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]
         _lib = L
     return _lib
 

@@ -322,4 +322,91 @@ LAB_DEV void gather_fixup_body(Geom g, uint16_t *grid, Result const *res, int32_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Row bands (one band of a taller maze per GPU).  Between two local searches the ranks exchange
+// the levels of their first / last ROW; these bodies translate between those plain rows
+// (tiles_x*64 entries) and the tile-major structures of one band.
+
+// passable flags (one byte per column) of the band's first and last row.  One thread per column.
+LAB_DEV void band_path_rows_body(Geom g, uint64_t const *path, uint8_t *top, uint8_t *bottom, long long i) {
+    long long const n = static_cast<long long>(g.tiles_x) * TS;
+    if (i >= n) return;
+    long long const tx = i / TS;
+    int const c = static_cast<int>(i % TS);
+    int const last_row = (g.rows - 1) % TS;
+    top[i] = static_cast<uint8_t>((path[tx * TS + 0] >> c) & 1ull);
+    bottom[i] = static_cast<uint8_t>((path[((static_cast<long long>(g.tiles_y) - 1) * g.tiles_x + tx) * TS + last_row] >> c) & 1ull);
+}
+
+// neighbours' border rows (bytes) -> one 64-bit word per tile column, as cross_body wants them.
+// One warp per tile column; a null pointer means "no band there".
+LAB_DEV void band_ghost_words_body(Geom g, uint8_t const *above_bottom, uint8_t const *below_top, uint64_t *ghost_n,
+                                   uint64_t *ghost_s, long long gwarp, long long nwarps, int lane) {
+    for (long long tx = gwarp; tx < g.tiles_x; tx += nwarps) {
+        uint64_t const wn = above_bottom ? lab_ballot64(above_bottom[tx * TS + lane] != 0, above_bottom[tx * TS + lane + 32] != 0) : 0ull;
+        uint64_t const wsb = below_top ? lab_ballot64(below_top[tx * TS + lane] != 0, below_top[tx * TS + lane + 32] != 0) : 0ull;
+        if (lane == 0) {
+            ghost_n[tx] = wn;
+            ghost_s[tx] = wsb;
+        }
+    }
+}
+
+// levels of the band's first row (top tiles' N edges) and last row (bottom tiles' S edges).
+LAB_DEV void band_export_edges_body(Geom g, uint32_t const *edges, uint32_t *top, uint32_t *bottom, long long i) {
+    long long const n = static_cast<long long>(g.tiles_x) * TS;
+    if (i >= n) return;
+    long long const tx = i / TS;
+    int const c = static_cast<int>(i % TS);
+    long long const t_top = tx, t_bot = (static_cast<long long>(g.tiles_y) - 1) * g.tiles_x + tx;
+    top[i] = edges[(t_top + g.tiles_x) * (4 * TS) + SIDE_N * TS + c];
+    bottom[i] = edges[(t_bot + g.tiles_x) * (4 * TS) + SIDE_S * TS + c];
+}
+
+// Take the neighbours' border levels into the ghost tile rows; a border tile whose ghost improved
+// where the border can be crossed becomes active and is queued.  One warp per tile column.
+// (Runs between two launches of the search kernel: every tile is idle, the queue is empty.)
+LAB_DEV void band_import_edges_body(Params p, uint32_t const *above_bottom, uint32_t const *below_top, uint32_t *activated,
+                                    long long gwarp, long long nwarps, int lane) {
+    Geom const &g = p.g;
+    Plane const &pl = p.plane[0];
+    for (long long tx = gwarp; tx < g.tiles_x; tx += nwarps) {
+        for (int side = 0; side < 2; side++) {
+            uint32_t const *src = side == 0 ? above_bottom : below_top;
+            if (!src) continue;
+            long long const t = side == 0 ? tx : (static_cast<long long>(g.tiles_y) - 1) * g.tiles_x + tx;
+            // ghost tile: the one above the top row / below the bottom row in the padded edge array
+            uint32_t *ghost = pl.edges + (side == 0 ? tx : (static_cast<long long>(g.ntiles) + g.tiles_x + tx)) * (4 * TS)
+                              + (side == 0 ? SIDE_S : SIDE_N) * TS;
+            uint32_t const *own = pl.edges + (t + g.tiles_x) * (4 * TS) + (side == 0 ? SIDE_N : SIDE_S) * TS;
+            uint64_t const X = p.cross[t * 4 + (side == 0 ? SIDE_N : SIDE_S)];
+            bool improved = false;
+            for (int h = 0; h < 2; h++) {
+                int const c = lane + 32 * h;
+                uint32_t const v = src[tx * TS + c];
+                if (v < ghost[c]) {
+                    ghost[c] = v;
+                    if (((X >> c) & 1ull) && v + 1 < own[c]) improved = true;
+                }
+            }
+            if (lab_any(improved) && lane == 0) {
+                if (lab_atomic_or(&pl.state[t], ST_ACTIVE) == 0u) {
+                    lab_atomic_add(&p.ctl->pending, 1u);
+                    queue_push(p, static_cast<uint32_t>(t));
+                    lab_atomic_add(activated, 1u);
+                }
+            }
+        }
+    }
+}
+
+// One thread: make the control block ready for another launch of the search kernel.
+LAB_DEV void band_rearm_body(Params p, unsigned long long budget_ns) {
+    p.ctl->head = 0;
+    p.ctl->tail = 0;
+    p.ctl->done = 0;
+    p.ctl->deadline_ns = lab_clock_ns() + budget_ns;
+}
+
 } // namespace lab

@@ -112,6 +112,22 @@ __global__ void k_or_bits(uint16_t *grid, long long cols, int32_t const *cells_r
     }
 }
 
+__global__ void __launch_bounds__(256) k_band_path_rows(Geom g, uint64_t const *path, uint8_t *top, uint8_t *bottom) {
+    band_path_rows_body(g, path, top, bottom, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(256) k_band_ghost_words(Geom g, uint8_t const *above_bottom, uint8_t const *below_top,
+                                                          uint64_t *ghost_n, uint64_t *ghost_s) {
+    band_ghost_words_body(g, above_bottom, below_top, ghost_n, ghost_s, gwarp_id(), nwarps_total(), lane_id());
+}
+__global__ void __launch_bounds__(256) k_band_export_edges(Geom g, uint32_t const *edges, uint32_t *top, uint32_t *bottom) {
+    band_export_edges_body(g, edges, top, bottom, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(256) k_band_import_edges(Params p, uint32_t const *above_bottom, uint32_t const *below_top,
+                                                           uint32_t *activated) {
+    band_import_edges_body(p, above_bottom, below_top, activated, gwarp_id(), nwarps_total(), lane_id());
+}
+__global__ void k_band_rearm(Params p, unsigned long long budget_ns) { band_rearm_body(p, budget_ns); }
+
 __global__ void __launch_bounds__(256) k_and_bits(uint16_t *grid, long long n, uint16_t mask) {
     long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -192,6 +208,11 @@ struct lab_grid {
     lab_stats stats{};
     Result last{};
     float h2d_ms = 0, d2h_ms = 0;
+    // row-band state
+    uint64_t *ghost_n = nullptr, *ghost_s = nullptr; // neighbours' border path rows, one word per tile column
+    uint32_t *d_activated = nullptr;
+    Run_desc band_desc{};
+    bool band_open = false;
 };
 
 namespace {
@@ -293,8 +314,10 @@ int blocks_for(lab_grid *h, long long warps_wanted, int threads) {
     return static_cast<int>(std::max<long long>(1, std::min(b, cap)));
 }
 
-// Reset the workspace, pack the grid, run the persistent search.  Leaves EV_POST0 recorded.
-int run_search(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass_value) {
+unsigned long long budget_ns() { return static_cast<unsigned long long>(env_ll("LAB_BFS_BUDGET_MS", 20000)) * 1000000ull; }
+
+// Reset the workspace and pack the grid into tile bit masks (sources forced passable).
+int search_prepare(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass_value) {
     int rc = ensure_planes(h, d.nplanes);
     if (rc) {
         return rc;
@@ -303,8 +326,6 @@ int run_search(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass
     Geom const &g = h->g;
     size_t const nt = static_cast<size_t>(g.ntiles);
     size_t const cells = static_cast<size_t>(g.rows) * g.cols;
-    Params p = make_params(h, d.nplanes);
-
     CU(cudaEventRecord(h->ev[EV_SETUP0], s));
     CU(cudaMemsetAsync(h->ctl, 0, sizeof(Control), s));
     CU(cudaMemsetAsync(h->res, 0, sizeof(Result), s));
@@ -322,16 +343,42 @@ int run_search(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass
     TRACE("k_pack", s);
     k_force_sources<<<1, 1, 0, s>>>(g, h->path, d);
     TRACE("k_force_sources", s);
-    k_cross<<<blocks_for(h, g.ntiles, 256), 256, 0, s>>>(g, h->path, h->cross, nullptr, nullptr);
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+// Border masks (optionally against the neighbouring bands' rows) and the seeded control block.
+int search_arm(lab_grid *h, Run_desc const &d, uint64_t const *ghost_n, uint64_t const *ghost_s) {
+    cudaStream_t s = h->stream;
+    Geom const &g = h->g;
+    Params p = make_params(h, d.nplanes);
+    k_cross<<<blocks_for(h, g.ntiles, 256), 256, 0, s>>>(g, h->path, h->cross, ghost_n, ghost_s);
     TRACE("k_cross", s);
-    unsigned long long const budget_ns = static_cast<unsigned long long>(env_ll("LAB_BFS_BUDGET_MS", 20000)) * 1000000ull;
-    k_init_run<<<1, 1, 0, s>>>(p, d, budget_ns);
+    k_init_run<<<1, 1, 0, s>>>(p, d, budget_ns());
     TRACE("k_init_run", s);
-    CU(cudaEventRecord(h->ev[EV_SEARCH0], s));
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+int search_launch(lab_grid *h, int nplanes) {
+    cudaStream_t s = h->stream;
+    Params p = make_params(h, nplanes);
     k_bfs_tiles<<<h->bfs_blocks, h->bfs_threads, 0, s>>>(p);
     TRACE("k_bfs_tiles", s);
-    CU(cudaEventRecord(h->ev[EV_POST0], s));
     CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+// Reset the workspace, pack the grid, run the persistent search.  Leaves EV_POST0 recorded.
+int run_search(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass_value) {
+    int rc = search_prepare(h, d, pass_mask, pass_value);
+    if (rc) return rc;
+    rc = search_arm(h, d, nullptr, nullptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev[EV_SEARCH0], h->stream));
+    rc = search_launch(h, d.nplanes);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev[EV_POST0], h->stream));
     return LAB_OK;
 }
 
@@ -508,6 +555,9 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->d_paths);
     cudaFree(h->d_cells);
     cudaFree(h->d_bits);
+    cudaFree(h->ghost_n);
+    cudaFree(h->ghost_s);
+    cudaFree(h->d_activated);
     for (auto &e : h->ev) {
         if (e) cudaEventDestroy(e);
     }
@@ -822,6 +872,120 @@ int lab_bfs_corners(lab_grid *h, const lab_point starts[4], lab_point finish, in
     if (winner) *winner = h->last.winner;
     if (path_len) *path_len = h->last.path_len[0];
     return want ? copy_path(h, 0, path, path_cap, h->last.path_len[0]) : LAB_OK;
+}
+
+// ---- row bands -------------------------------------------------------------------------------
+int lab_band_cols_padded(const lab_grid *h) { return h ? h->g.tiles_x * TS : 0; }
+
+int lab_band_begin(lab_grid *h, int src_r, int src_c) {
+    if (!h) {
+        return fail(LAB_ERR_ARG, "null grid");
+    }
+    if (src_r >= 0 && !in_grid(h, {src_r, src_c})) {
+        return fail(LAB_ERR_ARG, "source (%d,%d) outside the band", src_r, src_c);
+    }
+    Run_desc d{};
+    d.game = GAME_DISTANCE;
+    d.nplanes = 1;
+    for (int k = 0; k < MAX_PLANES; k++) {
+        d.src_r[k] = d.src_c[k] = -1;
+    }
+    if (src_r >= 0) {
+        d.src_r[0] = src_r;
+        d.src_c[0] = src_c;
+    }
+    d.bound_mode = BOUND_NONE;
+    h->band_desc = d;
+    if (!h->ghost_n) {
+        CU(cudaMalloc(&h->ghost_n, static_cast<size_t>(h->g.tiles_x) * sizeof(uint64_t)));
+        CU(cudaMalloc(&h->ghost_s, static_cast<size_t>(h->g.tiles_x) * sizeof(uint64_t)));
+        CU(cudaMalloc(&h->d_activated, sizeof(uint32_t)));
+    }
+    int const rc = search_prepare(h, d, SQ_PATH | SQ_MEASURE, SQ_PATH);
+    h->band_open = rc == LAB_OK;
+    return rc;
+}
+
+int lab_band_path_rows(lab_grid *h, void *top_dev, void *bottom_dev) {
+    if (!h || !h->band_open || !top_dev || !bottom_dev) {
+        return fail(LAB_ERR_ARG, "lab_band_path_rows: bad arguments or no band search open");
+    }
+    int const n = h->g.tiles_x * TS;
+    k_band_path_rows<<<(n + 255) / 256, 256, 0, h->stream>>>(h->g, h->path, static_cast<uint8_t *>(top_dev), static_cast<uint8_t *>(bottom_dev));
+    TRACE("k_band_path_rows", h->stream);
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+int lab_band_set_neighbour_paths(lab_grid *h, const void *above_bottom_dev, const void *below_top_dev) {
+    if (!h || !h->band_open) {
+        return fail(LAB_ERR_ARG, "no band search open");
+    }
+    if (below_top_dev && h->g.rows % TS != 0) {
+        return fail(LAB_ERR_ARG, "a band with a neighbour below must have a multiple of %d rows (has %d)", TS, h->g.rows);
+    }
+    k_band_ghost_words<<<blocks_for(h, h->g.tiles_x, 256), 256, 0, h->stream>>>(
+        h->g, static_cast<uint8_t const *>(above_bottom_dev), static_cast<uint8_t const *>(below_top_dev), h->ghost_n, h->ghost_s);
+    TRACE("k_band_ghost_words", h->stream);
+    int const rc = search_arm(h, h->band_desc, h->ghost_n, h->ghost_s);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev[EV_SEARCH0], h->stream));
+    return LAB_OK;
+}
+
+int lab_band_relax(lab_grid *h) {
+    if (!h || !h->band_open) {
+        return fail(LAB_ERR_ARG, "no band search open");
+    }
+    return search_launch(h, 1);
+}
+
+int lab_band_export_edges(lab_grid *h, void *top_levels_dev, void *bottom_levels_dev) {
+    if (!h || !h->band_open || !top_levels_dev || !bottom_levels_dev) {
+        return fail(LAB_ERR_ARG, "lab_band_export_edges: bad arguments");
+    }
+    int const n = h->g.tiles_x * TS;
+    k_band_export_edges<<<(n + 255) / 256, 256, 0, h->stream>>>(h->g, h->plane[0].edges, static_cast<uint32_t *>(top_levels_dev),
+                                                               static_cast<uint32_t *>(bottom_levels_dev));
+    TRACE("k_band_export_edges", h->stream);
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+int lab_band_import_edges(lab_grid *h, const void *above_bottom_levels_dev, const void *below_top_levels_dev, uint32_t *activated) {
+    if (!h || !h->band_open || !activated) {
+        return fail(LAB_ERR_ARG, "lab_band_import_edges: bad arguments");
+    }
+    cudaStream_t s = h->stream;
+    Params p = make_params(h, 1);
+    CU(cudaMemsetAsync(h->d_activated, 0, sizeof(uint32_t), s));
+    k_band_rearm<<<1, 1, 0, s>>>(p, budget_ns());
+    k_band_import_edges<<<blocks_for(h, h->g.tiles_x, 256), 256, 0, s>>>(p, static_cast<uint32_t const *>(above_bottom_levels_dev),
+                                                                         static_cast<uint32_t const *>(below_top_levels_dev), h->d_activated);
+    TRACE("k_band_import_edges", s);
+    CU(cudaMemcpyAsync(activated, h->d_activated, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return LAB_OK;
+}
+
+int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
+    if (!h || !h->band_open) {
+        return fail(LAB_ERR_ARG, "no band search open");
+    }
+    cudaStream_t s = h->stream;
+    CU(cudaEventRecord(h->ev[EV_POST0], s));
+    Params p = make_params(h, 1);
+    k_resolve<<<1, 1, 0, s>>>(p, h->band_desc, h->res, h->d_finish_rc);
+    k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
+    long long const items = static_cast<long long>(h->g.rows) * h->g.tiles_x;
+    k_measure<<<blocks_for(h, items, 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
+    CU(cudaGetLastError());
+    h->band_open = false;
+    int const rc = finish_run(h);
+    if (rc) return rc;
+    if (local_max) *local_max = h->last.max_level;
+    if (local_settled) *local_settled = h->last.settled;
+    return LAB_OK;
 }
 
 uint64_t lab_last_painted(const lab_grid *h) { return h ? h->last.settled : 0; }

@@ -1,0 +1,172 @@
+"""Row-band sharding (N > 1).
+
+* world_size-2 and -3 gloo runs of the REAL driver (multithreading-with-mazes_b200/bands.py) on the
+  CPU with a numpy stand-in for the per-band search, checked against the oracle: this covers the
+  host-side protocol (row exchange, border crossing, re-activation, termination).
+* on a GPU: the lab_band_* entry points themselves, two and three bands driven in one process on
+  one device (no rank ever waits on another inside a kernel), bit-exact against the oracle.
+"""
+import os
+import sys
+from collections import deque
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INF = 0xFFFFFFFF
+
+
+class NumpyBandEngine:
+    """Test double for GpuBandEngine: same interface, the band search is a plain label-correcting BFS."""
+
+    def __init__(self, squares: np.ndarray):
+        import torch
+
+        self.torch = torch
+        self.sq = squares
+        self.rows, self.cols = squares.shape
+        self.cols_padded = ((self.cols + 63) // 64) * 64
+        self.row_device = torch.device("cpu")
+
+    def begin(self, src_local):
+        self.path = ((self.sq & 0x2000) != 0) & ((self.sq & 0x0200) == 0)
+        self.dist = np.full((self.rows, self.cols), INF, np.uint64)
+        self.ghost_up = np.full(self.cols, INF, np.uint64)
+        self.ghost_dn = np.full(self.cols, INF, np.uint64)
+        self.todo = deque()
+        if src_local is not None:
+            self.path[src_local] = True
+            self.dist[src_local] = 0
+            self.todo.append(src_local)
+
+    def _row(self, a, dtype):
+        out = np.zeros(self.cols_padded, dtype)
+        out[: self.cols] = a
+        return self.torch.from_numpy(out)
+
+    def path_rows(self):
+        return self._row(self.path[0].astype(np.uint8), np.uint8), self._row(self.path[-1].astype(np.uint8), np.uint8)
+
+    def set_neighbour_paths(self, above_bottom, below_top):
+        self.up_ok = above_bottom.numpy()[: self.cols].astype(bool) if above_bottom is not None else np.zeros(self.cols, bool)
+        self.dn_ok = below_top.numpy()[: self.cols].astype(bool) if below_top is not None else np.zeros(self.cols, bool)
+
+    def relax(self):
+        d, p = self.dist, self.path
+        while self.todo:
+            r, c = self.todo.popleft()
+            for nr, nc in ((r - 1, c), (r, c + 1), (r + 1, c), (r, c - 1)):
+                if 0 <= nr < self.rows and 0 <= nc < self.cols and p[nr, nc] and d[nr, nc] > d[r, c] + 1:
+                    d[nr, nc] = d[r, c] + 1
+                    self.todo.append((nr, nc))
+
+    def export_edges(self):
+        return self._row(np.minimum(self.dist[0], INF).astype(np.int64).astype(np.uint32).view(np.int32), np.int32), \
+            self._row(np.minimum(self.dist[-1], INF).astype(np.int64).astype(np.uint32).view(np.int32), np.int32)
+
+    def import_edges(self, above_bottom, below_top):
+        n = 0
+        for src, row, ok in ((above_bottom, 0, self.up_ok), (below_top, self.rows - 1, self.dn_ok)):
+            if src is None:
+                continue
+            v = src.numpy().view(np.uint32)[: self.cols].astype(np.uint64)
+            for c in np.nonzero(ok & self.path[row] & (v != INF) & (v + 1 < self.dist[row]))[0]:
+                self.dist[row, c] = v[c] + 1
+                self.todo.append((row, int(c)))
+                n += 1
+        return n
+
+    def finish(self):
+        reached = self.dist != INF
+        self.sq[reached] |= 0x0200
+        return int(self.dist[reached].max()) if reached.any() else 0, int(reached.sum())
+
+    def new_row(self, like):
+        return self.torch.empty_like(like)
+
+
+def _gloo_worker(rank, world, port, maze_path, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    import __graft_entry__ as graft
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lab = graft.load_package()
+    from mazes_b200 import bands
+
+    maze = np.load(maze_path)
+    r0, n = bands.split_rows(maze.shape[0], world)[rank]
+    eng = NumpyBandEngine(maze[r0 : r0 + n].copy())
+    res = bands.sharded_distance_map(eng, lab.distance_start(*maze.shape), r0, n)
+    np.savez(os.path.join(out_dir, f"band{rank}.npz"), dist=np.minimum(eng.dist, INF).astype(np.uint32), sq=eng.sq, r0=r0,
+             mx=res["max"], settled=res["settled"], rounds=res["rounds"])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("builder,rows,cols,world", [("kruskal", 255, 131, 2), ("wilson", 193, 197, 3), ("grid", 257, 129, 2)])
+def test_sharded_driver_on_gloo(lab, O, tmp_path, builder, rows, cols, world):
+    import torch.multiprocessing as mp
+
+    maze = lab.build_maze(builder, rows, cols, seed=31)
+    path = str(tmp_path / "maze.npy")
+    np.save(path, maze)
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(world, port, path, str(tmp_path)), nprocs=world, join=True)
+    g_ref, d_ref, mx_ref, settled_ref = O.distance_map(maze)
+    for rank in range(world):
+        z = np.load(tmp_path / f"band{rank}.npz")
+        r0 = int(z["r0"])
+        n = z["dist"].shape[0]
+        assert (z["dist"] == d_ref[r0 : r0 + n]).all() and (z["sq"] == g_ref[r0 : r0 + n]).all()
+        assert int(z["mx"]) == mx_ref and int(z["settled"]) == settled_ref and int(z["rounds"]) >= 2
+
+
+def test_split_rows(lab):
+    from mazes_b200 import bands
+
+    assert bands.split_rows(65535, 8) == [(i * 8192, 8192) for i in range(7)] + [(57344, 8191)]
+    assert bands.split_rows(255, 2) == [(0, 128), (128, 127)]
+    with pytest.raises(ValueError):
+        bands.split_rows(63, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("builder,rows,cols,nb", [("kruskal", 511, 383, 2), ("wilson", 767, 257, 3), ("arena", 255, 255, 2), ("grid", 641, 513, 4)])
+def test_band_entry_points_one_process(lab, O, builder, rows, cols, nb):
+    """The lab_band_* kernels, several bands on ONE device driven in lock step by this process."""
+    import torch
+
+    from mazes_b200 import bands
+
+    maze = lab.build_maze(builder, rows, cols, seed=77, mod="cross" if builder == "grid" else None)
+    split = bands.split_rows(rows, nb)
+    sq = [torch.from_numpy(maze[r0 : r0 + n].view(np.int16).copy()).cuda() for r0, n in split]
+    lv = [torch.empty((n, cols), dtype=torch.int32, device="cuda") for _, n in split]
+    eng = [bands.GpuBandEngine(lab, s) for s in sq]
+    for e, l in zip(eng, lv):
+        e.grid.bind_levels(0, l.data_ptr())
+    sr, sc = lab.distance_start(rows, cols)
+    for e, (r0, n) in zip(eng, split):
+        e.begin((sr - r0, sc) if r0 <= sr < r0 + n else None)
+    rows_p = [tuple(t.clone() for t in e.path_rows()) for e in eng]
+    for i, e in enumerate(eng):
+        e.set_neighbour_paths(rows_p[i - 1][1] if i > 0 else None, rows_p[i + 1][0] if i < nb - 1 else None)
+    rounds = 0
+    while True:
+        rounds += 1
+        for e in eng:
+            e.relax()
+        edges = [tuple(t.clone() for t in e.export_edges()) for e in eng]
+        act = [e.import_edges(edges[i - 1][1] if i > 0 else None, edges[i + 1][0] if i < nb - 1 else None) for i, e in enumerate(eng)]
+        if not any(act):
+            break
+        assert rounds < 100000
+    res = [e.finish() for e in eng]
+    g_ref, d_ref, mx_ref, settled_ref = O.distance_map(maze)
+    got_d = np.concatenate([l.cpu().numpy().view(np.uint32) for l in lv])
+    got_g = np.concatenate([s.cpu().numpy().view(np.uint16) for s in sq])
+    assert (got_d == d_ref).all() and (got_g == g_ref).all()
+    assert max(r[0] for r in res) == mx_ref and sum(r[1] for r in res) == settled_ref
