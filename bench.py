@@ -103,12 +103,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_case(lab, workload: str, seed_offset: int = 0):
+def make_case(lab, workload: str, seed_offset: int = 0, bands: int = 1):
+    """The workload's maze.  bands > 1: the same builder/seed on a maze `bands` times taller (each
+    GPU's band keeps the single-GPU workload's size: weak scaling)."""
     game, builder, n, mod, _ = WORKLOADS[workload]
-    maze = lab.build_maze(builder, n, n, seed=SEED + 2 + seed_offset, mod=mod)
-    spec = {"game": game, "rows": n, "cols": n}
+    rows = n if bands == 1 else ((n + 63) // 64) * 64 * bands - 1
+    maze = lab.build_maze(builder, rows, n, seed=SEED + 2 + seed_offset, mod=mod)
+    spec = {"game": game, "rows": rows, "cols": n}
     if game == "distance":
-        spec["start"] = lab.distance_start(n, n)
+        spec["start"] = lab.distance_start(rows, n)
     elif game == "gather":
         maze, spec["start"], spec["finishes"] = lab.place_gather(maze, seed=SEED + 3 + seed_offset)
     elif game == "hunt":
@@ -145,6 +148,8 @@ def ours(args):
     lab = graft.load_package()
     workload = args.workload
     game, builder, n, mod, stands_for = WORKLOADS[workload]
+    if world > 1 and game == "distance" and args.sharding == "bands":
+        return ours_bands(args, lab, dist, torch, world, rank, local)
 
     # ---- synthetic input: one seeded maze per rank (independent mazes: no data-path collective) ----
     t0 = time.time()
@@ -275,6 +280,104 @@ def ours(args):
         dist.destroy_process_group()
 
 
+def ours_bands(args, lab, dist, torch, world, rank, local):
+    """N > 1: ONE maze N times taller than the workload's, sharded as row bands:
+    local persistent searches, one row of levels exchanged with each neighbour over NCCL and a
+    one-word all-reduce between them.  Weak scaling: every GPU's band is the single-GPU workload's size."""
+    from mazes_b200 import bands
+
+    workload = args.workload
+    game, builder, n, mod, stands_for = WORKLOADS[workload]
+    t0 = time.time()
+    maze, spec = make_case(lab, workload, bands=world)  # same seed on every rank -> same maze
+    build_s = time.time() - t0
+    rows, cols = maze.shape
+    r0, nloc = bands.split_rows(rows, world)[rank]
+    stream = torch.cuda.current_stream()
+    pristine = torch.from_numpy(maze[r0:r0 + nloc].view(np.int16).copy()).cuda()
+    work = torch.empty_like(pristine)
+    levels = torch.empty((nloc, cols), dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    eng = bands.GpuBandEngine(lab, work)
+    eng.grid.bind_levels(0, levels.data_ptr())
+
+    def step(ev=None):
+        work.copy_(pristine)
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if ev:
+            ev[0].record(stream)
+        res = bands.sharded_distance_map(eng, spec["start"], r0, nloc)
+        if ev:
+            ev[1].record(stream)
+        return res
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    settled, rounds, search_ms = 0, 0, 0.0
+    for e in evs:
+        res = step(e)
+        settled += res["settled"]
+        rounds += res["rounds"]
+        search_ms += eng.grid.timing()["search_ms"]
+    torch.cuda.synchronize()
+    step_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # end to end: this rank's band from pinned host memory and back (Squares + levels)
+    host_in = torch.from_numpy(maze[r0:r0 + nloc].view(np.int16).copy()).pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    host_lv = torch.empty((nloc, cols), dtype=torch.int32).pin_memory()
+    e_ms, e_settled, e_steps = 0.0, 0, max(1, min(args.steps, 3))
+    for i in range(e_steps + 1):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        work.copy_(host_in, non_blocking=True)
+        res = bands.sharded_distance_map(eng, spec["start"], r0, nloc)
+        host_out.copy_(work, non_blocking=True)
+        host_lv.copy_(levels, non_blocking=True)
+        b.record(stream)
+        torch.cuda.synchronize()
+        if i > 0:
+            e_ms += a.elapsed_time(b)
+            e_settled += res["settled"]
+    clocks = sampler.stop() if rank == 0 else None
+    vec = torch.tensor([step_ms, e_ms, search_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+    step_ms_max, e_ms_max, search_ms_max = (float(x) for x in vec.tolist())
+    if rank == 0:
+        peak, peak_src = peaks()
+        cells = rows * cols
+        alg_bytes = ALG_BYTES_PER_CELL[game] * cells
+        achieved = alg_bytes / (search_ms_max / args.steps * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": "cells settled/sec (G/s) for BFS distance map & bfs-gather; % of HBM roofline",
+            "value": settled / (step_ms_max * 1e-3) / 1e9, "unit": "Gcells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+            "data": "synthetic",
+            "config": {"workload": workload, "stands_for": stands_for, "game": game, "builder": builder, "mod": mod, "rows": rows, "cols": cols,
+                       "seed": SEED + 2, "cells_settled_per_step": settled // args.steps,
+                       "parallelism": f"{world} row bands of one {rows}x{cols} maze, one per GPU; NCCL send/recv of one row of levels per neighbour + 1-word all-reduce between local searches",
+                       "exchange_rounds_per_step": rounds / args.steps, "l2": "256 MB flush buffer written between timed steps",
+                       "maze_build_s_host": round(build_s, 2)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
+                         "kernel": "k_bfs_tiles (all launches of a step, exchanges included)", "peak_source": peak_src + f" x {world} GPUs",
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": search_ms_max / args.steps},
+            "e2e": {"value": e_settled / (e_ms_max * 1e-3) / 1e9, "unit": "Gcells/s", "h2d_bytes_per_step": cells * 2,
+                    "d2h_bytes_per_step": cells * 6, "ms_per_step": e_ms_max / e_steps, "steps": e_steps},
+            "gpu_launches": int((8 + 5 * rounds / args.steps) * args.steps), "clocks": clocks,
+        }))
+    dist.destroy_process_group()
+
+
 def port_once(O, maze, spec) -> int:
     """One run of the oracle's CPU restatement of the workload's game -> cells settled."""
     game = spec["game"]
@@ -371,6 +474,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharding", default="bands", choices=["bands", "replicas"],
+                    help="N > 1: row bands of one tall maze (distance workloads) or one independent maze per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
