@@ -258,6 +258,7 @@ LAB_DEV void source_force_passable(Geom g, uint64_t *path, int r, int c) {
 // an already settled square, so nothing is ever written twice.
 
 constexpr int WINDOW = 64; // levels per batch
+constexpr uint32_t DENSE_BATCH = 384; // squares settled in a batch from which the row-wise write-out pays
 
 // Per-warp shared-memory stage for writing a batch out (see emit_batch).
 // layout (uint64 units): [0,6*64) level planes, [6*64,7*64) visited-before, [7*64,8*64) facing levels
@@ -390,6 +391,69 @@ LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint
     }
     stage[6 * TS + 2 * lane] = V0;
     stage[6 * TS + 2 * lane + 1] = V1;
+    uint32_t const *fW = reinterpret_cast<uint32_t const *>(stage + 7 * TS);
+    uint32_t const *fE = fW + TS;
+    acc.settled += mine;
+    acc.resettled += static_cast<uint32_t>(lab_popc64(S0 & V0) + lab_popc64(S1 & V1));
+    if (total >= DENSE_BATCH) {
+        // ---- dense batch (open areas): one tile ROW at a time, lane l writes columns l and l+32, so
+        // the level stores of a row are two coalesced 128-byte transactions and nothing is serial
+        uint64_t *Srow = stage + STAGE_FIXED_U64; // the cell-list area is free in this mode
+        Srow[2 * lane] = S0;
+        Srow[2 * lane + 1] = S1;
+        lab_syncwarp();
+        uint32_t const even_rows = lab_ballot(S0 != 0); // bit i <-> row 2i
+        uint32_t const odd_rows = lab_ballot(S1 != 0);  // bit i <-> row 2i+1
+        uint32_t kmax = 0;
+        bool any_mine = false;
+        for (int parity = 0; parity < 2; parity++) {
+            uint32_t rows = parity ? odd_rows : even_rows;
+            while (rows) {
+                int const r = 2 * (lab_ffs64(rows) - 1) + parity;
+                rows &= rows - 1;
+                uint64_t const S = Srow[r];
+                uint64_t const Vold = stage[6 * TS + r];
+                uint64_t Bp[6];
+#pragma unroll
+                for (int b = 0; b < 6; b++) {
+                    Bp[b] = stage[b * TS + r];
+                }
+                uint32_t *drow = tc.dist0 + r * tc.cols;
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    int const c = lane + 32 * half;
+                    uint32_t const sbit = (static_cast<uint32_t>(S >> (32 * half)) >> lane) & 1u;
+                    uint32_t k = 0;
+#pragma unroll
+                    for (int b = 0; b < 6; b++) {
+                        k |= ((static_cast<uint32_t>(Bp[b] >> (32 * half)) >> lane) & 1u) << b;
+                    }
+                    uint32_t const lvl = base + k;
+                    bool const old = (static_cast<uint32_t>(Vold >> (32 * half)) >> lane) & 1u;
+                    if (sbit) {
+                        kmax = k > kmax ? k : kmax;
+                        any_mine = true;
+                        if (!old) {
+                            drow[c] = lvl;
+                        } else {
+                            lab_atomic_min(drow + c, lvl);
+                        }
+                        if (c == 0 || c == TS - 1 || r == 0 || r == TS - 1) {
+                            if (c == 0) edge_update(tc.edges + SIDE_W * TS + r, lvl, old, fW[r], SIDE_W, acc);
+                            if (c == TS - 1) edge_update(tc.edges + SIDE_E * TS + r, lvl, old, fE[r], SIDE_E, acc);
+                            if (r == 0) edge_update(tc.edges + SIDE_N * TS + c, lvl, old, fNmax, SIDE_N, acc);
+                            if (r == TS - 1) edge_update(tc.edges + SIDE_S * TS + c, lvl, old, fSmax, SIDE_S, acc);
+                        }
+                    }
+                }
+            }
+        }
+        if (any_mine && base + kmax > acc.max_lvl) {
+            acc.max_lvl = base + kmax;
+        }
+        lab_syncwarp();
+        return;
+    }
     uint16_t *cells = reinterpret_cast<uint16_t *>(stage + STAGE_FIXED_U64);
     {
         uint32_t q = incl - mine;
@@ -407,10 +471,6 @@ LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint
         }
     }
     lab_syncwarp();
-    uint32_t const *fW = reinterpret_cast<uint32_t const *>(stage + 7 * TS);
-    uint32_t const *fE = fW + TS;
-    acc.settled += mine;
-    acc.resettled += static_cast<uint32_t>(lab_popc64(S0 & V0) + lab_popc64(S1 & V1));
     for (uint32_t q = static_cast<uint32_t>(lane); q < total; q += 32) {
         uint32_t const rc = cells[q];
         int const r = static_cast<int>(rc >> 6), c = static_cast<int>(rc & 63u);
