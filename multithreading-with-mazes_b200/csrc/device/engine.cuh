@@ -358,54 +358,74 @@ template <bool INJECT, bool NS> LAB_DEV void step_group(Wave &w, Seeds const &sd
     if (gi & 4) { w.B0[5] |= G0; w.B1[5] |= G1; }
 }
 
-// Write a batch out.  Two steps so that no lane is left holding a long corridor alone:
-//   1. every lane lists the squares settled in ITS two rows as (row << 6 | col) in the warp's
-//      shared-memory cell list (cheap serial loop: find bit, store a halfword), at the offset a
-//      warp-wide prefix sum of the per-lane counts gives it;
-//   2. the list is consumed 32 squares at a time, one square per lane: look the level up in the
-//      staged bit-sliced planes, store it (atomicMin if the square already had a level), and keep
-//      the tile's edge arrays / wake flags up to date for border squares.
-// S0/S1 = squares settled in the batch (rows 2*lane, 2*lane+1), V0/V1 = squares that already had a
-// level before this pass.
-LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint64_t S0, uint64_t S1, uint64_t V0,
-                        uint64_t V1, uint32_t base, int lane, uint32_t fNmax, uint32_t fSmax, Emit_acc &acc) {
-    uint32_t const mine = static_cast<uint32_t>(lab_popc64(S0) + lab_popc64(S1));
-    // inclusive prefix sum over lanes
-    uint32_t incl = mine;
+// level (relative to the batch base) of square c of a row whose bit-sliced planes are B
+LAB_DEV uint32_t plane_level(uint64_t const (&B)[6], int c) {
+    uint32_t k = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t const v = lab_shfl_up(incl, d);
-        if (lane >= d) {
-            incl += v;
+    for (int b = 0; b < 6; b++) {
+        k |= static_cast<uint32_t>((B[b] >> c) & 1ull) << b;
+    }
+    return k;
+}
+// largest relative level among the squares S of a row
+LAB_DEV uint32_t plane_max_level(uint64_t const (&B)[6], uint64_t S) {
+    uint32_t k = 0;
+#pragma unroll
+    for (int b = 5; b >= 0; b--) {
+        uint64_t const t = S & B[b];
+        if (t) {
+            k |= 1u << b;
+            S = t;
+        } else {
+            S &= ~B[b];
         }
     }
-    uint32_t const total = lab_shfl(incl, 31);
+    return k;
+}
+
+// Write a batch out: levels into the dense field, border squares into the tile's edge arrays.
+//   * dense batch (open areas): one tile ROW at a time, lane l writes columns l and l+32 -- two
+//     coalesced 128-byte stores per row, nothing serial, no data-dependent branches;
+//   * sparse batch (corridors): every lane lists the squares of ITS two rows as (row<<6|col) in the
+//     warp's shared-memory cell list at a prefix-sum offset (cheap serial loop), then the list is
+//     consumed 32 squares at a time, so no lane is left holding a long corridor alone;
+//   * border squares are handled once per batch, outside those loops: columns 0/63 by the lane that
+//     owns the row (from its registers), rows 0/63 by the whole warp.
+// S0/S1 = squares settled in the batch (rows 2*lane, 2*lane+1), V0/V1 = squares that already had a
+// level before this pass (they get atomicMin instead of a store).
+LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint64_t S0, uint64_t S1, uint64_t V0,
+                        uint64_t V1, uint32_t base, int lane, uint32_t fW0, uint32_t fW1, uint32_t fE0, uint32_t fE1,
+                        uint32_t fNmax, uint32_t fSmax, Emit_acc &acc) {
+    uint32_t const mine = static_cast<uint32_t>(lab_popc64(S0) + lab_popc64(S1));
+    uint32_t const total = lab_reduce_add(mine);
     if (total == 0) {
         return;
     }
-    // stage[wd * 64 + row]: level planes and visited-before, for step 2
+    int const r0 = 2 * lane, r1 = 2 * lane + 1;
+    // stage[wd * 64 + row]: level planes and visited-before
 #pragma unroll
     for (int b = 0; b < 6; b++) {
-        stage[b * TS + 2 * lane] = w.B0[b];
-        stage[b * TS + 2 * lane + 1] = w.B1[b];
+        stage[b * TS + r0] = w.B0[b];
+        stage[b * TS + r1] = w.B1[b];
     }
-    stage[6 * TS + 2 * lane] = V0;
-    stage[6 * TS + 2 * lane + 1] = V1;
-    uint32_t const *fW = reinterpret_cast<uint32_t const *>(stage + 7 * TS);
-    uint32_t const *fE = fW + TS;
+    stage[6 * TS + r0] = V0;
+    stage[6 * TS + r1] = V1;
     acc.settled += mine;
     acc.resettled += static_cast<uint32_t>(lab_popc64(S0 & V0) + lab_popc64(S1 & V1));
+    {
+        uint32_t const k0 = S0 ? plane_max_level(w.B0, S0) : 0u, k1 = S1 ? plane_max_level(w.B1, S1) : 0u;
+        uint32_t const top = base + (k0 > k1 ? k0 : k1);
+        if (mine && top > acc.max_lvl) {
+            acc.max_lvl = top;
+        }
+    }
     if (total >= DENSE_BATCH) {
-        // ---- dense batch (open areas): one tile ROW at a time, lane l writes columns l and l+32, so
-        // the level stores of a row are two coalesced 128-byte transactions and nothing is serial
         uint64_t *Srow = stage + STAGE_FIXED_U64; // the cell-list area is free in this mode
-        Srow[2 * lane] = S0;
-        Srow[2 * lane + 1] = S1;
+        Srow[r0] = S0;
+        Srow[r1] = S1;
         lab_syncwarp();
         uint32_t const even_rows = lab_ballot(S0 != 0); // bit i <-> row 2i
         uint32_t const odd_rows = lab_ballot(S1 != 0);  // bit i <-> row 2i+1
-        uint32_t kmax = 0;
-        bool any_mine = false;
         for (int parity = 0; parity < 2; parity++) {
             uint32_t rows = parity ? odd_rows : even_rows;
             while (rows) {
@@ -421,81 +441,98 @@ LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint
                 uint32_t *drow = tc.dist0 + r * tc.cols;
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
-                    int const c = lane + 32 * half;
                     uint32_t const sbit = (static_cast<uint32_t>(S >> (32 * half)) >> lane) & 1u;
+                    uint32_t const old = (static_cast<uint32_t>(Vold >> (32 * half)) >> lane) & 1u;
                     uint32_t k = 0;
 #pragma unroll
                     for (int b = 0; b < 6; b++) {
                         k |= ((static_cast<uint32_t>(Bp[b] >> (32 * half)) >> lane) & 1u) << b;
                     }
-                    uint32_t const lvl = base + k;
-                    bool const old = (static_cast<uint32_t>(Vold >> (32 * half)) >> lane) & 1u;
-                    if (sbit) {
-                        kmax = k > kmax ? k : kmax;
-                        any_mine = true;
-                        if (!old) {
-                            drow[c] = lvl;
-                        } else {
-                            lab_atomic_min(drow + c, lvl);
-                        }
-                        if (c == 0 || c == TS - 1 || r == 0 || r == TS - 1) {
-                            if (c == 0) edge_update(tc.edges + SIDE_W * TS + r, lvl, old, fW[r], SIDE_W, acc);
-                            if (c == TS - 1) edge_update(tc.edges + SIDE_E * TS + r, lvl, old, fE[r], SIDE_E, acc);
-                            if (r == 0) edge_update(tc.edges + SIDE_N * TS + c, lvl, old, fNmax, SIDE_N, acc);
-                            if (r == TS - 1) edge_update(tc.edges + SIDE_S * TS + c, lvl, old, fSmax, SIDE_S, acc);
-                        }
+                    if (sbit & ~old) {
+                        drow[lane + 32 * half] = base + k;
+                    }
+                    if (sbit & old) {
+                        lab_atomic_min(drow + lane + 32 * half, base + k);
                     }
                 }
             }
         }
-        if (any_mine && base + kmax > acc.max_lvl) {
-            acc.max_lvl = base + kmax;
+    } else {
+        // inclusive prefix sum of the per-lane counts
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t const v = lab_shfl_up(incl, d);
+            if (lane >= d) {
+                incl += v;
+            }
+        }
+        uint16_t *cells = reinterpret_cast<uint16_t *>(stage + STAGE_FIXED_U64);
+        {
+            uint32_t q = incl - mine;
+            uint64_t m = S0;
+            while (m) {
+                int const c = lab_ffs64(m) - 1;
+                m &= m - 1;
+                cells[q++] = static_cast<uint16_t>((r0 << 6) | c);
+            }
+            m = S1;
+            while (m) {
+                int const c = lab_ffs64(m) - 1;
+                m &= m - 1;
+                cells[q++] = static_cast<uint16_t>((r1 << 6) | c);
+            }
         }
         lab_syncwarp();
-        return;
-    }
-    uint16_t *cells = reinterpret_cast<uint16_t *>(stage + STAGE_FIXED_U64);
-    {
-        uint32_t q = incl - mine;
-        uint64_t m = S0;
-        while (m) {
-            int const c = lab_ffs64(m) - 1;
-            m &= m - 1;
-            cells[q++] = static_cast<uint16_t>(((2 * lane) << 6) | c);
-        }
-        m = S1;
-        while (m) {
-            int const c = lab_ffs64(m) - 1;
-            m &= m - 1;
-            cells[q++] = static_cast<uint16_t>(((2 * lane + 1) << 6) | c);
-        }
-    }
-    lab_syncwarp();
-    for (uint32_t q = static_cast<uint32_t>(lane); q < total; q += 32) {
-        uint32_t const rc = cells[q];
-        int const r = static_cast<int>(rc >> 6), c = static_cast<int>(rc & 63u);
-        uint32_t k = 0;
+        for (uint32_t q = static_cast<uint32_t>(lane); q < total; q += 32) {
+            uint32_t const rc = cells[q];
+            int const r = static_cast<int>(rc >> 6), c = static_cast<int>(rc & 63u);
+            uint32_t k = 0;
 #pragma unroll
-        for (int b = 0; b < 6; b++) {
-            k |= static_cast<uint32_t>((stage[b * TS + r] >> c) & 1ull) << b;
-        }
-        uint32_t const lvl = base + k;
-        bool const old = (stage[6 * TS + r] >> c) & 1ull;
-        uint32_t *d = tc.dist0 + r * tc.cols + c;
-        acc.max_lvl = lvl > acc.max_lvl ? lvl : acc.max_lvl;
-        bool const border = c == 0 || c == TS - 1 || r == 0 || r == TS - 1;
-        if (!old && !border) { // the common case: an interior square settled for the first time
-            *d = lvl;
-        } else {
-            if (!old) {
-                *d = lvl;
-            } else {
-                lab_atomic_min(d, lvl);
+            for (int b = 0; b < 6; b++) {
+                k |= static_cast<uint32_t>((stage[b * TS + r] >> c) & 1ull) << b;
             }
-            if (c == 0) edge_update(tc.edges + SIDE_W * TS + r, lvl, old, fW[r], SIDE_W, acc);
-            if (c == TS - 1) edge_update(tc.edges + SIDE_E * TS + r, lvl, old, fE[r], SIDE_E, acc);
-            if (r == 0) edge_update(tc.edges + SIDE_N * TS + c, lvl, old, fNmax, SIDE_N, acc);
-            if (r == TS - 1) edge_update(tc.edges + SIDE_S * TS + c, lvl, old, fSmax, SIDE_S, acc);
+            bool const old = (stage[6 * TS + r] >> c) & 1ull;
+            uint32_t *d = tc.dist0 + r * tc.cols + c;
+            if (!old) {
+                *d = base + k;
+            } else {
+                lab_atomic_min(d, base + k);
+            }
+        }
+    }
+    // ---- border squares -----------------------------------------------------------------------
+    // columns 0 and 63: the lane that owns the row, straight from its registers
+    uint64_t const edge_cols = (1ull << 63) | 1ull;
+    if ((S0 | S1) & edge_cols) {
+        if (S0 & 1ull) edge_update(tc.edges + SIDE_W * TS + r0, base + plane_level(w.B0, 0), V0 & 1ull, fW0, SIDE_W, acc);
+        if (S1 & 1ull) edge_update(tc.edges + SIDE_W * TS + r1, base + plane_level(w.B1, 0), V1 & 1ull, fW1, SIDE_W, acc);
+        if (S0 >> 63) edge_update(tc.edges + SIDE_E * TS + r0, base + plane_level(w.B0, 63), V0 >> 63, fE0, SIDE_E, acc);
+        if (S1 >> 63) edge_update(tc.edges + SIDE_E * TS + r1, base + plane_level(w.B1, 63), V1 >> 63, fE1, SIDE_E, acc);
+    }
+    // rows 0 and 63: the whole warp, lane l looks after columns l and l+32
+    uint64_t const Sn = lab_shfl64(S0, 0), Ss = lab_shfl64(S1, 31);
+    if (Sn | Ss) {
+        lab_syncwarp();
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            uint64_t const S = side == 0 ? Sn : Ss;
+            if (S == 0) continue;
+            int const r = side == 0 ? 0 : TS - 1;
+            uint64_t Bp[6];
+#pragma unroll
+            for (int b = 0; b < 6; b++) {
+                Bp[b] = stage[b * TS + r];
+            }
+            uint64_t const Vold = stage[6 * TS + r];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                int const c = lane + 32 * half;
+                if ((S >> c) & 1ull) {
+                    edge_update(tc.edges + (side == 0 ? SIDE_N : SIDE_S) * TS + c, base + plane_level(Bp, c), (Vold >> c) & 1ull,
+                                side == 0 ? fNmax : fSmax, side == 0 ? SIDE_N : SIDE_S, acc);
+                }
+            }
         }
     }
     lab_syncwarp(); // the stage is reused by the next batch
@@ -685,14 +722,6 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
             // beats the WORST level over there (conservative; the exact per-column test is not needed)
             uint32_t const fNmax = XN ? lab_reduce_max(fN0 > fN1 ? fN0 : fN1) : 0u;
             uint32_t const fSmax = XS ? lab_reduce_max(fS0 > fS1 ? fS0 : fS1) : 0u;
-            {   // W/E facing levels per row, for the lanes that will write columns 0 and 63 out
-                uint32_t *fW = reinterpret_cast<uint32_t *>(stage + 7 * TS);
-                uint32_t *fE = fW + TS;
-                fW[r0] = fW0;
-                fW[r1] = fW1;
-                fE[r0] = fE0;
-                fE[r1] = fE1;
-            }
             bool const any_ns = lab_any((sN0 & sN1 & sS0 & sS1) != INF);
             Wave w;
             w.A0 = P0;
@@ -775,7 +804,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                 // ---- write the batch out ---------------------------------------------------------
                 LAB_PROF(uint64_t const ps1 = lab_cycles(); ws.c_step += ps1 - ps0;)
                 uint64_t const S0 = A0s & ~w.A0, S1 = A1s & ~w.A1;
-                emit_batch(tc, stage, w, S0, S1, V0, V1, base, lane, fNmax, fSmax, acc);
+                emit_batch(tc, stage, w, S0, S1, V0, V1, base, lane, fW0, fW1, fE0, fE1, fNmax, fSmax, acc);
                 Vn0 |= S0;
                 Vn1 |= S1;
                 LAB_PROF(ws.c_emit += lab_cycles() - ps1;)

@@ -43,7 +43,7 @@ __global__ void k_force_sources(Geom g, uint64_t *path, Run_desc d) { force_sour
 __global__ void k_init_run(Params p, Run_desc d, unsigned long long budget_ns) { init_run_body(p, d, budget_ns); }
 
 // The persistent search kernel: every warp is a worker until the search is done.
-__global__ void __launch_bounds__(128) k_bfs_tiles(Params p) {
+__global__ void __launch_bounds__(128, 3) k_bfs_tiles(Params p) {
     __shared__ __align__(16) uint64_t stage[4][STAGE_U64];
     bfs_worker_body(p, lane_id(), stage[threadIdx.x >> 5]);
 }
