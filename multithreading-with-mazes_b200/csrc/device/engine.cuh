@@ -383,23 +383,29 @@ LAB_DEV uint32_t plane_max_level(uint64_t const (&B)[6], uint64_t S) {
     return k;
 }
 
-// Write a batch out: levels into the dense field, border squares into the tile's edge arrays.
-//   * dense batch (open areas): one tile ROW at a time, lane l writes columns l and l+32 -- two
-//     coalesced 128-byte stores per row, nothing serial, no data-dependent branches;
-//   * sparse batch (corridors): every lane lists the squares of ITS two rows as (row<<6|col) in the
-//     warp's shared-memory cell list at a prefix-sum offset (cheap serial loop), then the list is
-//     consumed 32 squares at a time, so no lane is left holding a long corridor alone;
-//   * border squares are handled once per batch, outside those loops: columns 0/63 by the lane that
-//     owns the row (from its registers), rows 0/63 by the whole warp.
+// Writing a batch out happens in two steps so that the neighbouring tiles can start as early as
+// possible:
+//   emit_borders   stages the batch (bit-sliced level planes, visited-before) in the warp's shared
+//                  memory, brings the tile's EDGE arrays up to date for the border squares settled in
+//                  the batch (columns 0/63: the lane that owns the row, from its registers; rows
+//                  0/63: the whole warp) and tells which neighbours can use them.  Cheap.
+//   -- the caller wakes those neighbours here --
+//   emit_interior  writes the levels of all settled squares into the dense field:
+//                  * dense batch (open areas): one tile ROW at a time, lane l writes columns l and
+//                    l+32: two coalesced 128-byte stores per row, no data-dependent branches;
+//                  * sparse batch (corridors): every lane lists the squares of ITS two rows as
+//                    (row<<6|col) in a shared-memory cell list at a prefix-sum offset, then the list
+//                    is consumed 32 squares at a time, so no lane holds a long corridor alone.
 // S0/S1 = squares settled in the batch (rows 2*lane, 2*lane+1), V0/V1 = squares that already had a
 // level before this pass (they get atomicMin instead of a store).
-LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint64_t S0, uint64_t S1, uint64_t V0,
-                        uint64_t V1, uint32_t base, int lane, uint32_t fW0, uint32_t fW1, uint32_t fE0, uint32_t fE1,
-                        uint32_t fNmax, uint32_t fSmax, Emit_acc &acc) {
+// Returns the number of squares settled in the batch (warp-wide).
+LAB_DEV uint32_t emit_borders(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint64_t S0, uint64_t S1, uint64_t V0,
+                              uint64_t V1, uint32_t base, int lane, uint32_t fW0, uint32_t fW1, uint32_t fE0, uint32_t fE1,
+                              uint32_t fNmax, uint32_t fSmax, Emit_acc &acc) {
     uint32_t const mine = static_cast<uint32_t>(lab_popc64(S0) + lab_popc64(S1));
     uint32_t const total = lab_reduce_add(mine);
     if (total == 0) {
-        return;
+        return 0;
     }
     int const r0 = 2 * lane, r1 = 2 * lane + 1;
     // stage[wd * 64 + row]: level planes and visited-before
@@ -419,6 +425,47 @@ LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint
             acc.max_lvl = top;
         }
     }
+    // columns 0 and 63: the lane that owns the row, straight from its registers
+    uint64_t const edge_cols = (1ull << 63) | 1ull;
+    if ((S0 | S1) & edge_cols) {
+        if (S0 & 1ull) edge_update(tc.edges + SIDE_W * TS + r0, base + plane_level(w.B0, 0), V0 & 1ull, fW0, SIDE_W, acc);
+        if (S1 & 1ull) edge_update(tc.edges + SIDE_W * TS + r1, base + plane_level(w.B1, 0), V1 & 1ull, fW1, SIDE_W, acc);
+        if (S0 >> 63) edge_update(tc.edges + SIDE_E * TS + r0, base + plane_level(w.B0, 63), V0 >> 63, fE0, SIDE_E, acc);
+        if (S1 >> 63) edge_update(tc.edges + SIDE_E * TS + r1, base + plane_level(w.B1, 63), V1 >> 63, fE1, SIDE_E, acc);
+    }
+    // rows 0 and 63: the whole warp, lane l looks after columns l and l+32
+    uint64_t const Sn = lab_shfl64(S0, 0), Ss = lab_shfl64(S1, 31);
+    lab_syncwarp(); // the stage is complete (also needed by emit_interior)
+    if (Sn | Ss) {
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            uint64_t const S = side == 0 ? Sn : Ss;
+            if (S == 0) continue;
+            int const r = side == 0 ? 0 : TS - 1;
+            uint64_t Bp[6];
+#pragma unroll
+            for (int b = 0; b < 6; b++) {
+                Bp[b] = stage[b * TS + r];
+            }
+            uint64_t const Vold = stage[6 * TS + r];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                int const c = lane + 32 * half;
+                if ((S >> c) & 1ull) {
+                    edge_update(tc.edges + (side == 0 ? SIDE_N : SIDE_S) * TS + c, base + plane_level(Bp, c), (Vold >> c) & 1ull,
+                                side == 0 ? fNmax : fSmax, side == 0 ? SIDE_N : SIDE_S, acc);
+                }
+            }
+        }
+    }
+    return total;
+}
+
+LAB_DEV void emit_interior(Tile_ctx const &tc, uint64_t *stage, uint64_t S0, uint64_t S1, uint32_t base, int lane, uint32_t total) {
+    if (total == 0) {
+        return;
+    }
+    int const r0 = 2 * lane, r1 = 2 * lane + 1;
     if (total >= DENSE_BATCH) {
         uint64_t *Srow = stage + STAGE_FIXED_U64; // the cell-list area is free in this mode
         Srow[r0] = S0;
@@ -458,8 +505,8 @@ LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint
             }
         }
     } else {
-        // inclusive prefix sum of the per-lane counts
-        uint32_t incl = mine;
+        uint32_t const mine = static_cast<uint32_t>(lab_popc64(S0) + lab_popc64(S1));
+        uint32_t incl = mine; // inclusive prefix sum of the per-lane counts
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t const v = lab_shfl_up(incl, d);
@@ -498,40 +545,6 @@ LAB_DEV void emit_batch(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint
                 *d = base + k;
             } else {
                 lab_atomic_min(d, base + k);
-            }
-        }
-    }
-    // ---- border squares -----------------------------------------------------------------------
-    // columns 0 and 63: the lane that owns the row, straight from its registers
-    uint64_t const edge_cols = (1ull << 63) | 1ull;
-    if ((S0 | S1) & edge_cols) {
-        if (S0 & 1ull) edge_update(tc.edges + SIDE_W * TS + r0, base + plane_level(w.B0, 0), V0 & 1ull, fW0, SIDE_W, acc);
-        if (S1 & 1ull) edge_update(tc.edges + SIDE_W * TS + r1, base + plane_level(w.B1, 0), V1 & 1ull, fW1, SIDE_W, acc);
-        if (S0 >> 63) edge_update(tc.edges + SIDE_E * TS + r0, base + plane_level(w.B0, 63), V0 >> 63, fE0, SIDE_E, acc);
-        if (S1 >> 63) edge_update(tc.edges + SIDE_E * TS + r1, base + plane_level(w.B1, 63), V1 >> 63, fE1, SIDE_E, acc);
-    }
-    // rows 0 and 63: the whole warp, lane l looks after columns l and l+32
-    uint64_t const Sn = lab_shfl64(S0, 0), Ss = lab_shfl64(S1, 31);
-    if (Sn | Ss) {
-        lab_syncwarp();
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            uint64_t const S = side == 0 ? Sn : Ss;
-            if (S == 0) continue;
-            int const r = side == 0 ? 0 : TS - 1;
-            uint64_t Bp[6];
-#pragma unroll
-            for (int b = 0; b < 6; b++) {
-                Bp[b] = stage[b * TS + r];
-            }
-            uint64_t const Vold = stage[6 * TS + r];
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                int const c = lane + 32 * half;
-                if ((S >> c) & 1ull) {
-                    edge_update(tc.edges + (side == 0 ? SIDE_N : SIDE_S) * TS + c, base + plane_level(Bp, c), (Vold >> c) & 1ull,
-                                side == 0 ? fNmax : fSmax, side == 0 ? SIDE_N : SIDE_S, acc);
-                }
             }
         }
     }
@@ -656,7 +669,6 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
     if (lane == SIDE_S) nb = ty < g.tiles_y - 1 ? t + g.tiles_x : -1;
     if (lane == SIDE_W) nb = tx > 0 ? t - 1 : -1;
     if (lane == SIDE_E) nb = tx < g.tiles_x - 1 ? t + 1 : -1;
-    bool owned = false; // this lane's neighbour was made active by us and is ours to run or queue
 
     Emit_acc acc{0u, 0u, 0u, 0u};
     bool first_pass = true;
@@ -791,7 +803,19 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                         step_group<true, false>(w, sd, gi, lane);
                     }
                     ws.levels += 8;
-                    if (!lab_any((w.F0 | w.F1) != 0)) {
+                    // a border square was settled: end the batch here so the neighbour hears of it now
+                    // (only squares whose level can beat what the neighbour holds across the border count)
+                    uint64_t const Sb0 = A0s & ~w.A0, Sb1 = A1s & ~w.A1;
+                    uint32_t const l1 = base + 8u * static_cast<uint32_t>(gi) + 1u;
+                    uint64_t const h0 = (l1 < fW0 ? 1ull : 0ull) | (l1 < fE0 ? (1ull << 63) : 0ull) | ((lane == 0 && l1 < fNmax) ? XN : 0ull);
+                    uint64_t const h1 = (l1 < fW1 ? 1ull : 0ull) | (l1 < fE1 ? (1ull << 63) : 0ull) | ((lane == 31 && l1 < fSmax) ? XS : 0ull);
+                    bool const hit = ((Sb0 & h0) | (Sb1 & h1)) != 0;
+                    uint32_t const gflags = lab_reduce_or((((w.F0 | w.F1) != 0) ? 1u : 0u) | (hit ? 2u : 0u));
+                    if (gflags & 2u) {
+                        gi++;
+                        break;
+                    }
+                    if (!(gflags & 1u)) {
                         // nothing moving: skip to the next group of this window that holds a seed, if any
                         uint32_t const later = grp & ~((2u << gi) - 1u);
                         if (later == 0 || base + 8u * static_cast<uint32_t>(lab_ffs64(later) - 1) > bound) {
@@ -804,7 +828,19 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                 // ---- write the batch out ---------------------------------------------------------
                 LAB_PROF(uint64_t const ps1 = lab_cycles(); ws.c_step += ps1 - ps0;)
                 uint64_t const S0 = A0s & ~w.A0, S1 = A1s & ~w.A1;
-                emit_batch(tc, stage, w, S0, S1, V0, V1, base, lane, fW0, fW1, fE0, fE1, fNmax, fSmax, acc);
+                uint32_t const n_batch = emit_borders(tc, stage, w, S0, S1, V0, V1, base, lane, fW0, fW1, fE0, fE1, fNmax, fSmax, acc);
+                // let the neighbours this batch reached start NOW, on other warps: they only read our
+                // edge arrays, which are complete; the interior levels are written out afterwards
+                uint32_t const woke_now = lab_reduce_or(acc.wake);
+                if (woke_now) {
+                    acc.wake = 0;
+                    bool const got = wake_neighbours(pl, ctl, woke_now, lane, nb, false);
+                    if (got) {
+                        queue_push(p, static_cast<uint32_t>(plane) * static_cast<uint32_t>(g.ntiles) + static_cast<uint32_t>(nb));
+                    }
+                    ws.pushes += static_cast<uint32_t>(lab_popc64(lab_ballot(got)));
+                }
+                emit_interior(tc, stage, S0, S1, base, lane, n_batch);
                 Vn0 |= S0;
                 Vn1 |= S1;
                 LAB_PROF(ws.c_emit += lab_cycles() - ps1;)
@@ -837,37 +873,19 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                 if (base > bound) {
                     break;
                 }
-                // More batches to come here: let the neighbours this batch reached start NOW, on other
-                // warps, instead of at the end of the pass (their wave does not wait for our leftovers).
-                uint32_t const woke_now = lab_reduce_or(acc.wake);
-                if (woke_now) {
-                    acc.wake = 0;
-                    bool const got = wake_neighbours(pl, ctl, woke_now, lane, nb, owned);
-                    if (got) {
-                        queue_push(p, static_cast<uint32_t>(plane) * static_cast<uint32_t>(g.ntiles) + static_cast<uint32_t>(nb));
-                    }
-                    ws.pushes += static_cast<uint32_t>(lab_popc64(lab_ballot(got)));
-                }
             }
             if ((Vn0 != V0) | (Vn1 != V1)) {
                 lab_st_cg(pl.visited + t * TS + r0, Vn0);
                 lab_st_cg(pl.visited + t * TS + r1, Vn1);
             }
         }
-        uint32_t const woke = lab_reduce_or(acc.wake);
         bool const settled_any = lab_any(acc.settled != 0);
         LAB_PROF(uint64_t const pt2 = lab_cycles(); ws.c_loop += pt2 - pt1;)
 
-        // ---- publish ----------------------------------------------------------------------------
-        // wake protocol: a neighbour is taken with CAS(idle -> ACTIVE), i.e. it starts with DIRTY
-        // clear and needs no clearing round trip before it reads the edges; if it is already
-        // active it is marked DIRTY instead and whoever runs it goes round again.
-        bool const attempt = lane < 4 && ((woke >> lane) & 1u) && nb >= 0 && !owned;
-        uint32_t const n_attempt = static_cast<uint32_t>(lab_popc64(lab_ballot(attempt)));
-        if (lane == 0 && n_attempt) {
-            lab_atomic_add(&ctl->pending, n_attempt); // over-counts until the failures are taken back
+        // ---- publish: the levels and visited bits above must be visible before the tile is let go ---
+        if (settled_any) {
+            lab_threadfence();
         }
-        lab_threadfence(); // levels, edges and visited bits above are visible before any flag below
         lab_syncwarp();
 
         // targets in this tile: refresh their values and the search bound
@@ -899,26 +917,10 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
             }
         }
 
-        // one round trip: lanes 0..3 try to take their neighbour, lane 4 tries to let this tile go idle
+        // let this tile go idle; if somebody marked it DIRTY meanwhile, go round again
         uint32_t r = 0;
-        if (attempt) {
-            r = lab_atomic_cas(&pl.state[nb], 0u, ST_ACTIVE);
-        } else if (lane == 4) {
+        if (lane == 4) {
             r = lab_atomic_cas(&pl.state[t], ST_ACTIVE, 0u);
-        }
-        bool failed = attempt && r != 0u;
-        if (attempt && !failed) {
-            owned = true;
-        }
-        if (lab_any(failed)) {
-            if (failed) { // already active over there: make sure it looks again
-                uint32_t const old = lab_atomic_or(&pl.state[nb], ST_ACTIVE | ST_DIRTY);
-                if (!(old & ST_ACTIVE)) {
-                    owned = true; // it went idle in between: ours after all (it will do one spurious rerun)
-                } else {
-                    lab_atomic_sub(&ctl->pending, 1u);
-                }
-            }
         }
         uint32_t const r4 = lab_shfl(r, 4); // what this tile's state word held when we tried to let go
         bool const again = r4 != ST_ACTIVE;
@@ -936,31 +938,14 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
     }
     LAB_PROF(uint64_t const pt3 = lab_cycles();)
 
-    // ---- hand the woken neighbours on: keep the first for ourselves, queue the rest --------------
-    uint32_t const own_mask = lab_ballot(owned);
-    uint32_t next = ITEM_NONE;
-    if (own_mask) {
-        int const first = lab_ffs64(own_mask) - 1;
-        uint32_t const base_item = static_cast<uint32_t>(plane) * static_cast<uint32_t>(g.ntiles);
-        uint32_t const mine = owned ? base_item + static_cast<uint32_t>(nb) : ITEM_NONE;
-        next = lab_shfl(mine, first);
-        if (owned && lane != first) {
-            queue_push(p, mine);
-        }
-    }
-    {
-        uint32_t const n_own = static_cast<uint32_t>(lab_popc64(own_mask));
-        ws.pushes += n_own > 1 ? n_own - 1 : 0;
-        ws.direct += n_own ? 1 : 0;
-        ws.settled += acc.settled;
-        ws.resettled += acc.resettled;
-        ws.max_lvl = acc.max_lvl > ws.max_lvl ? acc.max_lvl : ws.max_lvl;
-    }
+    ws.settled += acc.settled;
+    ws.resettled += acc.resettled;
+    ws.max_lvl = acc.max_lvl > ws.max_lvl ? acc.max_lvl : ws.max_lvl;
     if (lane == 0) {
         lab_atomic_sub(&ctl->pending, 1u); // this tile is idle now
     }
     LAB_PROF(ws.c_pub += lab_cycles() - pt3;)
-    return next;
+    return ITEM_NONE; // every woken neighbour went through the queue
 }
 
 // The persistent worker: every warp of the launch runs this until no tile is active any more.
