@@ -803,19 +803,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                         step_group<true, false>(w, sd, gi, lane);
                     }
                     ws.levels += 8;
-                    // a border square was settled: end the batch here so the neighbour hears of it now
-                    // (only squares whose level can beat what the neighbour holds across the border count)
-                    uint64_t const Sb0 = A0s & ~w.A0, Sb1 = A1s & ~w.A1;
-                    uint32_t const l1 = base + 8u * static_cast<uint32_t>(gi) + 1u;
-                    uint64_t const h0 = (l1 < fW0 ? 1ull : 0ull) | (l1 < fE0 ? (1ull << 63) : 0ull) | ((lane == 0 && l1 < fNmax) ? XN : 0ull);
-                    uint64_t const h1 = (l1 < fW1 ? 1ull : 0ull) | (l1 < fE1 ? (1ull << 63) : 0ull) | ((lane == 31 && l1 < fSmax) ? XS : 0ull);
-                    bool const hit = ((Sb0 & h0) | (Sb1 & h1)) != 0;
-                    uint32_t const gflags = lab_reduce_or((((w.F0 | w.F1) != 0) ? 1u : 0u) | (hit ? 2u : 0u));
-                    if (gflags & 2u) {
-                        gi++;
-                        break;
-                    }
-                    if (!(gflags & 1u)) {
+                    if (!lab_any((w.F0 | w.F1) != 0)) {
                         // nothing moving: skip to the next group of this window that holds a seed, if any
                         uint32_t const later = grp & ~((2u << gi) - 1u);
                         if (later == 0 || base + 8u * static_cast<uint32_t>(lab_ffs64(later) - 1) > bound) {
