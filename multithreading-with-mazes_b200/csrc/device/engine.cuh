@@ -471,29 +471,32 @@ LAB_DEV void emit_interior(Tile_ctx const &tc, uint64_t *stage, uint64_t S0, uin
         Srow[r0] = S0;
         Srow[r1] = S1;
         lab_syncwarp();
-        uint32_t const even_rows = lab_ballot(S0 != 0); // bit i <-> row 2i
-        uint32_t const odd_rows = lab_ballot(S1 != 0);  // bit i <-> row 2i+1
-        for (int parity = 0; parity < 2; parity++) {
-            uint32_t rows = parity ? odd_rows : even_rows;
-            while (rows) {
-                int const r = 2 * (lab_ffs64(rows) - 1) + parity;
-                rows &= rows - 1;
-                uint64_t const S = Srow[r];
-                uint64_t const Vold = stage[6 * TS + r];
-                uint64_t Bp[6];
+        // two rows (2i, 2i+1) per iteration, branch free: an empty row simply stores nothing
+        uint32_t pairs = lab_ballot((S0 | S1) != 0); // bit i <-> rows 2i, 2i+1
+        while (pairs) {
+            int const r = 2 * (lab_ffs64(pairs) - 1);
+            pairs &= pairs - 1;
+            uint64_t Sx[2], Vx[2], Bp[2][6];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                Sx[j] = Srow[r + j];
+                Vx[j] = stage[6 * TS + r + j];
 #pragma unroll
                 for (int b = 0; b < 6; b++) {
-                    Bp[b] = stage[b * TS + r];
+                    Bp[j][b] = stage[b * TS + r + j];
                 }
-                uint32_t *drow = tc.dist0 + r * tc.cols;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                uint32_t *drow = tc.dist0 + (r + j) * tc.cols;
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
-                    uint32_t const sbit = (static_cast<uint32_t>(S >> (32 * half)) >> lane) & 1u;
-                    uint32_t const old = (static_cast<uint32_t>(Vold >> (32 * half)) >> lane) & 1u;
+                    uint32_t const sbit = (static_cast<uint32_t>(Sx[j] >> (32 * half)) >> lane) & 1u;
+                    uint32_t const old = (static_cast<uint32_t>(Vx[j] >> (32 * half)) >> lane) & 1u;
                     uint32_t k = 0;
 #pragma unroll
                     for (int b = 0; b < 6; b++) {
-                        k |= ((static_cast<uint32_t>(Bp[b] >> (32 * half)) >> lane) & 1u) << b;
+                        k |= ((static_cast<uint32_t>(Bp[j][b] >> (32 * half)) >> lane) & 1u) << b;
                     }
                     if (sbit & ~old) {
                         drow[lane + 32 * half] = base + k;
@@ -531,20 +534,33 @@ LAB_DEV void emit_interior(Tile_ctx const &tc, uint64_t *stage, uint64_t S0, uin
             }
         }
         lab_syncwarp();
-        for (uint32_t q = static_cast<uint32_t>(lane); q < total; q += 32) {
-            uint32_t const rc = cells[q];
-            int const r = static_cast<int>(rc >> 6), c = static_cast<int>(rc & 63u);
-            uint32_t k = 0;
+        for (uint32_t q = static_cast<uint32_t>(lane); q < total; q += 64) {
+            // two squares per lane and iteration (independent: their latencies overlap)
+            bool const two = q + 32 < total;
+            uint32_t const rcA = cells[q], rcB = two ? cells[q + 32] : rcA;
+            int const rA = static_cast<int>(rcA >> 6), cA = static_cast<int>(rcA & 63u);
+            int const rB = static_cast<int>(rcB >> 6), cB = static_cast<int>(rcB & 63u);
+            uint32_t kA = 0, kB = 0;
 #pragma unroll
             for (int b = 0; b < 6; b++) {
-                k |= static_cast<uint32_t>((stage[b * TS + r] >> c) & 1ull) << b;
+                kA |= static_cast<uint32_t>((stage[b * TS + rA] >> cA) & 1ull) << b;
+                kB |= static_cast<uint32_t>((stage[b * TS + rB] >> cB) & 1ull) << b;
             }
-            bool const old = (stage[6 * TS + r] >> c) & 1ull;
-            uint32_t *d = tc.dist0 + r * tc.cols + c;
-            if (!old) {
-                *d = base + k;
+            bool const oldA = (stage[6 * TS + rA] >> cA) & 1ull;
+            bool const oldB = (stage[6 * TS + rB] >> cB) & 1ull;
+            uint32_t *dA = tc.dist0 + rA * tc.cols + cA;
+            uint32_t *dB = tc.dist0 + rB * tc.cols + cB;
+            if (!oldA) {
+                *dA = base + kA;
             } else {
-                lab_atomic_min(d, base + k);
+                lab_atomic_min(dA, base + kA);
+            }
+            if (two) {
+                if (!oldB) {
+                    *dB = base + kB;
+                } else {
+                    lab_atomic_min(dB, base + kB);
+                }
             }
         }
     }
