@@ -150,33 +150,35 @@ LAB_DEV uint32_t lab_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 // One warp-item = 64 squares of one row (lane reads squares lane and lane+32).
 LAB_DEV void pack_body(Geom g, uint16_t const *grid, uint64_t *path, uint16_t mask, uint16_t value,
                        long long gwarp, long long nwarps, int lane) {
+    // one warp per row (grid stride), the row's 64-square words four at a time: 8 independent
+    // 2-byte loads per lane in flight, no division in the loop
     constexpr int U = 4;
-    long long const rows_pad = static_cast<long long>(g.tiles_y) * TS;
-    long long const total = rows_pad * g.tiles_x;
-    for (long long base = gwarp * U; base < total; base += nwarps * U) {
-        uint16_t a[U], b[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            long long const item = base + u;
-            long long const r = item / g.tiles_x;
-            int const j = static_cast<int>(item % g.tiles_x);
-            int const c0 = j * TS + lane;
-            int const c1 = c0 + 32;
-            bool const in_r = item < total && r < g.rows;
-            a[u] = (in_r && c0 < g.cols) ? lab_ld_ro(grid + r * g.cols + c0) : static_cast<uint16_t>(~value);
-            b[u] = (in_r && c1 < g.cols) ? lab_ld_ro(grid + r * g.cols + c1) : static_cast<uint16_t>(~value);
+    int const rows_pad = g.tiles_y * TS;
+    for (long long rr = gwarp; rr < rows_pad; rr += nwarps) {
+        int const r = static_cast<int>(rr);
+        uint64_t *out = path + (static_cast<long long>(r / TS) * g.tiles_x) * TS + (r % TS);
+        if (r >= g.rows) { // padding rows of the last tile row: not passable
+            for (int j = lane; j < g.tiles_x; j += 32) {
+                out[static_cast<long long>(j) * TS] = 0;
+            }
+            continue;
         }
+        uint16_t const *row = grid + static_cast<long long>(r) * g.cols;
+        for (int j0 = 0; j0 < g.tiles_x; j0 += U) {
+            uint16_t a[U], b[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            long long const item = base + u;
-            long long const r = item / g.tiles_x;
-            int const j = static_cast<int>(item % g.tiles_x);
-            bool const in_r = item < total && r < g.rows;
-            int const c0 = j * TS + lane;
-            uint64_t const w = lab_ballot64(in_r && c0 < g.cols && (a[u] & mask) == value,
-                                            in_r && c0 + 32 < g.cols && (b[u] & mask) == value);
-            if (lane == 0 && item < total) {
-                path[((r / TS) * g.tiles_x + j) * TS + (r % TS)] = w;
+            for (int u = 0; u < U; u++) {
+                int const c0 = (j0 + u) * TS + lane;
+                a[u] = c0 < g.cols ? lab_ld_ro(row + c0) : static_cast<uint16_t>(~value);
+                b[u] = c0 + 32 < g.cols ? lab_ld_ro(row + c0 + 32) : static_cast<uint16_t>(~value);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                int const c0 = (j0 + u) * TS + lane;
+                uint64_t const w = lab_ballot64(c0 < g.cols && (a[u] & mask) == value, c0 + 32 < g.cols && (b[u] & mask) == value);
+                if (lane == 0 && j0 + u < g.tiles_x) {
+                    out[static_cast<long long>(j0 + u) * TS] = w;
+                }
             }
         }
     }

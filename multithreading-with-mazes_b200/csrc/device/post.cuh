@@ -95,24 +95,26 @@ LAB_DEV void force_sources_body(Geom g, uint64_t *path, Run_desc d) {
 // Same row/word item space as pack_body.
 LAB_DEV void measure_body(Geom g, uint16_t *grid, uint64_t const *visited, Result *res, long long gwarp,
                           long long nwarps, int lane) {
-    long long const total = static_cast<long long>(g.rows) * g.tiles_x;
+    // one warp per row (grid stride); a 64-square word with no visited square costs one 8-byte load
     unsigned long long count = 0;
-    for (long long item = gwarp; item < total; item += nwarps) {
-        long long const r = item / g.tiles_x;
-        int const j = static_cast<int>(item % g.tiles_x);
-        uint64_t const v = visited[((r / TS) * g.tiles_x + j) * TS + (r % TS)];
-        if (v == 0) {
-            continue;
+    for (long long rr = gwarp; rr < g.rows; rr += nwarps) {
+        int const r = static_cast<int>(rr);
+        uint64_t const *vrow = visited + (static_cast<long long>(r / TS) * g.tiles_x) * TS + (r % TS);
+        uint16_t *row = grid + static_cast<long long>(r) * g.cols;
+        for (int j = 0; j < g.tiles_x; j++) {
+            uint64_t const v = vrow[static_cast<long long>(j) * TS];
+            if (v == 0) {
+                continue;
+            }
+            int const c0 = j * TS + lane;
+            if ((v >> lane) & 1) {
+                row[c0] |= SQ_MEASURE;
+            }
+            if ((v >> (lane + 32)) & 1) {
+                row[c0 + 32] |= SQ_MEASURE;
+            }
+            count += static_cast<unsigned long long>(lab_popc64(v));
         }
-        int const c0 = j * TS + lane;
-        int const c1 = c0 + 32;
-        if ((v >> lane) & 1) {
-            grid[r * g.cols + c0] |= SQ_MEASURE;
-        }
-        if ((v >> (lane + 32)) & 1) {
-            grid[r * g.cols + c1] |= SQ_MEASURE;
-        }
-        count += static_cast<unsigned long long>(lab_popc64(v));
     }
     if (lane == 0 && count) {
         lab_atomic_add(reinterpret_cast<uint64_t *>(&res->settled), static_cast<uint64_t>(count));

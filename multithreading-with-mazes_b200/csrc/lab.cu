@@ -338,8 +338,7 @@ int search_prepare(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t 
         CU(cudaMemsetAsync(pl.dist, 0xFF, cells * sizeof(uint32_t), s));
     }
     CU(cudaEventRecord(h->ev[EV_PACK0], s));
-    long long const pack_items = static_cast<long long>(g.tiles_y) * TS * g.tiles_x;
-    k_pack<<<blocks_for(h, (pack_items + 3) / 4, 256), 256, 0, s>>>(g, h->squares, h->path, pass_mask, pass_value);
+    k_pack<<<blocks_for(h, static_cast<long long>(g.tiles_y) * TS, 256), 256, 0, s>>>(g, h->squares, h->path, pass_mask, pass_value);
     TRACE("k_pack", s);
     k_force_sources<<<1, 1, 0, s>>>(g, h->path, d);
     TRACE("k_force_sources", s);
@@ -688,8 +687,7 @@ int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t 
     TRACE("k_resolve", s);
     k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
     TRACE("k_max_level", s);
-    long long const items = static_cast<long long>(h->g.rows) * h->g.tiles_x;
-    k_measure<<<blocks_for(h, items, 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
+    k_measure<<<blocks_for(h, h->g.rows, 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
     TRACE("k_measure", s);
     CU(cudaGetLastError());
     rc = finish_run(h);
@@ -977,8 +975,7 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
     Params p = make_params(h, 1);
     k_resolve<<<1, 1, 0, s>>>(p, h->band_desc, h->res, h->d_finish_rc);
     k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
-    long long const items = static_cast<long long>(h->g.rows) * h->g.tiles_x;
-    k_measure<<<blocks_for(h, items, 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
+    k_measure<<<blocks_for(h, h->g.rows, 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
     CU(cudaGetLastError());
     h->band_open = false;
     int const rc = finish_run(h);
