@@ -74,6 +74,9 @@ typedef struct lab_stats {
     uint32_t error;         /* Control.error                                             */
     /* SM cycles summed over worker warps; non-zero only in the -DLAB_PROFILE build */
     uint64_t cyc_load, cyc_loop, cyc_publish, cyc_idle, cyc_step, cyc_emit, batches;
+    /* spanning-tree pipeline (csrc/device/tree.cuh): passable squares, adjacent passable pairs (a tree
+     * has pairs == squares - 1), tile-border crossings, and whether the pipeline produced the field */
+    uint64_t tree_squares, tree_pairs, tree_crossings, tree_used;
 } lab_stats;
 
 /* ---- grid lifetime (replaces Maze::Maze construction, maze/maze.cc:349-354, for the GPU side) -- */

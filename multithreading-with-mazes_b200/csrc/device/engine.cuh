@@ -401,6 +401,8 @@ LAB_DEV uint32_t plane_max_level(uint64_t const (&B)[6], uint64_t S) {
 // S0/S1 = squares settled in the batch (rows 2*lane, 2*lane+1), V0/V1 = squares that already had a
 // level before this pass (they get atomicMin instead of a store).
 // Returns the number of squares settled in the batch (warp-wide).
+// EDGES = false: only stage the batch and keep the statistics (tree.cuh's final flood has no neighbours to tell).
+template <bool EDGES>
 LAB_DEV uint32_t emit_borders(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint64_t S0, uint64_t S1, uint64_t V0,
                               uint64_t V1, uint32_t base, int lane, uint32_t fW0, uint32_t fW1, uint32_t fE0, uint32_t fE1,
                               uint32_t fNmax, uint32_t fSmax, Emit_acc &acc) {
@@ -426,6 +428,10 @@ LAB_DEV uint32_t emit_borders(Tile_ctx const &tc, uint64_t *stage, Wave const &w
         if (mine && top > acc.max_lvl) {
             acc.max_lvl = top;
         }
+    }
+    if (!EDGES) {
+        lab_syncwarp(); // the stage is complete
+        return total;
     }
     // columns 0 and 63: the lane that owns the row, straight from its registers
     uint64_t const edge_cols = (1ull << 63) | 1ull;
@@ -834,7 +840,7 @@ LAB_DEV uint32_t relax_tile(Params const &p, uint32_t item, int lane, uint64_t *
                 // ---- write the batch out ---------------------------------------------------------
                 LAB_PROF(uint64_t const ps1 = lab_cycles(); ws.c_step += ps1 - ps0;)
                 uint64_t const S0 = A0s & ~w.A0, S1 = A1s & ~w.A1;
-                uint32_t const n_batch = emit_borders(tc, stage, w, S0, S1, V0, V1, base, lane, fW0, fW1, fE0, fE1, fNmax, fSmax, acc);
+                uint32_t const n_batch = emit_borders<true>(tc, stage, w, S0, S1, V0, V1, base, lane, fW0, fW1, fE0, fE1, fNmax, fSmax, acc);
                 // let the neighbours this batch reached start NOW, on other warps: they only read our
                 // edge arrays, which are complete; the interior levels are written out afterwards
                 uint32_t const woke_now = lab_reduce_or(acc.wake);

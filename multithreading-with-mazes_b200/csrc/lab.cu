@@ -15,6 +15,7 @@
 #include "../../include/labyrinth_b200.h"
 #include "device/engine.cuh"
 #include "device/post.cuh"
+#include "device/tree.cuh"
 #include "host/builders.hh"
 #include "host/points.hh"
 
@@ -47,6 +48,36 @@ __global__ void __launch_bounds__(128, 3) k_bfs_tiles(Params p) {
     __shared__ __align__(16) uint64_t stage[4][STAGE_U64];
     bfs_worker_body(p, lane_id(), stage[threadIdx.x >> 5]);
 }
+
+// ---- spanning-tree pipeline (device/tree.cuh) ----
+__global__ void __launch_bounds__(256) k_tree_count(Params p, Tree tr) { tree_count_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
+__global__ void k_tree_init(Tree tr) { tree_init_body(tr); }
+__global__ void __launch_bounds__(256) k_tree_walk(Params p, Tree tr) {
+    __shared__ __align__(16) uint64_t sm[8][WALK_U64];
+    tree_walk_body(p, tr, lane_id(), sm[threadIdx.x >> 5]);
+}
+__global__ void __launch_bounds__(256) k_tree_rank_round(Tree tr, uint32_t round) {
+    tree_rank_round_body(tr, round, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+                         static_cast<long long>(gridDim.x) * blockDim.x);
+}
+__global__ void __launch_bounds__(256) k_tree_orient(Params p, Tree tr) { tree_orient_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
+__global__ void __launch_bounds__(128, 4) k_tree_local(Params p, Tree tr) {
+    __shared__ __align__(16) uint64_t stage[4][LOCAL_STAGE_U64];
+    tree_local_body(p, tr, lane_id(), stage[threadIdx.x >> 5]);
+}
+__global__ void __launch_bounds__(256) k_tree_parent(Params p, Tree tr) {
+    tree_parent_body(p, tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+                     static_cast<long long>(gridDim.x) * blockDim.x);
+}
+__global__ void __launch_bounds__(256) k_tree_prefix_round(Tree tr, uint32_t round) {
+    tree_prefix_round_body(tr, round, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+                           static_cast<long long>(gridDim.x) * blockDim.x);
+}
+__global__ void __launch_bounds__(128, 3) k_tree_final(Params p, Tree tr) {
+    __shared__ __align__(16) uint64_t stage[4][STAGE_U64];
+    tree_final_body(p, tr, lane_id(), stage[threadIdx.x >> 5]);
+}
+__global__ void k_tree_gate(Params p, Tree tr) { tree_gate_body(p, tr); }
 
 __global__ void __launch_bounds__(256) k_measure(Geom g, uint16_t *grid, uint64_t const *visited, Result *res) {
     measure_body(g, grid, visited, res, gwarp_id(), nwarps_total(), lane_id());
@@ -213,6 +244,11 @@ struct lab_grid {
     uint32_t *d_activated = nullptr;
     Run_desc band_desc{};
     bool band_open = false;
+    // spanning-tree pipeline workspace (allocated on first use)
+    Tree tree{};
+    bool tree_alloc = false;
+    Tree_ctl tree_last{};
+    bool tree_tried = false;
 };
 
 namespace {
@@ -368,6 +404,95 @@ int search_launch(lab_grid *h, int nplanes) {
     return LAB_OK;
 }
 
+int ensure_tree(lab_grid *h) {
+    if (h->tree_alloc) {
+        return LAB_OK;
+    }
+    Tree &tr = h->tree;
+    size_t const nt = static_cast<size_t>(h->g.ntiles);
+    if (nt * SLOTS + 2 >= (1ull << 32)) {
+        return fail(LAB_ERR_ARG, "maze too large for the tree pipeline");
+    }
+    tr.nslots = static_cast<uint32_t>(nt * SLOTS);
+    size_t const n = (nt * SLOTS + 2) * sizeof(uint32_t);
+    CU(cudaMalloc(&tr.succ0, n));
+    CU(cudaMalloc(&tr.s[0], n));
+    CU(cudaMalloc(&tr.s[1], n));
+    CU(cudaMalloc(&tr.r[0], n));
+    CU(cudaMalloc(&tr.r[1], n));
+    CU(cudaMalloc(&tr.inmask, nt * 4 * sizeof(uint64_t)));
+    CU(cudaMalloc(&tr.loc, nt * SLOTS * sizeof(uint32_t)));
+    CU(cudaMalloc(&tr.tc, sizeof(Tree_ctl)));
+    h->tree_alloc = true;
+    return LAB_OK;
+}
+
+int ceil_log2(unsigned long long n) {
+    int r = 0;
+    while ((1ull << r) < n) {
+        r++;
+    }
+    return r;
+}
+
+// The spanning-tree pipeline (device/tree.cuh), between search_arm and the wave kernel.  One host
+// round trip: the square / adjacency counts decide whether the maze can be a tree at all.  Everything
+// after that is gated on the device; if any check fails the wave kernel finds its control block
+// untouched and does the search.
+int run_tree(lab_grid *h, Run_desc const &d) {
+    h->tree_last = Tree_ctl{};
+    h->tree_tried = false;
+    if (d.nplanes != 1 || d.src_r[0] < 0 || env_ll("LAB_TREE", 1) == 0) {
+        return LAB_OK;
+    }
+    int rc = ensure_tree(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Tree const tr = h->tree;
+    Params p = make_params(h, 1);
+    CU(cudaMemsetAsync(tr.tc, 0, sizeof(Tree_ctl), s));
+    k_tree_count<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, tr);
+    TRACE("k_tree_count", s);
+    Tree_ctl c{};
+    CU(cudaMemcpyAsync(&c, tr.tc, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    h->tree_last = c;
+    if (c.V < 2 || c.E + 1 != c.V) {
+        return LAB_OK; // not a tree: the wave does it
+    }
+    uint32_t const one = 1;
+    CU(cudaMemcpyAsync(&tr.tc->ok, &one, sizeof one, cudaMemcpyHostToDevice, s));
+    k_tree_init<<<1, 1, 0, s>>>(tr);
+    int const walk_blocks = std::min<long long>((h->g.ntiles + 7) / 8, static_cast<long long>(h->sm_count) * 8);
+    k_tree_walk<<<walk_blocks, 256, 0, s>>>(p, tr);
+    TRACE("k_tree_walk", s);
+    long long const nslots = static_cast<long long>(tr.nslots) + 2;
+    int const slot_blocks = static_cast<int>(std::min<long long>((nslots + 255) / 256, static_cast<long long>(h->sm_count) * 16));
+    int const rounds = ceil_log2(static_cast<unsigned long long>(nslots));
+    for (int r = 0; r < rounds; r++) {
+        k_tree_rank_round<<<slot_blocks, 256, 0, s>>>(tr, static_cast<uint32_t>(r));
+    }
+    TRACE("k_tree_rank_round", s);
+    k_tree_orient<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, tr);
+    TRACE("k_tree_orient", s);
+    int const fill_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 4);
+    k_tree_local<<<fill_blocks, 128, 0, s>>>(p, tr);
+    TRACE("k_tree_local", s);
+    k_tree_parent<<<slot_blocks, 256, 0, s>>>(p, tr);
+    TRACE("k_tree_parent", s);
+    for (int r = 0; r < rounds; r++) {
+        k_tree_prefix_round<<<slot_blocks, 256, 0, s>>>(tr, static_cast<uint32_t>(r));
+    }
+    TRACE("k_tree_prefix_round", s);
+    k_tree_final<<<std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 3), 128, 0, s>>>(p, tr);
+    TRACE("k_tree_final", s);
+    k_tree_gate<<<1, 1, 0, s>>>(p, tr);
+    TRACE("k_tree_gate", s);
+    h->tree_tried = true; // finish_run reads the pipeline's control block back
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
 // Reset the workspace, pack the grid, run the persistent search.  Leaves EV_POST0 recorded.
 int run_search(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass_value) {
     int rc = search_prepare(h, d, pass_mask, pass_value);
@@ -375,6 +500,8 @@ int run_search(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass
     rc = search_arm(h, d, nullptr, nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(h->ev[EV_SEARCH0], h->stream));
+    rc = run_tree(h, d);
+    if (rc) return rc;
     rc = search_launch(h, d.nplanes);
     if (rc) return rc;
     CU(cudaEventRecord(h->ev[EV_POST0], h->stream));
@@ -388,6 +515,9 @@ int finish_run(lab_grid *h) {
     Control c{};
     CU(cudaMemcpyAsync(&h->last, h->res, sizeof(Result), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(&c, h->ctl, sizeof(Control), cudaMemcpyDeviceToHost, s));
+    if (h->tree_tried) {
+        CU(cudaMemcpyAsync(&h->tree_last, h->tree.tc, sizeof(Tree_ctl), cudaMemcpyDeviceToHost, s));
+    }
     CU(cudaStreamSynchronize(s));
     lab_timing &t = h->timing;
     CU(cudaEventElapsedTime(&t.setup_ms, h->ev[EV_SETUP0], h->ev[EV_PACK0]));
@@ -415,6 +545,10 @@ int finish_run(lab_grid *h) {
     st.cyc_step = c.cyc_step;
     st.cyc_emit = c.cyc_emit;
     st.batches = c.n_batches;
+    st.tree_squares = h->tree_last.V;
+    st.tree_pairs = h->tree_last.E;
+    st.tree_crossings = h->tree_last.n_arcs;
+    st.tree_used = h->tree_last.used;
     if (c.error == 1) {
         return fail(LAB_ERR_TIMEOUT, "search kernel passed its deadline (LAB_BFS_BUDGET_MS); %llu tiles still active",
                     static_cast<unsigned long long>(c.pending));
@@ -557,6 +691,14 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->ghost_n);
     cudaFree(h->ghost_s);
     cudaFree(h->d_activated);
+    cudaFree(h->tree.succ0);
+    cudaFree(h->tree.s[0]);
+    cudaFree(h->tree.s[1]);
+    cudaFree(h->tree.r[0]);
+    cudaFree(h->tree.r[1]);
+    cudaFree(h->tree.inmask);
+    cudaFree(h->tree.loc);
+    cudaFree(h->tree.tc);
     for (auto &e : h->ev) {
         if (e) cudaEventDestroy(e);
     }

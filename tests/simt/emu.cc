@@ -6,6 +6,7 @@
 
 #include "../../multithreading-with-mazes_b200/csrc/device/engine.cuh"
 #include "../../multithreading-with-mazes_b200/csrc/device/post.cuh"
+#include "../../multithreading-with-mazes_b200/csrc/device/tree.cuh"
 
 #include <cstring>
 #include <vector>
@@ -24,6 +25,52 @@ struct Workspace {
     std::vector<uint32_t> queue;
     Result res;
 };
+
+int g_tree_mode = 1;      // 0: never, 1: when the counts allow it (as csrc/lab.cu does)
+Tree_ctl g_tree_last{};
+
+// The spanning-tree pipeline, orchestrated as run_tree() in csrc/lab.cu does.
+void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned sched_seed) {
+    g_tree_last = Tree_ctl{};
+    if (d.nplanes != 1 || d.src_r[0] < 0 || !g_tree_mode) return;
+    size_t const nt = static_cast<size_t>(w.g.ntiles);
+    size_t const n = nt * SLOTS + 2;
+    std::vector<uint32_t> succ0(n), s0(n), s1(n), r0(n), r1(n), loc(nt * SLOTS);
+    std::vector<uint64_t> inmask(nt * 4);
+    Tree_ctl tc{};
+    Tree tr{};
+    tr.succ0 = succ0.data();
+    tr.s[0] = s0.data();
+    tr.s[1] = s1.data();
+    tr.r[0] = r0.data();
+    tr.r[1] = r1.data();
+    tr.inmask = inmask.data();
+    tr.loc = loc.data();
+    tr.tc = &tc;
+    tr.nslots = static_cast<uint32_t>(nt * SLOTS);
+    simt::launch(nwarps, [&](int wid, int lane) { tree_count_body(p, tr, wid, nwarps, lane); });
+    g_tree_last = tc;
+    if (tc.V < 2 || tc.E + 1 != tc.V) return;
+    tc.ok = 1;
+    tree_init_body(tr);
+    std::vector<uint64_t> sm(static_cast<size_t>(nwarps) * STAGE_U64);
+    simt::launch(nwarps, [&](int wid, int lane) { tree_walk_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * STAGE_U64); }, sched_seed);
+    long long const nthreads = static_cast<long long>(nwarps) * 32;
+    int rounds = 0;
+    while ((1ull << rounds) < n) rounds++;
+    for (int r = 0; r < rounds; r++) {
+        simt::launch(nwarps, [&](int wid, int lane) { tree_rank_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
+    }
+    simt::launch(nwarps, [&](int wid, int lane) { tree_orient_body(p, tr, wid, nwarps, lane); });
+    simt::launch(nwarps, [&](int wid, int lane) { tree_local_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * STAGE_U64); }, sched_seed);
+    simt::launch(nwarps, [&](int wid, int lane) { tree_parent_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    for (int r = 0; r < rounds; r++) {
+        simt::launch(nwarps, [&](int wid, int lane) { tree_prefix_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
+    }
+    simt::launch(nwarps, [&](int wid, int lane) { tree_final_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * STAGE_U64); }, sched_seed);
+    tree_gate_body(p, tr);
+    g_tree_last = tc;
+}
 
 Params make_params(Workspace &w, int nplanes) {
     Params p{};
@@ -69,6 +116,7 @@ int search(Workspace &w, uint16_t *grid, int rows, int cols, Run_desc const &d, 
     force_sources_body(g, w.path.data(), d);
     simt::launch(nwarps, [&](int wid, int lane) { cross_body(g, w.path.data(), w.cross.data(), nullptr, nullptr, wid, nwarps, lane); });
     init_run_body(p, d, 60ull * 1000000000ull);
+    run_tree(w, p, d, nwarps, sched_seed);
     std::vector<uint64_t> stages(static_cast<size_t>(nwarps) * STAGE_U64);
     simt::launch(nwarps, [&](int wid, int lane) { bfs_worker_body(p, lane, stages.data() + static_cast<size_t>(wid) * STAGE_U64); }, sched_seed);
     if (w.ctl.error) return -100 - static_cast<int>(w.ctl.error);
@@ -96,6 +144,10 @@ void stats_out(Workspace const &w, uint64_t *st) {
 } // namespace
 
 extern "C" {
+
+void emu_set_tree(int mode) { g_tree_mode = mode; }
+// 0: the tile wave made the field; 1: the tree pipeline did
+int emu_last_tree_used(void) { return static_cast<int>(g_tree_last.used); }
 
 int emu_distance(int rows, int cols, uint16_t *grid, int sr, int sc, uint32_t *dist_out, uint64_t *max_out,
                  uint64_t *settled_out, int nwarps, unsigned sched_seed, uint64_t *stats) {
