@@ -100,15 +100,31 @@ LAB_DEV void tree_count_body(Params const &p, Tree const &tr, long long gwarp, l
 // arrived with); it takes the first open direction among right, straight, left, back.  On a tree
 // that visits every arc exactly once, i.e. it is the Euler tour.
 //
-// shared memory per warp (uint64 units): open[64][4] | res[256] uint32 | list[256] uint8 | counter
-constexpr int WALK_U64 = 4 * TS + SLOTS / 2 + SLOTS / 8 + 2;
+// A segment between two crossings of a tile can be thousands of steps long (the tour of a whole
+// subtree), and one thread would walk it alone.  So the walk is cut once more, at the borders of
+// the tile's sixteen 16x16 BLOCKS: phase A starts a walker at every open border between two blocks
+// as well (in both directions) and every walker stops at the first block border it crosses -- a few
+// dozen steps; phase B then hops from piece to piece (one shared-memory look-up each) from every
+// tile crossing to the crossing its segment ends at.
+//
+// walker ids: [0,256) tile crossings [side][pos]; 256 + h*192 + (b-1)*64 + pos: heading h over inner
+// border b (1..3, at row/column 16*b), pos = row (h = E, W) or column (h = N, S); 1024: the root.
+// piece results (uint16): < 1024 the next piece; 1024 + s: leaves the tile into the neighbour's slot s;
+// 0xFFFF: the end of the tour.
+//
+// shared memory per warp (uint64 units): open[64][4] | res16[1032] | list16[1032] (later res32[256]) | masks[16] | counter
+constexpr int WALK_IDS = 1025;
+constexpr int WALK_U64 = 4 * TS + 260 + 260 + 16 + 2;
+constexpr uint32_t WALK_END = 0xFFFFu;
 
 LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, uint64_t *sm) {
     Geom const &g = p.g;
     uint64_t *open = sm;
-    uint32_t *res = reinterpret_cast<uint32_t *>(sm + 4 * TS);
-    uint8_t *list = reinterpret_cast<uint8_t *>(sm + 4 * TS + SLOTS / 2);
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(sm + 4 * TS + SLOTS / 2 + SLOTS / 8);
+    uint16_t *res16 = reinterpret_cast<uint16_t *>(sm + 4 * TS);
+    uint16_t *list = reinterpret_cast<uint16_t *>(sm + 4 * TS + 260);
+    uint32_t *res32 = reinterpret_cast<uint32_t *>(sm + 4 * TS + 260); // after phase A the list is dead
+    uint64_t *masks = sm + 4 * TS + 520;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(sm + 4 * TS + 536);
     uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
     int const r0 = 2 * lane, r1 = 2 * lane + 1;
 
@@ -127,9 +143,26 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
     open[r1 * 4 + 1] = (P1 & (P1 >> 1)) | (((X[SIDE_E] >> r1) & 1ull) << 63);
     open[r0 * 4 + 3] = (P0 & (P0 << 1)) | ((X[SIDE_W] >> r0) & 1ull);
     open[r1 * 4 + 3] = (P1 & (P1 << 1)) | ((X[SIDE_W] >> r1) & 1ull);
+    lab_syncwarp();
 
-    // the tile's crossings, listed; lane looks after slots 8*lane .. 8*lane+7 (side = lane / 8)
-    uint32_t const my_bits = static_cast<uint32_t>((X[lane >> 3] >> ((lane & 7) * 8)) & 0xFFull);
+    // which walkers exist: 16 masks of 64 positions (4 tile sides, then heading-major inner borders)
+    if (lane < 4) {
+        masks[lane] = X[lane];
+    }
+#pragma unroll
+    for (int b = 1; b <= 3; b++) {
+        // vertical inner border b: squares (pos, 16b-1) and (pos, 16b) both passable
+        uint64_t const v = lab_ballot64((open[lane * 4 + 1] >> (16 * b - 1)) & 1ull, (open[(lane + 32) * 4 + 1] >> (16 * b - 1)) & 1ull);
+        if (lane == 0) {
+            uint64_t const hmask = open[(16 * b - 1) * 4 + 2]; // horizontal inner border b
+            masks[4 + 0 * 3 + (b - 1)] = hmask; // heading N
+            masks[4 + 1 * 3 + (b - 1)] = v;     // heading E
+            masks[4 + 2 * 3 + (b - 1)] = hmask; // heading S
+            masks[4 + 3 * 3 + (b - 1)] = v;     // heading W
+        }
+    }
+    lab_syncwarp();
+    uint32_t const my_bits = static_cast<uint32_t>(masks[lane >> 1] >> (32 * (lane & 1)));
     uint32_t const mine = static_cast<uint32_t>(lab_popc64(my_bits));
     uint32_t incl = mine;
 #pragma unroll
@@ -145,12 +178,8 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
         while (m) {
             int const b = lab_ffs64(m) - 1;
             m &= m - 1;
-            list[q++] = static_cast<uint8_t>(8 * lane + b);
+            list[q++] = static_cast<uint16_t>(32 * lane + b);
         }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        res[lane + 32 * k] = END;
     }
     if (lane == 0) {
         *cnt = 0;
@@ -172,75 +201,112 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
             }
         }
     }
+    // ---- phase A: every walker to the first block border ----------------------------------------
+    // One flat loop, one step per iteration: a lane whose walker has arrived fetches its next one in
+    // the same iteration, so the lanes of the warp stay converged whatever the lengths of their pieces.
     uint32_t const nitems = total + (root_tile ? 1u : 0u);
+    bool have = false, skip = false;
+    int r = 0, c = 0, h = 0;
+    uint32_t id = 0, steps = 0;
     for (;;) {
-        uint32_t const idx = lab_atomic_add(cnt, 1u);
-        if (idx >= nitems) {
-            break;
-        }
-        bool const rootw = idx == total;
-        int r, c, h;
-        uint32_t s = 0;
-        if (rootw) {
-            r = rr;
-            c = rc;
-            h = rh;
-        } else {
-            s = list[idx];
-            int const side = static_cast<int>(s >> 6), pos = static_cast<int>(s & 63u);
-            r = side == SIDE_N ? 0 : (side == SIDE_S ? TS - 1 : pos);
-            c = side == SIDE_W ? 0 : (side == SIDE_E ? TS - 1 : pos);
-            h = side == SIDE_N ? 2 : (side == SIDE_S ? 0 : (side == SIDE_W ? 1 : 3));
-        }
-        bool skip = rootw; // the root's own walker leaves the root state instead of ending there
-        uint32_t result = END;
-        uint32_t steps = 0;
-        for (;;) {
-            if (root_tile && !skip && r == rr && c == rc && h == rh && root_open) {
-                break; // the tour ends where it began
+        if (!have) {
+            uint32_t const idx = lab_atomic_add(cnt, 1u);
+            if (idx >= nitems) {
+                break;
             }
-            skip = false;
-            uint64_t const *o = open + r * 4;
-            uint32_t const nib = static_cast<uint32_t>((o[0] >> c) & 1ull) | (static_cast<uint32_t>((o[1] >> c) & 1ull) << 1)
-                                 | (static_cast<uint32_t>((o[2] >> c) & 1ull) << 2) | (static_cast<uint32_t>((o[3] >> c) & 1ull) << 3);
-            if (nib == 0) {
-                break; // a square on its own (only the root can be one)
+            have = true;
+            steps = 0;
+            skip = idx == total; // the root's own walker leaves the root state instead of ending there
+            if (skip) {
+                id = WALK_IDS - 1;
+                r = rr;
+                c = rc;
+                h = rh;
+            } else {
+                id = list[idx];
+                int const pos = static_cast<int>(id & 63u);
+                if (id < SLOTS) {
+                    int const side = static_cast<int>(id >> 6);
+                    r = side == SIDE_N ? 0 : (side == SIDE_S ? TS - 1 : pos);
+                    c = side == SIDE_W ? 0 : (side == SIDE_E ? TS - 1 : pos);
+                    h = side == SIDE_N ? 2 : (side == SIDE_S ? 0 : (side == SIDE_W ? 1 : 3));
+                } else {
+                    uint32_t const k = (id - SLOTS) >> 6; // h*3 + (b-1)
+                    h = static_cast<int>(k / 3u);
+                    int const line = 16 * (static_cast<int>(k % 3u) + 1);
+                    r = h == 2 ? line : (h == 0 ? line - 1 : pos);
+                    c = h == 1 ? line : (h == 3 ? line - 1 : pos);
+                }
             }
+        }
+        uint32_t result = WALK_END;
+        bool arrived = root_tile && !skip && r == rr && c == rc && h == rh && root_open; // the tour ends where it began
+        skip = false;
+        uint64_t const *o = open + r * 4;
+        uint32_t const nib = static_cast<uint32_t>((o[0] >> c) & 1ull) | (static_cast<uint32_t>((o[1] >> c) & 1ull) << 1)
+                             | (static_cast<uint32_t>((o[2] >> c) & 1ull) << 2) | (static_cast<uint32_t>((o[3] >> c) & 1ull) << 3);
+        arrived |= nib == 0; // a square on its own (only the root can be one)
+        if (!arrived) {
             uint32_t const rot = ((nib >> h) | (nib << (4 - h))) & 15u; // bit j: direction h + j
             int const j = (rot & 2u) ? 1 : ((rot & 1u) ? 0 : ((rot & 8u) ? 3 : 2));
             h = (h + j) & 3;
             int const nr = r + (h == 2) - (h == 0), nc = c + (h == 1) - (h == 3);
-            if ((nr | nc) & ~(TS - 1)) { // left the tile: the segment ends, the neighbour's begins
-                uint32_t nt, ns;
-                if (h == 0) {
-                    nt = t - static_cast<uint32_t>(g.tiles_x);
-                    ns = SIDE_S * TS + static_cast<uint32_t>(c);
-                } else if (h == 2) {
-                    nt = t + static_cast<uint32_t>(g.tiles_x);
-                    ns = SIDE_N * TS + static_cast<uint32_t>(c);
-                } else if (h == 1) {
-                    nt = t + 1u;
-                    ns = SIDE_W * TS + static_cast<uint32_t>(r);
-                } else {
-                    nt = t - 1u;
-                    ns = SIDE_E * TS + static_cast<uint32_t>(r);
-                }
-                result = nt * SLOTS + ns;
-                break;
+            if ((nr | nc) & ~(TS - 1)) { // left the tile: into the neighbour's slot
+                uint32_t const ns = h == 0 ? SIDE_S * TS + static_cast<uint32_t>(c)
+                                           : (h == 2 ? SIDE_N * TS + static_cast<uint32_t>(c)
+                                                     : (h == 1 ? SIDE_W * TS + static_cast<uint32_t>(r) : SIDE_E * TS + static_cast<uint32_t>(r)));
+                result = 1024u + ns;
+                arrived = true;
+            } else if (((r ^ nr) | (c ^ nc)) & 0x30) { // crossed a block border: the next piece starts here
+                int const line = (h == 1 ? nc : (h == 3 ? c : (h == 2 ? nr : r))) >> 4; // 1..3
+                result = SLOTS + static_cast<uint32_t>(h * 3 + line - 1) * 64u + static_cast<uint32_t>((h & 1) ? r : c);
+                arrived = true;
+            } else if (++steps > 4u * 16u * 16u + 8u) {
+                lab_atomic_max(&tr.tc->walk_error, 1u);
+                arrived = true;
             }
             r = nr;
             c = nc;
-            if (++steps > 4u * TS * TS + 8u) {
-                lab_atomic_max(&tr.tc->walk_error, 1u);
-                break;
+        }
+        if (arrived) {
+            res16[id] = static_cast<uint16_t>(result);
+            have = false;
+        }
+    }
+    lab_syncwarp();
+    // ---- phase B: from every tile crossing (and the root) piece by piece to the end of its segment ----
+    for (int k = 0; k < 9; k++) {
+        int const s = k < 8 ? lane + 32 * k : WALK_IDS - 1;
+        bool const active = k < 8 ? ((X[s >> 6] >> (s & 63)) & 1ull) != 0 : (root_tile && lane == 0);
+        uint32_t out = END;
+        if (active) {
+            uint32_t cur = static_cast<uint32_t>(s);
+            uint32_t v = WALK_END;
+            int hops = 0;
+            for (; hops <= WALK_IDS; hops++) {
+                v = res16[cur];
+                if (v >= 1024u) {
+                    break;
+                }
+                cur = v;
+            }
+            if (hops > WALK_IDS) {
+                lab_atomic_max(&tr.tc->walk_error, 2u);
+                v = WALK_END;
+            }
+            if (v != WALK_END) {
+                uint32_t const ns = v - 1024u, side = ns >> 6;
+                uint32_t const nt = side == SIDE_S ? t - static_cast<uint32_t>(g.tiles_x)
+                                                   : (side == SIDE_N ? t + static_cast<uint32_t>(g.tiles_x) : (side == SIDE_W ? t + 1u : t - 1u));
+                out = nt * SLOTS + ns;
             }
         }
-        if (rootw) {
-            tr.succ0[ROOT] = result;
-            tr.s[0][ROOT] = result;
+        if (k < 8) {
+            res32[s] = out; // (the list it overwrites was last read before the barrier above)
+        } else if (root_tile && lane == 0) {
+            tr.succ0[ROOT] = out;
+            tr.s[0][ROOT] = out;
             tr.r[0][ROOT] = 1u;
-        } else {
-            res[s] = result;
         }
     }
     lab_syncwarp();
@@ -248,14 +314,14 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int const s = lane + 32 * k;
-        uint32_t const v = res[s];
+        uint32_t const v = res32[s];
         bool const active = (X[s >> 6] >> (s & 63)) & 1ull;
         tr.succ0[o + s] = v;
         tr.s[0][o + s] = v;
         tr.r[0][o + s] = active ? 1u : 0u;
     }
     if (lane == 0 && total) {
-        lab_atomic_add(&tr.tc->n_arcs, total);
+        lab_atomic_add(&tr.tc->n_arcs, static_cast<uint32_t>(lab_popc64(X[0]) + lab_popc64(X[1]) + lab_popc64(X[2]) + lab_popc64(X[3])));
     }
 }
 
@@ -300,8 +366,9 @@ LAB_DEV void tree_rank_round_body(Tree const &tr, uint32_t round, long long gthr
         return;
     }
     uint32_t const END = tr.nslots + 1u;
-    uint32_t const *sin = tr.s[round & 1u], *rin = tr.r[round & 1u];
-    uint32_t *sout = tr.s[(round & 1u) ^ 1u], *rout = tr.r[(round & 1u) ^ 1u];
+    bool const odd = round & 1u;
+    uint32_t const *sin = odd ? tr.s[1] : tr.s[0], *rin = odd ? tr.r[1] : tr.r[0];
+    uint32_t *sout = odd ? tr.s[0] : tr.s[1], *rout = odd ? tr.r[0] : tr.r[1];
     long long const n = static_cast<long long>(tr.nslots) + 2;
     bool more = false;
     for (long long i = gthread; i < n; i += nthreads) {
@@ -317,7 +384,9 @@ LAB_DEV void tree_rank_round_body(Tree const &tr, uint32_t round, long long gthr
             more |= s2 != END;
         }
     }
-    if (more) {
+    // (thousands of warps storing to -- or reading past L1 from -- one address would serialise in L2:
+    // look before writing, through L1; a stale zero only costs a redundant store)
+    if (lab_any(more) && (gthread & 31) == 0 && lab_ld_ro(&tc->rank_more[round]) == 0u) {
         lab_st_volatile(&tc->rank_more[round], 1u);
     }
     if (gthread == 0) {
@@ -334,7 +403,7 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
         return;
     }
     uint32_t const END = tr.nslots + 1u;
-    uint32_t const *sfin = tr.s[tc->rank_buf], *rfin = tr.r[tc->rank_buf];
+    uint32_t const *sfin = tc->rank_buf ? tr.s[1] : tr.s[0], *rfin = tc->rank_buf ? tr.r[1] : tr.r[0];
     uint32_t bad = 0;
     for (long long t = gwarp; t < p.g.ntiles; t += nwarps) {
         long long const o = t * SLOTS;
@@ -531,8 +600,9 @@ LAB_DEV void tree_prefix_round_body(Tree const &tr, uint32_t round, long long gt
         return;
     }
     uint32_t const ROOT = tr.nslots;
-    uint32_t const *pin = tr.s[round & 1u], *vin = tr.r[round & 1u];
-    uint32_t *pout = tr.s[(round & 1u) ^ 1u], *vout = tr.r[(round & 1u) ^ 1u];
+    bool const odd = round & 1u;
+    uint32_t const *pin = odd ? tr.s[1] : tr.s[0], *vin = odd ? tr.r[1] : tr.r[0];
+    uint32_t *pout = odd ? tr.s[0] : tr.s[1], *vout = odd ? tr.r[0] : tr.r[1];
     long long const n = static_cast<long long>(tr.nslots) + 2;
     bool more = false;
     for (long long i = gthread; i < n; i += nthreads) {
@@ -548,7 +618,7 @@ LAB_DEV void tree_prefix_round_body(Tree const &tr, uint32_t round, long long gt
             more |= p2 != ROOT;
         }
     }
-    if (more) {
+    if (lab_any(more) && (gthread & 31) == 0 && lab_ld_ro(&tc->prefix_more[round]) == 0u) {
         lab_st_volatile(&tc->prefix_more[round], 1u);
     }
     if (gthread == 0) {
@@ -689,7 +759,7 @@ LAB_DEV void tree_final_body(Params const &p, Tree const &tr, int lane, uint64_t
     if (!tree_live(tc)) {
         return;
     }
-    uint32_t const *lvl = tr.r[tc->prefix_buf];
+    uint32_t const *lvl = tc->prefix_buf ? tr.r[1] : tr.r[0];
     Warp_stats ws;
     for (;;) {
         uint32_t t = 0;

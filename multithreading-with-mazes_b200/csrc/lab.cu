@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(128, 3) k_bfs_tiles(Params p) {
 // ---- spanning-tree pipeline (device/tree.cuh) ----
 __global__ void __launch_bounds__(256) k_tree_count(Params p, Tree tr) { tree_count_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void k_tree_init(Tree tr) { tree_init_body(tr); }
-__global__ void __launch_bounds__(256) k_tree_walk(Params p, Tree tr) {
-    __shared__ __align__(16) uint64_t sm[8][WALK_U64];
+__global__ void __launch_bounds__(128) k_tree_walk(Params p, Tree tr) {
+    __shared__ __align__(16) uint64_t sm[4][WALK_U64];
     tree_walk_body(p, tr, lane_id(), sm[threadIdx.x >> 5]);
 }
 __global__ void __launch_bounds__(256) k_tree_rank_round(Tree tr, uint32_t round) {
@@ -249,6 +249,8 @@ struct lab_grid {
     bool tree_alloc = false;
     Tree_ctl tree_last{};
     bool tree_tried = false;
+    cudaEvent_t tev[10]{}; // LAB_TREE_TIMING=1: per-phase events
+    bool tev_on = false;
 };
 
 namespace {
@@ -462,10 +464,20 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     }
     uint32_t const one = 1;
     CU(cudaMemcpyAsync(&tr.tc->ok, &one, sizeof one, cudaMemcpyHostToDevice, s));
+    h->tev_on = env_ll("LAB_TREE_TIMING", 0) != 0;
+    int tev_i = 0;
+    auto mark = [&]() {
+        if (h->tev_on) {
+            if (!h->tev[tev_i]) cudaEventCreate(&h->tev[tev_i]);
+            cudaEventRecord(h->tev[tev_i++], s);
+        }
+    };
+    mark();
     k_tree_init<<<1, 1, 0, s>>>(tr);
-    int const walk_blocks = std::min<long long>((h->g.ntiles + 7) / 8, static_cast<long long>(h->sm_count) * 8);
-    k_tree_walk<<<walk_blocks, 256, 0, s>>>(p, tr);
+    int const walk_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 8);
+    k_tree_walk<<<walk_blocks, 128, 0, s>>>(p, tr);
     TRACE("k_tree_walk", s);
+    mark();
     long long const nslots = static_cast<long long>(tr.nslots) + 2;
     int const slot_blocks = static_cast<int>(std::min<long long>((nslots + 255) / 256, static_cast<long long>(h->sm_count) * 16));
     int const rounds = ceil_log2(static_cast<unsigned long long>(nslots));
@@ -473,21 +485,28 @@ int run_tree(lab_grid *h, Run_desc const &d) {
         k_tree_rank_round<<<slot_blocks, 256, 0, s>>>(tr, static_cast<uint32_t>(r));
     }
     TRACE("k_tree_rank_round", s);
+    mark();
     k_tree_orient<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, tr);
     TRACE("k_tree_orient", s);
+    mark();
     int const fill_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 4);
     k_tree_local<<<fill_blocks, 128, 0, s>>>(p, tr);
     TRACE("k_tree_local", s);
+    mark();
     k_tree_parent<<<slot_blocks, 256, 0, s>>>(p, tr);
     TRACE("k_tree_parent", s);
+    mark();
     for (int r = 0; r < rounds; r++) {
         k_tree_prefix_round<<<slot_blocks, 256, 0, s>>>(tr, static_cast<uint32_t>(r));
     }
     TRACE("k_tree_prefix_round", s);
+    mark();
     k_tree_final<<<std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 3), 128, 0, s>>>(p, tr);
     TRACE("k_tree_final", s);
+    mark();
     k_tree_gate<<<1, 1, 0, s>>>(p, tr);
     TRACE("k_tree_gate", s);
+    mark();
     h->tree_tried = true; // finish_run reads the pipeline's control block back
     CU(cudaGetLastError());
     return LAB_OK;
@@ -519,6 +538,16 @@ int finish_run(lab_grid *h) {
         CU(cudaMemcpyAsync(&h->tree_last, h->tree.tc, sizeof(Tree_ctl), cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(s));
+    if (h->tree_tried && h->tev_on) {
+        static char const *const names[] = {"walk", "rank", "orient", "local", "parent", "prefix", "final", "gate"};
+        fprintf(stderr, "[lab tree]");
+        for (int i = 0; i < 8; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->tev[i], h->tev[i + 1]);
+            fprintf(stderr, " %s %.1fus", names[i], ms * 1000.f);
+        }
+        fprintf(stderr, "\n");
+    }
     lab_timing &t = h->timing;
     CU(cudaEventElapsedTime(&t.setup_ms, h->ev[EV_SETUP0], h->ev[EV_PACK0]));
     CU(cudaEventElapsedTime(&t.pack_ms, h->ev[EV_PACK0], h->ev[EV_SEARCH0]));
