@@ -14,14 +14,13 @@
 //             along the tour that starts at the root.
 //   3 orient  of the two directions of a crossing the one met first leads AWAY from the root.  Every
 //             tile-local component of the tree now knows the one crossing it is entered through.
-//   4 local   the bit-sliced tile engine (engine.cuh step_group) floods every tile from its entry
-//             crossings, all tiles at once, no tile waiting for another: local levels of the border
-//             squares.
+//   4 flood   every tile is flooded from its entry crossings, all tiles at once, no tile waiting for
+//             another (register bitboards as in engine.cuh, one warp per tile): every square gets
+//             component << 16 | local level, written to the dense field as whole rows.
 //   5 prefix  the components form a tree themselves (parent = the component on the other side of the
 //             entry crossing, edge weight = local level of that crossing + 1); pointer jumping sums
 //             the weights down from the root: the exact level of every entry crossing.
-//   6 final   the tile engine floods every tile once more from its entry crossings, now at their exact
-//             levels, and writes the dense level field.  Again all tiles are independent.
+//   6 fix-up  one streaming pass over the field: level of the component's entry + local level.
 //
 // Whether the maze IS a tree is checked, not assumed: passable squares V and adjacent passable pairs
 // E are counted (a tree has E == V-1), every crossing must lie on the root's tour and the local
@@ -41,11 +40,12 @@ struct Tree_ctl {
     uint32_t unreached;  // crossings that are not on the root's tour
     uint32_t bad_weight; // an entry crossing whose far side got no local level
     uint32_t walk_error; // a walker ran longer than any tile allows
-    uint32_t ticket[3];  // dynamic tile counters: walk, local, final
+    uint32_t ticket[3];  // dynamic tile counters: walk, flood
     uint32_t rank_buf, prefix_buf; // which ping-pong buffer holds the finished ranking / prefix
     uint32_t rank_more[40], prefix_more[40]; // round r left work for round r+1
-    uint32_t n_arcs;     // crossings in total (diagnostics)
+    uint32_t n_arcs;     // crossings in total = entries of Tree::alist
     uint32_t used;       // the tree pipeline produced the field (set by gate)
+    uint32_t barrier[2]; // grid barriers of the two multi-round kernels (rank, prefix)
 };
 
 struct Tree {
@@ -54,6 +54,7 @@ struct Tree {
     uint32_t *r[2];      // [nslots+2] ping-pong: segments to the end of the tour / level of the entry
     uint64_t *inmask;    // [ntiles][4]  crossings through which a tile's components are ENTERED
     uint32_t *loc;       // [nslots]     local level of border squares ([side][pos], like edges)
+    uint32_t *alist;     // [n_arcs]     the slots that ARE crossings (the pointer-jumping rounds only visit these)
     Tree_ctl *tc;
     uint32_t nslots;     // ntiles * SLOTS; ROOT = nslots, END = nslots + 1
 };
@@ -320,8 +321,30 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
         tr.s[0][o + s] = v;
         tr.r[0][o + s] = active ? 1u : 0u;
     }
-    if (lane == 0 && total) {
-        lab_atomic_add(&tr.tc->n_arcs, static_cast<uint32_t>(lab_popc64(X[0]) + lab_popc64(X[1]) + lab_popc64(X[2]) + lab_popc64(X[3])));
+    // the tile's crossings join the global list of arcs
+    uint32_t const xbits = static_cast<uint32_t>((X[lane >> 3] >> ((lane & 7) * 8)) & 0xFFull); // slots 8*lane .. 8*lane+7
+    uint32_t const xmine = static_cast<uint32_t>(lab_popc64(xbits));
+    uint32_t xincl = xmine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t const v = lab_shfl_up(xincl, d);
+        if (lane >= d) {
+            xincl += v;
+        }
+    }
+    uint32_t const xtotal = lab_shfl(xincl, 31);
+    uint32_t xbase = 0;
+    if (lane == 0 && xtotal) {
+        xbase = lab_atomic_add(&tr.tc->n_arcs, xtotal);
+    }
+    xbase = lab_shfl(xbase, 0);
+    {
+        uint32_t q = xbase + xincl - xmine, m = xbits;
+        while (m) {
+            int const b = lab_ffs64(m) - 1;
+            m &= m - 1;
+            tr.alist[q++] = static_cast<uint32_t>(o) + static_cast<uint32_t>(8 * lane + b);
+        }
     }
 }
 
@@ -360,27 +383,31 @@ LAB_DEV void tree_init_body(Tree const &tr) {
 // 2 rank.  One round of pointer jumping: r = segments from here to the end of the tour.
 // Round `round` reads buffer round&1 and writes the other one; a round that finds the previous one
 // left nothing to do returns at once (the launches are fixed in number, the work is not).
+// Only crossings (Tree::alist) and the root are visited.  The same body runs as one launch per round
+// (tests/simt) or inside one persistent launch with a grid barrier between rounds (csrc/lab.cu), hence
+// the loads that bypass L1: the other buffer was written by other SMs a moment ago.
 LAB_DEV void tree_rank_round_body(Tree const &tr, uint32_t round, long long gthread, long long nthreads) {
     Tree_ctl *tc = tr.tc;
-    if (!tree_live(tc) || (round > 0 && tc->rank_more[round - 1] == 0)) {
+    if (!tree_live(tc) || (round > 0 && lab_ld_volatile(&tc->rank_more[round - 1]) == 0)) {
         return;
     }
-    uint32_t const END = tr.nslots + 1u;
+    uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
     bool const odd = round & 1u;
     uint32_t const *sin = odd ? tr.s[1] : tr.s[0], *rin = odd ? tr.r[1] : tr.r[0];
     uint32_t *sout = odd ? tr.s[0] : tr.s[1], *rout = odd ? tr.r[0] : tr.r[1];
-    long long const n = static_cast<long long>(tr.nslots) + 2;
+    long long const n = static_cast<long long>(tc->n_arcs) + 1;
     bool more = false;
     for (long long i = gthread; i < n; i += nthreads) {
-        uint32_t const s = sin[i];
-        uint32_t const r = rin[i];
+        uint32_t const a = i + 1 < n ? tr.alist[i] : ROOT;
+        uint32_t const s = lab_ld_cg(sin + a);
+        uint32_t const r = lab_ld_cg(rin + a);
         if (s == END) {
-            sout[i] = END;
-            rout[i] = r;
+            sout[a] = END;
+            rout[a] = r;
         } else {
-            uint32_t const s2 = sin[s];
-            sout[i] = s2;
-            rout[i] = r + rin[s];
+            uint32_t const s2 = lab_ld_cg(sin + s);
+            sout[a] = s2;
+            rout[a] = r + lab_ld_cg(rin + s);
             more |= s2 != END;
         }
     }
@@ -390,7 +417,7 @@ LAB_DEV void tree_rank_round_body(Tree const &tr, uint32_t round, long long gthr
         lab_st_volatile(&tc->rank_more[round], 1u);
     }
     if (gthread == 0) {
-        tc->rank_buf = (round & 1u) ^ 1u;
+        lab_st_volatile(&tc->rank_buf, (round & 1u) ^ 1u);
     }
 }
 
@@ -436,90 +463,199 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// emit_borders with the facing levels "never worth waking"
-LAB_DEV uint32_t tree_emit_borders(Tile_ctx const &tc, uint64_t *stage, Wave const &w, uint64_t S0, uint64_t S1, uint32_t base,
-                                   int lane, Emit_acc &acc, bool edges) {
-    if (edges) {
-        return emit_borders<true>(tc, stage, w, S0, S1, 0ull, 0ull, base, lane, 0u, 0u, 0u, 0u, 0u, 0u, acc);
-    }
-    return emit_borders<false>(tc, stage, w, S0, S1, 0ull, 0ull, base, lane, 0u, 0u, 0u, 0u, 0u, 0u, acc);
+// 4 flood.  Every tile flooded from its entry crossings (and the root), all its components at once,
+// one warp per tile.  lane i holds rows 2i, 2i+1 of the frontier in registers; a level is the same
+// shuffle + shift step as engine.cuh's, but what is recorded per square goes to a per-warp
+// shared-memory array instead of bit-sliced planes: every newly settled square looks up its PARENT
+// (the neighbour that was in the last frontier) and takes parent + 1.  The array holds
+//     component << 16 | local level      (component = the slot of its entry crossing, 256 = the root's)
+// so that once the entry crossings' exact levels are known (5 prefix) one streaming pass turns the
+// field into global levels (6 fix-up); nothing is flooded twice.  The tile is written to the dense
+// field as whole rows (walls = INF); the local levels of border squares go to tr.loc.
+constexpr int FLOOD_LIST = 1024;                       // squares one level may settle through the list
+constexpr int FLOOD_U64 = TS * TS / 2 + FLOOD_LIST / 4; // per warp: uint32[64][64] levels, uint16 cell list
+constexpr uint32_t ROOT_COMP = SLOTS;
+
+LAB_DEV void flood_note_border(Tree const &tr, uint32_t t, int r, int c, uint32_t ld) {
+    uint32_t *loc = tr.loc + static_cast<long long>(t) * SLOTS;
+    if (r == 0) loc[SIDE_N * TS + c] = ld;
+    if (r == TS - 1) loc[SIDE_S * TS + c] = ld;
+    if (c == 0) loc[SIDE_W * TS + r] = ld;
+    if (c == TS - 1) loc[SIDE_E * TS + r] = ld;
 }
 
-// 4 local.  Every tile flooded from its entry crossings (and the root) at local level 0; the local
-// levels of its border squares go to tr.loc.  stage: 7*64 uint64 per warp.
-constexpr int LOCAL_STAGE_U64 = 7 * TS;
+// One newly settled square x = row << 6 | col.  It has exactly one settled neighbour, its parent
+// (tree!), and every unsettled square reads as INF: parent = the minimum over the four neighbours.
+LAB_DEV void flood_settle(Tree const &tr, uint32_t t, uint32_t *L, int x) {
+    int const r = x >> 6, c = x & 63;
+    uint32_t const vw = c > 0 ? L[x - 1] : INF, ve = c < TS - 1 ? L[x + 1] : INF;
+    uint32_t const vn = r > 0 ? L[x - TS] : INF, vs = r < TS - 1 ? L[x + TS] : INF;
+    uint32_t const v = lab_umin(lab_umin(vw, ve), lab_umin(vn, vs)) + 1u;
+    L[x] = v;
+    if (((r + 1) & (TS - 1)) < 2 || ((c + 1) & (TS - 1)) < 2) {
+        flood_note_border(tr, t, r, c, v & 0xFFFFu);
+    }
+}
 
-LAB_DEV void local_fill_tile(Params const &p, Tree const &tr, uint32_t t, int lane, uint64_t *stage, uint32_t &settled) {
+LAB_DEV void flood_tile(Params const &p, Tree const &tr, uint32_t t, int lane, uint64_t *sm, Warp_stats &ws) {
+    Geom const &g = p.g;
+    uint32_t *L = reinterpret_cast<uint32_t *>(sm);
+    uint16_t *cells = reinterpret_cast<uint16_t *>(sm + TS * TS / 2);
     int const r0 = 2 * lane, r1 = 2 * lane + 1;
+    int const ty = static_cast<int>(t / static_cast<uint32_t>(g.tiles_x)), tx = static_cast<int>(t % static_cast<uint32_t>(g.tiles_x));
     uint64_t const inN = tr.inmask[static_cast<long long>(t) * 4 + SIDE_N], inS = tr.inmask[static_cast<long long>(t) * 4 + SIDE_S];
     uint64_t const inW = tr.inmask[static_cast<long long>(t) * 4 + SIDE_W], inE = tr.inmask[static_cast<long long>(t) * 4 + SIDE_E];
-    Seeds sd;
-    sd.src0 = 0;
-    sd.src1 = 0;
-    if (p.ctl->src_tile[0] == t) {
-        uint32_t const rc = p.ctl->src_rc[0];
-        int const sr = static_cast<int>(rc >> 8), sc = static_cast<int>(rc & 0xFF);
-        if (sr == r0) sd.src0 = 1ull << sc;
-        if (sr == r1) sd.src1 = 1ull << sc;
-    }
-    bool const has_src = lab_any((sd.src0 | sd.src1) != 0);
-    if (!(inN | inS | inW | inE) && !has_src) {
-        return; // nothing enters this tile
-    }
-    Wave w;
-    w.A0 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + r0);
-    w.A1 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + r1);
-    w.F0 = 0;
-    w.F1 = 0;
-    sd.rW0 = ((inW >> r0) & 1ull) ? 0u : INF;
-    sd.rW1 = ((inW >> r1) & 1ull) ? 0u : INF;
-    sd.rE0 = ((inE >> r0) & 1ull) ? 0u : INF;
-    sd.rE1 = ((inE >> r1) & 1ull) ? 0u : INF;
-    sd.rSrc = has_src ? 0u : INF;
-    sd.nsv = lane == 0 ? inN : (lane == 31 ? inS : 0ull);
-#pragma unroll
-    for (int b = 0; b < 6; b++) {
-        sd.nsp[b] = 0;
-    }
-    Tile_ctx tc;
-    tc.cols = 0;
-    tc.dist0 = nullptr;
-    tc.edges = tr.loc + static_cast<long long>(t) * SLOTS;
-    Emit_acc acc{0u, 0u, 0u, 0u};
-    uint32_t base = 0;
-    bool first = true;
-    for (;;) {
-#pragma unroll
-        for (int b = 0; b < 6; b++) {
-            w.B0[b] = 0;
-            w.B1[b] = 0;
+    uint64_t const P0 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + r0), P1 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + r1);
+    // everything a wall until settled
+    {
+        struct alignas(16) Quad {
+            uint32_t a, b, c, d;
+        };
+        Quad const inf4 = {INF, INF, INF, INF};
+        Quad *L4 = reinterpret_cast<Quad *>(L);
+#pragma unroll 8
+        for (int k = 0; k < TS * TS / 4 / 32; k++) {
+            L4[lane + 32 * k] = inf4;
         }
-        uint64_t const A0s = w.A0, A1s = w.A1;
-        bool moving = true;
-        for (int gi = 0; gi < WINDOW / 8 && moving; gi++) {
-            if (first && gi == 0) {
-                step_group<true, true>(w, sd, 0, lane);
-            } else {
-                step_group<false, false>(w, sd, gi, lane);
+    }
+    lab_syncwarp();
+    // seeds: local level 0, component = the entry's slot
+    uint64_t F0 = 0, F1 = 0;
+    {
+        uint64_t const w0 = (inW >> r0) & 1ull, w1 = (inW >> r1) & 1ull, e0 = (inE >> r0) & 1ull, e1 = (inE >> r1) & 1ull;
+        F0 = w0 | (e0 << 63) | (lane == 0 ? inN : 0ull);
+        F1 = w1 | (e1 << 63) | (lane == 31 ? inS : 0ull);
+        if (w0) L[r0 * TS] = (SIDE_W * TS + static_cast<uint32_t>(r0)) << 16;
+        if (w1) L[r1 * TS] = (SIDE_W * TS + static_cast<uint32_t>(r1)) << 16;
+        if (e0) L[r0 * TS + TS - 1] = (SIDE_E * TS + static_cast<uint32_t>(r0)) << 16;
+        if (e1) L[r1 * TS + TS - 1] = (SIDE_E * TS + static_cast<uint32_t>(r1)) << 16;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            int const c = lane + 32 * half;
+            if ((inN >> c) & 1ull) L[c] = (SIDE_N * TS + static_cast<uint32_t>(c)) << 16;
+            if ((inS >> c) & 1ull) L[(TS - 1) * TS + c] = (SIDE_S * TS + static_cast<uint32_t>(c)) << 16;
+        }
+        if (p.ctl->src_tile[0] == t) {
+            uint32_t const rc = p.ctl->src_rc[0];
+            int const sr = static_cast<int>(rc >> 8), sc = static_cast<int>(rc & 0xFF);
+            if (sr == r0) F0 |= 1ull << sc;
+            if (sr == r1) F1 |= 1ull << sc;
+            if (lane == 0) L[sr * TS + sc] = ROOT_COMP << 16;
+        }
+    }
+    F0 &= P0;
+    F1 &= P1;
+    ws.passes++;
+    if (!lab_any((F0 | F1) != 0)) {
+        ws.empty++; // nothing enters this tile: all walls as far as the tree is concerned
+    } else {
+        // the seeds' own border entries (a corner square lies on two sides)
+        {
+            uint64_t m = F0;
+            while (m) {
+                int const c = lab_ffs64(m) - 1;
+                m &= m - 1;
+                flood_note_border(tr, t, r0, c, 0u);
             }
-            moving = lab_any((w.F0 | w.F1) != 0);
+            m = F1;
+            while (m) {
+                int const c = lab_ffs64(m) - 1;
+                m &= m - 1;
+                flood_note_border(tr, t, r1, c, 0u);
+            }
         }
-        first = false;
-        tree_emit_borders(tc, stage, w, A0s & ~w.A0, A1s & ~w.A1, base, lane, acc, true);
+        uint64_t A0 = P0 & ~F0, A1 = P1 & ~F1;
+        uint32_t settled = static_cast<uint32_t>(lab_popc64(F0) + lab_popc64(F1));
         lab_syncwarp();
-        if (!moving) {
-            break;
+        for (;;) {
+            uint64_t up = lab_shfl_up64(F1, 1);     // row 2*lane-1
+            uint64_t down = lab_shfl_down64(F0, 1); // row 2*lane+2
+            if (lane == 0) up = 0;                  // (the out-of-range shuffles return the lane's own row)
+            if (lane == 31) down = 0;
+            uint64_t const N0 = ((F0 << 1) | (F0 >> 1) | F1 | up) & A0;
+            uint64_t const N1 = ((F1 << 1) | (F1 >> 1) | F0 | down) & A1;
+            if (!lab_any((N0 | N1) != 0)) {
+                break;
+            }
+            ws.levels++;
+            A0 &= ~N0;
+            A1 &= ~N1;
+            // the squares settled at this level, listed across the warp (a lane's own rows hold 0..2 of
+            // them; handled in place, most lanes would idle), then taken 32 at a time
+            uint32_t const mine = static_cast<uint32_t>(lab_popc64(N0) + lab_popc64(N1));
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t const v = lab_shfl_up(incl, d);
+                if (lane >= d) {
+                    incl += v;
+                }
+            }
+            uint32_t const total = lab_shfl(incl, 31);
+            settled += mine;
+            if (total <= static_cast<uint32_t>(FLOOD_LIST)) {
+                uint32_t q = incl - mine;
+                uint64_t m = N0;
+                while (m) {
+                    int const c = lab_ffs64(m) - 1;
+                    m &= m - 1;
+                    cells[q++] = static_cast<uint16_t>((r0 << 6) | c);
+                }
+                m = N1;
+                while (m) {
+                    int const c = lab_ffs64(m) - 1;
+                    m &= m - 1;
+                    cells[q++] = static_cast<uint16_t>((r1 << 6) | c);
+                }
+                lab_syncwarp();
+                for (q = static_cast<uint32_t>(lane); q < total; q += 32) {
+                    flood_settle(tr, t, L, cells[q]);
+                }
+            } else { // a frontier wider than the list (never seen on a maze): every lane its own rows
+                uint64_t m = N0;
+                while (m) {
+                    int const c = lab_ffs64(m) - 1;
+                    m &= m - 1;
+                    flood_settle(tr, t, L, (r0 << 6) | c);
+                }
+                m = N1;
+                while (m) {
+                    int const c = lab_ffs64(m) - 1;
+                    m &= m - 1;
+                    flood_settle(tr, t, L, (r1 << 6) | c);
+                }
+            }
+            lab_syncwarp();
+            F0 = N0;
+            F1 = N1;
         }
-        base += WINDOW;
+        ws.settled += settled;
+        lab_st_cg(p.plane[0].visited + static_cast<long long>(t) * TS + r0, P0 & ~A0);
+        lab_st_cg(p.plane[0].visited + static_cast<long long>(t) * TS + r1, P1 & ~A1);
     }
-    settled += acc.settled;
+    // the tile's rows into the dense field: lane writes columns lane and lane + 32 of every row
+    lab_syncwarp();
+    {
+        int const row0 = ty * TS, col0 = tx * TS;
+        int const rows_here = g.rows - row0 < TS ? g.rows - row0 : TS;
+        bool const lo = col0 + lane < g.cols, hi = col0 + lane + 32 < g.cols;
+        uint32_t *d = p.plane[0].dist + static_cast<long long>(row0) * g.cols + col0 + lane;
+#pragma unroll 4
+        for (int r = 0; r < rows_here; r++) {
+            uint32_t const a = L[r * TS + lane], b = L[r * TS + lane + 32];
+            if (lo) d[0] = a;
+            if (hi) d[32] = b;
+            d += g.cols;
+        }
+    }
+    lab_syncwarp();
 }
 
-LAB_DEV void tree_local_body(Params const &p, Tree const &tr, int lane, uint64_t *stage) {
+LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t *sm) {
     if (!tree_live(tr.tc)) {
         return;
     }
-    uint32_t settled = 0;
+    Warp_stats ws;
     for (;;) {
         uint32_t t = 0;
         if (lane == 0) {
@@ -529,11 +665,16 @@ LAB_DEV void tree_local_body(Params const &p, Tree const &tr, int lane, uint64_t
         if (t >= static_cast<uint32_t>(p.g.ntiles)) {
             break;
         }
-        local_fill_tile(p, tr, t, lane, stage, settled);
+        flood_tile(p, tr, t, lane, sm, ws);
     }
-    settled = lab_reduce_add(settled);
-    if (lane == 0 && settled) {
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&tr.tc->local_settled), static_cast<uint64_t>(settled));
+    uint32_t const settled = lab_reduce_add(ws.settled);
+    if (lane == 0) {
+        if (settled) {
+            lab_atomic_add(reinterpret_cast<uint64_t *>(&tr.tc->local_settled), static_cast<uint64_t>(settled));
+        }
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&p.ctl->n_activations), static_cast<uint64_t>(ws.passes));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&p.ctl->n_empty), static_cast<uint64_t>(ws.empty));
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&p.ctl->n_levels), static_cast<uint64_t>(ws.levels));
     }
 }
 
@@ -555,12 +696,13 @@ LAB_DEV void tree_parent_body(Params const &p, Tree const &tr, long long gthread
     }
     uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
     uint32_t *par = tr.s[0], *val = tr.r[0];
-    for (long long i = gthread; i < static_cast<long long>(tr.nslots) + 2; i += nthreads) {
+    long long const n = static_cast<long long>(tc->n_arcs) + 1;
+    for (long long i = gthread; i < n; i += nthreads) {
         uint32_t pa = ROOT, v = INF;
-        if (i == ROOT) {
+        uint32_t const e = i + 1 < n ? tr.alist[i] : ROOT;
+        if (e == ROOT) {
             v = 0;
-        } else if (i < tr.nslots) {
-            uint32_t const e = static_cast<uint32_t>(i);
+        } else {
             uint32_t const t = e / SLOTS, s = e % SLOTS;
             if ((tr.inmask[static_cast<long long>(t) * 4 + s / TS] >> (s % TS)) & 1ull) {
                 uint32_t const a = tree_twin(p.g, e);
@@ -571,7 +713,8 @@ LAB_DEV void tree_parent_body(Params const &p, Tree const &tr, long long gthread
                     v = lq + 1u;
                 }
                 uint32_t cur = a;
-                for (int guard = 0; guard <= static_cast<int>(SLOTS); guard++) {
+                int guard = 0;
+                for (; guard <= static_cast<int>(SLOTS); guard++) {
                     uint32_t const ct = cur / SLOTS, cs = cur % SLOTS;
                     if ((tr.inmask[static_cast<long long>(ct) * 4 + cs / TS] >> (cs % TS)) & 1ull) {
                         pa = cur;
@@ -583,38 +726,39 @@ LAB_DEV void tree_parent_body(Params const &p, Tree const &tr, long long gthread
                         break;
                     }
                     cur = tree_twin(p.g, nx);
-                    if (guard == static_cast<int>(SLOTS)) {
-                        lab_atomic_max(&tc->bad_weight, 2u);
-                    }
+                }
+                if (guard > static_cast<int>(SLOTS)) {
+                    lab_atomic_max(&tc->bad_weight, 2u);
                 }
             }
         }
-        par[i] = pa;
-        val[i] = v;
+        par[e] = pa;
+        val[e] = v;
     }
 }
 
 LAB_DEV void tree_prefix_round_body(Tree const &tr, uint32_t round, long long gthread, long long nthreads) {
     Tree_ctl *tc = tr.tc;
-    if (!tree_live(tc) || (round > 0 && tc->prefix_more[round - 1] == 0)) {
+    if (!tree_live(tc) || (round > 0 && lab_ld_volatile(&tc->prefix_more[round - 1]) == 0)) {
         return;
     }
     uint32_t const ROOT = tr.nslots;
     bool const odd = round & 1u;
     uint32_t const *pin = odd ? tr.s[1] : tr.s[0], *vin = odd ? tr.r[1] : tr.r[0];
     uint32_t *pout = odd ? tr.s[0] : tr.s[1], *vout = odd ? tr.r[0] : tr.r[1];
-    long long const n = static_cast<long long>(tr.nslots) + 2;
+    long long const n = static_cast<long long>(tc->n_arcs) + 1;
     bool more = false;
     for (long long i = gthread; i < n; i += nthreads) {
-        uint32_t const pa = pin[i];
-        uint32_t const v = vin[i];
+        uint32_t const a = i + 1 < n ? tr.alist[i] : ROOT;
+        uint32_t const pa = lab_ld_cg(pin + a);
+        uint32_t const v = lab_ld_cg(vin + a);
         if (pa == ROOT) {
-            pout[i] = ROOT;
-            vout[i] = v;
+            pout[a] = ROOT;
+            vout[a] = v;
         } else {
-            uint32_t const p2 = pin[pa];
-            pout[i] = p2;
-            vout[i] = v + vin[pa];
+            uint32_t const p2 = lab_ld_cg(pin + pa);
+            pout[a] = p2;
+            vout[a] = v + lab_ld_cg(vin + pa);
             more |= p2 != ROOT;
         }
     }
@@ -622,166 +766,73 @@ LAB_DEV void tree_prefix_round_body(Tree const &tr, uint32_t round, long long gt
         lab_st_volatile(&tc->prefix_more[round], 1u);
     }
     if (gthread == 0) {
-        tc->prefix_buf = (round & 1u) ^ 1u;
+        lab_st_volatile(&tc->prefix_buf, (round & 1u) ^ 1u);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// 6 final.  Every tile flooded from its entry crossings at their exact levels; dense field written.
-LAB_DEV void final_fill_tile(Params const &p, Tree const &tr, uint32_t const *lvl, uint32_t t, int lane, uint64_t *stage, Warp_stats &ws) {
-    Geom const &g = p.g;
-    Plane const &pl = p.plane[0];
-    int const ty = static_cast<int>(t / static_cast<uint32_t>(g.tiles_x)), tx = static_cast<int>(t % static_cast<uint32_t>(g.tiles_x));
-    int const r0 = 2 * lane, r1 = 2 * lane + 1;
-    uint32_t const *b = lvl + static_cast<long long>(t) * SLOTS;
-    uint32_t sN0 = b[SIDE_N * TS + lane], sN1 = b[SIDE_N * TS + lane + 32];
-    uint32_t sS0 = b[SIDE_S * TS + lane], sS1 = b[SIDE_S * TS + lane + 32];
-    uint32_t sW0 = b[SIDE_W * TS + r0], sW1 = b[SIDE_W * TS + r1];
-    uint32_t sE0 = b[SIDE_E * TS + r0], sE1 = b[SIDE_E * TS + r1];
-    Seeds sd;
-    sd.src0 = 0;
-    sd.src1 = 0;
-    if (p.ctl->src_tile[0] == t) {
-        uint32_t const rc = p.ctl->src_rc[0];
-        int const sr = static_cast<int>(rc >> 8), sc = static_cast<int>(rc & 0xFF);
-        if (sr == r0) sd.src0 = 1ull << sc;
-        if (sr == r1) sd.src1 = 1ull << sc;
-    }
-    uint32_t sSrc = (sd.src0 | sd.src1) ? 0u : INF;
-    uint32_t pending_min = lab_umin(lab_umin(lab_min3(sN0, sN1, sS0), lab_min3(sS1, sW0, sW1)), lab_min3(sE0, sE1, sSrc));
-    pending_min = lab_reduce_min(pending_min);
-    ws.passes++;
-    if (pending_min == INF) {
-        ws.empty++;
-        return;
-    }
-    Tile_ctx tc;
-    tc.cols = g.cols;
-    tc.edges = nullptr;
-    tc.dist0 = pl.dist + (static_cast<long long>(ty) * TS) * g.cols + static_cast<long long>(tx) * TS;
-    bool const any_ns = lab_any((sN0 & sN1 & sS0 & sS1) != INF);
-    Wave w;
-    w.A0 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + r0);
-    w.A1 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + r1);
-    uint64_t const P0 = w.A0, P1 = w.A1;
-    w.F0 = 0;
-    w.F1 = 0;
-    Emit_acc acc{0u, 0u, 0u, 0u};
-    uint32_t base = pending_min;
-    for (;;) { // one batch of up to WINDOW levels (cf. relax_tile)
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            w.B0[k] = 0;
-            w.B1[k] = 0;
-        }
-        uint64_t const A0s = w.A0, A1s = w.A1;
-        sd.rW0 = sW0 - base;
-        sd.rW1 = sW1 - base;
-        sd.rE0 = sE0 - base;
-        sd.rE1 = sE1 - base;
-        sd.rSrc = sSrc - base;
-        uint32_t grp = seed_group_bit(sW0, base) | seed_group_bit(sW1, base) | seed_group_bit(sE0, base) | seed_group_bit(sE1, base)
-                       | seed_group_bit(sSrc, base);
-        sd.nsv = 0;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            sd.nsp[k] = 0;
-        }
-        bool ns_window = false;
-        if (any_ns) {
-            uint32_t const rN0 = sN0 - base, rN1 = sN1 - base, rS0 = sS0 - base, rS1 = sS1 - base;
-            bool const vN0 = rN0 < WINDOW, vN1 = rN1 < WINDOW, vS0 = rS0 < WINDOW, vS1 = rS1 < WINDOW;
-            uint64_t const wn = lab_ballot64(vN0, vN1), wsb = lab_ballot64(vS0, vS1);
-            sd.nsv = lane == 0 ? wn : (lane == 31 ? wsb : 0ull);
-            if (wn | wsb) {
-                ns_window = true;
-                grp |= seed_group_bit(sN0, base) | seed_group_bit(sN1, base) | seed_group_bit(sS0, base) | seed_group_bit(sS1, base);
-#pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    uint64_t const pn = lab_ballot64(vN0 && ((rN0 >> k) & 1), vN1 && ((rN1 >> k) & 1));
-                    uint64_t const ps = lab_ballot64(vS0 && ((rS0 >> k) & 1), vS1 && ((rS1 >> k) & 1));
-                    sd.nsp[k] = lane == 0 ? pn : (lane == 31 ? ps : 0ull);
-                }
-            }
-        }
-        grp = lab_reduce_or(grp);
-        int gi = 0;
-        for (; gi < WINDOW / 8; gi++) {
-            if (!((grp >> gi) & 1u)) {
-                step_group<false, false>(w, sd, gi, lane);
-            } else if (ns_window) {
-                step_group<true, true>(w, sd, gi, lane);
-            } else {
-                step_group<true, false>(w, sd, gi, lane);
-            }
-            ws.levels += 8;
-            if (!lab_any((w.F0 | w.F1) != 0)) {
-                uint32_t const later = grp & ~((2u << gi) - 1u);
-                if (later == 0) {
-                    gi++;
-                    break;
-                }
-                gi = lab_ffs64(later) - 2;
-            }
-        }
-        uint64_t const S0 = A0s & ~w.A0, S1 = A1s & ~w.A1;
-        uint32_t const n_batch = tree_emit_borders(tc, stage, w, S0, S1, base, lane, acc, false);
-        emit_interior(tc, stage, S0, S1, base, lane, n_batch);
-        uint32_t const done_lvl = base + 8u * static_cast<uint32_t>(gi) - 1u;
-        sN0 = seed_after(sN0, done_lvl);
-        sN1 = seed_after(sN1, done_lvl);
-        sS0 = seed_after(sS0, done_lvl);
-        sS1 = seed_after(sS1, done_lvl);
-        sW0 = seed_after(sW0, done_lvl);
-        sW1 = seed_after(sW1, done_lvl);
-        sE0 = seed_after(sE0, done_lvl);
-        sE1 = seed_after(sE1, done_lvl);
-        sSrc = seed_after(sSrc, done_lvl);
-        if (lab_any((w.F0 | w.F1) != 0)) {
-            base = done_lvl + 1;
-        } else {
-            pending_min = lab_umin(lab_umin(lab_min3(sN0, sN1, sS0), lab_min3(sS1, sW0, sW1)), lab_min3(sE0, sE1, sSrc));
-            pending_min = lab_reduce_min(pending_min);
-            if (pending_min == INF) {
-                break;
-            }
-            base = pending_min;
-        }
-    }
-    lab_st_cg(pl.visited + static_cast<long long>(t) * TS + r0, P0 & ~w.A0);
-    lab_st_cg(pl.visited + static_cast<long long>(t) * TS + r1, P1 & ~w.A1);
-    ws.settled += acc.settled;
-    ws.max_lvl = acc.max_lvl > ws.max_lvl ? acc.max_lvl : ws.max_lvl;
-}
-
-LAB_DEV void tree_final_body(Params const &p, Tree const &tr, int lane, uint64_t *stage) {
+// 6 fix-up.  component << 16 | local level  ->  level of the component's entry + local level.
+// One warp-item = 64 squares of one row inside one tile (so the entry levels it needs are one 1 KB
+// table); lane reads squares lane and lane + 32.
+LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, long long gwarp, long long nwarps, int lane) {
     Tree_ctl *tc = tr.tc;
     if (!tree_live(tc)) {
         return;
     }
+    Geom const &g = p.g;
     uint32_t const *lvl = tc->prefix_buf ? tr.r[1] : tr.r[0];
-    Warp_stats ws;
-    for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) {
-            t = lab_atomic_add(&tc->ticket[2], 1u);
+    uint32_t *dist = p.plane[0].dist;
+    uint32_t mx = 0;
+    // one warp-item = four tiles' worth of one row: eight independent loads per lane in flight
+    constexpr int U = 4;
+    long long const chunks = (g.tiles_x + U - 1) / U;
+    long long const items = static_cast<long long>(g.rows) * chunks;
+    for (long long it = gwarp; it < items; it += nwarps) {
+        int const r = static_cast<int>(it / chunks);
+        int const j0 = static_cast<int>(it % chunks) * U;
+        uint32_t *row = dist + static_cast<long long>(r) * g.cols;
+        long long const trow = static_cast<long long>(r / TS) * g.tiles_x;
+        uint32_t v[2 * U];
+#pragma unroll
+        for (int u = 0; u < 2 * U; u++) {
+            int const c = j0 * TS + lane + 32 * u;
+            v[u] = c < g.cols ? row[c] : INF;
         }
-        t = lab_shfl(t, 0);
-        if (t >= static_cast<uint32_t>(p.g.ntiles)) {
-            break;
+#pragma unroll
+        for (int u = 0; u < 2 * U; u++) {
+            if (v[u] != INF) {
+                uint32_t const comp = v[u] >> 16;
+                uint32_t const *b = lvl + (trow + j0 + u / 2) * SLOTS;
+                uint32_t const out = (comp == ROOT_COMP ? 0u : b[comp]) + (v[u] & 0xFFFFu);
+                row[j0 * TS + lane + 32 * u] = out;
+                mx = out > mx ? out : mx;
+            }
         }
-        final_fill_tile(p, tr, lvl, t, lane, stage, ws);
     }
-    flush_stats(p.ctl, ws, lane);
+    mx = lab_reduce_max(mx);
+    if (lane == 0 && mx) {
+        lab_atomic_max(&p.ctl->max_level, mx);
+    }
 }
 
-// One thread, after the final flood: if the tree pipeline made the field, take the targets' levels
-// (the solvers' bounds and paint rules come from them) and call the wave off; otherwise leave the
-// control block as init_run_body armed it and the tile wave runs as if nothing had happened.
-LAB_DEV void tree_gate_body(Params const &p, Tree const &tr) {
+// After the fix-up.  If the tree pipeline made the field (thread 0): take the targets' levels (the
+// solvers' bounds and paint rules come from them) and call the wave off.  If it gave up after the
+// flood had already written its packed field: wipe field and visited masks, and the tile wave finds
+// everything as init_run_body armed it.
+LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, long long nthreads) {
     Tree_ctl *tc = tr.tc;
     Control *ctl = p.ctl;
     if (!tree_live(tc)) {
+        long long const cells = static_cast<long long>(p.g.rows) * p.g.cols;
+        for (long long i = gthread; i < cells; i += nthreads) {
+            p.plane[0].dist[i] = INF;
+        }
+        for (long long i = gthread; i < static_cast<long long>(p.g.ntiles) * TS; i += nthreads) {
+            p.plane[0].visited[i] = 0;
+        }
+        return;
+    }
+    if (gthread != 0) {
         return;
     }
     for (uint32_t j = 0; j < ctl->n_targets; j++) {
@@ -796,6 +847,7 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr) {
     ctl->tail = 0;
     ctl->pending = 0;
     ctl->done = 1;
+    ctl->n_settled = tc->local_settled;
     tc->used = 1;
 }
 

@@ -56,28 +56,58 @@ __global__ void __launch_bounds__(128) k_tree_walk(Params p, Tree tr) {
     __shared__ __align__(16) uint64_t sm[4][WALK_U64];
     tree_walk_body(p, tr, lane_id(), sm[threadIdx.x >> 5]);
 }
-__global__ void __launch_bounds__(256) k_tree_rank_round(Tree tr, uint32_t round) {
-    tree_rank_round_body(tr, round, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
-                         static_cast<long long>(gridDim.x) * blockDim.x);
+// All blocks of a cooperative launch meet here (they are co-resident: cudaLaunchCooperativeKernel).
+// `target` counts the arrivals expected so far; the counter only ever grows.
+__device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<uint32_t volatile *>(counter) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+// Pointer jumping, all rounds in one persistent launch: a round costs a grid barrier, not a launch.
+__global__ void __launch_bounds__(512) k_tree_rank(Tree tr, uint32_t max_rounds) {
+    long long const gthread = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    uint32_t target = 0;
+    for (uint32_t round = 0; round < max_rounds; round++) {
+        tree_rank_round_body(tr, round, gthread, nthreads);
+        grid_barrier(&tr.tc->barrier[0], target);
+        if (*reinterpret_cast<uint32_t volatile *>(&tr.tc->rank_more[round]) == 0u) {
+            break;
+        }
+    }
+}
+__global__ void __launch_bounds__(512) k_tree_prefix(Tree tr, uint32_t max_rounds) {
+    long long const gthread = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    uint32_t target = 0;
+    for (uint32_t round = 0; round < max_rounds; round++) {
+        tree_prefix_round_body(tr, round, gthread, nthreads);
+        grid_barrier(&tr.tc->barrier[1], target);
+        if (*reinterpret_cast<uint32_t volatile *>(&tr.tc->prefix_more[round]) == 0u) {
+            break;
+        }
+    }
 }
 __global__ void __launch_bounds__(256) k_tree_orient(Params p, Tree tr) { tree_orient_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
-__global__ void __launch_bounds__(128, 4) k_tree_local(Params p, Tree tr) {
-    __shared__ __align__(16) uint64_t stage[4][LOCAL_STAGE_U64];
-    tree_local_body(p, tr, lane_id(), stage[threadIdx.x >> 5]);
+__global__ void __launch_bounds__(128) k_tree_flood(Params p, Tree tr) {
+    extern __shared__ __align__(16) uint64_t flood_sm[];
+    tree_flood_body(p, tr, lane_id(), flood_sm + static_cast<size_t>(threadIdx.x >> 5) * FLOOD_U64);
 }
 __global__ void __launch_bounds__(256) k_tree_parent(Params p, Tree tr) {
     tree_parent_body(p, tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
                      static_cast<long long>(gridDim.x) * blockDim.x);
 }
-__global__ void __launch_bounds__(256) k_tree_prefix_round(Tree tr, uint32_t round) {
-    tree_prefix_round_body(tr, round, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
-                           static_cast<long long>(gridDim.x) * blockDim.x);
+__global__ void __launch_bounds__(256) k_tree_fixup(Params p, Tree tr) { tree_fixup_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
+__global__ void __launch_bounds__(256) k_tree_gate(Params p, Tree tr) {
+    tree_gate_body(p, tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
 }
-__global__ void __launch_bounds__(128, 3) k_tree_final(Params p, Tree tr) {
-    __shared__ __align__(16) uint64_t stage[4][STAGE_U64];
-    tree_final_body(p, tr, lane_id(), stage[threadIdx.x >> 5]);
-}
-__global__ void k_tree_gate(Params p, Tree tr) { tree_gate_body(p, tr); }
 
 __global__ void __launch_bounds__(256) k_measure(Geom g, uint16_t *grid, uint64_t const *visited, Result *res) {
     measure_body(g, grid, visited, res, gwarp_id(), nwarps_total(), lane_id());
@@ -249,6 +279,8 @@ struct lab_grid {
     bool tree_alloc = false;
     Tree_ctl tree_last{};
     bool tree_tried = false;
+    int tree_coop_blocks = 0; // co-resident blocks of the multi-round kernels
+    int tree_flood_per_sm = 1;
     cudaEvent_t tev[10]{}; // LAB_TREE_TIMING=1: per-phase events
     bool tev_on = false;
 };
@@ -424,6 +456,16 @@ int ensure_tree(lab_grid *h) {
     CU(cudaMalloc(&tr.r[1], n));
     CU(cudaMalloc(&tr.inmask, nt * 4 * sizeof(uint64_t)));
     CU(cudaMalloc(&tr.loc, nt * SLOTS * sizeof(uint32_t)));
+    CU(cudaMalloc(&tr.alist, nt * SLOTS * sizeof(uint32_t)));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree_rank, 512, 0));
+    int per_sm2 = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_tree_prefix, 512, 0));
+    h->tree_coop_blocks = std::max(1, std::min(per_sm, per_sm2)) * h->sm_count;
+    size_t const flood_smem = 4 * FLOOD_U64 * sizeof(uint64_t);
+    CU(cudaFuncSetAttribute(k_tree_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(flood_smem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tree_flood_per_sm, k_tree_flood, 128, flood_smem));
+    h->tree_flood_per_sm = std::max(1, h->tree_flood_per_sm);
     CU(cudaMalloc(&tr.tc, sizeof(Tree_ctl)));
     h->tree_alloc = true;
     return LAB_OK;
@@ -480,31 +522,35 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     mark();
     long long const nslots = static_cast<long long>(tr.nslots) + 2;
     int const slot_blocks = static_cast<int>(std::min<long long>((nslots + 255) / 256, static_cast<long long>(h->sm_count) * 16));
-    int const rounds = ceil_log2(static_cast<unsigned long long>(nslots));
-    for (int r = 0; r < rounds; r++) {
-        k_tree_rank_round<<<slot_blocks, 256, 0, s>>>(tr, static_cast<uint32_t>(r));
+    uint32_t rounds = static_cast<uint32_t>(ceil_log2(static_cast<unsigned long long>(nslots)));
+    // few crossings: fewer blocks make a cheaper barrier (a 64x64 tile has ~64 crossings)
+    int const coop_blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(h->tree_coop_blocks, (static_cast<long long>(h->g.ntiles) * 64 + 1023) / 1024)));
+    {
+        void *args[] = {const_cast<Tree *>(&tr), &rounds};
+        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_rank), dim3(coop_blocks), dim3(512), args, 0, s));
     }
-    TRACE("k_tree_rank_round", s);
+    TRACE("k_tree_rank", s);
     mark();
     k_tree_orient<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, tr);
     TRACE("k_tree_orient", s);
     mark();
-    int const fill_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 4);
-    k_tree_local<<<fill_blocks, 128, 0, s>>>(p, tr);
-    TRACE("k_tree_local", s);
+    int const fill_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_flood_per_sm);
+    k_tree_flood<<<fill_blocks, 128, 4 * FLOOD_U64 * sizeof(uint64_t), s>>>(p, tr);
+    TRACE("k_tree_flood", s);
     mark();
     k_tree_parent<<<slot_blocks, 256, 0, s>>>(p, tr);
     TRACE("k_tree_parent", s);
     mark();
-    for (int r = 0; r < rounds; r++) {
-        k_tree_prefix_round<<<slot_blocks, 256, 0, s>>>(tr, static_cast<uint32_t>(r));
+    {
+        void *args[] = {const_cast<Tree *>(&tr), &rounds};
+        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_prefix), dim3(coop_blocks), dim3(512), args, 0, s));
     }
-    TRACE("k_tree_prefix_round", s);
+    TRACE("k_tree_prefix", s);
     mark();
-    k_tree_final<<<std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 3), 128, 0, s>>>(p, tr);
-    TRACE("k_tree_final", s);
+    k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, tr);
+    TRACE("k_tree_fixup", s);
     mark();
-    k_tree_gate<<<1, 1, 0, s>>>(p, tr);
+    k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, tr);
     TRACE("k_tree_gate", s);
     mark();
     h->tree_tried = true; // finish_run reads the pipeline's control block back
@@ -539,7 +585,7 @@ int finish_run(lab_grid *h) {
     }
     CU(cudaStreamSynchronize(s));
     if (h->tree_tried && h->tev_on) {
-        static char const *const names[] = {"walk", "rank", "orient", "local", "parent", "prefix", "final", "gate"};
+        static char const *const names[] = {"walk", "rank", "orient", "flood", "parent", "prefix", "fixup", "gate"};
         fprintf(stderr, "[lab tree]");
         for (int i = 0; i < 8; i++) {
             float ms = 0;
@@ -727,6 +773,7 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->tree.r[1]);
     cudaFree(h->tree.inmask);
     cudaFree(h->tree.loc);
+    cudaFree(h->tree.alist);
     cudaFree(h->tree.tc);
     for (auto &e : h->ev) {
         if (e) cudaEventDestroy(e);

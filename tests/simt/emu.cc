@@ -35,7 +35,7 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
     if (d.nplanes != 1 || d.src_r[0] < 0 || !g_tree_mode) return;
     size_t const nt = static_cast<size_t>(w.g.ntiles);
     size_t const n = nt * SLOTS + 2;
-    std::vector<uint32_t> succ0(n), s0(n), s1(n), r0(n), r1(n), loc(nt * SLOTS);
+    std::vector<uint32_t> succ0(n), s0(n), s1(n), r0(n), r1(n), loc(nt * SLOTS), alist(nt * SLOTS);
     std::vector<uint64_t> inmask(nt * 4);
     Tree_ctl tc{};
     Tree tr{};
@@ -46,6 +46,7 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
     tr.r[1] = r1.data();
     tr.inmask = inmask.data();
     tr.loc = loc.data();
+    tr.alist = alist.data();
     tr.tc = &tc;
     tr.nslots = static_cast<uint32_t>(nt * SLOTS);
     simt::launch(nwarps, [&](int wid, int lane) { tree_count_body(p, tr, wid, nwarps, lane); });
@@ -53,8 +54,9 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
     if (tc.V < 2 || tc.E + 1 != tc.V) return;
     tc.ok = 1;
     tree_init_body(tr);
-    std::vector<uint64_t> sm(static_cast<size_t>(nwarps) * STAGE_U64);
-    simt::launch(nwarps, [&](int wid, int lane) { tree_walk_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * STAGE_U64); }, sched_seed);
+    size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
+    std::vector<uint64_t> sm(static_cast<size_t>(nwarps) * SM);
+    simt::launch(nwarps, [&](int wid, int lane) { tree_walk_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * SM); }, sched_seed);
     long long const nthreads = static_cast<long long>(nwarps) * 32;
     int rounds = 0;
     while ((1ull << rounds) < n) rounds++;
@@ -62,13 +64,13 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
         simt::launch(nwarps, [&](int wid, int lane) { tree_rank_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
     }
     simt::launch(nwarps, [&](int wid, int lane) { tree_orient_body(p, tr, wid, nwarps, lane); });
-    simt::launch(nwarps, [&](int wid, int lane) { tree_local_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * STAGE_U64); }, sched_seed);
+    simt::launch(nwarps, [&](int wid, int lane) { tree_flood_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * SM); }, sched_seed);
     simt::launch(nwarps, [&](int wid, int lane) { tree_parent_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
     for (int r = 0; r < rounds; r++) {
         simt::launch(nwarps, [&](int wid, int lane) { tree_prefix_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
     }
-    simt::launch(nwarps, [&](int wid, int lane) { tree_final_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * STAGE_U64); }, sched_seed);
-    tree_gate_body(p, tr);
+    simt::launch(nwarps, [&](int wid, int lane) { tree_fixup_body(p, tr, wid, nwarps, lane); });
+    simt::launch(nwarps, [&](int wid, int lane) { tree_gate_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
     g_tree_last = tc;
 }
 
