@@ -28,6 +28,7 @@ LAB_DEV void lab_syncwarp() { __syncwarp(); }
 
 LAB_DEV int lab_ffs64(uint64_t v) { return __ffsll(static_cast<long long>(v)); } // 1-based, 0 if none
 LAB_DEV int lab_popc64(uint64_t v) { return __popcll(v); }
+LAB_DEV int lab_ffs32(uint32_t v) { return __ffs(static_cast<int>(v)); } // 1-based, 0 if none
 
 // loads that must observe other SMs' stores (L1 is not coherent inside a persistent kernel)
 LAB_DEV uint32_t lab_ld_cg(uint32_t const *p) { return __ldcg(p); }

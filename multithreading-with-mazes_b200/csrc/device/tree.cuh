@@ -14,9 +14,9 @@
 //             along the tour that starts at the root.
 //   3 orient  of the two directions of a crossing the one met first leads AWAY from the root.  Every
 //             tile-local component of the tree now knows the one crossing it is entered through.
-//   4 flood   every tile is flooded from its entry crossings, all tiles at once, no tile waiting for
-//             another (register bitboards as in engine.cuh, one warp per tile): every square gets
-//             component << 16 | local level, written to the dense field as whole rows.
+//   4 flood   every tile's components are traversed from their entry crossings, all tiles at once, no
+//             tile waiting for another: every square gets component << 16 | local level (its parent's
+//             value + 1; junctions hand their other branches to idle lanes).
 //   5 prefix  the components form a tree themselves (parent = the component on the other side of the
 //             entry crossing, edge weight = local level of that crossing + 1); pointer jumping sums
 //             the weights down from the root: the exact level of every entry crossing.
@@ -97,6 +97,48 @@ LAB_DEV void tree_count_body(Params const &p, Tree const &tr, long long gwarp, l
 }
 
 // ---------------------------------------------------------------------------------------------
+// A tile as a byte per square, in shared memory: bits 0-3 = the neighbour to the N, E, S, W is
+// passable and inside the tile, bits 4-7 = ... is passable and across the tile's border (an open
+// crossing).  One look-up per step for the walkers below.  Lane i brings rows 2i, 2i+1.
+LAB_DEV uint32_t spread4(uint32_t bits) { // bits 0..3 -> bit 0 of bytes 0..3
+    return ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
+}
+LAB_DEV void tile_open_row(uint8_t *O, int r, uint64_t n, uint64_t e, uint64_t s, uint64_t w) {
+    uint32_t *out = reinterpret_cast<uint32_t *>(O + r * TS);
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        uint32_t const n32 = static_cast<uint32_t>(n >> (32 * half)), e32 = static_cast<uint32_t>(e >> (32 * half));
+        uint32_t const s32 = static_cast<uint32_t>(s >> (32 * half)), w32 = static_cast<uint32_t>(w >> (32 * half));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            out[half * 8 + k] = spread4(n32 >> (4 * k)) | (spread4(e32 >> (4 * k)) << 1) | (spread4(s32 >> (4 * k)) << 2) | (spread4(w32 >> (4 * k)) << 3);
+        }
+    }
+}
+LAB_DEV void tile_open_table(uint8_t *O, uint64_t P0, uint64_t P1, uint64_t const (&X)[4], int lane) {
+    int const r0 = 2 * lane, r1 = 2 * lane + 1;
+    uint64_t const up = lab_shfl_up64(P1, 1), down = lab_shfl_down64(P0, 1);
+    tile_open_row(O, r0, lane == 0 ? 0ull : (P0 & up), P0 & (P0 >> 1), P0 & P1, P0 & (P0 << 1));
+    tile_open_row(O, r1, P1 & P0, P1 & (P1 >> 1), lane == 31 ? 0ull : (P1 & down), P1 & (P1 << 1));
+    lab_syncwarp();
+    // the open crossings: lane looks after columns / rows lane and lane + 32 of each side
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        int const q = lane + 32 * half;
+        if ((X[SIDE_N] >> q) & 1ull) O[q] |= 0x10;
+        if ((X[SIDE_S] >> q) & 1ull) O[(TS - 1) * TS + q] |= 0x40;
+    }
+    lab_syncwarp(); // (a corner square belongs to two sides)
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        int const q = lane + 32 * half;
+        if ((X[SIDE_E] >> q) & 1ull) O[q * TS + TS - 1] |= 0x20;
+        if ((X[SIDE_W] >> q) & 1ull) O[q * TS] |= 0x80;
+    }
+    lab_syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // 1 walk.  Directions clockwise: N=0, E=1, S=2, W=3.  A walker's state is (square, heading it
 // arrived with); it takes the first open direction among right, straight, left, back.  On a tree
 // that visits every arc exactly once, i.e. it is the Euler tour.
@@ -113,19 +155,20 @@ LAB_DEV void tree_count_body(Params const &p, Tree const &tr, long long gwarp, l
 // piece results (uint16): < 1024 the next piece; 1024 + s: leaves the tile into the neighbour's slot s;
 // 0xFFFF: the end of the tour.
 //
-// shared memory per warp (uint64 units): open[64][4] | res16[1032] | list16[1032] (later res32[256]) | masks[16] | counter
+// shared memory per warp (uint64 units): byte table[4096] | res16[1032] | list16[1032] (later res32[256]) | masks[16] | counter
 constexpr int WALK_IDS = 1025;
-constexpr int WALK_U64 = 4 * TS + 260 + 260 + 16 + 2;
+constexpr int WALK_TAB = TS * TS / 8;
+constexpr int WALK_U64 = WALK_TAB + 260 + 260 + 16 + 2;
 constexpr uint32_t WALK_END = 0xFFFFu;
 
 LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, uint64_t *sm) {
     Geom const &g = p.g;
-    uint64_t *open = sm;
-    uint16_t *res16 = reinterpret_cast<uint16_t *>(sm + 4 * TS);
-    uint16_t *list = reinterpret_cast<uint16_t *>(sm + 4 * TS + 260);
-    uint32_t *res32 = reinterpret_cast<uint32_t *>(sm + 4 * TS + 260); // after phase A the list is dead
-    uint64_t *masks = sm + 4 * TS + 520;
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(sm + 4 * TS + 536);
+    uint8_t *O = reinterpret_cast<uint8_t *>(sm);
+    uint16_t *res16 = reinterpret_cast<uint16_t *>(sm + WALK_TAB);
+    uint16_t *list = reinterpret_cast<uint16_t *>(sm + WALK_TAB + 260);
+    uint32_t *res32 = reinterpret_cast<uint32_t *>(sm + WALK_TAB + 260); // after phase A the list is dead
+    uint64_t *masks = sm + WALK_TAB + 520;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(sm + WALK_TAB + 536);
     uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
     int const r0 = 2 * lane, r1 = 2 * lane + 1;
 
@@ -135,16 +178,7 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
     for (int s = 0; s < 4; s++) {
         X[s] = lab_ld_ro(p.cross + static_cast<long long>(t) * 4 + s);
     }
-    uint64_t const up = lab_shfl_up64(P1, 1), down = lab_shfl_down64(P0, 1);
-    open[r0 * 4 + 0] = lane == 0 ? X[SIDE_N] : (P0 & up);
-    open[r1 * 4 + 0] = P1 & P0;
-    open[r0 * 4 + 2] = P0 & P1;
-    open[r1 * 4 + 2] = lane == 31 ? X[SIDE_S] : (P1 & down);
-    open[r0 * 4 + 1] = (P0 & (P0 >> 1)) | (((X[SIDE_E] >> r0) & 1ull) << 63);
-    open[r1 * 4 + 1] = (P1 & (P1 >> 1)) | (((X[SIDE_E] >> r1) & 1ull) << 63);
-    open[r0 * 4 + 3] = (P0 & (P0 << 1)) | ((X[SIDE_W] >> r0) & 1ull);
-    open[r1 * 4 + 3] = (P1 & (P1 << 1)) | ((X[SIDE_W] >> r1) & 1ull);
-    lab_syncwarp();
+    tile_open_table(O, P0, P1, X, lane);
 
     // which walkers exist: 16 masks of 64 positions (4 tile sides, then heading-major inner borders)
     if (lane < 4) {
@@ -153,9 +187,10 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
 #pragma unroll
     for (int b = 1; b <= 3; b++) {
         // vertical inner border b: squares (pos, 16b-1) and (pos, 16b) both passable
-        uint64_t const v = lab_ballot64((open[lane * 4 + 1] >> (16 * b - 1)) & 1ull, (open[(lane + 32) * 4 + 1] >> (16 * b - 1)) & 1ull);
+        uint64_t const v = lab_ballot64((O[lane * TS + 16 * b - 1] >> 1) & 1, (O[(lane + 32) * TS + 16 * b - 1] >> 1) & 1);
+        // horizontal inner border b: squares (16b-1, pos) and (16b, pos)
+        uint64_t const hmask = lab_ballot64((O[(16 * b - 1) * TS + lane] >> 2) & 1, (O[(16 * b - 1) * TS + lane + 32] >> 2) & 1);
         if (lane == 0) {
-            uint64_t const hmask = open[(16 * b - 1) * 4 + 2]; // horizontal inner border b
             masks[4 + 0 * 3 + (b - 1)] = hmask; // heading N
             masks[4 + 1 * 3 + (b - 1)] = v;     // heading E
             masks[4 + 2 * 3 + (b - 1)] = hmask; // heading S
@@ -195,8 +230,9 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
         uint32_t const rcv = p.ctl->src_rc[0];
         rr = static_cast<int>(rcv >> 8);
         rc = static_cast<int>(rcv & 0xFF);
+        uint32_t const b = O[rr * TS + rc];
         for (int d = 3; d >= 0; d--) {
-            if ((open[rr * 4 + d] >> rc) & 1ull) {
+            if (((b | (b >> 4)) >> d) & 1u) {
                 rh = (d + 2) & 3;
                 root_open = true;
             }
@@ -243,16 +279,15 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
         uint32_t result = WALK_END;
         bool arrived = root_tile && !skip && r == rr && c == rc && h == rh && root_open; // the tour ends where it began
         skip = false;
-        uint64_t const *o = open + r * 4;
-        uint32_t const nib = static_cast<uint32_t>((o[0] >> c) & 1ull) | (static_cast<uint32_t>((o[1] >> c) & 1ull) << 1)
-                             | (static_cast<uint32_t>((o[2] >> c) & 1ull) << 2) | (static_cast<uint32_t>((o[3] >> c) & 1ull) << 3);
+        uint32_t const b = O[r * TS + c];
+        uint32_t const nib = (b | (b >> 4)) & 15u;
         arrived |= nib == 0; // a square on its own (only the root can be one)
         if (!arrived) {
             uint32_t const rot = ((nib >> h) | (nib << (4 - h))) & 15u; // bit j: direction h + j
-            int const j = (rot & 2u) ? 1 : ((rot & 1u) ? 0 : ((rot & 8u) ? 3 : 2));
+            int const j = static_cast<int>((0x53535252u >> (2 * (rot & 15u))) & 3u); // right, else straight, else left, else back
             h = (h + j) & 3;
             int const nr = r + (h == 2) - (h == 0), nc = c + (h == 1) - (h == 3);
-            if ((nr | nc) & ~(TS - 1)) { // left the tile: into the neighbour's slot
+            if ((b >> (4 + h)) & 1u) { // through an open crossing: into the neighbour's slot
                 uint32_t const ns = h == 0 ? SIDE_S * TS + static_cast<uint32_t>(c)
                                            : (h == 2 ? SIDE_N * TS + static_cast<uint32_t>(c)
                                                      : (h == 1 ? SIDE_W * TS + static_cast<uint32_t>(r) : SIDE_E * TS + static_cast<uint32_t>(r)));
@@ -430,7 +465,9 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
         return;
     }
     uint32_t const END = tr.nslots + 1u;
-    uint32_t const *sfin = tc->rank_buf ? tr.s[1] : tr.s[0], *rfin = tc->rank_buf ? tr.r[1] : tr.r[0];
+    // (read past L1: in csrc/lab.cu this runs at the tail of the ranking kernel, whose other blocks wrote these)
+    bool const fin1 = lab_ld_volatile(&tc->rank_buf) != 0u;
+    uint32_t const *sfin = fin1 ? tr.s[1] : tr.s[0], *rfin = fin1 ? tr.r[1] : tr.r[0];
     uint32_t bad = 0;
     for (long long t = gwarp; t < p.g.ntiles; t += nwarps) {
         long long const o = t * SLOTS;
@@ -463,18 +500,24 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// 4 flood.  Every tile flooded from its entry crossings (and the root), all its components at once,
-// one warp per tile.  lane i holds rows 2i, 2i+1 of the frontier in registers; a level is the same
-// shuffle + shift step as engine.cuh's, but what is recorded per square goes to a per-warp
-// shared-memory array instead of bit-sliced planes: every newly settled square looks up its PARENT
-// (the neighbour that was in the last frontier) and takes parent + 1.  The array holds
-//     component << 16 | local level      (component = the slot of its entry crossing, 256 = the root's)
-// so that once the entry crossings' exact levels are known (5 prefix) one streaming pass turns the
-// field into global levels (6 fix-up); nothing is flooded twice.  The tile is written to the dense
-// field as whole rows (walls = INF); the local levels of border squares go to tr.loc.
-constexpr int FLOOD_LIST = 1024;                       // squares one level may settle through the list
-constexpr int FLOOD_U64 = TS * TS / 2 + FLOOD_LIST / 4; // per warp: uint32[64][64] levels, uint16 cell list
+// 4 flood.  Every component of every tile gets  component << 16 | local level  on each of its
+// squares (component = the slot of its entry crossing, 256 = the root's), all tiles at once, no tile
+// waiting for another.  On a tree that needs no wave either: a square's value is its parent's + 1,
+// so a component is a set of independent TASKS "square x holds v, came from direction b": a lane
+// follows its branch square by square (one look-up of the path rows, one store per square), and at
+// every junction pushes the other branches on the warp's shared-memory stack for idle lanes to pop.
+// No level synchronisation, no frontier, every lane busy as long as the stack holds work; a warp keeps
+// FLOOD_SLOTS tiles open at a time so that the tail of one tile overlaps the bulk of the next.
+// Once the entry crossings' exact levels are known (5 prefix) one streaming pass turns the packed
+// field into global levels (6 fix-up).  The local levels of border squares go to tr.loc.
+constexpr int FLOOD_SLOTS = 2;
+constexpr int FLOOD_STACK = 512; // tasks
+// per warp, uint64 units: byte tables of the open tiles | task stack | control words
+constexpr int FLOOD_TAB = TS * TS / 8; // one byte table (tile_open_table) per open tile
+constexpr int FLOOD_STEPS = 4;         // squares a lane advances between two looks at the stack
+constexpr int FLOOD_U64 = FLOOD_SLOTS * FLOOD_TAB + FLOOD_STACK + 2 + 2 * FLOOD_SLOTS;
 constexpr uint32_t ROOT_COMP = SLOTS;
+constexpr uint32_t NO_TILE = 0xFFFFFFFFu;
 
 LAB_DEV void flood_note_border(Tree const &tr, uint32_t t, int r, int c, uint32_t ld) {
     uint32_t *loc = tr.loc + static_cast<long long>(t) * SLOTS;
@@ -484,178 +527,28 @@ LAB_DEV void flood_note_border(Tree const &tr, uint32_t t, int r, int c, uint32_
     if (c == TS - 1) loc[SIDE_E * TS + r] = ld;
 }
 
-// One newly settled square x = row << 6 | col.  It has exactly one settled neighbour, its parent
-// (tree!), and every unsettled square reads as INF: parent = the minimum over the four neighbours.
-LAB_DEV void flood_settle(Tree const &tr, uint32_t t, uint32_t *L, int x) {
-    int const r = x >> 6, c = x & 63;
-    uint32_t const vw = c > 0 ? L[x - 1] : INF, ve = c < TS - 1 ? L[x + 1] : INF;
-    uint32_t const vn = r > 0 ? L[x - TS] : INF, vs = r < TS - 1 ? L[x + TS] : INF;
-    uint32_t const v = lab_umin(lab_umin(vw, ve), lab_umin(vn, vs)) + 1u;
-    L[x] = v;
-    if (((r + 1) & (TS - 1)) < 2 || ((c + 1) & (TS - 1)) < 2) {
-        flood_note_border(tr, t, r, c, v & 0xFFFFu);
-    }
-}
+struct Flood_sm {
+    uint8_t *O;           // [FLOOD_SLOTS][4096] tile_open_table
+    uint64_t *stack;      // [FLOOD_STACK]  v | (x | back << 12 | slot << 15) << 32
+    uint32_t *top;        // tasks on the stack
+    uint32_t *error;
+    uint32_t *live;       // [FLOOD_SLOTS] tasks of the slot's tile not finished yet (0 = slot free)
+    uint32_t *tile;       // [FLOOD_SLOTS]
+    uint64_t *origin;     // [FLOOD_SLOTS] index of the tile's first square in the dense field
+};
 
-LAB_DEV void flood_tile(Params const &p, Tree const &tr, uint32_t t, int lane, uint64_t *sm, Warp_stats &ws) {
-    Geom const &g = p.g;
-    uint32_t *L = reinterpret_cast<uint32_t *>(sm);
-    uint16_t *cells = reinterpret_cast<uint16_t *>(sm + TS * TS / 2);
-    int const r0 = 2 * lane, r1 = 2 * lane + 1;
-    int const ty = static_cast<int>(t / static_cast<uint32_t>(g.tiles_x)), tx = static_cast<int>(t % static_cast<uint32_t>(g.tiles_x));
-    uint64_t const inN = tr.inmask[static_cast<long long>(t) * 4 + SIDE_N], inS = tr.inmask[static_cast<long long>(t) * 4 + SIDE_S];
-    uint64_t const inW = tr.inmask[static_cast<long long>(t) * 4 + SIDE_W], inE = tr.inmask[static_cast<long long>(t) * 4 + SIDE_E];
-    uint64_t const P0 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + r0), P1 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + r1);
-    // everything a wall until settled
-    {
-        struct alignas(16) Quad {
-            uint32_t a, b, c, d;
-        };
-        Quad const inf4 = {INF, INF, INF, INF};
-        Quad *L4 = reinterpret_cast<Quad *>(L);
-#pragma unroll 8
-        for (int k = 0; k < TS * TS / 4 / 32; k++) {
-            L4[lane + 32 * k] = inf4;
-        }
-    }
-    lab_syncwarp();
-    // seeds: local level 0, component = the entry's slot
-    uint64_t F0 = 0, F1 = 0;
-    {
-        uint64_t const w0 = (inW >> r0) & 1ull, w1 = (inW >> r1) & 1ull, e0 = (inE >> r0) & 1ull, e1 = (inE >> r1) & 1ull;
-        F0 = w0 | (e0 << 63) | (lane == 0 ? inN : 0ull);
-        F1 = w1 | (e1 << 63) | (lane == 31 ? inS : 0ull);
-        if (w0) L[r0 * TS] = (SIDE_W * TS + static_cast<uint32_t>(r0)) << 16;
-        if (w1) L[r1 * TS] = (SIDE_W * TS + static_cast<uint32_t>(r1)) << 16;
-        if (e0) L[r0 * TS + TS - 1] = (SIDE_E * TS + static_cast<uint32_t>(r0)) << 16;
-        if (e1) L[r1 * TS + TS - 1] = (SIDE_E * TS + static_cast<uint32_t>(r1)) << 16;
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            int const c = lane + 32 * half;
-            if ((inN >> c) & 1ull) L[c] = (SIDE_N * TS + static_cast<uint32_t>(c)) << 16;
-            if ((inS >> c) & 1ull) L[(TS - 1) * TS + c] = (SIDE_S * TS + static_cast<uint32_t>(c)) << 16;
-        }
-        if (p.ctl->src_tile[0] == t) {
-            uint32_t const rc = p.ctl->src_rc[0];
-            int const sr = static_cast<int>(rc >> 8), sc = static_cast<int>(rc & 0xFF);
-            if (sr == r0) F0 |= 1ull << sc;
-            if (sr == r1) F1 |= 1ull << sc;
-            if (lane == 0) L[sr * TS + sc] = ROOT_COMP << 16;
-        }
-    }
-    F0 &= P0;
-    F1 &= P1;
-    ws.passes++;
-    if (!lab_any((F0 | F1) != 0)) {
-        ws.empty++; // nothing enters this tile: all walls as far as the tree is concerned
+LAB_DEV void flood_push(Flood_sm const &f, uint32_t v, uint32_t x, uint32_t back, uint32_t slot) {
+    uint32_t const pos = lab_atomic_add(f.top, 1u);
+    if (pos < static_cast<uint32_t>(FLOOD_STACK)) {
+        f.stack[pos] = static_cast<uint64_t>(v) | (static_cast<uint64_t>(x | (back << 12) | (slot << 15)) << 32);
     } else {
-        // the seeds' own border entries (a corner square lies on two sides)
-        {
-            uint64_t m = F0;
-            while (m) {
-                int const c = lab_ffs64(m) - 1;
-                m &= m - 1;
-                flood_note_border(tr, t, r0, c, 0u);
-            }
-            m = F1;
-            while (m) {
-                int const c = lab_ffs64(m) - 1;
-                m &= m - 1;
-                flood_note_border(tr, t, r1, c, 0u);
-            }
-        }
-        uint64_t A0 = P0 & ~F0, A1 = P1 & ~F1;
-        uint32_t settled = static_cast<uint32_t>(lab_popc64(F0) + lab_popc64(F1));
-        lab_syncwarp();
-        for (;;) {
-            uint64_t up = lab_shfl_up64(F1, 1);     // row 2*lane-1
-            uint64_t down = lab_shfl_down64(F0, 1); // row 2*lane+2
-            if (lane == 0) up = 0;                  // (the out-of-range shuffles return the lane's own row)
-            if (lane == 31) down = 0;
-            uint64_t const N0 = ((F0 << 1) | (F0 >> 1) | F1 | up) & A0;
-            uint64_t const N1 = ((F1 << 1) | (F1 >> 1) | F0 | down) & A1;
-            if (!lab_any((N0 | N1) != 0)) {
-                break;
-            }
-            ws.levels++;
-            A0 &= ~N0;
-            A1 &= ~N1;
-            // the squares settled at this level, listed across the warp (a lane's own rows hold 0..2 of
-            // them; handled in place, most lanes would idle), then taken 32 at a time
-            uint32_t const mine = static_cast<uint32_t>(lab_popc64(N0) + lab_popc64(N1));
-            uint32_t incl = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t const v = lab_shfl_up(incl, d);
-                if (lane >= d) {
-                    incl += v;
-                }
-            }
-            uint32_t const total = lab_shfl(incl, 31);
-            settled += mine;
-            if (total <= static_cast<uint32_t>(FLOOD_LIST)) {
-                uint32_t q = incl - mine;
-                uint64_t m = N0;
-                while (m) {
-                    int const c = lab_ffs64(m) - 1;
-                    m &= m - 1;
-                    cells[q++] = static_cast<uint16_t>((r0 << 6) | c);
-                }
-                m = N1;
-                while (m) {
-                    int const c = lab_ffs64(m) - 1;
-                    m &= m - 1;
-                    cells[q++] = static_cast<uint16_t>((r1 << 6) | c);
-                }
-                lab_syncwarp();
-                for (q = static_cast<uint32_t>(lane); q < total; q += 32) {
-                    flood_settle(tr, t, L, cells[q]);
-                }
-            } else { // a frontier wider than the list (never seen on a maze): every lane its own rows
-                uint64_t m = N0;
-                while (m) {
-                    int const c = lab_ffs64(m) - 1;
-                    m &= m - 1;
-                    flood_settle(tr, t, L, (r0 << 6) | c);
-                }
-                m = N1;
-                while (m) {
-                    int const c = lab_ffs64(m) - 1;
-                    m &= m - 1;
-                    flood_settle(tr, t, L, (r1 << 6) | c);
-                }
-            }
-            lab_syncwarp();
-            F0 = N0;
-            F1 = N1;
-        }
-        ws.settled += settled;
-        lab_st_cg(p.plane[0].visited + static_cast<long long>(t) * TS + r0, P0 & ~A0);
-        lab_st_cg(p.plane[0].visited + static_cast<long long>(t) * TS + r1, P1 & ~A1);
+        *f.error = 1u;
     }
-    // the tile's rows into the dense field: lane writes columns lane and lane + 32 of every row
-    lab_syncwarp();
-    {
-        int const row0 = ty * TS, col0 = tx * TS;
-        int const rows_here = g.rows - row0 < TS ? g.rows - row0 : TS;
-        bool const lo = col0 + lane < g.cols, hi = col0 + lane + 32 < g.cols;
-        uint32_t *d = p.plane[0].dist + static_cast<long long>(row0) * g.cols + col0 + lane;
-#pragma unroll 4
-        for (int r = 0; r < rows_here; r++) {
-            uint32_t const a = L[r * TS + lane], b = L[r * TS + lane + 32];
-            if (lo) d[0] = a;
-            if (hi) d[32] = b;
-            d += g.cols;
-        }
-    }
-    lab_syncwarp();
 }
 
-LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t *sm) {
-    if (!tree_live(tr.tc)) {
-        return;
-    }
-    Warp_stats ws;
+// Take the next tile into `slot`: its path rows, and one task per entry crossing (and the root).
+// Returns false when there are no tiles left.  Whole warp.
+LAB_DEV bool flood_open(Params const &p, Tree const &tr, Flood_sm const &f, int slot, int lane, Warp_stats &ws) {
     for (;;) {
         uint32_t t = 0;
         if (lane == 0) {
@@ -663,18 +556,160 @@ LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t
         }
         t = lab_shfl(t, 0);
         if (t >= static_cast<uint32_t>(p.g.ntiles)) {
-            break;
+            return false;
         }
-        flood_tile(p, tr, t, lane, sm, ws);
+        ws.passes++;
+        uint64_t const in_side = lane < 4 ? tr.inmask[static_cast<long long>(t) * 4 + lane] : 0ull;
+        bool const root_here = p.ctl->src_tile[0] == t;
+        if (!lab_any(in_side != 0) && !root_here) {
+            ws.empty++;
+            continue; // nothing enters this tile
+        }
+        {
+            uint64_t X[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                X[k] = lab_ld_ro(p.cross + static_cast<long long>(t) * 4 + k);
+            }
+            tile_open_table(f.O + slot * TS * TS, lab_ld_ro(p.path + static_cast<long long>(t) * TS + 2 * lane),
+                            lab_ld_ro(p.path + static_cast<long long>(t) * TS + 2 * lane + 1), X, lane);
+        }
+        // lane looks after slots 8*lane .. 8*lane+7 (side = lane / 8)
+        uint64_t const m_side = lab_shfl64(in_side, lane >> 3);
+        uint32_t m = static_cast<uint32_t>((m_side >> ((lane & 7) * 8)) & 0xFFull);
+        uint32_t n = static_cast<uint32_t>(lab_popc64(m));
+        int const side = lane >> 3;
+        while (m) {
+            int const b = lab_ffs64(m) - 1;
+            m &= m - 1;
+            uint32_t const pos = static_cast<uint32_t>((lane & 7) * 8 + b);
+            uint32_t const r = side == SIDE_N ? 0u : (side == SIDE_S ? TS - 1u : pos);
+            uint32_t const c = side == SIDE_W ? 0u : (side == SIDE_E ? TS - 1u : pos);
+            flood_push(f, (static_cast<uint32_t>(side) * TS + pos) << 16, (r << 6) | c, 4u, static_cast<uint32_t>(slot));
+        }
+        if (root_here && lane == 0) {
+            uint32_t const rc = p.ctl->src_rc[0];
+            flood_push(f, ROOT_COMP << 16, ((rc >> 8) << 6) | (rc & 0xFFu), 4u, static_cast<uint32_t>(slot));
+            n++;
+        }
+        n = lab_reduce_add(n);
+        if (lane == 0) {
+            int const ty = static_cast<int>(t / static_cast<uint32_t>(p.g.tiles_x)), tx = static_cast<int>(t % static_cast<uint32_t>(p.g.tiles_x));
+            f.live[slot] = n;
+            f.tile[slot] = t;
+            f.origin[slot] = static_cast<uint64_t>(ty) * TS * static_cast<uint64_t>(p.g.cols) + static_cast<uint64_t>(tx) * TS;
+        }
+        lab_syncwarp();
+        return true;
     }
-    uint32_t const settled = lab_reduce_add(ws.settled);
+}
+
+LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t *sm) {
+    if (!tree_live(tr.tc)) {
+        return;
+    }
+    Flood_sm f;
+    f.O = reinterpret_cast<uint8_t *>(sm);
+    f.stack = sm + FLOOD_SLOTS * FLOOD_TAB;
+    f.top = reinterpret_cast<uint32_t *>(sm + FLOOD_SLOTS * FLOOD_TAB + FLOOD_STACK);
+    f.error = f.top + 1;
+    f.live = f.top + 2;
+    f.tile = f.live + FLOOD_SLOTS;
+    f.origin = sm + FLOOD_SLOTS * FLOOD_TAB + FLOOD_STACK + 2 + FLOOD_SLOTS;
+    if (lane == 0) {
+        *f.top = 0;
+        *f.error = 0;
+        for (int s = 0; s < FLOOD_SLOTS; s++) {
+            f.live[s] = 0;
+            f.tile[s] = NO_TILE;
+        }
+    }
+    lab_syncwarp();
+    Warp_stats ws;
+    uint32_t *dist = p.plane[0].dist;
+    long long const cols = p.g.cols;
+    bool exhausted = false, have = false;
+    uint32_t xs = 0, back = 4, v = 0, settled = 0; // xs = slot << 12 | row << 6 | column
+    uint32_t *dp = dist;                            // the square's place in the dense field
+    for (;;) {
+        // keep the stack fed: a free slot takes the next tile
+        uint32_t top = *f.top;
+        if (top < 32u && !exhausted) {
+            for (int s = 0; s < FLOOD_SLOTS && !exhausted; s++) {
+                if (f.live[s] == 0) {
+                    exhausted = !flood_open(p, tr, f, s, lane, ws);
+                }
+            }
+            top = *f.top;
+        }
+        // idle lanes pop (lane 0 settles the new top afterwards)
+        uint32_t const need = lab_ballot(!have);
+        if (need) {
+            uint32_t const rank = static_cast<uint32_t>(lab_popc64(need & ((1u << lane) - 1u)));
+            if (!have && rank < top) {
+                uint64_t const task = f.stack[top - 1u - rank];
+                v = static_cast<uint32_t>(task);
+                uint32_t const hi = static_cast<uint32_t>(task >> 32);
+                back = (hi >> 12) & 7u;
+                xs = (hi & 0xFFFu) | ((hi >> 15) << 12);
+                dp = dist + (f.origin[hi >> 15] + static_cast<uint64_t>((hi >> 6) & 63u) * static_cast<uint64_t>(cols) + (hi & 63u));
+                have = true;
+            }
+            uint32_t const want = static_cast<uint32_t>(lab_popc64(need));
+            lab_syncwarp();
+            if (lane == 0) {
+                *f.top = top - (want < top ? want : top);
+            }
+        }
+        lab_syncwarp();
+        if (!lab_any(have)) {
+            if (exhausted) {
+                break; // no tasks, no tiles
+            }
+            continue;
+        }
+#pragma unroll 1
+        for (int k = 0; k < FLOOD_STEPS; k++) {
+            if (have) {
+                uint32_t const b = f.O[xs];
+                uint32_t const nib = b & 15u & ~(1u << back);
+                *dp = v;
+                if (b >> 4) { // a square with an open crossing: its local level is an edge weight of 5 prefix
+                    flood_note_border(tr, f.tile[xs >> 12], static_cast<int>((xs >> 6) & 63u), static_cast<int>(xs & 63u), v & 0xFFFFu);
+                }
+                settled++;
+                if (nib == 0) { // the branch ends here
+                    have = false;
+                    lab_atomic_sub(&f.live[xs >> 12], 1u);
+                } else {
+                    int const d = lab_ffs32(nib) - 1;
+                    uint32_t rest = nib & (nib - 1u);
+                    while (rest) { // junction: the other branches are somebody else's
+                        int const d2 = lab_ffs32(rest) - 1;
+                        rest &= rest - 1u;
+                        lab_atomic_add(&f.live[xs >> 12], 1u);
+                        flood_push(f, v + 1u, static_cast<uint32_t>(static_cast<int>(xs & 0xFFFu) + ((d2 & 1) ? 2 - d2 : (d2 - 1) * TS)),
+                                   static_cast<uint32_t>((d2 + 2) & 3), xs >> 12);
+                    }
+                    xs = static_cast<uint32_t>(static_cast<int>(xs) + ((d & 1) ? 2 - d : (d - 1) * TS));
+                    dp += (d & 1) ? static_cast<long long>(2 - d) : static_cast<long long>(d - 1) * cols;
+                    back = static_cast<uint32_t>((d + 2) & 3);
+                    v++;
+                }
+            }
+        }
+        lab_syncwarp();
+    }
+    if (*f.error) {
+        lab_atomic_max(&tr.tc->walk_error, 3u);
+    }
+    settled = lab_reduce_add(settled);
     if (lane == 0) {
         if (settled) {
             lab_atomic_add(reinterpret_cast<uint64_t *>(&tr.tc->local_settled), static_cast<uint64_t>(settled));
         }
         lab_atomic_add(reinterpret_cast<uint64_t *>(&p.ctl->n_activations), static_cast<uint64_t>(ws.passes));
         lab_atomic_add(reinterpret_cast<uint64_t *>(&p.ctl->n_empty), static_cast<uint64_t>(ws.empty));
-        lab_atomic_add(reinterpret_cast<uint64_t *>(&p.ctl->n_levels), static_cast<uint64_t>(ws.levels));
     }
 }
 
@@ -831,6 +866,9 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
             p.plane[0].visited[i] = 0;
         }
         return;
+    }
+    for (long long i = gthread; i < static_cast<long long>(p.g.ntiles) * TS; i += nthreads) {
+        p.plane[0].visited[i] = p.path[i]; // one tree: every passable square was reached
     }
     if (gthread != 0) {
         return;

@@ -71,38 +71,102 @@ __device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t &target
     __syncthreads();
 }
 // Pointer jumping, all rounds in one persistent launch: a round costs a grid barrier, not a launch.
-__global__ void __launch_bounds__(512) k_tree_rank(Tree tr, uint32_t max_rounds) {
+// The rounds are tree_rank_round_body / tree_prefix_round_body (device/tree.cuh, which tests/simt runs
+// one launch per round) with one refinement: a thread keeps its first JUMP_K list entries (slot,
+// pointer, value) in registers from round to round, so a round is ONE dependent pair of L2 loads.
+// KIND 0: rank  (pointer = successor, stop at END; then 3 orient, which only needs the ranks)
+// KIND 1: prefix (after 5's parent pass; pointer = parent entry, stop at ROOT)
+constexpr int JUMP_K = 4;
+template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p, Tree tr, uint32_t max_rounds) {
+    Tree_ctl *tc = tr.tc;
+    if (!tree_live(tc)) {
+        return; // every block sees the same flags: nobody waits at a barrier
+    }
     long long const gthread = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
     uint32_t target = 0;
+    uint32_t *const barrier = &tc->barrier[KIND];
+    if (KIND == 1) {
+        tree_parent_body(p, tr, gthread, nthreads);
+        grid_barrier(barrier, target);
+        if (*reinterpret_cast<uint32_t volatile *>(&tc->ok) == 0u || *reinterpret_cast<uint32_t volatile *>(&tc->bad_weight) != 0u) {
+            return;
+        }
+    }
+    uint32_t const ROOT = tr.nslots, STOP = KIND == 0 ? tr.nslots + 1u : tr.nslots;
+    uint32_t *const more = KIND == 0 ? tc->rank_more : tc->prefix_more;
+    long long const n = static_cast<long long>(tc->n_arcs) + 1;
+    uint32_t a[JUMP_K], s[JUMP_K], r[JUMP_K];
+    bool own[JUMP_K];
+#pragma unroll
+    for (int k = 0; k < JUMP_K; k++) {
+        long long const i = gthread + k * nthreads;
+        own[k] = i < n;
+        a[k] = own[k] ? (i + 1 < n ? tr.alist[i] : ROOT) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < JUMP_K; k++) {
+        s[k] = own[k] ? __ldcg(tr.s[0] + a[k]) : STOP;
+        r[k] = own[k] ? __ldcg(tr.r[0] + a[k]) : 0u;
+    }
+    bool const spill = n > JUMP_K * nthreads; // more entries than registers: the rest goes the plain way
     for (uint32_t round = 0; round < max_rounds; round++) {
-        tree_rank_round_body(tr, round, gthread, nthreads);
-        grid_barrier(&tr.tc->barrier[0], target);
-        if (*reinterpret_cast<uint32_t volatile *>(&tr.tc->rank_more[round]) == 0u) {
+        bool const odd = round & 1u;
+        uint32_t const *sin = odd ? tr.s[1] : tr.s[0], *rin = odd ? tr.r[1] : tr.r[0];
+        uint32_t *sout = odd ? tr.s[0] : tr.s[1], *rout = odd ? tr.r[0] : tr.r[1];
+        uint32_t s2[JUMP_K], r2[JUMP_K];
+#pragma unroll
+        for (int k = 0; k < JUMP_K; k++) {
+            bool const go = s[k] != STOP;
+            s2[k] = go ? __ldcg(sin + s[k]) : STOP;
+            r2[k] = go ? __ldcg(rin + s[k]) : 0u;
+        }
+        bool m = false;
+#pragma unroll
+        for (int k = 0; k < JUMP_K; k++) {
+            if (own[k]) {
+                if (s[k] != STOP) {
+                    r[k] += r2[k];
+                    s[k] = s2[k];
+                    m |= s[k] != STOP;
+                }
+                sout[a[k]] = s[k];
+                rout[a[k]] = r[k];
+            }
+        }
+        if (spill) {
+            for (long long i = gthread + JUMP_K * nthreads; i < n; i += nthreads) {
+                uint32_t const ai = i + 1 < n ? tr.alist[i] : ROOT;
+                uint32_t const si = __ldcg(sin + ai), ri = __ldcg(rin + ai);
+                if (si == STOP) {
+                    sout[ai] = STOP;
+                    rout[ai] = ri;
+                } else {
+                    uint32_t const si2 = __ldcg(sin + si);
+                    sout[ai] = si2;
+                    rout[ai] = ri + __ldcg(rin + si);
+                    m |= si2 != STOP;
+                }
+            }
+        }
+        if (__syncthreads_or(m) && threadIdx.x == 0) {
+            *reinterpret_cast<uint32_t volatile *>(&more[round]) = 1u;
+        }
+        if (gthread == 0) {
+            *reinterpret_cast<uint32_t volatile *>(KIND == 0 ? &tc->rank_buf : &tc->prefix_buf) = odd ? 0u : 1u;
+        }
+        grid_barrier(barrier, target);
+        if (*reinterpret_cast<uint32_t volatile *>(&more[round]) == 0u) {
             break;
         }
     }
-}
-__global__ void __launch_bounds__(512) k_tree_prefix(Tree tr, uint32_t max_rounds) {
-    long long const gthread = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
-    uint32_t target = 0;
-    for (uint32_t round = 0; round < max_rounds; round++) {
-        tree_prefix_round_body(tr, round, gthread, nthreads);
-        grid_barrier(&tr.tc->barrier[1], target);
-        if (*reinterpret_cast<uint32_t volatile *>(&tr.tc->prefix_more[round]) == 0u) {
-            break;
-        }
+    if (KIND == 0) {
+        tree_orient_body(p, tr, gthread >> 5, nthreads >> 5, static_cast<int>(threadIdx.x & 31));
     }
 }
-__global__ void __launch_bounds__(256) k_tree_orient(Params p, Tree tr) { tree_orient_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void __launch_bounds__(128) k_tree_flood(Params p, Tree tr) {
     extern __shared__ __align__(16) uint64_t flood_sm[];
     tree_flood_body(p, tr, lane_id(), flood_sm + static_cast<size_t>(threadIdx.x >> 5) * FLOOD_U64);
-}
-__global__ void __launch_bounds__(256) k_tree_parent(Params p, Tree tr) {
-    tree_parent_body(p, tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
-                     static_cast<long long>(gridDim.x) * blockDim.x);
 }
 __global__ void __launch_bounds__(256) k_tree_fixup(Params p, Tree tr) { tree_fixup_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void __launch_bounds__(256) k_tree_gate(Params p, Tree tr) {
@@ -458,9 +522,9 @@ int ensure_tree(lab_grid *h) {
     CU(cudaMalloc(&tr.loc, nt * SLOTS * sizeof(uint32_t)));
     CU(cudaMalloc(&tr.alist, nt * SLOTS * sizeof(uint32_t)));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree_rank, 512, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree_jump<0>, 512, 0));
     int per_sm2 = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_tree_prefix, 512, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_tree_jump<1>, 512, 0));
     h->tree_coop_blocks = std::max(1, std::min(per_sm, per_sm2)) * h->sm_count;
     size_t const flood_smem = 4 * FLOOD_U64 * sizeof(uint64_t);
     CU(cudaFuncSetAttribute(k_tree_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(flood_smem)));
@@ -521,31 +585,27 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     TRACE("k_tree_walk", s);
     mark();
     long long const nslots = static_cast<long long>(tr.nslots) + 2;
-    int const slot_blocks = static_cast<int>(std::min<long long>((nslots + 255) / 256, static_cast<long long>(h->sm_count) * 16));
     uint32_t rounds = static_cast<uint32_t>(ceil_log2(static_cast<unsigned long long>(nslots)));
     // few crossings: fewer blocks make a cheaper barrier (a 64x64 tile has ~64 crossings)
-    int const coop_blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(h->tree_coop_blocks, (static_cast<long long>(h->g.ntiles) * 64 + 1023) / 1024)));
+    int const coop_blocks = static_cast<int>(std::max<long long>(
+        1, std::min<long long>(h->tree_coop_blocks, (static_cast<long long>(h->g.ntiles) * 64 + 512 * JUMP_K - 1) / (512 * JUMP_K))));
     {
-        void *args[] = {const_cast<Tree *>(&tr), &rounds};
-        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_rank), dim3(coop_blocks), dim3(512), args, 0, s));
+        void *args[] = {&p, const_cast<Tree *>(&tr), &rounds};
+        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_jump<0>), dim3(coop_blocks), dim3(512), args, 0, s));
     }
-    TRACE("k_tree_rank", s);
+    TRACE("k_tree_jump<rank+orient>", s);
     mark();
-    k_tree_orient<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, tr);
-    TRACE("k_tree_orient", s);
     mark();
     int const fill_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_flood_per_sm);
     k_tree_flood<<<fill_blocks, 128, 4 * FLOOD_U64 * sizeof(uint64_t), s>>>(p, tr);
     TRACE("k_tree_flood", s);
     mark();
-    k_tree_parent<<<slot_blocks, 256, 0, s>>>(p, tr);
-    TRACE("k_tree_parent", s);
     mark();
     {
-        void *args[] = {const_cast<Tree *>(&tr), &rounds};
-        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_prefix), dim3(coop_blocks), dim3(512), args, 0, s));
+        void *args[] = {&p, const_cast<Tree *>(&tr), &rounds};
+        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_jump<1>), dim3(coop_blocks), dim3(512), args, 0, s));
     }
-    TRACE("k_tree_prefix", s);
+    TRACE("k_tree_jump<parent+prefix>", s);
     mark();
     k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, tr);
     TRACE("k_tree_fixup", s);

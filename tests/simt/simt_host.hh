@@ -215,6 +215,7 @@ LAB_DEV void lab_syncwarp() { (void)simt::exchange(0); }
 
 LAB_DEV int lab_ffs64(uint64_t v) { return v ? __builtin_ctzll(v) + 1 : 0; }
 LAB_DEV int lab_popc64(uint64_t v) { return __builtin_popcountll(v); }
+LAB_DEV int lab_ffs32(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 
 template <class T> LAB_DEV T lab_ld_cg(T const *p) {
     simt::maybe_yield();
