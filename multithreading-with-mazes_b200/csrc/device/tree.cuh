@@ -632,6 +632,9 @@ LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t
     uint32_t xs = 0, back = 4, v = 0, settled = 0; // xs = slot << 12 | row << 6 | column
     uint32_t *dp = dist;                            // the square's place in the dense field
     for (;;) {
+        if (*f.error) { // (nobody writes it between the barrier that ended the last round and here)
+            break;      // not a tree (a cycle keeps spawning tasks): the result is void anyway, stop
+        }
         // keep the stack fed: a free slot takes the next tile
         uint32_t top = *f.top;
         if (top < 32u && !exhausted) {
@@ -641,6 +644,9 @@ LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t
                 }
             }
             top = *f.top;
+        }
+        if (top > static_cast<uint32_t>(FLOOD_STACK)) {
+            top = FLOOD_STACK; // pushes beyond the stack were dropped (and flagged): not a tree
         }
         // idle lanes pop (lane 0 settles the new top afterwards)
         uint32_t const need = lab_ballot(!have);
@@ -660,6 +666,8 @@ LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t
             if (lane == 0) {
                 *f.top = top - (want < top ? want : top);
             }
+        } else if (lane == 0 && *f.top != top) {
+            *f.top = top;
         }
         lab_syncwarp();
         if (!lab_any(have)) {
@@ -678,7 +686,11 @@ LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t
                     flood_note_border(tr, f.tile[xs >> 12], static_cast<int>((xs >> 6) & 63u), static_cast<int>(xs & 63u), v & 0xFFFFu);
                 }
                 settled++;
-                if (nib == 0) { // the branch ends here
+                if (nib == 0 || (v & 0xFFFFu) > static_cast<uint32_t>(TS * TS)) {
+                    // the branch ends here (or runs in circles: not a tree, the checks after the flood say so)
+                    if (nib != 0) {
+                        *f.error = 1u;
+                    }
                     have = false;
                     lab_atomic_sub(&f.live[xs >> 12], 1u);
                 } else {
