@@ -49,11 +49,13 @@ WORKLOADS = {
     "h-distance-arena-32767": ("distance", "arena", 32767, None, "north_star headline size, open maze"),
     "h-gather-arena-32767": ("gather", "arena", 32767, None, "north_star headline size, open maze"),
     "distance-wilson-4095": ("distance", "wilson", 4095, None, "configs[4] builder at 4095"),
+    "distance-kruskal-16383": ("distance", "kruskal", 16383, None, "configs[1] builder at 16383 (20 s host build)"),
+    "h-distance-kruskal-32767": ("distance", "kruskal", 32767, None, "north_star headline size, perfect maze (90 s host build)"),
+    "gather-kruskal-4095": ("gather", "kruskal", 4095, None, "bfs-gather on configs[1]'s maze"),
     "distance-arena-16383": ("distance", "arena", 16383, None, "configs[2] maze, distance map"),
 }
 DEFAULT = "c2-distance-kruskal-4095"
 ALG_BYTES_PER_CELL = {"distance": 8.0, "gather": 4.0, "hunt": 4.0, "corners": 4.0}
-KERNELS_PER_STEP = {"distance": 8, "gather": 10, "hunt": 8, "corners": 8}  # my kernels launched per step
 
 
 def peaks():
@@ -195,6 +197,7 @@ def ours(args):
     torch.cuda.synchronize()
     step_ms = sum(a.elapsed_time(b) for a, b in evs)
     stats = grid.stats()
+    launches_per_step = int(stats["launches"])  # counted by the library as it launches them
 
     # ---- end to end: pinned host buffers, copies inside the timed region ---------------------------
     host_in = torch.from_numpy(maze.view(np.int16)).pin_memory()
@@ -262,16 +265,20 @@ def ours(args):
             "l2": "256 MB flush buffer written between timed steps", "maze_build_s_host": round(build_s, 2),
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "k_bfs_tiles", "peak_source": peak_src,
+                     "traffic": traffic,
+                     "kernel": ("search phase = spanning-tree pipeline: k_tree_walk, k_tree_jump<rank>, k_tree_flood, "
+                                "k_tree_jump<prefix>, k_tree_fixup (csrc/device/tree.cuh)") if stats["tree_used"] else "k_bfs_tiles",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": search_ms_avg,
                      "kernel_share_of_step": t["search_ms"] / step_ms},
         "e2e": {"value": e_settled_all / (e_ms_max * 1e-3) / 1e9, "unit": "Gcells/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e_ms_max / e2e_steps, "steps": e2e_steps},
-        "gpu_launches": KERNELS_PER_STEP[game] * args.steps,
+        "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "phases_ms_per_step": {k: v / args.steps for k, v in t.items()},
         "search_stats_last_step": {k: stats[k] for k in ("tiles", "activations", "empty", "levels", "settled", "resettles",
-                                                         "queue_pushes", "direct", "worker_warps")},
+                                                         "queue_pushes", "direct", "worker_warps", "tree_used", "tree_squares",
+                                                         "tree_pairs", "tree_crossings", "launches")},
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_port_baseline(maze, spec, budget_s=args.cpu_budget)

@@ -77,6 +77,7 @@ typedef struct lab_stats {
     /* spanning-tree pipeline (csrc/device/tree.cuh): passable squares, adjacent passable pairs (a tree
      * has pairs == squares - 1), tile-border crossings, and whether the pipeline produced the field */
     uint64_t tree_squares, tree_pairs, tree_crossings, tree_used;
+    uint64_t launches; /* kernels launched by the search (reset, pack, search, epilogue) */
 } lab_stats;
 
 /* ---- grid lifetime (replaces Maze::Maze construction, maze/maze.cc:349-354, for the GPU side) -- */

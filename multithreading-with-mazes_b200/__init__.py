@@ -60,7 +60,7 @@ class Stats(Structure):
     _fields_ = [(n, c_uint64) for n in ("tiles", "activations", "empty", "levels", "settled", "rechecks", "resettles",
                                         "queue_pushes", "direct")] + [("worker_warps", c_uint32), ("error", c_uint32)] + [
         (n, c_uint64) for n in ("cyc_load", "cyc_loop", "cyc_publish", "cyc_idle", "cyc_step", "cyc_emit", "batches",
-                                "tree_squares", "tree_pairs", "tree_crossings", "tree_used")]
+                                "tree_squares", "tree_pairs", "tree_crossings", "tree_used", "launches")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -158,7 +158,8 @@ LAB_DEV void tile_open_table(uint8_t *O, uint64_t P0, uint64_t P1, uint64_t cons
 // shared memory per warp (uint64 units): byte table[4096] | res16[1032] | list16[1032] (later res32[256]) | masks[16] | counter
 constexpr int WALK_IDS = 1025;
 constexpr int WALK_TAB = TS * TS / 8;
-constexpr int WALK_U64 = WALK_TAB + 260 + 260 + 16 + 2;
+constexpr int WALK_LIST = 640; // walkers of one tile (a 64x64 piece of a perfect maze has at most 513)
+constexpr int WALK_U64 = WALK_TAB + 260 + WALK_LIST / 4 + 2; // 7.4 KB: seven 4-warp blocks per SM
 constexpr uint32_t WALK_END = 0xFFFFu;
 
 LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, uint64_t *sm) {
@@ -167,8 +168,8 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
     uint16_t *res16 = reinterpret_cast<uint16_t *>(sm + WALK_TAB);
     uint16_t *list = reinterpret_cast<uint16_t *>(sm + WALK_TAB + 260);
     uint32_t *res32 = reinterpret_cast<uint32_t *>(sm + WALK_TAB + 260); // after phase A the list is dead
-    uint64_t *masks = sm + WALK_TAB + 520;
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(sm + WALK_TAB + 536);
+    uint64_t *masks = sm + WALK_TAB + 260 + WALK_LIST / 4 - 16; // (read before the list grows that far)
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(sm + WALK_TAB + 260 + WALK_LIST / 4);
     uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
     int const r0 = 2 * lane, r1 = 2 * lane + 1;
 
@@ -208,8 +209,12 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
             incl += v;
         }
     }
-    uint32_t const total = lab_shfl(incl, 31);
-    {
+    uint32_t total = lab_shfl(incl, 31);
+    lab_syncwarp(); // every lane has read its mask word: the list may overwrite them
+    if (total > static_cast<uint32_t>(WALK_LIST)) { // more walkers than any maze tile has: leave it to the wave
+        lab_atomic_max(&tr.tc->walk_error, 4u);
+        total = 0;
+    } else {
         uint32_t q = incl - mine, m = my_bits;
         while (m) {
             int const b = lab_ffs64(m) - 1;
@@ -241,10 +246,12 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
     // ---- phase A: every walker to the first block border ----------------------------------------
     // One flat loop, one step per iteration: a lane whose walker has arrived fetches its next one in
     // the same iteration, so the lanes of the warp stay converged whatever the lengths of their pieces.
+    // A walker's state is one word: square (row << 6 | column) << 2 | heading.
     uint32_t const nitems = total + (root_tile ? 1u : 0u);
+    uint32_t const root_state = root_tile && root_open ? ((static_cast<uint32_t>(rr) << 6 | static_cast<uint32_t>(rc)) << 2 | static_cast<uint32_t>(rh))
+                                                       : 0xFFFFFFFFu;
     bool have = false, skip = false;
-    int r = 0, c = 0, h = 0;
-    uint32_t id = 0, steps = 0;
+    uint32_t st = 0, id = 0;
     for (;;) {
         if (!have) {
             uint32_t const idx = lab_atomic_add(cnt, 1u);
@@ -252,57 +259,55 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
                 break;
             }
             have = true;
-            steps = 0;
             skip = idx == total; // the root's own walker leaves the root state instead of ending there
             if (skip) {
                 id = WALK_IDS - 1;
-                r = rr;
-                c = rc;
-                h = rh;
+                st = (static_cast<uint32_t>(rr) << 6 | static_cast<uint32_t>(rc)) << 2 | static_cast<uint32_t>(rh);
             } else {
                 id = list[idx];
-                int const pos = static_cast<int>(id & 63u);
-                if (id < SLOTS) {
-                    int const side = static_cast<int>(id >> 6);
-                    r = side == SIDE_N ? 0 : (side == SIDE_S ? TS - 1 : pos);
-                    c = side == SIDE_W ? 0 : (side == SIDE_E ? TS - 1 : pos);
-                    h = side == SIDE_N ? 2 : (side == SIDE_S ? 0 : (side == SIDE_W ? 1 : 3));
-                } else {
-                    uint32_t const k = (id - SLOTS) >> 6; // h*3 + (b-1)
-                    h = static_cast<int>(k / 3u);
-                    int const line = 16 * (static_cast<int>(k % 3u) + 1);
-                    r = h == 2 ? line : (h == 0 ? line - 1 : pos);
-                    c = h == 1 ? line : (h == 3 ? line - 1 : pos);
+                uint32_t const pos = id & 63u;
+                uint32_t r, c, h;
+                if (id < SLOTS) { // a tile crossing: the first square inside, heading inwards
+                    uint32_t const side = id >> 6;
+                    bool const ns = side < 2u;
+                    r = ns ? side * (TS - 1u) : pos;
+                    c = ns ? pos : (side & 1u) * (TS - 1u);
+                    h = (0xD2u >> (2u * side)) & 3u; // N -> S, S -> N, W -> E, E -> W
+                } else { // over an inner border at row / column `line`
+                    uint32_t const k = (id - SLOTS) >> 6; // heading * 3 + (border - 1)
+                    h = (k * 11u) >> 5;
+                    uint32_t const line = 16u * (k - 3u * h + 1u);
+                    uint32_t const at = line - ((h == 0u || h == 3u) ? 1u : 0u); // heading N / W: the square before the line
+                    r = (h & 1u) ? pos : at;
+                    c = (h & 1u) ? at : pos;
                 }
+                st = (r << 6 | c) << 2 | h;
             }
         }
         uint32_t result = WALK_END;
-        bool arrived = root_tile && !skip && r == rr && c == rc && h == rh && root_open; // the tour ends where it began
+        bool arrived = st == root_state && !skip; // the tour ends where it began
         skip = false;
-        uint32_t const b = O[r * TS + c];
+        uint32_t const x = st >> 2;
+        uint32_t h = st & 3u;
+        uint32_t const b = O[x];
         uint32_t const nib = (b | (b >> 4)) & 15u;
         arrived |= nib == 0; // a square on its own (only the root can be one)
         if (!arrived) {
-            uint32_t const rot = ((nib >> h) | (nib << (4 - h))) & 15u; // bit j: direction h + j
-            int const j = static_cast<int>((0x53535252u >> (2 * (rot & 15u))) & 3u); // right, else straight, else left, else back
-            h = (h + j) & 3;
-            int const nr = r + (h == 2) - (h == 0), nc = c + (h == 1) - (h == 3);
-            if ((b >> (4 + h)) & 1u) { // through an open crossing: into the neighbour's slot
-                uint32_t const ns = h == 0 ? SIDE_S * TS + static_cast<uint32_t>(c)
-                                           : (h == 2 ? SIDE_N * TS + static_cast<uint32_t>(c)
-                                                     : (h == 1 ? SIDE_W * TS + static_cast<uint32_t>(r) : SIDE_E * TS + static_cast<uint32_t>(r)));
-                result = 1024u + ns;
+            uint32_t const rot = ((nib >> h) | (nib << (4u - h))) & 15u; // bit j: direction heading + j
+            h = (h + ((0x53535252u >> (2u * rot)) & 3u)) & 3u;           // right, else straight, else left, else back
+            uint32_t const nx = x + ((0x3F804100u >> (8u * h)) & 0xFFu) - 64u; // -64, +1, +64, -1
+            if ((b >> (4u + h)) & 1u) { // through an open crossing: into the neighbour's slot
+                uint32_t const r = x >> 6, c = x & 63u;
+                // heading N enters the neighbour's S side, E its W side, S its N side, W its E side
+                result = 1024u + ((0xC9u >> (2u * h)) & 3u) * TS + ((h & 1u) ? r : c);
                 arrived = true;
-            } else if (((r ^ nr) | (c ^ nc)) & 0x30) { // crossed a block border: the next piece starts here
-                int const line = (h == 1 ? nc : (h == 3 ? c : (h == 2 ? nr : r))) >> 4; // 1..3
-                result = SLOTS + static_cast<uint32_t>(h * 3 + line - 1) * 64u + static_cast<uint32_t>((h & 1) ? r : c);
-                arrived = true;
-            } else if (++steps > 4u * 16u * 16u + 8u) {
-                lab_atomic_max(&tr.tc->walk_error, 1u);
+            } else if ((x ^ nx) & 0xC30u) { // crossed a block border: the next piece starts here
+                uint32_t const r = x >> 6, c = x & 63u, nr = nx >> 6, nc = nx & 63u;
+                uint32_t const line = (h == 1u ? nc : (h == 3u ? c : (h == 2u ? nr : r))) >> 4; // 1..3
+                result = SLOTS + (h * 3u + line - 1u) * 64u + ((h & 1u) ? r : c);
                 arrived = true;
             }
-            r = nr;
-            c = nc;
+            st = nx << 2 | h;
         }
         if (arrived) {
             res16[id] = static_cast<uint16_t>(result);
@@ -510,8 +515,8 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
 // FLOOD_SLOTS tiles open at a time so that the tail of one tile overlaps the bulk of the next.
 // Once the entry crossings' exact levels are known (5 prefix) one streaming pass turns the packed
 // field into global levels (6 fix-up).  The local levels of border squares go to tr.loc.
-constexpr int FLOOD_SLOTS = 2;
-constexpr int FLOOD_STACK = 512; // tasks
+constexpr int FLOOD_SLOTS = 1;
+constexpr int FLOOD_STACK = 256; // tasks
 // per warp, uint64 units: byte tables of the open tiles | task stack | control words
 constexpr int FLOOD_TAB = TS * TS / 8; // one byte table (tile_open_table) per open tile
 constexpr int FLOOD_STEPS = 4;         // squares a lane advances between two looks at the stack
@@ -630,7 +635,8 @@ LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t
     long long const cols = p.g.cols;
     bool exhausted = false, have = false;
     uint32_t xs = 0, back = 4, v = 0, settled = 0; // xs = slot << 12 | row << 6 | column
-    uint32_t *dp = dist;                            // the square's place in the dense field
+    uint32_t di = 0;                                // the square's index in the dense field (< 2^32: make_geom)
+    int const icols = static_cast<int>(cols);
     for (;;) {
         if (*f.error) { // (nobody writes it between the barrier that ended the last round and here)
             break;      // not a tree (a cycle keeps spawning tasks): the result is void anyway, stop
@@ -658,7 +664,7 @@ LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t
                 uint32_t const hi = static_cast<uint32_t>(task >> 32);
                 back = (hi >> 12) & 7u;
                 xs = (hi & 0xFFFu) | ((hi >> 15) << 12);
-                dp = dist + (f.origin[hi >> 15] + static_cast<uint64_t>((hi >> 6) & 63u) * static_cast<uint64_t>(cols) + (hi & 63u));
+                di = static_cast<uint32_t>(f.origin[hi >> 15]) + ((hi >> 6) & 63u) * static_cast<uint32_t>(icols) + (hi & 63u);
                 have = true;
             }
             uint32_t const want = static_cast<uint32_t>(lab_popc64(need));
@@ -681,7 +687,7 @@ LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t
             if (have) {
                 uint32_t const b = f.O[xs];
                 uint32_t const nib = b & 15u & ~(1u << back);
-                *dp = v;
+                dist[di] = v;
                 if (b >> 4) { // a square with an open crossing: its local level is an edge weight of 5 prefix
                     flood_note_border(tr, f.tile[xs >> 12], static_cast<int>((xs >> 6) & 63u), static_cast<int>(xs & 63u), v & 0xFFFFu);
                 }
@@ -704,7 +710,7 @@ LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t
                                    static_cast<uint32_t>((d2 + 2) & 3), xs >> 12);
                     }
                     xs = static_cast<uint32_t>(static_cast<int>(xs) + ((d & 1) ? 2 - d : (d - 1) * TS));
-                    dp += (d & 1) ? static_cast<long long>(2 - d) : static_cast<long long>(d - 1) * cols;
+                    di = static_cast<uint32_t>(static_cast<int>(di) + ((d & 1) ? 2 - d : (d - 1) * icols));
                     back = static_cast<uint32_t>((d + 2) & 3);
                     v++;
                 }

@@ -343,8 +343,9 @@ struct lab_grid {
     bool tree_alloc = false;
     Tree_ctl tree_last{};
     bool tree_tried = false;
+    uint64_t launches = 0; // kernels launched by the last search (bench.py reports them)
     int tree_coop_blocks = 0; // co-resident blocks of the multi-round kernels
-    int tree_flood_per_sm = 1;
+    int tree_flood_per_sm = 1, tree_walk_per_sm = 1;
     cudaEvent_t tev[10]{}; // LAB_TREE_TIMING=1: per-phase events
     bool tev_on = false;
 };
@@ -460,6 +461,7 @@ int search_prepare(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t 
     Geom const &g = h->g;
     size_t const nt = static_cast<size_t>(g.ntiles);
     size_t const cells = static_cast<size_t>(g.rows) * g.cols;
+    h->launches = 0;
     CU(cudaEventRecord(h->ev[EV_SETUP0], s));
     CU(cudaMemsetAsync(h->ctl, 0, sizeof(Control), s));
     CU(cudaMemsetAsync(h->res, 0, sizeof(Result), s));
@@ -476,6 +478,7 @@ int search_prepare(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t 
     TRACE("k_pack", s);
     k_force_sources<<<1, 1, 0, s>>>(g, h->path, d);
     TRACE("k_force_sources", s);
+    h->launches += 2;
     CU(cudaGetLastError());
     return LAB_OK;
 }
@@ -489,6 +492,7 @@ int search_arm(lab_grid *h, Run_desc const &d, uint64_t const *ghost_n, uint64_t
     TRACE("k_cross", s);
     k_init_run<<<1, 1, 0, s>>>(p, d, budget_ns());
     TRACE("k_init_run", s);
+    h->launches += 2;
     CU(cudaGetLastError());
     return LAB_OK;
 }
@@ -498,6 +502,7 @@ int search_launch(lab_grid *h, int nplanes) {
     Params p = make_params(h, nplanes);
     k_bfs_tiles<<<h->bfs_blocks, h->bfs_threads, 0, s>>>(p);
     TRACE("k_bfs_tiles", s);
+    h->launches += 1;
     CU(cudaGetLastError());
     return LAB_OK;
 }
@@ -530,6 +535,10 @@ int ensure_tree(lab_grid *h) {
     CU(cudaFuncSetAttribute(k_tree_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(flood_smem)));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tree_flood_per_sm, k_tree_flood, 128, flood_smem));
     h->tree_flood_per_sm = std::max(1, h->tree_flood_per_sm);
+    CU(cudaFuncSetAttribute(k_tree_walk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_tree_flood, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tree_walk_per_sm, k_tree_walk, 128, 0));
+    h->tree_walk_per_sm = std::max(1, h->tree_walk_per_sm);
     CU(cudaMalloc(&tr.tc, sizeof(Tree_ctl)));
     h->tree_alloc = true;
     return LAB_OK;
@@ -561,6 +570,7 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     CU(cudaMemsetAsync(tr.tc, 0, sizeof(Tree_ctl), s));
     k_tree_count<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, tr);
     TRACE("k_tree_count", s);
+    h->launches += 1;
     Tree_ctl c{};
     CU(cudaMemcpyAsync(&c, tr.tc, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -580,7 +590,7 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     };
     mark();
     k_tree_init<<<1, 1, 0, s>>>(tr);
-    int const walk_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 8);
+    int const walk_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_walk_per_sm);
     k_tree_walk<<<walk_blocks, 128, 0, s>>>(p, tr);
     TRACE("k_tree_walk", s);
     mark();
@@ -614,6 +624,7 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     TRACE("k_tree_gate", s);
     mark();
     h->tree_tried = true; // finish_run reads the pipeline's control block back
+    h->launches += 7;     // init, walk, jump<rank>, flood, jump<prefix>, fixup, gate
     CU(cudaGetLastError());
     return LAB_OK;
 }
@@ -684,6 +695,7 @@ int finish_run(lab_grid *h) {
     st.tree_pairs = h->tree_last.E;
     st.tree_crossings = h->tree_last.n_arcs;
     st.tree_used = h->tree_last.used;
+    st.launches = h->launches;
     if (c.error == 1) {
         return fail(LAB_ERR_TIMEOUT, "search kernel passed its deadline (LAB_BFS_BUDGET_MS); %llu tiles still active",
                     static_cast<unsigned long long>(c.pending));
@@ -967,6 +979,7 @@ int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t 
     TRACE("k_max_level", s);
     k_measure<<<blocks_for(h, h->g.rows, 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
     TRACE("k_measure", s);
+    h->launches += 3;
     CU(cudaGetLastError());
     rc = finish_run(h);
     if (rc) {
@@ -1003,6 +1016,7 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
     TRACE("k_resolve", s);
     k_paint<<<grid_blocks(h), 256, 0, s>>>(p, h->squares, h->res);
     TRACE("k_paint", s);
+    h->launches += 2 + (d.game == GAME_GATHER ? (want_paths ? 3 : 2) : 1);
     if (d.game == GAME_GATHER) {
         CU(cudaMemsetAsync(h->d_front_rc, 0xFF, 8 * sizeof(int32_t), s));
         k_walk<<<4, 32, 0, s>>>(p, d.game, h->squares, h->res, h->d_finish_rc, h->d_front_rc, 1, 1, 1);
