@@ -97,23 +97,35 @@ LAB_DEV void measure_body(Geom g, uint16_t *grid, uint64_t const *visited, Resul
                           long long nwarps, int lane) {
     // one warp per row (grid stride); a 64-square word with no visited square costs one 8-byte load
     unsigned long long count = 0;
-    for (long long rr = gwarp; rr < g.rows; rr += nwarps) {
-        int const r = static_cast<int>(rr);
+    constexpr int U = 4; // 64-square words of a row handled together: independent read-modify-writes in flight
+    long long const chunks = (g.tiles_x + U - 1) / U;
+    for (long long it = gwarp; it < static_cast<long long>(g.rows) * chunks; it += nwarps) {
+        int const r = static_cast<int>(it / chunks);
+        int const j0 = static_cast<int>(it % chunks) * U;
         uint64_t const *vrow = visited + (static_cast<long long>(r / TS) * g.tiles_x) * TS + (r % TS);
         uint16_t *row = grid + static_cast<long long>(r) * g.cols;
-        for (int j = 0; j < g.tiles_x; j++) {
-            uint64_t const v = vrow[static_cast<long long>(j) * TS];
-            if (v == 0) {
-                continue;
+        uint64_t v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            v[u] = j0 + u < g.tiles_x ? vrow[static_cast<long long>(j0 + u) * TS] : 0ull;
+        }
+        uint16_t a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int const c0 = (j0 + u) * TS + lane;
+            a[u] = ((v[u] >> lane) & 1) ? row[c0] : static_cast<uint16_t>(0);
+            b[u] = ((v[u] >> (lane + 32)) & 1) ? row[c0 + 32] : static_cast<uint16_t>(0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int const c0 = (j0 + u) * TS + lane;
+            if ((v[u] >> lane) & 1) {
+                row[c0] = a[u] | SQ_MEASURE;
             }
-            int const c0 = j * TS + lane;
-            if ((v >> lane) & 1) {
-                row[c0] |= SQ_MEASURE;
+            if ((v[u] >> (lane + 32)) & 1) {
+                row[c0 + 32] = b[u] | SQ_MEASURE;
             }
-            if ((v >> (lane + 32)) & 1) {
-                row[c0 + 32] |= SQ_MEASURE;
-            }
-            count += static_cast<unsigned long long>(lab_popc64(v));
+            count += static_cast<unsigned long long>(lab_popc64(v[u]));
         }
     }
     if (lane == 0 && count) {
@@ -227,21 +239,40 @@ LAB_DEV void paint_body(Params p, uint16_t *grid, Result *res, long long gthread
     }
     uint32_t painted = 0;
     bool const same_plane = nr <= 1 || (r[0].plane == r[1].plane && r[0].plane == r[2].plane && r[0].plane == r[3].plane);
-    for (long long i = gthread; i < n; i += nthreads) {
-        uint32_t bits = 0;
+    constexpr int U = 8; // independent loads in flight per thread (a streaming pass: HBM latency x bandwidth)
+    for (long long i0 = gthread; i0 < n; i0 += nthreads * U) {
+        uint32_t dv[U];
+        uint32_t bits[U];
         if (same_plane) {
-            uint32_t const dv = p.plane[r[0].plane].dist[i];
-            for (uint32_t k = 0; k < nr; k++) {
-                bits |= dv < r[k].below ? r[k].bits : 0u;
+            uint32_t const *d = p.plane[r[0].plane].dist;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                long long const i = i0 + u * nthreads;
+                dv[u] = i < n ? d[i] : INF;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                bits[u] = 0;
+                for (uint32_t k = 0; k < nr; k++) {
+                    bits[u] |= dv[u] < r[k].below ? r[k].bits : 0u;
+                }
             }
         } else {
-            for (uint32_t k = 0; k < nr; k++) {
-                bits |= p.plane[r[k].plane].dist[i] < r[k].below ? r[k].bits : 0u;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                long long const i = i0 + u * nthreads;
+                bits[u] = 0;
+                for (uint32_t k = 0; k < nr; k++) {
+                    bits[u] |= (i < n && p.plane[r[k].plane].dist[i] < r[k].below) ? r[k].bits : 0u;
+                }
             }
         }
-        if (bits) {
-            grid[i] |= static_cast<uint16_t>(bits);
-            painted++;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (bits[u]) { // (levels < threshold only exist inside the grid)
+                grid[i0 + u * nthreads] |= static_cast<uint16_t>(bits[u]);
+                painted++;
+            }
         }
     }
     painted = lab_reduce_add(painted);

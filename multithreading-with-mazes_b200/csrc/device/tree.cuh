@@ -46,6 +46,7 @@ struct Tree_ctl {
     uint32_t n_arcs;     // crossings in total = entries of Tree::alist
     uint32_t used;       // the tree pipeline produced the field (set by gate)
     uint32_t barrier[2]; // grid barriers of the two multi-round kernels (rank, prefix)
+    uint32_t dirty;      // the flood has started writing its packed field into the dense level field
 };
 
 struct Tree {
@@ -406,9 +407,10 @@ LAB_DEV void tree_walk_body(Params const &p, Tree const &tr, int lane, uint64_t 
     }
 }
 
-// One thread, before the walk: the two list ends.
+// One thread, after the count and before the walk: can it be a tree at all?  And the two list ends.
 LAB_DEV void tree_init_body(Tree const &tr) {
     uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
+    tr.tc->ok = (tr.tc->V >= 2 && tr.tc->E + 1 == tr.tc->V) ? 1u : 0u; // a tree has squares - 1 adjacent pairs
     tr.succ0[ROOT] = END;
     tr.succ0[END] = END;
     for (int b = 0; b < 2; b++) {
@@ -612,6 +614,9 @@ LAB_DEV bool flood_open(Params const &p, Tree const &tr, Flood_sm const &f, int 
 LAB_DEV void tree_flood_body(Params const &p, Tree const &tr, int lane, uint64_t *sm) {
     if (!tree_live(tr.tc)) {
         return;
+    }
+    if (lane == 0 && lab_ld_ro(&tr.tc->dirty) == 0u) {
+        lab_st_volatile(&tr.tc->dirty, 1u);
     }
     Flood_sm f;
     f.O = reinterpret_cast<uint8_t *>(sm);
@@ -876,6 +881,9 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
     Tree_ctl *tc = tr.tc;
     Control *ctl = p.ctl;
     if (!tree_live(tc)) {
+        if (tc->dirty == 0) {
+            return; // gave up before anything was written
+        }
         long long const cells = static_cast<long long>(p.g.rows) * p.g.cols;
         for (long long i = gthread; i < cells; i += nthreads) {
             p.plane[0].dist[i] = INF;

@@ -114,12 +114,27 @@ template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p,
         bool const odd = round & 1u;
         uint32_t const *sin = odd ? tr.s[1] : tr.s[0], *rin = odd ? tr.r[1] : tr.r[0];
         uint32_t *sout = odd ? tr.s[0] : tr.s[1], *rout = odd ? tr.r[0] : tr.r[1];
+        // three hops per round through the buffer of the last round: a pointer's span grows fourfold
         uint32_t s2[JUMP_K], r2[JUMP_K];
 #pragma unroll
         for (int k = 0; k < JUMP_K; k++) {
-            bool const go = s[k] != STOP;
-            s2[k] = go ? __ldcg(sin + s[k]) : STOP;
-            r2[k] = go ? __ldcg(rin + s[k]) : 0u;
+            s2[k] = s[k];
+            r2[k] = 0u;
+        }
+#pragma unroll
+        for (int hop = 0; hop < 3; hop++) {
+            uint32_t sn[JUMP_K], rn[JUMP_K];
+#pragma unroll
+            for (int k = 0; k < JUMP_K; k++) {
+                bool const go = s2[k] != STOP;
+                sn[k] = go ? __ldcg(sin + s2[k]) : STOP;
+                rn[k] = go ? __ldcg(rin + s2[k]) : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < JUMP_K; k++) {
+                s2[k] = sn[k];
+                r2[k] += rn[k];
+            }
         }
         bool m = false;
 #pragma unroll
@@ -552,10 +567,9 @@ int ceil_log2(unsigned long long n) {
     return r;
 }
 
-// The spanning-tree pipeline (device/tree.cuh), between search_arm and the wave kernel.  One host
-// round trip: the square / adjacency counts decide whether the maze can be a tree at all.  Everything
-// after that is gated on the device; if any check fails the wave kernel finds its control block
-// untouched and does the search.
+// The spanning-tree pipeline (device/tree.cuh), between search_arm and the wave kernel.  Everything is
+// decided and gated on the device (no host round trip): if the counts or any later check say "not a
+// tree", the remaining kernels return at once and the wave kernel finds its control block untouched.
 int run_tree(lab_grid *h, Run_desc const &d) {
     h->tree_last = Tree_ctl{};
     h->tree_tried = false;
@@ -571,15 +585,8 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     k_tree_count<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, tr);
     TRACE("k_tree_count", s);
     h->launches += 1;
-    Tree_ctl c{};
-    CU(cudaMemcpyAsync(&c, tr.tc, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    h->tree_last = c;
-    if (c.V < 2 || c.E + 1 != c.V) {
-        return LAB_OK; // not a tree: the wave does it
-    }
-    uint32_t const one = 1;
-    CU(cudaMemcpyAsync(&tr.tc->ok, &one, sizeof one, cudaMemcpyHostToDevice, s));
+    // No host round trip: k_tree_init decides on the device whether the counts allow a tree, and every
+    // later kernel of the pipeline returns at once if not (a handful of empty launches on an arena).
     h->tev_on = env_ll("LAB_TREE_TIMING", 0) != 0;
     int tev_i = 0;
     auto mark = [&]() {
@@ -977,7 +984,7 @@ int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t 
     TRACE("k_resolve", s);
     k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
     TRACE("k_max_level", s);
-    k_measure<<<blocks_for(h, h->g.rows, 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
+    k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
     TRACE("k_measure", s);
     h->launches += 3;
     CU(cudaGetLastError());
@@ -1267,7 +1274,7 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
     Params p = make_params(h, 1);
     k_resolve<<<1, 1, 0, s>>>(p, h->band_desc, h->res, h->d_finish_rc);
     k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
-    k_measure<<<blocks_for(h, h->g.rows, 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
+    k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
     CU(cudaGetLastError());
     h->band_open = false;
     int const rc = finish_run(h);

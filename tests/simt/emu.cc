@@ -50,9 +50,6 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
     tr.tc = &tc;
     tr.nslots = static_cast<uint32_t>(nt * SLOTS);
     simt::launch(nwarps, [&](int wid, int lane) { tree_count_body(p, tr, wid, nwarps, lane); });
-    g_tree_last = tc;
-    if (tc.V < 2 || tc.E + 1 != tc.V) return;
-    tc.ok = 1;
     tree_init_body(tr);
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
     std::vector<uint64_t> sm(static_cast<size_t>(nwarps) * SM);
