@@ -4,7 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one maze: the whole search (workspace reset, pack,
-persistent tile-relaxation kernel, epilogue) for the workload named in ``config.workload``.
+search phase -- the spanning-tree pipeline on perfect mazes, the persistent tile-relaxation kernel
+otherwise --, epilogue) for the workload named in ``config.workload``.
 Default workload = BASELINE.json configs[1]: Distance map from the centre of a 4095x4095 Kruskal
 perfect maze (seeded, built by the product's linear-time builder, byte-identical to the
 reference builder's output for that seed).
@@ -15,8 +16,8 @@ reference builder's output for that seed).
   e2e        the same metric through the host-facing call path: pinned host Squares -> H2D -> search
              -> D2H of the Squares (and the level field for the distance map), copies timed.
   roofline   HBM: algorithmic bytes per launch (8 B x rows x cols for the distance
-             map, 4 B x rows x cols for the solvers) / the search kernel's CUDA-event time, against
-             MEASURED_PEAKS.json's copy bandwidth.
+             map, 4 B x rows x cols for the solvers) / the search phase's CUDA-event time (events on
+             the library's stream around its kernels), against MEASURED_PEAKS.json's copy bandwidth.
   cpu_baseline  the oracle's CPU restatement ("port", 1 thread) on the same maze, rank 0, N = 1.
 
 ``--impl reference`` times the reference's own CPU implementation (oracle/_ref = the real
