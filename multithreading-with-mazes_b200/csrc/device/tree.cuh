@@ -850,20 +850,31 @@ LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, long long gwarp, l
         int const j0 = static_cast<int>(it % chunks) * U;
         uint32_t *row = dist + static_cast<long long>(r) * g.cols;
         long long const trow = static_cast<long long>(r / TS) * g.tiles_x;
+        // The field was NOT reset before the flood: what is passable comes from the tile masks (all
+        // passable squares were reached: one tree), everything else becomes INF here.
+        uint64_t w[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            w[u] = j0 + u < g.tiles_x ? lab_ld_ro(p.path + (trow + j0 + u) * TS + (r % TS)) : 0ull;
+        }
         uint32_t v[2 * U];
 #pragma unroll
         for (int u = 0; u < 2 * U; u++) {
             int const c = j0 * TS + lane + 32 * u;
-            v[u] = c < g.cols ? row[c] : INF;
+            bool const pass = (w[u / 2] >> (lane + 32 * (u & 1))) & 1ull;
+            v[u] = pass ? row[c] : INF;
         }
 #pragma unroll
         for (int u = 0; u < 2 * U; u++) {
+            int const c = j0 * TS + lane + 32 * u;
             if (v[u] != INF) {
                 uint32_t const comp = v[u] >> 16;
                 uint32_t const *b = lvl + (trow + j0 + u / 2) * SLOTS;
                 uint32_t const out = (comp == ROOT_COMP ? 0u : b[comp]) + (v[u] & 0xFFFFu);
-                row[j0 * TS + lane + 32 * u] = out;
+                row[c] = out;
                 mx = out > mx ? out : mx;
+            } else if (c < g.cols) {
+                row[c] = INF;
             }
         }
     }
@@ -881,9 +892,8 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
     Tree_ctl *tc = tr.tc;
     Control *ctl = p.ctl;
     if (!tree_live(tc)) {
-        if (tc->dirty == 0) {
-            return; // gave up before anything was written
-        }
+        // the wave takes over: it needs a field of INF and empty visited masks (search_prepare left the
+        // reset of the field to whoever writes it: the fix-up above, or this)
         long long const cells = static_cast<long long>(p.g.rows) * p.g.cols;
         for (long long i = gthread; i < cells; i += nthreads) {
             p.plane[0].dist[i] = INF;

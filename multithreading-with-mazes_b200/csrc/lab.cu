@@ -353,6 +353,7 @@ struct lab_grid {
     uint32_t *d_activated = nullptr;
     Run_desc band_desc{};
     bool band_open = false;
+    bool band_mode = false; // the search being prepared is one band of a sharded one
     // spanning-tree pipeline workspace (allocated on first use)
     Tree tree{};
     bool tree_alloc = false;
@@ -466,6 +467,12 @@ int blocks_for(lab_grid *h, long long warps_wanted, int threads) {
 
 unsigned long long budget_ns() { return static_cast<unsigned long long>(env_ll("LAB_BFS_BUDGET_MS", 20000)) * 1000000ull; }
 
+// The spanning-tree pipeline is tried for single-field searches that have their source in this grid.
+// (not for row bands: lab_band_* runs the tile wave in every band)
+bool tree_may_run(lab_grid const *h, Run_desc const &d) {
+    return !h->band_mode && d.nplanes == 1 && d.src_r[0] >= 0 && env_ll("LAB_TREE", 1) != 0;
+}
+
 // Reset the workspace and pack the grid into tile bit masks (sources forced passable).
 int search_prepare(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass_value) {
     int rc = ensure_planes(h, d.nplanes);
@@ -486,7 +493,9 @@ int search_prepare(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t 
         CU(cudaMemsetAsync(pl.visited, 0, nt * TS * sizeof(uint64_t), s));
         CU(cudaMemsetAsync(pl.edges, 0xFF, (nt + 2 * static_cast<size_t>(g.tiles_x)) * 4 * TS * sizeof(uint32_t), s));
         CU(cudaMemsetAsync(pl.state, 0, nt * sizeof(uint32_t), s));
-        CU(cudaMemsetAsync(pl.dist, 0xFF, cells * sizeof(uint32_t), s));
+        if (!tree_may_run(h, d)) { // (else the tree pipeline's fix-up or gate writes every square of the field)
+            CU(cudaMemsetAsync(pl.dist, 0xFF, cells * sizeof(uint32_t), s));
+        }
     }
     CU(cudaEventRecord(h->ev[EV_PACK0], s));
     k_pack<<<blocks_for(h, static_cast<long long>(g.tiles_y) * TS, 256), 256, 0, s>>>(g, h->squares, h->path, pass_mask, pass_value);
@@ -573,7 +582,7 @@ int ceil_log2(unsigned long long n) {
 int run_tree(lab_grid *h, Run_desc const &d) {
     h->tree_last = Tree_ctl{};
     h->tree_tried = false;
-    if (d.nplanes != 1 || d.src_r[0] < 0 || env_ll("LAB_TREE", 1) == 0) {
+    if (!tree_may_run(h, d)) {
         return LAB_OK;
     }
     int rc = ensure_tree(h);
@@ -638,6 +647,7 @@ int run_tree(lab_grid *h, Run_desc const &d) {
 
 // Reset the workspace, pack the grid, run the persistent search.  Leaves EV_POST0 recorded.
 int run_search(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass_value) {
+    h->band_mode = false;
     int rc = search_prepare(h, d, pass_mask, pass_value);
     if (rc) return rc;
     rc = search_arm(h, d, nullptr, nullptr);
@@ -1198,6 +1208,7 @@ int lab_band_begin(lab_grid *h, int src_r, int src_c) {
         CU(cudaMalloc(&h->ghost_s, static_cast<size_t>(h->g.tiles_x) * sizeof(uint64_t)));
         CU(cudaMalloc(&h->d_activated, sizeof(uint32_t)));
     }
+    h->band_mode = true;
     int const rc = search_prepare(h, d, SQ_PATH | SQ_MEASURE, SQ_PATH);
     h->band_open = rc == LAB_OK;
     return rc;
