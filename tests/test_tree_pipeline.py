@@ -3,6 +3,8 @@ floods.  It must (a) be the path that runs on the reference builders' perfect ma
 the levels of the FIFO search (painters/distance.cc:129-153) and (c) step aside -- leaving the tile wave
 to do the search -- on anything that is not one tree, including mazes whose square / adjacency counts
 LOOK like a tree's.  CPU half: the same kernel bodies on the warp emulator; GPU half: through the C ABI."""
+import os
+
 import numpy as np
 import pytest
 
@@ -146,3 +148,20 @@ def test_gpu_gather_on_a_tree_uses_the_pipeline(lab, O):
     g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
     assert stats["tree_used"] == 1
     assert (after == g_ref).all() and (res.claimed_by == c_ref).all() and paths_equal(res.paths, p_ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("LAB_BIG_TESTS"), reason="north_star headline size: ~3 min of host work; set LAB_BIG_TESTS=1")
+@pytest.mark.parametrize("builder", ["kruskal"])
+def test_gpu_tree_headline_size_32767(lab, O, builder):
+    """BASELINE north_star size, one GPU: bit-exact against the oracle's CPU restatement."""
+    n = 32767
+    maze = lab.build_maze(builder, n, n, seed=0xB2000002)
+    with lab.Grid.from_host(maze) as g:
+        r = g.distance_map()
+        stats = g.stats()
+        t = g.timing()
+    g_ref, d_ref, max_ref, settled_ref = O.distance_map(maze)
+    assert stats["tree_used"] == 1 and r.settled == settled_ref == 2 * 16383 * 16383 - 1 and r.max == max_ref
+    assert (r.dist == d_ref).all()
+    print(f"32767^2 {builder}: max level {r.max}, search {t['search_ms']:.2f} ms, total {t['total_ms']:.2f} ms")
