@@ -91,6 +91,11 @@ struct Control {
     unsigned long long n_activations, n_empty, n_levels, n_rechecks, n_resettles, n_settled, n_pushes, n_direct;
     // SM cycles summed over warps (LAB_PROFILE builds only): loading a tile, the level loop, publishing, idle
     unsigned long long cyc_load, cyc_loop, cyc_publish, cyc_idle, cyc_step, cyc_emit, n_batches;
+    // the open room (device/room.cuh; decided by tree_init_body): the passable squares are exactly the
+    // rectangle [room_r0, room_r1] x [room_c0, room_c1], so plane 0's level of a square is its Manhattan
+    // distance from the source (room_sr, room_sc) and no field has to be searched
+    uint32_t room;
+    uint32_t room_r0, room_r1, room_c0, room_c1, room_sr, room_sc;
 };
 
 struct Params {
@@ -142,18 +147,37 @@ LAB_DEV uint32_t lab_ld_uniform(uint32_t const *p, int lane) {
 }
 LAB_DEV uint32_t lab_min3(uint32_t a, uint32_t b, uint32_t c) { return a < b ? (a < c ? a : c) : (b < c ? b : c); }
 LAB_DEV uint32_t lab_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+LAB_DEV uint32_t lab_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
 // ---------------------------------------------------------------------------------------------
 // pack: Square grid -> one passable bit per square, tile-major.
 // passable  <=>  (square & mask) == value     (solvers: path_bit, bfs_threads.cc:71-72;
 //                                              distance: path_bit set AND measure clear, distance.cc:145-148)
-// One warp-item = 64 squares of one row (lane reads squares lane and lane+32).
+// One warp per row (grid stride), 256 squares per step: every lane loads 16 bytes (8 squares) and makes
+// an 8-bit mask; three shuffles join eight neighbouring masks into the 64 bits of a tile word.  Rows of
+// an odd-sized maze do not start on a 16-byte boundary, so a row is read as  head (the a < 8 squares
+// before the first boundary, one scalar load each) + aligned 16-byte loads, and every word is put
+// together from two pieces: (64 - a bits of this step) | (a bits carried over from the one before).
+LAB_DEV uint32_t pack_mask8(lab_u32x4 v, uint32_t mask2, uint32_t value2) {
+    // halfword h of x passes  <=>  ((x & mask) ^ value) has no bit in that halfword
+    uint32_t const w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t const d = (w[k] & mask2) ^ value2;
+        m |= ((d & 0xFFFFu) == 0 ? 1u : 0u) << (2 * k);
+        m |= ((d >> 16) == 0 ? 1u : 0u) << (2 * k + 1);
+    }
+    return m;
+}
+
 LAB_DEV void pack_body(Geom g, uint16_t const *grid, uint64_t *path, uint16_t mask, uint16_t value,
                        long long gwarp, long long nwarps, int lane) {
-    // one warp per row (grid stride), the row's 64-square words four at a time: 8 independent
-    // 2-byte loads per lane in flight, no division in the loop
-    constexpr int U = 4;
+    constexpr int U = 4; // steps whose loads are in flight together (2 KB per warp)
     int const rows_pad = g.tiles_y * TS;
+    uint32_t const mask2 = static_cast<uint32_t>(mask) * 0x10001u, value2 = static_cast<uint32_t>(value) * 0x10001u;
+    unsigned long long const total = static_cast<unsigned long long>(g.rows) * static_cast<unsigned long long>(g.cols);
+    int const nsteps = (g.tiles_x + 3) / 4; // a step makes four words
     for (long long rr = gwarp; rr < rows_pad; rr += nwarps) {
         int const r = static_cast<int>(rr);
         uint64_t *out = path + (static_cast<long long>(r / TS) * g.tiles_x) * TS + (r % TS);
@@ -163,21 +187,49 @@ LAB_DEV void pack_body(Geom g, uint16_t const *grid, uint64_t *path, uint16_t ma
             }
             continue;
         }
-        uint16_t const *row = grid + static_cast<long long>(r) * g.cols;
-        for (int j0 = 0; j0 < g.tiles_x; j0 += U) {
-            uint16_t a[U], b[U];
+        unsigned long long const row0 = static_cast<unsigned long long>(r) * static_cast<unsigned long long>(g.cols);
+        uint16_t const *row = grid + row0;
+        int a = static_cast<int>(((16u - (reinterpret_cast<uintptr_t>(row) & 15u)) & 15u) >> 1); // squares before the boundary
+        a = a < g.cols ? a : g.cols;
+        // head: bits [0, a) of word 0, parked in the top bits of the carry
+        uint32_t const head = lab_ballot(lane < a && (lab_ld_ro(row + (lane < a ? lane : 0)) & mask) == value);
+        uint64_t carry = a ? static_cast<uint64_t>(head) << (64 - a) : 0ull;
+        for (int s0 = 0; s0 < nsteps; s0 += U) {
+            lab_u32x4 v[U];
+            uint32_t valid[U]; // which of the lane's 8 squares are inside the row
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                int const c0 = (j0 + u) * TS + lane;
-                a[u] = c0 < g.cols ? lab_ld_ro(row + c0) : static_cast<uint16_t>(~value);
-                b[u] = c0 + 32 < g.cols ? lab_ld_ro(row + c0 + 32) : static_cast<uint16_t>(~value);
+                int const c = a + 256 * (s0 + u) + 8 * lane;
+                int const left = g.cols - c;
+                valid[u] = left >= 8 ? 0xFFu : (left > 0 ? (1u << left) - 1u : 0u);
+                v[u] = lab_u32x4{~value2, ~value2, ~value2, ~value2};
+                if (left > 0) {
+                    if (row0 + static_cast<unsigned long long>(c) + 8ull <= total) { // (may run into the next row: masked below)
+                        v[u] = lab_ld_ro_v4(row + c);
+                    } else { // the last few squares of the grid
+                        uint32_t w[4] = {~value2, ~value2, ~value2, ~value2};
+                        for (int k = 0; k < left && k < 8; k++) {
+                            uint32_t const sq = lab_ld_ro(row + c + k);
+                            w[k >> 1] = (k & 1) ? ((w[k >> 1] & 0x0000FFFFu) | (sq << 16)) : ((w[k >> 1] & 0xFFFF0000u) | sq);
+                        }
+                        v[u] = lab_u32x4{w[0], w[1], w[2], w[3]};
+                    }
+                }
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                int const c0 = (j0 + u) * TS + lane;
-                uint64_t const w = lab_ballot64(c0 < g.cols && (a[u] & mask) == value, c0 + 32 < g.cols && (b[u] & mask) == value);
-                if (lane == 0 && j0 + u < g.tiles_x) {
-                    out[static_cast<long long>(j0 + u) * TS] = w;
+                uint32_t x = pack_mask8(v[u], mask2, value2) & valid[u];
+                x |= lab_shfl_down(x, 1) << 8;
+                x |= lab_shfl_down(x, 2) << 16;
+                uint32_t const hi = lab_shfl_down(x, 4);
+                uint64_t const R = static_cast<uint64_t>(x) | (static_cast<uint64_t>(hi) << 32); // squares 8*lane .. 8*lane+63 of the step (lanes 0, 8, 16, 24)
+                uint64_t const before = lab_shfl_up64(R, 8);
+                uint64_t const prev = lane == 0 ? carry : before;
+                carry = lab_shfl64(R, 24);
+                uint64_t const word = a ? ((R << a) | (prev >> (64 - a))) : R;
+                int const j = 4 * (s0 + u) + (lane >> 3);
+                if ((lane & 7) == 0 && j < g.tiles_x) {
+                    out[static_cast<long long>(j) * TS] = word;
                 }
             }
         }

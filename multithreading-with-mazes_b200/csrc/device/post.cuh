@@ -11,6 +11,7 @@
 // exactly the squares whose level in k's field is below the level at which k's game ends.
 #pragma once
 #include "engine.cuh"
+#include "room.cuh"
 
 namespace lab {
 
@@ -93,8 +94,11 @@ LAB_DEV void force_sources_body(Geom g, uint64_t *path, Run_desc d) {
 
 // distance epilogue: measure bit on every visited square + exact count of visited squares.
 // Same row/word item space as pack_body.
-LAB_DEV void measure_body(Geom g, uint16_t *grid, uint64_t const *visited, Result *res, long long gwarp,
+LAB_DEV void measure_body(Geom g, uint16_t *grid, uint64_t const *visited, Control const *ctl, Result *res, long long gwarp,
                           long long nwarps, int lane) {
+    if (ctl->room) {
+        return; // an open room: room_distance_body has set the bits and counted the squares
+    }
     // one warp per row (grid stride); a 64-square word with no visited square costs one 8-byte load
     unsigned long long count = 0;
     constexpr int U = 4; // 64-square words of a row handled together: independent read-modify-writes in flight
@@ -237,6 +241,16 @@ LAB_DEV void paint_body(Params p, uint16_t *grid, Result *res, long long gthread
     for (uint32_t k = 0; k < 4; k++) {
         r[k] = res->rule[k < nr ? k : 0];
     }
+    if (p.ctl->room) { // an open room: no field was searched, the levels are a closed form (room.cuh)
+        Room_rules q{};
+        q.n = nr;
+        for (uint32_t k = 0; k < 4; k++) {
+            q.below[k] = r[k].below;
+            q.bits[k] = r[k].bits;
+        }
+        room_paint_body(p, q, grid, &res->settled, gthread, nthreads);
+        return;
+    }
     uint32_t painted = 0;
     bool const same_plane = nr <= 1 || (r[0].plane == r[1].plane && r[0].plane == r[2].plane && r[0].plane == r[3].plane);
     constexpr int U = 8; // independent loads in flight per thread (a streaming pass: HBM latency x bandwidth)
@@ -291,8 +305,13 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
                        int lane) {
     Geom const &g = p.g;
     uint32_t const *dist = p.plane[plane].dist;
+    bool const room = p.ctl->room != 0; // (single-field games only: the levels are room_level, no field exists)
+    Room const m = room_load(p.ctl);
+    auto level = [&](long long rr, long long cc) {
+        return room ? room_level(m, static_cast<uint32_t>(rr), static_cast<uint32_t>(cc)) : dist[rr * g.cols + cc];
+    };
     long long r = fr, c = fc;
-    uint32_t d = dist[r * g.cols + c];
+    uint32_t d = level(r, c);
     unsigned long long n = 0;
     if (d == INF) {
         if (lane == 0) res->path_len[slot] = 0;
@@ -305,7 +324,7 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
         if (lane < 4) {
             long long const nr = r + dr[lane], nc = c + dc[lane];
             if (nr >= 0 && nr < g.rows && nc >= 0 && nc < g.cols) {
-                hit = dist[nr * g.cols + nc] == d - 1;
+                hit = level(nr, nc) == d - 1;
             }
         }
         uint32_t const m = lab_ballot(hit);
@@ -332,7 +351,7 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
         }
     }
     if (lane == 0) {
-        res->path_len[slot] = first_only ? static_cast<unsigned long long>(dist[static_cast<long long>(fr) * g.cols + fc]) : n;
+        res->path_len[slot] = first_only ? static_cast<unsigned long long>(level(fr, fc)) : n;
     }
 }
 

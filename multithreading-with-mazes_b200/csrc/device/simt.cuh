@@ -28,6 +28,7 @@ LAB_DEV void lab_syncwarp() { __syncwarp(); }
 
 LAB_DEV int lab_ffs64(uint64_t v) { return __ffsll(static_cast<long long>(v)); } // 1-based, 0 if none
 LAB_DEV int lab_popc64(uint64_t v) { return __popcll(v); }
+LAB_DEV int lab_clz64(uint64_t v) { return __clzll(static_cast<long long>(v)); } // 64 if none
 LAB_DEV int lab_ffs32(uint32_t v) { return __ffs(static_cast<int>(v)); } // 1-based, 0 if none
 
 // loads that must observe other SMs' stores (L1 is not coherent inside a persistent kernel)
@@ -47,6 +48,19 @@ LAB_DEV void lab_st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
 LAB_DEV void lab_st_cg(uint64_t *p, uint64_t v) {
     __stcg(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v));
 }
+// 16 bytes at a time (p is 16-byte aligned), streaming: read once / written once, nothing to keep in the caches
+struct lab_u32x4 {
+    uint32_t x, y, z, w;
+};
+LAB_DEV lab_u32x4 lab_ld_stream_v4(void const *p) {
+    uint4 const t = __ldcs(reinterpret_cast<uint4 const *>(p));
+    return {t.x, t.y, t.z, t.w};
+}
+LAB_DEV lab_u32x4 lab_ld_ro_v4(void const *p) { // read-only data
+    uint4 const t = __ldg(reinterpret_cast<uint4 const *>(p));
+    return {t.x, t.y, t.z, t.w};
+}
+LAB_DEV void lab_st_stream_v4(void *p, lab_u32x4 v) { __stcs(reinterpret_cast<uint4 *>(p), make_uint4(v.x, v.y, v.z, v.w)); }
 LAB_DEV void lab_st_volatile(uint32_t *p, uint32_t v) { *reinterpret_cast<uint32_t volatile *>(p) = v; }
 
 LAB_DEV uint32_t lab_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }

@@ -28,6 +28,7 @@
 // masked by measure bits) takes the tile wave of engine.cuh instead; both give identical levels.
 #pragma once
 #include "engine.cuh"
+#include "room.cuh"
 
 namespace lab {
 
@@ -47,6 +48,9 @@ struct Tree_ctl {
     uint32_t used;       // the tree pipeline produced the field (set by gate)
     uint32_t barrier[2]; // grid barriers of the two multi-round kernels (rank, prefix)
     uint32_t dirty;      // the flood has started writing its packed field into the dense level field
+    // bounding box of the passable squares (0x7FFFFFFF - min as a running max, so that the all-zero reset
+    // means "nothing yet"): a box that holds exactly V squares is an OPEN ROOM (device/room.cuh)
+    uint32_t box_r0_inv, box_r1, box_c0_inv, box_c1;
 };
 
 struct Tree {
@@ -77,8 +81,18 @@ LAB_DEV uint32_t tree_twin(Geom const &g, uint32_t a) {
 // V and E.  Warp per tile, grid stride; lane i holds rows 2i, 2i+1.
 LAB_DEV void tree_count_body(Params const &p, Tree const &tr, long long gwarp, long long nwarps, int lane) {
     unsigned long long v = 0, e = 0;
+    uint32_t r0i = 0, r1 = 0, c0i = 0, c1 = 0; // the warp's share of the bounding box (see Tree_ctl)
     for (long long t = gwarp; t < p.g.ntiles; t += nwarps) {
         uint64_t const P0 = lab_ld_ro(p.path + t * TS + 2 * lane), P1 = lab_ld_ro(p.path + t * TS + 2 * lane + 1);
+        if (P0 | P1) {
+            uint32_t const row0 = static_cast<uint32_t>(t / p.g.tiles_x) * TS, col0 = static_cast<uint32_t>(t % p.g.tiles_x) * TS;
+            uint32_t const ra = row0 + static_cast<uint32_t>(2 * lane + (P0 ? 0 : 1)), rb = row0 + static_cast<uint32_t>(2 * lane + (P1 ? 1 : 0));
+            uint32_t const ca = col0 + static_cast<uint32_t>(lab_ffs64(P0 | P1) - 1), cb = col0 + static_cast<uint32_t>(63 - lab_clz64(P0 | P1));
+            r0i = lab_umax(r0i, 0x7FFFFFFFu - ra);
+            r1 = lab_umax(r1, rb);
+            c0i = lab_umax(c0i, 0x7FFFFFFFu - ca);
+            c1 = lab_umax(c1, cb);
+        }
         uint64_t below = lab_shfl_down64(P0, 1); // row 2*lane+2
         if (lane == 31) {
             below = 0;
@@ -91,9 +105,19 @@ LAB_DEV void tree_count_body(Params const &p, Tree const &tr, long long gwarp, l
     }
     uint32_t const vs = lab_reduce_add(static_cast<uint32_t>(v)), es = lab_reduce_add(static_cast<uint32_t>(e));
     uint32_t const vh = lab_reduce_add(static_cast<uint32_t>(v >> 32)), eh = lab_reduce_add(static_cast<uint32_t>(e >> 32));
+    r0i = lab_reduce_max(r0i);
+    r1 = lab_reduce_max(r1);
+    c0i = lab_reduce_max(c0i);
+    c1 = lab_reduce_max(c1);
     if (lane == 0) {
         lab_atomic_add(reinterpret_cast<uint64_t *>(&tr.tc->V), (static_cast<uint64_t>(vh) << 32) + vs);
         lab_atomic_add(reinterpret_cast<uint64_t *>(&tr.tc->E), (static_cast<uint64_t>(eh) << 32) + es);
+        if (r0i) { // (some square of this warp's tiles is passable)
+            lab_atomic_max(&tr.tc->box_r0_inv, r0i);
+            lab_atomic_max(&tr.tc->box_r1, r1);
+            lab_atomic_max(&tr.tc->box_c0_inv, c0i);
+            lab_atomic_max(&tr.tc->box_c1, c1);
+        }
     }
 }
 
@@ -408,9 +432,27 @@ LAB_DEV void tree_walk_body(Params const &p, Tree const &tr, int lane, uint64_t 
 }
 
 // One thread, after the count and before the walk: can it be a tree at all?  And the two list ends.
-LAB_DEV void tree_init_body(Tree const &tr) {
+LAB_DEV void tree_init_body(Params const &p, Tree const &tr) {
     uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
-    tr.tc->ok = (tr.tc->V >= 2 && tr.tc->E + 1 == tr.tc->V) ? 1u : 0u; // a tree has squares - 1 adjacent pairs
+    Tree_ctl *tc = tr.tc;
+    tc->ok = (tc->V >= 2 && tc->E + 1 == tc->V) ? 1u : 0u; // a tree has squares - 1 adjacent pairs
+    // Not a tree, but the bounding box of the passable squares holds nothing else: an open room (the
+    // reference's arena builder).  Levels are a closed form there (device/room.cuh); the source is one of
+    // the passable squares (force_sources_body), so it lies inside.
+    if (!tc->ok && tc->V >= 1) {
+        uint32_t const r0 = 0x7FFFFFFFu - tc->box_r0_inv, c0 = 0x7FFFFFFFu - tc->box_c0_inv;
+        unsigned long long const area = static_cast<unsigned long long>(tc->box_r1 - r0 + 1u) * (tc->box_c1 - c0 + 1u);
+        if (area == tc->V && p.ctl->src_tile[0] != 0xFFFFFFFFu) {
+            Control *ctl = p.ctl;
+            ctl->room_r0 = r0;
+            ctl->room_r1 = tc->box_r1;
+            ctl->room_c0 = c0;
+            ctl->room_c1 = tc->box_c1;
+            ctl->room_sr = (ctl->src_tile[0] / static_cast<uint32_t>(p.g.tiles_x)) * TS + (ctl->src_rc[0] >> 8);
+            ctl->room_sc = (ctl->src_tile[0] % static_cast<uint32_t>(p.g.tiles_x)) * TS + (ctl->src_rc[0] & 0xFFu);
+            ctl->room = 1u;
+        }
+    }
     tr.succ0[ROOT] = END;
     tr.succ0[END] = END;
     for (int b = 0; b < 2; b++) {
@@ -891,6 +933,32 @@ LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, long long gwarp, l
 LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, long long nthreads) {
     Tree_ctl *tc = tr.tc;
     Control *ctl = p.ctl;
+    if (ctl->room) {
+        // An open room: nothing to search.  The levels are a closed form (room.cuh): the distance map's
+        // fused pass has written them (and the measure bits: `visited` stays empty for measure_body), the
+        // solvers paint straight from the formula and never materialise the field.
+        if (gthread != 0) {
+            return;
+        }
+        Room const m = room_load(ctl);
+        for (uint32_t j = 0; j < ctl->n_targets; j++) {
+            unsigned long long const cell = ctl->target_cell[j];
+            ctl->target_val[j] = room_level(m, static_cast<uint32_t>(cell / static_cast<unsigned long long>(p.g.cols)),
+                                            static_cast<uint32_t>(cell % static_cast<unsigned long long>(p.g.cols)));
+        }
+        uint32_t const far_r = lab_umax(m.sr - m.r0, m.r1 - m.sr), far_c = lab_umax(m.sc - m.c0, m.c1 - m.sc);
+        ctl->max_level = far_r + far_c; // the farthest corner of the box
+        for (unsigned long long q = 0; q < ctl->tail; q++) {
+            p.queue[q & p.qmask] = Q_EMPTY;
+        }
+        p.plane[0].state[ctl->src_tile[0]] = 0;
+        ctl->tail = 0;
+        ctl->pending = 0;
+        ctl->done = 1;
+        ctl->n_settled = tc->V;
+        tc->used = 2;
+        return;
+    }
     if (!tree_live(tc)) {
         // the wave takes over: it needs a field of INF and empty visited masks (search_prepare left the
         // reset of the field to whoever writes it: the fix-up above, or this)

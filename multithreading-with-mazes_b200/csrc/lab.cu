@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(128, 3) k_bfs_tiles(Params p) {
 
 // ---- spanning-tree pipeline (device/tree.cuh) ----
 __global__ void __launch_bounds__(256) k_tree_count(Params p, Tree tr) { tree_count_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
-__global__ void k_tree_init(Tree tr) { tree_init_body(tr); }
+__global__ void k_tree_init(Params p, Tree tr) { tree_init_body(p, tr); }
 __global__ void __launch_bounds__(128) k_tree_walk(Params p, Tree tr) {
     __shared__ __align__(16) uint64_t sm[4][WALK_U64];
     tree_walk_body(p, tr, lane_id(), sm[threadIdx.x >> 5]);
@@ -184,12 +184,17 @@ __global__ void __launch_bounds__(128) k_tree_flood(Params p, Tree tr) {
     tree_flood_body(p, tr, lane_id(), flood_sm + static_cast<size_t>(threadIdx.x >> 5) * FLOOD_U64);
 }
 __global__ void __launch_bounds__(256) k_tree_fixup(Params p, Tree tr) { tree_fixup_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
+// the open room (device/room.cuh): the whole distance map in one streaming pass
+__global__ void __launch_bounds__(256) k_room_distance(Params p, uint16_t *grid, Result *res) {
+    room_distance_body(p, grid, &res->settled, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+                       static_cast<long long>(gridDim.x) * blockDim.x);
+}
 __global__ void __launch_bounds__(256) k_tree_gate(Params p, Tree tr) {
     tree_gate_body(p, tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
 }
 
-__global__ void __launch_bounds__(256) k_measure(Geom g, uint16_t *grid, uint64_t const *visited, Result *res) {
-    measure_body(g, grid, visited, res, gwarp_id(), nwarps_total(), lane_id());
+__global__ void __launch_bounds__(256) k_measure(Geom g, uint16_t *grid, uint64_t const *visited, Control const *ctl, Result *res) {
+    measure_body(g, grid, visited, ctl, res, gwarp_id(), nwarps_total(), lane_id());
 }
 
 __global__ void k_resolve(Params p, Run_desc d, Result *res, int32_t const *finish_rc) {
@@ -605,7 +610,7 @@ int run_tree(lab_grid *h, Run_desc const &d) {
         }
     };
     mark();
-    k_tree_init<<<1, 1, 0, s>>>(tr);
+    k_tree_init<<<1, 1, 0, s>>>(p, tr);
     int const walk_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_walk_per_sm);
     k_tree_walk<<<walk_blocks, 128, 0, s>>>(p, tr);
     TRACE("k_tree_walk", s);
@@ -636,6 +641,11 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, tr);
     TRACE("k_tree_fixup", s);
     mark();
+    if (d.game == GAME_DISTANCE) { // (the solvers paint an open room straight from the closed form: k_paint)
+        k_room_distance<<<h->sm_count * 8, 256, 0, s>>>(p, h->squares, h->res);
+        TRACE("k_room_distance", s);
+        h->launches += 1;
+    }
     k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, tr);
     TRACE("k_tree_gate", s);
     mark();
@@ -994,7 +1004,7 @@ int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t 
     TRACE("k_resolve", s);
     k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
     TRACE("k_max_level", s);
-    k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
+    k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->ctl, h->res);
     TRACE("k_measure", s);
     h->launches += 3;
     CU(cudaGetLastError());
@@ -1285,7 +1295,7 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
     Params p = make_params(h, 1);
     k_resolve<<<1, 1, 0, s>>>(p, h->band_desc, h->res, h->d_finish_rc);
     k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
-    k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->res);
+    k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->ctl, h->res);
     CU(cudaGetLastError());
     h->band_open = false;
     int const rc = finish_run(h);

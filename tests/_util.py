@@ -59,9 +59,13 @@ class Emu:
     def _p(a):
         return a.ctypes.data_as(ctypes.c_void_p)
 
-    def distance(self, grid, start=None, nwarps=4, sched=0):
+    def distance(self, grid, start=None, nwarps=4, sched=0, misalign=0):
         rows, cols = grid.shape
-        g = np.ascontiguousarray(grid, np.uint16).copy()
+        # misalign: the Square array starts that many squares past a 16-byte boundary (a caller's sub-view)
+        buf = np.zeros(rows * cols + 16, np.uint16)
+        off = (-(buf.ctypes.data // 2) % 8 + misalign) % 8 if misalign else 0
+        g = buf[off : off + rows * cols].reshape(rows, cols) if misalign else np.ascontiguousarray(grid, np.uint16).copy()
+        g[...] = grid
         d = np.zeros((rows, cols), np.uint32)
         mx, st = ctypes.c_uint64(), ctypes.c_uint64()
         stats = np.zeros(8, np.uint64)

@@ -17,7 +17,7 @@ namespace {
 
 struct Workspace {
     Geom g;
-    std::vector<uint16_t> *grid;
+    uint16_t *grid_ptr = nullptr;
     std::vector<uint64_t> path, cross;
     std::vector<uint64_t> visited[MAX_PLANES];
     std::vector<uint32_t> edges[MAX_PLANES], state[MAX_PLANES], dist[MAX_PLANES];
@@ -50,7 +50,7 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
     tr.tc = &tc;
     tr.nslots = static_cast<uint32_t>(nt * SLOTS);
     simt::launch(nwarps, [&](int wid, int lane) { tree_count_body(p, tr, wid, nwarps, lane); });
-    tree_init_body(tr);
+    tree_init_body(p, tr);
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
     std::vector<uint64_t> sm(static_cast<size_t>(nwarps) * SM);
     simt::launch(nwarps, [&](int wid, int lane) { tree_walk_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * SM); }, sched_seed);
@@ -67,6 +67,9 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
         simt::launch(nwarps, [&](int wid, int lane) { tree_prefix_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
     }
     simt::launch(nwarps, [&](int wid, int lane) { tree_fixup_body(p, tr, wid, nwarps, lane); });
+    if (d.game == GAME_DISTANCE) {
+        simt::launch(nwarps, [&](int wid, int lane) { room_distance_body(p, w.grid_ptr, &w.res.settled, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    }
     simt::launch(nwarps, [&](int wid, int lane) { tree_gate_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
     g_tree_last = tc;
 }
@@ -90,6 +93,7 @@ Params make_params(Workspace &w, int nplanes) {
 int search(Workspace &w, uint16_t *grid, int rows, int cols, Run_desc const &d, uint16_t mask, uint16_t value,
            int nwarps, unsigned sched_seed) {
     Geom &g = w.g;
+    w.grid_ptr = grid;
     g.rows = rows;
     g.cols = cols;
     g.tiles_y = (rows + TS - 1) / TS;
@@ -170,7 +174,7 @@ int emu_distance(int rows, int cols, uint16_t *grid, int sr, int sc, uint32_t *d
     simt::launch(nwarps, [&](int wid, int lane) {
         max_level_body(w.g, w.dist[0].data(), &w.ctl, &w.res, static_cast<long long>(wid) * 32 + lane, nthreads);
     });
-    simt::launch(nwarps, [&](int wid, int lane) { measure_body(w.g, grid, w.visited[0].data(), &w.res, wid, nwarps, lane); });
+    simt::launch(nwarps, [&](int wid, int lane) { measure_body(w.g, grid, w.visited[0].data(), &w.ctl, &w.res, wid, nwarps, lane); });
     std::memcpy(dist_out, w.dist[0].data(), w.dist[0].size() * sizeof(uint32_t));
     *max_out = w.res.max_level;
     *settled_out = w.res.settled;

@@ -13,6 +13,7 @@
 
 #include <chrono>
 #include <cstdint>
+#include <cstring>
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
@@ -215,6 +216,7 @@ LAB_DEV void lab_syncwarp() { (void)simt::exchange(0); }
 
 LAB_DEV int lab_ffs64(uint64_t v) { return v ? __builtin_ctzll(v) + 1 : 0; }
 LAB_DEV int lab_popc64(uint64_t v) { return __builtin_popcountll(v); }
+LAB_DEV int lab_clz64(uint64_t v) { return v ? __builtin_clzll(v) : 64; }
 LAB_DEV int lab_ffs32(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 
 template <class T> LAB_DEV T lab_ld_cg(T const *p) {
@@ -227,6 +229,16 @@ template <class T> LAB_DEV T lab_ld_volatile(T const *p) {
 }
 template <class T> LAB_DEV T lab_ld_ro(T const *p) { return *p; }
 template <class T> LAB_DEV void lab_st_cg(T *p, typename std::common_type<T>::type v) { *p = v; }
+struct lab_u32x4 {
+    uint32_t x, y, z, w;
+};
+LAB_DEV lab_u32x4 lab_ld_stream_v4(void const *p) {
+    lab_u32x4 v;
+    std::memcpy(&v, p, sizeof v);
+    return v;
+}
+LAB_DEV lab_u32x4 lab_ld_ro_v4(void const *p) { return lab_ld_stream_v4(p); }
+LAB_DEV void lab_st_stream_v4(void *p, lab_u32x4 v) { std::memcpy(p, &v, sizeof v); }
 LAB_DEV void lab_st_volatile(uint32_t *p, uint32_t v) { *p = v; }
 
 template <class T> LAB_DEV T lab_atomic_add(T *p, typename std::common_type<T>::type v) {

@@ -78,5 +78,12 @@ def test_canonical_model_brackets_the_real_threads(ref, builder):
             d = O.bfs_levels(placed, int(s[0]), int(s[1]))
             Dmax = max(int(d[r, c]) for r, c in fin)
             assert not ((real & O.PAINT_MASK) != 0)[d > Dmax].any()
-            for r, c in fin:  # every finish ends up claimed (non-zero cache nibble)
-                assert real[r, c] & O.CACHE_MASK
+            # every finish ends up claimed (non-zero cache nibble) -- unless two of the reference's threads
+            # pass its unsynchronised check-then-or at one finish together (bfs_threads.cc:158-160) and both
+            # stop there, which leaves another finish unclaimed: rare, so a few re-runs must show a clean game
+            for attempt in range(5):
+                if all(real[r, c] & O.CACHE_MASK for r, c in fin):
+                    break
+                real = O.ref_game(O.GATHER, grid, seed + 200)
+            else:
+                raise AssertionError("the reference left a finish unclaimed in five games in a row")
