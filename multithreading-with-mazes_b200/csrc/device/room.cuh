@@ -83,16 +83,65 @@ LAB_DEV uint32_t room_stream(Params const &p, Room const &m, Room_rules const &q
             uint32_t w[4] = {in[j].x, in[j].y, in[j].z, in[j].w};
             uint32_t lv[8];
             uint32_t any = 0;
+            // Nearly every chunk lies in one row and wholly inside the room: its levels are dr + |d0 + u|, and
+            // (solvers) usually all of them on the same side of every rule's threshold.
+            if (c + 8u <= cols && r - m.r0 <= m.r1 - m.r0 && c >= m.c0 && c + 7u <= m.c1) {
+                uint32_t const dr = r > m.sr ? r - m.sr : m.sr - r;
+                int const d0 = static_cast<int>(c) - static_cast<int>(m.sc);
+                if (MODE == 0) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                lv[u] = room_level(m, r, c);
-                uint32_t const b = MODE == 0 ? (lv[u] != INF ? static_cast<uint32_t>(SQ_MEASURE) : 0u) : room_rule_bits(q, lv[u]);
-                w[u >> 1] |= b << (16 * (u & 1));
-                any |= b;
-                marked += b != 0;
-                if (++c == cols) {
-                    c = 0;
-                    r++;
+                    for (int u = 0; u < 8; u++) {
+                        int const d = d0 + u;
+                        lv[u] = dr + static_cast<uint32_t>(d < 0 ? -d : d);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        w[h] |= static_cast<uint32_t>(SQ_MEASURE) * 0x10001u;
+                    }
+                    any = 1;
+                    marked += 8;
+                } else {
+                    uint32_t const e0 = static_cast<uint32_t>(d0 < 0 ? -d0 : d0), e7 = static_cast<uint32_t>(d0 + 7 < 0 ? -(d0 + 7) : d0 + 7);
+                    uint32_t const hi = dr + lab_umax(e0, e7), lo = (d0 <= 0 && d0 + 7 >= 0) ? dr : dr + lab_umin(e0, e7);
+                    uint32_t all = 0;
+                    bool mixed = false;
+#pragma unroll
+                    for (uint32_t rk = 0; rk < 4; rk++) {
+                        if (rk < q.n) {
+                            all |= hi < q.below[rk] ? q.bits[rk] : 0u;
+                            mixed |= hi >= q.below[rk] && lo < q.below[rk];
+                        }
+                    }
+                    if (!mixed) {
+#pragma unroll
+                        for (int h = 0; h < 4; h++) {
+                            w[h] |= all * 0x10001u;
+                        }
+                        any = all;
+                        marked += all ? 8u : 0u;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            int const d = d0 + u;
+                            uint32_t const b = room_rule_bits(q, dr + static_cast<uint32_t>(d < 0 ? -d : d));
+                            w[u >> 1] |= b << (16 * (u & 1));
+                            any |= b;
+                            marked += b != 0;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    lv[u] = room_level(m, r, c);
+                    uint32_t const b = MODE == 0 ? (lv[u] != INF ? static_cast<uint32_t>(SQ_MEASURE) : 0u) : room_rule_bits(q, lv[u]);
+                    w[u >> 1] |= b << (16 * (u & 1));
+                    any |= b;
+                    marked += b != 0;
+                    if (++c == cols) {
+                        c = 0;
+                        r++;
+                    }
                 }
             }
             if (any) {
