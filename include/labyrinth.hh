@@ -343,33 +343,32 @@ inline void animate_corners(Maze::Maze &maze, Speed::Speed) { corners(maze); }
 // ------------------------------------------------------------------------------------- painters
 namespace Distance {
 
-// painters/distance.cc:129-156: the BFS runs on the GPU; the painter (distance.cc:45-70) is the
-// reference's colour arithmetic on the returned levels.
+// painters/distance.cc:129-156: the BFS and the painter's colour arithmetic (distance.cc:45-70) both run on
+// the GPU (lab_distance_map, lab_distance_paint); what is left here is the reference's printing.
 inline void paint_distance_from_center(Maze::Maze &maze) {
     int const rows = maze.row_size(), cols = maze.col_size();
-    std::vector<uint32_t> levels(static_cast<size_t>(rows) * cols);
+    std::vector<uint32_t> pixels;
     uint64_t max = 0, settled = 0;
+    std::mt19937 rng(Lab::device_seed());
+    std::uniform_int_distribution<int> uid(0, 2);
+    int const choice = uid(rng); // (drawn whether or not anything is printed: the same RNG stream either way)
     {
         Lab::Device_maze d(maze);
         lab_point const s = lab_distance_start(rows, cols);
-        Lab::check(lab_distance_map(d.g, s.row, s.col, levels.data(), &max, &settled), "lab_distance_map");
+        Lab::check(lab_distance_map(d.g, s.row, s.col, nullptr, &max, &settled), "lab_distance_map");
+        if (!Lab::g_quiet) {
+            pixels.resize(static_cast<size_t>(rows) * cols);
+            Lab::check(lab_distance_paint(d.g, choice, pixels.data()), "lab_distance_paint");
+        }
         d.download();
     }
     if (Lab::g_quiet) return;
-    std::mt19937 rng(Lab::device_seed());
-    std::uniform_int_distribution<int> uid(0, 2);
-    int const choice = uid(rng);
     for (int r = 0; r < rows; r++) {
         for (int c = 0; c < cols; c++) {
             std::cout << "\033[" << r + 1 << ";" << c + 1 << "f";
-            uint32_t const lv = levels[static_cast<size_t>(r) * cols + c];
-            if (lv != LAB_INF) {
-                auto const intensity = static_cast<double>(max - lv) / static_cast<double>(max);
-                auto const dark = static_cast<uint8_t>(255.0 * intensity);
-                auto const bright = static_cast<uint8_t>(128) + static_cast<uint8_t>(127.0 * intensity);
-                uint16_t rgb[3] = {dark, dark, dark};
-                rgb[choice] = static_cast<uint16_t>(bright);
-                std::cout << "\033[38;2;" << rgb[0] << ";" << rgb[1] << ";" << rgb[2] << "m█\033[0m";
+            uint32_t const px = pixels[static_cast<size_t>(r) * cols + c];
+            if (px >> 24) {
+                std::cout << "\033[38;2;" << (px & 0xFF) << ";" << ((px >> 8) & 0xFF) << ";" << ((px >> 16) & 0xFF) << "m█\033[0m";
             } else {
                 std::cout << Sutil::wall_styles.at(maze.style_index() * 16 + (maze[r][c].load() & Maze::wall_mask));
             }

@@ -108,10 +108,24 @@ int lab_distance_map(lab_grid *g, int sr, int sc, uint32_t *dist_host, uint64_t 
                      uint64_t *settled_out);
 /* The reference's start square for a rows x cols maze (distance.cc:131-134). */
 lab_point lab_distance_start(int rows, int cols);
-/* Device pointer to plane k's level field of the last search (rows*cols uint32), or NULL. */
+/* Device pointer to plane k's level field (rows*cols uint32), or NULL.  It holds the last
+ * lab_distance_map's levels; the solvers use the fields as scratch (bounded searches leave squares
+ * beyond the end of the game at LAB_INF; in an open room -- csrc/device/room.cuh -- no field is written). */
 void *lab_levels_device(lab_grid *g, int plane);
 /* Use caller-owned device memory (rows*cols uint32) as plane k's level field from now on. */
 int lab_levels_bind(lab_grid *g, int plane, void *device_levels);
+
+/* ---- Distance painter (painters/distance.cc:45-70, `painter`) -------------------------------- */
+/* The colour the reference prints for every square of the last lab_distance_map, computed on the
+ * device with the reference's double arithmetic: intensity = double(max - level) / double(max),
+ * dark = uint8(255.0 * intensity), bright = 128 + uint8(127.0 * intensity); `channel` (0 red, 1 green,
+ * 2 blue: the reference draws it at random once per picture, :47-49) gets bright, the other two dark.
+ * One pixel per square: R | G << 8 | B << 16 | 0xFF << 24; 0 where the reference prints a wall glyph
+ * (no map entry).  pixels_host: NULL or rows*cols uint32 (copied D2H).  The pixels stay resident
+ * (lab_pixels_device); lab_pixels_bind makes the painter write into caller-owned device memory. */
+int lab_distance_paint(lab_grid *g, int channel, uint32_t *pixels_host);
+void *lab_pixels_device(lab_grid *g);
+int lab_pixels_bind(lab_grid *g, void *device_pixels);
 
 /* ---- Bfs::hunt / gather / corners, thread part (solvers/bfs_threads.cc:35-85,144-185) --------- */
 /* The caller has placed start_bit / finish_bit (and carved the centre for corners) exactly as

@@ -31,6 +31,7 @@ ABI_SYMBOLS = (
     "lab_grid_create", "lab_grid_create_on_device", "lab_grid_upload", "lab_grid_download", "lab_grid_destroy",
     "lab_grid_set_stream", "lab_grid_device_squares", "lab_grid_rows", "lab_grid_cols", "lab_grid_or_bits",
     "lab_grid_and_bits", "lab_distance_map", "lab_distance_start", "lab_levels_device", "lab_levels_bind",
+    "lab_distance_paint", "lab_pixels_device", "lab_pixels_bind",
     "lab_bfs_hunt", "lab_bfs_gather", "lab_bfs_corners", "lab_last_painted", "lab_last_timing", "lab_last_stats",
     "lab_last_error", "lab_pick_random_point", "lab_set_corner_starts", "lab_place_hunt", "lab_place_gather",
     "lab_place_corners", "lab_build_maze", "lab_device_info",
@@ -82,6 +83,7 @@ def lib():
         L.lab_last_error.restype = c_char_p
         L.lab_grid_device_squares.restype = c_void_p
         L.lab_levels_device.restype = c_void_p
+        L.lab_pixels_device.restype = c_void_p
         L.lab_last_painted.restype = c_uint64
         L.lab_distance_start.restype = Point
         L.lab_grid_create.argtypes = [c_int, c_int, c_void_p, POINTER(c_void_p)]
@@ -97,6 +99,9 @@ def lib():
         L.lab_distance_start.argtypes = [c_int, c_int]
         L.lab_levels_device.argtypes = [c_void_p, c_int]
         L.lab_levels_bind.argtypes = [c_void_p, c_int, c_void_p]
+        L.lab_distance_paint.argtypes = [c_void_p, c_int, c_void_p]
+        L.lab_pixels_device.argtypes = [c_void_p]
+        L.lab_pixels_bind.argtypes = [c_void_p, c_void_p]
         L.lab_bfs_hunt.argtypes = [c_void_p, Point, Point, POINTER(c_int32), c_void_p, c_uint64, POINTER(c_uint64)]
         L.lab_bfs_gather.argtypes = [c_void_p, Point, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]
         L.lab_bfs_corners.argtypes = [c_void_p, c_void_p, Point, POINTER(c_int32), c_void_p, c_uint64, POINTER(c_uint64)]
@@ -300,6 +305,24 @@ class Grid:
             ptr = _np_ptr(dist)
         _check(lib().lab_distance_map(self._h, sr, sc, ptr, byref(mx), byref(st)))
         return DistanceResult(mx.value, st.value, dist)
+
+    # -- Distance painter (painters/distance.cc:45-70): one R | G<<8 | B<<16 | 0xFF<<24 pixel per map square, 0 = wall glyph
+    def paint(self, channel: int, want_pixels: bool = True, pixels_host_ptr: Optional[int] = None) -> Optional[np.ndarray]:
+        px = None
+        ptr = None
+        if pixels_host_ptr is not None:
+            ptr = c_void_p(pixels_host_ptr)
+        elif want_pixels:
+            px = np.empty((self.rows, self.cols), np.uint32)
+            ptr = _np_ptr(px)
+        _check(lib().lab_distance_paint(self._h, channel, ptr))
+        return px
+
+    def pixels_device(self) -> int:
+        return int(lib().lab_pixels_device(self._h) or 0)
+
+    def bind_pixels(self, ptr: int) -> None:
+        _check(lib().lab_pixels_bind(self._h, c_void_p(ptr)))
 
     # -- Bfs::hunt / gather / corners, thread part
     def hunt(self, start, finish, want_path: bool = True) -> SolveResult:

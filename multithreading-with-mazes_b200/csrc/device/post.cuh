@@ -376,6 +376,60 @@ LAB_DEV void gather_fixup_body(Geom g, uint16_t *grid, Result const *res, int32_
 
 
 // ---------------------------------------------------------------------------------------------
+// The heat map (painters/distance.cc:45-70, `painter`): the colour of every square of the distance map.
+//   intensity = double(max - level) / double(max);  dark = uint8(255.0 * intensity);
+//   bright = 128 + uint8(127.0 * intensity);  one channel (the reference draws it once per picture,
+//   `channel` here) gets bright, the other two dark.
+// Same IEEE double arithmetic as the reference, evaluated per square (div.rn.f64 / mul.rn.f64 and a
+// truncating conversion: no fused or approximate operation is involved).  One 32-bit pixel per square:
+// R | G << 8 | B << 16 | 0xFF << 24; squares without a map entry (the reference prints a wall glyph
+// there) are 0.  max == 0 (a map of the start square alone): 0.0 / 0.0, which the reference's x86 casts
+// turn into dark 0, bright 128.  Streaming, 4 squares per thread and step: 4 B read + 4 B written per square.
+LAB_DEV uint32_t heat_pixel(uint32_t level, uint32_t max, double dmax, int channel) {
+    if (level == INF) {
+        return 0u;
+    }
+    uint32_t dark = 0, bright = 128;
+    if (max != 0) {
+        double const intensity = static_cast<double>(max - level) / dmax;
+        dark = static_cast<uint32_t>(255.0 * intensity) & 0xFFu;
+        bright = 128u + (static_cast<uint32_t>(127.0 * intensity) & 0xFFu);
+    }
+    uint32_t const grey = dark * 0x010101u;
+    return ((grey & ~(0xFFu << (8 * channel))) | (bright << (8 * channel))) | 0xFF000000u;
+}
+
+LAB_DEV void heatmap_body(Geom g, uint32_t const *dist, Result const *res, int channel, uint32_t *pixels, long long gthread,
+                          long long nthreads) {
+    unsigned long long const n = static_cast<unsigned long long>(g.rows) * static_cast<unsigned long long>(g.cols);
+    uint32_t const max = static_cast<uint32_t>(res->max_level);
+    double const dmax = static_cast<double>(res->max_level);
+    bool const aligned = ((reinterpret_cast<uintptr_t>(dist) | reinterpret_cast<uintptr_t>(pixels)) & 15u) == 0;
+    unsigned long long const nvec = aligned ? n / 4 : 0;
+    constexpr int U = 2;
+    unsigned long long const stride = static_cast<unsigned long long>(nthreads);
+    for (unsigned long long k0 = static_cast<unsigned long long>(gthread); k0 < nvec; k0 += stride * U) {
+        lab_u32x4 in[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            unsigned long long const k = k0 + j * stride;
+            in[j] = k < nvec ? lab_ld_stream_v4(dist + k * 4) : lab_u32x4{INF, INF, INF, INF};
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            unsigned long long const k = k0 + j * stride;
+            if (k < nvec) {
+                lab_st_stream_v4(pixels + k * 4, {heat_pixel(in[j].x, max, dmax, channel), heat_pixel(in[j].y, max, dmax, channel),
+                                                  heat_pixel(in[j].z, max, dmax, channel), heat_pixel(in[j].w, max, dmax, channel)});
+            }
+        }
+    }
+    for (unsigned long long i = nvec * 4 + static_cast<unsigned long long>(gthread); i < n; i += stride) {
+        pixels[i] = heat_pixel(dist[i], max, dmax, channel);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row bands (one band of a taller maze per GPU).  Between two local searches the ranks exchange
 // the levels of their first / last ROW; these bodies translate between those plain rows
 // (tiles_x*64 entries) and the tile-major structures of one band.

@@ -197,6 +197,11 @@ __global__ void __launch_bounds__(256) k_measure(Geom g, uint16_t *grid, uint64_
     measure_body(g, grid, visited, ctl, res, gwarp_id(), nwarps_total(), lane_id());
 }
 
+__global__ void __launch_bounds__(256) k_heatmap(Geom g, uint32_t const *dist, Result const *res, int channel, uint32_t *pixels) {
+    heatmap_body(g, dist, res, channel, pixels, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+                 static_cast<long long>(gridDim.x) * blockDim.x);
+}
+
 __global__ void k_resolve(Params p, Run_desc d, Result *res, int32_t const *finish_rc) {
     resolve_body(p, d, res, finish_rc);
 }
@@ -342,6 +347,9 @@ struct lab_grid {
     int32_t *d_front_rc = nullptr;  // 4 (r,c)
     int32_t *d_paths = nullptr;     // 4 * path_cap (r,c)
     unsigned long long path_cap = 0;
+    uint32_t *pixels = nullptr; // heat map of the last distance map (lab_distance_paint), rows*cols
+    bool owns_pixels = false;
+    bool have_map = false;      // plane 0 holds a finished distance map
     int32_t *d_cells = nullptr; // scratch for or_bits
     uint16_t *d_bits = nullptr;
     cudaStream_t stream = nullptr;
@@ -860,6 +868,9 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->d_finish_rc);
     cudaFree(h->d_front_rc);
     cudaFree(h->d_paths);
+    if (h->owns_pixels) {
+        cudaFree(h->pixels);
+    }
     cudaFree(h->d_cells);
     cudaFree(h->d_bits);
     cudaFree(h->ghost_n);
@@ -1012,6 +1023,7 @@ int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t 
     if (rc) {
         return rc;
     }
+    h->have_map = true;
     if (max_out) *max_out = h->last.max_level;
     if (settled_out) *settled_out = h->last.settled;
     if (dist_host) {
@@ -1025,8 +1037,49 @@ int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t 
     return LAB_OK;
 }
 
+int lab_distance_paint(lab_grid *h, int channel, uint32_t *pixels_host) {
+    if (!h) {
+        return fail(LAB_ERR_ARG, "null grid");
+    }
+    if (channel < 0 || channel > 2) {
+        return fail(LAB_ERR_ARG, "colour channel %d (0 red, 1 green, 2 blue)", channel);
+    }
+    if (!h->have_map) {
+        return fail(LAB_ERR_ARG, "no distance map to paint: call lab_distance_map first");
+    }
+    size_t const bytes = static_cast<size_t>(h->g.rows) * h->g.cols * sizeof(uint32_t);
+    if (!h->pixels) {
+        CU(cudaMalloc(&h->pixels, bytes));
+        h->owns_pixels = true;
+    }
+    cudaStream_t s = h->stream;
+    k_heatmap<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->res, channel, h->pixels);
+    TRACE("k_heatmap", s);
+    CU(cudaGetLastError());
+    if (pixels_host) {
+        CU(cudaMemcpyAsync(pixels_host, h->pixels, bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    return LAB_OK;
+}
+
+void *lab_pixels_device(lab_grid *h) { return h ? h->pixels : nullptr; }
+
+int lab_pixels_bind(lab_grid *h, void *device_pixels) {
+    if (!h || !device_pixels) {
+        return fail(LAB_ERR_ARG, "null grid or pixel buffer");
+    }
+    if (h->owns_pixels && h->pixels) {
+        CU(cudaFree(h->pixels));
+    }
+    h->pixels = static_cast<uint32_t *>(device_pixels);
+    h->owns_pixels = false;
+    return LAB_OK;
+}
+
 static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finishes, int nfinish, bool want_paths,
                          uint64_t path_cap) {
+    h->have_map = false; // (plane 0 is about to be reused, or -- in an open room -- not written at all)
     int32_t frc[8] = {0};
     for (int i = 0; i < nfinish; i++) {
         frc[2 * i] = finishes[i].row;

@@ -182,6 +182,18 @@ int emu_distance(int rows, int cols, uint16_t *grid, int sr, int sc, uint32_t *d
     return 0;
 }
 
+// The heat map of a level field (post.cuh heatmap_body), as lab_distance_paint runs it.
+int emu_heatmap(int rows, int cols, uint32_t const *dist, uint64_t max, int channel, uint32_t *pixels, int nwarps) {
+    Geom g{};
+    g.rows = rows;
+    g.cols = cols;
+    Result res{};
+    res.max_level = max;
+    long long const nthreads = static_cast<long long>(nwarps) * 32;
+    simt::launch(nwarps, [&](int wid, int lane) { heatmap_body(g, dist, &res, channel, pixels, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    return 0;
+}
+
 // game: 1 hunt, 2 gather, 3 corners.  starts: 4 (r,c) (hunt/gather use the first).  finishes: 4 (r,c)
 // (hunt/corners use the first).  paths_out: 4 * max_path (r,c).
 int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *starts, int32_t const *finishes,
