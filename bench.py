@@ -345,12 +345,14 @@ def ours_bands(args, lab, dist, torch, world, rank, local):
     if rank == 0:
         sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    settled, rounds, search_ms = 0, 0, 0.0
+    settled, rounds, search_ms, tree_steps, launches = 0, 0, 0.0, 0, 0
     for e in evs:
         res = step(e)
         settled += res["settled"]
         rounds += res["rounds"]
+        tree_steps += int(res.get("tree", False))
         search_ms += eng.grid.timing()["search_ms"]
+        launches += int(eng.grid.stats()["launches"])
     torch.cuda.synchronize()
     step_ms = sum(a.elapsed_time(b) for a, b in evs)
     # end to end: this rank's band from pinned host memory and back (Squares + levels)
@@ -389,15 +391,21 @@ def ours_bands(args, lab, dist, torch, world, rank, local):
             "data": "synthetic",
             "config": {"workload": workload, "stands_for": stands_for, "game": game, "builder": builder, "mod": mod, "rows": rows, "cols": cols,
                        "seed": SEED + 2, "cells_settled_per_step": settled // args.steps,
-                       "parallelism": f"{world} row bands of one {rows}x{cols} maze, one per GPU; NCCL send/recv of one row of levels per neighbour + 1-word all-reduce between local searches",
+                       "parallelism": (f"{world} row bands of one {rows}x{cols} maze, one per GPU; " +
+                                       ("sharded spanning-tree pipeline: walk / flood / fix-up on the band's tiles, pointer jumping over all crossings on "
+                                        "every rank, NCCL all-gathers of the crossing arrays' slices + one-word all-reduces between the phases"
+                                        if tree_steps == args.steps else
+                                        "NCCL send/recv of one row of levels per neighbour + 1-word all-reduce between local searches")),
                        "exchange_rounds_per_step": rounds / args.steps, "l2": "256 MB flush buffer written between timed steps",
                        "maze_build_s_host": round(build_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
-                         "kernel": "k_bfs_tiles (all launches of a step, exchanges included)", "peak_source": peak_src + f" x {world} GPUs",
+                         "kernel": ("spanning-tree pipeline across the bands (k_tree_walk, k_tree_jump<rank>, k_tree_flood, k_tree_jump<prefix>, "
+                                    "k_tree_fixup; exchanges included)" if tree_steps == args.steps
+                                    else "k_bfs_tiles (all launches of a step, exchanges included)"), "peak_source": peak_src + f" x {world} GPUs",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": search_ms_max / args.steps},
             "e2e": {"value": e_settled / (e_ms_max * 1e-3) / 1e9, "unit": "Gcells/s", "h2d_bytes_per_step": cells * 2,
                     "d2h_bytes_per_step": cells * 6, "ms_per_step": e_ms_max / e_steps, "steps": e_steps},
-            "gpu_launches": int((8 + 5 * rounds / args.steps) * args.steps), "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks,
         }))
     dist.destroy_process_group()
 

@@ -163,6 +163,42 @@ int lab_band_export_edges(lab_grid *g, void *top_levels_dev, void *bottom_levels
 int lab_band_import_edges(lab_grid *g, const void *above_bottom_levels_dev, const void *below_top_levels_dev, uint32_t *activated);
 int lab_band_finish(lab_grid *g, uint64_t *local_max, uint64_t *local_settled);
 
+/* The spanning-tree pipeline (csrc/device/tree.cuh) across row bands: what replaces the relax / exchange
+ * loop above when the maze is one tree (every reference builder without -m), whose diameter would cross the
+ * band borders thousands of times.  The walk, the flood and the fix-up are tile-local and run on the band's
+ * own tiles; the two pointer-jumping phases run over ALL the maze's crossings on every rank (they are a few
+ * per cent of the squares), so the arrays they work on are GLOBAL: indexed by slot = global tile * 256 +
+ * side * 64 + position, global tile = tile_base + the band's tile.  The caller owns them (device memory,
+ * e.g. torch tensors it can hand to NCCL) and moves the bands' slices between the phases:
+ *     lab_band_tree_bind      succ0, s0, s1, r0, r1: uint32[ntiles_global*256 + 2]; loc: uint32[ntiles_global*256];
+ *                             inmask: uint64[ntiles_global*4]; alist_global: uint32[ntiles_global*256];
+ *                             alist_local: uint32[the band's tiles * 256]
+ *     lab_band_tree_count     -> the band's passable squares and adjacent pairs; sum over the ranks: a tree has
+ *                             pairs == squares - 1 (anything else: stay with the loop above)
+ *     lab_band_tree_walk      (global sums in) Euler-tour segments of the band's tiles -> succ0 slice
+ *                             [tile_base*256, +tiles*256), the band's crossings -> alist_local[0, arcs_local)
+ *          exchange: every rank gets all succ0 slices; succ0[ntiles_global*256 .. +2) (the tour's two ends) from
+ *          the rank that holds the start; alist_global = the ranks' alist_local pieces, concatenated;
+ *          s0 = succ0; r0 = 1 everywhere but r0[ntiles_global*256 + 1] = 0
+ *     lab_band_tree_rank      (arcs_global in) ranks every crossing along the tour, orients the band's tiles
+ *                             -> inmask slice [tile_base*4, +tiles*4); unreached != 0 on any rank: not a tree
+ *          exchange: every rank gets all inmask slices
+ *     lab_band_tree_flood     packed component / local level field of the band, loc slice [tile_base*256, ...)
+ *                             -> the band's settled squares (sum over ranks must equal the squares), error
+ *          exchange: every rank gets all loc slices
+ *     lab_band_tree_levels    (settled sum in) exact level of every entry crossing; error != 0: not a tree
+ *     lab_band_tree_finish    commit = 1 (no rank saw an error): the band's levels are final, lab_band_finish next;
+ *                             commit = 0: the field is wiped and the relax / exchange loop above takes over
+ * Results are identical to the loop's, bit for bit. */
+int lab_band_tree_bind(lab_grid *g, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *s0, void *s1, void *r0,
+                       void *r1, void *loc, void *inmask, void *alist_global, void *alist_local);
+int lab_band_tree_count(lab_grid *g, uint64_t *squares, uint64_t *pairs);
+int lab_band_tree_walk(lab_grid *g, uint64_t squares_global, uint64_t pairs_global, uint32_t *arcs_local, uint32_t *error);
+int lab_band_tree_rank(lab_grid *g, uint32_t arcs_global, uint32_t *unreached);
+int lab_band_tree_flood(lab_grid *g, uint64_t *settled_local, uint32_t *error);
+int lab_band_tree_levels(lab_grid *g, uint64_t settled_global, uint32_t *error);
+int lab_band_tree_finish(lab_grid *g, int commit);
+
 int lab_last_timing(const lab_grid *g, lab_timing *out);
 int lab_last_stats(const lab_grid *g, lab_stats *out);
 const char *lab_last_error(void);

@@ -7,13 +7,20 @@ each way (cols x 4 bytes) and all ranks agree, with a one-word all-reduce, wheth
 was re-activated.  The loop ends when nobody was.  Levels are global BFS levels, so the result is
 bit-identical to the single-GPU search.
 
+Perfect mazes (one tree: every reference builder without ``-m``) do not take that loop -- their diameter
+crosses the band borders thousands of times -- but the spanning-tree pipeline of csrc/device/tree.cuh, sharded:
+walk, flood and fix-up run on each band's own tiles, the two pointer-jumping phases run over all the maze's
+border crossings on every rank, and between the phases the ranks exchange their slices of the (global) crossing
+arrays: four all-gathers and a few one-word all-reduces per map, whatever the diameter
+(``_sharded_tree`` below; protocol in include/labyrinth_b200.h).
+
 ``torch`` is plumbing here (device buffers for the exchanged rows, the process group); every
 kernel is the library's own.
 """
 from __future__ import annotations
 
 import ctypes
-from ctypes import byref, c_uint32, c_uint64, c_void_p
+from ctypes import byref, c_int, c_uint32, c_uint64, c_void_p
 from typing import List, Optional, Tuple
 
 TS = 64
@@ -33,8 +40,117 @@ def split_rows(rows: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
-class GpuBandEngine:
-    """One band on one GPU: ctypes over the lab_band_* entry points, row buffers are torch tensors."""
+class _BandEngine:
+    """One band: ctypes over <prefix>band_* entry points that share one protocol (include/labyrinth_b200.h).
+    Subclasses set self.L (the library), self.h (the band's handle), self.prefix, self.row_device."""
+
+    supports_tree = True
+
+    def _setup_rows(self):
+        torch = self.torch
+        self.cols_padded = int(self._f("cols_padded")(self.h))
+        dev = self.row_device
+        self._u8 = [torch.empty(self.cols_padded, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self._u32 = [torch.empty(self.cols_padded, dtype=torch.int32, device=dev) for _ in range(2)]
+        self._tree_bufs = None
+
+    def _f(self, name):
+        return getattr(self.L, self.prefix + name)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}* call failed: {rc}")
+
+    @staticmethod
+    def _ptr(t):
+        return c_void_p(t.data_ptr()) if t is not None else None
+
+    def begin(self, src_local: Optional[Tuple[int, int]]):
+        r, c = src_local if src_local is not None else (-1, -1)
+        self._check(self._f("begin")(self.h, c_int(r), c_int(c)))
+
+    def path_rows(self):
+        self._check(self._f("path_rows")(self.h, self._ptr(self._u8[0]), self._ptr(self._u8[1])))
+        return self._u8[0], self._u8[1]
+
+    def set_neighbour_paths(self, above_bottom, below_top):
+        self._check(self._f("set_neighbour_paths")(self.h, self._ptr(above_bottom), self._ptr(below_top)))
+
+    def relax(self):
+        self._check(self._f("relax")(self.h))
+
+    def export_edges(self):
+        self._check(self._f("export_edges")(self.h, self._ptr(self._u32[0]), self._ptr(self._u32[1])))
+        return self._u32[0], self._u32[1]
+
+    def import_edges(self, above_bottom, below_top) -> int:
+        n = c_uint32()
+        self._check(self._f("import_edges")(self.h, self._ptr(above_bottom), self._ptr(below_top), byref(n)))
+        return int(n.value)
+
+    def finish(self) -> Tuple[int, int]:
+        mx, st = c_uint64(), c_uint64()
+        self._check(self._f("finish")(self.h, byref(mx), byref(st)))
+        return int(mx.value), int(st.value)
+
+    def new_row(self, like):
+        return self.torch.empty_like(like)
+
+    # -- the spanning-tree pipeline across bands (lab_band_tree_*) --
+    def tree_bind(self, tile_base: int, ntiles_global: int, ntiles_local: int):
+        """Allocates (once per maze size) the global crossing arrays and binds them.  Returns the dict of tensors."""
+        torch = self.torch
+        key = (tile_base, ntiles_global, ntiles_local)
+        if self._tree_bufs is None or self._tree_bufs["key"] != key:
+            n = ntiles_global * 256
+            dev = self.row_device
+            b = {"key": key}
+            for name in ("succ0", "s0", "s1", "r0", "r1"):
+                b[name] = torch.empty(n + 2, dtype=torch.int32, device=dev)
+            b["loc"] = torch.empty(n, dtype=torch.int32, device=dev)
+            b["inmask"] = torch.zeros(ntiles_global * 4, dtype=torch.int64, device=dev)
+            b["alist"] = torch.empty(n, dtype=torch.int32, device=dev)
+            b["alist_local"] = torch.empty(ntiles_local * 256, dtype=torch.int32, device=dev)
+            self._tree_bufs = b
+        b = self._tree_bufs
+        self._check(self._f("tree_bind")(self.h, c_uint32(tile_base), c_uint32(ntiles_global), self._ptr(b["succ0"]), self._ptr(b["s0"]),
+                                         self._ptr(b["s1"]), self._ptr(b["r0"]), self._ptr(b["r1"]), self._ptr(b["loc"]),
+                                         self._ptr(b["inmask"]), self._ptr(b["alist"]), self._ptr(b["alist_local"])))
+        return b
+
+    def tree_count(self) -> Tuple[int, int]:
+        v, e = c_uint64(), c_uint64()
+        self._check(self._f("tree_count")(self.h, byref(v), byref(e)))
+        return int(v.value), int(e.value)
+
+    def tree_walk(self, squares_global: int, pairs_global: int) -> Tuple[int, int]:
+        n, err = c_uint32(), c_uint32()
+        self._check(self._f("tree_walk")(self.h, c_uint64(squares_global), c_uint64(pairs_global), byref(n), byref(err)))
+        return int(n.value), int(err.value)
+
+    def tree_rank(self, arcs_global: int) -> int:
+        u = c_uint32()
+        self._check(self._f("tree_rank")(self.h, c_uint32(arcs_global), byref(u)))
+        return int(u.value)
+
+    def tree_flood(self) -> Tuple[int, int]:
+        st, err = c_uint64(), c_uint32()
+        self._check(self._f("tree_flood")(self.h, byref(st), byref(err)))
+        return int(st.value), int(err.value)
+
+    def tree_levels(self, settled_global: int) -> int:
+        err = c_uint32()
+        self._check(self._f("tree_levels")(self.h, c_uint64(settled_global), byref(err)))
+        return int(err.value)
+
+    def tree_finish(self, commit: bool):
+        self._check(self._f("tree_finish")(self.h, c_int(1 if commit else 0)))
+
+
+class GpuBandEngine(_BandEngine):
+    """One band on one GPU: the lab_band_* entry points of liblabyrinth_b200; buffers are CUDA torch tensors."""
+
+    prefix = "lab_band_"
 
     def __init__(self, lab, squares, device=None):
         import torch
@@ -46,50 +162,12 @@ class GpuBandEngine:
         self.grid.set_stream(torch.cuda.current_stream().cuda_stream)
         self.L = lab.lib()
         self.h = self.grid._h
-        self.cols_padded = int(self.L.lab_band_cols_padded(self.h))
-        dev = squares.device
-        self._u8 = [torch.empty(self.cols_padded, dtype=torch.uint8, device=dev) for _ in range(2)]
-        self._u32 = [torch.empty(self.cols_padded, dtype=torch.int32, device=dev) for _ in range(2)]
-        self.row_device = dev
+        self.row_device = squares.device
+        self._setup_rows()
 
     def _check(self, rc):
         if rc != 0:
             raise self.lab.LabError(rc, self.L.lab_last_error().decode(errors="replace"))
-
-    @staticmethod
-    def _ptr(t):
-        return c_void_p(t.data_ptr()) if t is not None else None
-
-    def begin(self, src_local: Optional[Tuple[int, int]]):
-        r, c = src_local if src_local is not None else (-1, -1)
-        self._check(self.L.lab_band_begin(self.h, r, c))
-
-    def path_rows(self):
-        self._check(self.L.lab_band_path_rows(self.h, self._ptr(self._u8[0]), self._ptr(self._u8[1])))
-        return self._u8[0], self._u8[1]
-
-    def set_neighbour_paths(self, above_bottom, below_top):
-        self._check(self.L.lab_band_set_neighbour_paths(self.h, self._ptr(above_bottom), self._ptr(below_top)))
-
-    def relax(self):
-        self._check(self.L.lab_band_relax(self.h))
-
-    def export_edges(self):
-        self._check(self.L.lab_band_export_edges(self.h, self._ptr(self._u32[0]), self._ptr(self._u32[1])))
-        return self._u32[0], self._u32[1]
-
-    def import_edges(self, above_bottom, below_top) -> int:
-        n = c_uint32()
-        self._check(self.L.lab_band_import_edges(self.h, self._ptr(above_bottom), self._ptr(below_top), byref(n)))
-        return int(n.value)
-
-    def finish(self) -> Tuple[int, int]:
-        mx, st = c_uint64(), c_uint64()
-        self._check(self.L.lab_band_finish(self.h, byref(mx), byref(st)))
-        return int(mx.value), int(st.value)
-
-    def new_row(self, like):
-        return self.torch.empty_like(like)
 
 
 def _exchange(dist, rank, world, up_payload, down_payload, engine, group):
@@ -107,7 +185,8 @@ def _exchange(dist, rank, world, up_payload, down_payload, engine, group):
     return from_up, from_down
 
 
-def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_local: int, group=None, max_rounds: int = 1 << 20):
+def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_local: int, group=None, max_rounds: int = 1 << 20,
+                         use_tree: bool = True):
     """Run the sharded distance map on this rank's band.  Collective: every rank of `group` calls it.
 
     Returns {"max", "settled", "rounds"} (global values; the level field stays in the engine)."""
@@ -124,7 +203,8 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     engine.set_neighbour_paths(above_bottom, below_top)
     flag = torch.zeros(1, dtype=torch.int32, device=engine.row_device)
     rounds = 0
-    while True:
+    tree = use_tree and getattr(engine, "supports_tree", False) and _sharded_tree(engine, start_global, row0, rows_local, group)
+    while not tree:
         rounds += 1
         engine.relax()
         top, bottom = engine.export_edges()
@@ -140,4 +220,88 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     st_t = agg[1:].clone()
     dist.all_reduce(mx_t, op=dist.ReduceOp.MAX, group=group)
     dist.all_reduce(st_t, op=dist.ReduceOp.SUM, group=group)
-    return {"max": int(mx_t.item()), "settled": int(st_t.item()), "rounds": rounds}
+    return {"max": int(mx_t.item()), "settled": int(st_t.item()), "rounds": rounds, "tree": bool(tree)}
+
+
+def _share(dist, t, offs, lens, rank, world, group):
+    """Every rank contributes t[offs[rank] : offs[rank] + lens[rank]]; afterwards all ranks hold all slices."""
+    if world == 1:
+        return
+    if len(set(lens)) == 1 and all(offs[r] == offs[0] + r * lens[0] for r in range(world)) and dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(t[offs[0] : offs[0] + world * lens[0]], t[offs[rank] : offs[rank] + lens[rank]].clone(), group=group)
+        return
+    for r in range(world):  # uneven bands (or a backend without the flat all-gather): one broadcast per band
+        if lens[r]:
+            dist.broadcast(t[offs[r] : offs[r] + lens[r]], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+
+
+def _sharded_tree(engine, start_global, row0, rows_local, group) -> bool:
+    """The spanning-tree pipeline across the bands.  Collective.  True: the bands' level fields are final (only
+    engine.finish() is left); False: the maze is not one tree, the fields are as engine.begin() left them."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    dev = engine.row_device
+    tiles_x = engine.cols_padded // TS
+
+    def agree(values, op):
+        t = torch.tensor(values, dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op, group=group)
+        return [int(x) for x in t.tolist()]
+
+    # who holds which tiles (bands are whole tile rows, in rank order)
+    mine = torch.tensor([row0, rows_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine, group=group)
+        split = [tuple(int(x) for x in e.tolist()) for e in every]
+    else:
+        split = [(row0, rows_local)]
+    tile_rows = [(n + TS - 1) // TS for _, n in split]
+    bases = [(r0 // TS) * tiles_x for r0, _ in split]
+    ntiles = [tr * tiles_x for tr in tile_rows]
+    ntiles_global = sum(ntiles)
+    if any(r0 % TS for r0, _ in split) or any(bases[r] != sum(ntiles[:r]) for r in range(world)) or ntiles_global * 256 + 2 >= 1 << 32:
+        return False
+    b = engine.tree_bind(bases[rank], ntiles_global, ntiles[rank])
+    nslots = ntiles_global * 256
+
+    squares, pairs = agree(list(engine.tree_count()), dist.ReduceOp.SUM)
+    if squares < 2 or pairs + 1 != squares:
+        return False  # (nothing has been written yet)
+    arcs_local, err = engine.tree_walk(squares, pairs)
+    counts = torch.tensor([arcs_local, err], dtype=torch.int64, device=dev)
+    if world > 1:
+        every = [torch.empty_like(counts) for _ in range(world)]
+        dist.all_gather(every, counts, group=group)
+        counts_all = [tuple(int(x) for x in e.tolist()) for e in every]
+    else:
+        counts_all = [(arcs_local, err)]
+    if any(e for _, e in counts_all):
+        return False
+    arcs = [n for n, _ in counts_all]
+    arc_offs = [sum(arcs[:r]) for r in range(world)]
+    arcs_global = sum(arcs)
+    # the tour's segments of every band, its two ends from the band that holds the start, the list of crossings
+    _share(dist, b["succ0"], [x * 256 for x in bases], [x * 256 for x in ntiles], rank, world, group)
+    owner = next((r for r, (r0, n) in enumerate(split) if r0 <= start_global[0] < r0 + n), 0)
+    if world > 1:
+        dist.broadcast(b["succ0"][nslots : nslots + 2], src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+    b["alist"][arc_offs[rank] : arc_offs[rank] + arcs[rank]].copy_(b["alist_local"][: arcs[rank]])
+    _share(dist, b["alist"], arc_offs, arcs, rank, world, group)
+    b["s0"].copy_(b["succ0"])
+    b["r0"].fill_(1)
+    b["r0"][nslots + 1] = 0  # END
+    unreached = engine.tree_rank(arcs_global)
+    settled_local, err = engine.tree_flood()
+    unreached, settled, err = agree([unreached, settled_local, err], dist.ReduceOp.SUM)
+    ok = unreached == 0 and err == 0 and settled == squares
+    if ok:
+        _share(dist, b["inmask"], [x * 4 for x in bases], [x * 4 for x in ntiles], rank, world, group)
+        _share(dist, b["loc"], [x * 256 for x in bases], [x * 256 for x in ntiles], rank, world, group)
+        ok = agree([engine.tree_levels(settled)], dist.ReduceOp.SUM)[0] == 0
+    engine.tree_finish(ok)
+    return ok

@@ -62,6 +62,12 @@ struct Tree {
     uint32_t *alist;     // [n_arcs]     the slots that ARE crossings (the pointer-jumping rounds only visit these)
     Tree_ctl *tc;
     uint32_t nslots;     // ntiles * SLOTS; ROOT = nslots, END = nslots + 1
+    // Row bands (one band of a taller maze per GPU): the arrays above are indexed by GLOBAL
+    // slot / tile (every rank holds all of them; the ranks exchange their slices between the phases), nslots
+    // counts the whole maze's slots, and Params describes this band only: its tile t is global tile
+    // tile_base + t.  Single GPU: tile_base = 0, banded = 0.
+    uint32_t tile_base;
+    uint32_t banded;
 };
 
 LAB_DEV bool tree_live(Tree_ctl const *tc) { return tc->ok != 0 && tc->unreached == 0 && tc->bad_weight == 0 && tc->walk_error == 0; }
@@ -196,6 +202,7 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
     uint64_t *masks = sm + WALK_TAB + 260 + WALK_LIST / 4 - 16; // (read before the list grows that far)
     uint32_t *cnt = reinterpret_cast<uint32_t *>(sm + WALK_TAB + 260 + WALK_LIST / 4);
     uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
+    uint32_t const gt = t + tr.tile_base; // the tile's id in the whole maze (row bands)
     int const r0 = 2 * lane, r1 = 2 * lane + 1;
 
     uint64_t const P0 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + r0), P1 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + r1);
@@ -362,8 +369,8 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
             }
             if (v != WALK_END) {
                 uint32_t const ns = v - 1024u, side = ns >> 6;
-                uint32_t const nt = side == SIDE_S ? t - static_cast<uint32_t>(g.tiles_x)
-                                                   : (side == SIDE_N ? t + static_cast<uint32_t>(g.tiles_x) : (side == SIDE_W ? t + 1u : t - 1u));
+                uint32_t const nt = side == SIDE_S ? gt - static_cast<uint32_t>(g.tiles_x)
+                                                   : (side == SIDE_N ? gt + static_cast<uint32_t>(g.tiles_x) : (side == SIDE_W ? gt + 1u : gt - 1u));
                 out = nt * SLOTS + ns;
             }
         }
@@ -376,7 +383,7 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
         }
     }
     lab_syncwarp();
-    long long const o = static_cast<long long>(t) * SLOTS;
+    long long const o = static_cast<long long>(gt) * SLOTS;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int const s = lane + 32 * k;
@@ -439,7 +446,7 @@ LAB_DEV void tree_init_body(Params const &p, Tree const &tr) {
     // Not a tree, but the bounding box of the passable squares holds nothing else: an open room (the
     // reference's arena builder).  Levels are a closed form there (device/room.cuh); the source is one of
     // the passable squares (force_sources_body), so it lies inside.
-    if (!tc->ok && tc->V >= 1) {
+    if (!tc->ok && tc->V >= 1 && !tr.banded) {
         uint32_t const r0 = 0x7FFFFFFFu - tc->box_r0_inv, c0 = 0x7FFFFFFFu - tc->box_c0_inv;
         unsigned long long const area = static_cast<unsigned long long>(tc->box_r1 - r0 + 1u) * (tc->box_c1 - c0 + 1u);
         if (area == tc->V && p.ctl->src_tile[0] != 0xFFFFFFFFu) {
@@ -519,7 +526,7 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
     uint32_t const *sfin = fin1 ? tr.s[1] : tr.s[0], *rfin = fin1 ? tr.r[1] : tr.r[0];
     uint32_t bad = 0;
     for (long long t = gwarp; t < p.g.ntiles; t += nwarps) {
-        long long const o = t * SLOTS;
+        long long const o = (t + tr.tile_base) * SLOTS;
         uint64_t masks[4];
 #pragma unroll
         for (int side = 0; side < 4; side++) {
@@ -540,7 +547,7 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
             masks[side] = lab_ballot64(in[0], in[1]);
         }
         if (lane < 4) {
-            tr.inmask[t * 4 + lane] = masks[lane];
+            tr.inmask[(t + tr.tile_base) * 4 + lane] = masks[lane];
         }
     }
     if (lab_any(bad != 0) && lane == 0) {
@@ -569,7 +576,7 @@ constexpr uint32_t ROOT_COMP = SLOTS;
 constexpr uint32_t NO_TILE = 0xFFFFFFFFu;
 
 LAB_DEV void flood_note_border(Tree const &tr, uint32_t t, int r, int c, uint32_t ld) {
-    uint32_t *loc = tr.loc + static_cast<long long>(t) * SLOTS;
+    uint32_t *loc = tr.loc + static_cast<long long>(t + tr.tile_base) * SLOTS;
     if (r == 0) loc[SIDE_N * TS + c] = ld;
     if (r == TS - 1) loc[SIDE_S * TS + c] = ld;
     if (c == 0) loc[SIDE_W * TS + r] = ld;
@@ -608,7 +615,7 @@ LAB_DEV bool flood_open(Params const &p, Tree const &tr, Flood_sm const &f, int 
             return false;
         }
         ws.passes++;
-        uint64_t const in_side = lane < 4 ? tr.inmask[static_cast<long long>(t) * 4 + lane] : 0ull;
+        uint64_t const in_side = lane < 4 ? tr.inmask[static_cast<long long>(t + tr.tile_base) * 4 + lane] : 0ull;
         bool const root_here = p.ctl->src_tile[0] == t;
         if (!lab_any(in_side != 0) && !root_here) {
             ws.empty++;
@@ -911,7 +918,7 @@ LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, long long gwarp, l
             int const c = j0 * TS + lane + 32 * u;
             if (v[u] != INF) {
                 uint32_t const comp = v[u] >> 16;
-                uint32_t const *b = lvl + (trow + j0 + u / 2) * SLOTS;
+                uint32_t const *b = lvl + (trow + j0 + u / 2 + tr.tile_base) * SLOTS;
                 uint32_t const out = (comp == ROOT_COMP ? 0u : b[comp]) + (v[u] & 0xFFFFu);
                 row[c] = out;
                 mx = out > mx ? out : mx;

@@ -373,6 +373,12 @@ struct lab_grid {
     Tree_ctl tree_last{};
     bool tree_tried = false;
     uint64_t launches = 0; // kernels launched by the last search (bench.py reports them)
+    bool tree_cfg = false;
+    // the pipeline across row bands (lab_band_tree_*): the caller's global arrays, this band's control block
+    Tree band_tree{};
+    uint32_t *band_alist_global = nullptr, *band_alist_local = nullptr;
+    uint32_t band_ntiles_global = 0;
+    bool band_tree_bound = false;
     int tree_coop_blocks = 0; // co-resident blocks of the multi-round kernels
     int tree_flood_per_sm = 1, tree_walk_per_sm = 1;
     cudaEvent_t tev[10]{}; // LAB_TREE_TIMING=1: per-phase events
@@ -544,10 +550,34 @@ int search_launch(lab_grid *h, int nplanes) {
     return LAB_OK;
 }
 
+// Launch shapes of the pipeline's kernels (occupancy of the co-resident ones), once per grid.
+int tree_configure(lab_grid *h) {
+    if (h->tree_cfg) {
+        return LAB_OK;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree_jump<0>, 512, 0));
+    int per_sm2 = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_tree_jump<1>, 512, 0));
+    h->tree_coop_blocks = std::max(1, std::min(per_sm, per_sm2)) * h->sm_count;
+    size_t const flood_smem = 4 * FLOOD_U64 * sizeof(uint64_t);
+    CU(cudaFuncSetAttribute(k_tree_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(flood_smem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tree_flood_per_sm, k_tree_flood, 128, flood_smem));
+    h->tree_flood_per_sm = std::max(1, h->tree_flood_per_sm);
+    CU(cudaFuncSetAttribute(k_tree_walk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_tree_flood, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tree_walk_per_sm, k_tree_walk, 128, 0));
+    h->tree_walk_per_sm = std::max(1, h->tree_walk_per_sm);
+    h->tree_cfg = true;
+    return LAB_OK;
+}
+
 int ensure_tree(lab_grid *h) {
     if (h->tree_alloc) {
         return LAB_OK;
     }
+    int const rc = tree_configure(h);
+    if (rc) return rc;
     Tree &tr = h->tree;
     size_t const nt = static_cast<size_t>(h->g.ntiles);
     if (nt * SLOTS + 2 >= (1ull << 32)) {
@@ -563,19 +593,6 @@ int ensure_tree(lab_grid *h) {
     CU(cudaMalloc(&tr.inmask, nt * 4 * sizeof(uint64_t)));
     CU(cudaMalloc(&tr.loc, nt * SLOTS * sizeof(uint32_t)));
     CU(cudaMalloc(&tr.alist, nt * SLOTS * sizeof(uint32_t)));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree_jump<0>, 512, 0));
-    int per_sm2 = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_tree_jump<1>, 512, 0));
-    h->tree_coop_blocks = std::max(1, std::min(per_sm, per_sm2)) * h->sm_count;
-    size_t const flood_smem = 4 * FLOOD_U64 * sizeof(uint64_t);
-    CU(cudaFuncSetAttribute(k_tree_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(flood_smem)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tree_flood_per_sm, k_tree_flood, 128, flood_smem));
-    h->tree_flood_per_sm = std::max(1, h->tree_flood_per_sm);
-    CU(cudaFuncSetAttribute(k_tree_walk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_tree_flood, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tree_walk_per_sm, k_tree_walk, 128, 0));
-    h->tree_walk_per_sm = std::max(1, h->tree_walk_per_sm);
     CU(cudaMalloc(&tr.tc, sizeof(Tree_ctl)));
     h->tree_alloc = true;
     return LAB_OK;
@@ -868,6 +885,7 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->d_finish_rc);
     cudaFree(h->d_front_rc);
     cudaFree(h->d_paths);
+    cudaFree(h->band_tree.tc);
     if (h->owns_pixels) {
         cudaFree(h->pixels);
     }
@@ -1272,6 +1290,8 @@ int lab_band_begin(lab_grid *h, int src_r, int src_c) {
         CU(cudaMalloc(&h->d_activated, sizeof(uint32_t)));
     }
     h->band_mode = true;
+    h->tree_last = Tree_ctl{};
+    h->tree_tried = false;
     int const rc = search_prepare(h, d, SQ_PATH | SQ_MEASURE, SQ_PATH);
     h->band_open = rc == LAB_OK;
     return rc;
@@ -1284,6 +1304,7 @@ int lab_band_path_rows(lab_grid *h, void *top_dev, void *bottom_dev) {
     int const n = h->g.tiles_x * TS;
     k_band_path_rows<<<(n + 255) / 256, 256, 0, h->stream>>>(h->g, h->path, static_cast<uint8_t *>(top_dev), static_cast<uint8_t *>(bottom_dev));
     TRACE("k_band_path_rows", h->stream);
+    h->launches += 1;
     CU(cudaGetLastError());
     return LAB_OK;
 }
@@ -1298,6 +1319,7 @@ int lab_band_set_neighbour_paths(lab_grid *h, const void *above_bottom_dev, cons
     k_band_ghost_words<<<blocks_for(h, h->g.tiles_x, 256), 256, 0, h->stream>>>(
         h->g, static_cast<uint8_t const *>(above_bottom_dev), static_cast<uint8_t const *>(below_top_dev), h->ghost_n, h->ghost_s);
     TRACE("k_band_ghost_words", h->stream);
+    h->launches += 1;
     int const rc = search_arm(h, h->band_desc, h->ghost_n, h->ghost_s);
     if (rc) return rc;
     CU(cudaEventRecord(h->ev[EV_SEARCH0], h->stream));
@@ -1319,6 +1341,7 @@ int lab_band_export_edges(lab_grid *h, void *top_levels_dev, void *bottom_levels
     k_band_export_edges<<<(n + 255) / 256, 256, 0, h->stream>>>(h->g, h->plane[0].edges, static_cast<uint32_t *>(top_levels_dev),
                                                                static_cast<uint32_t *>(bottom_levels_dev));
     TRACE("k_band_export_edges", h->stream);
+    h->launches += 1;
     CU(cudaGetLastError());
     return LAB_OK;
 }
@@ -1334,6 +1357,7 @@ int lab_band_import_edges(lab_grid *h, const void *above_bottom_levels_dev, cons
     k_band_import_edges<<<blocks_for(h, h->g.tiles_x, 256), 256, 0, s>>>(p, static_cast<uint32_t const *>(above_bottom_levels_dev),
                                                                          static_cast<uint32_t const *>(below_top_levels_dev), h->d_activated);
     TRACE("k_band_import_edges", s);
+    h->launches += 2;
     CU(cudaMemcpyAsync(activated, h->d_activated, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return LAB_OK;
@@ -1349,6 +1373,7 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
     k_resolve<<<1, 1, 0, s>>>(p, h->band_desc, h->res, h->d_finish_rc);
     k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
     k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->ctl, h->res);
+    h->launches += 3;
     CU(cudaGetLastError());
     h->band_open = false;
     int const rc = finish_run(h);
@@ -1356,6 +1381,185 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
     if (local_max) *local_max = h->last.max_level;
     if (local_settled) *local_settled = h->last.settled;
     return LAB_OK;
+}
+
+// ---- the spanning-tree pipeline across row bands (device/tree.cuh; protocol in include/labyrinth_b200.h) ----
+int lab_band_tree_bind(lab_grid *h, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *s0, void *s1, void *r0, void *r1,
+                       void *loc, void *inmask, void *alist_global, void *alist_local) {
+    if (!h || !succ0 || !s0 || !s1 || !r0 || !r1 || !loc || !inmask || !alist_global || !alist_local) {
+        return fail(LAB_ERR_ARG, "lab_band_tree_bind: null argument");
+    }
+    if (static_cast<unsigned long long>(ntiles_global) * SLOTS + 2 >= (1ull << 32) || tile_base + static_cast<uint32_t>(h->g.ntiles) > ntiles_global) {
+        return fail(LAB_ERR_ARG, "lab_band_tree_bind: band tiles [%u, %u) do not fit a maze of %u tiles (or the maze is too large)", tile_base,
+                    tile_base + static_cast<uint32_t>(h->g.ntiles), ntiles_global);
+    }
+    int const rc = tree_configure(h);
+    if (rc) return rc;
+    Tree &tr = h->band_tree;
+    if (!tr.tc) {
+        CU(cudaMalloc(&tr.tc, sizeof(Tree_ctl)));
+    }
+    tr.succ0 = static_cast<uint32_t *>(succ0);
+    tr.s[0] = static_cast<uint32_t *>(s0);
+    tr.s[1] = static_cast<uint32_t *>(s1);
+    tr.r[0] = static_cast<uint32_t *>(r0);
+    tr.r[1] = static_cast<uint32_t *>(r1);
+    tr.loc = static_cast<uint32_t *>(loc);
+    tr.inmask = static_cast<uint64_t *>(inmask);
+    tr.alist = static_cast<uint32_t *>(alist_local);
+    tr.nslots = ntiles_global * SLOTS;
+    tr.tile_base = tile_base;
+    tr.banded = 1;
+    h->band_alist_global = static_cast<uint32_t *>(alist_global);
+    h->band_alist_local = static_cast<uint32_t *>(alist_local);
+    h->band_ntiles_global = ntiles_global;
+    h->band_tree_bound = true;
+    return LAB_OK;
+}
+
+static int band_tree_ready(lab_grid *h, char const *who) {
+    if (!h || !h->band_open || !h->band_tree_bound) {
+        return fail(LAB_ERR_ARG, "%s: no band search open, or lab_band_tree_bind not called", who);
+    }
+    return LAB_OK;
+}
+static int band_tree_read(lab_grid *h, Tree_ctl &out) {
+    CU(cudaMemcpyAsync(&out, h->band_tree.tc, sizeof(Tree_ctl), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LAB_OK;
+}
+static int band_tree_coop_blocks(lab_grid *h) {
+    return static_cast<int>(std::max<long long>(
+        1, std::min<long long>(h->tree_coop_blocks, (static_cast<long long>(h->band_ntiles_global) * 64 + 512 * JUMP_K - 1) / (512 * JUMP_K))));
+}
+
+int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs) {
+    int rc = band_tree_ready(h, "lab_band_tree_count");
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Tree const tr = h->band_tree;
+    Params p = make_params(h, 1);
+    CU(cudaMemsetAsync(tr.tc, 0, sizeof(Tree_ctl), s));
+    k_tree_count<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, tr);
+    TRACE("k_tree_count", s);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    Tree_ctl tc{};
+    rc = band_tree_read(h, tc);
+    if (rc) return rc;
+    if (squares) *squares = tc.V;
+    if (pairs) *pairs = tc.E;
+    return LAB_OK;
+}
+
+int lab_band_tree_walk(lab_grid *h, uint64_t squares_global, uint64_t pairs_global, uint32_t *arcs_local, uint32_t *error) {
+    int rc = band_tree_ready(h, "lab_band_tree_walk");
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Tree tr = h->band_tree;
+    tr.alist = h->band_alist_local;
+    Params p = make_params(h, 1);
+    unsigned long long const ve[2] = {squares_global, pairs_global};
+    CU(cudaMemcpyAsync(&tr.tc->V, ve, sizeof ve, cudaMemcpyHostToDevice, s)); // (V and E are the struct's first two members)
+    k_tree_init<<<1, 1, 0, s>>>(p, tr);
+    int const walk_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_walk_per_sm);
+    k_tree_walk<<<walk_blocks, 128, 0, s>>>(p, tr);
+    TRACE("k_tree_walk", s);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    Tree_ctl tc{};
+    rc = band_tree_read(h, tc);
+    if (rc) return rc;
+    if (arcs_local) *arcs_local = tc.n_arcs;
+    if (error) *error = tc.ok ? tc.walk_error : 0xFFFFu;
+    return LAB_OK;
+}
+
+int lab_band_tree_rank(lab_grid *h, uint32_t arcs_global, uint32_t *unreached) {
+    int rc = band_tree_ready(h, "lab_band_tree_rank");
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Tree tr = h->band_tree;
+    tr.alist = h->band_alist_global;
+    Params p = make_params(h, 1);
+    CU(cudaMemcpyAsync(&tr.tc->n_arcs, &arcs_global, sizeof arcs_global, cudaMemcpyHostToDevice, s));
+    uint32_t rounds = static_cast<uint32_t>(ceil_log2(static_cast<unsigned long long>(tr.nslots) + 2));
+    {
+        void *args[] = {&p, &tr, &rounds};
+        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_jump<0>), dim3(band_tree_coop_blocks(h)), dim3(512), args, 0, s));
+    }
+    TRACE("k_tree_jump<rank+orient>", s);
+    h->launches += 1;
+    Tree_ctl tc{};
+    rc = band_tree_read(h, tc);
+    if (rc) return rc;
+    if (unreached) *unreached = tc.unreached;
+    return LAB_OK;
+}
+
+int lab_band_tree_flood(lab_grid *h, uint64_t *settled_local, uint32_t *error) {
+    int rc = band_tree_ready(h, "lab_band_tree_flood");
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Tree tr = h->band_tree;
+    tr.alist = h->band_alist_global;
+    Params p = make_params(h, 1);
+    int const fill_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_flood_per_sm);
+    k_tree_flood<<<fill_blocks, 128, 4 * FLOOD_U64 * sizeof(uint64_t), s>>>(p, tr);
+    TRACE("k_tree_flood", s);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    Tree_ctl tc{};
+    rc = band_tree_read(h, tc);
+    if (rc) return rc;
+    if (settled_local) *settled_local = tc.local_settled;
+    if (error) *error = tc.walk_error;
+    return LAB_OK;
+}
+
+int lab_band_tree_levels(lab_grid *h, uint64_t settled_global, uint32_t *error) {
+    int rc = band_tree_ready(h, "lab_band_tree_levels");
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Tree tr = h->band_tree;
+    tr.alist = h->band_alist_global;
+    Params p = make_params(h, 1);
+    unsigned long long const st = settled_global;
+    CU(cudaMemcpyAsync(&tr.tc->local_settled, &st, sizeof st, cudaMemcpyHostToDevice, s));
+    uint32_t rounds = static_cast<uint32_t>(ceil_log2(static_cast<unsigned long long>(tr.nslots) + 2));
+    {
+        void *args[] = {&p, &tr, &rounds};
+        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_jump<1>), dim3(band_tree_coop_blocks(h)), dim3(512), args, 0, s));
+    }
+    TRACE("k_tree_jump<parent+prefix>", s);
+    Tree_ctl tc{};
+    rc = band_tree_read(h, tc); // (the entry levels are final: the caller's ranks agree on going on before anybody writes the field)
+    if (rc) return rc;
+    h->launches += 1;
+    if (error) *error = (tc.ok && tc.bad_weight == 0 && tc.walk_error == 0 && tc.unreached == 0) ? 0u : 1u;
+    return LAB_OK;
+}
+
+int lab_band_tree_finish(lab_grid *h, int commit) {
+    int rc = band_tree_ready(h, "lab_band_tree_finish");
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Tree tr = h->band_tree;
+    tr.alist = h->band_alist_global;
+    Params p = make_params(h, 1);
+    if (!commit) { // some rank found out that this is not one tree: hand the field back to the wave, clean
+        uint32_t const zero = 0;
+        CU(cudaMemcpyAsync(&tr.tc->ok, &zero, sizeof zero, cudaMemcpyHostToDevice, s));
+    } else {
+        k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, tr);
+        TRACE("k_tree_fixup", s);
+        h->launches += 1;
+    }
+    k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, tr);
+    TRACE("k_tree_gate", s);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return band_tree_read(h, h->tree_last);
 }
 
 uint64_t lab_last_painted(const lab_grid *h) { return h ? h->last.settled : 0; }

@@ -2,6 +2,7 @@
 import ctypes
 import glob
 import os
+import sys
 
 import numpy as np
 
@@ -95,3 +96,41 @@ class Emu:
                                  self._p(paths), ctypes.c_longlong(mp), self._p(lens), ctypes.byref(painted), nwarps, sched, self._p(stats))
         assert rc == 0, f"emulated search failed: {rc}"
         return g, win.value, claimed, [paths[k, : lens[k]].copy() for k in range(4)], painted.value
+
+
+def emu_band_engine(squares: np.ndarray, nwarps: int = 4, sched: int = 0):
+    """The real band driver's engine interface (multithreading-with-mazes_b200/bands.py) over the emulator's
+    emu_band_* entry points: the product's kernel bodies, host memory instead of device memory."""
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as graft
+
+    graft.load_package()
+    from mazes_b200 import bands
+
+    class EmuBandEngine(bands._BandEngine):
+        prefix = "emu_band_"
+
+        def __init__(self):
+            self.torch = torch
+            self.sq = np.ascontiguousarray(squares, np.uint16)
+            self.rows, self.cols = self.sq.shape
+            self.L = Emu().lib
+            self.L.emu_band_create.restype = ctypes.c_void_p
+            self.L.emu_band_levels.restype = ctypes.c_void_p
+            self.h = ctypes.c_void_p(self.L.emu_band_create(self.rows, self.cols, self.sq.ctypes.data_as(ctypes.c_void_p), nwarps, sched))
+            self.row_device = torch.device("cpu")
+            self._setup_rows()
+
+        def levels(self):
+            ptr = self.L.emu_band_levels(self.h)
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(self.rows, self.cols)).copy()
+
+        def tree_used(self):
+            return int(self.L.emu_band_tree_used(self.h))
+
+        def close(self):
+            self.L.emu_band_destroy(self.h)
+
+    return EmuBandEngine()

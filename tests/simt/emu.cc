@@ -194,6 +194,256 @@ int emu_heatmap(int rows, int cols, uint32_t const *dist, uint64_t max, int chan
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row bands: the lab_band_* / lab_band_tree_* entry points of csrc/lab.cu, same names, same protocol, with
+// host memory standing in for device memory (so that the real driver, multithreading-with-mazes_b200/bands.py,
+// can run under gloo on CPU tensors with these kernel bodies underneath).
+struct Emu_band {
+    Workspace w;
+    Run_desc d;
+    std::vector<uint64_t> ghost_n, ghost_s;
+    std::vector<uint64_t> stages, sm;
+    int nwarps = 4;
+    unsigned sched = 0;
+    Tree tr{};
+    Tree_ctl tc{};
+    uint32_t *alist_global = nullptr, *alist_local = nullptr;
+    uint32_t ntiles_global = 0;
+    Tree_ctl tree_last{};
+};
+
+void *emu_band_create(int rows, int cols, uint16_t *grid, int nwarps, unsigned sched_seed) {
+    auto *e = new Emu_band;
+    Geom &g = e->w.g;
+    g.rows = rows;
+    g.cols = cols;
+    g.tiles_y = (rows + TS - 1) / TS;
+    g.tiles_x = (cols + TS - 1) / TS;
+    g.ntiles = g.tiles_y * g.tiles_x;
+    e->w.grid_ptr = grid;
+    e->nwarps = nwarps;
+    e->sched = sched_seed;
+    return e;
+}
+void emu_band_destroy(void *h) { delete static_cast<Emu_band *>(h); }
+int emu_band_cols_padded(void *h) { return static_cast<Emu_band *>(h)->w.g.tiles_x * TS; }
+uint32_t *emu_band_levels(void *h) { return static_cast<Emu_band *>(h)->w.dist[0].data(); }
+int emu_band_tree_used(void *h) { return static_cast<int>(static_cast<Emu_band *>(h)->tree_last.used); }
+
+int emu_band_begin(void *h, int src_r, int src_c) {
+    auto *e = static_cast<Emu_band *>(h);
+    Workspace &w = e->w;
+    Geom const &g = w.g;
+    fill_desc(e->d);
+    e->d.game = GAME_DISTANCE;
+    e->d.nplanes = 1;
+    if (src_r >= 0) {
+        e->d.src_r[0] = src_r;
+        e->d.src_c[0] = src_c;
+    }
+    e->d.bound_mode = BOUND_NONE;
+    size_t const nt = static_cast<size_t>(g.ntiles), cells = static_cast<size_t>(g.rows) * g.cols;
+    w.path.assign(nt * TS, 0);
+    w.cross.assign(nt * 4, 0);
+    w.visited[0].assign(nt * TS, 0);
+    w.edges[0].assign((nt + 2 * static_cast<size_t>(g.tiles_x)) * 4 * TS, INF);
+    w.state[0].assign(nt, 0);
+    w.dist[0].assign(cells, INF);
+    std::memset(&w.ctl, 0, sizeof w.ctl);
+    std::memset(&w.res, 0, sizeof w.res);
+    size_t cap = 1024;
+    while (cap < 2 * (nt + static_cast<size_t>(e->nwarps) + 64)) cap <<= 1;
+    w.queue.assign(cap, Q_EMPTY);
+    e->ghost_n.assign(g.tiles_x, 0);
+    e->ghost_s.assign(g.tiles_x, 0);
+    e->tree_last = Tree_ctl{};
+    int const nw = e->nwarps;
+    simt::launch(nw, [&](int wid, int lane) { pack_body(g, w.grid_ptr, w.path.data(), SQ_PATH | SQ_MEASURE, SQ_PATH, wid, nw, lane); });
+    force_sources_body(g, w.path.data(), e->d);
+    return 0;
+}
+
+int emu_band_path_rows(void *h, uint8_t *top, uint8_t *bottom) {
+    auto *e = static_cast<Emu_band *>(h);
+    for (long long i = 0; i < static_cast<long long>(e->w.g.tiles_x) * TS; i++) {
+        band_path_rows_body(e->w.g, e->w.path.data(), top, bottom, i);
+    }
+    return 0;
+}
+
+int emu_band_set_neighbour_paths(void *h, uint8_t const *above_bottom, uint8_t const *below_top) {
+    auto *e = static_cast<Emu_band *>(h);
+    Workspace &w = e->w;
+    int const nw = e->nwarps;
+    simt::launch(nw, [&](int wid, int lane) { band_ghost_words_body(w.g, above_bottom, below_top, e->ghost_n.data(), e->ghost_s.data(), wid, nw, lane); });
+    simt::launch(nw, [&](int wid, int lane) { cross_body(w.g, w.path.data(), w.cross.data(), e->ghost_n.data(), e->ghost_s.data(), wid, nw, lane); });
+    Params p = make_params(w, 1);
+    init_run_body(p, e->d, 60ull * 1000000000ull);
+    return 0;
+}
+
+int emu_band_relax(void *h) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    e->stages.assign(static_cast<size_t>(nw) * STAGE_U64, 0);
+    simt::launch(nw, [&](int wid, int lane) { bfs_worker_body(p, lane, e->stages.data() + static_cast<size_t>(wid) * STAGE_U64); }, e->sched);
+    if (e->w.ctl.error) return -100 - static_cast<int>(e->w.ctl.error);
+    return 0;
+}
+
+int emu_band_export_edges(void *h, uint32_t *top, uint32_t *bottom) {
+    auto *e = static_cast<Emu_band *>(h);
+    for (long long i = 0; i < static_cast<long long>(e->w.g.tiles_x) * TS; i++) {
+        band_export_edges_body(e->w.g, e->w.edges[0].data(), top, bottom, i);
+    }
+    return 0;
+}
+
+int emu_band_import_edges(void *h, uint32_t const *above_bottom, uint32_t const *below_top, uint32_t *activated) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    *activated = 0;
+    band_rearm_body(p, 60ull * 1000000000ull);
+    simt::launch(nw, [&](int wid, int lane) { band_import_edges_body(p, above_bottom, below_top, activated, wid, nw, lane); });
+    return 0;
+}
+
+int emu_band_finish(void *h, uint64_t *local_max, uint64_t *local_settled) {
+    auto *e = static_cast<Emu_band *>(h);
+    Workspace &w = e->w;
+    Params p = make_params(w, 1);
+    int const nw = e->nwarps;
+    int32_t frc[8] = {0};
+    resolve_body(p, e->d, &w.res, frc);
+    long long const nthreads = static_cast<long long>(nw) * 32;
+    simt::launch(nw, [&](int wid, int lane) { max_level_body(w.g, w.dist[0].data(), &w.ctl, &w.res, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    simt::launch(nw, [&](int wid, int lane) { measure_body(w.g, w.grid_ptr, w.visited[0].data(), &w.ctl, &w.res, wid, nw, lane); });
+    if (w.ctl.pending != 0) return -200;
+    *local_max = w.res.max_level;
+    *local_settled = w.res.settled;
+    return 0;
+}
+
+int emu_band_tree_bind(void *h, uint32_t tile_base, uint32_t ntiles_global, uint32_t *succ0, uint32_t *s0, uint32_t *s1, uint32_t *r0,
+                       uint32_t *r1, uint32_t *loc, uint64_t *inmask, uint32_t *alist_global, uint32_t *alist_local) {
+    auto *e = static_cast<Emu_band *>(h);
+    Tree &tr = e->tr;
+    tr.succ0 = succ0;
+    tr.s[0] = s0;
+    tr.s[1] = s1;
+    tr.r[0] = r0;
+    tr.r[1] = r1;
+    tr.loc = loc;
+    tr.inmask = inmask;
+    tr.alist = alist_local;
+    tr.tc = &e->tc;
+    tr.nslots = ntiles_global * SLOTS;
+    tr.tile_base = tile_base;
+    tr.banded = 1;
+    e->alist_global = alist_global;
+    e->alist_local = alist_local;
+    e->ntiles_global = ntiles_global;
+    size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
+    e->sm.assign(static_cast<size_t>(e->nwarps) * SM, 0);
+    return 0;
+}
+
+int emu_band_tree_count(void *h, uint64_t *squares, uint64_t *pairs) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    e->tc = Tree_ctl{};
+    Tree const tr = e->tr;
+    simt::launch(nw, [&](int wid, int lane) { tree_count_body(p, tr, wid, nw, lane); });
+    *squares = e->tc.V;
+    *pairs = e->tc.E;
+    return 0;
+}
+
+int emu_band_tree_walk(void *h, uint64_t squares_global, uint64_t pairs_global, uint32_t *arcs_local, uint32_t *error) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    Tree tr = e->tr;
+    tr.alist = e->alist_local;
+    e->tc.V = squares_global;
+    e->tc.E = pairs_global;
+    tree_init_body(p, tr);
+    size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
+    simt::launch(nw, [&](int wid, int lane) { tree_walk_body(p, tr, lane, e->sm.data() + static_cast<size_t>(wid) * SM); }, e->sched);
+    *arcs_local = e->tc.n_arcs;
+    *error = e->tc.ok ? e->tc.walk_error : 0xFFFFu;
+    return 0;
+}
+
+int emu_band_tree_rank(void *h, uint32_t arcs_global, uint32_t *unreached) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    Tree tr = e->tr;
+    tr.alist = e->alist_global;
+    e->tc.n_arcs = arcs_global;
+    long long const nthreads = static_cast<long long>(nw) * 32;
+    int rounds = 0;
+    while ((1ull << rounds) < static_cast<unsigned long long>(tr.nslots) + 2) rounds++;
+    for (int r = 0; r < rounds; r++) {
+        simt::launch(nw, [&](int wid, int lane) { tree_rank_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
+    }
+    simt::launch(nw, [&](int wid, int lane) { tree_orient_body(p, tr, wid, nw, lane); });
+    *unreached = e->tc.unreached;
+    return 0;
+}
+
+int emu_band_tree_flood(void *h, uint64_t *settled_local, uint32_t *error) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    Tree tr = e->tr;
+    tr.alist = e->alist_global;
+    size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
+    simt::launch(nw, [&](int wid, int lane) { tree_flood_body(p, tr, lane, e->sm.data() + static_cast<size_t>(wid) * SM); }, e->sched);
+    *settled_local = e->tc.local_settled;
+    *error = e->tc.walk_error;
+    return 0;
+}
+
+int emu_band_tree_levels(void *h, uint64_t settled_global, uint32_t *error) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    Tree tr = e->tr;
+    tr.alist = e->alist_global;
+    e->tc.local_settled = settled_global;
+    long long const nthreads = static_cast<long long>(nw) * 32;
+    simt::launch(nw, [&](int wid, int lane) { tree_parent_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    int rounds = 0;
+    while ((1ull << rounds) < static_cast<unsigned long long>(tr.nslots) + 2) rounds++;
+    for (int r = 0; r < rounds; r++) {
+        simt::launch(nw, [&](int wid, int lane) { tree_prefix_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
+    }
+    *error = (e->tc.ok && e->tc.bad_weight == 0 && e->tc.walk_error == 0 && e->tc.unreached == 0) ? 0u : 1u;
+    return 0;
+}
+
+int emu_band_tree_finish(void *h, int commit) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    Tree tr = e->tr;
+    tr.alist = e->alist_global;
+    long long const nthreads = static_cast<long long>(nw) * 32;
+    if (!commit) {
+        e->tc.ok = 0;
+    } else {
+        simt::launch(nw, [&](int wid, int lane) { tree_fixup_body(p, tr, wid, nw, lane); });
+    }
+    simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    e->tree_last = e->tc;
+    return 0;
+}
+
 // game: 1 hunt, 2 gather, 3 corners.  starts: 4 (r,c) (hunt/gather use the first).  finishes: 4 (r,c)
 // (hunt/corners use the first).  paths_out: 4 * max_path (r,c).
 int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *starts, int32_t const *finishes,

@@ -124,6 +124,73 @@ def test_sharded_driver_on_gloo(lab, O, tmp_path, builder, rows, cols, world):
         assert int(z["mx"]) == mx_ref and int(z["settled"]) == settled_ref and int(z["rounds"]) >= 2
 
 
+def _gloo_emu_worker(rank, world, port, maze_path, out_dir, use_tree):
+    """Like _gloo_worker, but the band engine runs the PRODUCT's kernel bodies (tests/simt emulator): the wave's
+    and -- for mazes that are one tree -- the sharded spanning-tree pipeline's."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    import __graft_entry__ as graft
+    from _util import emu_band_engine
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lab = graft.load_package()
+    from mazes_b200 import bands
+
+    maze = np.load(maze_path)
+    r0, n = bands.split_rows(maze.shape[0], world)[rank]
+    eng = emu_band_engine(maze[r0 : r0 + n].copy(), nwarps=3, sched=rank + 1)
+    res = bands.sharded_distance_map(eng, lab.distance_start(*maze.shape), r0, n, use_tree=use_tree)
+    np.savez(os.path.join(out_dir, f"band{rank}.npz"), dist=eng.levels(), sq=eng.sq, r0=r0, mx=res["max"], settled=res["settled"],
+             rounds=res["rounds"], tree=int(res["tree"]), used=eng.tree_used())
+    eng.close()
+    dist.destroy_process_group()
+
+
+def _check_bands(tmp_path, world, maze, O, want_tree):
+    g_ref, d_ref, mx_ref, settled_ref = O.distance_map(maze)
+    for rank in range(world):
+        z = np.load(tmp_path / f"band{rank}.npz")
+        r0 = int(z["r0"])
+        n = z["dist"].shape[0]
+        assert int(z["tree"]) == int(want_tree) and int(z["used"]) == int(want_tree), (rank, int(z["tree"]), int(z["used"]))
+        assert (int(z["rounds"]) == 0) == want_tree
+        assert (z["dist"] == d_ref[r0 : r0 + n]).all(), (rank, int((z["dist"] != d_ref[r0 : r0 + n]).sum()))
+        assert (z["sq"] == g_ref[r0 : r0 + n]).all()
+        assert int(z["mx"]) == mx_ref and int(z["settled"]) == settled_ref
+
+
+@pytest.mark.parametrize("builder,rows,cols,world", [("kruskal", 255, 131, 2), ("wilson", 193, 197, 3), ("rdfs", 257, 67, 2), ("kruskal", 447, 65, 3)])
+def test_sharded_tree_pipeline_on_gloo(lab, O, tmp_path, builder, rows, cols, world):
+    """One tree across 2-3 bands: the sharded spanning-tree pipeline (no relax/exchange round at all), bit-exact.
+    (447 rows over 3 ranks: uneven bands; the start lies in the first, middle or last band.)"""
+    import torch.multiprocessing as mp
+
+    maze = lab.build_maze(builder, rows, cols, seed=31)
+    path = str(tmp_path / "maze.npy")
+    np.save(path, maze)
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_emu_worker, args=(world, port, path, str(tmp_path), True), nprocs=world, join=True)
+    _check_bands(tmp_path, world, maze, O, want_tree=True)
+
+
+def test_sharded_non_trees_fall_back_to_the_wave_on_gloo(lab, O, tmp_path):
+    """Not one tree: the counts say so (grid + cross), or only the later checks do (a cycle plus a cut-off part with
+    a tree's counts): every rank gives the field back and the relax/exchange loop does the search."""
+    import torch.multiprocessing as mp
+
+    from test_tree_pipeline import tree_looking_non_tree
+
+    for i, maze in enumerate([lab.build_maze("grid", 257, 129, seed=31, mod="cross"), tree_looking_non_tree(lab, 255, 131, 2)]):
+        path = str(tmp_path / "maze.npy")
+        np.save(path, maze)
+        port = 33500 + (os.getpid() % 2000) + i
+        mp.spawn(_gloo_emu_worker, args=(2, port, path, str(tmp_path), True), nprocs=2, join=True)
+        _check_bands(tmp_path, 2, maze, O, want_tree=False)
+
+
 def test_split_rows(lab):
     from mazes_b200 import bands
 
@@ -154,6 +221,131 @@ def test_band_entry_points_one_process(lab, O, builder, rows, cols, nb):
     rows_p = [tuple(t.clone() for t in e.path_rows()) for e in eng]
     for i, e in enumerate(eng):
         e.set_neighbour_paths(rows_p[i - 1][1] if i > 0 else None, rows_p[i + 1][0] if i < nb - 1 else None)
+    rounds = 0
+    while True:
+        rounds += 1
+        for e in eng:
+            e.relax()
+        edges = [tuple(t.clone() for t in e.export_edges()) for e in eng]
+        act = [e.import_edges(edges[i - 1][1] if i > 0 else None, edges[i + 1][0] if i < nb - 1 else None) for i, e in enumerate(eng)]
+        if not any(act):
+            break
+        assert rounds < 100000
+    res = [e.finish() for e in eng]
+    g_ref, d_ref, mx_ref, settled_ref = O.distance_map(maze)
+    got_d = np.concatenate([l.cpu().numpy().view(np.uint32) for l in lv])
+    got_g = np.concatenate([s.cpu().numpy().view(np.uint16) for s in sq])
+    assert (got_d == d_ref).all() and (got_g == g_ref).all()
+    assert max(r[0] for r in res) == mx_ref and sum(r[1] for r in res) == settled_ref
+
+
+def _lockstep_tree(eng, split, start, cols):
+    """_sharded_tree of bands.py for several bands driven by ONE process: the collectives become copies between
+    the bands' own (separate) global arrays."""
+    import torch
+
+    nb = len(eng)
+    tiles_x = eng[0].cols_padded // 64
+    ntiles = [((n + 63) // 64) * tiles_x for _, n in split]
+    bases = [(r0 // 64) * tiles_x for r0, _ in split]
+    total = sum(ntiles)
+    nslots = total * 256
+    bufs = [e.tree_bind(bases[i], total, ntiles[i]) for i, e in enumerate(eng)]
+
+    def share(name, offs, lens):
+        for src in range(nb):
+            for dst in range(nb):
+                if dst != src and lens[src]:
+                    bufs[dst][name][offs[src] : offs[src] + lens[src]].copy_(bufs[src][name][offs[src] : offs[src] + lens[src]])
+
+    counts = [e.tree_count() for e in eng]
+    squares, pairs = sum(c[0] for c in counts), sum(c[1] for c in counts)
+    if squares < 2 or pairs + 1 != squares:
+        return False
+    walked = [e.tree_walk(squares, pairs) for e in eng]
+    if any(err for _, err in walked):
+        return False
+    arcs = [n for n, _ in walked]
+    offs = [sum(arcs[:i]) for i in range(nb)]
+    share("succ0", [b * 256 for b in bases], [n * 256 for n in ntiles])
+    owner = next(i for i, (r0, n) in enumerate(split) if r0 <= start[0] < r0 + n)
+    for i in range(nb):
+        if i != owner:
+            bufs[i]["succ0"][nslots : nslots + 2].copy_(bufs[owner]["succ0"][nslots : nslots + 2])
+        bufs[i]["alist"][offs[i] : offs[i] + arcs[i]].copy_(bufs[i]["alist_local"][: arcs[i]])
+    share("alist", offs, arcs)
+    for b in bufs:
+        b["s0"].copy_(b["succ0"])
+        b["r0"].fill_(1)
+        b["r0"][nslots + 1] = 0
+    unreached = sum(e.tree_rank(sum(arcs)) for e in eng)
+    flooded = [e.tree_flood() for e in eng]
+    settled = sum(f[0] for f in flooded)
+    ok = unreached == 0 and not any(f[1] for f in flooded) and settled == squares
+    if ok:
+        share("inmask", [b * 4 for b in bases], [n * 4 for n in ntiles])
+        share("loc", [b * 256 for b in bases], [n * 256 for n in ntiles])
+        ok = sum(e.tree_levels(settled) for e in eng) == 0
+    for e in eng:
+        e.tree_finish(ok)
+    return ok
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("builder,rows,cols,nb", [("kruskal", 511, 383, 2), ("wilson", 767, 257, 3), ("rdfs", 1023, 515, 4), ("kruskal", 2047, 1025, 8)])
+def test_band_tree_entry_points_one_process(lab, O, builder, rows, cols, nb):
+    """The lab_band_tree_* kernels: one tree across 2-8 bands on ONE device, driven in lock step by this process."""
+    import torch
+
+    from mazes_b200 import bands
+
+    maze = lab.build_maze(builder, rows, cols, seed=78)
+    split = bands.split_rows(rows, nb)
+    sq = [torch.from_numpy(maze[r0 : r0 + n].view(np.int16).copy()).cuda() for r0, n in split]
+    lv = [torch.full((n, cols), 0x5A5A5A5A, dtype=torch.int32, device="cuda") for _, n in split]
+    eng = [bands.GpuBandEngine(lab, s) for s in sq]
+    for e, l in zip(eng, lv):
+        e.grid.bind_levels(0, l.data_ptr())
+    start = lab.distance_start(rows, cols)
+    for e, (r0, n) in zip(eng, split):
+        e.begin((start[0] - r0, start[1]) if r0 <= start[0] < r0 + n else None)
+    rows_p = [tuple(t.clone() for t in e.path_rows()) for e in eng]
+    for i, e in enumerate(eng):
+        e.set_neighbour_paths(rows_p[i - 1][1] if i > 0 else None, rows_p[i + 1][0] if i < nb - 1 else None)
+    assert _lockstep_tree(eng, split, start, cols)
+    res = [e.finish() for e in eng]
+    assert all(e.grid.stats()["tree_used"] == 1 for e in eng)
+    g_ref, d_ref, mx_ref, settled_ref = O.distance_map(maze)
+    got_d = np.concatenate([l.cpu().numpy().view(np.uint32) for l in lv])
+    got_g = np.concatenate([s.cpu().numpy().view(np.uint16) for s in sq])
+    assert (got_d == d_ref).all() and (got_g == g_ref).all()
+    assert max(r[0] for r in res) == mx_ref and sum(r[1] for r in res) == settled_ref
+
+
+@pytest.mark.gpu
+def test_band_tree_gives_a_non_tree_back_to_the_wave(lab, O):
+    """A maze with a tree's counts that is not one: the flood says so, every band wipes its field and the relax /
+    exchange loop of test_band_entry_points_one_process takes over."""
+    import torch
+
+    from mazes_b200 import bands
+    from test_tree_pipeline import tree_looking_non_tree
+
+    rows, cols, nb = 511, 767, 3
+    maze = tree_looking_non_tree(lab, rows, cols, 3)
+    split = bands.split_rows(rows, nb)
+    sq = [torch.from_numpy(maze[r0 : r0 + n].view(np.int16).copy()).cuda() for r0, n in split]
+    lv = [torch.empty((n, cols), dtype=torch.int32, device="cuda") for _, n in split]
+    eng = [bands.GpuBandEngine(lab, s) for s in sq]
+    for e, l in zip(eng, lv):
+        e.grid.bind_levels(0, l.data_ptr())
+    start = lab.distance_start(rows, cols)
+    for e, (r0, n) in zip(eng, split):
+        e.begin((start[0] - r0, start[1]) if r0 <= start[0] < r0 + n else None)
+    rows_p = [tuple(t.clone() for t in e.path_rows()) for e in eng]
+    for i, e in enumerate(eng):
+        e.set_neighbour_paths(rows_p[i - 1][1] if i > 0 else None, rows_p[i + 1][0] if i < nb - 1 else None)
+    assert not _lockstep_tree(eng, split, start, cols)
     rounds = 0
     while True:
         rounds += 1
