@@ -170,34 +170,35 @@ int lab_band_finish(lab_grid *g, uint64_t *local_max, uint64_t *local_settled);
  * per cent of the squares), so the arrays they work on are GLOBAL: indexed by slot = global tile * 256 +
  * side * 64 + position, global tile = tile_base + the band's tile.  The caller owns them (device memory,
  * e.g. torch tensors it can hand to NCCL) and moves the bands' slices between the phases:
- *     lab_band_tree_bind      succ0, s0, s1, r0, r1: uint32[ntiles_global*256 + 2]; loc: uint32[ntiles_global*256];
- *                             inmask: uint64[ntiles_global*4]; alist_global: uint32[ntiles_global*256];
- *                             alist_local: uint32[the band's tiles * 256]
- *     lab_band_tree_count     -> the band's passable squares and adjacent pairs; sum over the ranks: a tree has
- *                             pairs == squares - 1 (anything else: stay with the loop above)
- *     lab_band_tree_walk      (global sums in) Euler-tour segments of the band's tiles -> succ0 slice
- *                             [tile_base*256, +tiles*256), the band's crossings -> alist_local[0, arcs_local)
- *          exchange: every rank gets all succ0 slices; succ0[ntiles_global*256 .. +2) (the tour's two ends) from
- *          the rank that holds the start; alist_global = the ranks' alist_local pieces, concatenated;
- *          s0 = succ0; r0 = 1 everywhere but r0[ntiles_global*256 + 1] = 0
- *     lab_band_tree_rank      (arcs_global in) ranks every crossing along the tour, orients the band's tiles
- *                             -> inmask slice [tile_base*4, +tiles*4); unreached != 0 on any rank: not a tree
- *          exchange: every rank gets all inmask slices
- *     lab_band_tree_flood     packed component / local level field of the band, loc slice [tile_base*256, ...)
- *                             -> the band's settled squares (sum over ranks must equal the squares), error
- *          exchange: every rank gets all loc slices
- *     lab_band_tree_levels    (settled sum in) exact level of every entry crossing; error != 0: not a tree
- *     lab_band_tree_finish    commit = 1 (no rank saw an error): the band's levels are final, lab_band_finish next;
- *                             commit = 0: the field is wiped and the relax / exchange loop above takes over
+ *     lab_band_tree_bind      succ0, s0, s1, r0, r1: uint32[ntiles_global*256 + 2]; loc, alist: uint32[ntiles_global*256];
+ *                             inmask: uint64[ntiles_global*4]
+ *     lab_band_tree_count     -> the band's passable squares, adjacent pairs and border crossings.  Over all ranks a
+ *                             tree has sum(pairs) == sum(squares) - 1 (anything else: stay with the loop above)
+ *     lab_band_tree_walk      (the sums in; alist_base = the crossings of the bands before this one) Euler-tour
+ *                             segments of the band's tiles -> succ0 slice [tile_base*256, +tiles*256), the band's
+ *                             crossings -> alist[alist_base, +crossings)
+ *          exchange: every rank gets all succ0 and alist slices, and succ0[ntiles_global*256 .. +2) (the tour's two
+ *          ends) from the rank that holds the start
+ *     lab_band_tree_rank      (arcs_global = all crossings) ranks every crossing along the tour, orients the band's
+ *                             tiles -> inmask slice [tile_base*4, +tiles*4)
+ *     lab_band_tree_flood     packed component / local-level field of the band, loc slice [tile_base*256, ...)
+ *                             -> unreached crossings, the band's settled squares, error.  Over all ranks: one tree
+ *                             iff no rank has unreached crossings or an error and sum(settled) == sum(squares);
+ *                             if not: lab_band_tree_abort on every rank (wipes the field), then the loop above
+ *          exchange: every rank gets all inmask and loc slices
+ *     lab_band_tree_levels    (the settled sum in) exact level of every entry crossing, then the band's final
+ *                             levels.  Every rank computes the same entry levels from the same arrays, so all reach
+ *                             the same verdict `used`: 1 = the band's field is final (lab_band_finish next); 0 = not
+ *                             a tree after all, the field is wiped, the loop above takes over
  * Results are identical to the loop's, bit for bit. */
 int lab_band_tree_bind(lab_grid *g, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *s0, void *s1, void *r0,
-                       void *r1, void *loc, void *inmask, void *alist_global, void *alist_local);
-int lab_band_tree_count(lab_grid *g, uint64_t *squares, uint64_t *pairs);
-int lab_band_tree_walk(lab_grid *g, uint64_t squares_global, uint64_t pairs_global, uint32_t *arcs_local, uint32_t *error);
-int lab_band_tree_rank(lab_grid *g, uint32_t arcs_global, uint32_t *unreached);
-int lab_band_tree_flood(lab_grid *g, uint64_t *settled_local, uint32_t *error);
-int lab_band_tree_levels(lab_grid *g, uint64_t settled_global, uint32_t *error);
-int lab_band_tree_finish(lab_grid *g, int commit);
+                       void *r1, void *loc, void *inmask, void *alist);
+int lab_band_tree_count(lab_grid *g, uint64_t *squares, uint64_t *pairs, uint32_t *crossings);
+int lab_band_tree_walk(lab_grid *g, uint64_t squares_global, uint64_t pairs_global, uint32_t alist_base);
+int lab_band_tree_rank(lab_grid *g, uint32_t arcs_global);
+int lab_band_tree_flood(lab_grid *g, uint32_t *unreached, uint64_t *settled_local, uint32_t *error);
+int lab_band_tree_levels(lab_grid *g, uint64_t settled_global, int32_t *used);
+int lab_band_tree_abort(lab_grid *g);
 
 int lab_last_timing(const lab_grid *g, lab_timing *out);
 int lab_last_stats(const lab_grid *g, lab_stats *out);

@@ -97,10 +97,10 @@ class _BandEngine:
         return self.torch.empty_like(like)
 
     # -- the spanning-tree pipeline across bands (lab_band_tree_*) --
-    def tree_bind(self, tile_base: int, ntiles_global: int, ntiles_local: int):
+    def tree_bind(self, tile_base: int, ntiles_global: int):
         """Allocates (once per maze size) the global crossing arrays and binds them.  Returns the dict of tensors."""
         torch = self.torch
-        key = (tile_base, ntiles_global, ntiles_local)
+        key = (tile_base, ntiles_global)
         if self._tree_bufs is None or self._tree_bufs["key"] != key:
             n = ntiles_global * 256
             dev = self.row_device
@@ -110,41 +110,36 @@ class _BandEngine:
             b["loc"] = torch.empty(n, dtype=torch.int32, device=dev)
             b["inmask"] = torch.zeros(ntiles_global * 4, dtype=torch.int64, device=dev)
             b["alist"] = torch.empty(n, dtype=torch.int32, device=dev)
-            b["alist_local"] = torch.empty(ntiles_local * 256, dtype=torch.int32, device=dev)
             self._tree_bufs = b
         b = self._tree_bufs
         self._check(self._f("tree_bind")(self.h, c_uint32(tile_base), c_uint32(ntiles_global), self._ptr(b["succ0"]), self._ptr(b["s0"]),
                                          self._ptr(b["s1"]), self._ptr(b["r0"]), self._ptr(b["r1"]), self._ptr(b["loc"]),
-                                         self._ptr(b["inmask"]), self._ptr(b["alist"]), self._ptr(b["alist_local"])))
+                                         self._ptr(b["inmask"]), self._ptr(b["alist"])))
         return b
 
-    def tree_count(self) -> Tuple[int, int]:
-        v, e = c_uint64(), c_uint64()
-        self._check(self._f("tree_count")(self.h, byref(v), byref(e)))
-        return int(v.value), int(e.value)
+    def tree_count(self) -> Tuple[int, int, int]:
+        v, e, x = c_uint64(), c_uint64(), c_uint32()
+        self._check(self._f("tree_count")(self.h, byref(v), byref(e), byref(x)))
+        return int(v.value), int(e.value), int(x.value)
 
-    def tree_walk(self, squares_global: int, pairs_global: int) -> Tuple[int, int]:
-        n, err = c_uint32(), c_uint32()
-        self._check(self._f("tree_walk")(self.h, c_uint64(squares_global), c_uint64(pairs_global), byref(n), byref(err)))
-        return int(n.value), int(err.value)
+    def tree_walk(self, squares_global: int, pairs_global: int, alist_base: int):
+        self._check(self._f("tree_walk")(self.h, c_uint64(squares_global), c_uint64(pairs_global), c_uint32(alist_base)))
 
-    def tree_rank(self, arcs_global: int) -> int:
-        u = c_uint32()
-        self._check(self._f("tree_rank")(self.h, c_uint32(arcs_global), byref(u)))
-        return int(u.value)
+    def tree_rank(self, arcs_global: int):
+        self._check(self._f("tree_rank")(self.h, c_uint32(arcs_global)))
 
-    def tree_flood(self) -> Tuple[int, int]:
-        st, err = c_uint64(), c_uint32()
-        self._check(self._f("tree_flood")(self.h, byref(st), byref(err)))
-        return int(st.value), int(err.value)
+    def tree_flood(self) -> Tuple[int, int, int]:
+        u, st, err = c_uint32(), c_uint64(), c_uint32()
+        self._check(self._f("tree_flood")(self.h, byref(u), byref(st), byref(err)))
+        return int(u.value), int(st.value), int(err.value)
 
-    def tree_levels(self, settled_global: int) -> int:
-        err = c_uint32()
-        self._check(self._f("tree_levels")(self.h, c_uint64(settled_global), byref(err)))
-        return int(err.value)
+    def tree_levels(self, settled_global: int) -> bool:
+        used = ctypes.c_int32()
+        self._check(self._f("tree_levels")(self.h, c_uint64(settled_global), byref(used)))
+        return used.value == 1
 
-    def tree_finish(self, commit: bool):
-        self._check(self._f("tree_finish")(self.h, c_int(1 if commit else 0)))
+    def tree_abort(self):
+        self._check(self._f("tree_abort")(self.h))
 
 
 class GpuBandEngine(_BandEngine):
@@ -216,21 +211,31 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
             break
     mx, settled = engine.finish()
     agg = torch.tensor([mx, settled], dtype=torch.int64, device=engine.row_device)
-    mx_t = agg[:1].clone()
-    st_t = agg[1:].clone()
-    dist.all_reduce(mx_t, op=dist.ReduceOp.MAX, group=group)
-    dist.all_reduce(st_t, op=dist.ReduceOp.SUM, group=group)
-    return {"max": int(mx_t.item()), "settled": int(st_t.item()), "rounds": rounds, "tree": bool(tree)}
+    every = [torch.empty_like(agg) for _ in range(world)]
+    dist.all_gather(every, agg, group=group)
+    every = [e.tolist() for e in every]
+    return {"max": max(int(e[0]) for e in every), "settled": sum(int(e[1]) for e in every), "rounds": rounds, "tree": bool(tree)}
 
 
 def _share(dist, t, offs, lens, rank, world, group):
     """Every rank contributes t[offs[rank] : offs[rank] + lens[rank]]; afterwards all ranks hold all slices."""
     if world == 1:
         return
-    if len(set(lens)) == 1 and all(offs[r] == offs[0] + r * lens[0] for r in range(world)) and dist.get_backend(group) == "nccl":
+    flat = dist.get_backend(group) == "nccl"
+    if flat and len(set(lens)) == 1 and all(offs[r] == offs[0] + r * lens[0] for r in range(world)):
         dist.all_gather_into_tensor(t[offs[0] : offs[0] + world * lens[0]], t[offs[rank] : offs[rank] + lens[rank]].clone(), group=group)
         return
-    for r in range(world):  # uneven bands (or a backend without the flat all-gather): one broadcast per band
+    if flat:  # uneven pieces: one all-gather of padded pieces, then the valid parts into place
+        longest = max(lens)
+        mine = t.new_empty(longest)
+        mine[: lens[rank]].copy_(t[offs[rank] : offs[rank] + lens[rank]])
+        every = t.new_empty(world * longest)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        for r in range(world):
+            if r != rank and lens[r]:
+                t[offs[r] : offs[r] + lens[r]].copy_(every[r * longest : r * longest + lens[r]])
+        return
+    for r in range(world):  # (gloo) one broadcast per band
         if lens[r]:
             dist.broadcast(t[offs[r] : offs[r] + lens[r]], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
 
@@ -246,62 +251,55 @@ def _sharded_tree(engine, start_global, row0, rows_local, group) -> bool:
     dev = engine.row_device
     tiles_x = engine.cols_padded // TS
 
-    def agree(values, op):
+    def gather(values):
+        """every rank's list of ints -> list (by rank) of lists, on the host"""
         t = torch.tensor(values, dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=op, group=group)
-        return [int(x) for x in t.tolist()]
+        if world == 1:
+            return [[int(x) for x in t.tolist()]]
+        if dist.get_backend(group) == "nccl":
+            out = torch.empty(world * len(values), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(out, t, group=group)
+            return [[int(x) for x in row] for row in out.view(world, len(values)).tolist()]
+        every = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(every, t, group=group)
+        return [[int(x) for x in e.tolist()] for e in every]
 
-    # who holds which tiles (bands are whole tile rows, in rank order)
-    mine = torch.tensor([row0, rows_local], dtype=torch.int64, device=dev)
-    if world > 1:
-        every = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(every, mine, group=group)
-        split = [tuple(int(x) for x in e.tolist()) for e in every]
-    else:
-        split = [(row0, rows_local)]
-    tile_rows = [(n + TS - 1) // TS for _, n in split]
-    bases = [(r0 // TS) * tiles_x for r0, _ in split]
-    ntiles = [tr * tiles_x for tr in tile_rows]
-    ntiles_global = sum(ntiles)
-    if any(r0 % TS for r0, _ in split) or any(bases[r] != sum(ntiles[:r]) for r in range(world)) or ntiles_global * 256 + 2 >= 1 << 32:
+    # who holds which tiles (bands are whole tile rows, in rank order); cached with the arrays
+    lay = getattr(engine, "_tree_layout", None)
+    if lay is None or lay["mine"] != (row0, rows_local, world):
+        split = [tuple(x) for x in gather([row0, rows_local])]
+        tile_rows = [(n + TS - 1) // TS for _, n in split]
+        bases = [(r0 // TS) * tiles_x for r0, _ in split]
+        ntiles = [tr * tiles_x for tr in tile_rows]
+        total = sum(ntiles)
+        ok = not (any(r0 % TS for r0, _ in split) or any(bases[r] != sum(ntiles[:r]) for r in range(world)) or total * 256 + 2 >= 1 << 32)
+        lay = {"mine": (row0, rows_local, world), "split": split, "bases": bases, "ntiles": ntiles, "total": total, "ok": ok}
+        engine._tree_layout = lay
+    if not lay["ok"]:
         return False
-    b = engine.tree_bind(bases[rank], ntiles_global, ntiles[rank])
-    nslots = ntiles_global * 256
+    split, bases, ntiles, total = lay["split"], lay["bases"], lay["ntiles"], lay["total"]
+    b = engine.tree_bind(bases[rank], total)
+    nslots = total * 256
 
-    squares, pairs = agree(list(engine.tree_count()), dist.ReduceOp.SUM)
+    counts = gather(list(engine.tree_count()))
+    squares, pairs = sum(c[0] for c in counts), sum(c[1] for c in counts)
     if squares < 2 or pairs + 1 != squares:
         return False  # (nothing has been written yet)
-    arcs_local, err = engine.tree_walk(squares, pairs)
-    counts = torch.tensor([arcs_local, err], dtype=torch.int64, device=dev)
-    if world > 1:
-        every = [torch.empty_like(counts) for _ in range(world)]
-        dist.all_gather(every, counts, group=group)
-        counts_all = [tuple(int(x) for x in e.tolist()) for e in every]
-    else:
-        counts_all = [(arcs_local, err)]
-    if any(e for _, e in counts_all):
-        return False
-    arcs = [n for n, _ in counts_all]
+    arcs = [c[2] for c in counts]
     arc_offs = [sum(arcs[:r]) for r in range(world)]
-    arcs_global = sum(arcs)
+    engine.tree_walk(squares, pairs, arc_offs[rank])
     # the tour's segments of every band, its two ends from the band that holds the start, the list of crossings
     _share(dist, b["succ0"], [x * 256 for x in bases], [x * 256 for x in ntiles], rank, world, group)
     owner = next((r for r, (r0, n) in enumerate(split) if r0 <= start_global[0] < r0 + n), 0)
     if world > 1:
         dist.broadcast(b["succ0"][nslots : nslots + 2], src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
-    b["alist"][arc_offs[rank] : arc_offs[rank] + arcs[rank]].copy_(b["alist_local"][: arcs[rank]])
     _share(dist, b["alist"], arc_offs, arcs, rank, world, group)
-    b["s0"].copy_(b["succ0"])
-    b["r0"].fill_(1)
-    b["r0"][nslots + 1] = 0  # END
-    unreached = engine.tree_rank(arcs_global)
-    settled_local, err = engine.tree_flood()
-    unreached, settled, err = agree([unreached, settled_local, err], dist.ReduceOp.SUM)
-    ok = unreached == 0 and err == 0 and settled == squares
-    if ok:
-        _share(dist, b["inmask"], [x * 4 for x in bases], [x * 4 for x in ntiles], rank, world, group)
-        _share(dist, b["loc"], [x * 256 for x in bases], [x * 256 for x in ntiles], rank, world, group)
-        ok = agree([engine.tree_levels(settled)], dist.ReduceOp.SUM)[0] == 0
-    engine.tree_finish(ok)
-    return ok
+    engine.tree_rank(sum(arcs))
+    flags = gather(list(engine.tree_flood()))
+    settled = sum(f[1] for f in flags)
+    if any(f[0] or f[2] for f in flags) or settled != squares:
+        engine.tree_abort()
+        return False
+    _share(dist, b["inmask"], [x * 4 for x in bases], [x * 4 for x in ntiles], rank, world, group)
+    _share(dist, b["loc"], [x * 256 for x in bases], [x * 256 for x in ntiles], rank, world, group)
+    return engine.tree_levels(settled)

@@ -51,6 +51,8 @@ struct Tree_ctl {
     // bounding box of the passable squares (0x7FFFFFFF - min as a running max, so that the all-zero reset
     // means "nothing yet"): a box that holds exactly V squares is an OPEN ROOM (device/room.cuh)
     uint32_t box_r0_inv, box_r1, box_c0_inv, box_c1;
+    uint32_t crossings;  // border crossings of the tiles counted (= the entries the walk will add to alist)
+    uint32_t alist_base; // row bands: where this band's piece of the global crossing list starts
 };
 
 struct Tree {
@@ -88,6 +90,7 @@ LAB_DEV uint32_t tree_twin(Geom const &g, uint32_t a) {
 LAB_DEV void tree_count_body(Params const &p, Tree const &tr, long long gwarp, long long nwarps, int lane) {
     unsigned long long v = 0, e = 0;
     uint32_t r0i = 0, r1 = 0, c0i = 0, c1 = 0; // the warp's share of the bounding box (see Tree_ctl)
+    uint32_t nx = 0;
     for (long long t = gwarp; t < p.g.ntiles; t += nwarps) {
         uint64_t const P0 = lab_ld_ro(p.path + t * TS + 2 * lane), P1 = lab_ld_ro(p.path + t * TS + 2 * lane + 1);
         if (P0 | P1) {
@@ -105,8 +108,12 @@ LAB_DEV void tree_count_body(Params const &p, Tree const &tr, long long gwarp, l
         }
         v += static_cast<unsigned>(lab_popc64(P0) + lab_popc64(P1));
         e += static_cast<unsigned>(lab_popc64(P0 & (P0 >> 1)) + lab_popc64(P1 & (P1 >> 1)) + lab_popc64(P0 & P1) + lab_popc64(P1 & below));
-        if (lane < 2) { // crossings counted once: this tile's S and E borders
-            e += static_cast<unsigned>(lab_popc64(lab_ld_ro(p.cross + t * 4 + (lane == 0 ? SIDE_S : SIDE_E))));
+        if (lane < 4) {
+            uint32_t const x = static_cast<uint32_t>(lab_popc64(lab_ld_ro(p.cross + t * 4 + lane)));
+            nx += x;
+            if (lane == SIDE_S || lane == SIDE_E) { // (as adjacent pairs they are counted once: this tile's S and E borders)
+                e += x;
+            }
         }
     }
     uint32_t const vs = lab_reduce_add(static_cast<uint32_t>(v)), es = lab_reduce_add(static_cast<uint32_t>(e));
@@ -115,7 +122,11 @@ LAB_DEV void tree_count_body(Params const &p, Tree const &tr, long long gwarp, l
     r1 = lab_reduce_max(r1);
     c0i = lab_reduce_max(c0i);
     c1 = lab_reduce_max(c1);
+    nx = lab_reduce_add(nx);
     if (lane == 0) {
+        if (nx) {
+            lab_atomic_add(&tr.tc->crossings, nx);
+        }
         lab_atomic_add(reinterpret_cast<uint64_t *>(&tr.tc->V), (static_cast<uint64_t>(vh) << 32) + vs);
         lab_atomic_add(reinterpret_cast<uint64_t *>(&tr.tc->E), (static_cast<uint64_t>(eh) << 32) + es);
         if (r0i) { // (some square of this warp's tiles is passable)
@@ -407,7 +418,7 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
     uint32_t const xtotal = lab_shfl(xincl, 31);
     uint32_t xbase = 0;
     if (lane == 0 && xtotal) {
-        xbase = lab_atomic_add(&tr.tc->n_arcs, xtotal);
+        xbase = lab_atomic_add(&tr.tc->n_arcs, xtotal) + tr.tc->alist_base;
     }
     xbase = lab_shfl(xbase, 0);
     {
@@ -467,6 +478,17 @@ LAB_DEV void tree_init_body(Params const &p, Tree const &tr) {
         tr.s[b][END] = END;
         tr.r[b][ROOT] = 1u;
         tr.r[b][END] = 0u;
+    }
+}
+
+// Row bands: the ranks have exchanged their slices of succ0 (and its two list ends); this makes round 0's
+// input of the ranking from them, the way walk_tile leaves it on a single GPU: s[0] = succ0, r[0] = 1 per
+// segment (slots that are no crossings are never looked at), r[0][END] = 0.
+LAB_DEV void tree_seed_body(Tree const &tr, long long gthread, long long nthreads) {
+    long long const n = static_cast<long long>(tr.nslots) + 2;
+    for (long long i = gthread; i < n; i += nthreads) {
+        tr.s[0][i] = tr.succ0[i];
+        tr.r[0][i] = i + 1 == n ? 0u : 1u;
     }
 }
 

@@ -52,6 +52,9 @@ __global__ void __launch_bounds__(128, 3) k_bfs_tiles(Params p) {
 // ---- spanning-tree pipeline (device/tree.cuh) ----
 __global__ void __launch_bounds__(256) k_tree_count(Params p, Tree tr) { tree_count_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void k_tree_init(Params p, Tree tr) { tree_init_body(p, tr); }
+__global__ void __launch_bounds__(256) k_tree_seed(Tree tr) {
+    tree_seed_body(tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
+}
 __global__ void __launch_bounds__(128) k_tree_walk(Params p, Tree tr) {
     __shared__ __align__(16) uint64_t sm[4][WALK_U64];
     tree_walk_body(p, tr, lane_id(), sm[threadIdx.x >> 5]);
@@ -376,7 +379,6 @@ struct lab_grid {
     bool tree_cfg = false;
     // the pipeline across row bands (lab_band_tree_*): the caller's global arrays, this band's control block
     Tree band_tree{};
-    uint32_t *band_alist_global = nullptr, *band_alist_local = nullptr;
     uint32_t band_ntiles_global = 0;
     bool band_tree_bound = false;
     int tree_coop_blocks = 0; // co-resident blocks of the multi-round kernels
@@ -1385,8 +1387,8 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
 
 // ---- the spanning-tree pipeline across row bands (device/tree.cuh; protocol in include/labyrinth_b200.h) ----
 int lab_band_tree_bind(lab_grid *h, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *s0, void *s1, void *r0, void *r1,
-                       void *loc, void *inmask, void *alist_global, void *alist_local) {
-    if (!h || !succ0 || !s0 || !s1 || !r0 || !r1 || !loc || !inmask || !alist_global || !alist_local) {
+                       void *loc, void *inmask, void *alist) {
+    if (!h || !succ0 || !s0 || !s1 || !r0 || !r1 || !loc || !inmask || !alist) {
         return fail(LAB_ERR_ARG, "lab_band_tree_bind: null argument");
     }
     if (static_cast<unsigned long long>(ntiles_global) * SLOTS + 2 >= (1ull << 32) || tile_base + static_cast<uint32_t>(h->g.ntiles) > ntiles_global) {
@@ -1406,12 +1408,10 @@ int lab_band_tree_bind(lab_grid *h, uint32_t tile_base, uint32_t ntiles_global, 
     tr.r[1] = static_cast<uint32_t *>(r1);
     tr.loc = static_cast<uint32_t *>(loc);
     tr.inmask = static_cast<uint64_t *>(inmask);
-    tr.alist = static_cast<uint32_t *>(alist_local);
+    tr.alist = static_cast<uint32_t *>(alist);
     tr.nslots = ntiles_global * SLOTS;
     tr.tile_base = tile_base;
     tr.banded = 1;
-    h->band_alist_global = static_cast<uint32_t *>(alist_global);
-    h->band_alist_local = static_cast<uint32_t *>(alist_local);
     h->band_ntiles_global = ntiles_global;
     h->band_tree_bound = true;
     return LAB_OK;
@@ -1433,7 +1433,7 @@ static int band_tree_coop_blocks(lab_grid *h) {
         1, std::min<long long>(h->tree_coop_blocks, (static_cast<long long>(h->band_ntiles_global) * 64 + 512 * JUMP_K - 1) / (512 * JUMP_K))));
 }
 
-int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs) {
+int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs, uint32_t *crossings) {
     int rc = band_tree_ready(h, "lab_band_tree_count");
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -1449,60 +1449,51 @@ int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs) {
     if (rc) return rc;
     if (squares) *squares = tc.V;
     if (pairs) *pairs = tc.E;
+    if (crossings) *crossings = tc.crossings;
     return LAB_OK;
 }
 
-int lab_band_tree_walk(lab_grid *h, uint64_t squares_global, uint64_t pairs_global, uint32_t *arcs_local, uint32_t *error) {
+int lab_band_tree_walk(lab_grid *h, uint64_t squares_global, uint64_t pairs_global, uint32_t alist_base) {
     int rc = band_tree_ready(h, "lab_band_tree_walk");
     if (rc) return rc;
     cudaStream_t s = h->stream;
-    Tree tr = h->band_tree;
-    tr.alist = h->band_alist_local;
+    Tree const tr = h->band_tree;
     Params p = make_params(h, 1);
     unsigned long long const ve[2] = {squares_global, pairs_global};
     CU(cudaMemcpyAsync(&tr.tc->V, ve, sizeof ve, cudaMemcpyHostToDevice, s)); // (V and E are the struct's first two members)
+    CU(cudaMemcpyAsync(&tr.tc->alist_base, &alist_base, sizeof alist_base, cudaMemcpyHostToDevice, s));
     k_tree_init<<<1, 1, 0, s>>>(p, tr);
     int const walk_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_walk_per_sm);
     k_tree_walk<<<walk_blocks, 128, 0, s>>>(p, tr);
     TRACE("k_tree_walk", s);
     h->launches += 2;
     CU(cudaGetLastError());
-    Tree_ctl tc{};
-    rc = band_tree_read(h, tc);
-    if (rc) return rc;
-    if (arcs_local) *arcs_local = tc.n_arcs;
-    if (error) *error = tc.ok ? tc.walk_error : 0xFFFFu;
     return LAB_OK;
 }
 
-int lab_band_tree_rank(lab_grid *h, uint32_t arcs_global, uint32_t *unreached) {
+int lab_band_tree_rank(lab_grid *h, uint32_t arcs_global) {
     int rc = band_tree_ready(h, "lab_band_tree_rank");
     if (rc) return rc;
     cudaStream_t s = h->stream;
     Tree tr = h->band_tree;
-    tr.alist = h->band_alist_global;
     Params p = make_params(h, 1);
     CU(cudaMemcpyAsync(&tr.tc->n_arcs, &arcs_global, sizeof arcs_global, cudaMemcpyHostToDevice, s));
+    k_tree_seed<<<h->sm_count * 4, 256, 0, s>>>(tr);
     uint32_t rounds = static_cast<uint32_t>(ceil_log2(static_cast<unsigned long long>(tr.nslots) + 2));
     {
         void *args[] = {&p, &tr, &rounds};
         CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_jump<0>), dim3(band_tree_coop_blocks(h)), dim3(512), args, 0, s));
     }
     TRACE("k_tree_jump<rank+orient>", s);
-    h->launches += 1;
-    Tree_ctl tc{};
-    rc = band_tree_read(h, tc);
-    if (rc) return rc;
-    if (unreached) *unreached = tc.unreached;
+    h->launches += 2;
     return LAB_OK;
 }
 
-int lab_band_tree_flood(lab_grid *h, uint64_t *settled_local, uint32_t *error) {
+int lab_band_tree_flood(lab_grid *h, uint32_t *unreached, uint64_t *settled_local, uint32_t *error) {
     int rc = band_tree_ready(h, "lab_band_tree_flood");
     if (rc) return rc;
     cudaStream_t s = h->stream;
-    Tree tr = h->band_tree;
-    tr.alist = h->band_alist_global;
+    Tree const tr = h->band_tree;
     Params p = make_params(h, 1);
     int const fill_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_flood_per_sm);
     k_tree_flood<<<fill_blocks, 128, 4 * FLOOD_U64 * sizeof(uint64_t), s>>>(p, tr);
@@ -1512,17 +1503,19 @@ int lab_band_tree_flood(lab_grid *h, uint64_t *settled_local, uint32_t *error) {
     Tree_ctl tc{};
     rc = band_tree_read(h, tc);
     if (rc) return rc;
+    if (unreached) *unreached = tc.unreached;
     if (settled_local) *settled_local = tc.local_settled;
-    if (error) *error = tc.walk_error;
+    if (error) *error = tc.ok ? tc.walk_error : 0xFFFFu;
     return LAB_OK;
 }
 
-int lab_band_tree_levels(lab_grid *h, uint64_t settled_global, uint32_t *error) {
+// Every rank computes the same entry levels from the same (exchanged) arrays, so all of them reach the same verdict:
+// the fix-up and the gate are gated on it on the device, nothing has to be agreed on in between.
+int lab_band_tree_levels(lab_grid *h, uint64_t settled_global, int32_t *used) {
     int rc = band_tree_ready(h, "lab_band_tree_levels");
     if (rc) return rc;
     cudaStream_t s = h->stream;
     Tree tr = h->band_tree;
-    tr.alist = h->band_alist_global;
     Params p = make_params(h, 1);
     unsigned long long const st = settled_global;
     CU(cudaMemcpyAsync(&tr.tc->local_settled, &st, sizeof st, cudaMemcpyHostToDevice, s));
@@ -1532,29 +1525,27 @@ int lab_band_tree_levels(lab_grid *h, uint64_t settled_global, uint32_t *error) 
         CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_jump<1>), dim3(band_tree_coop_blocks(h)), dim3(512), args, 0, s));
     }
     TRACE("k_tree_jump<parent+prefix>", s);
-    Tree_ctl tc{};
-    rc = band_tree_read(h, tc); // (the entry levels are final: the caller's ranks agree on going on before anybody writes the field)
+    k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, tr);
+    TRACE("k_tree_fixup", s);
+    k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, tr);
+    TRACE("k_tree_gate", s);
+    h->launches += 3;
+    CU(cudaGetLastError());
+    rc = band_tree_read(h, h->tree_last);
     if (rc) return rc;
-    h->launches += 1;
-    if (error) *error = (tc.ok && tc.bad_weight == 0 && tc.walk_error == 0 && tc.unreached == 0) ? 0u : 1u;
+    if (used) *used = static_cast<int32_t>(h->tree_last.used);
     return LAB_OK;
 }
 
-int lab_band_tree_finish(lab_grid *h, int commit) {
-    int rc = band_tree_ready(h, "lab_band_tree_finish");
+// Some rank found out that the maze is not one tree: the field is wiped and the relax / exchange loop takes over.
+int lab_band_tree_abort(lab_grid *h) {
+    int rc = band_tree_ready(h, "lab_band_tree_abort");
     if (rc) return rc;
     cudaStream_t s = h->stream;
-    Tree tr = h->band_tree;
-    tr.alist = h->band_alist_global;
+    Tree const tr = h->band_tree;
     Params p = make_params(h, 1);
-    if (!commit) { // some rank found out that this is not one tree: hand the field back to the wave, clean
-        uint32_t const zero = 0;
-        CU(cudaMemcpyAsync(&tr.tc->ok, &zero, sizeof zero, cudaMemcpyHostToDevice, s));
-    } else {
-        k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, tr);
-        TRACE("k_tree_fixup", s);
-        h->launches += 1;
-    }
+    uint32_t const zero = 0;
+    CU(cudaMemcpyAsync(&tr.tc->ok, &zero, sizeof zero, cudaMemcpyHostToDevice, s));
     k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, tr);
     TRACE("k_tree_gate", s);
     h->launches += 1;

@@ -207,7 +207,6 @@ struct Emu_band {
     unsigned sched = 0;
     Tree tr{};
     Tree_ctl tc{};
-    uint32_t *alist_global = nullptr, *alist_local = nullptr;
     uint32_t ntiles_global = 0;
     Tree_ctl tree_last{};
 };
@@ -327,7 +326,7 @@ int emu_band_finish(void *h, uint64_t *local_max, uint64_t *local_settled) {
 }
 
 int emu_band_tree_bind(void *h, uint32_t tile_base, uint32_t ntiles_global, uint32_t *succ0, uint32_t *s0, uint32_t *s1, uint32_t *r0,
-                       uint32_t *r1, uint32_t *loc, uint64_t *inmask, uint32_t *alist_global, uint32_t *alist_local) {
+                       uint32_t *r1, uint32_t *loc, uint64_t *inmask, uint32_t *alist) {
     auto *e = static_cast<Emu_band *>(h);
     Tree &tr = e->tr;
     tr.succ0 = succ0;
@@ -337,20 +336,18 @@ int emu_band_tree_bind(void *h, uint32_t tile_base, uint32_t ntiles_global, uint
     tr.r[1] = r1;
     tr.loc = loc;
     tr.inmask = inmask;
-    tr.alist = alist_local;
+    tr.alist = alist;
     tr.tc = &e->tc;
     tr.nslots = ntiles_global * SLOTS;
     tr.tile_base = tile_base;
     tr.banded = 1;
-    e->alist_global = alist_global;
-    e->alist_local = alist_local;
     e->ntiles_global = ntiles_global;
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
     e->sm.assign(static_cast<size_t>(e->nwarps) * SM, 0);
     return 0;
 }
 
-int emu_band_tree_count(void *h, uint64_t *squares, uint64_t *pairs) {
+int emu_band_tree_count(void *h, uint64_t *squares, uint64_t *pairs, uint32_t *crossings) {
     auto *e = static_cast<Emu_band *>(h);
     Params p = make_params(e->w, 1);
     int const nw = e->nwarps;
@@ -359,62 +356,68 @@ int emu_band_tree_count(void *h, uint64_t *squares, uint64_t *pairs) {
     simt::launch(nw, [&](int wid, int lane) { tree_count_body(p, tr, wid, nw, lane); });
     *squares = e->tc.V;
     *pairs = e->tc.E;
+    *crossings = e->tc.crossings;
     return 0;
 }
 
-int emu_band_tree_walk(void *h, uint64_t squares_global, uint64_t pairs_global, uint32_t *arcs_local, uint32_t *error) {
+int emu_band_tree_walk(void *h, uint64_t squares_global, uint64_t pairs_global, uint32_t alist_base) {
     auto *e = static_cast<Emu_band *>(h);
     Params p = make_params(e->w, 1);
     int const nw = e->nwarps;
-    Tree tr = e->tr;
-    tr.alist = e->alist_local;
+    Tree const tr = e->tr;
     e->tc.V = squares_global;
     e->tc.E = pairs_global;
+    e->tc.alist_base = alist_base;
     tree_init_body(p, tr);
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
     simt::launch(nw, [&](int wid, int lane) { tree_walk_body(p, tr, lane, e->sm.data() + static_cast<size_t>(wid) * SM); }, e->sched);
-    *arcs_local = e->tc.n_arcs;
-    *error = e->tc.ok ? e->tc.walk_error : 0xFFFFu;
     return 0;
 }
 
-int emu_band_tree_rank(void *h, uint32_t arcs_global, uint32_t *unreached) {
+int emu_band_tree_rank(void *h, uint32_t arcs_global) {
     auto *e = static_cast<Emu_band *>(h);
     Params p = make_params(e->w, 1);
     int const nw = e->nwarps;
-    Tree tr = e->tr;
-    tr.alist = e->alist_global;
+    Tree const tr = e->tr;
     e->tc.n_arcs = arcs_global;
     long long const nthreads = static_cast<long long>(nw) * 32;
+    simt::launch(nw, [&](int wid, int lane) { tree_seed_body(tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
     int rounds = 0;
     while ((1ull << rounds) < static_cast<unsigned long long>(tr.nslots) + 2) rounds++;
     for (int r = 0; r < rounds; r++) {
         simt::launch(nw, [&](int wid, int lane) { tree_rank_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
     }
     simt::launch(nw, [&](int wid, int lane) { tree_orient_body(p, tr, wid, nw, lane); });
-    *unreached = e->tc.unreached;
     return 0;
 }
 
-int emu_band_tree_flood(void *h, uint64_t *settled_local, uint32_t *error) {
+int emu_band_tree_flood(void *h, uint32_t *unreached, uint64_t *settled_local, uint32_t *error) {
     auto *e = static_cast<Emu_band *>(h);
     Params p = make_params(e->w, 1);
     int const nw = e->nwarps;
-    Tree tr = e->tr;
-    tr.alist = e->alist_global;
+    Tree const tr = e->tr;
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
     simt::launch(nw, [&](int wid, int lane) { tree_flood_body(p, tr, lane, e->sm.data() + static_cast<size_t>(wid) * SM); }, e->sched);
+    *unreached = e->tc.unreached;
     *settled_local = e->tc.local_settled;
-    *error = e->tc.walk_error;
+    *error = e->tc.ok ? e->tc.walk_error : 0xFFFFu;
     return 0;
 }
 
-int emu_band_tree_levels(void *h, uint64_t settled_global, uint32_t *error) {
+static void emu_band_gate(Emu_band *e) {
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    Tree const tr = e->tr;
+    long long const nthreads = static_cast<long long>(nw) * 32;
+    simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    e->tree_last = e->tc;
+}
+
+int emu_band_tree_levels(void *h, uint64_t settled_global, int32_t *used) {
     auto *e = static_cast<Emu_band *>(h);
     Params p = make_params(e->w, 1);
     int const nw = e->nwarps;
-    Tree tr = e->tr;
-    tr.alist = e->alist_global;
+    Tree const tr = e->tr;
     e->tc.local_settled = settled_global;
     long long const nthreads = static_cast<long long>(nw) * 32;
     simt::launch(nw, [&](int wid, int lane) { tree_parent_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
@@ -423,24 +426,16 @@ int emu_band_tree_levels(void *h, uint64_t settled_global, uint32_t *error) {
     for (int r = 0; r < rounds; r++) {
         simt::launch(nw, [&](int wid, int lane) { tree_prefix_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
     }
-    *error = (e->tc.ok && e->tc.bad_weight == 0 && e->tc.walk_error == 0 && e->tc.unreached == 0) ? 0u : 1u;
+    simt::launch(nw, [&](int wid, int lane) { tree_fixup_body(p, tr, wid, nw, lane); });
+    emu_band_gate(e);
+    *used = static_cast<int32_t>(e->tree_last.used);
     return 0;
 }
 
-int emu_band_tree_finish(void *h, int commit) {
+int emu_band_tree_abort(void *h) {
     auto *e = static_cast<Emu_band *>(h);
-    Params p = make_params(e->w, 1);
-    int const nw = e->nwarps;
-    Tree tr = e->tr;
-    tr.alist = e->alist_global;
-    long long const nthreads = static_cast<long long>(nw) * 32;
-    if (!commit) {
-        e->tc.ok = 0;
-    } else {
-        simt::launch(nw, [&](int wid, int lane) { tree_fixup_body(p, tr, wid, nw, lane); });
-    }
-    simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
-    e->tree_last = e->tc;
+    e->tc.ok = 0;
+    emu_band_gate(e);
     return 0;
 }
 

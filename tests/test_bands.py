@@ -242,15 +242,13 @@ def test_band_entry_points_one_process(lab, O, builder, rows, cols, nb):
 def _lockstep_tree(eng, split, start, cols):
     """_sharded_tree of bands.py for several bands driven by ONE process: the collectives become copies between
     the bands' own (separate) global arrays."""
-    import torch
-
     nb = len(eng)
     tiles_x = eng[0].cols_padded // 64
     ntiles = [((n + 63) // 64) * tiles_x for _, n in split]
     bases = [(r0 // 64) * tiles_x for r0, _ in split]
     total = sum(ntiles)
     nslots = total * 256
-    bufs = [e.tree_bind(bases[i], total, ntiles[i]) for i, e in enumerate(eng)]
+    bufs = [e.tree_bind(bases[i], total) for i, e in enumerate(eng)]
 
     def share(name, offs, lens):
         for src in range(nb):
@@ -262,33 +260,29 @@ def _lockstep_tree(eng, split, start, cols):
     squares, pairs = sum(c[0] for c in counts), sum(c[1] for c in counts)
     if squares < 2 or pairs + 1 != squares:
         return False
-    walked = [e.tree_walk(squares, pairs) for e in eng]
-    if any(err for _, err in walked):
-        return False
-    arcs = [n for n, _ in walked]
+    arcs = [c[2] for c in counts]
     offs = [sum(arcs[:i]) for i in range(nb)]
+    for i, e in enumerate(eng):
+        e.tree_walk(squares, pairs, offs[i])
     share("succ0", [b * 256 for b in bases], [n * 256 for n in ntiles])
     owner = next(i for i, (r0, n) in enumerate(split) if r0 <= start[0] < r0 + n)
     for i in range(nb):
         if i != owner:
             bufs[i]["succ0"][nslots : nslots + 2].copy_(bufs[owner]["succ0"][nslots : nslots + 2])
-        bufs[i]["alist"][offs[i] : offs[i] + arcs[i]].copy_(bufs[i]["alist_local"][: arcs[i]])
     share("alist", offs, arcs)
-    for b in bufs:
-        b["s0"].copy_(b["succ0"])
-        b["r0"].fill_(1)
-        b["r0"][nslots + 1] = 0
-    unreached = sum(e.tree_rank(sum(arcs)) for e in eng)
-    flooded = [e.tree_flood() for e in eng]
-    settled = sum(f[0] for f in flooded)
-    ok = unreached == 0 and not any(f[1] for f in flooded) and settled == squares
-    if ok:
-        share("inmask", [b * 4 for b in bases], [n * 4 for n in ntiles])
-        share("loc", [b * 256 for b in bases], [n * 256 for n in ntiles])
-        ok = sum(e.tree_levels(settled) for e in eng) == 0
     for e in eng:
-        e.tree_finish(ok)
-    return ok
+        e.tree_rank(sum(arcs))
+    flags = [e.tree_flood() for e in eng]
+    settled = sum(f[1] for f in flags)
+    if any(f[0] or f[2] for f in flags) or settled != squares:
+        for e in eng:
+            e.tree_abort()
+        return False
+    share("inmask", [b * 4 for b in bases], [n * 4 for n in ntiles])
+    share("loc", [b * 256 for b in bases], [n * 256 for n in ntiles])
+    used = [e.tree_levels(settled) for e in eng]
+    assert all(u == used[0] for u in used)
+    return used[0]
 
 
 @pytest.mark.gpu
