@@ -299,7 +299,7 @@ def ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_port_baseline(maze, spec, budget_s=args.cpu_budget)
-    print(json.dumps(out))
+    emit_line(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -384,7 +384,7 @@ def ours_bands(args, lab, dist, torch, world, rank, local):
         cells = rows * cols
         alg_bytes = ALG_BYTES_PER_CELL[game] * cells
         achieved = alg_bytes / (search_ms_max / args.steps * 1e-3) / 1e9
-        print(json.dumps({
+        emit_line(json.dumps({
             "metric": "cells settled/sec (G/s) for BFS distance map & bfs-gather; % of HBM roofline",
             "value": settled / (step_ms_max * 1e-3) / 1e9, "unit": "Gcells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
@@ -485,7 +485,7 @@ def reference_arm(args):
         settled += one()
     el = time.perf_counter() - t0
     value = settled / el / 1e9
-    print(json.dumps({
+    emit_line(json.dumps({
         "impl": "reference", "metric": "cells settled/sec (G/s) for BFS distance map & bfs-gather; % of HBM roofline",
         "value": value, "unit": "Gcells/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
         "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
@@ -497,7 +497,21 @@ def reference_arm(args):
     }))
 
 
+_RESULT_FD = None
+
+
+def emit_line(line: str) -> None:
+    """The ONE JSON line goes to the process's real stdout; everything libraries print on fd 1 meanwhile (NCCL's
+    version banner, for one) has been pointed at stderr by main()."""
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (line + "\n").encode())
+
+
 def main():
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
