@@ -165,40 +165,38 @@ int lab_band_finish(lab_grid *g, uint64_t *local_max, uint64_t *local_settled);
 
 /* The spanning-tree pipeline (csrc/device/tree.cuh) across row bands: what replaces the relax / exchange
  * loop above when the maze is one tree (every reference builder without -m), whose diameter would cross the
- * band borders thousands of times.  The walk, the flood and the fix-up are tile-local and run on the band's
- * own tiles; the two pointer-jumping phases run over ALL the maze's crossings on every rank (they are a few
- * per cent of the squares), so the arrays they work on are GLOBAL: indexed by slot = global tile * 256 +
- * side * 64 + position, global tile = tile_base + the band's tile.  The caller owns them (device memory,
- * e.g. torch tensors it can hand to NCCL) and moves the bands' slices between the phases:
- *     lab_band_tree_bind      succ0, s0, s1, r0, r1: uint32[ntiles_global*256 + 2]; loc, alist: uint32[ntiles_global*256];
- *                             inmask: uint64[ntiles_global*4]
- *     lab_band_tree_count     -> the band's passable squares, adjacent pairs and border crossings.  Over all ranks a
- *                             tree has sum(pairs) == sum(squares) - 1 (anything else: stay with the loop above)
- *     lab_band_tree_walk      (the sums in; alist_base = the crossings of the bands before this one) Euler-tour
- *                             segments of the band's tiles -> succ0 slice [tile_base*256, +tiles*256), the band's
- *                             crossings -> alist[alist_base, +crossings)
- *          exchange: every rank gets all succ0 and alist slices, and succ0[ntiles_global*256 .. +2) (the tour's two
- *          ends) from the rank that holds the start
- *     lab_band_tree_rank      (arcs_global = all crossings) ranks every crossing along the tour, orients the band's
- *                             tiles -> inmask slice [tile_base*4, +tiles*4)
- *     lab_band_tree_flood     packed component / local-level field of the band, loc slice [tile_base*256, ...)
- *                             -> unreached crossings, the band's settled squares, error.  Over all ranks: one tree
- *                             iff no rank has unreached crossings or an error and sum(settled) == sum(squares);
- *                             if not: lab_band_tree_abort on every rank (wipes the field), then the loop above
- *          exchange: every rank gets all inmask and loc slices
- *     lab_band_tree_levels    (the settled sum in) exact level of every entry crossing, then the band's final
- *                             levels.  Every rank computes the same entry levels from the same arrays, so all reach
- *                             the same verdict `used`: 1 = the band's field is final (lab_band_finish next); 0 = not
- *                             a tree after all, the field is wiped, the loop above takes over
+ * band borders thousands of times.  Everything heavy is local: the walk, the flood and the fix-up work on the
+ * band's own tiles, and each of the two pointer-jumping phases first contracts the band's own part of the
+ * list (pointers are followed only inside the band's slots).  What is left of a list then runs over the bands'
+ * BORDER TILE ROWS only (the first and last tile row of every band: the only tiles another band's pointers can
+ * lead into); the ranks all-gather those rows -- one fixed-size chunk of uint32 per rank and stage, with the
+ * rank's error flags and counts in its header -- every rank finishes the short list itself, and a last local
+ * pass adds the two.  Three all-gathers per map, whatever its diameter; the ranks agree on "one tree or not"
+ * through the flags in the chunks, without a host round trip.
+ *     lab_band_tree_bind      the caller's device arrays, indexed by slot = global tile * 256 + side * 64 + position
+ *                             (global tile = tile_base + the band's tile): succ0, s0, s1, r0, r1: uint32[ntiles_global*256+2];
+ *                             loc: uint32[ntiles_global*256]; inmask: uint64[ntiles_global*4]; alist: uint32[the band's
+ *                             tiles * 256]; border_list: the slots of every band's first and last tile row (uint32
+ *                             [border_count]); layout: {tile_base, ntiles} of every rank (uint32[world][2])
+ *     lab_band_tree_count     -> the band's passable squares, adjacent pairs, border crossings.  Over all ranks a tree
+ *                             has sum(pairs) == sum(squares) - 1 (anything else: stay with the loop above)
+ *     lab_band_tree_rank_local   (the sums in) walk + windowed ranking                      -> chunk 1
+ *     lab_band_tree_flood        (all ranks' chunks 1 in; root_rank = who holds the start) short list, final ranks,
+ *                                orientation, flood                                          -> chunk 2
+ *     lab_band_tree_prefix_local (all chunks 2 in) parents + windowed prefix sums            -> chunk 3
+ *     lab_band_tree_levels       (all chunks 3 in) short list, the band's final levels -> used: 1 = the field is final
+ *                                (lab_band_finish next); 0 = not one tree, the field is wiped, the loop above takes over
+ *     lab_band_tree_chunk_words  uint32 words of a stage's chunk (stage 1..3)
  * Results are identical to the loop's, bit for bit. */
 int lab_band_tree_bind(lab_grid *g, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *s0, void *s1, void *r0,
-                       void *r1, void *loc, void *inmask, void *alist);
+                       void *r1, void *loc, void *inmask, void *alist, const void *border_list, uint32_t border_count,
+                       const void *layout, int world, int me);
+int lab_band_tree_chunk_words(const lab_grid *g, int stage);
 int lab_band_tree_count(lab_grid *g, uint64_t *squares, uint64_t *pairs, uint32_t *crossings);
-int lab_band_tree_walk(lab_grid *g, uint64_t squares_global, uint64_t pairs_global, uint32_t alist_base);
-int lab_band_tree_rank(lab_grid *g, uint32_t arcs_global);
-int lab_band_tree_flood(lab_grid *g, uint32_t *unreached, uint64_t *settled_local, uint32_t *error);
-int lab_band_tree_levels(lab_grid *g, uint64_t settled_global, int32_t *used);
-int lab_band_tree_abort(lab_grid *g);
+int lab_band_tree_rank_local(lab_grid *g, uint64_t squares_global, uint64_t pairs_global, void *chunk1);
+int lab_band_tree_flood(lab_grid *g, const void *all_chunks1, int root_rank, void *chunk2);
+int lab_band_tree_prefix_local(lab_grid *g, const void *all_chunks2, void *chunk3);
+int lab_band_tree_levels(lab_grid *g, const void *all_chunks3, int32_t *used);
 
 int lab_last_timing(const lab_grid *g, lab_timing *out);
 int lab_last_stats(const lab_grid *g, lab_stats *out);

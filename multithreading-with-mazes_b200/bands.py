@@ -97,24 +97,39 @@ class _BandEngine:
         return self.torch.empty_like(like)
 
     # -- the spanning-tree pipeline across bands (lab_band_tree_*) --
-    def tree_bind(self, tile_base: int, ntiles_global: int):
-        """Allocates (once per maze size) the global crossing arrays and binds them.  Returns the dict of tensors."""
+    def tree_bind(self, lay, rank: int):
+        """Allocates (once per layout) the crossing arrays, the short list over the bands' border tile rows and the
+        exchange chunks, and binds them.  lay: {"bases", "ntiles", "total", "tiles_x"}."""
         torch = self.torch
-        key = (tile_base, ntiles_global)
+        key = (tuple(lay["bases"]), tuple(lay["ntiles"]), rank)
         if self._tree_bufs is None or self._tree_bufs["key"] != key:
-            n = ntiles_global * 256
+            n = lay["total"] * 256
             dev = self.row_device
+            world = len(lay["bases"])
             b = {"key": key}
             for name in ("succ0", "s0", "s1", "r0", "r1"):
                 b[name] = torch.empty(n + 2, dtype=torch.int32, device=dev)
             b["loc"] = torch.empty(n, dtype=torch.int32, device=dev)
-            b["inmask"] = torch.zeros(ntiles_global * 4, dtype=torch.int64, device=dev)
-            b["alist"] = torch.empty(n, dtype=torch.int32, device=dev)
+            b["inmask"] = torch.zeros(lay["total"] * 4, dtype=torch.int64, device=dev)
+            b["alist"] = torch.empty(lay["ntiles"][rank] * 256, dtype=torch.int32, device=dev)
+            rows = []  # every band's first and last tile row (once, if it has only one)
+            for base, nt in zip(lay["bases"], lay["ntiles"]):
+                rows.append(base)
+                if nt > lay["tiles_x"]:
+                    rows.append(base + nt - lay["tiles_x"])
+            slots = torch.cat([torch.arange(t * 256, (t + lay["tiles_x"]) * 256, dtype=torch.int64) for t in rows])
+            b["border_list"] = slots.to(torch.int32).to(dev)
+            b["layout"] = torch.tensor([[x, y] for x, y in zip(lay["bases"], lay["ntiles"])], dtype=torch.int32, device=dev)
+            for stage in (1, 2, 3):
+                words = int(self._f("tree_chunk_words")(self.h, c_int(stage)))
+                b[f"chunk{stage}"] = torch.zeros(words, dtype=torch.int32, device=dev)
+                b[f"all{stage}"] = torch.zeros(world * words, dtype=torch.int32, device=dev)
             self._tree_bufs = b
         b = self._tree_bufs
-        self._check(self._f("tree_bind")(self.h, c_uint32(tile_base), c_uint32(ntiles_global), self._ptr(b["succ0"]), self._ptr(b["s0"]),
+        self._check(self._f("tree_bind")(self.h, c_uint32(lay["bases"][rank]), c_uint32(lay["total"]), self._ptr(b["succ0"]), self._ptr(b["s0"]),
                                          self._ptr(b["s1"]), self._ptr(b["r0"]), self._ptr(b["r1"]), self._ptr(b["loc"]),
-                                         self._ptr(b["inmask"]), self._ptr(b["alist"])))
+                                         self._ptr(b["inmask"]), self._ptr(b["alist"]), self._ptr(b["border_list"]),
+                                         c_uint32(b["border_list"].numel()), self._ptr(b["layout"]), c_int(len(lay["bases"])), c_int(rank)))
         return b
 
     def tree_count(self) -> Tuple[int, int, int]:
@@ -122,24 +137,19 @@ class _BandEngine:
         self._check(self._f("tree_count")(self.h, byref(v), byref(e), byref(x)))
         return int(v.value), int(e.value), int(x.value)
 
-    def tree_walk(self, squares_global: int, pairs_global: int, alist_base: int):
-        self._check(self._f("tree_walk")(self.h, c_uint64(squares_global), c_uint64(pairs_global), c_uint32(alist_base)))
+    def tree_rank_local(self, squares_global: int, pairs_global: int, chunk1):
+        self._check(self._f("tree_rank_local")(self.h, c_uint64(squares_global), c_uint64(pairs_global), self._ptr(chunk1)))
 
-    def tree_rank(self, arcs_global: int):
-        self._check(self._f("tree_rank")(self.h, c_uint32(arcs_global)))
+    def tree_flood(self, all1, root_rank: int, chunk2):
+        self._check(self._f("tree_flood")(self.h, self._ptr(all1), c_int(root_rank), self._ptr(chunk2)))
 
-    def tree_flood(self) -> Tuple[int, int, int]:
-        u, st, err = c_uint32(), c_uint64(), c_uint32()
-        self._check(self._f("tree_flood")(self.h, byref(u), byref(st), byref(err)))
-        return int(u.value), int(st.value), int(err.value)
+    def tree_prefix_local(self, all2, chunk3):
+        self._check(self._f("tree_prefix_local")(self.h, self._ptr(all2), self._ptr(chunk3)))
 
-    def tree_levels(self, settled_global: int) -> bool:
+    def tree_levels(self, all3) -> bool:
         used = ctypes.c_int32()
-        self._check(self._f("tree_levels")(self.h, c_uint64(settled_global), byref(used)))
+        self._check(self._f("tree_levels")(self.h, self._ptr(all3), byref(used)))
         return used.value == 1
-
-    def tree_abort(self):
-        self._check(self._f("tree_abort")(self.h))
 
 
 class GpuBandEngine(_BandEngine):
@@ -217,27 +227,24 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     return {"max": max(int(e[0]) for e in every), "settled": sum(int(e[1]) for e in every), "rounds": rounds, "tree": bool(tree)}
 
 
-def _share(dist, t, offs, lens, rank, world, group):
-    """Every rank contributes t[offs[rank] : offs[rank] + lens[rank]]; afterwards all ranks hold all slices."""
+def _all_gather(dist, out, chunk, world, group):
+    """out (world x len(chunk)) <- every rank's chunk"""
     if world == 1:
-        return
-    flat = dist.get_backend(group) == "nccl"
-    if flat and len(set(lens)) == 1 and all(offs[r] == offs[0] + r * lens[0] for r in range(world)):
-        dist.all_gather_into_tensor(t[offs[0] : offs[0] + world * lens[0]], t[offs[rank] : offs[rank] + lens[rank]].clone(), group=group)
-        return
-    if flat:  # uneven pieces: one all-gather of padded pieces, then the valid parts into place
-        longest = max(lens)
-        mine = t.new_empty(longest)
-        mine[: lens[rank]].copy_(t[offs[rank] : offs[rank] + lens[rank]])
-        every = t.new_empty(world * longest)
-        dist.all_gather_into_tensor(every, mine, group=group)
-        for r in range(world):
-            if r != rank and lens[r]:
-                t[offs[r] : offs[r] + lens[r]].copy_(every[r * longest : r * longest + lens[r]])
-        return
-    for r in range(world):  # (gloo) one broadcast per band
-        if lens[r]:
-            dist.broadcast(t[offs[r] : offs[r] + lens[r]], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        out.copy_(chunk)
+    elif dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, chunk, group=group)
+    else:
+        dist.all_gather(list(out.view(world, -1).unbind(0)), chunk, group=group)
+
+
+def tree_layout(split, tiles_x: int):
+    """Who holds which tiles: bands are whole tile rows, in rank order.  None if they are not."""
+    ntiles = [((n + TS - 1) // TS) * tiles_x for _, n in split]
+    bases = [(r0 // TS) * tiles_x for r0, _ in split]
+    total = sum(ntiles)
+    if any(r0 % TS for r0, _ in split) or any(bases[r] != sum(ntiles[:r]) for r in range(len(split))) or total * 256 + 2 >= 1 << 32:
+        return None
+    return {"split": list(split), "bases": bases, "ntiles": ntiles, "total": total, "tiles_x": tiles_x}
 
 
 def _sharded_tree(engine, start_global, row0, rows_local, group) -> bool:
@@ -249,57 +256,31 @@ def _sharded_tree(engine, start_global, row0, rows_local, group) -> bool:
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
     dev = engine.row_device
-    tiles_x = engine.cols_padded // TS
 
     def gather(values):
         """every rank's list of ints -> list (by rank) of lists, on the host"""
         t = torch.tensor(values, dtype=torch.int64, device=dev)
-        if world == 1:
-            return [[int(x) for x in t.tolist()]]
-        if dist.get_backend(group) == "nccl":
-            out = torch.empty(world * len(values), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(out, t, group=group)
-            return [[int(x) for x in row] for row in out.view(world, len(values)).tolist()]
-        every = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(every, t, group=group)
-        return [[int(x) for x in e.tolist()] for e in every]
+        out = torch.empty(world * len(values), dtype=torch.int64, device=dev)
+        _all_gather(dist, out, t, world, group)
+        return [[int(x) for x in row] for row in out.view(world, len(values)).tolist()]
 
-    # who holds which tiles (bands are whole tile rows, in rank order); cached with the arrays
-    lay = getattr(engine, "_tree_layout", None)
-    if lay is None or lay["mine"] != (row0, rows_local, world):
-        split = [tuple(x) for x in gather([row0, rows_local])]
-        tile_rows = [(n + TS - 1) // TS for _, n in split]
-        bases = [(r0 // TS) * tiles_x for r0, _ in split]
-        ntiles = [tr * tiles_x for tr in tile_rows]
-        total = sum(ntiles)
-        ok = not (any(r0 % TS for r0, _ in split) or any(bases[r] != sum(ntiles[:r]) for r in range(world)) or total * 256 + 2 >= 1 << 32)
-        lay = {"mine": (row0, rows_local, world), "split": split, "bases": bases, "ntiles": ntiles, "total": total, "ok": ok}
-        engine._tree_layout = lay
-    if not lay["ok"]:
+    cached = getattr(engine, "_tree_layout", None)
+    if cached is None or cached[0] != (row0, rows_local, world):
+        cached = ((row0, rows_local, world), tree_layout([tuple(x) for x in gather([row0, rows_local])], engine.cols_padded // TS))
+        engine._tree_layout = cached
+    lay = cached[1]
+    if lay is None:
         return False
-    split, bases, ntiles, total = lay["split"], lay["bases"], lay["ntiles"], lay["total"]
-    b = engine.tree_bind(bases[rank], total)
-    nslots = total * 256
-
+    b = engine.tree_bind(lay, rank)
     counts = gather(list(engine.tree_count()))
     squares, pairs = sum(c[0] for c in counts), sum(c[1] for c in counts)
     if squares < 2 or pairs + 1 != squares:
         return False  # (nothing has been written yet)
-    arcs = [c[2] for c in counts]
-    arc_offs = [sum(arcs[:r]) for r in range(world)]
-    engine.tree_walk(squares, pairs, arc_offs[rank])
-    # the tour's segments of every band, its two ends from the band that holds the start, the list of crossings
-    _share(dist, b["succ0"], [x * 256 for x in bases], [x * 256 for x in ntiles], rank, world, group)
-    owner = next((r for r, (r0, n) in enumerate(split) if r0 <= start_global[0] < r0 + n), 0)
-    if world > 1:
-        dist.broadcast(b["succ0"][nslots : nslots + 2], src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
-    _share(dist, b["alist"], arc_offs, arcs, rank, world, group)
-    engine.tree_rank(sum(arcs))
-    flags = gather(list(engine.tree_flood()))
-    settled = sum(f[1] for f in flags)
-    if any(f[0] or f[2] for f in flags) or settled != squares:
-        engine.tree_abort()
-        return False
-    _share(dist, b["inmask"], [x * 4 for x in bases], [x * 4 for x in ntiles], rank, world, group)
-    _share(dist, b["loc"], [x * 256 for x in bases], [x * 256 for x in ntiles], rank, world, group)
-    return engine.tree_levels(settled)
+    owner = next((r for r, (r0, n) in enumerate(lay["split"]) if r0 <= start_global[0] < r0 + n), 0)
+    engine.tree_rank_local(squares, pairs, b["chunk1"])
+    _all_gather(dist, b["all1"], b["chunk1"], world, group)
+    engine.tree_flood(b["all1"], owner, b["chunk2"])
+    _all_gather(dist, b["all2"], b["chunk2"], world, group)
+    engine.tree_prefix_local(b["all2"], b["chunk3"])
+    _all_gather(dist, b["all3"], b["chunk3"], world, group)
+    return engine.tree_levels(b["all3"])

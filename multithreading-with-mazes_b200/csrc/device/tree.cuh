@@ -70,7 +70,18 @@ struct Tree {
     // tile_base + t.  Single GPU: tile_base = 0, banded = 0.
     uint32_t tile_base;
     uint32_t banded;
+    // Pointer jumping in a WINDOW (row bands): a pointer is only followed while it stays inside slots
+    // [jump_lo, jump_hi) -- the band's own -- so a band contracts its part of the list without looking at
+    // anybody else's; what is left is a list over the bands' border tile rows, short enough for every rank
+    // to finish on its own after ONE exchange of those rows (tree_border_*_body), and a last local pass adds
+    // the two (tree_finish_jump_body).  jump_hi == 0: no window.  jump_skip: bit 0 = no parent pass before
+    // the prefix rounds, bit 1 = no orient pass after the ranking rounds (they run as launches of their own).
+    uint32_t jump_lo, jump_hi, jump_skip;
 };
+
+LAB_DEV bool tree_follow(Tree const &tr, uint32_t slot) { // may a round follow a pointer to `slot`?
+    return slot < tr.nslots && (tr.jump_hi == 0u || slot - tr.jump_lo < tr.jump_hi - tr.jump_lo);
+}
 
 LAB_DEV bool tree_live(Tree_ctl const *tc) { return tc->ok != 0 && tc->unreached == 0 && tc->bad_weight == 0 && tc->walk_error == 0; }
 
@@ -481,17 +492,6 @@ LAB_DEV void tree_init_body(Params const &p, Tree const &tr) {
     }
 }
 
-// Row bands: the ranks have exchanged their slices of succ0 (and its two list ends); this makes round 0's
-// input of the ranking from them, the way walk_tile leaves it on a single GPU: s[0] = succ0, r[0] = 1 per
-// segment (slots that are no crossings are never looked at), r[0][END] = 0.
-LAB_DEV void tree_seed_body(Tree const &tr, long long gthread, long long nthreads) {
-    long long const n = static_cast<long long>(tr.nslots) + 2;
-    for (long long i = gthread; i < n; i += nthreads) {
-        tr.s[0][i] = tr.succ0[i];
-        tr.r[0][i] = i + 1 == n ? 0u : 1u;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // 2 rank.  One round of pointer jumping: r = segments from here to the end of the tour.
 // Round `round` reads buffer round&1 and writes the other one; a round that finds the previous one
@@ -504,7 +504,7 @@ LAB_DEV void tree_rank_round_body(Tree const &tr, uint32_t round, long long gthr
     if (!tree_live(tc) || (round > 0 && lab_ld_volatile(&tc->rank_more[round - 1]) == 0)) {
         return;
     }
-    uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
+    uint32_t const ROOT = tr.nslots;
     bool const odd = round & 1u;
     uint32_t const *sin = odd ? tr.s[1] : tr.s[0], *rin = odd ? tr.r[1] : tr.r[0];
     uint32_t *sout = odd ? tr.s[0] : tr.s[1], *rout = odd ? tr.r[0] : tr.r[1];
@@ -514,14 +514,14 @@ LAB_DEV void tree_rank_round_body(Tree const &tr, uint32_t round, long long gthr
         uint32_t const a = i + 1 < n ? tr.alist[i] : ROOT;
         uint32_t const s = lab_ld_cg(sin + a);
         uint32_t const r = lab_ld_cg(rin + a);
-        if (s == END) {
-            sout[a] = END;
+        if (!tree_follow(tr, s)) { // the end of the tour, or (row bands) a segment of another band
+            sout[a] = s;
             rout[a] = r;
         } else {
             uint32_t const s2 = lab_ld_cg(sin + s);
             sout[a] = s2;
             rout[a] = r + lab_ld_cg(rin + s);
-            more |= s2 != END;
+            more |= tree_follow(tr, s2);
         }
     }
     // (thousands of warps storing to -- or reading past L1 from -- one address would serialise in L2:
@@ -543,9 +543,8 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
         return;
     }
     uint32_t const END = tr.nslots + 1u;
-    // (read past L1: in csrc/lab.cu this runs at the tail of the ranking kernel, whose other blocks wrote these)
-    bool const fin1 = lab_ld_volatile(&tc->rank_buf) != 0u;
-    uint32_t const *sfin = fin1 ? tr.s[1] : tr.s[0], *rfin = fin1 ? tr.r[1] : tr.r[0];
+    // (the rounds' result has been brought back to buffer 0: tree_jump_settle_body)
+    uint32_t const *sfin = tr.s[0], *rfin = tr.r[0];
     uint32_t bad = 0;
     for (long long t = gwarp; t < p.g.ntiles; t += nwarps) {
         long long const o = (t + tr.tile_base) * SLOTS;
@@ -561,8 +560,8 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
                 in[half] = false;
                 if ((X >> pos) & 1ull) {
                     uint32_t const tw = tree_twin(p.g, a);
-                    in[half] = rfin[a] > rfin[tw];
-                    bad += sfin[a] != END;
+                    in[half] = lab_ld_cg(rfin + a) > lab_ld_cg(rfin + tw);
+                    bad += lab_ld_cg(sfin + a) != END;
                 }
                 tr.loc[a] = INF;
             }
@@ -881,14 +880,14 @@ LAB_DEV void tree_prefix_round_body(Tree const &tr, uint32_t round, long long gt
         uint32_t const a = i + 1 < n ? tr.alist[i] : ROOT;
         uint32_t const pa = lab_ld_cg(pin + a);
         uint32_t const v = lab_ld_cg(vin + a);
-        if (pa == ROOT) {
-            pout[a] = ROOT;
+        if (!tree_follow(tr, pa)) { // the root, or (row bands) an entry of another band
+            pout[a] = pa;
             vout[a] = v;
         } else {
             uint32_t const p2 = lab_ld_cg(pin + pa);
             pout[a] = p2;
             vout[a] = v + lab_ld_cg(vin + pa);
-            more |= p2 != ROOT;
+            more |= tree_follow(tr, p2);
         }
     }
     if (lab_any(more) && (gthread & 31) == 0 && lab_ld_ro(&tc->prefix_more[round]) == 0u) {
@@ -896,6 +895,167 @@ LAB_DEV void tree_prefix_round_body(Tree const &tr, uint32_t round, long long gt
     }
     if (gthread == 0) {
         lab_st_volatile(&tc->prefix_buf, (round & 1u) ^ 1u);
+    }
+}
+
+// After the rounds of a ranking (kind 0) / prefix (kind 1): bring the entries of the list back to ping-pong
+// buffer 0 if the last round left them in buffer 1, so that everything downstream (orient, fix-up, the band
+// exchange) reads ONE place.  `buf` = the buffer the rounds ended in (read by the caller before anybody
+// could change it).
+LAB_DEV void tree_jump_settle_body(Tree const &tr, uint32_t buf, long long gthread, long long nthreads) {
+    if (buf == 0u) {
+        return;
+    }
+    uint32_t const ROOT = tr.nslots;
+    long long const n = static_cast<long long>(tr.tc->n_arcs) + 1;
+    for (long long i = gthread; i < n; i += nthreads) {
+        uint32_t const a = i + 1 < n ? tr.alist[i] : ROOT;
+        tr.s[0][a] = lab_ld_cg(tr.s[1] + a);
+        tr.r[0][a] = lab_ld_cg(tr.r[1] + a);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row bands: what the ranks tell each other between the phases.  Every rank contributes one CHUNK of
+// uint32: a header (its error flags and counts) and the slots of its first and last TILE ROW -- the only
+// tiles another band's pointers can lead into -- of up to three of the global arrays; after the all-gather
+// every rank copies the other ranks' rows into its own copy of those arrays and folds the headers into its
+// control block, so that all ranks come to the same verdict without a round trip through the host.
+//   stage 1 (after the windowed ranking)  s[0], r[0], succ0   + the tour's start (ROOT) from the rank that holds it
+//   stage 2 (after orient + flood)        loc, inmask
+//   stage 3 (after the windowed prefix)   s[0] (= parent), r[0] (= level so far)
+constexpr uint32_t BORDER_HDR = 8; // unreached, walk_error, bad_weight, !ok, settled lo, settled hi, ROOT pointer, ROOT value
+struct Band_layout {          // of every rank, in rank order (device memory, owned by the caller)
+    uint32_t tile_base, ntiles; // the band's first tile (global id) and number of tiles
+};
+LAB_DEV uint32_t border_row_words(Params const &p) { return static_cast<uint32_t>(p.g.tiles_x) * SLOTS; }
+LAB_DEV uint32_t border_chunk_words(Params const &p, int stage) {
+    uint32_t const R = border_row_words(p);
+    return BORDER_HDR + (stage == 1 ? 6u * R : (stage == 2 ? 2u * R + 2u * (R / 32u) : 4u * R));
+}
+// the arrays of a stage, as (pointer to uint32 view, words per tile)
+struct Border_arr {
+    uint32_t *base;
+    uint32_t per_tile;
+};
+LAB_DEV int border_arrays(Tree const &tr, int stage, Border_arr (&arr)[3]) {
+    if (stage == 1) {
+        arr[0] = {tr.s[0], SLOTS};
+        arr[1] = {tr.r[0], SLOTS};
+        arr[2] = {tr.succ0, SLOTS};
+        return 3;
+    }
+    if (stage == 2) {
+        arr[0] = {tr.loc, SLOTS};
+        arr[1] = {reinterpret_cast<uint32_t *>(tr.inmask), 8u}; // 4 x uint64 per tile
+        return 2;
+    }
+    arr[0] = {tr.s[0], SLOTS};
+    arr[1] = {tr.r[0], SLOTS};
+    return 2;
+}
+
+LAB_DEV void tree_border_export_body(Params const &p, Tree const &tr, int stage, uint32_t *chunk, long long gthread, long long nthreads) {
+    Tree_ctl *tc = tr.tc;
+    uint32_t const tiles_x = static_cast<uint32_t>(p.g.tiles_x), ntiles = static_cast<uint32_t>(p.g.ntiles);
+    if (gthread == 0) {
+        chunk[0] = tc->unreached;
+        chunk[1] = tc->walk_error;
+        chunk[2] = tc->bad_weight;
+        chunk[3] = tc->ok ? 0u : 1u;
+        chunk[4] = static_cast<uint32_t>(tc->local_settled);
+        chunk[5] = static_cast<uint32_t>(tc->local_settled >> 32);
+        chunk[6] = tr.s[0][tr.nslots];
+        chunk[7] = tr.r[0][tr.nslots];
+    }
+    Border_arr arr[3];
+    int const na = border_arrays(tr, stage, arr);
+    uint32_t off = BORDER_HDR;
+    for (int k = 0; k < na; k++) {
+        uint32_t const row = tiles_x * arr[k].per_tile; // words of one tile row of this array
+        for (int which = 0; which < 2; which++) {        // first, last tile row of the band
+            uint32_t const t0 = tr.tile_base + (which == 0 ? 0u : ntiles - tiles_x);
+            uint32_t const *src = arr[k].base + static_cast<size_t>(t0) * arr[k].per_tile;
+            for (long long i = gthread; i < row; i += nthreads) {
+                chunk[off + i] = src[i];
+            }
+            off += row;
+        }
+    }
+}
+
+// `all` = the gathered chunks (world x chunk words).  root_rank = the rank whose band holds the start.
+LAB_DEV void tree_border_import_body(Params const &p, Tree const &tr, int stage, uint32_t const *all, Band_layout const *lay, int world, int me,
+                                     int root_rank, long long gthread, long long nthreads) {
+    Tree_ctl *tc = tr.tc;
+    uint32_t const tiles_x = static_cast<uint32_t>(p.g.tiles_x);
+    uint32_t const words = border_chunk_words(p, stage);
+    if (gthread == 0) {
+        unsigned long long settled = 0;
+        uint32_t bad = 0;
+        for (int r = 0; r < world; r++) {
+            uint32_t const *h = all + static_cast<size_t>(r) * words;
+            bad |= h[0] | h[1] | h[2] | h[3];
+            settled += static_cast<unsigned long long>(h[4]) | (static_cast<unsigned long long>(h[5]) << 32);
+        }
+        if (bad) { // some rank found out that this is not one tree: every rank reads the same flags and stops here
+            tc->ok = 0;
+        }
+        if (stage == 2) {
+            tc->local_settled = settled; // (tree_parent_body compares it with V: both are the whole maze's now)
+        }
+        if (stage == 1 && me != root_rank) {
+            uint32_t const *h = all + static_cast<size_t>(root_rank) * words;
+            tr.s[0][tr.nslots] = h[6];
+            tr.r[0][tr.nslots] = h[7];
+        }
+    }
+    Border_arr arr[3];
+    int const na = border_arrays(tr, stage, arr);
+    for (int r = 0; r < world; r++) {
+        if (r == me) {
+            continue;
+        }
+        uint32_t const *c = all + static_cast<size_t>(r) * words;
+        uint32_t off = BORDER_HDR;
+        for (int k = 0; k < na; k++) {
+            uint32_t const row = tiles_x * arr[k].per_tile;
+            for (int which = 0; which < 2; which++) {
+                uint32_t const t0 = lay[r].tile_base + (which == 0 ? 0u : lay[r].ntiles - tiles_x);
+                uint32_t *dst = arr[k].base + static_cast<size_t>(t0) * arr[k].per_tile;
+                for (long long i = gthread; i < row; i += nthreads) {
+                    dst[i] = c[off + i];
+                }
+                off += row;
+            }
+        }
+    }
+}
+
+// The last pass of a windowed ranking (kind 0) / prefix (kind 1): an entry of the band's own list that stopped
+// at a pointer into another band adds what that band's border row -- finished by the short list's rounds --
+// holds.  Entries of the band's own border rows were on the short list themselves and are final already.
+LAB_DEV void tree_finish_jump_body(Params const &p, Tree const &tr, long long gthread, long long nthreads) {
+    Tree_ctl *tc = tr.tc;
+    if (!tree_live(tc)) {
+        return;
+    }
+    uint32_t const ROOT = tr.nslots;
+    uint32_t const tiles_x = static_cast<uint32_t>(p.g.tiles_x), ntiles = static_cast<uint32_t>(p.g.ntiles);
+    long long const n = static_cast<long long>(tc->n_arcs) + 1;
+    for (long long i = gthread; i < n; i += nthreads) {
+        uint32_t const a = i + 1 < n ? tr.alist[i] : ROOT;
+        if (a != ROOT) {
+            uint32_t const t = a / SLOTS - tr.tile_base;
+            if (t < tiles_x || t >= ntiles - tiles_x) {
+                continue; // a border row's entry
+            }
+        }
+        uint32_t const s = tr.s[0][a];
+        if (s < tr.nslots) { // stopped at the window's edge: s is an entry of another band's border row
+            tr.r[0][a] += tr.r[0][s];
+            tr.s[0][a] = tr.s[0][s];
+        }
     }
 }
 
@@ -909,7 +1069,7 @@ LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, long long gwarp, l
         return;
     }
     Geom const &g = p.g;
-    uint32_t const *lvl = tc->prefix_buf ? tr.r[1] : tr.r[0];
+    uint32_t const *lvl = tr.r[0]; // (tree_jump_settle_body)
     uint32_t *dist = p.plane[0].dist;
     uint32_t mx = 0;
     // one warp-item = four tiles' worth of one row: eight independent loads per lane in flight

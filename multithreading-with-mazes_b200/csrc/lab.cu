@@ -52,9 +52,6 @@ __global__ void __launch_bounds__(128, 3) k_bfs_tiles(Params p) {
 // ---- spanning-tree pipeline (device/tree.cuh) ----
 __global__ void __launch_bounds__(256) k_tree_count(Params p, Tree tr) { tree_count_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void k_tree_init(Params p, Tree tr) { tree_init_body(p, tr); }
-__global__ void __launch_bounds__(256) k_tree_seed(Tree tr) {
-    tree_seed_body(tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
-}
 __global__ void __launch_bounds__(128) k_tree_walk(Params p, Tree tr) {
     __shared__ __align__(16) uint64_t sm[4][WALK_U64];
     tree_walk_body(p, tr, lane_id(), sm[threadIdx.x >> 5]);
@@ -89,7 +86,7 @@ template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p,
     long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
     uint32_t target = 0;
     uint32_t *const barrier = &tc->barrier[KIND];
-    if (KIND == 1) {
+    if (KIND == 1 && !(tr.jump_skip & 1u)) {
         tree_parent_body(p, tr, gthread, nthreads);
         grid_barrier(barrier, target);
         if (*reinterpret_cast<uint32_t volatile *>(&tc->ok) == 0u || *reinterpret_cast<uint32_t volatile *>(&tc->bad_weight) != 0u) {
@@ -113,11 +110,13 @@ template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p,
         r[k] = own[k] ? __ldcg(tr.r[0] + a[k]) : 0u;
     }
     bool const spill = n > JUMP_K * nthreads; // more entries than registers: the rest goes the plain way
+    uint32_t last = 0; // the buffer the rounds end in
     for (uint32_t round = 0; round < max_rounds; round++) {
         bool const odd = round & 1u;
         uint32_t const *sin = odd ? tr.s[1] : tr.s[0], *rin = odd ? tr.r[1] : tr.r[0];
         uint32_t *sout = odd ? tr.s[0] : tr.s[1], *rout = odd ? tr.r[0] : tr.r[1];
-        // three hops per round through the buffer of the last round: a pointer's span grows fourfold
+        // three hops per round through the buffer of the last round: a pointer's span grows fourfold.
+        // (tree_follow: not past the end of the list, and -- row bands -- not out of the band's window)
         uint32_t s2[JUMP_K], r2[JUMP_K];
 #pragma unroll
         for (int k = 0; k < JUMP_K; k++) {
@@ -129,8 +128,8 @@ template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p,
             uint32_t sn[JUMP_K], rn[JUMP_K];
 #pragma unroll
             for (int k = 0; k < JUMP_K; k++) {
-                bool const go = s2[k] != STOP;
-                sn[k] = go ? __ldcg(sin + s2[k]) : STOP;
+                bool const go = tree_follow(tr, s2[k]);
+                sn[k] = go ? __ldcg(sin + s2[k]) : s2[k];
                 rn[k] = go ? __ldcg(rin + s2[k]) : 0u;
             }
 #pragma unroll
@@ -143,10 +142,10 @@ template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p,
 #pragma unroll
         for (int k = 0; k < JUMP_K; k++) {
             if (own[k]) {
-                if (s[k] != STOP) {
+                if (tree_follow(tr, s[k])) {
                     r[k] += r2[k];
                     s[k] = s2[k];
-                    m |= s[k] != STOP;
+                    m |= tree_follow(tr, s[k]);
                 }
                 sout[a[k]] = s[k];
                 rout[a[k]] = r[k];
@@ -156,32 +155,60 @@ template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p,
             for (long long i = gthread + JUMP_K * nthreads; i < n; i += nthreads) {
                 uint32_t const ai = i + 1 < n ? tr.alist[i] : ROOT;
                 uint32_t const si = __ldcg(sin + ai), ri = __ldcg(rin + ai);
-                if (si == STOP) {
-                    sout[ai] = STOP;
+                if (!tree_follow(tr, si)) {
+                    sout[ai] = si;
                     rout[ai] = ri;
                 } else {
                     uint32_t const si2 = __ldcg(sin + si);
                     sout[ai] = si2;
                     rout[ai] = ri + __ldcg(rin + si);
-                    m |= si2 != STOP;
+                    m |= tree_follow(tr, si2);
                 }
             }
         }
         if (__syncthreads_or(m) && threadIdx.x == 0) {
             *reinterpret_cast<uint32_t volatile *>(&more[round]) = 1u;
         }
-        if (gthread == 0) {
-            *reinterpret_cast<uint32_t volatile *>(KIND == 0 ? &tc->rank_buf : &tc->prefix_buf) = odd ? 0u : 1u;
-        }
+        last = odd ? 0u : 1u;
         grid_barrier(barrier, target);
         if (*reinterpret_cast<uint32_t volatile *>(&more[round]) == 0u) {
             break;
         }
     }
-    if (KIND == 0) {
+    // Everything downstream reads buffer 0 (tree_jump_settle_body): the registers still hold this thread's entries.
+    if (last == 1u) {
+#pragma unroll
+        for (int k = 0; k < JUMP_K; k++) {
+            if (own[k]) {
+                tr.s[0][a[k]] = s[k];
+                tr.r[0][a[k]] = r[k];
+            }
+        }
+        if (spill) {
+            for (long long i = gthread + JUMP_K * nthreads; i < n; i += nthreads) {
+                uint32_t const ai = i + 1 < n ? tr.alist[i] : ROOT;
+                tr.s[0][ai] = __ldcg(tr.s[1] + ai);
+                tr.r[0][ai] = __ldcg(tr.r[1] + ai);
+            }
+        }
+    }
+    if (KIND == 0 && !(tr.jump_skip & 2u)) {
+        grid_barrier(barrier, target); // (orient looks at other threads' entries -- twins -- in buffer 0)
         tree_orient_body(p, tr, gthread >> 5, nthreads >> 5, static_cast<int>(threadIdx.x & 31));
     }
 }
+__global__ void __launch_bounds__(256) k_tree_border_export(Params p, Tree tr, int stage, uint32_t *chunk) {
+    tree_border_export_body(p, tr, stage, chunk, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
+}
+__global__ void __launch_bounds__(256) k_tree_border_import(Params p, Tree tr, int stage, uint32_t const *all, Band_layout const *lay, int world, int me,
+                                                            int root_rank) {
+    tree_border_import_body(p, tr, stage, all, lay, world, me, root_rank, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+                            static_cast<long long>(gridDim.x) * blockDim.x);
+}
+__global__ void __launch_bounds__(256) k_tree_finish_jump(Params p, Tree tr) {
+    tree_finish_jump_body(p, tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
+}
+__global__ void __launch_bounds__(256) k_tree_orient(Params p, Tree tr) { tree_orient_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void __launch_bounds__(128) k_tree_flood(Params p, Tree tr) {
     extern __shared__ __align__(16) uint64_t flood_sm[];
     tree_flood_body(p, tr, lane_id(), flood_sm + static_cast<size_t>(threadIdx.x >> 5) * FLOOD_U64);
@@ -380,6 +407,11 @@ struct lab_grid {
     // the pipeline across row bands (lab_band_tree_*): the caller's global arrays, this band's control block
     Tree band_tree{};
     uint32_t band_ntiles_global = 0;
+    uint32_t *band_alist = nullptr;            // the band's own crossings
+    uint32_t const *band_border_list = nullptr; // every band's border-row slots (the short list)
+    uint32_t band_border_count = 0, band_crossings = 0;
+    Band_layout const *band_layout = nullptr;
+    int band_world = 1, band_me = 0;
     bool band_tree_bound = false;
     int tree_coop_blocks = 0; // co-resident blocks of the multi-round kernels
     int tree_flood_per_sm = 1, tree_walk_per_sm = 1;
@@ -1387,9 +1419,10 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
 
 // ---- the spanning-tree pipeline across row bands (device/tree.cuh; protocol in include/labyrinth_b200.h) ----
 int lab_band_tree_bind(lab_grid *h, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *s0, void *s1, void *r0, void *r1,
-                       void *loc, void *inmask, void *alist) {
-    if (!h || !succ0 || !s0 || !s1 || !r0 || !r1 || !loc || !inmask || !alist) {
-        return fail(LAB_ERR_ARG, "lab_band_tree_bind: null argument");
+                       void *loc, void *inmask, void *alist, const void *border_list, uint32_t border_count, const void *layout,
+                       int world, int me) {
+    if (!h || !succ0 || !s0 || !s1 || !r0 || !r1 || !loc || !inmask || !alist || !border_list || !layout || world < 1 || me < 0 || me >= world) {
+        return fail(LAB_ERR_ARG, "lab_band_tree_bind: bad argument");
     }
     if (static_cast<unsigned long long>(ntiles_global) * SLOTS + 2 >= (1ull << 32) || tile_base + static_cast<uint32_t>(h->g.ntiles) > ntiles_global) {
         return fail(LAB_ERR_ARG, "lab_band_tree_bind: band tiles [%u, %u) do not fit a maze of %u tiles (or the maze is too large)", tile_base,
@@ -1412,6 +1445,12 @@ int lab_band_tree_bind(lab_grid *h, uint32_t tile_base, uint32_t ntiles_global, 
     tr.nslots = ntiles_global * SLOTS;
     tr.tile_base = tile_base;
     tr.banded = 1;
+    h->band_alist = static_cast<uint32_t *>(alist);
+    h->band_border_list = static_cast<uint32_t const *>(border_list);
+    h->band_border_count = border_count;
+    h->band_layout = static_cast<Band_layout const *>(layout);
+    h->band_world = world;
+    h->band_me = me;
     h->band_ntiles_global = ntiles_global;
     h->band_tree_bound = true;
     return LAB_OK;
@@ -1428,9 +1467,45 @@ static int band_tree_read(lab_grid *h, Tree_ctl &out) {
     CU(cudaStreamSynchronize(h->stream));
     return LAB_OK;
 }
-static int band_tree_coop_blocks(lab_grid *h) {
-    return static_cast<int>(std::max<long long>(
-        1, std::min<long long>(h->tree_coop_blocks, (static_cast<long long>(h->band_ntiles_global) * 64 + 512 * JUMP_K - 1) / (512 * JUMP_K))));
+// The band's own list, followed only inside the band's slots ...
+static Tree band_tree_local(lab_grid *h) {
+    Tree tr = h->band_tree;
+    tr.alist = h->band_alist;
+    tr.jump_lo = tr.tile_base * SLOTS;
+    tr.jump_hi = tr.jump_lo + static_cast<uint32_t>(h->g.ntiles) * SLOTS;
+    tr.jump_skip = 3u;
+    return tr;
+}
+// ... and the short list over every band's border tile rows.
+static Tree band_tree_border(lab_grid *h) {
+    Tree tr = h->band_tree;
+    tr.alist = const_cast<uint32_t *>(h->band_border_list);
+    tr.jump_lo = tr.jump_hi = 0;
+    tr.jump_skip = 3u;
+    return tr;
+}
+// One pointer-jumping launch (rank: KIND 0, prefix: KIND 1) over `count` list entries.
+extern "C++" template <int KIND> int band_tree_jump(lab_grid *h, Tree tr, Params p, uint32_t count) {
+    cudaStream_t s = h->stream;
+    Tree_ctl *tc = tr.tc;
+    CU(cudaMemcpyAsync(&tc->n_arcs, &count, sizeof count, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(KIND == 0 ? tc->rank_more : tc->prefix_more, 0, sizeof tc->rank_more, s));
+    CU(cudaMemsetAsync(&tc->barrier[KIND], 0, sizeof(uint32_t), s));
+    uint32_t rounds = static_cast<uint32_t>(ceil_log2(static_cast<unsigned long long>(tr.nslots) + 2));
+    int const blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(h->tree_coop_blocks, (static_cast<long long>(count) + 512 * JUMP_K) / (512 * JUMP_K))));
+    void *args[] = {&p, &tr, &rounds};
+    CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_jump<KIND>), dim3(blocks), dim3(512), args, 0, s));
+    TRACE(KIND == 0 ? "k_tree_jump<rank>" : "k_tree_jump<prefix>", s);
+    h->launches += 1;
+    return LAB_OK;
+}
+
+int lab_band_tree_chunk_words(const lab_grid *h, int stage) {
+    if (!h || stage < 1 || stage > 3) {
+        return 0;
+    }
+    uint32_t const R = static_cast<uint32_t>(h->g.tiles_x) * SLOTS;
+    return static_cast<int>(BORDER_HDR + (stage == 1 ? 6u * R : (stage == 2 ? 2u * R + 2u * (R / 32u) : 4u * R)));
 }
 
 int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs, uint32_t *crossings) {
@@ -1447,110 +1522,103 @@ int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs, uint32_
     Tree_ctl tc{};
     rc = band_tree_read(h, tc);
     if (rc) return rc;
+    h->band_crossings = tc.crossings;
     if (squares) *squares = tc.V;
     if (pairs) *pairs = tc.E;
     if (crossings) *crossings = tc.crossings;
     return LAB_OK;
 }
 
-int lab_band_tree_walk(lab_grid *h, uint64_t squares_global, uint64_t pairs_global, uint32_t alist_base) {
-    int rc = band_tree_ready(h, "lab_band_tree_walk");
+// walk + the band's own part of the ranking -> chunk 1
+int lab_band_tree_rank_local(lab_grid *h, uint64_t squares_global, uint64_t pairs_global, void *chunk1) {
+    int rc = band_tree_ready(h, "lab_band_tree_rank_local");
     if (rc) return rc;
     cudaStream_t s = h->stream;
-    Tree const tr = h->band_tree;
+    Tree const tr = band_tree_local(h);
     Params p = make_params(h, 1);
     unsigned long long const ve[2] = {squares_global, pairs_global};
     CU(cudaMemcpyAsync(&tr.tc->V, ve, sizeof ve, cudaMemcpyHostToDevice, s)); // (V and E are the struct's first two members)
-    CU(cudaMemcpyAsync(&tr.tc->alist_base, &alist_base, sizeof alist_base, cudaMemcpyHostToDevice, s));
     k_tree_init<<<1, 1, 0, s>>>(p, tr);
     int const walk_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_walk_per_sm);
     k_tree_walk<<<walk_blocks, 128, 0, s>>>(p, tr);
     TRACE("k_tree_walk", s);
     h->launches += 2;
+    rc = band_tree_jump<0>(h, tr, p, h->band_crossings);
+    if (rc) return rc;
+    k_tree_border_export<<<h->sm_count, 256, 0, s>>>(p, tr, 1, static_cast<uint32_t *>(chunk1));
+    TRACE("k_tree_border_export", s);
+    h->launches += 1;
     CU(cudaGetLastError());
     return LAB_OK;
 }
 
-int lab_band_tree_rank(lab_grid *h, uint32_t arcs_global) {
-    int rc = band_tree_ready(h, "lab_band_tree_rank");
-    if (rc) return rc;
-    cudaStream_t s = h->stream;
-    Tree tr = h->band_tree;
-    Params p = make_params(h, 1);
-    CU(cudaMemcpyAsync(&tr.tc->n_arcs, &arcs_global, sizeof arcs_global, cudaMemcpyHostToDevice, s));
-    k_tree_seed<<<h->sm_count * 4, 256, 0, s>>>(tr);
-    uint32_t rounds = static_cast<uint32_t>(ceil_log2(static_cast<unsigned long long>(tr.nslots) + 2));
-    {
-        void *args[] = {&p, &tr, &rounds};
-        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_jump<0>), dim3(band_tree_coop_blocks(h)), dim3(512), args, 0, s));
-    }
-    TRACE("k_tree_jump<rank+orient>", s);
-    h->launches += 2;
-    return LAB_OK;
-}
-
-int lab_band_tree_flood(lab_grid *h, uint32_t *unreached, uint64_t *settled_local, uint32_t *error) {
+// all chunks 1 in: the short list's ranking, the band's final ranks, orientation, the flood -> chunk 2
+int lab_band_tree_flood(lab_grid *h, const void *all1, int root_rank, void *chunk2) {
     int rc = band_tree_ready(h, "lab_band_tree_flood");
     if (rc) return rc;
     cudaStream_t s = h->stream;
-    Tree const tr = h->band_tree;
+    Tree const local = band_tree_local(h), border = band_tree_border(h);
     Params p = make_params(h, 1);
-    int const fill_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_flood_per_sm);
-    k_tree_flood<<<fill_blocks, 128, 4 * FLOOD_U64 * sizeof(uint64_t), s>>>(p, tr);
-    TRACE("k_tree_flood", s);
-    h->launches += 1;
-    CU(cudaGetLastError());
-    Tree_ctl tc{};
-    rc = band_tree_read(h, tc);
+    k_tree_border_import<<<h->sm_count, 256, 0, s>>>(p, local, 1, static_cast<uint32_t const *>(all1), h->band_layout, h->band_world, h->band_me, root_rank);
+    TRACE("k_tree_border_import", s);
+    rc = band_tree_jump<0>(h, border, p, h->band_border_count);
     if (rc) return rc;
-    if (unreached) *unreached = tc.unreached;
-    if (settled_local) *settled_local = tc.local_settled;
-    if (error) *error = tc.ok ? tc.walk_error : 0xFFFFu;
+    CU(cudaMemcpyAsync(&local.tc->n_arcs, &h->band_crossings, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    k_tree_finish_jump<<<h->sm_count * 2, 256, 0, s>>>(p, local);
+    k_tree_orient<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, local);
+    TRACE("k_tree_orient", s);
+    int const fill_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_flood_per_sm);
+    k_tree_flood<<<fill_blocks, 128, 4 * FLOOD_U64 * sizeof(uint64_t), s>>>(p, local);
+    TRACE("k_tree_flood", s);
+    k_tree_border_export<<<h->sm_count, 256, 0, s>>>(p, local, 2, static_cast<uint32_t *>(chunk2));
+    h->launches += 5;
+    CU(cudaGetLastError());
     return LAB_OK;
 }
 
-// Every rank computes the same entry levels from the same (exchanged) arrays, so all of them reach the same verdict:
-// the fix-up and the gate are gated on it on the device, nothing has to be agreed on in between.
-int lab_band_tree_levels(lab_grid *h, uint64_t settled_global, int32_t *used) {
+// all chunks 2 in: parents of the band's entries, the band's own part of the prefix sums -> chunk 3
+int lab_band_tree_prefix_local(lab_grid *h, const void *all2, void *chunk3) {
+    int rc = band_tree_ready(h, "lab_band_tree_prefix_local");
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Tree local = band_tree_local(h);
+    Params p = make_params(h, 1);
+    k_tree_border_import<<<h->sm_count, 256, 0, s>>>(p, local, 2, static_cast<uint32_t const *>(all2), h->band_layout, h->band_world, h->band_me, 0);
+    TRACE("k_tree_border_import", s);
+    local.jump_skip = 2u; // (the parent pass runs at the head of this launch)
+    rc = band_tree_jump<1>(h, local, p, h->band_crossings);
+    if (rc) return rc;
+    k_tree_border_export<<<h->sm_count, 256, 0, s>>>(p, local, 3, static_cast<uint32_t *>(chunk3));
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+// all chunks 3 in: the short list's prefix sums, the band's final entry levels, the band's final field.
+// Every rank has read the same flags, so all reach the same verdict `used`: 1 = the band's field is final;
+// 0 = not one tree, the field is wiped (tree_gate_body) and the relax / exchange loop takes over.
+int lab_band_tree_levels(lab_grid *h, const void *all3, int32_t *used) {
     int rc = band_tree_ready(h, "lab_band_tree_levels");
     if (rc) return rc;
     cudaStream_t s = h->stream;
-    Tree tr = h->band_tree;
+    Tree const local = band_tree_local(h), border = band_tree_border(h);
     Params p = make_params(h, 1);
-    unsigned long long const st = settled_global;
-    CU(cudaMemcpyAsync(&tr.tc->local_settled, &st, sizeof st, cudaMemcpyHostToDevice, s));
-    uint32_t rounds = static_cast<uint32_t>(ceil_log2(static_cast<unsigned long long>(tr.nslots) + 2));
-    {
-        void *args[] = {&p, &tr, &rounds};
-        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_tree_jump<1>), dim3(band_tree_coop_blocks(h)), dim3(512), args, 0, s));
-    }
-    TRACE("k_tree_jump<parent+prefix>", s);
-    k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, tr);
+    k_tree_border_import<<<h->sm_count, 256, 0, s>>>(p, local, 3, static_cast<uint32_t const *>(all3), h->band_layout, h->band_world, h->band_me, 0);
+    TRACE("k_tree_border_import", s);
+    rc = band_tree_jump<1>(h, border, p, h->band_border_count);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(&local.tc->n_arcs, &h->band_crossings, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    k_tree_finish_jump<<<h->sm_count * 2, 256, 0, s>>>(p, local);
+    k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, local);
     TRACE("k_tree_fixup", s);
-    k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, tr);
+    k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, local);
     TRACE("k_tree_gate", s);
-    h->launches += 3;
+    h->launches += 4;
     CU(cudaGetLastError());
     rc = band_tree_read(h, h->tree_last);
     if (rc) return rc;
     if (used) *used = static_cast<int32_t>(h->tree_last.used);
     return LAB_OK;
-}
-
-// Some rank found out that the maze is not one tree: the field is wiped and the relax / exchange loop takes over.
-int lab_band_tree_abort(lab_grid *h) {
-    int rc = band_tree_ready(h, "lab_band_tree_abort");
-    if (rc) return rc;
-    cudaStream_t s = h->stream;
-    Tree const tr = h->band_tree;
-    Params p = make_params(h, 1);
-    uint32_t const zero = 0;
-    CU(cudaMemcpyAsync(&tr.tc->ok, &zero, sizeof zero, cudaMemcpyHostToDevice, s));
-    k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, tr);
-    TRACE("k_tree_gate", s);
-    h->launches += 1;
-    CU(cudaGetLastError());
-    return band_tree_read(h, h->tree_last);
 }
 
 uint64_t lab_last_painted(const lab_grid *h) { return h ? h->last.settled : 0; }

@@ -60,12 +60,14 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
     for (int r = 0; r < rounds; r++) {
         simt::launch(nwarps, [&](int wid, int lane) { tree_rank_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
     }
+    simt::launch(nwarps, [&](int wid, int lane) { tree_jump_settle_body(tr, tc.rank_buf, static_cast<long long>(wid) * 32 + lane, nthreads); });
     simt::launch(nwarps, [&](int wid, int lane) { tree_orient_body(p, tr, wid, nwarps, lane); });
     simt::launch(nwarps, [&](int wid, int lane) { tree_flood_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * SM); }, sched_seed);
     simt::launch(nwarps, [&](int wid, int lane) { tree_parent_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
     for (int r = 0; r < rounds; r++) {
         simt::launch(nwarps, [&](int wid, int lane) { tree_prefix_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
     }
+    simt::launch(nwarps, [&](int wid, int lane) { tree_jump_settle_body(tr, tc.prefix_buf, static_cast<long long>(wid) * 32 + lane, nthreads); });
     simt::launch(nwarps, [&](int wid, int lane) { tree_fixup_body(p, tr, wid, nwarps, lane); });
     if (d.game == GAME_DISTANCE) {
         simt::launch(nwarps, [&](int wid, int lane) { room_distance_body(p, w.grid_ptr, &w.res.settled, static_cast<long long>(wid) * 32 + lane, nthreads); });
@@ -207,7 +209,11 @@ struct Emu_band {
     unsigned sched = 0;
     Tree tr{};
     Tree_ctl tc{};
-    uint32_t ntiles_global = 0;
+    uint32_t *alist = nullptr;
+    uint32_t const *border_list = nullptr;
+    uint32_t border_count = 0, crossings = 0;
+    Band_layout const *layout = nullptr;
+    int world = 1, me = 0;
     Tree_ctl tree_last{};
 };
 
@@ -326,7 +332,8 @@ int emu_band_finish(void *h, uint64_t *local_max, uint64_t *local_settled) {
 }
 
 int emu_band_tree_bind(void *h, uint32_t tile_base, uint32_t ntiles_global, uint32_t *succ0, uint32_t *s0, uint32_t *s1, uint32_t *r0,
-                       uint32_t *r1, uint32_t *loc, uint64_t *inmask, uint32_t *alist) {
+                       uint32_t *r1, uint32_t *loc, uint64_t *inmask, uint32_t *alist, uint32_t const *border_list, uint32_t border_count,
+                       Band_layout const *layout, int world, int me) {
     auto *e = static_cast<Emu_band *>(h);
     Tree &tr = e->tr;
     tr.succ0 = succ0;
@@ -341,10 +348,57 @@ int emu_band_tree_bind(void *h, uint32_t tile_base, uint32_t ntiles_global, uint
     tr.nslots = ntiles_global * SLOTS;
     tr.tile_base = tile_base;
     tr.banded = 1;
-    e->ntiles_global = ntiles_global;
+    e->alist = alist;
+    e->border_list = border_list;
+    e->border_count = border_count;
+    e->layout = layout;
+    e->world = world;
+    e->me = me;
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
     e->sm.assign(static_cast<size_t>(e->nwarps) * SM, 0);
     return 0;
+}
+
+static Tree emu_band_local(Emu_band *e) {
+    Tree tr = e->tr;
+    tr.alist = e->alist;
+    tr.jump_lo = tr.tile_base * SLOTS;
+    tr.jump_hi = tr.jump_lo + static_cast<uint32_t>(e->w.g.ntiles) * SLOTS;
+    tr.jump_skip = 3u;
+    return tr;
+}
+static Tree emu_band_border(Emu_band *e) {
+    Tree tr = e->tr;
+    tr.alist = const_cast<uint32_t *>(e->border_list);
+    tr.jump_lo = tr.jump_hi = 0;
+    tr.jump_skip = 3u;
+    return tr;
+}
+// the rounds of one pointer-jumping launch of csrc/lab.cu (k_tree_jump), one emulated launch per round
+static void emu_band_jump(Emu_band *e, Tree const &tr, int kind, uint32_t count) {
+    int const nw = e->nwarps;
+    long long const nthreads = static_cast<long long>(nw) * 32;
+    if (!tree_live(&e->tc)) return;
+    e->tc.n_arcs = count;
+    std::memset(kind == 0 ? e->tc.rank_more : e->tc.prefix_more, 0, sizeof e->tc.rank_more);
+    int rounds = 0;
+    while ((1ull << rounds) < static_cast<unsigned long long>(tr.nslots) + 2) rounds++;
+    (kind == 0 ? e->tc.rank_buf : e->tc.prefix_buf) = 0;
+    for (int r = 0; r < rounds; r++) {
+        if (kind == 0) {
+            simt::launch(nw, [&](int wid, int lane) { tree_rank_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
+        } else {
+            simt::launch(nw, [&](int wid, int lane) { tree_prefix_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
+        }
+    }
+    uint32_t const buf = kind == 0 ? e->tc.rank_buf : e->tc.prefix_buf;
+    simt::launch(nw, [&](int wid, int lane) { tree_jump_settle_body(tr, buf, static_cast<long long>(wid) * 32 + lane, nthreads); });
+}
+
+int emu_band_tree_chunk_words(void *h, int stage) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    return static_cast<int>(border_chunk_words(p, stage));
 }
 
 int emu_band_tree_count(void *h, uint64_t *squares, uint64_t *pairs, uint32_t *crossings) {
@@ -354,88 +408,74 @@ int emu_band_tree_count(void *h, uint64_t *squares, uint64_t *pairs, uint32_t *c
     e->tc = Tree_ctl{};
     Tree const tr = e->tr;
     simt::launch(nw, [&](int wid, int lane) { tree_count_body(p, tr, wid, nw, lane); });
+    e->crossings = e->tc.crossings;
     *squares = e->tc.V;
     *pairs = e->tc.E;
     *crossings = e->tc.crossings;
     return 0;
 }
 
-int emu_band_tree_walk(void *h, uint64_t squares_global, uint64_t pairs_global, uint32_t alist_base) {
+int emu_band_tree_rank_local(void *h, uint64_t squares_global, uint64_t pairs_global, uint32_t *chunk1) {
     auto *e = static_cast<Emu_band *>(h);
     Params p = make_params(e->w, 1);
     int const nw = e->nwarps;
-    Tree const tr = e->tr;
+    long long const nthreads = static_cast<long long>(nw) * 32;
+    Tree const tr = emu_band_local(e);
     e->tc.V = squares_global;
     e->tc.E = pairs_global;
-    e->tc.alist_base = alist_base;
     tree_init_body(p, tr);
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
     simt::launch(nw, [&](int wid, int lane) { tree_walk_body(p, tr, lane, e->sm.data() + static_cast<size_t>(wid) * SM); }, e->sched);
+    emu_band_jump(e, tr, 0, e->crossings);
+    simt::launch(nw, [&](int wid, int lane) { tree_border_export_body(p, tr, 1, chunk1, static_cast<long long>(wid) * 32 + lane, nthreads); });
     return 0;
 }
 
-int emu_band_tree_rank(void *h, uint32_t arcs_global) {
+int emu_band_tree_flood(void *h, uint32_t const *all1, int root_rank, uint32_t *chunk2) {
     auto *e = static_cast<Emu_band *>(h);
     Params p = make_params(e->w, 1);
     int const nw = e->nwarps;
-    Tree const tr = e->tr;
-    e->tc.n_arcs = arcs_global;
     long long const nthreads = static_cast<long long>(nw) * 32;
-    simt::launch(nw, [&](int wid, int lane) { tree_seed_body(tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
-    int rounds = 0;
-    while ((1ull << rounds) < static_cast<unsigned long long>(tr.nslots) + 2) rounds++;
-    for (int r = 0; r < rounds; r++) {
-        simt::launch(nw, [&](int wid, int lane) { tree_rank_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
-    }
-    simt::launch(nw, [&](int wid, int lane) { tree_orient_body(p, tr, wid, nw, lane); });
-    return 0;
-}
-
-int emu_band_tree_flood(void *h, uint32_t *unreached, uint64_t *settled_local, uint32_t *error) {
-    auto *e = static_cast<Emu_band *>(h);
-    Params p = make_params(e->w, 1);
-    int const nw = e->nwarps;
-    Tree const tr = e->tr;
+    Tree const local = emu_band_local(e), border = emu_band_border(e);
+    simt::launch(nw, [&](int wid, int lane) { tree_border_import_body(p, local, 1, all1, e->layout, e->world, e->me, root_rank, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    emu_band_jump(e, border, 0, e->border_count);
+    e->tc.n_arcs = e->crossings;
+    simt::launch(nw, [&](int wid, int lane) { tree_finish_jump_body(p, local, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    simt::launch(nw, [&](int wid, int lane) { tree_orient_body(p, local, wid, nw, lane); });
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
-    simt::launch(nw, [&](int wid, int lane) { tree_flood_body(p, tr, lane, e->sm.data() + static_cast<size_t>(wid) * SM); }, e->sched);
-    *unreached = e->tc.unreached;
-    *settled_local = e->tc.local_settled;
-    *error = e->tc.ok ? e->tc.walk_error : 0xFFFFu;
+    simt::launch(nw, [&](int wid, int lane) { tree_flood_body(p, local, lane, e->sm.data() + static_cast<size_t>(wid) * SM); }, e->sched);
+    simt::launch(nw, [&](int wid, int lane) { tree_border_export_body(p, local, 2, chunk2, static_cast<long long>(wid) * 32 + lane, nthreads); });
     return 0;
 }
 
-static void emu_band_gate(Emu_band *e) {
+int emu_band_tree_prefix_local(void *h, uint32_t const *all2, uint32_t *chunk3) {
+    auto *e = static_cast<Emu_band *>(h);
     Params p = make_params(e->w, 1);
     int const nw = e->nwarps;
-    Tree const tr = e->tr;
     long long const nthreads = static_cast<long long>(nw) * 32;
-    simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    Tree const local = emu_band_local(e);
+    simt::launch(nw, [&](int wid, int lane) { tree_border_import_body(p, local, 2, all2, e->layout, e->world, e->me, 0, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    e->tc.n_arcs = e->crossings;
+    simt::launch(nw, [&](int wid, int lane) { tree_parent_body(p, local, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    emu_band_jump(e, local, 1, e->crossings);
+    simt::launch(nw, [&](int wid, int lane) { tree_border_export_body(p, local, 3, chunk3, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    return 0;
+}
+
+int emu_band_tree_levels(void *h, uint32_t const *all3, int32_t *used) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    long long const nthreads = static_cast<long long>(nw) * 32;
+    Tree const local = emu_band_local(e), border = emu_band_border(e);
+    simt::launch(nw, [&](int wid, int lane) { tree_border_import_body(p, local, 3, all3, e->layout, e->world, e->me, 0, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    emu_band_jump(e, border, 1, e->border_count);
+    e->tc.n_arcs = e->crossings;
+    simt::launch(nw, [&](int wid, int lane) { tree_finish_jump_body(p, local, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    simt::launch(nw, [&](int wid, int lane) { tree_fixup_body(p, local, wid, nw, lane); });
+    simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, local, static_cast<long long>(wid) * 32 + lane, nthreads); });
     e->tree_last = e->tc;
-}
-
-int emu_band_tree_levels(void *h, uint64_t settled_global, int32_t *used) {
-    auto *e = static_cast<Emu_band *>(h);
-    Params p = make_params(e->w, 1);
-    int const nw = e->nwarps;
-    Tree const tr = e->tr;
-    e->tc.local_settled = settled_global;
-    long long const nthreads = static_cast<long long>(nw) * 32;
-    simt::launch(nw, [&](int wid, int lane) { tree_parent_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
-    int rounds = 0;
-    while ((1ull << rounds) < static_cast<unsigned long long>(tr.nslots) + 2) rounds++;
-    for (int r = 0; r < rounds; r++) {
-        simt::launch(nw, [&](int wid, int lane) { tree_prefix_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
-    }
-    simt::launch(nw, [&](int wid, int lane) { tree_fixup_body(p, tr, wid, nw, lane); });
-    emu_band_gate(e);
     *used = static_cast<int32_t>(e->tree_last.used);
-    return 0;
-}
-
-int emu_band_tree_abort(void *h) {
-    auto *e = static_cast<Emu_band *>(h);
-    e->tc.ok = 0;
-    emu_band_gate(e);
     return 0;
 }
 

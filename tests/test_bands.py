@@ -240,47 +240,37 @@ def test_band_entry_points_one_process(lab, O, builder, rows, cols, nb):
 
 
 def _lockstep_tree(eng, split, start, cols):
-    """_sharded_tree of bands.py for several bands driven by ONE process: the collectives become copies between
-    the bands' own (separate) global arrays."""
-    nb = len(eng)
-    tiles_x = eng[0].cols_padded // 64
-    ntiles = [((n + 63) // 64) * tiles_x for _, n in split]
-    bases = [(r0 // 64) * tiles_x for r0, _ in split]
-    total = sum(ntiles)
-    nslots = total * 256
-    bufs = [e.tree_bind(bases[i], total) for i, e in enumerate(eng)]
+    """_sharded_tree of bands.py for several bands driven by ONE process: an all-gather becomes the concatenation
+    of the bands' chunks, copied into every band's receive buffer."""
+    import torch
 
-    def share(name, offs, lens):
-        for src in range(nb):
-            for dst in range(nb):
-                if dst != src and lens[src]:
-                    bufs[dst][name][offs[src] : offs[src] + lens[src]].copy_(bufs[src][name][offs[src] : offs[src] + lens[src]])
+    from mazes_b200 import bands
+
+    nb = len(eng)
+    lay = bands.tree_layout(split, eng[0].cols_padded // 64)
+    assert lay is not None
+    bufs = [e.tree_bind(lay, i) for i, e in enumerate(eng)]
+
+    def all_gather(stage):
+        every = torch.cat([b[f"chunk{stage}"] for b in bufs])
+        for b in bufs:
+            b[f"all{stage}"].copy_(every)
 
     counts = [e.tree_count() for e in eng]
     squares, pairs = sum(c[0] for c in counts), sum(c[1] for c in counts)
     if squares < 2 or pairs + 1 != squares:
         return False
-    arcs = [c[2] for c in counts]
-    offs = [sum(arcs[:i]) for i in range(nb)]
-    for i, e in enumerate(eng):
-        e.tree_walk(squares, pairs, offs[i])
-    share("succ0", [b * 256 for b in bases], [n * 256 for n in ntiles])
     owner = next(i for i, (r0, n) in enumerate(split) if r0 <= start[0] < r0 + n)
-    for i in range(nb):
-        if i != owner:
-            bufs[i]["succ0"][nslots : nslots + 2].copy_(bufs[owner]["succ0"][nslots : nslots + 2])
-    share("alist", offs, arcs)
-    for e in eng:
-        e.tree_rank(sum(arcs))
-    flags = [e.tree_flood() for e in eng]
-    settled = sum(f[1] for f in flags)
-    if any(f[0] or f[2] for f in flags) or settled != squares:
-        for e in eng:
-            e.tree_abort()
-        return False
-    share("inmask", [b * 4 for b in bases], [n * 4 for n in ntiles])
-    share("loc", [b * 256 for b in bases], [n * 256 for n in ntiles])
-    used = [e.tree_levels(settled) for e in eng]
+    for e, b in zip(eng, bufs):
+        e.tree_rank_local(squares, pairs, b["chunk1"])
+    all_gather(1)
+    for e, b in zip(eng, bufs):
+        e.tree_flood(b["all1"], owner, b["chunk2"])
+    all_gather(2)
+    for e, b in zip(eng, bufs):
+        e.tree_prefix_local(b["all2"], b["chunk3"])
+    all_gather(3)
+    used = [e.tree_levels(b["all3"]) for e, b in zip(eng, bufs)]
     assert all(u == used[0] for u in used)
     return used[0]
 
