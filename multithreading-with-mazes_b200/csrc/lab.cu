@@ -655,7 +655,7 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     Tree const tr = h->tree;
     Params p = make_params(h, 1);
     CU(cudaMemsetAsync(tr.tc, 0, sizeof(Tree_ctl), s));
-    k_tree_count<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, tr);
+    k_tree_count<<<std::min(blocks_for(h, h->g.ntiles, 256), h->sm_count * 8), 256, 0, s>>>(p, tr); // (few warps: seven same-address atomics each)
     TRACE("k_tree_count", s);
     h->launches += 1;
     // No host round trip: k_tree_init decides on the device whether the counts allow a tree, and every
@@ -1515,7 +1515,7 @@ int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs, uint32_
     Tree const tr = h->band_tree;
     Params p = make_params(h, 1);
     CU(cudaMemsetAsync(tr.tc, 0, sizeof(Tree_ctl), s));
-    k_tree_count<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, tr);
+    k_tree_count<<<std::min(blocks_for(h, h->g.ntiles, 256), h->sm_count * 8), 256, 0, s>>>(p, tr); // (few warps: seven same-address atomics each)
     TRACE("k_tree_count", s);
     h->launches += 1;
     CU(cudaGetLastError());
