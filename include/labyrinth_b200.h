@@ -75,7 +75,8 @@ typedef struct lab_stats {
     /* SM cycles summed over worker warps; non-zero only in the -DLAB_PROFILE build */
     uint64_t cyc_load, cyc_loop, cyc_publish, cyc_idle, cyc_step, cyc_emit, batches;
     /* spanning-tree pipeline (csrc/device/tree.cuh): passable squares, adjacent passable pairs (a tree
-     * has pairs == squares - 1), tile-border crossings, and whether the pipeline produced the field */
+     * has pairs == squares - 1), tile-border crossings, and which road produced the field: 0 the tile
+     * wave, 1 the spanning-tree pipeline, 2 the open room (csrc/device/room.cuh: closed-form levels) */
     uint64_t tree_squares, tree_pairs, tree_crossings, tree_used;
     uint64_t launches; /* kernels launched by the search (reset, pack, search, epilogue) */
 } lab_stats;
