@@ -53,6 +53,8 @@ WORKLOADS = {
     "distance-kruskal-16383": ("distance", "kruskal", 16383, None, "configs[1] builder at 16383 (20 s host build)"),
     "h-distance-kruskal-32767": ("distance", "kruskal", 32767, None, "north_star headline size, perfect maze (90 s host build)"),
     "gather-kruskal-4095": ("gather", "kruskal", 4095, None, "bfs-gather on configs[1]'s maze"),
+    "hunt-kruskal-4095": ("hunt", "kruskal", 4095, None, "bfs-hunt (configs[0]'s game) on configs[1]'s maze; the winner's path is walked and repainted"),
+    "hunt-wilson-4095": ("hunt", "wilson", 4095, None, "bfs-hunt on configs[4]'s builder at 4095"),
     "distance-arena-16383": ("distance", "arena", 16383, None, "configs[2] maze, distance map"),
     "h-distance-arena-pillar-32767": ("distance", "arena", 32767, "pillar", "headline size, arena with ONE wall square inside: the tile wave"),
     "h-gather-arena-pillar-32767": ("gather", "arena", 32767, "pillar", "headline size, arena with ONE wall square inside: the tile wave"),

@@ -27,6 +27,38 @@ TS = 64
 INF = 0xFFFFFFFF
 
 
+class _Trace:
+    """LAB_BANDS_TRACE=1: wall time of every phase of a sharded map (device synchronised after each, so the phases
+    do not overlap as they do otherwise); rank 0 prints one line per map on stderr.  Developer aid."""
+
+    def __init__(self, device):
+        import os
+
+        self.on = os.environ.get("LAB_BANDS_TRACE", "0") not in ("", "0")
+        self.cuda = self.on and getattr(device, "type", "cpu") == "cuda"
+        self.marks = []
+        if self.on:
+            self.mark("start")
+
+    def mark(self, name):
+        if not self.on:
+            return
+        import time
+
+        if self.cuda:
+            import torch
+
+            torch.cuda.synchronize()
+        self.marks.append((name, time.perf_counter()))
+
+    def report(self, rank):
+        if self.on and rank == 0:
+            import sys
+
+            parts = [f"{b[0]} {1e6 * (b[1] - a[1]):.0f}us" for a, b in zip(self.marks, self.marks[1:])]
+            print("[lab bands] " + " | ".join(parts) + f" | total {1e6 * (self.marks[-1][1] - self.marks[0][1]):.0f}us", file=sys.stderr, flush=True)
+
+
 def split_rows(rows: int, world: int) -> List[Tuple[int, int]]:
     """Band r = rows [row0, row0 + n).  Every band but the last is a multiple of 64 rows."""
     tiles = (rows + TS - 1) // TS
@@ -126,6 +158,9 @@ class _BandEngine:
                 b[f"all{stage}"] = torch.zeros(world * words, dtype=torch.int32, device=dev)
             self._tree_bufs = b
         b = self._tree_bufs
+        if b.get("bound"):
+            return b
+        b["bound"] = True
         self._check(self._f("tree_bind")(self.h, c_uint32(lay["bases"][rank]), c_uint32(lay["total"]), self._ptr(b["succ0"]), self._ptr(b["s0"]),
                                          self._ptr(b["s1"]), self._ptr(b["r0"]), self._ptr(b["r1"]), self._ptr(b["loc"]),
                                          self._ptr(b["inmask"]), self._ptr(b["alist"]), self._ptr(b["border_list"]),
@@ -202,13 +237,25 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     world = dist.get_world_size(group)
     sr, sc = start_global
     src_local = (sr - row0, sc) if row0 <= sr < row0 + rows_local else None
+    tr = _Trace(engine.row_device)
     engine.begin(src_local)
+    tr.mark("begin")
     top, bottom = engine.path_rows()
-    above_bottom, below_top = _exchange(dist, rank, world, top, bottom, engine, group)
+    if world > 1 and dist.get_backend(group) == "nccl":  # one flat all-gather beats two send/recv pairs for rows this small
+        n = top.numel()
+        every = torch.empty(world * 2 * n, dtype=top.dtype, device=top.device)
+        dist.all_gather_into_tensor(every, torch.cat([top, bottom]), group=group)
+        every = every.view(world, 2, n)
+        above_bottom = every[rank - 1, 1] if rank > 0 else None
+        below_top = every[rank + 1, 0] if rank < world - 1 else None
+    else:
+        above_bottom, below_top = _exchange(dist, rank, world, top, bottom, engine, group)
+    tr.mark("path rows")
     engine.set_neighbour_paths(above_bottom, below_top)
+    tr.mark("cross")
     flag = torch.zeros(1, dtype=torch.int32, device=engine.row_device)
     rounds = 0
-    tree = use_tree and getattr(engine, "supports_tree", False) and _sharded_tree(engine, start_global, row0, rows_local, group)
+    tree = use_tree and getattr(engine, "supports_tree", False) and _sharded_tree(engine, start_global, row0, rows_local, group, tr)
     while not tree:
         rounds += 1
         engine.relax()
@@ -219,11 +266,15 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
         dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
         if int(flag.item()) == 0 or rounds >= max_rounds:
             break
+    tr.mark("search")
     mx, settled = engine.finish()
+    tr.mark("finish")
     agg = torch.tensor([mx, settled], dtype=torch.int64, device=engine.row_device)
-    every = [torch.empty_like(agg) for _ in range(world)]
-    dist.all_gather(every, agg, group=group)
-    every = [e.tolist() for e in every]
+    out = torch.empty(2 * world, dtype=torch.int64, device=engine.row_device)
+    _all_gather(dist, out, agg, world, group)
+    every = out.view(world, 2).tolist()
+    tr.mark("results")
+    tr.report(rank)
     return {"max": max(int(e[0]) for e in every), "settled": sum(int(e[1]) for e in every), "rounds": rounds, "tree": bool(tree)}
 
 
@@ -247,7 +298,7 @@ def tree_layout(split, tiles_x: int):
     return {"split": list(split), "bases": bases, "ntiles": ntiles, "total": total, "tiles_x": tiles_x}
 
 
-def _sharded_tree(engine, start_global, row0, rows_local, group) -> bool:
+def _sharded_tree(engine, start_global, row0, rows_local, group, tr=None) -> bool:
     """The spanning-tree pipeline across the bands.  Collective.  True: the bands' level fields are final (only
     engine.finish() is left); False: the maze is not one tree, the fields are as engine.begin() left them."""
     import torch
@@ -271,16 +322,29 @@ def _sharded_tree(engine, start_global, row0, rows_local, group) -> bool:
     lay = cached[1]
     if lay is None:
         return False
+    mark = tr.mark if tr is not None else (lambda name: None)
     b = engine.tree_bind(lay, rank)
-    counts = gather(list(engine.tree_count()))
+    mark("bind")
+    counts = engine.tree_count()
+    mark("count")
+    counts = gather(list(counts))
+    mark("gather counts")
     squares, pairs = sum(c[0] for c in counts), sum(c[1] for c in counts)
     if squares < 2 or pairs + 1 != squares:
         return False  # (nothing has been written yet)
     owner = next((r for r, (r0, n) in enumerate(lay["split"]) if r0 <= start_global[0] < r0 + n), 0)
     engine.tree_rank_local(squares, pairs, b["chunk1"])
+    mark("walk + rank")
     _all_gather(dist, b["all1"], b["chunk1"], world, group)
+    mark("all-gather 1")
     engine.tree_flood(b["all1"], owner, b["chunk2"])
+    mark("short rank + flood")
     _all_gather(dist, b["all2"], b["chunk2"], world, group)
+    mark("all-gather 2")
     engine.tree_prefix_local(b["all2"], b["chunk3"])
+    mark("parent + prefix")
     _all_gather(dist, b["all3"], b["chunk3"], world, group)
-    return engine.tree_levels(b["all3"])
+    mark("all-gather 3")
+    used = engine.tree_levels(b["all3"])
+    mark("short prefix + fix-up")
+    return used
