@@ -179,8 +179,9 @@ int lab_band_finish(lab_grid *g, uint64_t *local_max, uint64_t *local_settled);
  *                             loc: uint32[ntiles_global*256]; inmask: uint64[ntiles_global*4]; alist: uint32[the band's
  *                             tiles * 256]; border_list: the slots of every band's first and last tile row (uint32
  *                             [border_count]); layout: {tile_base, ntiles} of every rank (uint32[world][2])
- *     lab_band_tree_count     -> the band's passable squares, adjacent pairs, border crossings.  Over all ranks a tree
- *                             has sum(pairs) == sum(squares) - 1 (anything else: stay with the loop above)
+ *     lab_band_tree_count     -> the band's passable squares, adjacent pairs, border crossings, bounding box.  Over all
+ *                             ranks a tree has sum(pairs) == sum(squares) - 1 (anything else: lab_band_room if it
+ *                             applies, or stay with the loop above)
  *     lab_band_tree_rank_local   (the sums in) walk + windowed ranking                      -> chunk 1
  *     lab_band_tree_flood        (all ranks' chunks 1 in; root_rank = who holds the start) short list, final ranks,
  *                                orientation, flood                                          -> chunk 2
@@ -193,7 +194,13 @@ int lab_band_tree_bind(lab_grid *g, uint32_t tile_base, uint32_t ntiles_global, 
                        void *r1, void *loc, void *inmask, void *alist, const void *border_list, uint32_t border_count,
                        const void *layout, int world, int me);
 int lab_band_tree_chunk_words(const lab_grid *g, int stage);
-int lab_band_tree_count(lab_grid *g, uint64_t *squares, uint64_t *pairs, uint32_t *crossings);
+int lab_band_tree_count(lab_grid *g, uint64_t *squares, uint64_t *pairs, uint32_t *crossings, int32_t box[4]);
+/* The open room (csrc/device/room.cuh) across row bands: if the ranks' boxes (lab_band_tree_count: bounding box
+ * r0, r1, c0, c1 of the band's passable squares, rows relative to the band) add up to one rectangle that holds
+ * exactly sum(squares) squares, there is nothing to search: every band writes the part [r0, r1] x [c0, c1] of the
+ * room it holds (r0 > r1: none) from the closed form, the source (src_r, src_c) again relative to the band (it may
+ * lie above row 0 or below the band's last row).  lab_band_finish next.  No exchange at all. */
+int lab_band_room(lab_grid *g, int r0, int r1, int c0, int c1, int src_r, int src_c);
 int lab_band_tree_rank_local(lab_grid *g, uint64_t squares_global, uint64_t pairs_global, void *chunk1);
 int lab_band_tree_flood(lab_grid *g, const void *all_chunks1, int root_rank, void *chunk2);
 int lab_band_tree_prefix_local(lab_grid *g, const void *all_chunks2, void *chunk3);

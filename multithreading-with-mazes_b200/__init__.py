@@ -38,7 +38,7 @@ ABI_SYMBOLS = (
     "lab_band_cols_padded", "lab_band_begin", "lab_band_path_rows", "lab_band_set_neighbour_paths", "lab_band_relax",
     "lab_band_export_edges", "lab_band_import_edges", "lab_band_finish",
     "lab_band_tree_bind", "lab_band_tree_chunk_words", "lab_band_tree_count", "lab_band_tree_rank_local", "lab_band_tree_flood",
-    "lab_band_tree_prefix_local", "lab_band_tree_levels",
+    "lab_band_tree_prefix_local", "lab_band_tree_levels", "lab_band_room",
 )
 
 

@@ -167,10 +167,15 @@ class _BandEngine:
                                          c_uint32(b["border_list"].numel()), self._ptr(b["layout"]), c_int(len(lay["bases"])), c_int(rank)))
         return b
 
-    def tree_count(self) -> Tuple[int, int, int]:
+    def tree_count(self):
+        """-> squares, pairs, crossings, then the bounding box r0, r1, c0, c1 of the band's passable squares"""
         v, e, x = c_uint64(), c_uint64(), c_uint32()
-        self._check(self._f("tree_count")(self.h, byref(v), byref(e), byref(x)))
-        return int(v.value), int(e.value), int(x.value)
+        box = (ctypes.c_int32 * 4)()
+        self._check(self._f("tree_count")(self.h, byref(v), byref(e), byref(x), box))
+        return (int(v.value), int(e.value), int(x.value)) + tuple(int(b) for b in box)
+
+    def room(self, r0: int, r1: int, c0: int, c1: int, src_r: int, src_c: int):
+        self._check(self._f("room")(self.h, c_int(r0), c_int(r1), c_int(c0), c_int(c1), c_int(src_r), c_int(src_c)))
 
     def tree_rank_local(self, squares_global: int, pairs_global: int, chunk1):
         self._check(self._f("tree_rank_local")(self.h, c_uint64(squares_global), c_uint64(pairs_global), self._ptr(chunk1)))
@@ -275,7 +280,7 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     every = out.view(world, 2).tolist()
     tr.mark("results")
     tr.report(rank)
-    return {"max": max(int(e[0]) for e in every), "settled": sum(int(e[1]) for e in every), "rounds": rounds, "tree": bool(tree)}
+    return {"max": max(int(e[0]) for e in every), "settled": sum(int(e[1]) for e in every), "rounds": rounds, "tree": tree is True, "road": "wave" if not tree else ("tree" if tree is True else "room")}
 
 
 def _all_gather(dist, out, chunk, world, group):
@@ -331,7 +336,16 @@ def _sharded_tree(engine, start_global, row0, rows_local, group, tr=None) -> boo
     mark("gather counts")
     squares, pairs = sum(c[0] for c in counts), sum(c[1] for c in counts)
     if squares < 2 or pairs + 1 != squares:
-        return False  # (nothing has been written yet)
+        # not a tree (nothing has been written yet) -- but maybe an open room: the passable squares fill their bounding box
+        boxes = [(split_r0 + c[3], split_r0 + c[4], c[5], c[6]) for c, (split_r0, _) in zip(counts, lay["split"]) if c[0]]
+        if boxes:
+            R0, R1 = min(b[0] for b in boxes), max(b[1] for b in boxes)
+            C0, C1 = min(b[2] for b in boxes), max(b[3] for b in boxes)
+            if squares == (R1 - R0 + 1) * (C1 - C0 + 1):
+                engine.room(max(R0, row0) - row0, min(R1, row0 + rows_local - 1) - row0, C0, C1, start_global[0] - row0, start_global[1])
+                mark("room")
+                return "room"
+        return False
     owner = next((r for r, (r0, n) in enumerate(lay["split"]) if r0 <= start_global[0] < r0 + n), 0)
     engine.tree_rank_local(squares, pairs, b["chunk1"])
     mark("walk + rank")

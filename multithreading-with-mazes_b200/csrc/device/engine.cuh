@@ -95,7 +95,7 @@ struct Control {
     // rectangle [room_r0, room_r1] x [room_c0, room_c1], so plane 0's level of a square is its Manhattan
     // distance from the source (room_sr, room_sc) and no field has to be searched
     uint32_t room;
-    uint32_t room_r0, room_r1, room_c0, room_c1, room_sr, room_sc;
+    int32_t room_r0, room_r1, room_c0, room_c1, room_sr, room_sc; // (row bands: relative to the band, see room.cuh)
 };
 
 struct Params {

@@ -296,23 +296,60 @@ LAB_DEV void paint_body(Params p, uint16_t *grid, Result *res, long long gthread
 }
 
 // Canonical shortest path (orc canonical_path): from the finish step to the FIRST neighbour in
-// N,E,S,W order whose level is one less.  One warp per path; lanes 0..3 read the 4 neighbours.
+// N,E,S,W order whose level is one less.  One warp per path; lanes 0..3 look at the 4 neighbours.
 // out (may be null) receives (row,col) pairs finish-side first, the start last.
 // If repaint_bits != 0 every path square gets its paint nibble replaced by repaint_bits (hunt).
 // Returns via res->path_len[slot].  `first_only` stops after the first step (gather's path.front()).
+//
+// The walk is one dependent chain, 10^4 .. 10^6 steps long on the reference's mazes; with a global load (and the
+// Square's read-modify-write) on that chain a step costs a DRAM round trip, and the walk used to take 7 x as long
+// as the search that made the field.  So: the 64x64 tile of levels under the walker is kept in shared memory (a
+// step inside it is four LDS + a vote; only border squares look outside), and nothing is written on the chain --
+// path squares are collected in shared memory and flushed WALK_BATCH at a time with all lanes in flight.
+constexpr int WALK_BATCH = 1024;
+constexpr int WALK_SM_U32 = TS * TS + WALK_BATCH; // per warp: cached levels | collected path squares (flat indices)
+
+LAB_DEV void walk_flush(Geom const &g, uint32_t const *batch, uint32_t nb, unsigned long long base, uint16_t *grid, int32_t *out,
+                        unsigned long long max_out, uint32_t repaint_bits, int lane) {
+    lab_syncwarp();
+    for (uint32_t i = static_cast<uint32_t>(lane); i < nb; i += 32u) {
+        uint32_t const idx = batch[i];
+        if (out && base + i < max_out) {
+            uint32_t const r = idx / static_cast<uint32_t>(g.cols);
+            out[2 * (base + i)] = static_cast<int32_t>(r);
+            out[2 * (base + i) + 1] = static_cast<int32_t>(idx - r * static_cast<uint32_t>(g.cols));
+        }
+        if (repaint_bits) {
+            grid[idx] = static_cast<uint16_t>((grid[idx] & ~SQ_PAINT_MASK) | repaint_bits);
+        }
+    }
+    lab_syncwarp();
+}
+
 LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int32_t *out,
                        unsigned long long max_out, uint32_t repaint_bits, int first_only, Result *res, int slot,
-                       int lane) {
+                       int lane, uint32_t *sm) {
     Geom const &g = p.g;
     uint32_t const *dist = p.plane[plane].dist;
     bool const room = p.ctl->room != 0; // (single-field games only: the levels are room_level, no field exists)
     Room const m = room_load(p.ctl);
+    uint32_t *cache = sm, *batch = sm + TS * TS;
+    int cty = -1, ctx = -1; // the cached tile
     auto level = [&](long long rr, long long cc) {
-        return room ? room_level(m, static_cast<uint32_t>(rr), static_cast<uint32_t>(cc)) : dist[rr * g.cols + cc];
+        if (room) {
+            return room_level(m, static_cast<uint32_t>(rr), static_cast<uint32_t>(cc));
+        }
+        int const ty = static_cast<int>(rr / TS), tx = static_cast<int>(cc / TS);
+        if (ty == cty && tx == ctx) {
+            return cache[(rr % TS) * TS + (cc % TS)];
+        }
+        return dist[rr * g.cols + cc];
     };
     long long r = fr, c = fc;
-    uint32_t d = level(r, c);
-    unsigned long long n = 0;
+    uint32_t const d0 = room ? room_level(m, static_cast<uint32_t>(r), static_cast<uint32_t>(c)) : dist[r * g.cols + c];
+    uint32_t d = d0;
+    unsigned long long n = 0, flushed = 0;
+    uint32_t nb = 0;
     if (d == INF) {
         if (lane == 0) res->path_len[slot] = 0;
         return;
@@ -320,6 +357,16 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
     int const dr[4] = {-1, 0, 1, 0};
     int const dc[4] = {0, 1, 0, -1};
     while (d > 0) {
+        if (!room && !first_only && (static_cast<int>(r / TS) != cty || static_cast<int>(c / TS) != ctx)) {
+            lab_syncwarp(); // (everybody is done with the old tile)
+            cty = static_cast<int>(r / TS);
+            ctx = static_cast<int>(c / TS);
+            for (int i = lane; i < TS * TS; i += 32) {
+                long long const rr = static_cast<long long>(cty) * TS + i / TS, cc = static_cast<long long>(ctx) * TS + i % TS;
+                cache[i] = (rr < g.rows && cc < g.cols) ? dist[rr * g.cols + cc] : INF;
+            }
+            lab_syncwarp();
+        }
         bool hit = false;
         if (lane < 4) {
             long long const nr = r + dr[lane], nc = c + dc[lane];
@@ -327,31 +374,31 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
                 hit = level(nr, nc) == d - 1;
             }
         }
-        uint32_t const m = lab_ballot(hit);
-        if (m == 0) {
+        uint32_t const mk = lab_ballot(hit);
+        if (mk == 0) {
             break; // cannot happen on a converged field
         }
-        int const k = lab_ffs64(m) - 1;
+        int const k = lab_ffs64(mk) - 1;
         r += dr[k];
         c += dc[k];
         d--;
         if (lane == 0) {
-            if (out && n < max_out) {
-                out[2 * n] = static_cast<int32_t>(r);
-                out[2 * n + 1] = static_cast<int32_t>(c);
-            }
-            if (repaint_bits) {
-                uint16_t const s = grid[r * g.cols + c];
-                grid[r * g.cols + c] = static_cast<uint16_t>((s & ~SQ_PAINT_MASK) | repaint_bits);
-            }
+            batch[nb] = static_cast<uint32_t>(r * g.cols + c);
         }
+        nb++;
         n++;
+        if (nb == static_cast<uint32_t>(WALK_BATCH)) {
+            walk_flush(g, batch, nb, flushed, grid, out, max_out, repaint_bits, lane);
+            flushed += nb;
+            nb = 0;
+        }
         if (first_only) {
             break;
         }
     }
+    walk_flush(g, batch, nb, flushed, grid, out, max_out, repaint_bits, lane);
     if (lane == 0) {
-        res->path_len[slot] = first_only ? static_cast<unsigned long long>(level(fr, fc)) : n;
+        res->path_len[slot] = first_only ? static_cast<unsigned long long>(d0) : n;
     }
 }
 

@@ -23,17 +23,21 @@
 
 namespace lab {
 
+// (signed: in a row band the box is the part of the room inside the band -- empty if r0 > r1 -- and the source may
+// lie in another band, above row 0 or below the last row)
 struct Room {
-    uint32_t r0, r1, c0, c1, sr, sc;
+    int r0, r1, c0, c1, sr, sc;
 };
 
 LAB_DEV Room room_load(Control const *ctl) { return {ctl->room_r0, ctl->room_r1, ctl->room_c0, ctl->room_c1, ctl->room_sr, ctl->room_sc}; }
 
+LAB_DEV uint32_t room_absdiff(int a, int b) { return static_cast<uint32_t>(a > b ? a - b : b - a); }
+
 // plane 0's level of square (r, c): Manhattan distance inside the box, INF outside (nothing is passable there)
 LAB_DEV uint32_t room_level(Room const &m, uint32_t r, uint32_t c) {
-    bool const inside = r - m.r0 <= m.r1 - m.r0 && c - m.c0 <= m.c1 - m.c0; // (unsigned: below r0 wraps around)
-    uint32_t const dr = r > m.sr ? r - m.sr : m.sr - r, dc = c > m.sc ? c - m.sc : m.sc - c;
-    return inside ? dr + dc : INF;
+    int const ri = static_cast<int>(r), ci = static_cast<int>(c);
+    bool const inside = ri >= m.r0 && ri <= m.r1 && ci >= m.c0 && ci <= m.c1;
+    return inside ? room_absdiff(ri, m.sr) + room_absdiff(ci, m.sc) : INF;
 }
 
 // What a paint rule set gives a square at level lv (Paint_rule of post.cuh, flattened: below[k], bits[k]).
@@ -85,9 +89,10 @@ LAB_DEV uint32_t room_stream(Params const &p, Room const &m, Room_rules const &q
             uint32_t any = 0;
             // Nearly every chunk lies in one row and wholly inside the room: its levels are dr + |d0 + u|, and
             // (solvers) usually all of them on the same side of every rule's threshold.
-            if (c + 8u <= cols && r - m.r0 <= m.r1 - m.r0 && c >= m.c0 && c + 7u <= m.c1) {
-                uint32_t const dr = r > m.sr ? r - m.sr : m.sr - r;
-                int const d0 = static_cast<int>(c) - static_cast<int>(m.sc);
+            if (c + 8u <= cols && static_cast<int>(r) >= m.r0 && static_cast<int>(r) <= m.r1 && static_cast<int>(c) >= m.c0 &&
+                static_cast<int>(c) + 7 <= m.c1) {
+                uint32_t const dr = room_absdiff(static_cast<int>(r), m.sr);
+                int const d0 = static_cast<int>(c) - m.sc;
                 if (MODE == 0) {
 #pragma unroll
                     for (int u = 0; u < 8; u++) {

@@ -83,6 +83,18 @@ LAB_DEV bool tree_follow(Tree const &tr, uint32_t slot) { // may a round follow 
     return slot < tr.nslots && (tr.jump_hi == 0u || slot - tr.jump_lo < tr.jump_hi - tr.jump_lo);
 }
 
+// Row bands: the ranks found (from their counts and bounding boxes) that the whole maze is an open room; this band's
+// part of it and the source, relative to the band, come from the host.  One thread.
+LAB_DEV void room_set_body(Control *ctl, int r0, int r1, int c0, int c1, int sr, int sc) {
+    ctl->room_r0 = r0;
+    ctl->room_r1 = r1;
+    ctl->room_c0 = c0;
+    ctl->room_c1 = c1;
+    ctl->room_sr = sr;
+    ctl->room_sc = sc;
+    ctl->room = 1u;
+}
+
 LAB_DEV bool tree_live(Tree_ctl const *tc) { return tc->ok != 0 && tc->unreached == 0 && tc->bad_weight == 0 && tc->walk_error == 0; }
 
 // the arc entering the neighbouring tile through the same crossing
@@ -473,12 +485,12 @@ LAB_DEV void tree_init_body(Params const &p, Tree const &tr) {
         unsigned long long const area = static_cast<unsigned long long>(tc->box_r1 - r0 + 1u) * (tc->box_c1 - c0 + 1u);
         if (area == tc->V && p.ctl->src_tile[0] != 0xFFFFFFFFu) {
             Control *ctl = p.ctl;
-            ctl->room_r0 = r0;
-            ctl->room_r1 = tc->box_r1;
-            ctl->room_c0 = c0;
-            ctl->room_c1 = tc->box_c1;
-            ctl->room_sr = (ctl->src_tile[0] / static_cast<uint32_t>(p.g.tiles_x)) * TS + (ctl->src_rc[0] >> 8);
-            ctl->room_sc = (ctl->src_tile[0] % static_cast<uint32_t>(p.g.tiles_x)) * TS + (ctl->src_rc[0] & 0xFFu);
+            ctl->room_r0 = static_cast<int32_t>(r0);
+            ctl->room_r1 = static_cast<int32_t>(tc->box_r1);
+            ctl->room_c0 = static_cast<int32_t>(c0);
+            ctl->room_c1 = static_cast<int32_t>(tc->box_c1);
+            ctl->room_sr = static_cast<int32_t>((ctl->src_tile[0] / static_cast<uint32_t>(p.g.tiles_x)) * TS + (ctl->src_rc[0] >> 8));
+            ctl->room_sc = static_cast<int32_t>((ctl->src_tile[0] % static_cast<uint32_t>(p.g.tiles_x)) * TS + (ctl->src_rc[0] & 0xFFu));
             ctl->room = 1u;
         }
     }
@@ -1135,12 +1147,15 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
             ctl->target_val[j] = room_level(m, static_cast<uint32_t>(cell / static_cast<unsigned long long>(p.g.cols)),
                                             static_cast<uint32_t>(cell % static_cast<unsigned long long>(p.g.cols)));
         }
-        uint32_t const far_r = lab_umax(m.sr - m.r0, m.r1 - m.sr), far_c = lab_umax(m.sc - m.c0, m.c1 - m.sc);
-        ctl->max_level = far_r + far_c; // the farthest corner of the box
+        if (m.r0 <= m.r1 && m.c0 <= m.c1) { // the farthest corner of the box (row bands: of the band's part of it, if any)
+            ctl->max_level = lab_umax(room_absdiff(m.r0, m.sr), room_absdiff(m.r1, m.sr)) + lab_umax(room_absdiff(m.c0, m.sc), room_absdiff(m.c1, m.sc));
+        }
         for (unsigned long long q = 0; q < ctl->tail; q++) {
             p.queue[q & p.qmask] = Q_EMPTY;
         }
-        p.plane[0].state[ctl->src_tile[0]] = 0;
+        if (ctl->src_tile[0] != 0xFFFFFFFFu) {
+            p.plane[0].state[ctl->src_tile[0]] = 0;
+        }
         ctl->tail = 0;
         ctl->pending = 0;
         ctl->done = 1;

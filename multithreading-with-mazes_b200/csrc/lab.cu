@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(256) k_room_distance(Params p, uint16_t *grid,
     room_distance_body(p, grid, &res->settled, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
                        static_cast<long long>(gridDim.x) * blockDim.x);
 }
+__global__ void k_room_set(Control *ctl, int r0, int r1, int c0, int c1, int sr, int sc) { room_set_body(ctl, r0, r1, c0, c1, sr, sc); }
 __global__ void __launch_bounds__(256) k_tree_gate(Params p, Tree tr) {
     tree_gate_body(p, tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
 }
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(256) k_paint(Params p, uint16_t *grid, Result 
 // the resolved result so that no host round trip sits between the search and the walk.
 __global__ void k_walk(Params p, int game, uint16_t *grid, Result *res, int32_t const *finish_rc, int32_t *out,
                        unsigned long long out_stride, unsigned long long max_out, int first_only) {
+    __shared__ uint32_t sm[WALK_SM_U32]; // one warp per block
     int const slot = static_cast<int>(blockIdx.x);
     int plane = 0, fj = 0;
     uint32_t repaint = 0;
@@ -278,7 +280,7 @@ __global__ void k_walk(Params p, int game, uint16_t *grid, Result *res, int32_t 
         }
     }
     walk_body(p, plane, finish_rc[2 * fj], finish_rc[2 * fj + 1], grid, out ? out + slot * out_stride * 2 : nullptr,
-              max_out, repaint, first_only, res, slot, lane_id());
+              max_out, repaint, first_only, res, slot, lane_id(), sm);
 }
 
 __global__ void k_gather_fixup(Geom g, uint16_t *grid, Result const *res, int32_t const *finish_rc,
@@ -1508,7 +1510,7 @@ int lab_band_tree_chunk_words(const lab_grid *h, int stage) {
     return static_cast<int>(BORDER_HDR + (stage == 1 ? 6u * R : (stage == 2 ? 2u * R + 2u * (R / 32u) : 4u * R)));
 }
 
-int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs, uint32_t *crossings) {
+int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs, uint32_t *crossings, int32_t box[4]) {
     int rc = band_tree_ready(h, "lab_band_tree_count");
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -1526,7 +1528,31 @@ int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs, uint32_
     if (squares) *squares = tc.V;
     if (pairs) *pairs = tc.E;
     if (crossings) *crossings = tc.crossings;
+    if (box) { // bounding box of the band's passable squares, rows relative to the band (r0 > r1: none)
+        box[0] = tc.V ? static_cast<int32_t>(0x7FFFFFFFu - tc.box_r0_inv) : 1;
+        box[1] = tc.V ? static_cast<int32_t>(tc.box_r1) : 0;
+        box[2] = tc.V ? static_cast<int32_t>(0x7FFFFFFFu - tc.box_c0_inv) : 1;
+        box[3] = tc.V ? static_cast<int32_t>(tc.box_c1) : 0;
+    }
     return LAB_OK;
+}
+
+// The ranks' counts and boxes say that the whole maze is one open room (device/room.cuh): this band's part of it
+// [r0, r1] x [c0, c1] (empty if r0 > r1) and the source, all relative to the band; levels in one streaming pass.
+int lab_band_room(lab_grid *h, int r0, int r1, int c0, int c1, int src_r, int src_c) {
+    int rc = band_tree_ready(h, "lab_band_room");
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Tree const tr = h->band_tree;
+    Params p = make_params(h, 1);
+    k_room_set<<<1, 1, 0, s>>>(h->ctl, r0, r1, c0, c1, src_r, src_c);
+    k_room_distance<<<h->sm_count * 8, 256, 0, s>>>(p, h->squares, h->res);
+    TRACE("k_room_distance", s);
+    k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, tr);
+    TRACE("k_tree_gate", s);
+    h->launches += 3;
+    CU(cudaGetLastError());
+    return band_tree_read(h, h->tree_last);
 }
 
 // walk + the band's own part of the ranking -> chunk 1

@@ -401,7 +401,7 @@ int emu_band_tree_chunk_words(void *h, int stage) {
     return static_cast<int>(border_chunk_words(p, stage));
 }
 
-int emu_band_tree_count(void *h, uint64_t *squares, uint64_t *pairs, uint32_t *crossings) {
+int emu_band_tree_count(void *h, uint64_t *squares, uint64_t *pairs, uint32_t *crossings, int32_t *box) {
     auto *e = static_cast<Emu_band *>(h);
     Params p = make_params(e->w, 1);
     int const nw = e->nwarps;
@@ -412,6 +412,23 @@ int emu_band_tree_count(void *h, uint64_t *squares, uint64_t *pairs, uint32_t *c
     *squares = e->tc.V;
     *pairs = e->tc.E;
     *crossings = e->tc.crossings;
+    box[0] = e->tc.V ? static_cast<int32_t>(0x7FFFFFFFu - e->tc.box_r0_inv) : 1;
+    box[1] = e->tc.V ? static_cast<int32_t>(e->tc.box_r1) : 0;
+    box[2] = e->tc.V ? static_cast<int32_t>(0x7FFFFFFFu - e->tc.box_c0_inv) : 1;
+    box[3] = e->tc.V ? static_cast<int32_t>(e->tc.box_c1) : 0;
+    return 0;
+}
+
+int emu_band_room(void *h, int r0, int r1, int c0, int c1, int src_r, int src_c) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    long long const nthreads = static_cast<long long>(nw) * 32;
+    Tree const tr = e->tr;
+    room_set_body(&e->w.ctl, r0, r1, c0, c1, src_r, src_c);
+    simt::launch(nw, [&](int wid, int lane) { room_distance_body(p, e->w.grid_ptr, &e->w.res.settled, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    e->tree_last = e->tc;
     return 0;
 }
 
@@ -546,8 +563,9 @@ int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *star
             fj = w.res.finish_of[slot];
             if (fj < 0) return;
         }
+        std::vector<uint32_t> wsm(WALK_SM_U32);
         simt::launch(1, [&](int, int lane) {
-            walk_body(p, plane, frc[2 * fj], frc[2 * fj + 1], grid, out, max_out, repaint, first_only, &w.res, slot, lane);
+            walk_body(p, plane, frc[2 * fj], frc[2 * fj + 1], grid, out, max_out, repaint, first_only, &w.res, slot, lane, wsm.data());
         });
     };
     if (game == GAME_GATHER) {

@@ -144,19 +144,19 @@ def _gloo_emu_worker(rank, world, port, maze_path, out_dir, use_tree):
     eng = emu_band_engine(maze[r0 : r0 + n].copy(), nwarps=3, sched=rank + 1)
     res = bands.sharded_distance_map(eng, lab.distance_start(*maze.shape), r0, n, use_tree=use_tree)
     np.savez(os.path.join(out_dir, f"band{rank}.npz"), dist=eng.levels(), sq=eng.sq, r0=r0, mx=res["max"], settled=res["settled"],
-             rounds=res["rounds"], tree=int(res["tree"]), used=eng.tree_used())
+             rounds=res["rounds"], road=res["road"], used=eng.tree_used())
     eng.close()
     dist.destroy_process_group()
 
 
-def _check_bands(tmp_path, world, maze, O, want_tree):
+def _check_bands(tmp_path, world, maze, O, road):
     g_ref, d_ref, mx_ref, settled_ref = O.distance_map(maze)
     for rank in range(world):
         z = np.load(tmp_path / f"band{rank}.npz")
         r0 = int(z["r0"])
         n = z["dist"].shape[0]
-        assert int(z["tree"]) == int(want_tree) and int(z["used"]) == int(want_tree), (rank, int(z["tree"]), int(z["used"]))
-        assert (int(z["rounds"]) == 0) == want_tree
+        assert str(z["road"]) == road and int(z["used"]) == {"wave": 0, "tree": 1, "room": 2}[road], (rank, str(z["road"]), int(z["used"]))
+        assert (int(z["rounds"]) == 0) == (road != "wave")
         assert (z["dist"] == d_ref[r0 : r0 + n]).all(), (rank, int((z["dist"] != d_ref[r0 : r0 + n]).sum()))
         assert (z["sq"] == g_ref[r0 : r0 + n]).all()
         assert int(z["mx"]) == mx_ref and int(z["settled"]) == settled_ref
@@ -173,7 +173,7 @@ def test_sharded_tree_pipeline_on_gloo(lab, O, tmp_path, builder, rows, cols, wo
     np.save(path, maze)
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_gloo_emu_worker, args=(world, port, path, str(tmp_path), True), nprocs=world, join=True)
-    _check_bands(tmp_path, world, maze, O, want_tree=True)
+    _check_bands(tmp_path, world, maze, O, "tree")
 
 
 def test_sharded_non_trees_fall_back_to_the_wave_on_gloo(lab, O, tmp_path):
@@ -188,7 +188,24 @@ def test_sharded_non_trees_fall_back_to_the_wave_on_gloo(lab, O, tmp_path):
         np.save(path, maze)
         port = 33500 + (os.getpid() % 2000) + i
         mp.spawn(_gloo_emu_worker, args=(2, port, path, str(tmp_path), True), nprocs=2, join=True)
-        _check_bands(tmp_path, 2, maze, O, want_tree=False)
+        _check_bands(tmp_path, 2, maze, O, "wave")
+
+
+def test_sharded_open_room_on_gloo(lab, O, tmp_path):
+    """An arena across 3 bands: no search and no exchange, every band writes its part of the room from the closed form
+    (the start lies in the middle band; for the other two it is above / below the band).  One wall square inside
+    and it is the relax/exchange loop again."""
+    import torch.multiprocessing as mp
+
+    arena = lab.build_maze("arena", 193, 131, seed=1)
+    holed = arena.copy()
+    holed[150, 20] &= ~np.uint16(lab.PATH_BIT)
+    for i, (maze, road) in enumerate([(arena, "room"), (holed, "wave")]):
+        path = str(tmp_path / "maze.npy")
+        np.save(path, maze)
+        port = 35500 + (os.getpid() % 2000) + i
+        mp.spawn(_gloo_emu_worker, args=(3, port, path, str(tmp_path), True), nprocs=3, join=True)
+        _check_bands(tmp_path, 3, maze, O, road)
 
 
 def test_split_rows(lab):
@@ -259,7 +276,13 @@ def _lockstep_tree(eng, split, start, cols):
     counts = [e.tree_count() for e in eng]
     squares, pairs = sum(c[0] for c in counts), sum(c[1] for c in counts)
     if squares < 2 or pairs + 1 != squares:
-        return False
+        boxes = [(r0 + c[3], r0 + c[4], c[5], c[6]) for c, (r0, _) in zip(counts, split) if c[0]]
+        R0, R1, C0, C1 = min(b[0] for b in boxes), max(b[1] for b in boxes), min(b[2] for b in boxes), max(b[3] for b in boxes)
+        if squares != (R1 - R0 + 1) * (C1 - C0 + 1):
+            return False
+        for e, (r0, n) in zip(eng, split):
+            e.room(max(R0, r0) - r0, min(R1, r0 + n - 1) - r0, C0, C1, start[0] - r0, start[1])
+        return "room"
     owner = next(i for i, (r0, n) in enumerate(split) if r0 <= start[0] < r0 + n)
     for e, b in zip(eng, bufs):
         e.tree_rank_local(squares, pairs, b["chunk1"])
@@ -346,3 +369,36 @@ def test_band_tree_gives_a_non_tree_back_to_the_wave(lab, O):
     got_g = np.concatenate([s.cpu().numpy().view(np.uint16) for s in sq])
     assert (got_d == d_ref).all() and (got_g == g_ref).all()
     assert max(r[0] for r in res) == mx_ref and sum(r[1] for r in res) == settled_ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,nb,start", [(511, 383, 3, None), (1023, 2049, 4, (1000, 7)), (129, 67, 2, (1, 65))])
+def test_band_room_one_process(lab, O, rows, cols, nb, start):
+    """lab_band_room: an arena across 2-4 bands on ONE device; every band writes its part of the room from the closed
+    form, whichever band the start lies in."""
+    import torch
+
+    from mazes_b200 import bands
+
+    maze = lab.build_maze("arena", rows, cols, seed=1)
+    split = bands.split_rows(rows, nb)
+    sq = [torch.from_numpy(maze[r0 : r0 + n].view(np.int16).copy()).cuda() for r0, n in split]
+    lv = [torch.full((n, cols), 0x5A5A5A5A, dtype=torch.int32, device="cuda") for _, n in split]
+    eng = [bands.GpuBandEngine(lab, s) for s in sq]
+    for e, l in zip(eng, lv):
+        e.grid.bind_levels(0, l.data_ptr())
+    start = start or lab.distance_start(rows, cols)
+    for e, (r0, n) in zip(eng, split):
+        e.begin((start[0] - r0, start[1]) if r0 <= start[0] < r0 + n else None)
+    rows_p = [tuple(t.clone() for t in e.path_rows()) for e in eng]
+    for i, e in enumerate(eng):
+        e.set_neighbour_paths(rows_p[i - 1][1] if i > 0 else None, rows_p[i + 1][0] if i < nb - 1 else None)
+    assert _lockstep_tree(eng, split, start, cols) == "room"
+    res = [e.finish() for e in eng]
+    assert all(e.grid.stats()["tree_used"] == 2 for e in eng)
+    d_ref = O.bfs_levels(maze, *start)
+    reached = d_ref != INF
+    got_d = np.concatenate([l.cpu().numpy().view(np.uint32) for l in lv])
+    got_g = np.concatenate([s.cpu().numpy().view(np.uint16) for s in sq])
+    assert (got_d == d_ref).all() and (((got_g & lab.MEASURE_BIT) != 0) == reached).all()
+    assert max(r[0] for r in res) == int(d_ref[reached].max()) and sum(r[1] for r in res) == int(reached.sum())

@@ -98,6 +98,17 @@ def test_emulated_games_on_trees_use_the_pipeline(lab, O, emu):
     assert (g == g_ref).all() and (c == c_ref).all() and paths_equal(paths, p_ref)
 
 
+def test_emulated_long_winner_path_is_walked_in_batches(lab, O, emu):
+    """rdfs: one corridor thousands of squares long.  The path walk (post.cuh walk_body) caches a tile of levels at a
+    time and flushes the collected squares 1024 at a time: several tiles, several flushes, same path and repaint."""
+    maze = lab.build_maze("rdfs", 131, 197, seed=4)
+    placed, s, f = lab.place_hunt(maze, seed=52)
+    g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
+    assert len(p_ref) > 1100, len(p_ref)
+    g, w, _, paths, _ = emu.solver(1, placed, [s], [f], 4, 1)
+    assert (g == g_ref).all() and w == w_ref and paths_equal([paths[0]], [p_ref])
+
+
 # ------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("builder,n", [("kruskal", 1023), ("wilson", 2047), ("rdfs", 1535), ("kruskal", 4095)])
