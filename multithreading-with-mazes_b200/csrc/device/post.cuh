@@ -312,15 +312,30 @@ constexpr int WALK_SM_U32 = TS * TS + WALK_BATCH; // per warp: cached levels | c
 LAB_DEV void walk_flush(Geom const &g, uint32_t const *batch, uint32_t nb, unsigned long long base, uint16_t *grid, int32_t *out,
                         unsigned long long max_out, uint32_t repaint_bits, int lane) {
     lab_syncwarp();
-    for (uint32_t i = static_cast<uint32_t>(lane); i < nb; i += 32u) {
-        uint32_t const idx = batch[i];
-        if (out && base + i < max_out) {
-            uint32_t const r = idx / static_cast<uint32_t>(g.cols);
-            out[2 * (base + i)] = static_cast<int32_t>(r);
-            out[2 * (base + i) + 1] = static_cast<int32_t>(idx - r * static_cast<uint32_t>(g.cols));
+    constexpr uint32_t U = 8; // squares per lane whose Squares are in flight together
+    for (uint32_t i0 = static_cast<uint32_t>(lane); i0 < nb; i0 += 32u * U) {
+        uint32_t idx[U];
+        uint16_t sq[U];
+#pragma unroll
+        for (uint32_t u = 0; u < U; u++) {
+            uint32_t const i = i0 + 32u * u;
+            idx[u] = i < nb ? batch[i] : 0xFFFFFFFFu;
+            sq[u] = (repaint_bits && idx[u] != 0xFFFFFFFFu) ? grid[idx[u]] : static_cast<uint16_t>(0);
         }
-        if (repaint_bits) {
-            grid[idx] = static_cast<uint16_t>((grid[idx] & ~SQ_PAINT_MASK) | repaint_bits);
+#pragma unroll
+        for (uint32_t u = 0; u < U; u++) {
+            uint32_t const i = i0 + 32u * u;
+            if (idx[u] == 0xFFFFFFFFu) {
+                continue;
+            }
+            if (out && base + i < max_out) {
+                uint32_t const r = idx[u] / static_cast<uint32_t>(g.cols);
+                out[2 * (base + i)] = static_cast<int32_t>(r);
+                out[2 * (base + i) + 1] = static_cast<int32_t>(idx[u] - r * static_cast<uint32_t>(g.cols));
+            }
+            if (repaint_bits) {
+                grid[idx[u]] = static_cast<uint16_t>((sq[u] & ~SQ_PAINT_MASK) | repaint_bits);
+            }
         }
     }
     lab_syncwarp();
@@ -335,58 +350,109 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
     Room const m = room_load(p.ctl);
     uint32_t *cache = sm, *batch = sm + TS * TS;
     int cty = -1, ctx = -1; // the cached tile
-    auto level = [&](long long rr, long long cc) {
-        if (room) {
-            return room_level(m, static_cast<uint32_t>(rr), static_cast<uint32_t>(cc));
-        }
-        int const ty = static_cast<int>(rr / TS), tx = static_cast<int>(cc / TS);
-        if (ty == cty && tx == ctx) {
-            return cache[(rr % TS) * TS + (cc % TS)];
-        }
-        return dist[rr * g.cols + cc];
-    };
-    long long r = fr, c = fc;
-    uint32_t const d0 = room ? room_level(m, static_cast<uint32_t>(r), static_cast<uint32_t>(c)) : dist[r * g.cols + c];
+    int r = fr, c = fc; // (rows, cols < 2^16: make_geom)
+    uint32_t const d0 = room ? room_level(m, static_cast<uint32_t>(r), static_cast<uint32_t>(c)) : dist[static_cast<long long>(r) * g.cols + c];
     uint32_t d = d0;
-    unsigned long long n = 0, flushed = 0;
+    unsigned long long flushed = 0;
     uint32_t nb = 0;
     if (d == INF) {
         if (lane == 0) res->path_len[slot] = 0;
         return;
     }
-    int const dr[4] = {-1, 0, 1, 0};
-    int const dc[4] = {0, 1, 0, -1};
+    // N, E, S, W (maze/maze.cc:213-218) without a table in local memory: k -> (k odd ? 0 : k - 1, k odd ? 2 - k : 0)
+    int const my_dr = (lane & 1) ? 0 : (lane & 3) - 1, my_dc = (lane & 1) ? 2 - (lane & 3) : 0;
     while (d > 0) {
-        if (!room && !first_only && (static_cast<int>(r / TS) != cty || static_cast<int>(c / TS) != ctx)) {
+        if (!room && !first_only && ((r >> 6) != cty || (c >> 6) != ctx)) {
             lab_syncwarp(); // (everybody is done with the old tile)
-            cty = static_cast<int>(r / TS);
-            ctx = static_cast<int>(c / TS);
-            for (int i = lane; i < TS * TS; i += 32) {
-                long long const rr = static_cast<long long>(cty) * TS + i / TS, cc = static_cast<long long>(ctx) * TS + i % TS;
-                cache[i] = (rr < g.rows && cc < g.cols) ? dist[rr * g.cols + cc] : INF;
+            cty = r >> 6;
+            ctx = c >> 6;
+            // all 128 loads of a lane are issued before the first is used: the tile costs ONE round trip to memory
+            {
+                uint32_t v[TS * TS / 32];
+                long long const row0 = static_cast<long long>(cty) * TS, col0 = static_cast<long long>(ctx) * TS + lane;
+                uint32_t const *src = dist + row0 * g.cols + col0;
+                bool const in0 = col0 < g.cols, in1 = col0 + 32 < g.cols;
+#pragma unroll
+                for (int k = 0; k < TS * TS / 32; k++) { // entry lane + 32 k: row k / 2, column lane + 32 (k % 2)
+                    bool const ok = row0 + (k >> 1) < g.rows && ((k & 1) ? in1 : in0);
+                    v[k] = ok ? lab_ld_ro(src + static_cast<long long>(k >> 1) * g.cols + 32 * (k & 1)) : INF;
+                }
+#pragma unroll
+                for (int k = 0; k < TS * TS / 32; k++) {
+                    cache[lane + 32 * k] = v[k];
+                }
             }
             lab_syncwarp();
         }
+        // Inside the cached tile, away from its border: an LDS, a vote and a shuffle per step and little else (a single
+        // warp issues one dependent instruction every ~5 cycles, so the step's instruction count IS the walk's speed).
+        if (!room && !first_only) {
+            uint32_t const origin = static_cast<uint32_t>(cty << 6) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(ctx << 6);
+            bool const voter = lane < 4;
+            int const my_off = voter ? my_dr * TS + my_dc : 0; // lanes 0..3 look N, E, S, W of the walker; the others at it
+            int idx = ((r & 63) << 6) | (c & 63);
+            int lr = idx >> 6, lc = idx & 63;
+            uint32_t const room_left = static_cast<uint32_t>(WALK_BATCH) - nb;
+            int budget = static_cast<int>(d < room_left ? d : room_left); // steps before the start is reached / the batch is full
+            bool lost = false;
+            while (budget > 0 && static_cast<unsigned>(lr - 1) < 62u && static_cast<unsigned>(lc - 1) < 62u) {
+                int const cand = idx + my_off;
+                uint32_t const mk = lab_ballot(voter && cache[cand] == d - 1);
+                if (mk == 0) {
+                    lost = true;
+                    break;
+                }
+                idx = static_cast<int>(lab_shfl(static_cast<uint32_t>(cand), lab_ffs32(mk) - 1)); // first of N, E, S, W one level lower
+                d--;
+                budget--;
+                lr = idx >> 6;
+                lc = idx & 63;
+                if (lane == 0) {
+                    batch[nb] = origin + static_cast<uint32_t>(lr) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(lc);
+                }
+                nb++;
+            }
+            r = (cty << 6) + lr;
+            c = (ctx << 6) + lc;
+            if (lost) {
+                break;
+            }
+            if (nb == static_cast<uint32_t>(WALK_BATCH)) {
+                walk_flush(g, batch, nb, flushed, grid, out, max_out, repaint_bits, lane);
+                flushed += nb;
+                nb = 0;
+            }
+            if (d == 0) {
+                break;
+            }
+        }
         bool hit = false;
         if (lane < 4) {
-            long long const nr = r + dr[lane], nc = c + dc[lane];
+            int const nr = r + my_dr, nc = c + my_dc;
             if (nr >= 0 && nr < g.rows && nc >= 0 && nc < g.cols) {
-                hit = level(nr, nc) == d - 1;
+                uint32_t lv;
+                if (room) {
+                    lv = room_level(m, static_cast<uint32_t>(nr), static_cast<uint32_t>(nc));
+                } else if ((nr >> 6) == cty && (nc >> 6) == ctx) {
+                    lv = cache[((nr & 63) << 6) | (nc & 63)];
+                } else {
+                    lv = dist[static_cast<long long>(nr) * g.cols + nc];
+                }
+                hit = lv == d - 1;
             }
         }
         uint32_t const mk = lab_ballot(hit);
         if (mk == 0) {
             break; // cannot happen on a converged field
         }
-        int const k = lab_ffs64(mk) - 1;
-        r += dr[k];
-        c += dc[k];
+        int const k = lab_ffs32(mk) - 1;
+        r += (k & 1) ? 0 : k - 1;
+        c += (k & 1) ? 2 - k : 0;
         d--;
         if (lane == 0) {
-            batch[nb] = static_cast<uint32_t>(r * g.cols + c);
+            batch[nb] = static_cast<uint32_t>(r) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(c);
         }
         nb++;
-        n++;
         if (nb == static_cast<uint32_t>(WALK_BATCH)) {
             walk_flush(g, batch, nb, flushed, grid, out, max_out, repaint_bits, lane);
             flushed += nb;
@@ -396,6 +462,7 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
             break;
         }
     }
+    unsigned long long const n = flushed + nb; // squares walked
     walk_flush(g, batch, nb, flushed, grid, out, max_out, repaint_bits, lane);
     if (lane == 0) {
         res->path_len[slot] = first_only ? static_cast<unsigned long long>(d0) : n;

@@ -8,12 +8,17 @@ what, builder, n, reps = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.arg
 maze = lab.build_maze(builder, n, n, seed=0xB2000002)
 if what == "gather":
     maze, start, fin = lab.place_gather(maze, seed=0xB2000003)
+if what == "hunt":
+    maze, start, fin = lab.place_hunt(maze, seed=0xB2000003)
 with lab.Grid.from_host(maze) as g:
     for rep in range(reps):
         g.upload(maze)
         if what == "distance":
             r = g.distance_map(want_dist=False)
             out = {"max": r.max, "settled": r.settled}
+        elif what == "hunt":
+            r = g.hunt(start, fin, want_path=False)
+            out = {"path_len": r.path_len, "painted": r.painted}
         else:
             r = g.gather(start, fin, want_paths=False)
             out = {"path_len": r.path_len, "painted": r.painted}
