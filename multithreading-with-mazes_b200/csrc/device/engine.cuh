@@ -94,6 +94,10 @@ struct Control {
     // the open room (device/room.cuh; decided by tree_init_body): the passable squares are exactly the
     // rectangle [room_r0, room_r1] x [room_c0, room_c1], so plane 0's level of a square is its Manhattan
     // distance from the source (room_sr, room_sc) and no field has to be searched
+    // distance map on a tree: the fix-up has set the measure bit on every square it gave a level (n_marked of them),
+    // measure_body only adds the count
+    uint32_t measured;
+    unsigned long long n_marked;
     uint32_t room;
     int32_t room_r0, room_r1, room_c0, room_c1, room_sr, room_sc; // (row bands: relative to the band, see room.cuh)
 };

@@ -99,6 +99,12 @@ LAB_DEV void measure_body(Geom g, uint16_t *grid, uint64_t const *visited, Contr
     if (ctl->room) {
         return; // an open room: room_distance_body has set the bits and counted the squares
     }
+    if (ctl->measured) { // one tree: tree_fixup_body has set the bits, this only reports how many
+        if (gwarp == 0 && lane == 0) {
+            lab_atomic_add(reinterpret_cast<uint64_t *>(&res->settled), static_cast<uint64_t>(ctl->n_marked));
+        }
+        return;
+    }
     // one warp per row (grid stride); a 64-square word with no visited square costs one 8-byte load
     unsigned long long count = 0;
     constexpr int U = 4; // 64-square words of a row handled together: independent read-modify-writes in flight

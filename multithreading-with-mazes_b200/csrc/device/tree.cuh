@@ -51,6 +51,7 @@ struct Tree_ctl {
     // bounding box of the passable squares (0x7FFFFFFF - min as a running max, so that the all-zero reset
     // means "nothing yet"): a box that holds exactly V squares is an OPEN ROOM (device/room.cuh)
     uint32_t box_r0_inv, box_r1, box_c0_inv, box_c1;
+    unsigned long long marked; // squares the fix-up has given Tree::mark_bits
     uint32_t crossings;  // border crossings of the tiles counted (= the entries the walk will add to alist)
     uint32_t alist_base; // row bands: where this band's piece of the global crossing list starts
 };
@@ -77,6 +78,9 @@ struct Tree {
     // the two (tree_finish_jump_body).  jump_hi == 0: no window.  jump_skip: bit 0 = no parent pass before
     // the prefix rounds, bit 1 = no orient pass after the ranking rounds (they run as launches of their own).
     uint32_t jump_lo, jump_hi, jump_skip;
+    // Square bits the fix-up ORs into every square it gives a level: Rgb::measure for the distance map
+    // (painters/distance.cc:138,149 -- saves measure_body's pass over the grid), 0 for the solvers.
+    uint32_t mark_bits;
 };
 
 LAB_DEV bool tree_follow(Tree const &tr, uint32_t slot) { // may a round follow a pointer to `slot`?
@@ -1075,7 +1079,7 @@ LAB_DEV void tree_finish_jump_body(Params const &p, Tree const &tr, long long gt
 // 6 fix-up.  component << 16 | local level  ->  level of the component's entry + local level.
 // One warp-item = 64 squares of one row inside one tile (so the entry levels it needs are one 1 KB
 // table); lane reads squares lane and lane + 32.
-LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, long long gwarp, long long nwarps, int lane) {
+LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, uint16_t *grid, long long gwarp, long long nwarps, int lane) {
     Tree_ctl *tc = tr.tc;
     if (!tree_live(tc)) {
         return;
@@ -1083,7 +1087,8 @@ LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, long long gwarp, l
     Geom const &g = p.g;
     uint32_t const *lvl = tr.r[0]; // (tree_jump_settle_body)
     uint32_t *dist = p.plane[0].dist;
-    uint32_t mx = 0;
+    uint32_t mx = 0, marked = 0;
+    uint16_t const mark = static_cast<uint16_t>(tr.mark_bits);
     // one warp-item = four tiles' worth of one row: eight independent loads per lane in flight
     constexpr int U = 4;
     long long const chunks = (g.tiles_x + U - 1) / U;
@@ -1092,6 +1097,7 @@ LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, long long gwarp, l
         int const r = static_cast<int>(it / chunks);
         int const j0 = static_cast<int>(it % chunks) * U;
         uint32_t *row = dist + static_cast<long long>(r) * g.cols;
+        uint16_t *srow = grid + static_cast<long long>(r) * g.cols;
         long long const trow = static_cast<long long>(r / TS) * g.tiles_x;
         // The field was NOT reset before the flood: what is passable comes from the tile masks (all
         // passable squares were reached: one tree), everything else becomes INF here.
@@ -1101,11 +1107,13 @@ LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, long long gwarp, l
             w[u] = j0 + u < g.tiles_x ? lab_ld_ro(p.path + (trow + j0 + u) * TS + (r % TS)) : 0ull;
         }
         uint32_t v[2 * U];
+        uint16_t sq[2 * U];
 #pragma unroll
         for (int u = 0; u < 2 * U; u++) {
             int const c = j0 * TS + lane + 32 * u;
             bool const pass = (w[u / 2] >> (lane + 32 * (u & 1))) & 1ull;
             v[u] = pass ? row[c] : INF;
+            sq[u] = (pass && mark) ? srow[c] : static_cast<uint16_t>(0);
         }
 #pragma unroll
         for (int u = 0; u < 2 * U; u++) {
@@ -1116,14 +1124,22 @@ LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, long long gwarp, l
                 uint32_t const out = (comp == ROOT_COMP ? 0u : b[comp]) + (v[u] & 0xFFFFu);
                 row[c] = out;
                 mx = out > mx ? out : mx;
+                if (mark) {
+                    srow[c] = static_cast<uint16_t>(sq[u] | mark);
+                    marked++;
+                }
             } else if (c < g.cols) {
                 row[c] = INF;
             }
         }
     }
     mx = lab_reduce_max(mx);
+    marked = lab_reduce_add(marked);
     if (lane == 0 && mx) {
         lab_atomic_max(&p.ctl->max_level, mx);
+    }
+    if (lane == 0 && marked) {
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&tc->marked), static_cast<uint64_t>(marked));
     }
 }
 
@@ -1175,11 +1191,17 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
         }
         return;
     }
-    for (long long i = gthread; i < static_cast<long long>(p.g.ntiles) * TS; i += nthreads) {
-        p.plane[0].visited[i] = p.path[i]; // one tree: every passable square was reached
+    if (!tr.mark_bits) { // (else the fix-up has marked the squares itself and measure_body has nothing to look at)
+        for (long long i = gthread; i < static_cast<long long>(p.g.ntiles) * TS; i += nthreads) {
+            p.plane[0].visited[i] = p.path[i]; // one tree: every passable square was reached
+        }
     }
     if (gthread != 0) {
         return;
+    }
+    if (tr.mark_bits) {
+        ctl->measured = 1u;
+        ctl->n_marked = tc->marked;
     }
     for (uint32_t j = 0; j < ctl->n_targets; j++) {
         ctl->target_val[j] = p.plane[0].dist[ctl->target_cell[j]];

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) k_tree_flood(Params p, Tree tr) {
     extern __shared__ __align__(16) uint64_t flood_sm[];
     tree_flood_body(p, tr, lane_id(), flood_sm + static_cast<size_t>(threadIdx.x >> 5) * FLOOD_U64);
 }
-__global__ void __launch_bounds__(256) k_tree_fixup(Params p, Tree tr) { tree_fixup_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
+__global__ void __launch_bounds__(256) k_tree_fixup(Params p, Tree tr, uint16_t *grid) { tree_fixup_body(p, tr, grid, gwarp_id(), nwarps_total(), lane_id()); }
 // the open room (device/room.cuh): the whole distance map in one streaming pass
 __global__ void __launch_bounds__(256) k_room_distance(Params p, uint16_t *grid, Result *res) {
     room_distance_body(p, grid, &res->settled, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
@@ -654,7 +654,8 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     int rc = ensure_tree(h);
     if (rc) return rc;
     cudaStream_t s = h->stream;
-    Tree const tr = h->tree;
+    Tree tr = h->tree;
+    tr.mark_bits = d.game == GAME_DISTANCE ? SQ_MEASURE : 0u;
     Params p = make_params(h, 1);
     CU(cudaMemsetAsync(tr.tc, 0, sizeof(Tree_ctl), s));
     k_tree_count<<<std::min(blocks_for(h, h->g.ntiles, 256), h->sm_count * 8), 256, 0, s>>>(p, tr); // (few warps: seven same-address atomics each)
@@ -699,7 +700,7 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     }
     TRACE("k_tree_jump<parent+prefix>", s);
     mark();
-    k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, tr);
+    k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, tr, h->squares);
     TRACE("k_tree_fixup", s);
     mark();
     if (d.game == GAME_DISTANCE) { // (the solvers paint an open room straight from the closed form: k_paint)
@@ -1472,6 +1473,7 @@ static int band_tree_read(lab_grid *h, Tree_ctl &out) {
 // The band's own list, followed only inside the band's slots ...
 static Tree band_tree_local(lab_grid *h) {
     Tree tr = h->band_tree;
+    tr.mark_bits = SQ_MEASURE; // (the sharded search is the distance map's)
     tr.alist = h->band_alist;
     tr.jump_lo = tr.tile_base * SLOTS;
     tr.jump_hi = tr.jump_lo + static_cast<uint32_t>(h->g.ntiles) * SLOTS;
@@ -1635,7 +1637,7 @@ int lab_band_tree_levels(lab_grid *h, const void *all3, int32_t *used) {
     if (rc) return rc;
     CU(cudaMemcpyAsync(&local.tc->n_arcs, &h->band_crossings, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     k_tree_finish_jump<<<h->sm_count * 2, 256, 0, s>>>(p, local);
-    k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, local);
+    k_tree_fixup<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(p, local, h->squares);
     TRACE("k_tree_fixup", s);
     k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, local);
     TRACE("k_tree_gate", s);

@@ -49,6 +49,7 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
     tr.alist = alist.data();
     tr.tc = &tc;
     tr.nslots = static_cast<uint32_t>(nt * SLOTS);
+    tr.mark_bits = d.game == GAME_DISTANCE ? SQ_MEASURE : 0u;
     simt::launch(nwarps, [&](int wid, int lane) { tree_count_body(p, tr, wid, nwarps, lane); });
     tree_init_body(p, tr);
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
@@ -68,7 +69,7 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
         simt::launch(nwarps, [&](int wid, int lane) { tree_prefix_round_body(tr, static_cast<uint32_t>(r), static_cast<long long>(wid) * 32 + lane, nthreads); });
     }
     simt::launch(nwarps, [&](int wid, int lane) { tree_jump_settle_body(tr, tc.prefix_buf, static_cast<long long>(wid) * 32 + lane, nthreads); });
-    simt::launch(nwarps, [&](int wid, int lane) { tree_fixup_body(p, tr, wid, nwarps, lane); });
+    simt::launch(nwarps, [&](int wid, int lane) { tree_fixup_body(p, tr, w.grid_ptr, wid, nwarps, lane); });
     if (d.game == GAME_DISTANCE) {
         simt::launch(nwarps, [&](int wid, int lane) { room_distance_body(p, w.grid_ptr, &w.res.settled, static_cast<long long>(wid) * 32 + lane, nthreads); });
     }
@@ -361,6 +362,7 @@ int emu_band_tree_bind(void *h, uint32_t tile_base, uint32_t ntiles_global, uint
 
 static Tree emu_band_local(Emu_band *e) {
     Tree tr = e->tr;
+    tr.mark_bits = SQ_MEASURE;
     tr.alist = e->alist;
     tr.jump_lo = tr.tile_base * SLOTS;
     tr.jump_hi = tr.jump_lo + static_cast<uint32_t>(e->w.g.ntiles) * SLOTS;
@@ -489,7 +491,7 @@ int emu_band_tree_levels(void *h, uint32_t const *all3, int32_t *used) {
     emu_band_jump(e, border, 1, e->border_count);
     e->tc.n_arcs = e->crossings;
     simt::launch(nw, [&](int wid, int lane) { tree_finish_jump_body(p, local, static_cast<long long>(wid) * 32 + lane, nthreads); });
-    simt::launch(nw, [&](int wid, int lane) { tree_fixup_body(p, local, wid, nw, lane); });
+    simt::launch(nw, [&](int wid, int lane) { tree_fixup_body(p, local, e->w.grid_ptr, wid, nw, lane); });
     simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, local, static_cast<long long>(wid) * 32 + lane, nthreads); });
     e->tree_last = e->tc;
     *used = static_cast<int32_t>(e->tree_last.used);
