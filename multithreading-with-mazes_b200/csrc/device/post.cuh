@@ -313,7 +313,8 @@ LAB_DEV void paint_body(Params p, uint16_t *grid, Result *res, long long gthread
 // step inside it is four LDS + a vote; only border squares look outside), and nothing is written on the chain --
 // path squares are collected in shared memory and flushed WALK_BATCH at a time with all lanes in flight.
 constexpr int WALK_BATCH = 1024;
-constexpr int WALK_SM_U32 = TS * TS + WALK_BATCH; // per warp: cached levels | collected path squares (flat indices)
+constexpr int WALK_W = TS + 2;                            // the cached tile with a one-square ring around it
+constexpr int WALK_SM_U32 = WALK_W * WALK_W + WALK_BATCH; // per warp: cached levels | collected path squares (flat indices)
 
 LAB_DEV void walk_flush(Geom const &g, uint32_t const *batch, uint32_t nb, unsigned long long base, uint16_t *grid, int32_t *out,
                         unsigned long long max_out, uint32_t repaint_bits, int lane) {
@@ -354,8 +355,7 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
     uint32_t const *dist = p.plane[plane].dist;
     bool const room = p.ctl->room != 0; // (single-field games only: the levels are room_level, no field exists)
     Room const m = room_load(p.ctl);
-    uint32_t *cache = sm, *batch = sm + TS * TS;
-    int cty = -1, ctx = -1; // the cached tile
+    uint32_t *cache = sm, *batch = sm + WALK_W * WALK_W;
     int r = fr, c = fc; // (rows, cols < 2^16: make_geom)
     uint32_t const d0 = room ? room_level(m, static_cast<uint32_t>(r), static_cast<uint32_t>(c)) : dist[static_cast<long long>(r) * g.cols + c];
     uint32_t d = d0;
@@ -366,106 +366,140 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
         return;
     }
     // N, E, S, W (maze/maze.cc:213-218) without a table in local memory: k -> (k odd ? 0 : k - 1, k odd ? 2 - k : 0)
+    bool const voter = lane < 4;
     int const my_dr = (lane & 1) ? 0 : (lane & 3) - 1, my_dc = (lane & 1) ? 2 - (lane & 3) : 0;
-    while (d > 0) {
-        if (!room && !first_only && ((r >> 6) != cty || (c >> 6) != ctx)) {
-            lab_syncwarp(); // (everybody is done with the old tile)
-            cty = r >> 6;
-            ctx = c >> 6;
-            // all 128 loads of a lane are issued before the first is used: the tile costs ONE round trip to memory
-            {
-                uint32_t v[TS * TS / 32];
-                long long const row0 = static_cast<long long>(cty) * TS, col0 = static_cast<long long>(ctx) * TS + lane;
-                uint32_t const *src = dist + row0 * g.cols + col0;
-                bool const in0 = col0 < g.cols, in1 = col0 + 32 < g.cols;
-#pragma unroll
-                for (int k = 0; k < TS * TS / 32; k++) { // entry lane + 32 k: row k / 2, column lane + 32 (k % 2)
-                    bool const ok = row0 + (k >> 1) < g.rows && ((k & 1) ? in1 : in0);
-                    v[k] = ok ? lab_ld_ro(src + static_cast<long long>(k >> 1) * g.cols + 32 * (k & 1)) : INF;
-                }
-#pragma unroll
-                for (int k = 0; k < TS * TS / 32; k++) {
-                    cache[lane + 32 * k] = v[k];
-                }
+    if (room) {
+        // In an open room the canonical path is two straight segments, known without walking: N is tried before E before
+        // S before W, so the walker goes up first if the start is above it, else sideways first if the start is to its
+        // right, else down and then left.  Every lane writes its share of the squares.
+        int const sr = m.sr, sc = m.sc;
+        int const vr = r > sr ? -1 : (r < sr ? 1 : 0), hc = c < sc ? 1 : (c > sc ? -1 : 0);
+        uint32_t const nv = room_absdiff(r, sr), nh = room_absdiff(c, sc);
+        bool const vertical_first = vr < 0 || (vr > 0 && hc <= 0);
+        uint32_t const limit = first_only ? (d0 ? 1u : 0u) : d0;
+        for (uint32_t i = static_cast<uint32_t>(lane); i < limit; i += 32u) { // the (i + 1)-th square after the finish
+            int rr, cc;
+            if (vertical_first) {
+                rr = i < nv ? r + vr * static_cast<int>(i + 1) : sr;
+                cc = i < nv ? c : c + hc * static_cast<int>(i + 1 - nv);
+            } else {
+                rr = i < nh ? r : r + vr * static_cast<int>(i + 1 - nh);
+                cc = i < nh ? c + hc * static_cast<int>(i + 1) : sc;
             }
-            lab_syncwarp();
+            if (out && i < max_out) {
+                out[2 * static_cast<unsigned long long>(i)] = rr;
+                out[2 * static_cast<unsigned long long>(i) + 1] = cc;
+            }
+            if (repaint_bits) {
+                long long const at = static_cast<long long>(rr) * g.cols + cc;
+                grid[at] = static_cast<uint16_t>((grid[at] & ~SQ_PAINT_MASK) | repaint_bits);
+            }
         }
-        // Inside the cached tile, away from its border: an LDS, a vote and a shuffle per step and little else (a single
-        // warp issues one dependent instruction every ~5 cycles, so the step's instruction count IS the walk's speed).
-        if (!room && !first_only) {
-            uint32_t const origin = static_cast<uint32_t>(cty << 6) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(ctx << 6);
-            bool const voter = lane < 4;
-            int const my_off = voter ? my_dr * TS + my_dc : 0; // lanes 0..3 look N, E, S, W of the walker; the others at it
-            int idx = ((r & 63) << 6) | (c & 63);
-            int lr = idx >> 6, lc = idx & 63;
-            uint32_t const room_left = static_cast<uint32_t>(WALK_BATCH) - nb;
-            int budget = static_cast<int>(d < room_left ? d : room_left); // steps before the start is reached / the batch is full
-            bool lost = false;
-            while (budget > 0 && static_cast<unsigned>(lr - 1) < 62u && static_cast<unsigned>(lc - 1) < 62u) {
-                int const cand = idx + my_off;
-                uint32_t const mk = lab_ballot(voter && cache[cand] == d - 1);
-                if (mk == 0) {
-                    lost = true;
-                    break;
+        if (lane == 0) {
+            res->path_len[slot] = d0;
+        }
+        return;
+    }
+    if (first_only) {
+        // A single step (gather's path.front()): the plain step on the field.
+        while (d > 0) {
+            bool hit = false;
+            if (voter) {
+                int const nr = r + my_dr, nc = c + my_dc;
+                if (nr >= 0 && nr < g.rows && nc >= 0 && nc < g.cols) {
+                    hit = dist[static_cast<long long>(nr) * g.cols + nc] == d - 1;
                 }
-                idx = static_cast<int>(lab_shfl(static_cast<uint32_t>(cand), lab_ffs32(mk) - 1)); // first of N, E, S, W one level lower
-                d--;
-                budget--;
-                lr = idx >> 6;
-                lc = idx & 63;
-                if (lane == 0) {
-                    batch[nb] = origin + static_cast<uint32_t>(lr) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(lc);
-                }
-                nb++;
             }
-            r = (cty << 6) + lr;
-            c = (ctx << 6) + lc;
-            if (lost) {
-                break;
+            uint32_t const mk = lab_ballot(hit);
+            if (mk == 0) {
+                break; // cannot happen on a converged field
             }
+            int const k = lab_ffs32(mk) - 1;
+            r += (k & 1) ? 0 : k - 1;
+            c += (k & 1) ? 2 - k : 0;
+            d--;
+            if (lane == 0) {
+                batch[nb] = static_cast<uint32_t>(r) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(c);
+            }
+            nb++;
             if (nb == static_cast<uint32_t>(WALK_BATCH)) {
                 walk_flush(g, batch, nb, flushed, grid, out, max_out, repaint_bits, lane);
                 flushed += nb;
                 nb = 0;
             }
-            if (d == 0) {
+            if (first_only) {
                 break;
             }
         }
-        bool hit = false;
-        if (lane < 4) {
-            int const nr = r + my_dr, nc = c + my_dc;
-            if (nr >= 0 && nr < g.rows && nc >= 0 && nc < g.cols) {
-                uint32_t lv;
-                if (room) {
-                    lv = room_level(m, static_cast<uint32_t>(nr), static_cast<uint32_t>(nc));
-                } else if ((nr >> 6) == cty && (nc >> 6) == ctx) {
-                    lv = cache[((nr & 63) << 6) | (nc & 63)];
-                } else {
-                    lv = dist[static_cast<long long>(nr) * g.cols + nc];
+    } else {
+        // The 64x64 tile under the walker plus a ring of one square, in shared memory: every step taken from a square of
+        // the tile is an LDS, a vote and a shuffle (a single warp issues one dependent instruction every ~5 cycles, so the
+        // step's instruction count IS the walk's speed); stepping onto the ring makes that square's tile the next one.
+        int const my_off = voter ? my_dr * WALK_W + my_dc : 0; // lanes 0..3 look N, E, S, W of the walker; the others at it
+        bool lost = false;
+        while (d > 0 && !lost) {
+            int const cty = r >> 6, ctx = c >> 6;
+            lab_syncwarp(); // (everybody is done with the old tile)
+            {
+                // all loads of a lane are issued before the first is used: the tile costs ONE round trip to memory
+                constexpr int K = TS * TS / 32;
+                uint32_t v[K], h[8];
+                long long const row0 = static_cast<long long>(cty) * TS, col0 = static_cast<long long>(ctx) * TS;
+                uint32_t const *src = dist + row0 * g.cols + col0 + lane;
+                bool const in0 = col0 + lane < g.cols, in1 = col0 + lane + 32 < g.cols;
+#pragma unroll
+                for (int k = 0; k < K; k++) { // entry lane + 32 k of the tile: row k / 2, column lane + 32 (k % 2)
+                    bool const ok = row0 + (k >> 1) < g.rows && ((k & 1) ? in1 : in0);
+                    v[k] = ok ? lab_ld_ro(src + static_cast<long long>(k >> 1) * g.cols + 32 * (k & 1)) : INF;
                 }
-                hit = lv == d - 1;
+                // the ring: rows -1 and 64 (columns lane, lane + 32), columns -1 and 64 (rows lane, lane + 32); corners unused
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    int const q = lane + 32 * (k & 1);
+                    long long const rr = k < 4 ? row0 + ((k & 2) ? TS : -1) : row0 + q;
+                    long long const cc = k < 4 ? col0 + q : col0 + ((k & 2) ? TS : -1);
+                    bool const ok = rr >= 0 && rr < g.rows && cc >= 0 && cc < g.cols;
+                    h[k] = ok ? lab_ld_ro(dist + rr * g.cols + cc) : INF;
+                }
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    cache[((k >> 1) + 1) * WALK_W + 1 + lane + 32 * (k & 1)] = v[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    int const q = lane + 32 * (k & 1);
+                    int const at = k < 4 ? ((k & 2) ? (TS + 1) * WALK_W : 0) + 1 + q : (q + 1) * WALK_W + ((k & 2) ? TS + 1 : 0);
+                    cache[at] = h[k];
+                }
             }
-        }
-        uint32_t const mk = lab_ballot(hit);
-        if (mk == 0) {
-            break; // cannot happen on a converged field
-        }
-        int const k = lab_ffs32(mk) - 1;
-        r += (k & 1) ? 0 : k - 1;
-        c += (k & 1) ? 2 - k : 0;
-        d--;
-        if (lane == 0) {
-            batch[nb] = static_cast<uint32_t>(r) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(c);
-        }
-        nb++;
-        if (nb == static_cast<uint32_t>(WALK_BATCH)) {
-            walk_flush(g, batch, nb, flushed, grid, out, max_out, repaint_bits, lane);
-            flushed += nb;
-            nb = 0;
-        }
-        if (first_only) {
-            break;
+            lab_syncwarp();
+            uint32_t const origin = static_cast<uint32_t>(cty << 6) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(ctx << 6);
+            int lr = r & 63, lc = c & 63;
+            int idx = (lr + 1) * WALK_W + lc + 1;
+            while (d > 0 && static_cast<unsigned>(lr) < 64u && static_cast<unsigned>(lc) < 64u) {
+                int const cand = idx + my_off;
+                uint32_t const mk = lab_ballot(voter && cache[cand] == d - 1);
+                if (mk == 0) {
+                    lost = true; // cannot happen on a converged field
+                    break;
+                }
+                int const k = lab_ffs32(mk) - 1; // first of N, E, S, W one level lower
+                idx = static_cast<int>(lab_shfl(static_cast<uint32_t>(cand), k));
+                lr += (k & 1) ? 0 : k - 1;
+                lc += (k & 1) ? 2 - k : 0;
+                d--;
+                if (lane == 0) { // (the ring's squares too: lr, lc in -1 .. 64; the maze's edge is never on a path)
+                    batch[nb] = origin + static_cast<uint32_t>(lr * g.cols + lc);
+                }
+                nb++;
+                if (nb == static_cast<uint32_t>(WALK_BATCH)) {
+                    walk_flush(g, batch, nb, flushed, grid, out, max_out, repaint_bits, lane);
+                    flushed += nb;
+                    nb = 0;
+                }
+            }
+            r = (cty << 6) + lr;
+            c = (ctx << 6) + lc;
         }
     }
     unsigned long long const n = flushed + nb; // squares walked

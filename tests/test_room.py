@@ -112,6 +112,22 @@ def test_emulated_games_in_a_room(lab, O, emu):
         assert (g == g_ref).all() and (c == c_ref).all() and paths_equal(paths, p_ref)
 
 
+@pytest.mark.parametrize("finish", [(5, 5), (5, 28), (5, 50), (20, 5), (20, 50), (35, 5), (35, 28), (35, 50), (19, 28), (20, 29), (21, 28), (20, 27),
+                                    (1, 1), (39, 55)])
+def test_emulated_room_paths_are_the_canonical_two_segments(lab, O, emu, finish):
+    """In a room the path is written from a closed form (post.cuh walk_body): it must be the oracle's canonical walk
+    (first of N, E, S, W one level lower) for every position of the finish relative to the start."""
+    maze = lab.build_maze("arena", 41, 57, seed=1)
+    start = (20, 28)
+    placed = maze.copy()
+    placed[start] |= lab.START_BIT
+    placed[finish] |= lab.FINISH_BIT
+    g_ref, w_ref, p_ref = O.canon_hunt(placed, start, finish)
+    g, w, _, paths, _ = emu.solver(1, placed, [start], [finish], 2, 1)
+    assert emu.lib.emu_last_tree_used() == ROOM
+    assert (g == g_ref).all() and w == w_ref and paths_equal([paths[0]], [p_ref])
+
+
 # ------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("rows,cols", [(7, 7), (255, 383), (1023, 1025), (2047, 4095)])
