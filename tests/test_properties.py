@@ -1,0 +1,98 @@
+"""Parity at sizes the CPU oracle cannot reach in seconds, through a size-independent property.
+
+A level field L over a maze is THE breadth-first field of painters/distance.cc:129-153 iff
+    L(start) = 0,   L(x) = 1 + min over the passable 4-neighbours y of L(y)   for every other reached square,
+and walls / unreached squares carry no level: following a neighbour one level lower from any square gives a path of
+exactly L(x) steps to the start (so L >= distance), and L(x) <= L(y) + 1 along a shortest path gives L <= distance.
+The check is a handful of torch ops on the device, row block by row block, so it runs at BASELINE's 32767 x 32767 --
+on every road a search can take: spanning-tree pipeline (Kruskal, Wilson), open room (arena), tile wave (grid + cross,
+arena with a pillar).  The Square grid's side effects are checked the same way (measure bit <=> reached)."""
+import numpy as np
+import pytest
+
+INF = 0xFFFFFFFF
+
+
+def check_field(torch, levels, squares, start, lab, block=2048):
+    """levels: int32 CUDA tensor (bit pattern of uint32), squares: int16 CUDA tensor (after the map), start: (r, c)."""
+    rows, cols = levels.shape
+    big = 1 << 40
+    reached_total, max_level = 0, 0
+    for r0 in range(0, rows, block):
+        r1 = min(rows, r0 + block)
+        lo, hi = max(0, r0 - 1), min(rows, r1 + 1)
+        L = levels[lo:hi].to(torch.int64) & 0xFFFFFFFF
+        L = torch.where(L == INF, torch.full_like(L, big), L)
+        # one ring of "no level" around the block, except where the maze really continues (the rows above / below)
+        P = torch.nn.functional.pad(L, (1, 1, 1 if lo == r0 else 0, 1 if hi == r1 else 0), value=big)
+        n = r1 - r0
+        C = P[1 : n + 1, 1:-1]
+        nmin = torch.minimum(torch.minimum(P[0:n, 1:-1], P[2 : n + 2, 1:-1]), torch.minimum(P[1 : n + 1, :-2], P[1 : n + 1, 2:]))
+        sq = squares[r0:r1].to(torch.int32) & 0xFFFF
+        passable = (sq & lab.PATH_BIT) != 0
+        reached = C < big
+        is_start = torch.zeros_like(reached)
+        if r0 <= start[0] < r1:
+            is_start[start[0] - r0, start[1]] = True
+            assert int(C[start[0] - r0, start[1]]) == 0
+        assert bool((reached == (passable | is_start)).all()), "a level on a wall, or a passable square without one"
+        assert bool(torch.where(reached & ~is_start, C == nmin + 1, torch.ones_like(reached)).all()), "not 1 + min of the neighbours"
+        assert bool((((sq & lab.MEASURE_BIT) != 0) == reached).all()), "measure bit != reached"
+        reached_total += int(reached.sum())
+        if bool(reached.any()):
+            max_level = max(max_level, int(C[reached].max()))
+    return reached_total, max_level
+
+
+CASES = [("kruskal", 8191, None, 1), ("wilson", 8191, None, 1), ("arena", 32767, None, 2), ("arena", 8191, "pillar", 0), ("grid", 4095, "cross", 0)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("builder,n,mod,road", CASES)
+def test_gpu_levels_satisfy_the_bfs_equations_at_scale(lab, builder, n, mod, road):
+    import torch
+
+    maze = lab.build_maze(builder, n, n, seed=0xB2000002, mod=None if mod == "pillar" else mod)
+    if mod == "pillar":
+        maze[n // 4, n // 4] &= ~np.uint16(lab.PATH_BIT)
+    start = lab.distance_start(n, n)
+    squares = torch.from_numpy(maze.view(np.int16)).cuda()
+    levels = torch.empty((n, n), dtype=torch.int32, device="cuda")
+    g = lab.Grid.from_device_ptr(n, n, squares.data_ptr(), keepalive=squares)
+    try:
+        g.set_stream(torch.cuda.current_stream().cuda_stream)
+        g.bind_levels(0, levels.data_ptr())
+        res = g.distance_map(start, want_dist=False)
+        assert g.stats()["tree_used"] == road
+        torch.cuda.synchronize()
+        reached, mx = check_field(torch, levels, squares, start, lab)
+        assert reached == res.settled and mx == res.max
+        passable = int(((maze & lab.PATH_BIT) != 0).sum()) + (0 if maze[start] & lab.PATH_BIT else 1)
+        assert reached == passable  # (the reference's builders make connected mazes)
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("builder,mod", [("kruskal", None), ("arena", None), ("grid", "cross")])
+def test_the_checker_itself(lab, O, builder, mod):
+    """CPU: the property accepts the oracle's fields (blocks smaller than the maze: the seams are checked too) and
+    rejects a field with one level off by one, a missing level and a missing measure bit."""
+    import torch
+
+    maze = lab.build_maze(builder, 131, 197, seed=3, mod=mod)
+    g, d, mx, settled = O.distance_map(maze)
+    start = lab.distance_start(131, 197)
+    as_t = lambda a, t: torch.from_numpy(a.view(t).copy())
+    assert check_field(torch, as_t(d, np.int32), as_t(g, np.int16), start, lab, block=50) == (settled, mx)
+    ys, xs = np.nonzero(d != INF)
+    for what in ("level", "hole", "bit"):
+        d2, g2 = d.copy(), g.copy()
+        y, x = ys[len(ys) // 2], xs[len(xs) // 2]
+        if what == "level":
+            d2[y, x] += 1
+        elif what == "hole":
+            d2[y, x] = INF
+        else:
+            g2[y, x] &= ~np.uint16(lab.MEASURE_BIT)
+        with pytest.raises(AssertionError):
+            check_field(torch, as_t(d2, np.int32), as_t(g2, np.int16), start, lab, block=50)
