@@ -96,3 +96,61 @@ def test_the_checker_itself(lab, O, builder, mod):
             g2[y, x] &= ~np.uint16(lab.MEASURE_BIT)
         with pytest.raises(AssertionError):
             check_field(torch, as_t(d2, np.int32), as_t(g2, np.int16), start, lab, block=50)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("builder,n", [("wilson", 8191), ("arena", 16383)])
+def test_gpu_hunt_and_gather_invariants_at_scale(lab, builder, n):
+    """SURVEY App. A.4's schedule-independent invariants of the games, at sizes beyond the oracle: the winner's path is a
+    wall-respecting chain of exactly the BFS length from a neighbour of the finish to the start, repainted in the winner's
+    colour only; every other square carries paint iff it is closer to the start than the finish is; gather: every finish
+    claimed, colour k's paint == cache, and paint iff closer than the finish colour k claims."""
+    import torch
+
+    from _util import valid_shortest_path
+
+    maze = lab.build_maze(builder, n, n, seed=0xB2000005)
+    # levels from the start of the game (a field the test above proves exact at this size)
+    placed, s, f = lab.place_hunt(maze, seed=0xB2000006)
+    with lab.Grid.from_host(placed) as g:
+        d = g.distance_map(tuple(s)).dist
+    D = int(d[f[0], f[1]])
+    with lab.Grid.from_host(placed) as g:
+        res = g.hunt(s, f)
+        after = g.download()
+    assert res.winner == 0 and res.path_len[0] == D
+    path = np.asarray(res.paths[0]).reshape(-1, 2)
+    assert valid_shortest_path(placed, path, s, f, D)
+    assert (d[path[:, 0], path[:, 1]] == np.arange(D - 1, -1, -1)).all()  # one level lower at every step
+    paint = (after & lab.PAINT_MASK) >> 4
+    want = np.where(d < D, 0xF, 0).astype(paint.dtype)
+    want[path[:, 0], path[:, 1]] = 1  # the winner's (colour 0's) bit alone
+    assert (paint == want).all() and ((after & ~np.uint16(lab.PAINT_MASK)) == (placed & ~np.uint16(lab.PAINT_MASK))).all()
+    del after, paint, want
+    # gather
+    placed, s, fin = lab.place_gather(maze, seed=0xB2000007)
+    with lab.Grid.from_host(placed) as g:
+        d = g.distance_map(tuple(s)).dist
+    with lab.Grid.from_host(placed) as g:
+        res = g.gather(s, fin)
+        after = g.download()
+    Dk = sorted(int(d[r, c]) for r, c in fin)
+    assert sorted(int(x) for x in res.claimed_by) == [0, 1, 2, 3]
+    cache = ((after & lab.CACHE_MASK) >> 8).astype(np.int32)
+    paint = ((after & lab.PAINT_MASK) >> 4).astype(np.int32)
+    want = np.zeros_like(cache)
+    for k in range(4):
+        want |= np.where(d < Dk[k], 1 << k, 0)
+    fronts = [np.asarray(p).reshape(-1, 2)[0] for p in res.paths if len(p)]
+    differs = paint != want
+    allowed = np.zeros_like(differs)
+    for fr in fronts:
+        allowed[fr[0], fr[1]] = True  # path.front() is recoloured (bfs_threads.cc:355-364)
+    assert not (differs & ~allowed).any()
+    want_cache = want.copy()
+    for j, (r, c) in enumerate(fin):
+        want_cache[r, c] |= 1 << int(res.claimed_by[j])  # the claim (bfs_threads.cc:158-161)
+    assert (cache == want_cache).all()
+    for k in range(4):
+        j = int(np.nonzero(np.asarray(res.claimed_by) == k)[0][0])
+        assert valid_shortest_path(placed, res.paths[k], s, fin[j], int(d[fin[j][0], fin[j][1]]))
