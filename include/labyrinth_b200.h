@@ -163,6 +163,25 @@ int lab_band_relax(lab_grid *g);
 int lab_band_export_edges(lab_grid *g, void *top_levels_dev, void *bottom_levels_dev);
 int lab_band_import_edges(lab_grid *g, const void *above_bottom_levels_dev, const void *below_top_levels_dev, uint32_t *activated);
 int lab_band_finish(lab_grid *g, uint64_t *local_max, uint64_t *local_settled);
+/* The solvers across row bands (Bfs::hunt / Bfs::gather, solvers/bfs_threads.cc:243-280,333-369, canonical model as on one
+ * GPU), on mazes whose level field the pipeline below or lab_band_room provides (one tree, an open room): compositions of
+ *     lab_band_begin_game     like lab_band_begin; game 1 hunt, 2 gather: passable <=> path_bit, no measure bits
+ *     lab_band_level_at       level of one square of this band (the finishes' levels: the games' thresholds)
+ *     lab_band_paint          the game's paint rules on this band's squares -> squares that received a bit
+ *     lab_band_walk           one piece of a canonical path inside this band, from the finish (include_first = 0) or from
+ *                             the square a walk taken over from the neighbouring band continues at (1), until the start or
+ *                             the band's border; repaint_bits != 0 replaces the paint nibble of its squares (hunt's winner).
+ *                             state = {squares walked, row, col where it stopped, level left (0: at the start)}
+ *     lab_band_recolour       paint nibble of one square := bits (gather's path.front(), bfs_threads.cc:355-364)
+ *     lab_band_finish_game    closes the game
+ * multithreading-with-mazes_b200/bands.py (sharded_hunt, sharded_gather) is the driver. */
+int lab_band_begin_game(lab_grid *g, int game, int src_r_local, int src_c);
+int lab_band_level_at(lab_grid *g, int r, int c, uint32_t *level);
+int lab_band_paint(lab_grid *g, int n_rules, const uint32_t *below, const uint32_t *bits, uint64_t *painted);
+int lab_band_walk(lab_grid *g, int r, int c, int include_first, int first_only, uint32_t repaint_bits, void *path_dev,
+                  uint64_t path_cap, int64_t state[4]);
+int lab_band_recolour(lab_grid *g, int r, int c, uint16_t paint_bits);
+int lab_band_finish_game(lab_grid *g);
 
 /* The spanning-tree pipeline (csrc/device/tree.cuh) across row bands: what replaces the relax / exchange
  * loop above when the maze is one tree (every reference builder without -m), whose diameter would cross the

@@ -174,6 +174,39 @@ class _BandEngine:
         self._check(self._f("tree_count")(self.h, byref(v), byref(e), byref(x), box))
         return (int(v.value), int(e.value), int(x.value)) + tuple(int(b) for b in box)
 
+    # -- the solvers across bands (lab_band_begin_game, _level_at, _paint, _walk, _recolour, _finish_game) --
+    def begin_game(self, game: int, src_local: Optional[Tuple[int, int]]):
+        r, c = src_local if src_local is not None else (-1, -1)
+        self._check(self._f("begin_game")(self.h, c_int(game), c_int(r), c_int(c)))
+
+    def level_at(self, r: int, c: int) -> int:
+        v = c_uint32()
+        self._check(self._f("level_at")(self.h, c_int(r), c_int(c), byref(v)))
+        return int(v.value)
+
+    def paint(self, rules) -> int:
+        """rules: [(below, bits)], at most 4 -> squares of this band that received a bit"""
+        n = len(rules)
+        below = (c_uint32 * 4)(*[r[0] for r in rules] + [0] * (4 - n))
+        bits = (c_uint32 * 4)(*[r[1] for r in rules] + [0] * (4 - n))
+        painted = c_uint64()
+        self._check(self._f("paint")(self.h, c_int(n), below, bits, byref(painted)))
+        return int(painted.value)
+
+    def walk(self, r: int, c: int, include_first: bool, first_only: bool, repaint_bits: int, path_buf=None):
+        """-> (squares walked, row, col where the walk stopped, level left); path_buf: int32 [cap, 2] tensor or None"""
+        state = (ctypes.c_int64 * 4)()
+        cap = int(path_buf.shape[0]) if path_buf is not None else 0
+        self._check(self._f("walk")(self.h, c_int(r), c_int(c), c_int(1 if include_first else 0), c_int(1 if first_only else 0),
+                                    c_uint32(repaint_bits), self._ptr(path_buf), c_uint64(cap), state))
+        return int(state[0]), int(state[1]), int(state[2]), int(state[3])
+
+    def recolour(self, r: int, c: int, paint_bits: int):
+        self._check(self._f("recolour")(self.h, c_int(r), c_int(c), ctypes.c_uint16(paint_bits)))
+
+    def finish_game(self):
+        self._check(self._f("finish_game")(self.h))
+
     def room(self, r0: int, r1: int, c0: int, c1: int, src_r: int, src_c: int):
         self._check(self._f("room")(self.h, c_int(r0), c_int(r1), c_int(c0), c_int(c1), c_int(src_r), c_int(src_c)))
 
@@ -213,6 +246,9 @@ class GpuBandEngine(_BandEngine):
     def _check(self, rc):
         if rc != 0:
             raise self.lab.LabError(rc, self.L.lab_last_error().decode(errors="replace"))
+
+    def or_bits(self, cells, bits):
+        self.grid.or_bits(cells, bits)
 
 
 def _exchange(dist, rank, world, up_payload, down_payload, engine, group):
@@ -362,3 +398,166 @@ def _sharded_tree(engine, start_global, row0, rows_local, group, tr=None) -> boo
     used = engine.tree_levels(b["all3"])
     mark("short prefix + fix-up")
     return used
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# The solvers across row bands (Bfs::hunt, Bfs::gather: solvers/bfs_threads.cc:243-280,333-369; canonical lock-step
+# model), on mazes whose level field needs no wave: one tree (the sharded spanning-tree pipeline) or
+# an open room.  The field is computed exactly as for the distance map; the games are then local passes (paint rules with
+# thresholds every rank knows) plus the canonical paths, which are walked band by band: a walk that reaches its band's
+# border is taken over by the neighbour (one tiny all-gather per hand-over); in a room every band writes its part of the
+# two-segment path at once.
+
+GAME_HUNT, GAME_GATHER = 1, 2
+PAINT_SHIFT, CACHE_SHIFT, PAINT_MASK = 4, 8, 0x00F0
+
+
+def _gather_ints(engine, values, group):
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    t = torch.tensor(values, dtype=torch.int64, device=engine.row_device)
+    out = torch.empty(world * len(values), dtype=torch.int64, device=engine.row_device)
+    _all_gather(dist, out, t, world, group)
+    return [[int(x) for x in row] for row in out.view(world, len(values)).tolist()]
+
+
+def _sharded_field(engine, game, start_global, row0, rows_local, group):
+    """begin + the level field from `start_global`: 'tree' or 'room'.  Anything else is not sharded for the solvers yet."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    sr, sc = start_global
+    tr = _Trace(engine.row_device)
+    engine.begin_game(game, (sr - row0, sc) if row0 <= sr < row0 + rows_local else None)
+    top, bottom = engine.path_rows()
+    above_bottom, below_top = _exchange(dist, rank, world, top, bottom, engine, group)
+    engine.set_neighbour_paths(above_bottom, below_top)
+    road = _sharded_tree(engine, start_global, row0, rows_local, group, tr)
+    if not road:
+        engine.finish_game()
+        raise NotImplementedError("the solvers are sharded on perfect mazes and open rooms only (a general maze needs the bounded wave across bands)")
+    return "tree" if road is True else "room"
+
+
+def _level_of(engine, road, square, start_global, row0, rows_local, group):
+    """BFS level of a global square, known to every rank afterwards (-1: unreachable)."""
+    r, c = square
+    if road == "room":  # (Manhattan distance: the closed form every rank can evaluate)
+        return abs(r - start_global[0]) + abs(c - start_global[1])
+    mine = engine.level_at(r - row0, c) if row0 <= r < row0 + rows_local else -1
+    mine = -1 if mine == INF else mine
+    return max(v[0] for v in _gather_ints(engine, [mine], group))
+
+
+def _walk_path(engine, road, finish, start_global, level, repaint_bits, want_path, row0, rows_local, group):
+    """The canonical path from `finish` (level `level`) to the start: repaints its squares (if repaint_bits) and returns it
+    as an int32 [level, 2] array of global (row, col) pairs, finish side first (None unless want_path)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    dev = engine.row_device
+    full = torch.full((max(level, 1), 2), -1, dtype=torch.int32, device=dev) if want_path else None
+    if level > 0:
+        if road == "room":  # every band writes its own squares of the two segments, at their indices along the path
+            engine.walk(finish[0] - row0, finish[1], False, False, repaint_bits, full)
+            if want_path:
+                full[:, 0] = torch.where(full[:, 0] >= 0, full[:, 0] + row0, full[:, 0])
+        else:
+            piece = torch.empty((level, 2), dtype=torch.int32, device=dev) if want_path else None
+            cur, include_first, done = (finish[0], finish[1]), False, 0
+            for _ in range(level + 2):  # (every hand-over makes progress: at most `level` of them)
+                own = row0 <= cur[0] < row0 + rows_local
+                state = [0, 0, 0, 0, 0]
+                if own:
+                    steps, r, c, left = engine.walk(cur[0] - row0, cur[1], include_first, False, repaint_bits, piece)
+                    state = [1, steps, r + row0, c, left]
+                    if want_path and steps:
+                        full[done : done + steps, 0] = piece[:steps, 0] + row0
+                        full[done : done + steps, 1] = piece[:steps, 1]
+                got = next(v for v in _gather_ints(engine, state, group) if v[0] == 1)
+                _, steps, r, c, left = got
+                done += steps
+                if left <= 0:
+                    break
+                # the walk stopped at its band's border: its next square is across it (one level lower, in the neighbour's band)
+                owner_r0, owner_n = next((a, n) for a, n in engine._tree_layout[1]["split"] if a <= r < a + n)
+                cur = (r - 1, c) if r == owner_r0 else (r + 1, c)
+                if not (r == owner_r0 or r == owner_r0 + owner_n - 1) or steps == 0 and include_first:
+                    raise RuntimeError(f"path walk lost at ({r},{c}) with {left} levels to go")
+                include_first = True
+            else:
+                raise RuntimeError("path walk did not reach the start")
+    if not want_path:
+        return None
+    if world > 1:
+        every = torch.empty((world,) + tuple(full.shape), dtype=torch.int32, device=dev)
+        _all_gather(dist, every.view(-1), full.view(-1), world, group)
+        full = every.max(dim=0).values
+    return full[:level].cpu().numpy()
+
+
+def sharded_hunt(engine, start_global, finish_global, row0: int, rows_local: int, group=None, want_path: bool = True):
+    """Bfs::hunt on this rank's band (the caller placed start_bit / finish_bit).  Collective.
+    -> {"winner", "path_len", "path" (global (row, col) pairs or None), "painted", "road"}"""
+    road = _sharded_field(engine, GAME_HUNT, start_global, row0, rows_local, group)
+    level = _level_of(engine, road, finish_global, start_global, row0, rows_local, group)
+    if level < 0:
+        engine.finish_game()
+        return {"winner": -1, "path_len": 0, "path": None, "painted": 0, "road": road}
+    painted = engine.paint([(level, PAINT_MASK)])
+    path = _walk_path(engine, road, finish_global, start_global, level, 1 << PAINT_SHIFT, want_path, row0, rows_local, group)
+    engine.finish_game()
+    painted = sum(v[0] for v in _gather_ints(engine, [painted], group))
+    return {"winner": 0, "path_len": level, "path": path, "painted": painted, "road": road}
+
+
+def sharded_gather(engine, start_global, finishes_global, row0: int, rows_local: int, group=None, want_paths: bool = True):
+    """Bfs::gather on this rank's band.  Collective.  -> {"claimed_by" (colour per finish), "path_len", "paths", "painted", "road"}"""
+    road = _sharded_field(engine, GAME_GATHER, start_global, row0, rows_local, group)
+    fins = [tuple(int(x) for x in f) for f in finishes_global]
+    levels = [_level_of(engine, road, f, start_global, row0, rows_local, group) for f in fins]
+    big = 1 << 40
+    order = sorted(range(4), key=lambda j: (levels[j] if levels[j] >= 0 else big, fins[j][0], fins[j][1]))  # colour k claims order[k]
+    rules = [(levels[order[k]] if levels[order[k]] >= 0 else INF, ((1 << k) << PAINT_SHIFT) | ((1 << k) << CACHE_SHIFT)) for k in range(4)]
+    painted = engine.paint(rules)
+    claimed_by = [-1] * 4
+    here = lambda sq: row0 <= sq[0] < row0 + rows_local
+    for k in range(4):  # the claims (bfs_threads.cc:158-161) ...
+        j = order[k]
+        if levels[j] >= 0:
+            claimed_by[j] = k
+            if here(fins[j]):
+                engine.or_bits([(fins[j][0] - row0, fins[j][1])], [(1 << k) << CACHE_SHIFT])
+    for k in range(4):  # ... then path.front() of every colour, in colour order (:355-364)
+        j = order[k]
+        if levels[j] <= 0:
+            continue
+        fr, fc = fins[j]
+        if road == "room":  # first of N, E, S, W that is one level lower
+            sr, sc = start_global
+            front = (fr - 1, fc) if fr > sr else (fr, fc + 1) if fc < sc else (fr + 1, fc) if fr < sr else (fr, fc - 1)
+        else:
+            state = [0, 0, 0, 0]
+            if here(fins[j]):
+                steps, r, c, left = engine.walk(fr - row0, fc, False, True, 0, None)
+                if left == levels[j]:  # no step inside the band: the front square is across the border
+                    r = r - 1 if fr == row0 else r + 1
+                state = [1, r + row0, c, 0]
+            got = next(v for v in _gather_ints(engine, state, group) if v[0] == 1)
+            front = (got[1], got[2])
+        if here(front):
+            engine.recolour(front[0] - row0, front[1], (1 << k) << PAINT_SHIFT)
+    paths, path_len = [None] * 4, [0] * 4
+    for k in range(4):
+        j = order[k]
+        if levels[j] >= 0:
+            path_len[k] = levels[j]
+            if want_paths:
+                paths[k] = _walk_path(engine, road, fins[j], start_global, levels[j], 0, True, row0, rows_local, group)
+    engine.finish_game()
+    painted = sum(v[0] for v in _gather_ints(engine, [painted], group))
+    return {"claimed_by": claimed_by, "path_len": path_len, "paths": paths, "painted": painted, "road": road}

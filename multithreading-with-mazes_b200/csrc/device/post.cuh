@@ -36,6 +36,10 @@ struct Result {
     uint32_t n_rules;
     uint32_t pad;
     Paint_rule rule[4];
+    // where walk `slot` stopped, and the level it still had to go (0: it reached the start).  Row bands: a walk that
+    // runs out of its band stops at the band's border with walk_left > 0 and goes on in the neighbouring band.
+    int32_t walk_r[4], walk_c[4];
+    uint32_t walk_left[4];
 };
 
 // Host-filled description of one search.
@@ -348,21 +352,28 @@ LAB_DEV void walk_flush(Geom const &g, uint32_t const *batch, uint32_t nb, unsig
     lab_syncwarp();
 }
 
+// include_first: (fr, fc) is itself a square of the path (a walk taken over from the neighbouring band), not the finish.
 LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int32_t *out,
                        unsigned long long max_out, uint32_t repaint_bits, int first_only, Result *res, int slot,
-                       int lane, uint32_t *sm) {
+                       int lane, uint32_t *sm, int include_first = 0) {
     Geom const &g = p.g;
     uint32_t const *dist = p.plane[plane].dist;
     bool const room = p.ctl->room != 0; // (single-field games only: the levels are room_level, no field exists)
     Room const m = room_load(p.ctl);
     uint32_t *cache = sm, *batch = sm + WALK_W * WALK_W;
     int r = fr, c = fc; // (rows, cols < 2^16: make_geom)
-    uint32_t const d0 = room ? room_level(m, static_cast<uint32_t>(r), static_cast<uint32_t>(c)) : dist[static_cast<long long>(r) * g.cols + c];
+    // (in a room the finish may lie in another band, outside this one's rows: the closed form does not care)
+    uint32_t const d0 = room ? room_absdiff(r, m.sr) + room_absdiff(c, m.sc) : dist[static_cast<long long>(r) * g.cols + c];
     uint32_t d = d0;
     unsigned long long flushed = 0;
     uint32_t nb = 0;
     if (d == INF) {
-        if (lane == 0) res->path_len[slot] = 0;
+        if (lane == 0) {
+            res->path_len[slot] = 0;
+            res->walk_r[slot] = r;
+            res->walk_c[slot] = c;
+            res->walk_left[slot] = INF;
+        }
         return;
     }
     // N, E, S, W (maze/maze.cc:213-218) without a table in local memory: k -> (k odd ? 0 : k - 1, k odd ? 2 - k : 0)
@@ -386,6 +397,9 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
                 rr = i < nh ? r : r + vr * static_cast<int>(i + 1 - nh);
                 cc = i < nh ? c + hc * static_cast<int>(i + 1) : sc;
             }
+            if (rr < 0 || rr >= g.rows) {
+                continue; // (row bands: another band's part of the path)
+            }
             if (out && i < max_out) {
                 out[2 * static_cast<unsigned long long>(i)] = rr;
                 out[2 * static_cast<unsigned long long>(i) + 1] = cc;
@@ -397,8 +411,17 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
         }
         if (lane == 0) {
             res->path_len[slot] = d0;
+            res->walk_r[slot] = sr;
+            res->walk_c[slot] = sc;
+            res->walk_left[slot] = 0;
         }
         return;
+    }
+    if (include_first) {
+        if (lane == 0) {
+            batch[0] = static_cast<uint32_t>(r) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(c);
+        }
+        nb = 1;
     }
     if (first_only) {
         // A single step (gather's path.front()): the plain step on the field.
@@ -506,6 +529,9 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
     walk_flush(g, batch, nb, flushed, grid, out, max_out, repaint_bits, lane);
     if (lane == 0) {
         res->path_len[slot] = first_only ? static_cast<unsigned long long>(d0) : n;
+        res->walk_r[slot] = r;
+        res->walk_c[slot] = c;
+        res->walk_left[slot] = d;
     }
 }
 

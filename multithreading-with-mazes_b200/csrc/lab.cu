@@ -283,6 +283,13 @@ __global__ void k_walk(Params p, int game, uint16_t *grid, Result *res, int32_t 
               max_out, repaint, first_only, res, slot, lane_id(), sm);
 }
 
+__global__ void k_band_walk(Params p, int r, int c, uint16_t *grid, int32_t *out, unsigned long long max_out, uint32_t repaint, int first_only,
+                            int include_first, Result *res) {
+    __shared__ uint32_t sm[WALK_SM_U32];
+    walk_body(p, 0, r, c, grid, out, max_out, repaint, first_only, res, 0, lane_id(), sm, include_first);
+}
+__global__ void k_recolour(uint16_t *square, uint16_t paint_bits) { *square = static_cast<uint16_t>((*square & ~SQ_PAINT_MASK) | paint_bits); }
+
 __global__ void k_gather_fixup(Geom g, uint16_t *grid, Result const *res, int32_t const *finish_rc,
                                int32_t const *front_rc) {
     gather_fixup_body(g, grid, res, finish_rc, front_rc);
@@ -1302,15 +1309,20 @@ int lab_bfs_corners(lab_grid *h, const lab_point starts[4], lab_point finish, in
 // ---- row bands -------------------------------------------------------------------------------
 int lab_band_cols_padded(const lab_grid *h) { return h ? h->g.tiles_x * TS : 0; }
 
-int lab_band_begin(lab_grid *h, int src_r, int src_c) {
+int lab_band_begin(lab_grid *h, int src_r, int src_c) { return lab_band_begin_game(h, GAME_DISTANCE, src_r, src_c); }
+
+int lab_band_begin_game(lab_grid *h, int game, int src_r, int src_c) {
     if (!h) {
         return fail(LAB_ERR_ARG, "null grid");
+    }
+    if (game != GAME_DISTANCE && game != GAME_HUNT && game != GAME_GATHER) {
+        return fail(LAB_ERR_ARG, "sharded game %d (0 distance, 1 hunt, 2 gather)", game);
     }
     if (src_r >= 0 && !in_grid(h, {src_r, src_c})) {
         return fail(LAB_ERR_ARG, "source (%d,%d) outside the band", src_r, src_c);
     }
     Run_desc d{};
-    d.game = GAME_DISTANCE;
+    d.game = game;
     d.nplanes = 1;
     for (int k = 0; k < MAX_PLANES; k++) {
         d.src_r[k] = d.src_c[k] = -1;
@@ -1329,7 +1341,8 @@ int lab_band_begin(lab_grid *h, int src_r, int src_c) {
     h->band_mode = true;
     h->tree_last = Tree_ctl{};
     h->tree_tried = false;
-    int const rc = search_prepare(h, d, SQ_PATH | SQ_MEASURE, SQ_PATH);
+    // passable: the distance map skips measured squares (distance.cc:145-148), the solvers look at path_bit alone
+    int const rc = game == GAME_DISTANCE ? search_prepare(h, d, SQ_PATH | SQ_MEASURE, SQ_PATH) : search_prepare(h, d, SQ_PATH, SQ_PATH);
     h->band_open = rc == LAB_OK;
     return rc;
 }
@@ -1473,7 +1486,7 @@ static int band_tree_read(lab_grid *h, Tree_ctl &out) {
 // The band's own list, followed only inside the band's slots ...
 static Tree band_tree_local(lab_grid *h) {
     Tree tr = h->band_tree;
-    tr.mark_bits = SQ_MEASURE; // (the sharded search is the distance map's)
+    tr.mark_bits = h->band_desc.game == GAME_DISTANCE ? SQ_MEASURE : 0u; // (only the distance map measures)
     tr.alist = h->band_alist;
     tr.jump_lo = tr.tile_base * SLOTS;
     tr.jump_hi = tr.jump_lo + static_cast<uint32_t>(h->g.ntiles) * SLOTS;
@@ -1548,8 +1561,10 @@ int lab_band_room(lab_grid *h, int r0, int r1, int c0, int c1, int src_r, int sr
     Tree const tr = h->band_tree;
     Params p = make_params(h, 1);
     k_room_set<<<1, 1, 0, s>>>(h->ctl, r0, r1, c0, c1, src_r, src_c);
-    k_room_distance<<<h->sm_count * 8, 256, 0, s>>>(p, h->squares, h->res);
-    TRACE("k_room_distance", s);
+    if (h->band_desc.game == GAME_DISTANCE) { // (the solvers paint and walk from the closed form: no field, no measure bits)
+        k_room_distance<<<h->sm_count * 8, 256, 0, s>>>(p, h->squares, h->res);
+        TRACE("k_room_distance", s);
+    }
     k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, tr);
     TRACE("k_tree_gate", s);
     h->launches += 3;
@@ -1647,6 +1662,87 @@ int lab_band_tree_levels(lab_grid *h, const void *all3, int32_t *used) {
     if (rc) return rc;
     if (used) *used = static_cast<int32_t>(h->tree_last.used);
     return LAB_OK;
+}
+
+// ---- the solvers across row bands: compositions of the pieces below, driven by bands.py (sharded_hunt / sharded_gather).
+// The level field is the sharded spanning-tree pipeline's or the open room's (begin with lab_band_begin_game).
+int lab_band_level_at(lab_grid *h, int r, int c, uint32_t *level) {
+    if (!h || !h->band_open || !level || !in_grid(h, {r, c})) {
+        return fail(LAB_ERR_ARG, "lab_band_level_at: bad arguments");
+    }
+    CU(cudaMemcpyAsync(level, h->plane[0].dist + static_cast<size_t>(r) * h->g.cols + c, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LAB_OK;
+}
+
+// Paint rules (post.cuh Paint_rule, plane 0): OR bits[k] into the band's squares whose level is below below[k].
+int lab_band_paint(lab_grid *h, int n_rules, const uint32_t *below, const uint32_t *bits, uint64_t *painted) {
+    if (!h || !h->band_open || n_rules < 1 || n_rules > 4 || !below || !bits) {
+        return fail(LAB_ERR_ARG, "lab_band_paint: bad arguments");
+    }
+    cudaStream_t s = h->stream;
+    Result r{};
+    r.winner = -1;
+    r.n_rules = static_cast<uint32_t>(n_rules);
+    for (int k = 0; k < n_rules; k++) {
+        r.rule[k] = {0u, below[k], bits[k], 0u};
+    }
+    CU(cudaMemcpyAsync(h->res, &r, sizeof r, cudaMemcpyHostToDevice, s));
+    Params p = make_params(h, 1);
+    k_paint<<<grid_blocks(h), 256, 0, s>>>(p, h->squares, h->res);
+    TRACE("k_paint", s);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&r, h->res, sizeof r, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (painted) *painted = r.settled;
+    return LAB_OK;
+}
+
+// One piece of a canonical path inside this band: from (r, c) -- the finish (include_first = 0) or the square a walk
+// taken over from the neighbouring band continues at (1) -- towards the start, until the start or the band's border.
+// path_dev: NULL or room for path_cap (row, col) pairs (band rows), written from index 0 (in an open room: from the
+// square's index along the whole path, other bands' squares left alone).  state: {steps, row, col, level left}.
+int lab_band_walk(lab_grid *h, int r, int c, int include_first, int first_only, uint32_t repaint_bits, void *path_dev, uint64_t path_cap,
+                  int64_t state[4]) {
+    if (!h || !h->band_open || !state) {
+        return fail(LAB_ERR_ARG, "lab_band_walk: bad arguments");
+    }
+    cudaStream_t s = h->stream;
+    Params p = make_params(h, 1);
+    k_band_walk<<<1, 32, 0, s>>>(p, r, c, h->squares, static_cast<int32_t *>(path_dev), path_cap, repaint_bits, first_only, include_first, h->res);
+    TRACE("k_band_walk", s);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    Result res{};
+    CU(cudaMemcpyAsync(&res, h->res, sizeof res, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    state[0] = static_cast<int64_t>(res.path_len[0]);
+    state[1] = res.walk_r[0];
+    state[2] = res.walk_c[0];
+    state[3] = res.walk_left[0] == INF ? -1 : static_cast<int64_t>(res.walk_left[0]);
+    return LAB_OK;
+}
+
+// gather's path.front() recolour (bfs_threads.cc:355-364) of one square of this band: paint nibble := bits
+int lab_band_recolour(lab_grid *h, int r, int c, uint16_t paint_bits) {
+    if (!h || !h->band_open || !in_grid(h, {r, c})) {
+        return fail(LAB_ERR_ARG, "lab_band_recolour: bad arguments");
+    }
+    k_recolour<<<1, 1, 0, h->stream>>>(h->squares + static_cast<size_t>(r) * h->g.cols + c, paint_bits);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+// closes a sharded game (the distance map closes with lab_band_finish): statistics, errors
+int lab_band_finish_game(lab_grid *h) {
+    if (!h || !h->band_open) {
+        return fail(LAB_ERR_ARG, "no band search open");
+    }
+    CU(cudaEventRecord(h->ev[EV_POST0], h->stream));
+    h->band_open = false;
+    return finish_run(h);
 }
 
 uint64_t lab_last_painted(const lab_grid *h) { return h ? h->last.settled : 0; }

@@ -127,6 +127,10 @@ def emu_band_engine(squares: np.ndarray, nwarps: int = 4, sched: int = 0):
             ptr = self.L.emu_band_levels(self.h)
             return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(self.rows, self.cols)).copy()
 
+        def or_bits(self, cells, bits):
+            for (r, c), b in zip(cells, bits):
+                self.sq[r, c] |= np.uint16(b)
+
         def tree_used(self):
             return int(self.L.emu_band_tree_used(self.h))
 

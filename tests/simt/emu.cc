@@ -236,12 +236,15 @@ int emu_band_cols_padded(void *h) { return static_cast<Emu_band *>(h)->w.g.tiles
 uint32_t *emu_band_levels(void *h) { return static_cast<Emu_band *>(h)->w.dist[0].data(); }
 int emu_band_tree_used(void *h) { return static_cast<int>(static_cast<Emu_band *>(h)->tree_last.used); }
 
-int emu_band_begin(void *h, int src_r, int src_c) {
+int emu_band_begin_game(void *h, int game, int src_r, int src_c);
+int emu_band_begin(void *h, int src_r, int src_c) { return emu_band_begin_game(h, GAME_DISTANCE, src_r, src_c); }
+
+int emu_band_begin_game(void *h, int game, int src_r, int src_c) {
     auto *e = static_cast<Emu_band *>(h);
     Workspace &w = e->w;
     Geom const &g = w.g;
     fill_desc(e->d);
-    e->d.game = GAME_DISTANCE;
+    e->d.game = game;
     e->d.nplanes = 1;
     if (src_r >= 0) {
         e->d.src_r[0] = src_r;
@@ -264,9 +267,59 @@ int emu_band_begin(void *h, int src_r, int src_c) {
     e->ghost_s.assign(g.tiles_x, 0);
     e->tree_last = Tree_ctl{};
     int const nw = e->nwarps;
-    simt::launch(nw, [&](int wid, int lane) { pack_body(g, w.grid_ptr, w.path.data(), SQ_PATH | SQ_MEASURE, SQ_PATH, wid, nw, lane); });
+    uint16_t const mask = game == GAME_DISTANCE ? (SQ_PATH | SQ_MEASURE) : SQ_PATH;
+    simt::launch(nw, [&](int wid, int lane) { pack_body(g, w.grid_ptr, w.path.data(), mask, SQ_PATH, wid, nw, lane); });
     force_sources_body(g, w.path.data(), e->d);
     return 0;
+}
+
+int emu_band_level_at(void *h, int r, int c, uint32_t *level) {
+    auto *e = static_cast<Emu_band *>(h);
+    *level = e->w.dist[0][static_cast<size_t>(r) * e->w.g.cols + c];
+    return 0;
+}
+
+int emu_band_paint(void *h, int n_rules, uint32_t const *below, uint32_t const *bits, uint64_t *painted) {
+    auto *e = static_cast<Emu_band *>(h);
+    Workspace &w = e->w;
+    Params p = make_params(w, 1);
+    int const nw = e->nwarps;
+    long long const nthreads = static_cast<long long>(nw) * 32;
+    w.res = Result{};
+    w.res.winner = -1;
+    w.res.n_rules = static_cast<uint32_t>(n_rules);
+    for (int k = 0; k < n_rules; k++) w.res.rule[k] = {0u, below[k], bits[k], 0u};
+    simt::launch(nw, [&](int wid, int lane) { paint_body(p, w.grid_ptr, &w.res, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    *painted = w.res.settled;
+    return 0;
+}
+
+int emu_band_walk(void *h, int r, int c, int include_first, int first_only, uint32_t repaint_bits, int32_t *path, uint64_t path_cap,
+                  int64_t *state) {
+    auto *e = static_cast<Emu_band *>(h);
+    Workspace &w = e->w;
+    Params p = make_params(w, 1);
+    std::vector<uint32_t> wsm(WALK_SM_U32);
+    simt::launch(1, [&](int, int lane) {
+        walk_body(p, 0, r, c, w.grid_ptr, path, path_cap, repaint_bits, first_only, &w.res, 0, lane, wsm.data(), include_first);
+    });
+    state[0] = static_cast<int64_t>(w.res.path_len[0]);
+    state[1] = w.res.walk_r[0];
+    state[2] = w.res.walk_c[0];
+    state[3] = w.res.walk_left[0] == INF ? -1 : static_cast<int64_t>(w.res.walk_left[0]);
+    return 0;
+}
+
+int emu_band_recolour(void *h, int r, int c, uint16_t paint_bits) {
+    auto *e = static_cast<Emu_band *>(h);
+    uint16_t &sq = e->w.grid_ptr[static_cast<size_t>(r) * e->w.g.cols + c];
+    sq = static_cast<uint16_t>((sq & ~SQ_PAINT_MASK) | paint_bits);
+    return 0;
+}
+
+int emu_band_finish_game(void *h) {
+    auto *e = static_cast<Emu_band *>(h);
+    return e->w.ctl.pending != 0 ? -200 : 0;
 }
 
 int emu_band_path_rows(void *h, uint8_t *top, uint8_t *bottom) {
@@ -362,7 +415,7 @@ int emu_band_tree_bind(void *h, uint32_t tile_base, uint32_t ntiles_global, uint
 
 static Tree emu_band_local(Emu_band *e) {
     Tree tr = e->tr;
-    tr.mark_bits = SQ_MEASURE;
+    tr.mark_bits = e->d.game == GAME_DISTANCE ? SQ_MEASURE : 0u;
     tr.alist = e->alist;
     tr.jump_lo = tr.tile_base * SLOTS;
     tr.jump_hi = tr.jump_lo + static_cast<uint32_t>(e->w.g.ntiles) * SLOTS;
@@ -428,7 +481,9 @@ int emu_band_room(void *h, int r0, int r1, int c0, int c1, int src_r, int src_c)
     long long const nthreads = static_cast<long long>(nw) * 32;
     Tree const tr = e->tr;
     room_set_body(&e->w.ctl, r0, r1, c0, c1, src_r, src_c);
-    simt::launch(nw, [&](int wid, int lane) { room_distance_body(p, e->w.grid_ptr, &e->w.res.settled, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    if (e->d.game == GAME_DISTANCE) {
+        simt::launch(nw, [&](int wid, int lane) { room_distance_body(p, e->w.grid_ptr, &e->w.res.settled, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    }
     simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, tr, static_cast<long long>(wid) * 32 + lane, nthreads); });
     e->tree_last = e->tc;
     return 0;

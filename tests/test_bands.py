@@ -208,6 +208,71 @@ def test_sharded_open_room_on_gloo(lab, O, tmp_path):
         _check_bands(tmp_path, 3, maze, O, road)
 
 
+def _gloo_game_worker(rank, world, port, maze_path, out_dir, game, spec):
+    """A sharded game (bands.sharded_hunt / sharded_gather) with the product's kernel bodies on the emulator."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    import __graft_entry__ as graft
+    from _util import emu_band_engine
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    graft.load_package()
+    from mazes_b200 import bands
+
+    maze = np.load(maze_path)
+    r0, n = bands.split_rows(maze.shape[0], world)[rank]
+    eng = emu_band_engine(maze[r0 : r0 + n].copy(), nwarps=3, sched=rank + 1)
+    if game == "hunt":
+        res = bands.sharded_hunt(eng, spec["start"], spec["finish"], r0, n)
+        extra = dict(winner=res["winner"], path=res["path"], path_len=res["path_len"])
+    else:
+        res = bands.sharded_gather(eng, spec["start"], spec["finishes"], r0, n)
+        extra = dict(claimed_by=np.asarray(res["claimed_by"]), path_len=np.asarray(res["path_len"]),
+                     **{f"path{k}": (res["paths"][k] if res["paths"][k] is not None else np.zeros((0, 2), np.int32)) for k in range(4)})
+    np.savez(os.path.join(out_dir, f"band{rank}.npz"), sq=eng.sq, r0=r0, road=res["road"], painted=res["painted"], **extra)
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("builder,rows,cols,world,road", [("kruskal", 255, 131, 2, "tree"), ("wilson", 193, 197, 3, "tree"), ("arena", 193, 131, 3, "room")])
+def test_sharded_hunt_and_gather_on_gloo(lab, O, tmp_path, builder, rows, cols, world, road):
+    """Bfs::hunt and Bfs::gather across 2-3 bands (one tree / an open room): grids, winner, claims and the canonical paths
+    -- walked band by band, handed over at the borders -- equal the single-maze canonical model's."""
+    import torch.multiprocessing as mp
+
+    maze = lab.build_maze(builder, rows, cols, seed=41)
+    for i, seed in enumerate((7, 8)):
+        # hunt
+        placed, s, f = lab.place_hunt(maze, seed=seed)
+        path = str(tmp_path / "maze.npy")
+        np.save(path, placed)
+        spec = {"start": tuple(int(x) for x in s), "finish": tuple(int(x) for x in f)}
+        mp.spawn(_gloo_game_worker, args=(world, 37500 + (os.getpid() % 2000) + 2 * i, path, str(tmp_path), "hunt", spec), nprocs=world, join=True)
+        g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
+        z = [np.load(tmp_path / f"band{r}.npz") for r in range(world)]
+        assert all(str(b["road"]) == road for b in z)
+        assert (np.concatenate([b["sq"] for b in z]) == g_ref).all()
+        for b in z:
+            assert int(b["winner"]) == w_ref and (b["path"] == np.asarray(p_ref)).all() and int(b["path_len"]) == len(p_ref)
+        assert int(z[0]["painted"]) == int(((g_ref & 0x00F0) != 0).sum())
+        # gather
+        placed, s, fin = lab.place_gather(maze, seed=seed + 20)
+        np.save(path, placed)
+        spec = {"start": tuple(int(x) for x in s), "finishes": [tuple(int(x) for x in q) for q in fin]}
+        mp.spawn(_gloo_game_worker, args=(world, 37501 + (os.getpid() % 2000) + 2 * i, path, str(tmp_path), "gather", spec), nprocs=world, join=True)
+        g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
+        z = [np.load(tmp_path / f"band{r}.npz") for r in range(world)]
+        got = np.concatenate([b["sq"] for b in z])
+        assert (got == g_ref).all(), int((got != g_ref).sum())
+        for b in z:
+            assert (b["claimed_by"] == c_ref).all()
+            for k in range(4):
+                assert (b[f"path{k}"] == np.asarray(p_ref[k]).reshape(-1, 2)).all()
+
+
 def test_split_rows(lab):
     from mazes_b200 import bands
 
@@ -402,3 +467,38 @@ def test_band_room_one_process(lab, O, rows, cols, nb, start):
     got_g = np.concatenate([s.cpu().numpy().view(np.uint16) for s in sq])
     assert (got_d == d_ref).all() and (((got_g & lab.MEASURE_BIT) != 0) == reached).all()
     assert max(r[0] for r in res) == int(d_ref[reached].max()) and sum(r[1] for r in res) == int(reached.sum())
+
+
+@pytest.mark.gpu
+def test_gpu_sharded_games_single_rank(lab, O):
+    """bands.sharded_hunt / sharded_gather with the CUDA band engine as a one-rank job (the lab_band_begin_game, _level_at,
+    _paint, _walk, _recolour entry points; hand-overs between ranks are covered by the gloo tests on the same kernel bodies
+    and by tools/run_bands.py --game ... --check over NCCL)."""
+    import torch
+    import torch.distributed as dist
+
+    from mazes_b200 import bands
+
+    created = not dist.is_initialized()
+    if created:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(39500 + os.getpid() % 2000))
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        for builder, rows, cols in [("kruskal", 511, 767), ("arena", 383, 1025), ("rdfs", 257, 259)]:
+            maze = lab.build_maze(builder, rows, cols, seed=5)
+            placed, s, f = lab.place_hunt(maze, seed=11)
+            sq = torch.from_numpy(placed.view(np.int16).copy()).cuda()
+            eng = bands.GpuBandEngine(lab, sq)
+            res = bands.sharded_hunt(eng, tuple(int(x) for x in s), tuple(int(x) for x in f), 0, rows)
+            g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
+            assert (sq.cpu().numpy().view(np.uint16) == g_ref).all() and res["winner"] == w_ref and (res["path"] == np.asarray(p_ref)).all()
+            placed, s, fin = lab.place_gather(maze, seed=12)
+            sq = torch.from_numpy(placed.view(np.int16).copy()).cuda()
+            eng = bands.GpuBandEngine(lab, sq)
+            res = bands.sharded_gather(eng, tuple(int(x) for x in s), [tuple(int(x) for x in q) for q in fin], 0, rows)
+            g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
+            assert (sq.cpu().numpy().view(np.uint16) == g_ref).all() and (np.asarray(res["claimed_by"]) == c_ref).all()
+            assert all((res["paths"][k] == np.asarray(p_ref[k]).reshape(-1, 2)).all() for k in range(4))
+    finally:
+        if created:
+            dist.destroy_process_group()

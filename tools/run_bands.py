@@ -11,6 +11,7 @@ import __graft_entry__ as graft
 ap = argparse.ArgumentParser()
 ap.add_argument("--builder", default="kruskal"); ap.add_argument("--rows", type=int, default=4095); ap.add_argument("--cols", type=int, default=4095)
 ap.add_argument("--check", action="store_true"); ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--game", default="distance", choices=["distance", "hunt", "gather"])
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -18,6 +19,39 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 lab = graft.load_package()
 from mazes_b200 import bands
 maze = lab.build_maze(a.builder, a.rows, a.cols, seed=0xB2000005)
+if a.game != "distance":
+    # the sharded solvers: place the game on the host as the reference does, run it band by band, compare with the oracle
+    if a.game == "hunt":
+        placed, s, f = lab.place_hunt(maze, seed=0xB2000006)
+    else:
+        placed, s, f = lab.place_gather(maze, seed=0xB2000007)
+    r0, n = bands.split_rows(a.rows, world)[rank]
+    for rep in range(a.reps):
+        sq = torch.from_numpy(placed[r0:r0 + n].view(np.int16).copy()).cuda()
+        eng = bands.GpuBandEngine(lab, sq)
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        if a.game == "hunt":
+            res = bands.sharded_hunt(eng, tuple(int(x) for x in s), tuple(int(x) for x in f), r0, n)
+        else:
+            res = bands.sharded_gather(eng, tuple(int(x) for x in s), [tuple(int(x) for x in q) for q in f], r0, n)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"game": a.game, "builder": a.builder, "rows": a.rows, "cols": a.cols, "world": world, "rep": rep,
+                              "wall_ms": round(float(t.item()) * 1e3, 3), "path_len": res["path_len"], "painted": res["painted"], "road": res["road"]}), flush=True)
+    if a.check:
+        O = graft.load_oracle()
+        if a.game == "hunt":
+            g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
+            ok = bool((sq.cpu().numpy().view(np.uint16) == g_ref[r0:r0 + n]).all() and res["winner"] == w_ref and (res["path"] == np.asarray(p_ref)).all())
+        else:
+            g_ref, c_ref, p_ref = O.canon_gather(placed, s, f)
+            ok = bool((sq.cpu().numpy().view(np.uint16) == g_ref[r0:r0 + n]).all() and (np.asarray(res["claimed_by"]) == c_ref).all()
+                      and all((res["paths"][k] == np.asarray(p_ref[k]).reshape(-1, 2)).all() for k in range(4)))
+        print(f"rank {rank}: band rows [{r0},{r0 + n}) {'OK' if ok else 'MISMATCH'}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0)
 r0, n = bands.split_rows(a.rows, world)[rank]
 pristine = torch.from_numpy(maze[r0:r0 + n].view(np.int16).copy()).cuda()
 sq = torch.empty_like(pristine)
