@@ -38,7 +38,7 @@ def test_emulated_random_cases(lab, O):
 @pytest.mark.gpu
 def test_gpu_random_cases(lab, O):
     rng = np.random.default_rng(4052)
-    for it in range(40):
+    for it in range(120):
         b, mod, maze = random_case(lab, rng, 330)
         tag = (it, b, mod, maze.shape)
         g_ref, d_ref, mx_ref, st_ref = O.distance_map(maze)
