@@ -194,7 +194,8 @@ int lab_band_finish_game(lab_grid *g);
  * pass adds the two.  Three all-gathers per map, whatever its diameter; the ranks agree on "one tree or not"
  * through the flags in the chunks, without a host round trip.
  *     lab_band_tree_bind      the caller's device arrays, indexed by slot = global tile * 256 + side * 64 + position
- *                             (global tile = tile_base + the band's tile): succ0, s0, s1, r0, r1: uint32[ntiles_global*256+2];
+ *                             (global tile = tile_base + the band's tile): succ0: uint32[ntiles_global*256+2]; sr0, sr1: the
+ *                             two ping-pong lists of (pointer, value) pairs, uint32[2*(ntiles_global*256+2)], 8-byte aligned;
  *                             loc: uint32[ntiles_global*256]; inmask: uint64[ntiles_global*4]; alist: uint32[the band's
  *                             tiles * 256]; border_list: the slots of every band's first and last tile row (uint32
  *                             [border_count]); layout: {tile_base, ntiles} of every rank (uint32[world][2])
@@ -209,8 +210,8 @@ int lab_band_finish_game(lab_grid *g);
  *                                (lab_band_finish next); 0 = not one tree, the field is wiped, the loop above takes over
  *     lab_band_tree_chunk_words  uint32 words of a stage's chunk (stage 1..3)
  * Results are identical to the loop's, bit for bit. */
-int lab_band_tree_bind(lab_grid *g, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *s0, void *s1, void *r0,
-                       void *r1, void *loc, void *inmask, void *alist, const void *border_list, uint32_t border_count,
+int lab_band_tree_bind(lab_grid *g, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *sr0, void *sr1,
+                       void *loc, void *inmask, void *alist, const void *border_list, uint32_t border_count,
                        const void *layout, int world, int me);
 int lab_band_tree_chunk_words(const lab_grid *g, int stage);
 int lab_band_tree_count(lab_grid *g, uint64_t *squares, uint64_t *pairs, uint32_t *crossings, int32_t box[4]);

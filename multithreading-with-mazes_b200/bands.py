@@ -139,8 +139,9 @@ class _BandEngine:
             dev = self.row_device
             world = len(lay["bases"])
             b = {"key": key}
-            for name in ("succ0", "s0", "s1", "r0", "r1"):
-                b[name] = torch.empty(n + 2, dtype=torch.int32, device=dev)
+            b["succ0"] = torch.empty(n + 2, dtype=torch.int32, device=dev)
+            for name in ("sr0", "sr1"):  # (pointer, value) pairs
+                b[name] = torch.empty(n + 2, dtype=torch.int64, device=dev)
             b["loc"] = torch.empty(n, dtype=torch.int32, device=dev)
             b["inmask"] = torch.zeros(lay["total"] * 4, dtype=torch.int64, device=dev)
             b["alist"] = torch.empty(lay["ntiles"][rank] * 256, dtype=torch.int32, device=dev)
@@ -161,8 +162,8 @@ class _BandEngine:
         if b.get("bound"):
             return b
         b["bound"] = True
-        self._check(self._f("tree_bind")(self.h, c_uint32(lay["bases"][rank]), c_uint32(lay["total"]), self._ptr(b["succ0"]), self._ptr(b["s0"]),
-                                         self._ptr(b["s1"]), self._ptr(b["r0"]), self._ptr(b["r1"]), self._ptr(b["loc"]),
+        self._check(self._f("tree_bind")(self.h, c_uint32(lay["bases"][rank]), c_uint32(lay["total"]), self._ptr(b["succ0"]), self._ptr(b["sr0"]),
+                                         self._ptr(b["sr1"]), self._ptr(b["loc"]),
                                          self._ptr(b["inmask"]), self._ptr(b["alist"]), self._ptr(b["border_list"]),
                                          c_uint32(b["border_list"].numel()), self._ptr(b["layout"]), c_int(len(lay["bases"])), c_int(rank)))
         return b

@@ -61,6 +61,16 @@ LAB_DEV lab_u32x4 lab_ld_ro_v4(void const *p) { // read-only data
     return {t.x, t.y, t.z, t.w};
 }
 LAB_DEV void lab_st_stream_v4(void *p, lab_u32x4 v) { __stcs(reinterpret_cast<uint4 *>(p), make_uint4(v.x, v.y, v.z, v.w)); }
+// a (pointer, value) pair of the pointer-jumping lists: ONE 8-byte access (a random 4-byte access costs a 32-byte sector
+// either way, so two separate arrays would move twice the sectors)
+struct lab_u32x2 {
+    uint32_t x, y;
+};
+LAB_DEV lab_u32x2 lab_ld_cg_x2(uint32_t const *base, uint32_t i) {
+    uint2 const t = __ldcg(reinterpret_cast<uint2 const *>(base) + i);
+    return {t.x, t.y};
+}
+LAB_DEV void lab_st_x2(uint32_t *base, uint32_t i, uint32_t x, uint32_t y) { reinterpret_cast<uint2 *>(base)[i] = make_uint2(x, y); }
 LAB_DEV void lab_st_volatile(uint32_t *p, uint32_t v) { *reinterpret_cast<uint32_t volatile *>(p) = v; }
 
 LAB_DEV uint32_t lab_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }

@@ -58,8 +58,8 @@ struct Tree_ctl {
 
 struct Tree {
     uint32_t *succ0;     // [nslots+2] successor segment, as walked (kept: it also chains a component's crossings)
-    uint32_t *s[2];      // [nslots+2] ping-pong: successor / parent entry
-    uint32_t *r[2];      // [nslots+2] ping-pong: segments to the end of the tour / level of the entry
+    uint32_t *sr[2];     // [2 * (nslots+2)] ping-pong, (pointer, value) PAIRS: [2a] successor / parent entry, [2a+1] segments
+                         //                  to the end of the tour / level of the entry (one 8-byte access: lab_ld_cg_x2)
     uint64_t *inmask;    // [ntiles][4]  crossings through which a tile's components are ENTERED
     uint32_t *loc;       // [nslots]     local level of border squares ([side][pos], like edges)
     uint32_t *alist;     // [n_arcs]     the slots that ARE crossings (the pointer-jumping rounds only visit these)
@@ -416,8 +416,7 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
             res32[s] = out; // (the list it overwrites was last read before the barrier above)
         } else if (root_tile && lane == 0) {
             tr.succ0[ROOT] = out;
-            tr.s[0][ROOT] = out;
-            tr.r[0][ROOT] = 1u;
+            lab_st_x2(tr.sr[0], ROOT, out, 1u);
         }
     }
     lab_syncwarp();
@@ -428,8 +427,7 @@ LAB_DEV void walk_tile(Params const &p, Tree const &tr, uint32_t t, int lane, ui
         uint32_t const v = res32[s];
         bool const active = (X[s >> 6] >> (s & 63)) & 1ull;
         tr.succ0[o + s] = v;
-        tr.s[0][o + s] = v;
-        tr.r[0][o + s] = active ? 1u : 0u;
+        lab_st_x2(tr.sr[0], static_cast<uint32_t>(o + s), v, active ? 1u : 0u);
     }
     // the tile's crossings join the global list of arcs
     uint32_t const xbits = static_cast<uint32_t>((X[lane >> 3] >> ((lane & 7) * 8)) & 0xFFull); // slots 8*lane .. 8*lane+7
@@ -501,10 +499,8 @@ LAB_DEV void tree_init_body(Params const &p, Tree const &tr) {
     tr.succ0[ROOT] = END;
     tr.succ0[END] = END;
     for (int b = 0; b < 2; b++) {
-        tr.s[b][ROOT] = END;
-        tr.s[b][END] = END;
-        tr.r[b][ROOT] = 1u;
-        tr.r[b][END] = 0u;
+        lab_st_x2(tr.sr[b], ROOT, END, 1u);
+        lab_st_x2(tr.sr[b], END, END, 0u);
     }
 }
 
@@ -522,22 +518,19 @@ LAB_DEV void tree_rank_round_body(Tree const &tr, uint32_t round, long long gthr
     }
     uint32_t const ROOT = tr.nslots;
     bool const odd = round & 1u;
-    uint32_t const *sin = odd ? tr.s[1] : tr.s[0], *rin = odd ? tr.r[1] : tr.r[0];
-    uint32_t *sout = odd ? tr.s[0] : tr.s[1], *rout = odd ? tr.r[0] : tr.r[1];
+    uint32_t const *in = odd ? tr.sr[1] : tr.sr[0];
+    uint32_t *out = odd ? tr.sr[0] : tr.sr[1];
     long long const n = static_cast<long long>(tc->n_arcs) + 1;
     bool more = false;
     for (long long i = gthread; i < n; i += nthreads) {
         uint32_t const a = i + 1 < n ? tr.alist[i] : ROOT;
-        uint32_t const s = lab_ld_cg(sin + a);
-        uint32_t const r = lab_ld_cg(rin + a);
-        if (!tree_follow(tr, s)) { // the end of the tour, or (row bands) a segment of another band
-            sout[a] = s;
-            rout[a] = r;
+        lab_u32x2 const me = lab_ld_cg_x2(in, a);
+        if (!tree_follow(tr, me.x)) { // the end of the tour, or (row bands) a segment of another band
+            lab_st_x2(out, a, me.x, me.y);
         } else {
-            uint32_t const s2 = lab_ld_cg(sin + s);
-            sout[a] = s2;
-            rout[a] = r + lab_ld_cg(rin + s);
-            more |= tree_follow(tr, s2);
+            lab_u32x2 const nx = lab_ld_cg_x2(in, me.x);
+            lab_st_x2(out, a, nx.x, me.y + nx.y);
+            more |= tree_follow(tr, nx.x);
         }
     }
     // (thousands of warps storing to -- or reading past L1 from -- one address would serialise in L2:
@@ -560,7 +553,7 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
     }
     uint32_t const END = tr.nslots + 1u;
     // (the rounds' result has been brought back to buffer 0: tree_jump_settle_body)
-    uint32_t const *sfin = tr.s[0], *rfin = tr.r[0];
+    uint32_t const *fin = tr.sr[0];
     uint32_t bad = 0;
     for (long long t = gwarp; t < p.g.ntiles; t += nwarps) {
         long long const o = (t + tr.tile_base) * SLOTS;
@@ -576,8 +569,9 @@ LAB_DEV void tree_orient_body(Params const &p, Tree const &tr, long long gwarp, 
                 in[half] = false;
                 if ((X >> pos) & 1ull) {
                     uint32_t const tw = tree_twin(p.g, a);
-                    in[half] = lab_ld_cg(rfin + a) > lab_ld_cg(rfin + tw);
-                    bad += lab_ld_cg(sfin + a) != END;
+                    lab_u32x2 const me = lab_ld_cg_x2(fin, a);
+                    in[half] = me.y > lab_ld_cg_x2(fin, tw).y;
+                    bad += me.x != END;
                 }
                 tr.loc[a] = INF;
             }
@@ -839,7 +833,7 @@ LAB_DEV void tree_parent_body(Params const &p, Tree const &tr, long long gthread
         return;
     }
     uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
-    uint32_t *par = tr.s[0], *val = tr.r[0];
+    uint32_t *parval = tr.sr[0];
     long long const n = static_cast<long long>(tc->n_arcs) + 1;
     for (long long i = gthread; i < n; i += nthreads) {
         uint32_t pa = ROOT, v = INF;
@@ -876,8 +870,7 @@ LAB_DEV void tree_parent_body(Params const &p, Tree const &tr, long long gthread
                 }
             }
         }
-        par[e] = pa;
-        val[e] = v;
+        lab_st_x2(parval, e, pa, v);
     }
 }
 
@@ -888,22 +881,19 @@ LAB_DEV void tree_prefix_round_body(Tree const &tr, uint32_t round, long long gt
     }
     uint32_t const ROOT = tr.nslots;
     bool const odd = round & 1u;
-    uint32_t const *pin = odd ? tr.s[1] : tr.s[0], *vin = odd ? tr.r[1] : tr.r[0];
-    uint32_t *pout = odd ? tr.s[0] : tr.s[1], *vout = odd ? tr.r[0] : tr.r[1];
+    uint32_t const *in = odd ? tr.sr[1] : tr.sr[0];
+    uint32_t *out = odd ? tr.sr[0] : tr.sr[1];
     long long const n = static_cast<long long>(tc->n_arcs) + 1;
     bool more = false;
     for (long long i = gthread; i < n; i += nthreads) {
         uint32_t const a = i + 1 < n ? tr.alist[i] : ROOT;
-        uint32_t const pa = lab_ld_cg(pin + a);
-        uint32_t const v = lab_ld_cg(vin + a);
-        if (!tree_follow(tr, pa)) { // the root, or (row bands) an entry of another band
-            pout[a] = pa;
-            vout[a] = v;
+        lab_u32x2 const me = lab_ld_cg_x2(in, a);
+        if (!tree_follow(tr, me.x)) { // the root, or (row bands) an entry of another band
+            lab_st_x2(out, a, me.x, me.y);
         } else {
-            uint32_t const p2 = lab_ld_cg(pin + pa);
-            pout[a] = p2;
-            vout[a] = v + lab_ld_cg(vin + pa);
-            more |= tree_follow(tr, p2);
+            lab_u32x2 const up = lab_ld_cg_x2(in, me.x);
+            lab_st_x2(out, a, up.x, me.y + up.y);
+            more |= tree_follow(tr, up.x);
         }
     }
     if (lab_any(more) && (gthread & 31) == 0 && lab_ld_ro(&tc->prefix_more[round]) == 0u) {
@@ -926,8 +916,8 @@ LAB_DEV void tree_jump_settle_body(Tree const &tr, uint32_t buf, long long gthre
     long long const n = static_cast<long long>(tr.tc->n_arcs) + 1;
     for (long long i = gthread; i < n; i += nthreads) {
         uint32_t const a = i + 1 < n ? tr.alist[i] : ROOT;
-        tr.s[0][a] = lab_ld_cg(tr.s[1] + a);
-        tr.r[0][a] = lab_ld_cg(tr.r[1] + a);
+        lab_u32x2 const v = lab_ld_cg_x2(tr.sr[1], a);
+        lab_st_x2(tr.sr[0], a, v.x, v.y);
     }
 }
 
@@ -937,9 +927,9 @@ LAB_DEV void tree_jump_settle_body(Tree const &tr, uint32_t buf, long long gthre
 // tiles another band's pointers can lead into -- of up to three of the global arrays; after the all-gather
 // every rank copies the other ranks' rows into its own copy of those arrays and folds the headers into its
 // control block, so that all ranks come to the same verdict without a round trip through the host.
-//   stage 1 (after the windowed ranking)  s[0], r[0], succ0   + the tour's start (ROOT) from the rank that holds it
+//   stage 1 (after the windowed ranking)  sr[0] (successor, segments) pairs, succ0   + the tour's start (ROOT) from its rank
 //   stage 2 (after orient + flood)        loc, inmask
-//   stage 3 (after the windowed prefix)   s[0] (= parent), r[0] (= level so far)
+//   stage 3 (after the windowed prefix)   sr[0] (parent, level so far) pairs
 constexpr uint32_t BORDER_HDR = 8; // unreached, walk_error, bad_weight, !ok, settled lo, settled hi, ROOT pointer, ROOT value
 struct Band_layout {          // of every rank, in rank order (device memory, owned by the caller)
     uint32_t tile_base, ntiles; // the band's first tile (global id) and number of tiles
@@ -956,19 +946,17 @@ struct Border_arr {
 };
 LAB_DEV int border_arrays(Tree const &tr, int stage, Border_arr (&arr)[3]) {
     if (stage == 1) {
-        arr[0] = {tr.s[0], SLOTS};
-        arr[1] = {tr.r[0], SLOTS};
-        arr[2] = {tr.succ0, SLOTS};
-        return 3;
+        arr[0] = {tr.sr[0], 2u * SLOTS};
+        arr[1] = {tr.succ0, SLOTS};
+        return 2;
     }
     if (stage == 2) {
         arr[0] = {tr.loc, SLOTS};
         arr[1] = {reinterpret_cast<uint32_t *>(tr.inmask), 8u}; // 4 x uint64 per tile
         return 2;
     }
-    arr[0] = {tr.s[0], SLOTS};
-    arr[1] = {tr.r[0], SLOTS};
-    return 2;
+    arr[0] = {tr.sr[0], 2u * SLOTS};
+    return 1;
 }
 
 LAB_DEV void tree_border_export_body(Params const &p, Tree const &tr, int stage, uint32_t *chunk, long long gthread, long long nthreads) {
@@ -981,8 +969,9 @@ LAB_DEV void tree_border_export_body(Params const &p, Tree const &tr, int stage,
         chunk[3] = tc->ok ? 0u : 1u;
         chunk[4] = static_cast<uint32_t>(tc->local_settled);
         chunk[5] = static_cast<uint32_t>(tc->local_settled >> 32);
-        chunk[6] = tr.s[0][tr.nslots];
-        chunk[7] = tr.r[0][tr.nslots];
+        lab_u32x2 const root = lab_ld_cg_x2(tr.sr[0], tr.nslots);
+        chunk[6] = root.x;
+        chunk[7] = root.y;
     }
     Border_arr arr[3];
     int const na = border_arrays(tr, stage, arr);
@@ -1022,8 +1011,7 @@ LAB_DEV void tree_border_import_body(Params const &p, Tree const &tr, int stage,
         }
         if (stage == 1 && me != root_rank) {
             uint32_t const *h = all + static_cast<size_t>(root_rank) * words;
-            tr.s[0][tr.nslots] = h[6];
-            tr.r[0][tr.nslots] = h[7];
+            lab_st_x2(tr.sr[0], tr.nslots, h[6], h[7]);
         }
     }
     Border_arr arr[3];
@@ -1067,10 +1055,10 @@ LAB_DEV void tree_finish_jump_body(Params const &p, Tree const &tr, long long gt
                 continue; // a border row's entry
             }
         }
-        uint32_t const s = tr.s[0][a];
-        if (s < tr.nslots) { // stopped at the window's edge: s is an entry of another band's border row
-            tr.r[0][a] += tr.r[0][s];
-            tr.s[0][a] = tr.s[0][s];
+        lab_u32x2 const me = lab_ld_cg_x2(tr.sr[0], a);
+        if (me.x < tr.nslots) { // stopped at the window's edge: me.x is an entry of another band's border row
+            lab_u32x2 const far = lab_ld_cg_x2(tr.sr[0], me.x);
+            lab_st_x2(tr.sr[0], a, far.x, me.y + far.y);
         }
     }
 }
@@ -1085,7 +1073,7 @@ LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, uint16_t *grid, lo
         return;
     }
     Geom const &g = p.g;
-    uint32_t const *lvl = tr.r[0]; // (tree_jump_settle_body)
+    uint32_t const *lvl = tr.sr[0]; // (tree_jump_settle_body) pairs: the level is the second word
     uint32_t *dist = p.plane[0].dist;
     uint32_t mx = 0, marked = 0;
     uint16_t const mark = static_cast<uint16_t>(tr.mark_bits);
@@ -1120,8 +1108,8 @@ LAB_DEV void tree_fixup_body(Params const &p, Tree const &tr, uint16_t *grid, lo
             int const c = j0 * TS + lane + 32 * u;
             if (v[u] != INF) {
                 uint32_t const comp = v[u] >> 16;
-                uint32_t const *b = lvl + (trow + j0 + u / 2 + tr.tile_base) * SLOTS;
-                uint32_t const out = (comp == ROOT_COMP ? 0u : b[comp]) + (v[u] & 0xFFFFu);
+                uint32_t const *b = lvl + (trow + j0 + u / 2 + tr.tile_base) * (2 * SLOTS);
+                uint32_t const out = (comp == ROOT_COMP ? 0u : b[2 * comp + 1]) + (v[u] & 0xFFFFu);
                 row[c] = out;
                 mx = out > mx ? out : mx;
                 if (mark) {

@@ -105,16 +105,17 @@ template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p,
         a[k] = own[k] ? (i + 1 < n ? tr.alist[i] : ROOT) : 0u;
     }
 #pragma unroll
-    for (int k = 0; k < JUMP_K; k++) {
-        s[k] = own[k] ? __ldcg(tr.s[0] + a[k]) : STOP;
-        r[k] = own[k] ? __ldcg(tr.r[0] + a[k]) : 0u;
+    for (int k = 0; k < JUMP_K; k++) { // (pointer, value) pairs: one 8-byte load each
+        uint2 const v = own[k] ? __ldcg(reinterpret_cast<uint2 const *>(tr.sr[0]) + a[k]) : make_uint2(STOP, 0u);
+        s[k] = v.x;
+        r[k] = v.y;
     }
     bool const spill = n > JUMP_K * nthreads; // more entries than registers: the rest goes the plain way
     uint32_t last = 0; // the buffer the rounds end in
     for (uint32_t round = 0; round < max_rounds; round++) {
         bool const odd = round & 1u;
-        uint32_t const *sin = odd ? tr.s[1] : tr.s[0], *rin = odd ? tr.r[1] : tr.r[0];
-        uint32_t *sout = odd ? tr.s[0] : tr.s[1], *rout = odd ? tr.r[0] : tr.r[1];
+        uint2 const *in = reinterpret_cast<uint2 const *>(odd ? tr.sr[1] : tr.sr[0]);
+        uint2 *out = reinterpret_cast<uint2 *>(odd ? tr.sr[0] : tr.sr[1]);
         // three hops per round through the buffer of the last round: a pointer's span grows fourfold.
         // (tree_follow: not past the end of the list, and -- row bands -- not out of the band's window)
         uint32_t s2[JUMP_K], r2[JUMP_K];
@@ -129,8 +130,9 @@ template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p,
 #pragma unroll
             for (int k = 0; k < JUMP_K; k++) {
                 bool const go = tree_follow(tr, s2[k]);
-                sn[k] = go ? __ldcg(sin + s2[k]) : s2[k];
-                rn[k] = go ? __ldcg(rin + s2[k]) : 0u;
+                uint2 const v = go ? __ldcg(in + s2[k]) : make_uint2(s2[k], 0u);
+                sn[k] = v.x;
+                rn[k] = v.y;
             }
 #pragma unroll
             for (int k = 0; k < JUMP_K; k++) {
@@ -147,22 +149,19 @@ template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p,
                     s[k] = s2[k];
                     m |= tree_follow(tr, s[k]);
                 }
-                sout[a[k]] = s[k];
-                rout[a[k]] = r[k];
+                out[a[k]] = make_uint2(s[k], r[k]);
             }
         }
         if (spill) {
             for (long long i = gthread + JUMP_K * nthreads; i < n; i += nthreads) {
                 uint32_t const ai = i + 1 < n ? tr.alist[i] : ROOT;
-                uint32_t const si = __ldcg(sin + ai), ri = __ldcg(rin + ai);
-                if (!tree_follow(tr, si)) {
-                    sout[ai] = si;
-                    rout[ai] = ri;
+                uint2 const me = __ldcg(in + ai);
+                if (!tree_follow(tr, me.x)) {
+                    out[ai] = me;
                 } else {
-                    uint32_t const si2 = __ldcg(sin + si);
-                    sout[ai] = si2;
-                    rout[ai] = ri + __ldcg(rin + si);
-                    m |= tree_follow(tr, si2);
+                    uint2 const nx = __ldcg(in + me.x);
+                    out[ai] = make_uint2(nx.x, me.y + nx.y);
+                    m |= tree_follow(tr, nx.x);
                 }
             }
         }
@@ -180,15 +179,13 @@ template <int KIND> __global__ void __launch_bounds__(512) k_tree_jump(Params p,
 #pragma unroll
         for (int k = 0; k < JUMP_K; k++) {
             if (own[k]) {
-                tr.s[0][a[k]] = s[k];
-                tr.r[0][a[k]] = r[k];
+                reinterpret_cast<uint2 *>(tr.sr[0])[a[k]] = make_uint2(s[k], r[k]);
             }
         }
         if (spill) {
             for (long long i = gthread + JUMP_K * nthreads; i < n; i += nthreads) {
                 uint32_t const ai = i + 1 < n ? tr.alist[i] : ROOT;
-                tr.s[0][ai] = __ldcg(tr.s[1] + ai);
-                tr.r[0][ai] = __ldcg(tr.r[1] + ai);
+                reinterpret_cast<uint2 *>(tr.sr[0])[ai] = __ldcg(reinterpret_cast<uint2 const *>(tr.sr[1]) + ai);
             }
         }
     }
@@ -629,10 +626,8 @@ int ensure_tree(lab_grid *h) {
     tr.nslots = static_cast<uint32_t>(nt * SLOTS);
     size_t const n = (nt * SLOTS + 2) * sizeof(uint32_t);
     CU(cudaMalloc(&tr.succ0, n));
-    CU(cudaMalloc(&tr.s[0], n));
-    CU(cudaMalloc(&tr.s[1], n));
-    CU(cudaMalloc(&tr.r[0], n));
-    CU(cudaMalloc(&tr.r[1], n));
+    CU(cudaMalloc(&tr.sr[0], 2 * n));
+    CU(cudaMalloc(&tr.sr[1], 2 * n));
     CU(cudaMalloc(&tr.inmask, nt * 4 * sizeof(uint64_t)));
     CU(cudaMalloc(&tr.loc, nt * SLOTS * sizeof(uint32_t)));
     CU(cudaMalloc(&tr.alist, nt * SLOTS * sizeof(uint32_t)));
@@ -939,10 +934,8 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->ghost_s);
     cudaFree(h->d_activated);
     cudaFree(h->tree.succ0);
-    cudaFree(h->tree.s[0]);
-    cudaFree(h->tree.s[1]);
-    cudaFree(h->tree.r[0]);
-    cudaFree(h->tree.r[1]);
+    cudaFree(h->tree.sr[0]);
+    cudaFree(h->tree.sr[1]);
     cudaFree(h->tree.inmask);
     cudaFree(h->tree.loc);
     cudaFree(h->tree.alist);
@@ -1434,10 +1427,10 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
 }
 
 // ---- the spanning-tree pipeline across row bands (device/tree.cuh; protocol in include/labyrinth_b200.h) ----
-int lab_band_tree_bind(lab_grid *h, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *s0, void *s1, void *r0, void *r1,
+int lab_band_tree_bind(lab_grid *h, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *sr0, void *sr1,
                        void *loc, void *inmask, void *alist, const void *border_list, uint32_t border_count, const void *layout,
                        int world, int me) {
-    if (!h || !succ0 || !s0 || !s1 || !r0 || !r1 || !loc || !inmask || !alist || !border_list || !layout || world < 1 || me < 0 || me >= world) {
+    if (!h || !succ0 || !sr0 || !sr1 || (reinterpret_cast<uintptr_t>(sr0) & 7u) || (reinterpret_cast<uintptr_t>(sr1) & 7u) || !loc || !inmask || !alist || !border_list || !layout || world < 1 || me < 0 || me >= world) {
         return fail(LAB_ERR_ARG, "lab_band_tree_bind: bad argument");
     }
     if (static_cast<unsigned long long>(ntiles_global) * SLOTS + 2 >= (1ull << 32) || tile_base + static_cast<uint32_t>(h->g.ntiles) > ntiles_global) {
@@ -1451,10 +1444,8 @@ int lab_band_tree_bind(lab_grid *h, uint32_t tile_base, uint32_t ntiles_global, 
         CU(cudaMalloc(&tr.tc, sizeof(Tree_ctl)));
     }
     tr.succ0 = static_cast<uint32_t *>(succ0);
-    tr.s[0] = static_cast<uint32_t *>(s0);
-    tr.s[1] = static_cast<uint32_t *>(s1);
-    tr.r[0] = static_cast<uint32_t *>(r0);
-    tr.r[1] = static_cast<uint32_t *>(r1);
+    tr.sr[0] = static_cast<uint32_t *>(sr0);
+    tr.sr[1] = static_cast<uint32_t *>(sr1);
     tr.loc = static_cast<uint32_t *>(loc);
     tr.inmask = static_cast<uint64_t *>(inmask);
     tr.alist = static_cast<uint32_t *>(alist);

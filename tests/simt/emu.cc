@@ -35,15 +35,13 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
     if (d.nplanes != 1 || d.src_r[0] < 0 || !g_tree_mode) return;
     size_t const nt = static_cast<size_t>(w.g.ntiles);
     size_t const n = nt * SLOTS + 2;
-    std::vector<uint32_t> succ0(n), s0(n), s1(n), r0(n), r1(n), loc(nt * SLOTS), alist(nt * SLOTS);
+    std::vector<uint32_t> succ0(n), sr0(2 * n), sr1(2 * n), loc(nt * SLOTS), alist(nt * SLOTS);
     std::vector<uint64_t> inmask(nt * 4);
     Tree_ctl tc{};
     Tree tr{};
     tr.succ0 = succ0.data();
-    tr.s[0] = s0.data();
-    tr.s[1] = s1.data();
-    tr.r[0] = r0.data();
-    tr.r[1] = r1.data();
+    tr.sr[0] = sr0.data();
+    tr.sr[1] = sr1.data();
     tr.inmask = inmask.data();
     tr.loc = loc.data();
     tr.alist = alist.data();
@@ -385,16 +383,14 @@ int emu_band_finish(void *h, uint64_t *local_max, uint64_t *local_settled) {
     return 0;
 }
 
-int emu_band_tree_bind(void *h, uint32_t tile_base, uint32_t ntiles_global, uint32_t *succ0, uint32_t *s0, uint32_t *s1, uint32_t *r0,
-                       uint32_t *r1, uint32_t *loc, uint64_t *inmask, uint32_t *alist, uint32_t const *border_list, uint32_t border_count,
+int emu_band_tree_bind(void *h, uint32_t tile_base, uint32_t ntiles_global, uint32_t *succ0, uint32_t *sr0, uint32_t *sr1,
+                       uint32_t *loc, uint64_t *inmask, uint32_t *alist, uint32_t const *border_list, uint32_t border_count,
                        Band_layout const *layout, int world, int me) {
     auto *e = static_cast<Emu_band *>(h);
     Tree &tr = e->tr;
     tr.succ0 = succ0;
-    tr.s[0] = s0;
-    tr.s[1] = s1;
-    tr.r[0] = r0;
-    tr.r[1] = r1;
+    tr.sr[0] = sr0;
+    tr.sr[1] = sr1;
     tr.loc = loc;
     tr.inmask = inmask;
     tr.alist = alist;

@@ -239,6 +239,17 @@ LAB_DEV lab_u32x4 lab_ld_stream_v4(void const *p) {
 }
 LAB_DEV lab_u32x4 lab_ld_ro_v4(void const *p) { return lab_ld_stream_v4(p); }
 LAB_DEV void lab_st_stream_v4(void *p, lab_u32x4 v) { std::memcpy(p, &v, sizeof v); }
+struct lab_u32x2 {
+    uint32_t x, y;
+};
+LAB_DEV lab_u32x2 lab_ld_cg_x2(uint32_t const *base, uint32_t i) {
+    simt::maybe_yield();
+    return {base[2 * static_cast<size_t>(i)], base[2 * static_cast<size_t>(i) + 1]};
+}
+LAB_DEV void lab_st_x2(uint32_t *base, uint32_t i, uint32_t x, uint32_t y) {
+    base[2 * static_cast<size_t>(i)] = x;
+    base[2 * static_cast<size_t>(i) + 1] = y;
+}
 LAB_DEV void lab_st_volatile(uint32_t *p, uint32_t v) { *p = v; }
 
 template <class T> LAB_DEV T lab_atomic_add(T *p, typename std::common_type<T>::type v) {
