@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one maze: the whole search (workspace reset, pack,
-search phase -- the spanning-tree pipeline on perfect mazes, the persistent tile-relaxation kernel
-otherwise --, epilogue) for the workload named in ``config.workload``.
+search phase -- the spanning-tree pipeline on perfect mazes, one streaming pass on open rooms (arenas),
+the persistent tile-relaxation kernel otherwise --, epilogue) for the workload named in ``config.workload``.
+N > 1 (torchrun): distance workloads run ONE maze N times taller, sharded as row bands, one band per GPU
+(``--sharding bands``, the default; multithreading-with-mazes_b200/bands.py); the other games run one maze per GPU.
 Default workload = BASELINE.json configs[1]: Distance map from the centre of a 4095x4095 Kruskal
 perfect maze (seeded, built by the product's linear-time builder, byte-identical to the
 reference builder's output for that seed).
