@@ -237,7 +237,8 @@ def _gloo_game_worker(rank, world, port, maze_path, out_dir, game, spec):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("builder,rows,cols,world,road", [("kruskal", 255, 131, 2, "tree"), ("wilson", 193, 197, 3, "tree"), ("arena", 193, 131, 3, "room")])
+@pytest.mark.parametrize("builder,rows,cols,world,road", [("kruskal", 255, 131, 2, "tree"), ("wilson", 193, 197, 3, "tree"), ("arena", 193, 131, 3, "room"),
+                                                          ("rdfs", 447, 67, 3, "tree")])  # (rdfs: corridors that cross the band borders again and again)
 def test_sharded_hunt_and_gather_on_gloo(lab, O, tmp_path, builder, rows, cols, world, road):
     """Bfs::hunt and Bfs::gather across 2-3 bands (one tree / an open room): grids, winner, claims and the canonical paths
     -- walked band by band, handed over at the borders -- equal the single-maze canonical model's."""
