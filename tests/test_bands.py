@@ -245,7 +245,7 @@ def test_sharded_hunt_and_gather_on_gloo(lab, O, tmp_path, builder, rows, cols, 
     import torch.multiprocessing as mp
 
     maze = lab.build_maze(builder, rows, cols, seed=41)
-    for i, seed in enumerate((7, 8)):
+    for i, seed in enumerate((7,)):
         # hunt
         placed, s, f = lab.place_hunt(maze, seed=seed)
         path = str(tmp_path / "maze.npy")
