@@ -37,7 +37,8 @@ typedef enum lab_status {
     LAB_ERR_CUDA = -2,     /* CUDA runtime error (no device, out of memory, launch failure)    */
     LAB_ERR_TIMEOUT = -3,  /* the persistent search kernel hit its deadline (LAB_BFS_BUDGET_MS) */
     LAB_ERR_INTERNAL = -4, /* invariant broken inside the search (queue overflow)              */
-    LAB_ERR_PLACE = -5     /* no valid square for a start/finish (reference aborts here)       */
+    LAB_ERR_PLACE = -5,    /* no valid square for a start/finish (reference aborts here)       */
+    LAB_ERR_IO = -6        /* maze file cannot be opened / written / is not a maze file        */
 } lab_status;
 
 /* Maze::Point, maze/maze.cc:116-119 */
@@ -243,6 +244,15 @@ int lab_place_corners(int rows, int cols, uint16_t *squares, uint32_t seed, lab_
 /* Linear-time seeded builders (builders/{arena,grid,recursive_backtracker,kruskal,
  * wilson_path_carver,mods}.cc): builder in arena|rdfs|grid|kruskal|wilson, mod in none|cross|x. */
 int lab_build_maze(const char *builder, const char *mod, int rows, int cols, uint32_t seed, uint16_t *squares);
+
+/* ---- the raw maze file ------------------------------------------------------------------------ */
+/* The reference has no file I/O; "identical serialized mazes" (BASELINE.json) need a
+ * format: "LABMAZE1", int32 rows, int32 cols (little endian), then rows*cols uint16 Squares, dense
+ * row-major exactly as Maze::Maze holds them (maze/maze.cc:127-144).  Data starts at byte 16 (mmap-able).
+ * The oracle, the CLIs (LAB_LOAD=path / LAB_DUMP=path) and bench.py's maze cache read and write it. */
+int lab_maze_write(const char *path, int rows, int cols, const uint16_t *squares);
+int lab_maze_header(const char *path, int *rows, int *cols);
+int lab_maze_read(const char *path, int rows, int cols, uint16_t *squares);
 
 /* Library / device probe: fills a short description, returns the number of CUDA devices (0 = none). */
 int lab_device_info(char *buf, size_t buflen);

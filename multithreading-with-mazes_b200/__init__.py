@@ -34,7 +34,7 @@ ABI_SYMBOLS = (
     "lab_distance_paint", "lab_pixels_device", "lab_pixels_bind",
     "lab_bfs_hunt", "lab_bfs_gather", "lab_bfs_corners", "lab_last_painted", "lab_last_timing", "lab_last_stats",
     "lab_last_error", "lab_pick_random_point", "lab_set_corner_starts", "lab_place_hunt", "lab_place_gather",
-    "lab_place_corners", "lab_build_maze", "lab_device_info",
+    "lab_place_corners", "lab_build_maze", "lab_device_info", "lab_maze_write", "lab_maze_header", "lab_maze_read",
     "lab_band_cols_padded", "lab_band_begin", "lab_band_path_rows", "lab_band_set_neighbour_paths", "lab_band_relax",
     "lab_band_export_edges", "lab_band_import_edges", "lab_band_finish",
     "lab_band_tree_bind", "lab_band_tree_chunk_words", "lab_band_tree_count", "lab_band_tree_rank_local", "lab_band_tree_flood",
@@ -118,6 +118,9 @@ def lib():
         L.lab_place_corners.argtypes = [c_int, c_int, c_void_p, c_uint32, c_void_p, POINTER(Point)]
         L.lab_build_maze.argtypes = [c_char_p, c_char_p, c_int, c_int, c_uint32, c_void_p]
         L.lab_device_info.argtypes = [c_char_p, c_size_t]
+        L.lab_maze_write.argtypes = [c_char_p, c_int, c_int, c_void_p]
+        L.lab_maze_header.argtypes = [c_char_p, POINTER(c_int), POINTER(c_int)]
+        L.lab_maze_read.argtypes = [c_char_p, c_int, c_int, c_void_p]
         L.lab_band_cols_padded.argtypes = [c_void_p]
         L.lab_band_begin.argtypes = [c_void_p, c_int, c_int]
         L.lab_band_path_rows.argtypes = [c_void_p, c_void_p, c_void_p]
@@ -150,6 +153,55 @@ def build_maze(builder: str, rows: int, cols: int, seed: int, mod: Optional[str]
     """Seeded linear-time builder (arena|rdfs|grid|kruskal|wilson, mod none|cross|x) -> uint16[rows, cols]."""
     g = np.empty((rows, cols), np.uint16)
     _check(lib().lab_build_maze(builder.encode(), (mod or "none").encode(), rows, cols, seed & 0xFFFFFFFF, _np_ptr(g)))
+    return g
+
+
+# The raw maze file (include/labyrinth_b200.h): "LABMAZE1", int32 rows, int32 cols, rows*cols uint16 LE, row-major.
+MAZE_FILE_HEADER_BYTES = 16
+
+
+def write_maze(path: str, squares: np.ndarray) -> None:
+    g = np.ascontiguousarray(squares, np.uint16)
+    _check(lib().lab_maze_write(os.fsencode(path), g.shape[0], g.shape[1], _np_ptr(g)))
+
+
+def maze_header(path: str) -> tuple[int, int]:
+    r, c = c_int(), c_int()
+    _check(lib().lab_maze_header(os.fsencode(path), byref(r), byref(c)))
+    return r.value, c.value
+
+
+def read_maze(path: str, mmap: bool = False) -> np.ndarray:
+    """-> uint16[rows, cols]; mmap=True maps the file read-only instead of copying it (the data starts 16-byte aligned)."""
+    rows, cols = maze_header(path)
+    if mmap:
+        return np.memmap(path, dtype=np.uint16, mode="r", offset=MAZE_FILE_HEADER_BYTES, shape=(rows, cols))
+    g = np.empty((rows, cols), np.uint16)
+    _check(lib().lab_maze_read(os.fsencode(path), rows, cols, _np_ptr(g)))
+    return g
+
+
+def cached_maze(builder: str, rows: int, cols: int, seed: int, mod: Optional[str] = None, cache_dir: Optional[str] = None,
+                mmap: bool = False) -> np.ndarray:
+    """build_maze() through a file cache keyed by (builder, mod, size, seed): a 32767 x 32767 Kruskal maze takes two
+    minutes of host time to build and a second to read back.  The cache lives in $LAB_MAZE_CACHE (default
+    /dev/shm/lab_mazes, else the temp dir); several ranks may race for one entry (files are written under a
+    temporary name and renamed)."""
+    d = cache_dir or os.environ.get("LAB_MAZE_CACHE") or ("/dev/shm/lab_mazes" if os.path.isdir("/dev/shm") else os.path.join(
+        __import__("tempfile").gettempdir(), "lab_mazes"))
+    path = os.path.join(d, f"{builder}-{mod or 'none'}-{rows}x{cols}-{seed & 0xFFFFFFFF:08x}.labmaze")
+    if os.path.exists(path):
+        try:
+            if maze_header(path) == (rows, cols):
+                return read_maze(path, mmap=mmap)
+        except LabError:
+            pass
+    g = build_maze(builder, rows, cols, seed, mod)
+    try:
+        os.makedirs(d, exist_ok=True)
+        write_maze(path, g)
+    except (OSError, LabError):
+        pass  # a cache that cannot be written is only slower
     return g
 
 

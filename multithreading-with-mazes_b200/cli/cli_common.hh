@@ -83,22 +83,38 @@ inline void apply_environment() {
     }
 }
 
-// LAB_DUMP=path writes the final Squares (rows, cols as int32, then rows*cols uint16, little endian)
-// so a run can be compared with the oracle.
+// LAB_DUMP=path writes the final Squares as a raw maze file (include/labyrinth_b200.h: "LABMAZE1", int32 rows,
+// int32 cols, rows*cols uint16 little endian) so a run can be compared with the oracle -- and fed back in:
 inline void dump_if_requested(Maze::Maze const &maze) {
     char const *path = std::getenv("LAB_DUMP");
     if (!path) {
         return;
     }
-    std::FILE *f = std::fopen(path, "wb");
-    if (!f) {
-        std::cerr << "cannot write " << path << "\n";
+    if (lab_maze_write(path, maze.row_size(), maze.col_size(), maze.squares()) != LAB_OK) {
+        std::cerr << lab_last_error() << "\n";
         std::exit(1);
     }
-    int32_t const dims[2] = {maze.row_size(), maze.col_size()};
-    std::fwrite(dims, sizeof dims, 1, f);
-    std::fwrite(maze.squares(), sizeof(uint16_t), static_cast<size_t>(dims[0]) * dims[1], f);
-    std::fclose(f);
+}
+
+// LAB_LOAD=path: the maze comes from a raw maze file instead of the builder (-b / -m are then ignored, -r / -c
+// must match the file or be left at their defaults: the file's size wins).  This is how "identical serialized
+// mazes" (BASELINE.json) reach the CLIs: a maze built once -- here, by the oracle, by bench.py -- is solved as it is.
+inline bool load_requested(int &rows, int &cols) {
+    char const *path = std::getenv("LAB_LOAD");
+    if (!path) {
+        return false;
+    }
+    if (lab_maze_header(path, &rows, &cols) != LAB_OK) {
+        std::cerr << lab_last_error() << "\n";
+        std::exit(1);
+    }
+    return true;
+}
+inline void load_into(Maze::Maze &maze) {
+    if (lab_maze_read(std::getenv("LAB_LOAD"), maze.row_size(), maze.col_size(), maze.squares()) != LAB_OK) {
+        std::cerr << lab_last_error() << "\n";
+        std::exit(1);
+    }
 }
 
 inline void print_build(Maze::Maze const &maze) {

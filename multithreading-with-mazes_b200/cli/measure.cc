@@ -89,8 +89,16 @@ int main(int argc, char **argv) {
             cli::print_invalid_arg(pairs, print_usage);
         }
     }
+    int file_rows = 0, file_cols = 0;
+    bool const from_file = cli::load_requested(file_rows, file_cols); // LAB_LOAD: a raw maze file instead of -b / -m
+    if (from_file) {
+        margs.odd_rows = static_cast<uint64_t>(file_rows);
+        margs.odd_cols = static_cast<uint64_t>(file_cols);
+    }
     Maze::Maze maze(margs);
-    if (builder_animated) {
+    if (from_file) {
+        cli::load_into(maze);
+    } else if (builder_animated) {
         std::get<1>(builder)(maze, builder_speed);
         if (modder) std::get<1>(*modder)(maze, builder_speed);
     } else {

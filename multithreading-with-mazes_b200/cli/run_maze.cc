@@ -102,8 +102,16 @@ int main(int argc, char **argv) {
         }
     }
 
+    int file_rows = 0, file_cols = 0;
+    bool const from_file = cli::load_requested(file_rows, file_cols); // LAB_LOAD: a raw maze file instead of -b / -m
+    if (from_file) {
+        runner.args.odd_rows = static_cast<uint64_t>(file_rows);
+        runner.args.odd_cols = static_cast<uint64_t>(file_cols);
+    }
     Maze::Maze maze(runner.args);
-    if (runner.builder_animated) {
+    if (from_file) {
+        cli::load_into(maze);
+    } else if (runner.builder_animated) {
         std::get<1>(runner.builder)(maze, runner.builder_speed);
         if (runner.modder) std::get<1>(*runner.modder)(maze, runner.builder_speed);
     } else {

@@ -17,6 +17,7 @@
 #include "device/post.cuh"
 #include "device/tree.cuh"
 #include "host/builders.hh"
+#include "host/mazefile.hh"
 #include "host/points.hh"
 
 using namespace lab;
@@ -1827,6 +1828,26 @@ int lab_build_maze(const char *builder, const char *mod, int rows, int cols, uin
     if (rc == -2) return fail(LAB_ERR_ARG, "unknown builder '%s'", builder ? builder : "(null)");
     if (rc == -3) return fail(LAB_ERR_ARG, "unknown modification '%s'", mod ? mod : "(null)");
     return LAB_OK;
+}
+
+// ---- the raw maze file (host/mazefile.cc) ----------------------------------------------------
+static int maze_file_status(int rc, char const *what, char const *path) {
+    switch (rc) {
+    case 0: return LAB_OK;
+    case -1: return fail(LAB_ERR_ARG, "%s: bad argument", what);
+    case -2: return fail(LAB_ERR_IO, "%s: cannot open or write '%s'", what, path ? path : "(null)");
+    case -3: return fail(LAB_ERR_IO, "%s: '%s' is not a maze file (or is truncated)", what, path ? path : "(null)");
+    default: return fail(LAB_ERR_ARG, "%s: the size asked for differs from the one in '%s'", what, path ? path : "(null)");
+    }
+}
+int lab_maze_write(const char *path, int rows, int cols, const uint16_t *squares) {
+    return maze_file_status(host::maze_file_write(path, rows, cols, squares), "lab_maze_write", path);
+}
+int lab_maze_header(const char *path, int *rows, int *cols) {
+    return maze_file_status(host::maze_file_header(path, rows, cols), "lab_maze_header", path);
+}
+int lab_maze_read(const char *path, int rows, int cols, uint16_t *squares) {
+    return maze_file_status(host::maze_file_read(path, rows, cols, squares), "lab_maze_read", path);
 }
 
 } // extern "C"

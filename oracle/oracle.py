@@ -60,6 +60,27 @@ def orc():
     return _ORC
 
 
+def read_maze_file(path: str) -> np.ndarray:
+    """A raw maze file (include/labyrinth_b200.h: "LABMAZE1", int32 rows, cols, then uint16 LE row-major), read
+    without the product's library so that oracle and product consume the same BYTES independently."""
+    with open(path, "rb") as f:
+        head = f.read(16)
+        if len(head) != 16 or head[:8] != b"LABMAZE1":
+            raise ValueError(f"{path} is not a maze file")
+        rows, cols = (int(x) for x in np.frombuffer(head[8:], "<i4"))
+        g = np.fromfile(f, dtype="<u2", count=rows * cols)
+    if g.size != rows * cols:
+        raise ValueError(f"{path} is truncated")
+    return g.astype(np.uint16, copy=False).reshape(rows, cols)
+
+
+def write_maze_file(path: str, grid: np.ndarray) -> None:
+    g = np.ascontiguousarray(grid, "<u2")
+    with open(path, "wb") as f:
+        f.write(b"LABMAZE1" + np.asarray(g.shape, "<i4").tobytes())
+        g.tofile(f)
+
+
 def have_ref() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "libref_bfs.so")) and os.path.exists(
         os.path.join(HERE, "_ref", "libref_dist.so")

@@ -34,8 +34,9 @@ def test_out_of_scope_solvers_are_argument_errors():
 
 def read_dump(path):
     raw = open(path, "rb").read()
-    rows, cols = np.frombuffer(raw[:8], np.int32)
-    return np.frombuffer(raw[8:], np.uint16).reshape(rows, cols).copy()
+    assert raw[:8] == b"LABMAZE1"
+    rows, cols = np.frombuffer(raw[8:16], np.int32)
+    return np.frombuffer(raw[16:], np.uint16).reshape(rows, cols).copy()
 
 
 @pytest.mark.gpu
