@@ -54,6 +54,7 @@ WORKLOADS = {
     "distance-wilson-4095": ("distance", "wilson", 4095, None, "configs[4] builder at 4095"),
     "distance-kruskal-16383": ("distance", "kruskal", 16383, None, "configs[1] builder at 16383 (20 s host build)"),
     "h-distance-kruskal-32767": ("distance", "kruskal", 32767, None, "north_star headline size, perfect maze (90 s host build)"),
+    "h-gather-kruskal-32767": ("gather", "kruskal", 32767, None, "north_star headline size, perfect maze (90 s host build)"),
     "gather-kruskal-4095": ("gather", "kruskal", 4095, None, "bfs-gather on configs[1]'s maze"),
     "hunt-kruskal-4095": ("hunt", "kruskal", 4095, None, "bfs-hunt (configs[0]'s game) on configs[1]'s maze; the winner's path is walked and repainted"),
     "hunt-wilson-4095": ("hunt", "wilson", 4095, None, "bfs-hunt on configs[4]'s builder at 4095"),
@@ -118,7 +119,7 @@ def make_case(lab, workload: str, seed_offset: int = 0, bands: int = 1):
     game, builder, n, mod, _ = WORKLOADS[workload]
     rows = n if bands == 1 else ((n + 63) // 64) * 64 * bands - 1
     pillar = mod == "pillar"  # (bench only) one wall square in the arena: no longer an open room, the tile wave runs
-    maze = lab.build_maze(builder, rows, n, seed=SEED + 2 + seed_offset, mod=None if pillar else mod)
+    maze = lab.cached_maze(builder, rows, n, seed=SEED + 2 + seed_offset, mod=None if pillar else mod)
     if pillar:
         maze[rows // 4, n // 4] &= ~np.uint16(lab.PATH_BIT)
     spec = {"game": game, "rows": rows, "cols": n}

@@ -97,6 +97,7 @@ struct Control {
     // distance map on a tree: the fix-up has set the measure bit on every square it gave a level (n_marked of them),
     // measure_body only adds the count
     uint32_t measured;
+    uint32_t spec_mark; // Square bits pack_body set speculatively on every passable square (see measure_body)
     unsigned long long n_marked;
     uint32_t room;
     int32_t room_r0, room_r1, room_c0, room_c1, room_sr, room_sc; // (row bands: relative to the band, see room.cuh)
@@ -175,7 +176,11 @@ LAB_DEV uint32_t pack_mask8(lab_u32x4 v, uint32_t mask2, uint32_t value2) {
     return m;
 }
 
-LAB_DEV void pack_body(Geom g, uint16_t const *grid, uint64_t *path, uint16_t mask, uint16_t value,
+// mark != 0 (the distance map on a maze that may be a lattice, device/lattice.cuh): the squares that pass also get
+// `mark` ORed in on the way -- the measure bit of painters/distance.cc:138,149, set SPECULATIVELY for every passable
+// square while the grid is being read anyway.  One tree: every passable square is reached and the bits are final;
+// otherwise measure_body clears them again on the squares the search did not reach.
+LAB_DEV void pack_body(Geom g, uint16_t *grid, uint64_t *path, uint16_t mask, uint16_t value, uint16_t mark,
                        long long gwarp, long long nwarps, int lane) {
     constexpr int U = 4; // steps whose loads are in flight together (2 KB per warp)
     int const rows_pad = g.tiles_y * TS;
@@ -192,11 +197,16 @@ LAB_DEV void pack_body(Geom g, uint16_t const *grid, uint64_t *path, uint16_t ma
             continue;
         }
         unsigned long long const row0 = static_cast<unsigned long long>(r) * static_cast<unsigned long long>(g.cols);
-        uint16_t const *row = grid + row0;
+        uint16_t *row = grid + row0;
         int a = static_cast<int>(((16u - (reinterpret_cast<uintptr_t>(row) & 15u)) & 15u) >> 1); // squares before the boundary
         a = a < g.cols ? a : g.cols;
         // head: bits [0, a) of word 0, parked in the top bits of the carry
-        uint32_t const head = lab_ballot(lane < a && (lab_ld_ro(row + (lane < a ? lane : 0)) & mask) == value);
+        uint16_t const hsq = lab_ld_ro(row + (lane < a ? lane : 0));
+        bool const hpass = lane < a && (hsq & mask) == value;
+        if (mark && hpass) {
+            row[lane] = static_cast<uint16_t>(hsq | mark);
+        }
+        uint32_t const head = lab_ballot(hpass);
         uint64_t carry = a ? static_cast<uint64_t>(head) << (64 - a) : 0ull;
         for (int s0 = 0; s0 < nsteps; s0 += U) {
             lab_u32x4 v[U];
@@ -209,7 +219,7 @@ LAB_DEV void pack_body(Geom g, uint16_t const *grid, uint64_t *path, uint16_t ma
                 v[u] = lab_u32x4{~value2, ~value2, ~value2, ~value2};
                 if (left > 0) {
                     if (row0 + static_cast<unsigned long long>(c) + 8ull <= total) { // (may run into the next row: masked below)
-                        v[u] = lab_ld_ro_v4(row + c);
+                        v[u] = lab_ld_stream_v4(row + c); // (read once; not the read-only path: pack may write the squares back)
                     } else { // the last few squares of the grid
                         uint32_t w[4] = {~value2, ~value2, ~value2, ~value2};
                         for (int k = 0; k < left && k < 8; k++) {
@@ -223,6 +233,24 @@ LAB_DEV void pack_body(Geom g, uint16_t const *grid, uint64_t *path, uint16_t ma
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 uint32_t x = pack_mask8(v[u], mask2, value2) & valid[u];
+                if (mark && x) {
+                    int const c = a + 256 * (s0 + u) + 8 * lane;
+                    if (valid[u] == 0xFFu && row0 + static_cast<unsigned long long>(c) + 8ull <= total) { // the whole vector is this row's
+                        uint32_t const m2 = static_cast<uint32_t>(mark);
+                        lab_u32x4 o = v[u];
+                        o.x |= ((x & 1u) ? m2 : 0u) | ((x & 2u) ? m2 << 16 : 0u);
+                        o.y |= ((x & 4u) ? m2 : 0u) | ((x & 8u) ? m2 << 16 : 0u);
+                        o.z |= ((x & 16u) ? m2 : 0u) | ((x & 32u) ? m2 << 16 : 0u);
+                        o.w |= ((x & 64u) ? m2 : 0u) | ((x & 128u) ? m2 << 16 : 0u);
+                        lab_st_v4(row + c, o);
+                    } else { // the row's last few squares
+                        for (int k = 0; k < 8; k++) {
+                            if ((x >> k) & 1u) {
+                                row[c + k] = static_cast<uint16_t>(row[c + k] | mark);
+                            }
+                        }
+                    }
+                }
                 x |= lab_shfl_down(x, 1) << 8;
                 x |= lab_shfl_down(x, 2) << 16;
                 uint32_t const hi = lab_shfl_down(x, 4);

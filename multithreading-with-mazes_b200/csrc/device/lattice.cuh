@@ -1,0 +1,800 @@
+// lattice.cuh -- the reference builders' perfect mazes as what they are: a spanning tree of a CELL LATTICE.
+//
+// Every builder of the reference without a -m modification (kruskal, wilson, rdfs, ...; builders/*.cc) carves a
+// perfect maze on the lattice of its odd squares: cells at (odd, odd), a passage square between two
+// neighbouring cells at (odd, even) / (even, odd), (even, even) squares always wall.  The
+// spanning-tree pipeline of tree.cuh takes any tree of squares and pays for that with divergent, square-by-square
+// walks (12 of 32 lanes busy, profiles/r01b_*).  On the lattice a 64x64-square tile is a 32x32 CELL board that
+// fits one 32-bit word per lane, and everything a tile has to do becomes a few warp-wide bit operations:
+//
+//   1 link    components of a tile by bit-board flood fill (one step = 2 shifts, 2 shuffles, 6 logic ops for
+//             all 1024 cells).  The tree is planar, so the Euler tour that enters a component through one
+//             border crossing leaves it through the NEXT crossing of the same component clockwise around the
+//             tile: no wall following at all, the tour's successor pointers come from the labels of the <= 128
+//             crossing slots (match_any).
+//   2 rank    hops to the end of the tour for every crossing arc, hierarchically: inside a super-tile of
+//             LST x LST tiles by in-place pointer jumping in shared memory (one warp, single-word (pointer,
+//             hops) entries, so any interleaving of reads and writes is valid and no barrier is needed), then
+//             over the super-tiles' border arcs only (1/LST of all arcs, L2 resident) by the same barrier-free
+//             in-place jumping in global memory, then one gather per arc.
+//   3 flood   of the two arcs of a crossing the one met first on the tour leads away from the root: every
+//             component knows its entry crossing.  One multi-source bit-board BFS per tile from all entry cells
+//             gives every cell its depth below its component's entry, recorded bit-sliced (10 planes).  The
+//             depth of a crossing cell + 1 is the weight of the tour's arc through it: +w going down, -w coming
+//             back, scattered to the arcs' tour positions.
+//   4 scan    an ordinary prefix sum over the tour positions: the depth of every component's entry.  (The second
+//             pointer jumping of tree.cuh is gone: the ranks of phase 2 sort the list.)
+//   5 levels  level of a cell = 2 * (entry depth + local depth); of a passage = the deeper of its two cells - 1.
+//             Written once, whole rows of the tile, from registers.
+//
+// Checked, not assumed: the lattice shape (pillars are walls, a passage has both its cells), E == V - 1
+// (tree_count_body), every arc reaches the end of the tour, the floods reach all V squares.  If anything fails
+// nothing has been written to the level field and the general pipeline (tree.cuh), then the tile wave
+// (engine.cuh), take over.  Results are bit-identical on all three roads (tests/test_lattice.py).
+#pragma once
+#include "tree.cuh"
+
+namespace lab {
+
+constexpr int LC = 32;             // cells per tile side
+constexpr uint32_t LSLOTS = 128;   // crossing slots of a tile: side * 32 + index, sides CLOCKWISE
+enum Lside : uint32_t { L_N = 0, L_E = 1, L_S = 2, L_W = 3 }; // index = cell column (N, S) / cell row (E, W)
+constexpr uint32_t L_END = 0xFFFFFFFEu, L_NONE = 0xFFFFFFFFu;
+constexpr int LST = 4;                                  // super-tile side, tiles
+constexpr uint32_t LB = 4u * LST * LC;                  // border slots of a super-tile
+constexpr uint32_t LSUP_SLOTS = LST * LST * LSLOTS;     // slots of a super-tile (8192: 13-bit local index)
+constexpr int L_LABEL_PLANES = 7, L_DEPTH_PLANES = 10;
+constexpr uint32_t L_CHUNK = 1024;                      // tour positions per scan chunk
+
+struct Lattice {
+    uint32_t *mask;   // [ntiles][3][32]  cell boards in COLUMN layout (lane = cell column, bit = cell row): cells, W passage open, N passage open
+    uint32_t *xmask;  // [ntiles][4]      open crossings per side (bit = index)
+    uint32_t *next;   // [ntiles][128]    the arc the tour continues with after entering through this slot (global arc id), L_END, L_NONE
+    uint8_t *label;   // [ntiles][128]    component of the slot's cell
+    uint32_t *lplane; // [ntiles][7][32]  component label of every cell, bit-sliced
+    uint64_t *xd;     // [ntiles][128]    after the local ranking: (dense border slot the chain leaves the super-tile to | hops to there << 32)
+    uint64_t *gb;     // [nsuper][LB]     the border arcs' list: (next dense border slot | hops << 32), jumped in place
+    uint32_t *R;      // [ntiles][128]    hops to the end of the tour (>= 1; larger = earlier)
+    uint32_t *dplane; // [ntiles][10][32] local depth of every cell, bit-sliced
+    uint32_t *emask;  // [ntiles][4]      slots that are their component's entry
+    uint32_t *wsum;   // [nslots + 2]     arc weights by R, then their inclusive prefix sums per chunk
+    uint32_t *chunk;  // [nslots / L_CHUNK + 2] exclusive prefix of the chunk totals
+    Tree_ctl *tc;
+    int sup_y, sup_x, nsuper;
+    uint32_t nslots; // ntiles * 128
+};
+
+LAB_DEV bool lat_live(Tree_ctl const *tc) { return tc->ok != 0 && tc->lat_on != 0 && tc->lat_err == 0; }
+
+// bits 0, 2, 4, ... of a 64-bit word, packed
+LAB_DEV uint32_t lat_even16(uint32_t x) {
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+LAB_DEV uint32_t lat_even(uint64_t x) { return lat_even16(static_cast<uint32_t>(x)) | (lat_even16(static_cast<uint32_t>(x >> 32)) << 16); }
+LAB_DEV uint32_t lat_odd(uint64_t x) { return lat_even(x >> 1); }
+
+// 32 x 32 bit matrix, one row per lane -> one column per lane
+LAB_DEV uint32_t lat_transpose(uint32_t x, int lane) {
+    uint32_t const m[5] = {0x0000FFFFu, 0x00FF00FFu, 0x0F0F0F0Fu, 0x33333333u, 0x55555555u};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        int const s = 16 >> k;
+        uint32_t const y = lab_shfl(x, lane ^ s);
+        x = (lane & s) ? ((x & ~m[k]) | ((y & ~m[k]) >> s)) : ((x & m[k]) | ((y & m[k]) << s));
+    }
+    return x;
+}
+
+// the arc entering the neighbouring tile through the same crossing
+LAB_DEV uint32_t lat_twin(Geom const &g, uint32_t t, uint32_t slot) {
+    uint32_t const side = slot >> 5, idx = slot & 31u;
+    switch (side) {
+    case L_N: return (t - static_cast<uint32_t>(g.tiles_x)) * LSLOTS + L_S * LC + idx;
+    case L_S: return (t + static_cast<uint32_t>(g.tiles_x)) * LSLOTS + L_N * LC + idx;
+    case L_W: return (t - 1u) * LSLOTS + L_E * LC + idx;
+    default: return (t + 1u) * LSLOTS + L_W * LC + idx;
+    }
+}
+
+// A tile's boards in column layout and the step masks of the bit-board BFS.
+struct Lat_tile {
+    uint32_t C, Wo, No;         // cells / W passage of the cell open / N passage of the cell open
+    uint32_t XN, XE, XS, XW;    // open crossings (uniform)
+    uint32_t mS, mN, mE, mW;    // a frontier bit may move south / north / east / west INTO these cells
+};
+LAB_DEV void lat_step_masks(Lat_tile &T, int lane) {
+    T.mS = T.No & ~1u;                                   // into row i from row i-1: the N passage of (i, j); bit 0 is a crossing
+    T.mN = T.No >> 1;                                    // into row i-1 from row i
+    T.mE = lane ? T.Wo : 0u;                             // into column j from column j-1: the W passage of (i, j); lane 0: crossings
+    uint32_t const right = lab_shfl_down(T.Wo, 1);
+    T.mW = lane < 31 ? right : 0u;                       // into column j from column j+1
+}
+LAB_DEV Lat_tile lat_load(Lattice const &lt, long long t, int lane) {
+    Lat_tile T;
+    uint32_t const *m = lt.mask + t * 96;
+    T.C = lab_ld_ro(m + lane);
+    T.Wo = lab_ld_ro(m + 32 + lane);
+    T.No = lab_ld_ro(m + 64 + lane);
+    uint32_t const *x = lt.xmask + t * 4;
+    T.XN = lab_ld_ro(x + L_N);
+    T.XE = lab_ld_ro(x + L_E);
+    T.XS = lab_ld_ro(x + L_S);
+    T.XW = lab_ld_ro(x + L_W);
+    lat_step_masks(T, lane);
+    return T;
+}
+// one level of the bit-board BFS: F = the cells reached now, V = every cell reached so far
+LAB_DEV void lat_step(Lat_tile const &T, uint32_t &F, uint32_t &V) {
+    uint32_t const west = lab_shfl_up(F, 1), east = lab_shfl_down(F, 1);
+    uint32_t a = (F << 1) & T.mS;
+    a |= (F >> 1) & T.mN;
+    a |= west & T.mE;
+    a |= east & T.mW;
+    F = a & ~V;
+    V |= F;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1 link.  Warp per tile.  sm: 128 words of shared memory per warp.
+LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int lane, uint32_t *sm, uint32_t &arcs) {
+    Geom const &g = p.g;
+    Tree_ctl *tc = lt.tc;
+    uint64_t const P0 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + 2 * lane), P1 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + 2 * lane + 1);
+    Lat_tile T;
+    T.XN = lat_odd(lab_ld_ro(p.cross + static_cast<long long>(t) * 4 + SIDE_N));
+    T.XE = lat_odd(lab_ld_ro(p.cross + static_cast<long long>(t) * 4 + SIDE_E));
+    T.XS = lat_odd(lab_ld_ro(p.cross + static_cast<long long>(t) * 4 + SIDE_S));
+    T.XW = lat_odd(lab_ld_ro(p.cross + static_cast<long long>(t) * 4 + SIDE_W));
+    {
+        // row layout first (lane = cell row i): the lattice's shape
+        uint32_t const rc = lat_odd(P1), rw = lat_even(P1), rn = lat_odd(P0), pillars = lat_even(P0);
+        uint32_t const above = lab_shfl_up(rc, 1);
+        bool bad = pillars != 0;
+        bad |= (rw & ~rc) != 0 || (rw & ~((rc << 1) | ((T.XW >> lane) & 1u))) != 0;          // a W passage has its cell and the cell to the left
+        bad |= (rn & ~rc) != 0 || (rn & ~(lane ? above : T.XN)) != 0;                          // an N passage has its cell and the cell above
+        if (lab_any(bad)) {
+            if (lane == 0 && lab_ld_ro(&tc->lat_err) == 0u) {
+                lab_st_volatile(&tc->lat_err, 1u);
+            }
+            return;
+        }
+        T.C = lat_transpose(rc, lane);
+        T.Wo = lat_transpose(rw, lane);
+        T.No = lat_transpose(rn, lane);
+    }
+    lat_step_masks(T, lane);
+    {
+        uint32_t *m = lt.mask + static_cast<long long>(t) * 96;
+        m[lane] = T.C;
+        m[32 + lane] = T.Wo;
+        m[64 + lane] = T.No;
+        if (lane < 4) {
+            lt.xmask[static_cast<long long>(t) * 4 + lane] = lane == L_N ? T.XN : (lane == L_E ? T.XE : (lane == L_S ? T.XS : T.XW));
+        }
+    }
+    arcs += lane == 0 ? static_cast<uint32_t>(lab_popc64(T.XN) + lab_popc64(T.XE) + lab_popc64(T.XS) + lab_popc64(T.XW)) : 0u;
+
+    // ---- components, one flood fill each, seeded from the crossing cells not reached yet ----
+    bool const root_tile = p.ctl->src_tile[0] == t;
+    int const rr = root_tile ? static_cast<int>(p.ctl->src_rc[0] >> 8) >> 1 : 0, rcol = root_tile ? static_cast<int>(p.ctl->src_rc[0] & 0xFFu) >> 1 : 0;
+    uint32_t U = ((T.XN >> lane) & 1u) | (((T.XS >> lane) & 1u) << 31) | (lane == 0 ? T.XW : 0u) | (lane == 31 ? T.XE : 0u);
+    uint32_t labs[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu}; // of slots (side, lane)
+    uint32_t L[L_LABEL_PLANES];
+#pragma unroll
+    for (int q = 0; q < L_LABEL_PLANES; q++) {
+        L[q] = 0;
+    }
+    uint32_t k = 0, root_label = 0xFFu;
+    bool root_pending = root_tile;
+    for (;;) {
+        uint32_t const b = lab_ballot(U != 0);
+        uint32_t F;
+        if (b) {
+            int const l0 = lab_ffs32(b) - 1;
+            F = lane == l0 ? (U & (0u - U)) : 0u;
+        } else if (root_pending) { // the root's component has no crossing (a maze inside one tile)
+            F = lane == rcol ? (1u << rr) : 0u;
+        } else {
+            break;
+        }
+        if (k >= LSLOTS - 1u) { // more components than crossings: cannot be
+            if (lane == 0) lab_st_volatile(&tc->lat_err, 2u);
+            return;
+        }
+        uint32_t M = F;
+        for (int it = 0; it < LC * LC / 4 + 1; it++) {
+            lat_step(T, F, M);
+            lat_step(T, F, M);
+            lat_step(T, F, M);
+            lat_step(T, F, M);
+            if (!lab_any(F != 0)) {
+                break;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < L_LABEL_PLANES; q++) {
+            if ((k >> q) & 1u) {
+                L[q] |= M;
+            }
+        }
+        uint32_t const west = lab_shfl(M, 0) & T.XW, east = lab_shfl(M, 31) & T.XE;
+        if (M & 1u & (T.XN >> lane)) labs[L_N] = k;
+        if ((M >> 31) & (T.XS >> lane) & 1u) labs[L_S] = k;
+        if ((west >> lane) & 1u) labs[L_W] = k;
+        if ((east >> lane) & 1u) labs[L_E] = k;
+        if (root_pending && ((lab_shfl(M, rcol) >> rr) & 1u)) {
+            root_label = k;
+            root_pending = false;
+        }
+        U &= ~M;
+        k++;
+    }
+    if (root_tile && lane == 0) {
+        lab_st_volatile(&tc->lat_root_label, root_label);
+    }
+    {
+        uint32_t *pl = lt.lplane + static_cast<long long>(t) * (L_LABEL_PLANES * 32);
+#pragma unroll
+        for (int q = 0; q < L_LABEL_PLANES; q++) {
+            pl[q * 32 + lane] = L[q];
+        }
+    }
+    // ---- the tour: from a slot to the next slot of the same component, clockwise (N ->, E down, S <-, W up) ----
+    // sm[side * 32 + (label / 4)] bytes: first slot index of the label on that side in clockwise order (0xFF: none)
+    uint8_t *first = reinterpret_cast<uint8_t *>(sm);
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        sm[s * 32 + lane] = 0xFFFFFFFFu;
+    }
+    lab_syncwarp();
+    uint32_t peers[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        peers[s] = lab_match_any(labs[s]);
+        if (labs[s] != 0xFFu) {
+            bool const ascending = s == L_N || s == L_E;
+            int const lead = ascending ? lab_ffs32(peers[s]) - 1 : 31 - lab_clz32(peers[s]);
+            if (lead == lane) {
+                first[s * 128 + labs[s]] = static_cast<uint8_t>(lane);
+            }
+        }
+    }
+    lab_syncwarp();
+    uint32_t root_first = L_NONE; // the root component's first slot clockwise: the tour is cut there
+    if (root_tile && root_label != 0xFFu) {
+        for (int s = 3; s >= 0; s--) {
+            uint32_t const f = first[s * 128 + root_label];
+            if (f != 0xFFu) root_first = static_cast<uint32_t>(s) * LC + f;
+        }
+    }
+    uint32_t const gt = t;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        uint32_t out = L_NONE;
+        uint32_t const lab = labs[s];
+        if (lab != 0xFFu) {
+            bool const ascending = s == L_N || s == L_E;
+            uint32_t const rest = ascending ? (peers[s] & ~((2u << lane) - 1u)) : (peers[s] & ((1u << lane) - 1u));
+            uint32_t nslot;
+            if (rest) {
+                nslot = static_cast<uint32_t>(s) * LC + static_cast<uint32_t>(ascending ? lab_ffs32(rest) - 1 : 31 - lab_clz32(rest));
+            } else {
+                nslot = L_NONE;
+#pragma unroll
+                for (int d = 1; d <= 4; d++) {
+                    int const s2 = (s + d) & 3;
+                    uint32_t const f = first[s2 * 128 + lab];
+                    if (nslot == L_NONE && f != 0xFFu) {
+                        nslot = static_cast<uint32_t>(s2) * LC + f;
+                    }
+                }
+            }
+            uint32_t const me = static_cast<uint32_t>(s) * LC + static_cast<uint32_t>(lane);
+            out = me == root_first ? L_END : lat_twin(g, gt, nslot);
+        }
+        lt.next[static_cast<long long>(t) * LSLOTS + s * LC + lane] = out;
+        lt.label[static_cast<long long>(t) * LSLOTS + s * LC + lane] = static_cast<uint8_t>(lab);
+    }
+    lab_syncwarp();
+}
+
+LAB_DEV void lat_link_body(Params const &p, Lattice const &lt, int lane, uint32_t *sm) {
+    if (!lat_live(lt.tc)) {
+        return;
+    }
+    uint32_t arcs = 0;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) {
+            t = lab_atomic_add(&lt.tc->lat_ticket[0], 1u);
+        }
+        t = lab_shfl(t, 0);
+        if (t >= static_cast<uint32_t>(p.g.ntiles)) {
+            break;
+        }
+        lat_link_tile(p, lt, t, lane, sm, arcs);
+    }
+    if (lane == 0 && arcs) {
+        lab_atomic_add(&lt.tc->n_arcs, arcs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2a local ranking.  Warp per super-tile; sm: LSUP_SLOTS words.  Entry: bit 31 = the chain has left the
+// super-tile (then bits 0-12 = the LAST slot inside), else bits 0-12 = a slot further along; bits 13-30 = hops.
+// One word per entry, read and written whole: whatever mix of old and new entries a lane sees, "slot a
+// reaches slot x in d hops" stays true, so the jumping runs in place with no barrier between rounds.
+constexpr uint32_t LX_OUT = 0x80000000u, LX_IDX = 0x1FFFu;
+LAB_DEV uint32_t lat_dense_border(Lattice const &lt, Geom const &g, uint32_t arc) { // arc: an inbound border slot of its super-tile
+    uint32_t const t = arc / LSLOTS, slot = arc % LSLOTS, side = slot >> 5, idx = slot & 31u;
+    uint32_t const ty = t / static_cast<uint32_t>(g.tiles_x), tx = t % static_cast<uint32_t>(g.tiles_x);
+    uint32_t const S = (ty / LST) * static_cast<uint32_t>(lt.sup_x) + tx / LST;
+    uint32_t const along = (side == L_N || side == L_S) ? tx % LST : ty % LST;
+    return S * LB + side * (LST * LC) + along * LC + idx;
+}
+LAB_DEV void lat_rank_local_super(Params const &p, Lattice const &lt, uint32_t S, int lane, uint32_t *sm) {
+    Geom const &g = p.g;
+    uint32_t const sy0 = (S / static_cast<uint32_t>(lt.sup_x)) * LST, sx0 = (S % static_cast<uint32_t>(lt.sup_x)) * LST;
+    for (uint32_t i = static_cast<uint32_t>(lane); i < LSUP_SLOTS; i += 32u) {
+        uint32_t const lt_y = i / (LST * LSLOTS), lt_x = (i / LSLOTS) % LST, slot = i % LSLOTS;
+        uint32_t const ty = sy0 + lt_y, tx = sx0 + lt_x;
+        uint32_t e = LX_OUT | i;
+        if (ty < static_cast<uint32_t>(g.tiles_y) && tx < static_cast<uint32_t>(g.tiles_x)) {
+            uint32_t const nx = lab_ld_cg(lt.next + (static_cast<long long>(ty) * g.tiles_x + tx) * LSLOTS + slot);
+            if (nx < L_END) {
+                uint32_t const nt = nx / LSLOTS, ny = nt / static_cast<uint32_t>(g.tiles_x), nxx = nt % static_cast<uint32_t>(g.tiles_x);
+                if (ny - sy0 < static_cast<uint32_t>(LST) && nxx - sx0 < static_cast<uint32_t>(LST)) {
+                    e = (((ny - sy0) * LST + (nxx - sx0)) * LSLOTS + nx % LSLOTS) | (1u << 13);
+                }
+            }
+        }
+        sm[i] = e;
+    }
+    lab_syncwarp();
+    bool pending = true;
+    for (int pass = 0; pass < 40 && pending; pass++) {
+        bool mine = false;
+        for (uint32_t i = static_cast<uint32_t>(lane); i < LSUP_SLOTS; i += 32u) {
+            uint32_t const e = sm[i];
+            if (!(e & LX_OUT)) {
+                uint32_t const e2 = sm[e & LX_IDX];
+                uint32_t const ne = (e2 & (LX_OUT | LX_IDX)) | ((e & ~(LX_OUT | LX_IDX)) + (e2 & ~(LX_OUT | LX_IDX)));
+                sm[i] = ne;
+                mine |= !(ne & LX_OUT);
+            }
+        }
+        pending = lab_any(mine);
+    }
+    if (pending) { // a chain that never leaves: a cycle, not a tree
+        if (lane == 0) lab_st_volatile(&lt.tc->lat_err, 3u);
+    }
+    lab_syncwarp();
+    for (uint32_t i = static_cast<uint32_t>(lane); i < LSUP_SLOTS; i += 32u) {
+        uint32_t const lt_y = i / (LST * LSLOTS), lt_x = (i / LSLOTS) % LST, slot = i % LSLOTS, side = slot >> 5;
+        uint32_t const ty = sy0 + lt_y, tx = sx0 + lt_x;
+        bool const present = ty < static_cast<uint32_t>(g.tiles_y) && tx < static_cast<uint32_t>(g.tiles_x);
+        uint64_t pair = 0xFFFFFFFFull; // (no arc: the end, 0 hops)
+        bool open = false;
+        if (present) {
+            long long const a = (static_cast<long long>(ty) * g.tiles_x + tx) * LSLOTS + slot;
+            open = lab_ld_cg(lt.next + a) != L_NONE;
+            if (open) {
+                uint32_t const e = sm[i];
+                uint32_t const last = e & LX_IDX, hops = ((e & ~LX_OUT) >> 13) + 1u;
+                uint32_t const ly = last / (LST * LSLOTS), lx = (last / LSLOTS) % LST;
+                uint32_t const nx = lab_ld_cg(lt.next + (static_cast<long long>(sy0 + ly) * g.tiles_x + sx0 + lx) * LSLOTS + last % LSLOTS);
+                uint32_t const dense = (nx >= L_END || !(e & LX_OUT)) ? 0xFFFFFFFFu : lat_dense_border(lt, g, nx);
+                pair = static_cast<uint64_t>(dense) | (static_cast<uint64_t>(hops) << 32);
+                lab_st_cg(lt.xd + a, pair);
+            }
+        }
+        bool const border = (side == L_N && lt_y == 0) || (side == L_S && lt_y == LST - 1) || (side == L_W && lt_x == 0) || (side == L_E && lt_x == LST - 1);
+        if (border) {
+            uint32_t const along = (side == L_N || side == L_S) ? lt_x : lt_y;
+            lab_st_cg(lt.gb + static_cast<long long>(S) * LB + side * (LST * LC) + along * LC + (slot & 31u), open ? pair : 0xFFFFFFFFull);
+        }
+    }
+    lab_syncwarp();
+}
+LAB_DEV void lat_rank_local_body(Params const &p, Lattice const &lt, int lane, uint32_t *sm) {
+    if (!lat_live(lt.tc)) {
+        return;
+    }
+    for (;;) {
+        uint32_t S = 0;
+        if (lane == 0) {
+            S = lab_atomic_add(&lt.tc->lat_ticket[1], 1u);
+        }
+        S = lab_shfl(S, 0);
+        if (S >= static_cast<uint32_t>(lt.nsuper)) {
+            break;
+        }
+        lat_rank_local_super(p, lt, S, lane, sm);
+    }
+}
+
+// 2b the border arcs.  In place, no barrier: an entry is one 8-byte word, so a thread that reads another thread's
+// entry sees SOME true statement "slot reaches x in d hops", old or new, and its own stays true.
+LAB_DEV void lat_rank_global_body(Lattice const &lt, long long gthread, long long nthreads) {
+    Tree_ctl *tc = lt.tc;
+    if (!lat_live(tc)) {
+        return;
+    }
+    long long const n = static_cast<long long>(lt.nsuper) * LB;
+    uint32_t const limit = lt.nslots + 2u;
+    for (int pass = 0; pass < (1 << 20); pass++) { // (a cycle ends through `limit`, not through the pass count)
+        bool pending = false;
+        for (long long i = gthread; i < n; i += nthreads) {
+            uint64_t e = lab_ld_cg(lt.gb + i);
+            uint32_t x = static_cast<uint32_t>(e), d = static_cast<uint32_t>(e >> 32);
+            if (x == 0xFFFFFFFFu) {
+                continue;
+            }
+            for (int hop = 0; hop < 6 && x != 0xFFFFFFFFu; hop++) {
+                uint64_t const e2 = lab_ld_cg(lt.gb + x);
+                x = static_cast<uint32_t>(e2);
+                d += static_cast<uint32_t>(e2 >> 32);
+            }
+            if (d > limit) { // longer than the tour can be: a cycle
+                lab_st_volatile(&tc->lat_err, 3u);
+                return;
+            }
+            lab_st_cg(lt.gb + i, static_cast<uint64_t>(x) | (static_cast<uint64_t>(d) << 32));
+            pending |= x != 0xFFFFFFFFu;
+        }
+        if (!pending) {
+            return;
+        }
+        if (lab_ld_volatile(&tc->lat_err)) {
+            return;
+        }
+    }
+    lab_st_volatile(&tc->lat_err, 3u);
+}
+
+// 2c every arc: its own hops to the border + the border arc's hops to the end
+LAB_DEV void lat_rank_expand_body(Lattice const &lt, long long gthread, long long nthreads) {
+    Tree_ctl *tc = lt.tc;
+    if (!lat_live(tc)) {
+        return;
+    }
+    bool bad = false;
+    for (long long a = gthread; a < static_cast<long long>(lt.nslots); a += nthreads) {
+        uint32_t r = 0;
+        if (lab_ld_cg(lt.next + a) != L_NONE) {
+            uint64_t const e = lab_ld_cg(lt.xd + a);
+            uint32_t const x = static_cast<uint32_t>(e);
+            r = static_cast<uint32_t>(e >> 32);
+            if (x != 0xFFFFFFFFu) {
+                uint64_t const b = lab_ld_cg(lt.gb + x);
+                bad |= static_cast<uint32_t>(b) != 0xFFFFFFFFu;
+                r += static_cast<uint32_t>(b >> 32);
+            }
+        }
+        lt.R[a] = r;
+    }
+    if (bad) {
+        lab_st_volatile(&tc->lat_err, 3u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3 flood.  Warp per tile.  Entry slots (the arc into the tile is met before its twin), one BFS from all entry
+// cells, local depths bit-sliced, the weights of the arcs through the tile's other crossings.
+LAB_DEV uint32_t lat_plane_value(uint32_t const (&D)[L_DEPTH_PLANES], int bit) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int q = 0; q < L_DEPTH_PLANES; q++) {
+        v |= ((D[q] >> bit) & 1u) << q;
+    }
+    return v;
+}
+template <int U> LAB_DEV void lat_depth_step(Lat_tile const &T, uint32_t &F, uint32_t &V, uint32_t &G, uint32_t (&D)[L_DEPTH_PLANES]) {
+    lat_step(T, F, V);
+    G |= F;
+    if (U & 1) D[0] |= F;
+    if (U & 2) D[1] |= F;
+    if (U & 4) D[2] |= F;
+}
+LAB_DEV void lat_flood_tile(Params const &p, Lattice const &lt, uint32_t t, int lane, unsigned long long &settled, uint32_t &bad) {
+    Geom const &g = p.g;
+    Lat_tile const T = lat_load(lt, t, lane);
+    uint32_t const X[4] = {T.XN, T.XE, T.XS, T.XW};
+    long long const base = static_cast<long long>(t) * LSLOTS;
+    uint32_t Ro[4], Rt[4];
+    bool open[4], entry[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        open[s] = (X[s] >> lane) & 1u;
+        Ro[s] = open[s] ? lab_ld_cg(lt.R + base + s * LC + lane) : 0u;
+        Rt[s] = open[s] ? lab_ld_cg(lt.R + lat_twin(g, t, static_cast<uint32_t>(s * LC + lane))) : 0u;
+        entry[s] = open[s] && Ro[s] > Rt[s];
+        bad |= (open[s] && (Ro[s] == Rt[s] || Ro[s] == 0u || Rt[s] == 0u)) ? 1u : 0u;
+    }
+    uint32_t const eW = lab_ballot(entry[L_W]), eE = lab_ballot(entry[L_E]), eN = lab_ballot(entry[L_N]), eS = lab_ballot(entry[L_S]);
+    if (lane < 4) {
+        lt.emask[static_cast<long long>(t) * 4 + lane] = lane == L_N ? eN : (lane == L_E ? eE : (lane == L_S ? eS : eW));
+    }
+    uint32_t F = (entry[L_N] ? 1u : 0u) | (entry[L_S] ? 0x80000000u : 0u) | (lane == 0 ? eW : 0u) | (lane == 31 ? eE : 0u);
+    if (p.ctl->src_tile[0] == t) {
+        int const rr = static_cast<int>(p.ctl->src_rc[0] >> 8) >> 1, rcol = static_cast<int>(p.ctl->src_rc[0] & 0xFFu) >> 1;
+        if (lane == rcol) F |= 1u << rr;
+    }
+    uint32_t V = F, G = 0;
+    uint32_t D[L_DEPTH_PLANES];
+#pragma unroll
+    for (int q = 0; q < L_DEPTH_PLANES; q++) {
+        D[q] = 0;
+    }
+    // depth = 8 * group + u: the seeds are (0, 0); the low three planes come from the unrolled position
+    lat_depth_step<1>(T, F, V, G, D);
+    lat_depth_step<2>(T, F, V, G, D);
+    lat_depth_step<3>(T, F, V, G, D);
+    lat_depth_step<4>(T, F, V, G, D);
+    lat_depth_step<5>(T, F, V, G, D);
+    lat_depth_step<6>(T, F, V, G, D);
+    lat_depth_step<7>(T, F, V, G, D);
+    for (uint32_t grp = 1; grp < 128u && lab_any(F != 0); grp++) {
+        G = 0;
+        lat_depth_step<0>(T, F, V, G, D);
+        lat_depth_step<1>(T, F, V, G, D);
+        lat_depth_step<2>(T, F, V, G, D);
+        lat_depth_step<3>(T, F, V, G, D);
+        lat_depth_step<4>(T, F, V, G, D);
+        lat_depth_step<5>(T, F, V, G, D);
+        lat_depth_step<6>(T, F, V, G, D);
+        lat_depth_step<7>(T, F, V, G, D);
+#pragma unroll
+        for (int q = 3; q < L_DEPTH_PLANES; q++) {
+            if ((grp >> (q - 3)) & 1u) {
+                D[q] |= G;
+            }
+        }
+    }
+    {
+        uint32_t *pl = lt.dplane + static_cast<long long>(t) * (L_DEPTH_PLANES * 32);
+#pragma unroll
+        for (int q = 0; q < L_DEPTH_PLANES; q++) {
+            pl[q * 32 + lane] = D[q];
+        }
+    }
+    // every cell reached <=> all the tile's passable squares have a level coming
+    bad |= (V != T.C) ? 2u : 0u;
+    settled += static_cast<unsigned>(lab_popc64(V) + lab_popc64(T.Wo) + lab_popc64(T.No));
+    // weights: through a crossing that is not an entry the tour goes DOWN into the neighbour (+w on the twin arc)
+    // and comes back UP (-w on this slot's arc); w = depth of the cell at the crossing + 1
+    uint32_t DW[L_DEPTH_PLANES], DE[L_DEPTH_PLANES];
+#pragma unroll
+    for (int q = 0; q < L_DEPTH_PLANES; q++) {
+        DW[q] = lab_shfl(D[q], 0);
+        DE[q] = lab_shfl(D[q], 31);
+    }
+    uint32_t const ld[4] = {lat_plane_value(D, 0), lat_plane_value(DE, lane), lat_plane_value(D, 31), lat_plane_value(DW, lane)};
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        if (open[s] && !entry[s]) {
+            uint32_t const w = ld[s] + 1u;
+            lt.wsum[Rt[s]] = w;
+            lt.wsum[Ro[s]] = 0u - w;
+        }
+    }
+}
+LAB_DEV void lat_flood_body(Params const &p, Lattice const &lt, int lane) {
+    Tree_ctl *tc = lt.tc;
+    if (!lat_live(tc)) {
+        return;
+    }
+    unsigned long long settled = 0;
+    uint32_t bad = 0;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) {
+            t = lab_atomic_add(&tc->lat_ticket[2], 1u);
+        }
+        t = lab_shfl(t, 0);
+        if (t >= static_cast<uint32_t>(p.g.ntiles)) {
+            break;
+        }
+        lat_flood_tile(p, lt, t, lane, settled, bad);
+    }
+    uint32_t const lo = lab_reduce_add(static_cast<uint32_t>(settled)), hi = lab_reduce_add(static_cast<uint32_t>(settled >> 32));
+    bad = lab_reduce_or(bad);
+    if (lane == 0) {
+        lab_atomic_add(reinterpret_cast<uint64_t *>(&tc->lat_settled), (static_cast<uint64_t>(hi) << 32) + lo);
+        if (bad) {
+            lab_atomic_or(&tc->lat_flood_bad, bad);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4 scan.  wsum[0 .. n_arcs] (index = R; [0] is nobody's) -> inclusive prefix sums inside chunks of L_CHUNK,
+// then the chunk totals' exclusive prefix.  Warp per chunk; the second pass is one warp.
+LAB_DEV void lat_scan_chunks_body(Lattice const &lt, long long gwarp, long long nwarps, int lane) {
+    Tree_ctl *tc = lt.tc;
+    if (!lat_live(tc)) {
+        return;
+    }
+    if (tc->lat_flood_bad || tc->lat_settled != tc->V) { // the floods did not reach every square: not one tree
+        if (gwarp == 0 && lane == 0) lab_st_volatile(&tc->lat_err, 4u);
+        return;
+    }
+    long long const n = static_cast<long long>(tc->n_arcs) + 1;
+    long long const chunks = (n + L_CHUNK - 1) / L_CHUNK;
+    for (long long c = gwarp; c < chunks; c += nwarps) {
+        uint32_t carry = 0;
+        uint32_t *w = lt.wsum + c * L_CHUNK;
+        long long const left = n - c * L_CHUNK;
+        uint32_t v[L_CHUNK / 32];
+#pragma unroll
+        for (int k = 0; k < static_cast<int>(L_CHUNK / 32); k++) {
+            long long const i = 32 * k + lane;
+            v[k] = (i < left && (c | i) != 0) ? w[i] : 0u; // ([0] was never written)
+        }
+#pragma unroll
+        for (int k = 0; k < static_cast<int>(L_CHUNK / 32); k++) {
+            uint32_t x = v[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t const y = lab_shfl_up(x, d);
+                if (lane >= d) x += y;
+            }
+            x += carry;
+            carry = lab_shfl(x, 31);
+            if (32 * k + lane < left) {
+                w[32 * k + lane] = x;
+            }
+        }
+        if (lane == 0) {
+            lt.chunk[c] = carry;
+        }
+    }
+}
+LAB_DEV void lat_scan_tops_body(Lattice const &lt, int lane) {
+    Tree_ctl *tc = lt.tc;
+    if (!lat_live(tc)) {
+        return;
+    }
+    long long const n = static_cast<long long>(tc->n_arcs) + 1;
+    long long const chunks = (n + L_CHUNK - 1) / L_CHUNK;
+    uint32_t carry = 0;
+    for (long long c0 = 0; c0 < chunks; c0 += 32) {
+        long long const c = c0 + lane;
+        uint32_t const own = c < chunks ? lt.chunk[c] : 0u;
+        uint32_t x = own;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t const y = lab_shfl_up(x, d);
+            if (lane >= d) x += y;
+        }
+        if (c < chunks) {
+            lt.chunk[c] = carry + x - own; // exclusive
+        }
+        carry += lab_shfl(x, 31);
+    }
+    if (lane == 0 && carry != 0u) { // every +w has its -w: a total that is not zero means a broken tour
+        lab_st_volatile(&tc->lat_err, 5u);
+    }
+}
+// sum of the weights of all arcs with R' < r
+LAB_DEV uint32_t lat_prefix_below(Lattice const &lt, uint32_t r) {
+    uint32_t const i = r - 1u;
+    return lab_ld_cg(lt.wsum + i) + lab_ld_cg(lt.chunk + i / L_CHUNK);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5 levels.  Warp per tile; sm: 128 words (entry depth per component label).
+LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int lane, uint32_t *sm, uint32_t &mx) {
+    Geom const &g = p.g;
+    Lat_tile const T = lat_load(lt, t, lane);
+    uint32_t const X[4] = {T.XN, T.XE, T.XS, T.XW};
+    long long const base = static_cast<long long>(t) * LSLOTS;
+    uint32_t em[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        em[s] = lab_ld_cg(lt.emask + static_cast<long long>(t) * 4 + s);
+    }
+    // entry depth of every component: minus the weights of the arcs later on the tour than its entry arc
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        if ((em[s] >> lane) & 1u) {
+            uint32_t const lab = lab_ld_cg(lt.label + base + s * LC + lane);
+            sm[lab & 127u] = 0u - lat_prefix_below(lt, lab_ld_cg(lt.R + base + s * LC + lane));
+        }
+    }
+    if (p.ctl->src_tile[0] == t && lane == 0) {
+        sm[lt.tc->lat_root_label & 127u] = 0u;
+    }
+    lab_syncwarp();
+    uint32_t L[L_LABEL_PLANES], D[L_DEPTH_PLANES];
+    {
+        uint32_t const *pl = lt.lplane + static_cast<long long>(t) * (L_LABEL_PLANES * 32);
+        uint32_t const *pd = lt.dplane + static_cast<long long>(t) * (L_DEPTH_PLANES * 32);
+#pragma unroll
+        for (int q = 0; q < L_LABEL_PLANES; q++) {
+            L[q] = lab_ld_cg(pl + q * 32 + lane);
+        }
+#pragma unroll
+        for (int q = 0; q < L_DEPTH_PLANES; q++) {
+            D[q] = lab_ld_cg(pd + q * 32 + lane);
+        }
+    }
+    // lane = cell column j: its 32 cells' levels (INF: no cell)
+    uint32_t lv[LC];
+#pragma unroll
+    for (int i = 0; i < LC; i++) {
+        uint32_t lab = 0, d = 0;
+#pragma unroll
+        for (int q = 0; q < L_LABEL_PLANES; q++) {
+            lab |= ((L[q] >> i) & 1u) << q;
+        }
+#pragma unroll
+        for (int q = 0; q < L_DEPTH_PLANES; q++) {
+            d |= ((D[q] >> i) & 1u) << q;
+        }
+        uint32_t const v = 2u * (sm[lab] + d);
+        lv[i] = ((T.C >> i) & 1u) ? v : INF;
+        mx = ((T.C >> i) & 1u) && v > mx ? v : mx;
+    }
+    // rows of squares: row 2i = [pillar, N passage of cell (i, j)], row 2i+1 = [W passage of cell (i, j), cell (i, j)];
+    // lane j writes columns 2j, 2j+1.  A passage lies one below the deeper of its two cells; across the tile's
+    // border the deeper one is this cell iff the crossing is its component's entry.
+    int const ty = static_cast<int>(t / static_cast<uint32_t>(g.tiles_x)), tx = static_cast<int>(t % static_cast<uint32_t>(g.tiles_x));
+    long long const c0 = static_cast<long long>(tx) * TS + 2 * lane;
+    bool const in0 = c0 < g.cols, in1 = c0 + 1 < g.cols;
+    uint32_t *dist = p.plane[0].dist;
+    bool const entryN = (em[L_N] >> lane) & 1u;
+#pragma unroll
+    for (int i = 0; i < LC; i++) {
+        long long const r0 = static_cast<long long>(ty) * TS + 2 * i;
+        uint32_t const me = lv[i];
+        uint32_t const left = lab_shfl_up(me, 1);
+        uint32_t np = INF, wp = INF;
+        if ((T.No >> i) & 1u) {
+            np = i ? (me > lv[i ? i - 1 : 0] ? me : lv[i ? i - 1 : 0]) - 1u : (entryN ? me - 1u : me + 1u);
+        }
+        if ((T.Wo >> i) & 1u) {
+            wp = lane ? (me > left ? me : left) - 1u : (((em[L_W] >> i) & 1u) ? me - 1u : me + 1u);
+        }
+        if (r0 < g.rows) {
+            uint32_t *row = dist + r0 * g.cols + c0;
+            if (in0) row[0] = INF;
+            if (in1) row[1] = np;
+        }
+        if (r0 + 1 < g.rows) {
+            uint32_t *row = dist + (r0 + 1) * g.cols + c0;
+            if (in0) row[0] = wp;
+            if (in1) row[1] = me;
+        }
+    }
+    lab_syncwarp();
+}
+LAB_DEV void lat_levels_body(Params const &p, Lattice const &lt, int lane, uint32_t *sm) {
+    Tree_ctl *tc = lt.tc;
+    if (!lat_live(tc)) {
+        return;
+    }
+    uint32_t mx = 0;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) {
+            t = lab_atomic_add(&tc->lat_ticket[3], 1u);
+        }
+        t = lab_shfl(t, 0);
+        if (t >= static_cast<uint32_t>(p.g.ntiles)) {
+            break;
+        }
+        lat_levels_tile(p, lt, t, lane, sm, mx);
+    }
+    mx = lab_reduce_max(mx);
+    if (lane == 0 && mx) {
+        lab_atomic_max(&p.ctl->max_level, mx);
+    }
+}
+
+} // namespace lab

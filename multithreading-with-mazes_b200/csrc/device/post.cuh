@@ -50,12 +50,14 @@ struct Run_desc {
     int n_targets;
     int32_t tgt_plane[MAX_TARGETS], tgt_r[MAX_TARGETS], tgt_c[MAX_TARGETS];
     uint32_t bound_mode;
+    uint32_t spec_mark; // Square bits pack_body has set speculatively on every passable square (0: none)
 };
 
 // One thread.  Control and the queue were memset by the host (0 / 0xFF); this seeds the sources.
 LAB_DEV void init_run_body(Params p, Run_desc d, unsigned long long budget_ns) {
     Control *ctl = p.ctl;
     ctl->bound = INF;
+    ctl->spec_mark = d.spec_mark;
     ctl->bound_mode = d.bound_mode;
     ctl->n_targets = static_cast<uint32_t>(d.n_targets);
     for (int j = 0; j < d.n_targets; j++) {
@@ -88,27 +90,33 @@ LAB_DEV void init_run_body(Params p, Run_desc d, unsigned long long budget_ns) {
 
 // Sources are passable whatever their Square says (the reference pushes its start unconditionally).
 // One thread, between pack and cross.
-LAB_DEV void force_sources_body(Geom g, uint64_t *path, Run_desc d) {
+LAB_DEV void force_sources_body(Geom g, uint64_t *path, Run_desc d, uint16_t *grid) {
     for (int k = 0; k < d.nplanes; k++) {
         if (d.src_r[k] >= 0) {
             source_force_passable(g, path, d.src_r[k], d.src_c[k]);
+            if (d.spec_mark) { // (the start is marked whatever its bits: distance.cc:138)
+                grid[static_cast<long long>(d.src_r[k]) * g.cols + d.src_c[k]] |= static_cast<uint16_t>(d.spec_mark);
+            }
         }
     }
 }
 
 // distance epilogue: measure bit on every visited square + exact count of visited squares.
 // Same row/word item space as pack_body.
-LAB_DEV void measure_body(Geom g, uint16_t *grid, uint64_t const *visited, Control const *ctl, Result *res, long long gwarp,
-                          long long nwarps, int lane) {
+LAB_DEV void measure_body(Geom g, uint16_t *grid, uint64_t const *visited, uint64_t const *path, Control const *ctl, Result *res,
+                          long long gwarp, long long nwarps, int lane) {
     if (ctl->room) {
         return; // an open room: room_distance_body has set the bits and counted the squares
     }
-    if (ctl->measured) { // one tree: tree_fixup_body has set the bits, this only reports how many
+    if (ctl->measured) { // one tree: tree_fixup_body (or pack_body, speculatively) has set the bits, this only reports how many
         if (gwarp == 0 && lane == 0) {
             lab_atomic_add(reinterpret_cast<uint64_t *>(&res->settled), static_cast<uint64_t>(ctl->n_marked));
         }
         return;
     }
+    // pack_body set the bit on every passable square in advance (spec_mark): it has to go again where the search
+    // did not come (parts of the maze cut off from the start)
+    bool const spec = ctl->spec_mark != 0;
     // one warp per row (grid stride); a 64-square word with no visited square costs one 8-byte load
     unsigned long long count = 0;
     constexpr int U = 4; // 64-square words of a row handled together: independent read-modify-writes in flight
@@ -116,28 +124,33 @@ LAB_DEV void measure_body(Geom g, uint16_t *grid, uint64_t const *visited, Contr
     for (long long it = gwarp; it < static_cast<long long>(g.rows) * chunks; it += nwarps) {
         int const r = static_cast<int>(it / chunks);
         int const j0 = static_cast<int>(it % chunks) * U;
-        uint64_t const *vrow = visited + (static_cast<long long>(r / TS) * g.tiles_x) * TS + (r % TS);
+        long long const w0 = (static_cast<long long>(r / TS) * g.tiles_x) * TS + (r % TS);
         uint16_t *row = grid + static_cast<long long>(r) * g.cols;
-        uint64_t v[U];
+        uint64_t v[U], x[U]; // reached / passable but not reached
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            v[u] = j0 + u < g.tiles_x ? vrow[static_cast<long long>(j0 + u) * TS] : 0ull;
+            v[u] = j0 + u < g.tiles_x ? visited[w0 + static_cast<long long>(j0 + u) * TS] : 0ull;
+            x[u] = (spec && j0 + u < g.tiles_x) ? (path[w0 + static_cast<long long>(j0 + u) * TS] & ~v[u]) : 0ull;
         }
         uint16_t a[U], b[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             int const c0 = (j0 + u) * TS + lane;
-            a[u] = ((v[u] >> lane) & 1) ? row[c0] : static_cast<uint16_t>(0);
-            b[u] = ((v[u] >> (lane + 32)) & 1) ? row[c0 + 32] : static_cast<uint16_t>(0);
+            a[u] = (((v[u] | x[u]) >> lane) & 1) ? row[c0] : static_cast<uint16_t>(0);
+            b[u] = (((v[u] | x[u]) >> (lane + 32)) & 1) ? row[c0 + 32] : static_cast<uint16_t>(0);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             int const c0 = (j0 + u) * TS + lane;
             if ((v[u] >> lane) & 1) {
                 row[c0] = a[u] | SQ_MEASURE;
+            } else if ((x[u] >> lane) & 1) {
+                row[c0] = a[u] & static_cast<uint16_t>(~SQ_MEASURE);
             }
             if ((v[u] >> (lane + 32)) & 1) {
                 row[c0 + 32] = b[u] | SQ_MEASURE;
+            } else if ((x[u] >> (lane + 32)) & 1) {
+                row[c0 + 32] = b[u] & static_cast<uint16_t>(~SQ_MEASURE);
             }
             count += static_cast<unsigned long long>(lab_popc64(v[u]));
         }

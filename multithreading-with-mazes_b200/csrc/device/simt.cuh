@@ -25,11 +25,13 @@ LAB_DEV uint32_t lab_reduce_max(uint32_t v) { return __reduce_max_sync(LAB_FULL,
 LAB_DEV uint32_t lab_reduce_or(uint32_t v) { return __reduce_or_sync(LAB_FULL, v); }
 LAB_DEV uint32_t lab_reduce_add(uint32_t v) { return __reduce_add_sync(LAB_FULL, v); }
 LAB_DEV void lab_syncwarp() { __syncwarp(); }
+LAB_DEV uint32_t lab_match_any(uint32_t v) { return __match_any_sync(LAB_FULL, v); } // lanes holding the same value
 
 LAB_DEV int lab_ffs64(uint64_t v) { return __ffsll(static_cast<long long>(v)); } // 1-based, 0 if none
 LAB_DEV int lab_popc64(uint64_t v) { return __popcll(v); }
 LAB_DEV int lab_clz64(uint64_t v) { return __clzll(static_cast<long long>(v)); } // 64 if none
 LAB_DEV int lab_ffs32(uint32_t v) { return __ffs(static_cast<int>(v)); } // 1-based, 0 if none
+LAB_DEV int lab_clz32(uint32_t v) { return __clz(static_cast<int>(v)); }  // 32 if none
 
 // loads that must observe other SMs' stores (L1 is not coherent inside a persistent kernel)
 LAB_DEV uint32_t lab_ld_cg(uint32_t const *p) { return __ldcg(p); }
@@ -44,6 +46,8 @@ LAB_DEV uint64_t lab_ld_ro(uint64_t const *p) {
 }
 LAB_DEV uint32_t lab_ld_ro(uint32_t const *p) { return __ldg(p); }
 LAB_DEV uint16_t lab_ld_ro(uint16_t const *p) { return __ldg(p); }
+LAB_DEV uint8_t lab_ld_ro(uint8_t const *p) { return __ldg(p); }
+LAB_DEV uint8_t lab_ld_cg(uint8_t const *p) { return __ldcg(p); }
 LAB_DEV void lab_st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
 LAB_DEV void lab_st_cg(uint64_t *p, uint64_t v) {
     __stcg(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v));
@@ -60,6 +64,7 @@ LAB_DEV lab_u32x4 lab_ld_ro_v4(void const *p) { // read-only data
     uint4 const t = __ldg(reinterpret_cast<uint4 const *>(p));
     return {t.x, t.y, t.z, t.w};
 }
+LAB_DEV void lab_st_v4(void *p, lab_u32x4 v) { *reinterpret_cast<uint4 *>(p) = make_uint4(v.x, v.y, v.z, v.w); }
 LAB_DEV void lab_st_stream_v4(void *p, lab_u32x4 v) { __stcs(reinterpret_cast<uint4 *>(p), make_uint4(v.x, v.y, v.z, v.w)); }
 // a (pointer, value) pair of the pointer-jumping lists: ONE 8-byte access (a random 4-byte access costs a 32-byte sector
 // either way, so two separate arrays would move twice the sectors)

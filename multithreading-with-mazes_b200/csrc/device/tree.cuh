@@ -54,6 +54,13 @@ struct Tree_ctl {
     unsigned long long marked; // squares the fix-up has given Tree::mark_bits
     uint32_t crossings;  // border crossings of the tiles counted (= the entries the walk will add to alist)
     uint32_t alist_base; // row bands: where this band's piece of the global crossing list starts
+    // the lattice road (device/lattice.cuh), tried first on mazes carved on the lattice of odd squares
+    uint32_t lat_err;        // why it gave up (1 not a lattice, 2 labels, 3 tour, 4 floods, 5 weights); nothing was written then
+    uint32_t lat_on;         // tree_init_body: the counts allow a tree and the host found odd sizes and an (odd, odd) start
+    uint32_t lat_root_label; // the root component's label in the root's tile
+    uint32_t lat_flood_bad;
+    uint32_t lat_ticket[4];  // dynamic tile counters: link, local ranking, flood, levels
+    unsigned long long lat_settled;
 };
 
 struct Tree {
@@ -81,6 +88,8 @@ struct Tree {
     // Square bits the fix-up ORs into every square it gives a level: Rgb::measure for the distance map
     // (painters/distance.cc:138,149 -- saves measure_body's pass over the grid), 0 for the solvers.
     uint32_t mark_bits;
+    // the host found odd sizes and an (odd, odd) start: the lattice road (device/lattice.cuh) is tried first
+    uint32_t lat_try;
 };
 
 LAB_DEV bool tree_follow(Tree const &tr, uint32_t slot) { // may a round follow a pointer to `slot`?
@@ -99,7 +108,12 @@ LAB_DEV void room_set_body(Control *ctl, int r0, int r1, int c0, int c1, int sr,
     ctl->room = 1u;
 }
 
-LAB_DEV bool tree_live(Tree_ctl const *tc) { return tc->ok != 0 && tc->unreached == 0 && tc->bad_weight == 0 && tc->walk_error == 0; }
+// The lattice road's kernels all run before the general pipeline's: once they are through, lat_on without an error
+// means the level field is made.
+LAB_DEV bool lat_made(Tree_ctl const *tc) { return tc->lat_on != 0 && tc->lat_err == 0; }
+LAB_DEV bool tree_live(Tree_ctl const *tc) {
+    return tc->ok != 0 && !lat_made(tc) && tc->unreached == 0 && tc->bad_weight == 0 && tc->walk_error == 0;
+}
 
 // the arc entering the neighbouring tile through the same crossing
 LAB_DEV uint32_t tree_twin(Geom const &g, uint32_t a) {
@@ -479,6 +493,7 @@ LAB_DEV void tree_init_body(Params const &p, Tree const &tr) {
     uint32_t const ROOT = tr.nslots, END = tr.nslots + 1u;
     Tree_ctl *tc = tr.tc;
     tc->ok = (tc->V >= 2 && tc->E + 1 == tc->V) ? 1u : 0u; // a tree has squares - 1 adjacent pairs
+    tc->lat_on = (tc->ok && tr.lat_try && !tr.banded) ? 1u : 0u;
     // Not a tree, but the bounding box of the passable squares holds nothing else: an open room (the
     // reference's arena builder).  Levels are a closed form there (device/room.cuh); the source is one of
     // the passable squares (force_sources_body), so it lies inside.
@@ -1167,7 +1182,8 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
         tc->used = 2;
         return;
     }
-    if (!tree_live(tc)) {
+    bool const lattice = tc->ok != 0 && lat_made(tc); // the lattice road made the field (it marks nothing itself)
+    if (!tree_live(tc) && !lattice) {
         // the wave takes over: it needs a field of INF and empty visited masks (search_prepare left the
         // reset of the field to whoever writes it: the fix-up above, or this)
         long long const cells = static_cast<long long>(p.g.rows) * p.g.cols;
@@ -1179,7 +1195,8 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
         }
         return;
     }
-    if (!tr.mark_bits) { // (else the fix-up has marked the squares itself and measure_body has nothing to look at)
+    bool const spec_final = lattice && ctl->spec_mark != 0; // pack_body's speculative marks are exactly the squares reached
+    if ((!tr.mark_bits || lattice) && !spec_final) { // (else the squares are marked already and measure_body has nothing to look at)
         for (long long i = gthread; i < static_cast<long long>(p.g.ntiles) * TS; i += nthreads) {
             p.plane[0].visited[i] = p.path[i]; // one tree: every passable square was reached
         }
@@ -1187,9 +1204,13 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
     if (gthread != 0) {
         return;
     }
-    if (tr.mark_bits) {
+    if (tr.mark_bits && !lattice) {
         ctl->measured = 1u;
         ctl->n_marked = tc->marked;
+    }
+    if (spec_final) {
+        ctl->measured = 1u;
+        ctl->n_marked = tc->lat_settled;
     }
     for (uint32_t j = 0; j < ctl->n_targets; j++) {
         ctl->target_val[j] = p.plane[0].dist[ctl->target_cell[j]];
@@ -1203,8 +1224,8 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
     ctl->tail = 0;
     ctl->pending = 0;
     ctl->done = 1;
-    ctl->n_settled = tc->local_settled;
-    tc->used = 1;
+    ctl->n_settled = lattice ? tc->lat_settled : tc->local_settled;
+    tc->used = lattice ? 3u : 1u;
 }
 
 } // namespace lab

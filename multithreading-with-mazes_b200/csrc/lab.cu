@@ -16,6 +16,7 @@
 #include "device/engine.cuh"
 #include "device/post.cuh"
 #include "device/tree.cuh"
+#include "device/lattice.cuh"
 #include "host/builders.hh"
 #include "host/mazefile.hh"
 #include "host/points.hh"
@@ -31,8 +32,8 @@ __device__ __forceinline__ long long gwarp_id() {
 __device__ __forceinline__ long long nwarps_total() { return (static_cast<long long>(gridDim.x) * blockDim.x) >> 5; }
 __device__ __forceinline__ int lane_id() { return static_cast<int>(threadIdx.x & 31); }
 
-__global__ void __launch_bounds__(256) k_pack(Geom g, uint16_t const *grid, uint64_t *path, uint16_t mask, uint16_t value) {
-    pack_body(g, grid, path, mask, value, gwarp_id(), nwarps_total(), lane_id());
+__global__ void __launch_bounds__(256) k_pack(Geom g, uint16_t *grid, uint64_t *path, uint16_t mask, uint16_t value, uint16_t mark) {
+    pack_body(g, grid, path, mask, value, mark, gwarp_id(), nwarps_total(), lane_id());
 }
 
 __global__ void __launch_bounds__(256) k_cross(Geom g, uint64_t const *path, uint64_t *cross, uint64_t const *ghost_n,
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) k_cross(Geom g, uint64_t const *path, uin
     cross_body(g, path, cross, ghost_n, ghost_s, gwarp_id(), nwarps_total(), lane_id());
 }
 
-__global__ void k_force_sources(Geom g, uint64_t *path, Run_desc d) { force_sources_body(g, path, d); }
+__global__ void k_force_sources(Geom g, uint64_t *path, Run_desc d, uint16_t *grid) { force_sources_body(g, path, d, grid); }
 
 __global__ void k_init_run(Params p, Run_desc d, unsigned long long budget_ns) { init_run_body(p, d, budget_ns); }
 
@@ -206,6 +207,29 @@ __global__ void __launch_bounds__(256) k_tree_border_import(Params p, Tree tr, i
 __global__ void __launch_bounds__(256) k_tree_finish_jump(Params p, Tree tr) {
     tree_finish_jump_body(p, tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
 }
+// ---- the lattice road (device/lattice.cuh) ----
+__global__ void __launch_bounds__(128) k_lat_link(Params p, Lattice lt) {
+    __shared__ uint32_t sm[4][LSLOTS];
+    lat_link_body(p, lt, lane_id(), sm[threadIdx.x >> 5]);
+}
+constexpr int LAT_RANK_WARPS = 4; // warps per block of the local ranking (LSUP_SLOTS words of shared memory each)
+__global__ void __launch_bounds__(32 * LAT_RANK_WARPS) k_lat_rank_local(Params p, Lattice lt) {
+    extern __shared__ uint32_t lat_dsm[];
+    lat_rank_local_body(p, lt, lane_id(), lat_dsm + (threadIdx.x >> 5) * LSUP_SLOTS);
+}
+__global__ void __launch_bounds__(256) k_lat_rank_global(Lattice lt) {
+    lat_rank_global_body(lt, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
+}
+__global__ void __launch_bounds__(256) k_lat_rank_expand(Lattice lt) {
+    lat_rank_expand_body(lt, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
+}
+__global__ void __launch_bounds__(128) k_lat_flood(Params p, Lattice lt) { lat_flood_body(p, lt, lane_id()); }
+__global__ void __launch_bounds__(256) k_lat_scan_chunks(Lattice lt) { lat_scan_chunks_body(lt, gwarp_id(), nwarps_total(), lane_id()); }
+__global__ void k_lat_scan_tops(Lattice lt) { lat_scan_tops_body(lt, lane_id()); }
+__global__ void __launch_bounds__(128) k_lat_levels(Params p, Lattice lt) {
+    __shared__ uint32_t sm[4][LSLOTS];
+    lat_levels_body(p, lt, lane_id(), sm[threadIdx.x >> 5]);
+}
 __global__ void __launch_bounds__(256) k_tree_orient(Params p, Tree tr) { tree_orient_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void __launch_bounds__(128) k_tree_flood(Params p, Tree tr) {
     extern __shared__ __align__(16) uint64_t flood_sm[];
@@ -222,8 +246,8 @@ __global__ void __launch_bounds__(256) k_tree_gate(Params p, Tree tr) {
     tree_gate_body(p, tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
 }
 
-__global__ void __launch_bounds__(256) k_measure(Geom g, uint16_t *grid, uint64_t const *visited, Control const *ctl, Result *res) {
-    measure_body(g, grid, visited, ctl, res, gwarp_id(), nwarps_total(), lane_id());
+__global__ void __launch_bounds__(256) k_measure(Geom g, uint16_t *grid, uint64_t const *visited, uint64_t const *path, Control const *ctl, Result *res) {
+    measure_body(g, grid, visited, path, ctl, res, gwarp_id(), nwarps_total(), lane_id());
 }
 
 __global__ void __launch_bounds__(256) k_heatmap(Geom g, uint32_t const *dist, Result const *res, int channel, uint32_t *pixels) {
@@ -409,6 +433,8 @@ struct lab_grid {
     bool tree_alloc = false;
     Tree_ctl tree_last{};
     bool tree_tried = false;
+    Lattice lat{}; // the lattice road's workspace (allocated on first use)
+    bool lat_alloc = false;
     uint64_t launches = 0; // kernels launched by the last search (bench.py reports them)
     bool tree_cfg = false;
     // the pipeline across row bands (lab_band_tree_*): the caller's global arrays, this band's control block
@@ -424,6 +450,8 @@ struct lab_grid {
     int tree_flood_per_sm = 1, tree_walk_per_sm = 1;
     cudaEvent_t tev[10]{}; // LAB_TREE_TIMING=1: per-phase events
     bool tev_on = false;
+    cudaEvent_t lev[10]{}; // ... and the lattice road's
+    bool lev_on = false;
 };
 
 namespace {
@@ -533,6 +561,11 @@ bool tree_may_run(lab_grid const *h, Run_desc const &d) {
     return !h->band_mode && d.nplanes == 1 && d.src_r[0] >= 0 && env_ll("LAB_TREE", 1) != 0;
 }
 
+// The lattice road (device/lattice.cuh) is tried where the maze can be one: odd sizes, the start on an (odd, odd) square.
+bool lattice_may_run(lab_grid const *h, Run_desc const &d) {
+    return tree_may_run(h, d) && env_ll("LAB_LATTICE", 1) != 0 && (h->g.rows & 1) && (h->g.cols & 1) && (d.src_r[0] & 1) && (d.src_c[0] & 1);
+}
+
 // Reset the workspace and pack the grid into tile bit masks (sources forced passable).
 int search_prepare(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t pass_value) {
     int rc = ensure_planes(h, d.nplanes);
@@ -558,9 +591,9 @@ int search_prepare(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t 
         }
     }
     CU(cudaEventRecord(h->ev[EV_PACK0], s));
-    k_pack<<<blocks_for(h, static_cast<long long>(g.tiles_y) * TS, 256), 256, 0, s>>>(g, h->squares, h->path, pass_mask, pass_value);
+    k_pack<<<blocks_for(h, static_cast<long long>(g.tiles_y) * TS, 256), 256, 0, s>>>(g, h->squares, h->path, pass_mask, pass_value, static_cast<uint16_t>(d.spec_mark));
     TRACE("k_pack", s);
-    k_force_sources<<<1, 1, 0, s>>>(g, h->path, d);
+    k_force_sources<<<1, 1, 0, s>>>(g, h->path, d, h->squares);
     TRACE("k_force_sources", s);
     h->launches += 2;
     CU(cudaGetLastError());
@@ -637,6 +670,85 @@ int ensure_tree(lab_grid *h) {
     return LAB_OK;
 }
 
+int ensure_lattice(lab_grid *h) {
+    if (h->lat_alloc) {
+        return LAB_OK;
+    }
+    Lattice &lt = h->lat;
+    size_t const nt = static_cast<size_t>(h->g.ntiles);
+    lt.sup_y = (h->g.tiles_y + LST - 1) / LST;
+    lt.sup_x = (h->g.tiles_x + LST - 1) / LST;
+    lt.nsuper = lt.sup_y * lt.sup_x;
+    lt.nslots = static_cast<uint32_t>(nt * LSLOTS);
+    CU(cudaMalloc(&lt.mask, nt * 96 * sizeof(uint32_t)));
+    CU(cudaMalloc(&lt.xmask, nt * 4 * sizeof(uint32_t)));
+    CU(cudaMalloc(&lt.next, nt * LSLOTS * sizeof(uint32_t)));
+    CU(cudaMalloc(&lt.label, nt * LSLOTS));
+    CU(cudaMalloc(&lt.lplane, nt * L_LABEL_PLANES * 32 * sizeof(uint32_t)));
+    CU(cudaMalloc(&lt.xd, nt * LSLOTS * sizeof(uint64_t)));
+    CU(cudaMalloc(&lt.gb, static_cast<size_t>(lt.nsuper) * LB * sizeof(uint64_t)));
+    CU(cudaMalloc(&lt.R, nt * LSLOTS * sizeof(uint32_t)));
+    CU(cudaMalloc(&lt.dplane, nt * L_DEPTH_PLANES * 32 * sizeof(uint32_t)));
+    CU(cudaMalloc(&lt.emask, nt * 4 * sizeof(uint32_t)));
+    CU(cudaMalloc(&lt.wsum, (nt * LSLOTS + 2 + L_CHUNK) * sizeof(uint32_t)));
+    CU(cudaMalloc(&lt.chunk, (nt * LSLOTS / L_CHUNK + 2) * sizeof(uint32_t)));
+    CU(cudaFuncSetAttribute(k_lat_rank_local, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(LAT_RANK_WARPS * LSUP_SLOTS * sizeof(uint32_t))));
+    h->lat_alloc = true;
+    return LAB_OK;
+}
+
+// The lattice road (device/lattice.cuh), tried before the general pipeline on mazes that can be lattices: odd
+// sizes, the start on an (odd, odd) square.  Whether the maze IS one is decided on the device, kernel by kernel;
+// after a failure the remaining launches return at once and nothing has been written.
+int run_lattice(lab_grid *h, Params const &p) {
+    int const rc = ensure_lattice(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Lattice lt = h->lat;
+    lt.tc = h->tree.tc;
+    int const nt = h->g.ntiles;
+    int const tile_blocks = static_cast<int>(std::min<long long>((nt + 3) / 4, static_cast<long long>(h->sm_count) * 16));
+    h->lev_on = env_ll("LAB_TREE_TIMING", 0) != 0;
+    int lev_i = 0;
+    auto mark = [&]() {
+        if (h->lev_on) {
+            if (!h->lev[lev_i]) cudaEventCreate(&h->lev[lev_i]);
+            cudaEventRecord(h->lev[lev_i++], s);
+        }
+    };
+    mark();
+    k_lat_link<<<tile_blocks, 128, 0, s>>>(p, lt);
+    TRACE("k_lat_link", s);
+    mark();
+    size_t const rank_smem = LAT_RANK_WARPS * LSUP_SLOTS * sizeof(uint32_t);
+    int const rank_blocks = std::min((lt.nsuper + LAT_RANK_WARPS - 1) / LAT_RANK_WARPS, h->sm_count * 6);
+    k_lat_rank_local<<<rank_blocks, 32 * LAT_RANK_WARPS, rank_smem, s>>>(p, lt);
+    TRACE("k_lat_rank_local", s);
+    mark();
+    long long const nb = static_cast<long long>(lt.nsuper) * LB;
+    k_lat_rank_global<<<static_cast<int>(std::min<long long>((nb + 255) / 256, static_cast<long long>(h->sm_count) * 8)), 256, 0, s>>>(lt);
+    TRACE("k_lat_rank_global", s);
+    mark();
+    k_lat_rank_expand<<<static_cast<int>(std::min<long long>((static_cast<long long>(lt.nslots) + 255) / 256, static_cast<long long>(h->sm_count) * 16)), 256, 0, s>>>(lt);
+    TRACE("k_lat_rank_expand", s);
+    mark();
+    k_lat_flood<<<tile_blocks, 128, 0, s>>>(p, lt);
+    TRACE("k_lat_flood", s);
+    mark();
+    k_lat_scan_chunks<<<static_cast<int>(std::min<long long>((static_cast<long long>(lt.nslots) / L_CHUNK + 8) / 8, static_cast<long long>(h->sm_count) * 8)), 256, 0, s>>>(lt);
+    TRACE("k_lat_scan_chunks", s);
+    mark();
+    k_lat_scan_tops<<<1, 32, 0, s>>>(lt);
+    TRACE("k_lat_scan_tops", s);
+    mark();
+    k_lat_levels<<<tile_blocks, 128, 0, s>>>(p, lt);
+    TRACE("k_lat_levels", s);
+    mark();
+    h->launches += 8;
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
 int ceil_log2(unsigned long long n) {
     int r = 0;
     while ((1ull << r) < n) {
@@ -674,8 +786,15 @@ int run_tree(lab_grid *h, Run_desc const &d) {
             cudaEventRecord(h->tev[tev_i++], s);
         }
     };
+    // odd sizes and an (odd, odd) start: the maze may be carved on the lattice of odd squares (every reference builder's is)
+    bool const lat_try = lattice_may_run(h, d);
+    tr.lat_try = lat_try ? 1u : 0u;
     mark();
     k_tree_init<<<1, 1, 0, s>>>(p, tr);
+    if (lat_try) {
+        rc = run_lattice(h, p);
+        if (rc) return rc;
+    }
     int const walk_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_walk_per_sm);
     k_tree_walk<<<walk_blocks, 128, 0, s>>>(p, tr);
     TRACE("k_tree_walk", s);
@@ -747,6 +866,17 @@ int finish_run(lab_grid *h) {
         CU(cudaMemcpyAsync(&h->tree_last, h->tree.tc, sizeof(Tree_ctl), cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(s));
+    if (h->tree_tried && h->lev_on) {
+        static char const *const names[] = {"link", "rank_local", "rank_global", "expand", "flood", "scan", "tops", "levels"};
+        fprintf(stderr, "[lab lattice]");
+        for (int i = 0; i < 8; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->lev[i], h->lev[i + 1]);
+            fprintf(stderr, " %s %.1fus", names[i], ms * 1000.f);
+        }
+        fprintf(stderr, " (err %u)\n", h->tree_last.lat_err);
+        h->lev_on = false;
+    }
     if (h->tree_tried && h->tev_on) {
         static char const *const names[] = {"walk", "rank", "orient", "flood", "parent", "prefix", "fixup", "gate"};
         fprintf(stderr, "[lab tree]");
@@ -941,6 +1071,13 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->tree.loc);
     cudaFree(h->tree.alist);
     cudaFree(h->tree.tc);
+    if (h->lat_alloc) {
+        Lattice &lt = h->lat;
+        void *const arrays[] = {lt.mask, lt.xmask, lt.next, lt.label, lt.lplane, lt.xd, lt.gb, lt.R, lt.dplane, lt.emask, lt.wsum, lt.chunk};
+        for (void *a : arrays) {
+            cudaFree(a);
+        }
+    }
     for (auto &e : h->ev) {
         if (e) cudaEventDestroy(e);
     }
@@ -1060,6 +1197,9 @@ int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t 
     d.src_c[0] = sc;
     d.n_targets = 0;
     d.bound_mode = BOUND_NONE;
+    // the lattice road makes no pass over the Squares of its own: pack sets the measure bits in advance (measure_body)
+    h->band_mode = false;
+    d.spec_mark = lattice_may_run(h, d) ? SQ_MEASURE : 0u;
     // passable <=> path_bit set and measure bit clear (distance.cc:145-148)
     int rc = run_search(h, d, SQ_PATH | SQ_MEASURE, SQ_PATH);
     if (rc) {
@@ -1071,7 +1211,7 @@ int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t 
     TRACE("k_resolve", s);
     k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
     TRACE("k_max_level", s);
-    k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->ctl, h->res);
+    k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->path, h->ctl, h->res);
     TRACE("k_measure", s);
     h->launches += 3;
     CU(cudaGetLastError());
@@ -1416,7 +1556,7 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
     Params p = make_params(h, 1);
     k_resolve<<<1, 1, 0, s>>>(p, h->band_desc, h->res, h->d_finish_rc);
     k_max_level<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->ctl, h->res);
-    k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->ctl, h->res);
+    k_measure<<<blocks_for(h, static_cast<long long>(h->g.rows) * ((h->g.tiles_x + 3) / 4), 256), 256, 0, s>>>(h->g, h->squares, h->plane[0].visited, h->path, h->ctl, h->res);
     h->launches += 3;
     CU(cudaGetLastError());
     h->band_open = false;

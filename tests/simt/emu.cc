@@ -7,6 +7,7 @@
 #include "../../multithreading-with-mazes_b200/csrc/device/engine.cuh"
 #include "../../multithreading-with-mazes_b200/csrc/device/post.cuh"
 #include "../../multithreading-with-mazes_b200/csrc/device/tree.cuh"
+#include "../../multithreading-with-mazes_b200/csrc/device/lattice.cuh"
 
 #include <cstring>
 #include <vector>
@@ -27,6 +28,7 @@ struct Workspace {
 };
 
 int g_tree_mode = 1;      // 0: never, 1: when the counts allow it (as csrc/lab.cu does)
+int g_lattice_mode = 1;   // 0: the general pipeline only, 1: the lattice road first (as csrc/lab.cu does)
 Tree_ctl g_tree_last{};
 
 // The spanning-tree pipeline, orchestrated as run_tree() in csrc/lab.cu does.
@@ -49,7 +51,34 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
     tr.nslots = static_cast<uint32_t>(nt * SLOTS);
     tr.mark_bits = d.game == GAME_DISTANCE ? SQ_MEASURE : 0u;
     simt::launch(nwarps, [&](int wid, int lane) { tree_count_body(p, tr, wid, nwarps, lane); });
+    bool const lat_try = g_lattice_mode && (w.g.rows & 1) && (w.g.cols & 1) && (d.src_r[0] & 1) && (d.src_c[0] & 1);
+    tr.lat_try = lat_try ? 1u : 0u;
     tree_init_body(p, tr);
+    if (lat_try) { // the lattice road, orchestrated as run_lattice() in csrc/lab.cu does
+        Lattice lt{};
+        lt.sup_y = (w.g.tiles_y + LST - 1) / LST;
+        lt.sup_x = (w.g.tiles_x + LST - 1) / LST;
+        lt.nsuper = lt.sup_y * lt.sup_x;
+        lt.nslots = static_cast<uint32_t>(nt * LSLOTS);
+        std::vector<uint32_t> mask(nt * 96, 0xDEADBEEFu), xmask(nt * 4), next(nt * LSLOTS, 0xDEADBEEFu), lplane(nt * L_LABEL_PLANES * 32), R(nt * LSLOTS, 0xDEADBEEFu),
+            dplane(nt * L_DEPTH_PLANES * 32), emask(nt * 4), wsum(nt * LSLOTS + 2 + L_CHUNK, 0xDEADBEEFu), chunk(nt * LSLOTS / L_CHUNK + 2);
+        std::vector<uint8_t> label(nt * LSLOTS);
+        std::vector<uint64_t> xd(nt * LSLOTS, 0xDEADBEEFDEADBEEFull), gb(static_cast<size_t>(lt.nsuper) * LB, 0xDEADBEEFDEADBEEFull);
+        lt.mask = mask.data(); lt.xmask = xmask.data(); lt.next = next.data(); lt.label = label.data(); lt.lplane = lplane.data();
+        lt.xd = xd.data(); lt.gb = gb.data(); lt.R = R.data(); lt.dplane = dplane.data(); lt.emask = emask.data(); lt.wsum = wsum.data();
+        lt.chunk = chunk.data();
+        lt.tc = &tc;
+        std::vector<uint32_t> lsm(static_cast<size_t>(nwarps) * LSUP_SLOTS);
+        long long const nth = static_cast<long long>(nwarps) * 32;
+        simt::launch(nwarps, [&](int wid, int lane) { lat_link_body(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS); }, sched_seed);
+        simt::launch(nwarps, [&](int wid, int lane) { lat_rank_local_body(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS); }, sched_seed);
+        simt::launch(nwarps, [&](int wid, int lane) { lat_rank_global_body(lt, static_cast<long long>(wid) * 32 + lane, nth); }, sched_seed);
+        simt::launch(nwarps, [&](int wid, int lane) { lat_rank_expand_body(lt, static_cast<long long>(wid) * 32 + lane, nth); });
+        simt::launch(nwarps, [&](int wid, int lane) { lat_flood_body(p, lt, lane); }, sched_seed);
+        simt::launch(nwarps, [&](int wid, int lane) { lat_scan_chunks_body(lt, wid, nwarps, lane); });
+        simt::launch(1, [&](int, int lane) { lat_scan_tops_body(lt, lane); });
+        simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS); }, sched_seed);
+    }
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
     std::vector<uint64_t> sm(static_cast<size_t>(nwarps) * SM);
     simt::launch(nwarps, [&](int wid, int lane) { tree_walk_body(p, tr, lane, sm.data() + static_cast<size_t>(wid) * SM); }, sched_seed);
@@ -119,8 +148,8 @@ int search(Workspace &w, uint16_t *grid, int rows, int cols, Run_desc const &d, 
     w.queue.assign(cap, Q_EMPTY);
     Params p = make_params(w, d.nplanes);
 
-    simt::launch(nwarps, [&](int wid, int lane) { pack_body(g, grid, w.path.data(), mask, value, wid, nwarps, lane); });
-    force_sources_body(g, w.path.data(), d);
+    simt::launch(nwarps, [&](int wid, int lane) { pack_body(g, grid, w.path.data(), mask, value, static_cast<uint16_t>(d.spec_mark), wid, nwarps, lane); });
+    force_sources_body(g, w.path.data(), d, grid);
     simt::launch(nwarps, [&](int wid, int lane) { cross_body(g, w.path.data(), w.cross.data(), nullptr, nullptr, wid, nwarps, lane); });
     init_run_body(p, d, 60ull * 1000000000ull);
     run_tree(w, p, d, nwarps, sched_seed);
@@ -153,6 +182,8 @@ void stats_out(Workspace const &w, uint64_t *st) {
 extern "C" {
 
 void emu_set_tree(int mode) { g_tree_mode = mode; }
+void emu_set_lattice(int mode) { g_lattice_mode = mode; }
+int emu_last_lattice_error(void) { return static_cast<int>(g_tree_last.lat_err); }
 // 0: the tile wave made the field; 1: the tree pipeline did
 int emu_last_tree_used(void) { return static_cast<int>(g_tree_last.used); }
 
@@ -166,6 +197,8 @@ int emu_distance(int rows, int cols, uint16_t *grid, int sr, int sc, uint32_t *d
     d.src_r[0] = sr;
     d.src_c[0] = sc;
     d.bound_mode = BOUND_NONE;
+    // (as lab_distance_map: where the lattice road is tried, pack sets the measure bits in advance)
+    d.spec_mark = (g_tree_mode && g_lattice_mode && (rows & 1) && (cols & 1) && (sr & 1) && (sc & 1)) ? SQ_MEASURE : 0u;
     int rc = search(w, grid, rows, cols, d, SQ_PATH | SQ_MEASURE, SQ_PATH, nwarps, sched_seed);
     if (rc) return rc;
     Params p = make_params(w, 1);
@@ -175,7 +208,7 @@ int emu_distance(int rows, int cols, uint16_t *grid, int sr, int sc, uint32_t *d
     simt::launch(nwarps, [&](int wid, int lane) {
         max_level_body(w.g, w.dist[0].data(), &w.ctl, &w.res, static_cast<long long>(wid) * 32 + lane, nthreads);
     });
-    simt::launch(nwarps, [&](int wid, int lane) { measure_body(w.g, grid, w.visited[0].data(), &w.ctl, &w.res, wid, nwarps, lane); });
+    simt::launch(nwarps, [&](int wid, int lane) { measure_body(w.g, grid, w.visited[0].data(), w.path.data(), &w.ctl, &w.res, wid, nwarps, lane); });
     std::memcpy(dist_out, w.dist[0].data(), w.dist[0].size() * sizeof(uint32_t));
     *max_out = w.res.max_level;
     *settled_out = w.res.settled;
@@ -266,8 +299,8 @@ int emu_band_begin_game(void *h, int game, int src_r, int src_c) {
     e->tree_last = Tree_ctl{};
     int const nw = e->nwarps;
     uint16_t const mask = game == GAME_DISTANCE ? (SQ_PATH | SQ_MEASURE) : SQ_PATH;
-    simt::launch(nw, [&](int wid, int lane) { pack_body(g, w.grid_ptr, w.path.data(), mask, SQ_PATH, wid, nw, lane); });
-    force_sources_body(g, w.path.data(), e->d);
+    simt::launch(nw, [&](int wid, int lane) { pack_body(g, w.grid_ptr, w.path.data(), mask, SQ_PATH, 0, wid, nw, lane); });
+    force_sources_body(g, w.path.data(), e->d, w.grid_ptr);
     return 0;
 }
 
@@ -376,7 +409,7 @@ int emu_band_finish(void *h, uint64_t *local_max, uint64_t *local_settled) {
     resolve_body(p, e->d, &w.res, frc);
     long long const nthreads = static_cast<long long>(nw) * 32;
     simt::launch(nw, [&](int wid, int lane) { max_level_body(w.g, w.dist[0].data(), &w.ctl, &w.res, static_cast<long long>(wid) * 32 + lane, nthreads); });
-    simt::launch(nw, [&](int wid, int lane) { measure_body(w.g, w.grid_ptr, w.visited[0].data(), &w.ctl, &w.res, wid, nw, lane); });
+    simt::launch(nw, [&](int wid, int lane) { measure_body(w.g, w.grid_ptr, w.visited[0].data(), w.path.data(), &w.ctl, &w.res, wid, nw, lane); });
     if (w.ctl.pending != 0) return -200;
     *local_max = w.res.max_level;
     *local_settled = w.res.settled;

@@ -213,11 +213,18 @@ LAB_DEV uint32_t lab_reduce_add(uint32_t v) {
     return m;
 }
 LAB_DEV void lab_syncwarp() { (void)simt::exchange(0); }
+LAB_DEV uint32_t lab_match_any(uint32_t v) {
+    uint64_t const *b = simt::exchange(v);
+    uint32_t m = 0;
+    for (int i = 0; i < 32; i++) m |= (static_cast<uint32_t>(b[i]) == v ? 1u : 0u) << i;
+    return m;
+}
 
 LAB_DEV int lab_ffs64(uint64_t v) { return v ? __builtin_ctzll(v) + 1 : 0; }
 LAB_DEV int lab_popc64(uint64_t v) { return __builtin_popcountll(v); }
 LAB_DEV int lab_clz64(uint64_t v) { return v ? __builtin_clzll(v) : 64; }
 LAB_DEV int lab_ffs32(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
+LAB_DEV int lab_clz32(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 
 template <class T> LAB_DEV T lab_ld_cg(T const *p) {
     simt::maybe_yield();
@@ -239,6 +246,7 @@ LAB_DEV lab_u32x4 lab_ld_stream_v4(void const *p) {
 }
 LAB_DEV lab_u32x4 lab_ld_ro_v4(void const *p) { return lab_ld_stream_v4(p); }
 LAB_DEV void lab_st_stream_v4(void *p, lab_u32x4 v) { std::memcpy(p, &v, sizeof v); }
+LAB_DEV void lab_st_v4(void *p, lab_u32x4 v) { std::memcpy(p, &v, sizeof v); }
 struct lab_u32x2 {
     uint32_t x, y;
 };
@@ -312,3 +320,4 @@ LAB_DEV uint64_t lab_clock_ns() {
 #define lab_reduce_or(...) (simt::g_site = __LINE__, lab_reduce_or(__VA_ARGS__))
 #define lab_reduce_add(...) (simt::g_site = __LINE__, lab_reduce_add(__VA_ARGS__))
 #define lab_syncwarp() (simt::g_site = __LINE__, lab_syncwarp())
+#define lab_match_any(...) (simt::g_site = __LINE__, lab_match_any(__VA_ARGS__))

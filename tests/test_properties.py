@@ -44,7 +44,7 @@ def check_field(torch, levels, squares, start, lab, block=2048):
     return reached_total, max_level
 
 
-CASES = [("kruskal", 8191, None, 1), ("wilson", 8191, None, 1), ("arena", 32767, None, 2), ("arena", 8191, "pillar", 0), ("grid", 4095, "cross", 0)]
+CASES = [("kruskal", 8191, None, 3), ("wilson", 8191, None, 3), ("arena", 32767, None, 2), ("arena", 8191, "pillar", 0), ("grid", 4095, "cross", 0)]
 
 
 @pytest.mark.gpu

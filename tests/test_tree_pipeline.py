@@ -18,6 +18,21 @@ def emu():
     return Emu()
 
 
+@pytest.fixture(autouse=True)
+def general_pipeline_only(emu):
+    """These tests are about the GENERAL pipeline (any tree of squares): the lattice road (device/lattice.cuh,
+    tests/test_lattice.py), which would take the reference builders' mazes first, is switched off."""
+    emu.lib.emu_set_lattice(0)
+    old = os.environ.get("LAB_LATTICE")
+    os.environ["LAB_LATTICE"] = "0"
+    yield
+    emu.lib.emu_set_lattice(1)
+    if old is None:
+        del os.environ["LAB_LATTICE"]
+    else:
+        os.environ["LAB_LATTICE"] = old
+
+
 def tree_looking_non_tree(lab, rows, cols, seed):
     """A perfect maze with one wall opened (a cycle) and one passage closed elsewhere (a part cut off):
     still squares - 1 adjacent pairs, but neither connected nor acyclic."""
