@@ -3,27 +3,34 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
-A "step" is one pass of the hot path over one maze: the whole search (workspace reset, pack,
-search phase -- the spanning-tree pipeline on perfect mazes, one streaming pass on open rooms (arenas),
-the persistent tile-relaxation kernel otherwise --, epilogue) for the workload named in ``config.workload``.
-N > 1 (torchrun): distance workloads run ONE maze N times taller, sharded as row bands, one band per GPU
-(``--sharding bands``, the default; multithreading-with-mazes_b200/bands.py); the other games run one maze per GPU.
-Default workload = BASELINE.json configs[1]: Distance map from the centre of a 4095x4095 Kruskal
-perfect maze (seeded, built by the product's linear-time builder, byte-identical to the
-reference builder's output for that seed).
+A "step" is one pass of the hot path over one maze: the whole search (workspace reset, pack, search phase,
+epilogue) for the workload named in ``config.workload``.  The search phase takes one of four roads, chosen on the
+device: the lattice road on the reference builders' perfect mazes (csrc/device/lattice.cuh), the general
+spanning-tree pipeline on other trees, one streaming pass on open rooms (arenas), the persistent tile-relaxation
+kernel on everything else.
+
+Default workload ``h-32767`` = BASELINE.json's north_star headline: the BFS distance map AND bfs-gather on ONE
+32767 x 32767 Kruskal perfect maze on one GPU (seeded, built by the product's linear-time builder, byte-identical
+to the reference builder's output for that seed; cached as a raw maze file under /dev/shm so that a box pays the
+host build once).  ``value`` / ``roofline`` / ``e2e`` are the distance map's, the ``gather`` object holds the same
+three for bfs-gather.  BASELINE configs[1..3] and the other sizes are ``--workload`` names.
+N > 1 (torchrun): the headline maze cut into N row bands, one per GPU (strong scaling; bands.py); other distance
+workloads run ONE maze N times taller (weak); the other games run one maze per GPU.
 
   value      cells settled / second (G/s) with the maze already resident in HBM: K steps, each timed
              with CUDA events on the launching stream (the Square grid is restored from a pristine
              device copy and L2 is flushed between steps, outside the timed region), max over ranks.
   e2e        the same metric through the host-facing call path: pinned host Squares -> H2D -> search
              -> D2H of the Squares (and the level field for the distance map), copies timed.
-  roofline   HBM: algorithmic bytes per launch (SURVEY.md §8(d): 8 B x rows x cols for the distance
+  roofline   HBM: algorithmic bytes per launch (SURVEY.md 8(d): 8 B x rows x cols for the distance
              map, 4 B x rows x cols for the solvers) / the search phase's CUDA-event time (events on
-             the library's stream around its kernels), against MEASURED_PEAKS.json's copy bandwidth.
+             the library's stream around its kernels), against MEASURED_PEAKS.json's copy bandwidth;
+             ``whole_step`` = the same bytes over the whole step.
   cpu_baseline  the oracle's CPU restatement ("port", 1 thread) on the same maze, rank 0, N = 1.
+  same_size_point  our arm on the mazes the reference arm samples (below): the like-for-like point.
 
-``--impl reference`` times the reference's own CPU implementation (oracle/_ref = the real
-reference text compiled here) on a bounded sample of the workload; see reference_arm().
+``--impl reference`` times the reference's own CPU implementation (oracle/_ref = the real reference text
+compiled here; nothing of the product is loaded) on a bounded sample of the same workload; see reference_arm().
 """
 from __future__ import annotations
 
@@ -46,6 +53,8 @@ import __graft_entry__ as graft  # noqa: E402
 SEED = 0xB2000000
 WORKLOADS = {
     # name: (game, builder, n, mod, BASELINE config it stands for)
+    "h-32767": ("distance+gather", "kruskal", 32767, None,
+                "north_star headline: BFS distance map AND bfs-gather on a 32767x32767 perfect maze, one GPU (value = distance map, `gather` = bfs-gather)"),
     "c2-distance-kruskal-4095": ("distance", "kruskal", 4095, None, "configs[1]"),
     "c3-gather-arena-16383": ("gather", "arena", 16383, None, "configs[2]"),
     "c4-corners-grid-cross-4095": ("corners", "grid", 4095, "cross", "configs[3] at 4095 (host build time)"),
@@ -62,7 +71,7 @@ WORKLOADS = {
     "h-distance-arena-pillar-32767": ("distance", "arena", 32767, "pillar", "headline size, arena with ONE wall square inside: the tile wave"),
     "h-gather-arena-pillar-32767": ("gather", "arena", 32767, "pillar", "headline size, arena with ONE wall square inside: the tile wave"),
 }
-DEFAULT = "c2-distance-kruskal-4095"
+DEFAULT = "h-32767"
 ALG_BYTES_PER_CELL = {"distance": 8.0, "gather": 4.0, "hunt": 4.0, "corners": 4.0}
 
 
@@ -113,14 +122,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_case(lab, workload: str, seed_offset: int = 0, bands: int = 1):
-    """The workload's maze.  bands > 1: the same builder/seed on a maze `bands` times taller (each
-    GPU's band keeps the single-GPU workload's size: weak scaling)."""
-    game, builder, n, mod, _ = WORKLOADS[workload]
-    rows = n if bands == 1 else ((n + 63) // 64) * 64 * bands - 1
+def make_case_for(lab, game, builder, n, mod, seed_offset, rows=None):
+    rows = rows or n
     pillar = mod == "pillar"  # (bench only) one wall square in the arena: no longer an open room, the tile wave runs
     maze = lab.cached_maze(builder, rows, n, seed=SEED + 2 + seed_offset, mod=None if pillar else mod)
     if pillar:
+        maze = maze.copy()
         maze[rows // 4, n // 4] &= ~np.uint16(lab.PATH_BIT)
     spec = {"game": game, "rows": rows, "cols": n}
     if game == "distance":
@@ -132,6 +139,21 @@ def make_case(lab, workload: str, seed_offset: int = 0, bands: int = 1):
     elif game == "corners":
         maze, spec["starts"], spec["finish"] = lab.place_corners(maze, seed=SEED + 3 + seed_offset)
     return maze, spec
+
+
+def make_case(lab, workload: str, seed_offset: int = 0, bands: int = 1):
+    """The workload's maze.  bands > 1: the same builder/seed on a maze `bands` times taller (each
+    GPU's band keeps the single-GPU workload's size: weak scaling)."""
+    game, builder, n, mod, _ = WORKLOADS[workload]
+    rows = n if bands == 1 else ((n + 63) // 64) * 64 * bands - 1
+    return make_case_for(lab, "distance" if game == "distance+gather" else game, builder, n, mod, seed_offset, rows)
+
+
+def make_cases(lab, workload: str, seed_offset: int = 0):
+    """[(maze, spec)]: one entry per game of the workload (the headline has two on the same maze)."""
+    game, builder, n, mod, _ = WORKLOADS[workload]
+    games = ("distance", "gather") if game == "distance+gather" else (game,)
+    return [make_case_for(lab, g, builder, n, mod, seed_offset) for g in games]
 
 
 def run_search(grid, spec):
@@ -146,35 +168,15 @@ def run_search(grid, spec):
     return grid.corners(spec["starts"], spec["finish"], want_path=False).painted
 
 
-def ours(args):
-    import torch
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lab = graft.load_package()
-    workload = args.workload
-    game, builder, n, mod, stands_for = WORKLOADS[workload]
-    if world > 1 and game == "distance" and args.sharding == "bands":
-        return ours_bands(args, lab, dist, torch, world, rank, local)
-
-    # ---- synthetic input: one seeded maze per rank (independent mazes: no data-path collective) ----
-    t0 = time.time()
-    maze, spec = make_case(lab, workload, seed_offset=rank)
-    build_s = time.time() - t0
+def bench_game(lab, torch, maze, spec, args, flush, e2e_steps):
+    """K timed steps of one game on a device-resident maze + the end-to-end leg -> raw measurements."""
+    game = spec["game"]
     rows, cols = maze.shape
     cells = rows * cols
     stream = torch.cuda.current_stream()
     pristine = torch.from_numpy(maze.view(np.int16)).cuda()
     work = torch.empty_like(pristine)
     levels = [torch.empty((rows, cols), dtype=torch.int32, device="cuda") for _ in range(4 if game == "corners" else 1)]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     grid = lab.Grid.from_device_ptr(rows, cols, work.data_ptr(), keepalive=work)
     grid.set_stream(stream.cuda_stream)
     for k, lv in enumerate(levels):
@@ -193,11 +195,6 @@ def ours(args):
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     settled = 0
     t = {"setup_ms": 0.0, "pack_ms": 0.0, "search_ms": 0.0, "post_ms": 0.0, "total_ms": 0.0}
@@ -208,13 +205,10 @@ def ours(args):
     torch.cuda.synchronize()
     step_ms = sum(a.elapsed_time(b) for a, b in evs)
     stats = grid.stats()
-    launches_per_step = int(stats["launches"])  # counted by the library as it launches them
-
     # ---- end to end: pinned host buffers, copies inside the timed region ---------------------------
     host_in = torch.from_numpy(maze.view(np.int16)).pin_memory()
     host_out = torch.empty_like(host_in).pin_memory()
     host_lv = torch.empty((rows, cols), dtype=torch.int32).pin_memory() if game == "distance" else None
-    e2e_steps = max(1, min(args.steps, 5))
     e_ms, e_settled = 0.0, 0
     for i in range(e2e_steps + 1):
         flush.fill_(1)
@@ -231,82 +225,156 @@ def ours(args):
         if i > 0:  # first one warms the pinned paths
             e_ms += a.elapsed_time(b)
             e_settled += s
-    h2d = cells * 2
-    d2h = cells * 2 + (cells * 4 if game == "distance" else 0)
+    grid.close()
+    del pristine, work, levels, host_in, host_out, host_lv
+    torch.cuda.empty_cache()
+    return {"game": game, "cells": cells, "step_ms": step_ms, "settled": settled, "t": t, "stats": stats, "e_ms": e_ms,
+            "e_settled": e_settled, "e_steps": e2e_steps, "h2d": cells * 2, "d2h": cells * 2 + (cells * 4 if game == "distance" else 0)}
 
-    clocks = sampler.stop() if rank == 0 else None
-    # ---- max over ranks, whole-job aggregate -------------------------------------------------------
-    vec = torch.tensor([step_ms, e_ms, t["search_ms"]], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(settled), float(e_settled)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    step_ms_max, e_ms_max, search_ms_max = (float(x) for x in vec.tolist())
-    settled_all, e_settled_all = (float(x) for x in tot.tolist())
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
+ROADS = {0: "tile wave (k_bfs_tiles, csrc/device/engine.cuh)",
+         1: "general spanning-tree pipeline (k_tree_walk, k_tree_jump<rank>, k_tree_flood, k_tree_jump<prefix>, k_tree_fixup; csrc/device/tree.cuh)",
+         2: "open room (closed-form levels in one streaming pass; csrc/device/room.cuh)",
+         3: "lattice road (k_lat_link, k_lat_rank_local/global/expand, k_lat_flood, k_lat_scan_*, k_lat_levels; csrc/device/lattice.cuh)"}
+
+
+def game_record(m, args, world, reduce_max, reduce_sum):
+    """One game's measurements -> the JSON fields (value, roofline, e2e ...), max over ranks / whole-job sums."""
+    step_ms, e_ms, search_ms, post_ms, total_ms = reduce_max([m["step_ms"], m["e_ms"], m["t"]["search_ms"], m["t"]["post_ms"], m["t"]["total_ms"]])
+    settled, e_settled = reduce_sum([float(m["settled"]), float(m["e_settled"])])
     peak, peak_src = peaks()
+    game, cells, stats = m["game"], m["cells"], m["stats"]
     alg_bytes = ALG_BYTES_PER_CELL[game] * cells
-    room = stats["tree_used"] == 2  # the open room (csrc/device/room.cuh): no search, one streaming pass
-    kernel_ms_sum = t["search_ms"]
-    if room and game != "distance":
-        kernel_ms_sum += t["post_ms"]  # the solvers' algorithmic bytes move in the epilogue's k_paint there
-    search_ms_avg = kernel_ms_sum / args.steps
-    achieved = alg_bytes / (search_ms_avg * 1e-3) / 1e9
-    if room:
-        kernel_name = ("k_room_distance (open room: closed-form levels + measure bits in one pass; csrc/device/room.cuh)" if game == "distance"
-                       else "k_paint, open-room branch (closed-form levels, no level field; search + epilogue phases timed together)")
-    elif stats["tree_used"]:
-        kernel_name = ("search phase = spanning-tree pipeline: k_tree_walk, k_tree_jump<rank>, k_tree_flood, "
-                       "k_tree_jump<prefix>, k_tree_fixup (csrc/device/tree.cuh)")
-    else:
-        kernel_name = "k_bfs_tiles"
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(workload)
-    out = {
-        "metric": "cells settled/sec (G/s) for BFS distance map & bfs-gather; % of HBM roofline",
-        "value": settled_all / (step_ms_max * 1e-3) / 1e9,
-        "unit": "Gcells/s",
-        "n_gpus": world,
-        "steps": args.steps,
-        "warmup": args.warmup,
-        "ms_per_step": step_ms_max / args.steps,
-        "higher_is_better": True,
-        "scaling": "weak",
-        "vs_baseline": None,
-        "dtype": "u16",
-        "data": "synthetic",
-        "config": {
-            "workload": workload, "stands_for": stands_for, "game": game, "builder": builder, "mod": mod, "rows": rows,
-            "cols": cols, "seed": SEED + 2, "cells_settled_per_step": settled // args.steps,
-            "parallelism": "1 maze per GPU (independent mazes, no data-path collective)" if world > 1 else "1 GPU",
-            "l2": "256 MB flush buffer written between timed steps", "maze_build_s_host": round(build_s, 2),
-        },
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic,
-                     "kernel": kernel_name,
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": search_ms_avg,
-                     "kernel_share_of_step": kernel_ms_sum / step_ms},
-        "e2e": {"value": e_settled_all / (e_ms_max * 1e-3) / 1e9, "unit": "Gcells/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e_ms_max / e2e_steps, "steps": e2e_steps},
-        "gpu_launches": launches_per_step * args.steps,
-        "clocks": clocks,
-        "phases_ms_per_step": {k: v / args.steps for k, v in t.items()},
+    road = int(stats["tree_used"])
+    kernel_ms_sum = search_ms
+    if road == 2 and game != "distance":
+        kernel_ms_sum += post_ms  # the solvers' algorithmic bytes move in the epilogue's k_paint there
+    kernel_ms = kernel_ms_sum / args.steps
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    whole = alg_bytes / (step_ms / args.steps * 1e-3) / 1e9
+    return {
+        "value": settled / (step_ms * 1e-3) / 1e9, "unit": "Gcells/s", "ms_per_step": step_ms / args.steps,
+        "cells_settled_per_step": m["settled"] // args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "search phase = " + ROADS.get(road, "?"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms_sum / step_ms,
+                     "whole_step": {"achieved": whole, "frac": whole / peak,
+                                    "note": "the same algorithmic bytes over the WHOLE step (reset, pack, search, epilogue)"}},
+        "e2e": {"value": e_settled / (e_ms * 1e-3) / 1e9, "unit": "Gcells/s", "h2d_bytes_per_step": m["h2d"],
+                "d2h_bytes_per_step": m["d2h"], "ms_per_step": e_ms / m["e_steps"], "steps": m["e_steps"]},
+        "gpu_launches": int(stats["launches"]) * args.steps,
+        "phases_ms_per_step": {k: v / args.steps for k, v in m["t"].items()},
         "search_stats_last_step": {k: stats[k] for k in ("tiles", "activations", "empty", "levels", "settled", "resettles",
                                                          "queue_pushes", "direct", "worker_warps", "tree_used", "tree_squares",
                                                          "tree_pairs", "tree_crossings", "launches")},
     }
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lab = graft.load_package()
+    workload = args.workload
+    game, builder, n, mod, stands_for = WORKLOADS[workload]
+    if world > 1 and game in ("distance", "distance+gather") and args.sharding == "bands":
+        return ours_bands(args, lab, dist, torch, world, rank, local)
+
+    # ---- synthetic input: one seeded maze per rank (independent mazes: no data-path collective) ----
+    t0 = time.time()
+    cases = make_cases(lab, workload, seed_offset=rank)
+    build_s = time.time() - t0
+    rows, cols = cases[0][0].shape
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e2e_steps = max(1, min(args.steps, 5 if rows * cols < (1 << 28) else 3))
+    measured = [bench_game(lab, torch, maze, spec, args, flush, e2e_steps) for maze, spec in cases]
+    clocks = sampler.stop() if rank == 0 else None
+
+    def reduce_max(xs):
+        v = torch.tensor(xs, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return [float(x) for x in v.tolist()]
+
+    def reduce_sum(xs):
+        v = torch.tensor(xs, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        return [float(x) for x in v.tolist()]
+
+    records = [game_record(m, args, world, reduce_max, reduce_sum) for m in measured]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    head = records[0]
+    out = {
+        "metric": "cells settled/sec (G/s) for BFS distance map & bfs-gather; % of HBM roofline",
+        "value": head["value"], "unit": "Gcells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+        "data": "synthetic",
+        "config": bench_config(workload, rows, cols, world),
+        "input": {"cells_settled_per_step": head["cells_settled_per_step"], "maze_build_or_cache_read_s_host": round(build_s, 2),
+                  "maze": "seeded, built by the product's linear-time builder (byte-identical to the reference builder's output for the seed), cached as a raw maze file"},
+        "roofline": head["roofline"], "e2e": head["e2e"],
+        "gpu_launches": sum(r["gpu_launches"] for r in records), "clocks": clocks,
+        "phases_ms_per_step": head["phases_ms_per_step"], "search_stats_last_step": head["search_stats_last_step"],
+    }
+    if len(records) > 1:  # the headline: `value` is the distance map, the second game of the metric rides along
+        g = records[1]
+        out["gather"] = {k: g[k] for k in ("value", "unit", "ms_per_step", "cells_settled_per_step", "roofline", "e2e",
+                                           "phases_ms_per_step", "search_stats_last_step")}
+        out["gather"]["unit"] = "Gcells/s (squares that received a paint or cache bit / s)"
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_port_baseline(maze, spec, budget_s=args.cpu_budget)
+        out["cpu_baseline"] = cpu_port_baseline(cases[0][0], cases[0][1], budget_s=args.cpu_budget)
+        if len(records) > 1:
+            out["gather"]["cpu_baseline"] = cpu_port_baseline(cases[1][0], cases[1][1], budget_s=args.cpu_budget)
+    if world == 1 and not args.no_same_size_point:
+        out["same_size_point"] = same_size_point(lab, torch, workload, args, flush)
     emit_line(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_config(workload, rows, cols, world):
+    """Identical in both arms (the driver compares them); what is specific to a run goes to `input`."""
+    game, builder, n, mod, stands_for = WORKLOADS[workload]
+    return {"workload": workload, "stands_for": stands_for, "game": game, "builder": builder, "mod": mod, "rows": rows,
+            "cols": cols, "seed": SEED + 2,
+            "parallelism": "1 maze per GPU (independent mazes, no data-path collective)" if world > 1 else "1 GPU",
+            "l2": "256 MB flush buffer written between timed steps"}
+
+
+REFERENCE_SAMPLE_N = {"distance": 511, "gather": 383, "hunt": 383, "corners": 383}
+
+
+def same_size_point(lab, torch, workload, args, flush):
+    """Our arm at the size of the reference arm's bounded sample (the real reference is super-linear: 2 s at 511^2,
+    51 s at 1023^2), same builder / seed / game: the one place where the two arms run the same input."""
+    game, builder, n, mod, _ = WORKLOADS[workload]
+    out = {}
+    for g in (("distance", "gather") if game == "distance+gather" else (game,)):
+        sn = REFERENCE_SAMPLE_N[g]
+        maze, spec = make_case_for(lab, g, builder, sn, None if mod == "pillar" else mod, 0)
+        m = bench_game(lab, torch, maze, spec, args, flush, 2)
+        out[g] = {"rows": sn, "cols": sn, "value": m["settled"] / (m["step_ms"] * 1e-3) / 1e9, "unit": "Gcells/s",
+                  "ms_per_step": m["step_ms"] / args.steps, "e2e_value": m["e_settled"] / (m["e_ms"] * 1e-3) / 1e9,
+                  "note": "--impl reference runs the real reference text on exactly this maze and game"}
+    return out
 
 
 def ours_bands(args, lab, dist, torch, world, rank, local):
@@ -318,7 +386,8 @@ def ours_bands(args, lab, dist, torch, world, rank, local):
     workload = args.workload
     game, builder, n, mod, stands_for = WORKLOADS[workload]
     t0 = time.time()
-    maze, spec = make_case(lab, workload, bands=world)  # same seed on every rank -> same maze
+    strong = game == "distance+gather"  # the headline maze itself, cut into `world` bands (a taller one could not be built in minutes)
+    maze, spec = make_case(lab, workload, bands=1 if strong else world)  # same seed on every rank -> same maze (one rank builds, the others read the cache)
     build_s = time.time() - t0
     rows, cols = maze.shape
     r0, nloc = bands.split_rows(rows, world)[rank]
@@ -387,14 +456,14 @@ def ours_bands(args, lab, dist, torch, world, rank, local):
     if rank == 0:
         peak, peak_src = peaks()
         cells = rows * cols
-        alg_bytes = ALG_BYTES_PER_CELL[game] * cells
+        alg_bytes = ALG_BYTES_PER_CELL["distance"] * cells
         achieved = alg_bytes / (search_ms_max / args.steps * 1e-3) / 1e9
         emit_line(json.dumps({
             "metric": "cells settled/sec (G/s) for BFS distance map & bfs-gather; % of HBM roofline",
             "value": settled / (step_ms_max * 1e-3) / 1e9, "unit": "Gcells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+            "ms_per_step": step_ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u16",
             "data": "synthetic",
-            "config": {"workload": workload, "stands_for": stands_for, "game": game, "builder": builder, "mod": mod, "rows": rows, "cols": cols,
+            "config": {"workload": workload, "stands_for": stands_for, "game": "distance" if strong else game, "builder": builder, "mod": mod, "rows": rows, "cols": cols,
                        "seed": SEED + 2, "cells_settled_per_step": settled // args.steps,
                        "parallelism": (f"{world} row bands of one {rows}x{cols} maze, one per GPU; " +
                                        ("sharded spanning-tree pipeline: walk / flood / fix-up on the band's tiles, pointer jumping over all crossings on "
@@ -445,61 +514,77 @@ def cpu_port_baseline(maze, spec, budget_s: float):
 
 
 def reference_arm(args):
-    """--impl reference: the reference's own CPU code on the box's host cores.
+    """--impl reference: the reference's own CPU code on the box's host cores, on OUR arm's config.
 
-    oracle/_ref holds the REAL reference text (compiled in the authoring container, travels as a
-    prebuilt .so).  Its hash (maze/maze.cc:397-405) makes it super-linear, so a step is a bounded
-    sample: the same builder/seed/game at 511x511 (distance) or 383x383 (solvers), which takes
-    seconds.  Distance is single-threaded upstream; the solvers spawn the reference's fixed 4
-    std::threads (solvers/solve_utilities.cc:57) whatever the core count.  Without _ref the oracle
-    port runs the full workload instead."""
+    oracle/_ref holds the REAL reference text (compiled in the authoring container, travels as a prebuilt .so).
+    Its hash (maze/maze.cc:397-405) makes it super-linear (distance: 2 s at 511^2, 51 s at 1023^2; 32767^2 is out of
+    reach by orders of magnitude), so a step is a BOUNDED SAMPLE of the workload: the same builder, seed rule and
+    game at 511x511 (distance) / 383x383 (solvers), built by the reference's own builder text -- nothing of the
+    product is loaded in this process.  Distance is single-threaded upstream; the solvers spawn the reference's
+    fixed 4 std::threads (solvers/solve_utilities.cc:57) whatever the core count.  Our arm's line carries a
+    `same_size_point` measured on exactly these sample mazes.  Without _ref (never the case on the GPU box: the
+    prebuilt files travel) the oracle port runs the sample instead."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    lab = graft.load_package()
     O = graft.load_oracle()
     workload = args.workload
     game, builder, n, mod, stands_for = WORKLOADS[workload]
+    games = ("distance", "gather") if game == "distance+gather" else (game,)
     use_ref = O.have_ref()
-    if use_ref:
-        sn = 511 if game == "distance" else 383
-        maze = lab.build_maze(builder, sn, sn, seed=SEED + 2, mod=None if mod == "pillar" else mod)
-        kind, cores = "reference", (1 if game == "distance" else 4)
-        game_id = {"hunt": O.HUNT, "gather": O.GATHER, "corners": O.CORNERS}.get(game)
-
-        def one():
-            if game == "distance":
-                d = O.ref_distance(maze, seed=1)[1]
-                return int((d != np.uint64(2**64 - 1)).sum())
-            g = O.ref_game(game_id, maze, seed=SEED + 3)
-            return int(((g & O.PAINT_MASK) != 0).sum())
-        sample = f"{builder} {sn}x{sn} (same seed/game), real reference text (oracle/_ref), {cores} thread(s)"
-    else:
-        maze, spec = make_case(lab, workload)
-        sn, kind, cores = n, "port", 1
-
-        def one():
-            return port_once(O, maze, spec)
-        sample = "full workload, oracle port (oracle/_ref not built here)"
-    for _ in range(min(args.warmup, 1)):
-        one()
+    kind = "reference" if use_ref else "port"
     steps = max(1, min(args.steps, 10))
-    t0 = time.perf_counter()
-    settled = 0
-    for _ in range(steps):
-        settled += one()
-    el = time.perf_counter() - t0
-    value = settled / el / 1e9
-    emit_line(json.dumps({
+    results = {}
+    for g in games:
+        sn = REFERENCE_SAMPLE_N[g]
+        rmod = None if mod == "pillar" else mod
+        if use_ref:
+            maze = O.ref_build(builder, sn, sn, seed=SEED + 2, mod=rmod)
+        else:
+            maze = graft.load_package().build_maze(builder, sn, sn, seed=SEED + 2, mod=rmod)
+        game_id = {"hunt": O.HUNT, "gather": O.GATHER, "corners": O.CORNERS}.get(g)
+        cores = 1 if g == "distance" else 4
+
+        def one():
+            if g == "distance":
+                if use_ref:
+                    d = O.ref_distance(maze, seed=1)[1]
+                    return int((d != np.uint64(2**64 - 1)).sum())
+                return O.distance_map(maze)[3]
+            if use_ref:
+                gg = O.ref_game(game_id, maze, seed=SEED + 3)
+            else:
+                placed, st, fin = O.place_gather(maze, SEED + 3) if g == "gather" else (None, None, None)
+                gg = O.canon_gather(placed, st, fin)[0] if g == "gather" else maze
+            return int(((gg & (O.PAINT_MASK | O.CACHE_MASK)) != 0).sum())
+        for _ in range(min(args.warmup, 1)):
+            one()
+        t0 = time.perf_counter()
+        settled = 0
+        for _ in range(steps):
+            settled += one()
+        el = time.perf_counter() - t0
+        results[g] = {"value": settled / el / 1e9, "ms_per_step": el / steps * 1e3, "cores": cores,
+                      "sample": f"{builder} {sn}x{sn}, same seed and game, built by the reference's own builder; "
+                                f"{'real reference text (oracle/_ref)' if use_ref else 'oracle port'}, {cores} thread(s)"}
+    head = results[games[0]]
+    line = {
         "impl": "reference", "metric": "cells settled/sec (G/s) for BFS distance map & bfs-gather; % of HBM roofline",
-        "value": value, "unit": "Gcells/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
-        "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
-        "data": "synthetic", "config": {"workload": workload, "stands_for": stands_for, "game": game, "builder": builder, "mod": mod,
-                                        "rows": sn, "cols": sn, "note": "bounded sample of the workload; the reference is super-linear in maze size"},
-        "cpu_baseline": {"value": value, "unit": "Gcells/s", "cores": cores, "kind": kind, "sample": sample,
+        "value": head["value"], "unit": "Gcells/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+        "data": "synthetic",
+        "config": bench_config(workload, n, n, 1),
+        "cpu_baseline": {"value": head["value"], "unit": "Gcells/s", "cores": head["cores"], "kind": kind, "sample": head["sample"],
                          "host_cores_available": os.cpu_count()},
-        "e2e": {"value": value, "unit": "Gcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+        "e2e": {"value": head["value"], "unit": "Gcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    line["sample_note"] = ("each step is a bounded sample of config's workload (cpu_baseline.sample): the reference is super-linear in maze "
+                           "size and cannot run the full configuration; our arm's `same_size_point` runs exactly these sample mazes")
+    if len(games) > 1:
+        g = results[games[1]]
+        line["gather"] = {"value": g["value"], "unit": "Gcells/s", "ms_per_step": g["ms_per_step"],
+                          "cpu_baseline": {"value": g["value"], "unit": "Gcells/s", "cores": g["cores"], "kind": kind, "sample": g["sample"]}}
+    emit_line(json.dumps(line))
 
 
 _RESULT_FD = None
@@ -525,6 +610,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-same-size-point", action="store_true")
     ap.add_argument("--sharding", default="bands", choices=["bands", "replicas"],
                     help="N > 1: row bands of one tall maze (distance workloads) or one independent maze per GPU")
     args = ap.parse_args()
