@@ -40,6 +40,7 @@ constexpr int LC = 32;             // cells per tile side
 constexpr uint32_t LSLOTS = 128;   // crossing slots of a tile: side * 32 + index, sides CLOCKWISE
 enum Lside : uint32_t { L_N = 0, L_E = 1, L_S = 2, L_W = 3 }; // index = cell column (N, S) / cell row (E, W)
 constexpr uint32_t L_END = 0xFFFFFFFEu, L_NONE = 0xFFFFFFFFu;
+constexpr uint32_t L_LINK = 0xFFFFFFFDu; // the first root's tour is over: the list goes on with the second root's (Tree_ctl::lat_head_b)
 constexpr int LST = 4;                                  // super-tile side, tiles
 constexpr uint32_t LB = 4u * LST * LC;                  // border slots of a super-tile
 constexpr uint32_t LSUP_SLOTS = LST * LST * LSLOTS;     // slots of a super-tile (8192: 13-bit local index)
@@ -101,6 +102,51 @@ LAB_DEV uint32_t lat_twin(Geom const &g, uint32_t t, uint32_t slot) {
     }
 }
 
+// The root.  A start on a cell (odd, odd) is the tree's root.  A start on a PASSAGE square (the solvers' starts are
+// any path square: solve_utilities.cc:275-285) is taken out of the lattice: what is left are two trees, rooted at the
+// passage's two cells, both at level 1; their tours are chained into one list (L_LINK) and every level is
+// 2 * depth + 1.  The passage itself gets level 0 from the tile that holds it.
+struct Lat_roots {
+    int n;               // root cells
+    uint32_t tile[2];
+    int row[2], col[2];  // cell coordinates inside the tile
+    bool passage, horizontal;
+    uint32_t ptile;      // the passage: W passage (horizontal) / N passage of cell (pi, pj) of tile ptile
+    int pi, pj;
+};
+LAB_DEV Lat_roots lat_roots(Params const &p) {
+    Lat_roots r{};
+    uint32_t const t0 = p.ctl->src_tile[0];
+    int const sr = static_cast<int>(p.ctl->src_rc[0] >> 8), sc = static_cast<int>(p.ctl->src_rc[0] & 0xFFu);
+    int const i = sr >> 1, j = sc >> 1;
+    r.ptile = t0;
+    r.pi = i;
+    r.pj = j;
+    if ((sr & 1) && (sc & 1)) {
+        r.n = 1;
+        r.tile[0] = t0;
+        r.row[0] = i;
+        r.col[0] = j;
+        return r;
+    }
+    r.n = 2;
+    r.passage = true;
+    r.horizontal = (sr & 1) != 0;
+    r.tile[1] = t0; // the cell the passage belongs to
+    r.row[1] = i;
+    r.col[1] = j;
+    if (r.horizontal) { // the cell to the left
+        r.tile[0] = j ? t0 : t0 - 1u;
+        r.row[0] = i;
+        r.col[0] = j ? j - 1 : LC - 1;
+    } else { // the cell above
+        r.tile[0] = i ? t0 : t0 - static_cast<uint32_t>(p.g.tiles_x);
+        r.row[0] = i ? i - 1 : LC - 1;
+        r.col[0] = j;
+    }
+    return r;
+}
+
 // A tile's boards in column layout and the step masks of the bit-board BFS.
 struct Lat_tile {
     uint32_t C, Wo, No;         // cells / W passage of the cell open / N passage of the cell open
@@ -144,6 +190,7 @@ LAB_DEV void lat_step(Lat_tile const &T, uint32_t &F, uint32_t &V) {
 LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int lane, uint32_t *sm, uint32_t &arcs) {
     Geom const &g = p.g;
     Tree_ctl *tc = lt.tc;
+    Lat_roots const roots = lat_roots(p);
     uint64_t const P0 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + 2 * lane), P1 = lab_ld_ro(p.path + static_cast<long long>(t) * TS + 2 * lane + 1);
     Lat_tile T;
     T.XN = lat_odd(lab_ld_ro(p.cross + static_cast<long long>(t) * 4 + SIDE_N));
@@ -163,9 +210,25 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
             }
             return;
         }
+        // a root on a passage square: that passage is closed (lat_roots)
+        uint32_t rw2 = rw, rn2 = rn;
+        if (roots.passage) {
+            if (roots.ptile == t && lane == roots.pi) {
+                if (roots.horizontal) rw2 &= ~(1u << roots.pj);
+                else rn2 &= ~(1u << roots.pj);
+            }
+            if (roots.horizontal && roots.pj == 0) {
+                if (roots.ptile == t) T.XW &= ~(1u << roots.pi);
+                if (roots.ptile == t + 1u) T.XE &= ~(1u << roots.pi);
+            }
+            if (!roots.horizontal && roots.pi == 0) {
+                if (roots.ptile == t) T.XN &= ~(1u << roots.pj);
+                if (roots.ptile == t + static_cast<uint32_t>(g.tiles_x)) T.XS &= ~(1u << roots.pj);
+            }
+        }
         T.C = lat_transpose(rc, lane);
-        T.Wo = lat_transpose(rw, lane);
-        T.No = lat_transpose(rn, lane);
+        T.Wo = lat_transpose(rw2, lane);
+        T.No = lat_transpose(rn2, lane);
     }
     lat_step_masks(T, lane);
     {
@@ -180,8 +243,6 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
     arcs += lane == 0 ? static_cast<uint32_t>(lab_popc64(T.XN) + lab_popc64(T.XE) + lab_popc64(T.XS) + lab_popc64(T.XW)) : 0u;
 
     // ---- components, one flood fill each, seeded from the crossing cells not reached yet ----
-    bool const root_tile = p.ctl->src_tile[0] == t;
-    int const rr = root_tile ? static_cast<int>(p.ctl->src_rc[0] >> 8) >> 1 : 0, rcol = root_tile ? static_cast<int>(p.ctl->src_rc[0] & 0xFFu) >> 1 : 0;
     uint32_t U = ((T.XN >> lane) & 1u) | (((T.XS >> lane) & 1u) << 31) | (lane == 0 ? T.XW : 0u) | (lane == 31 ? T.XE : 0u);
     uint32_t labs[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu}; // of slots (side, lane)
     uint32_t L[L_LABEL_PLANES];
@@ -189,16 +250,18 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
     for (int q = 0; q < L_LABEL_PLANES; q++) {
         L[q] = 0;
     }
-    uint32_t k = 0, root_label = 0xFFu;
-    bool root_pending = root_tile;
+    uint32_t k = 0, root_label[2] = {0xFFu, 0xFFu};
+    bool root_pending[2] = {roots.n > 0 && roots.tile[0] == t, roots.n > 1 && roots.tile[1] == t};
+    bool const root_tile = root_pending[0] || root_pending[1];
     for (;;) {
         uint32_t const b = lab_ballot(U != 0);
         uint32_t F;
         if (b) {
             int const l0 = lab_ffs32(b) - 1;
             F = lane == l0 ? (U & (0u - U)) : 0u;
-        } else if (root_pending) { // the root's component has no crossing (a maze inside one tile)
-            F = lane == rcol ? (1u << rr) : 0u;
+        } else if (root_pending[0] || root_pending[1]) { // a root's component has no crossing (a maze inside one tile)
+            int const q = root_pending[0] ? 0 : 1;
+            F = lane == roots.col[q] ? (1u << roots.row[q]) : 0u;
         } else {
             break;
         }
@@ -227,15 +290,23 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
         if ((M >> 31) & (T.XS >> lane) & 1u) labs[L_S] = k;
         if ((west >> lane) & 1u) labs[L_W] = k;
         if ((east >> lane) & 1u) labs[L_E] = k;
-        if (root_pending && ((lab_shfl(M, rcol) >> rr) & 1u)) {
-            root_label = k;
-            root_pending = false;
+        if (root_tile) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (root_pending[q] && ((lab_shfl(M, roots.col[q]) >> roots.row[q]) & 1u)) {
+                    root_label[q] = k;
+                    root_pending[q] = false;
+                }
+            }
         }
         U &= ~M;
         k++;
     }
     if (root_tile && lane == 0) {
-        lab_st_volatile(&tc->lat_root_label, root_label);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            if (roots.n > q && roots.tile[q] == t) lab_st_volatile(&tc->lat_root_label[q], root_label[q]);
+        }
     }
     {
         uint32_t *pl = lt.lplane + static_cast<long long>(t) * (L_LABEL_PLANES * 32);
@@ -265,11 +336,16 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
         }
     }
     lab_syncwarp();
-    uint32_t root_first = L_NONE; // the root component's first slot clockwise: the tour is cut there
-    if (root_tile && root_label != 0xFFu) {
-        for (int s = 3; s >= 0; s--) {
-            uint32_t const f = first[s * 128 + root_label];
-            if (f != 0xFFu) root_first = static_cast<uint32_t>(s) * LC + f;
+    // a root component's first slot clockwise: its tour is cut there (the last root's: the end of the list; with two
+    // roots the first one's tour is followed by the second's)
+    uint32_t root_first[2] = {L_NONE, L_NONE};
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        if (root_label[q] != 0xFFu) {
+            for (int s = 3; s >= 0; s--) {
+                uint32_t const f = first[s * 128 + root_label[q]];
+                if (f != 0xFFu) root_first[q] = static_cast<uint32_t>(s) * LC + f;
+            }
         }
     }
     uint32_t const gt = t;
@@ -295,7 +371,15 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
                 }
             }
             uint32_t const me = static_cast<uint32_t>(s) * LC + static_cast<uint32_t>(lane);
-            out = me == root_first ? L_END : lat_twin(g, gt, nslot);
+            out = lat_twin(g, gt, nslot);
+            if (me == root_first[roots.n - 1]) { // the last root's tour ends here ...
+                if (roots.n == 2) {
+                    lab_st_volatile(&tc->lat_head_b, out + 1u); // ... and would have begun with this arc
+                }
+                out = L_END;
+            } else if (roots.n == 2 && me == root_first[0]) {
+                out = L_LINK;
+            }
         }
         lt.next[static_cast<long long>(t) * LSLOTS + s * LC + lane] = out;
         lt.label[static_cast<long long>(t) * LSLOTS + s * LC + lane] = static_cast<uint8_t>(lab);
@@ -337,6 +421,15 @@ LAB_DEV uint32_t lat_dense_border(Lattice const &lt, Geom const &g, uint32_t arc
     uint32_t const along = (side == L_N || side == L_S) ? tx % LST : ty % LST;
     return S * LB + side * (LST * LC) + along * LC + idx;
 }
+// the arc after arc a; the end of the first root's tour continues with the second root's
+LAB_DEV uint32_t lat_next(Lattice const &lt, long long a) {
+    uint32_t nx = lab_ld_cg(lt.next + a);
+    if (nx == L_LINK) {
+        uint32_t const h = lab_ld_cg(&lt.tc->lat_head_b);
+        nx = h ? h - 1u : L_END;
+    }
+    return nx;
+}
 LAB_DEV void lat_rank_local_super(Params const &p, Lattice const &lt, uint32_t S, int lane, uint32_t *sm) {
     Geom const &g = p.g;
     uint32_t const sy0 = (S / static_cast<uint32_t>(lt.sup_x)) * LST, sx0 = (S % static_cast<uint32_t>(lt.sup_x)) * LST;
@@ -345,8 +438,8 @@ LAB_DEV void lat_rank_local_super(Params const &p, Lattice const &lt, uint32_t S
         uint32_t const ty = sy0 + lt_y, tx = sx0 + lt_x;
         uint32_t e = LX_OUT | i;
         if (ty < static_cast<uint32_t>(g.tiles_y) && tx < static_cast<uint32_t>(g.tiles_x)) {
-            uint32_t const nx = lab_ld_cg(lt.next + (static_cast<long long>(ty) * g.tiles_x + tx) * LSLOTS + slot);
-            if (nx < L_END) {
+            uint32_t const nx = lat_next(lt, (static_cast<long long>(ty) * g.tiles_x + tx) * LSLOTS + slot);
+            if (nx < L_LINK) {
                 uint32_t const nt = nx / LSLOTS, ny = nt / static_cast<uint32_t>(g.tiles_x), nxx = nt % static_cast<uint32_t>(g.tiles_x);
                 if (ny - sy0 < static_cast<uint32_t>(LST) && nxx - sx0 < static_cast<uint32_t>(LST)) {
                     e = (((ny - sy0) * LST + (nxx - sx0)) * LSLOTS + nx % LSLOTS) | (1u << 13);
@@ -387,8 +480,8 @@ LAB_DEV void lat_rank_local_super(Params const &p, Lattice const &lt, uint32_t S
                 uint32_t const e = sm[i];
                 uint32_t const last = e & LX_IDX, hops = ((e & ~LX_OUT) >> 13) + 1u;
                 uint32_t const ly = last / (LST * LSLOTS), lx = (last / LSLOTS) % LST;
-                uint32_t const nx = lab_ld_cg(lt.next + (static_cast<long long>(sy0 + ly) * g.tiles_x + sx0 + lx) * LSLOTS + last % LSLOTS);
-                uint32_t const dense = (nx >= L_END || !(e & LX_OUT)) ? 0xFFFFFFFFu : lat_dense_border(lt, g, nx);
+                uint32_t const nx = lat_next(lt, (static_cast<long long>(sy0 + ly) * g.tiles_x + sx0 + lx) * LSLOTS + last % LSLOTS);
+                uint32_t const dense = (nx >= L_LINK || !(e & LX_OUT)) ? 0xFFFFFFFFu : lat_dense_border(lt, g, nx);
                 pair = static_cast<uint64_t>(dense) | (static_cast<uint64_t>(hops) << 32);
                 lab_st_cg(lt.xd + a, pair);
             }
@@ -521,9 +614,10 @@ LAB_DEV void lat_flood_tile(Params const &p, Lattice const &lt, uint32_t t, int 
         lt.emask[static_cast<long long>(t) * 4 + lane] = lane == L_N ? eN : (lane == L_E ? eE : (lane == L_S ? eS : eW));
     }
     uint32_t F = (entry[L_N] ? 1u : 0u) | (entry[L_S] ? 0x80000000u : 0u) | (lane == 0 ? eW : 0u) | (lane == 31 ? eE : 0u);
-    if (p.ctl->src_tile[0] == t) {
-        int const rr = static_cast<int>(p.ctl->src_rc[0] >> 8) >> 1, rcol = static_cast<int>(p.ctl->src_rc[0] & 0xFFu) >> 1;
-        if (lane == rcol) F |= 1u << rr;
+    Lat_roots const roots = lat_roots(p);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        if (roots.n > q && roots.tile[q] == t && lane == roots.col[q]) F |= 1u << roots.row[q];
     }
     uint32_t V = F, G = 0;
     uint32_t D[L_DEPTH_PLANES];
@@ -566,6 +660,9 @@ LAB_DEV void lat_flood_tile(Params const &p, Lattice const &lt, uint32_t t, int 
     // every cell reached <=> all the tile's passable squares have a level coming
     bad |= (V != T.C) ? 2u : 0u;
     settled += static_cast<unsigned>(lab_popc64(V) + lab_popc64(T.Wo) + lab_popc64(T.No));
+    if (roots.passage && roots.ptile == t && lane == 0) {
+        settled++; // the root passage (closed in the boards)
+    }
     // weights: through a crossing that is not an entry the tour goes DOWN into the neighbour (+w on the twin arc)
     // and comes back UP (-w on this slot's arc); w = depth of the cell at the crossing + 1
     uint32_t DW[L_DEPTH_PLANES], DE[L_DEPTH_PLANES];
@@ -707,9 +804,14 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
             sm[lab & 127u] = 0u - lat_prefix_below(lt, lab_ld_cg(lt.R + base + s * LC + lane));
         }
     }
-    if (p.ctl->src_tile[0] == t && lane == 0) {
-        sm[lt.tc->lat_root_label & 127u] = 0u;
+    Lat_roots const roots = lat_roots(p);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            if (roots.n > q && roots.tile[q] == t) sm[lt.tc->lat_root_label[q] & 127u] = 0u;
+        }
     }
+    uint32_t const off = roots.passage ? 1u : 0u; // a root on a passage: its two cells are at level 1
     lab_syncwarp();
     uint32_t L[L_LABEL_PLANES], D[L_DEPTH_PLANES];
     {
@@ -737,7 +839,7 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
         for (int q = 0; q < L_DEPTH_PLANES; q++) {
             d |= ((D[q] >> i) & 1u) << q;
         }
-        uint32_t const v = 2u * (sm[lab] + d);
+        uint32_t const v = 2u * (sm[lab] + d) + off;
         lv[i] = ((T.C >> i) & 1u) ? v : INF;
         mx = ((T.C >> i) & 1u) && v > mx ? v : mx;
     }
@@ -749,6 +851,7 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
     bool const in0 = c0 < g.cols, in1 = c0 + 1 < g.cols;
     uint32_t *dist = p.plane[0].dist;
     bool const entryN = (em[L_N] >> lane) & 1u;
+    bool const pairs_ok = (reinterpret_cast<uintptr_t>(dist) & 7u) == 0; // (a caller's field may start anywhere)
 #pragma unroll
     for (int i = 0; i < LC; i++) {
         long long const r0 = static_cast<long long>(ty) * TS + 2 * i;
@@ -761,16 +864,38 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
         if ((T.Wo >> i) & 1u) {
             wp = lane ? (me > left ? me : left) - 1u : (((em[L_W] >> i) & 1u) ? me - 1u : me + 1u);
         }
+        // 8-byte stores: cols is odd, so in an even row the pair (c0, c0 + 1) starts on an 8-byte boundary and in an odd
+        // row the pair (c0 - 1, c0) does -- the cell of the lane to the left and this lane's W passage
         if (r0 < g.rows) {
             uint32_t *row = dist + r0 * g.cols + c0;
-            if (in0) row[0] = INF;
-            if (in1) row[1] = np;
+            if (pairs_ok && in1) {
+                lab_st_pair(row, INF, np);
+            } else {
+                if (in0) row[0] = INF;
+                if (in1) row[1] = np;
+            }
         }
         if (r0 + 1 < g.rows) {
             uint32_t *row = dist + (r0 + 1) * g.cols + c0;
-            if (in0) row[0] = wp;
-            if (in1) row[1] = me;
+            if (pairs_ok) {
+                if (lane && in0) {
+                    lab_st_pair(row - 1, left, wp);
+                } else if (lane && c0 - 1 < g.cols) {
+                    row[-1] = left;
+                }
+                if (lane == 0 && in0) row[0] = wp;
+                if (lane == 31 && in1) row[1] = me;
+            } else {
+                if (in0) row[0] = wp;
+                if (in1) row[1] = me;
+            }
         }
+    }
+    lab_syncwarp(); // (the rows' INF at the root passage was another lane's store)
+    if (roots.passage && roots.ptile == t && lane == roots.pj) {
+        long long const r = static_cast<long long>(ty) * TS + 2 * roots.pi + (roots.horizontal ? 1 : 0);
+        long long const c = static_cast<long long>(tx) * TS + 2 * roots.pj + (roots.horizontal ? 0 : 1);
+        dist[r * g.cols + c] = 0u;
     }
     lab_syncwarp();
 }

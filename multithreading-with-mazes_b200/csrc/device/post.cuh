@@ -276,6 +276,72 @@ LAB_DEV void paint_body(Params p, uint16_t *grid, Result *res, long long gthread
     }
     uint32_t painted = 0;
     bool const same_plane = nr <= 1 || (r[0].plane == r[1].plane && r[0].plane == r[2].plane && r[0].plane == r[3].plane);
+    // One field (hunt, gather), both arrays on 16-byte boundaries: eight squares per thread and step -- two 16-byte
+    // loads of levels, one 16-byte read-modify-write of Squares -- and a group whose levels are all at or beyond the
+    // largest threshold is not touched at all.
+    if (same_plane && nr >= 1 && (reinterpret_cast<uintptr_t>(grid) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p.plane[r[0].plane].dist) & 15u) == 0) {
+        uint32_t const *d = p.plane[r[0].plane].dist;
+        uint32_t top = 0;
+        for (uint32_t k = 0; k < nr; k++) {
+            top = r[k].below > top ? r[k].below : top;
+        }
+        long long const groups = n / 8;
+        constexpr int V = 2;
+        for (long long g0 = gthread; g0 < groups; g0 += nthreads * V) {
+            lab_u32x4 a[V], b[V];
+            bool any[V];
+#pragma unroll
+            for (int u = 0; u < V; u++) {
+                long long const gi = g0 + u * nthreads;
+                if (gi < groups) {
+                    a[u] = lab_ld_stream_v4(d + gi * 8);
+                    b[u] = lab_ld_stream_v4(d + gi * 8 + 4);
+                } else {
+                    a[u] = b[u] = lab_u32x4{INF, INF, INF, INF};
+                }
+                uint32_t const lo = lab_umin(lab_umin(lab_umin(a[u].x, a[u].y), lab_umin(a[u].z, a[u].w)), lab_umin(lab_umin(b[u].x, b[u].y), lab_umin(b[u].z, b[u].w)));
+                any[u] = lo < top;
+            }
+#pragma unroll
+            for (int u = 0; u < V; u++) {
+                if (!any[u]) {
+                    continue;
+                }
+                long long const gi = g0 + u * nthreads;
+                uint32_t const lv[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
+                uint32_t bits[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    bits[q] = 0;
+                    for (uint32_t k = 0; k < nr; k++) {
+                        bits[q] |= lv[q] < r[k].below ? r[k].bits : 0u;
+                    }
+                    painted += bits[q] ? 1u : 0u;
+                }
+                lab_u32x4 sq = lab_ld_stream_v4(grid + gi * 8);
+                sq.x |= bits[0] | (bits[1] << 16);
+                sq.y |= bits[2] | (bits[3] << 16);
+                sq.z |= bits[4] | (bits[5] << 16);
+                sq.w |= bits[6] | (bits[7] << 16);
+                lab_st_v4(grid + gi * 8, sq);
+            }
+        }
+        for (long long i = groups * 8 + gthread; i < n; i += nthreads) { // the last few squares
+            uint32_t bits = 0;
+            for (uint32_t k = 0; k < nr; k++) {
+                bits |= d[i] < r[k].below ? r[k].bits : 0u;
+            }
+            if (bits) {
+                grid[i] |= static_cast<uint16_t>(bits);
+                painted++;
+            }
+        }
+        painted = lab_reduce_add(painted);
+        if ((gthread & 31) == 0 && painted) {
+            lab_atomic_add(reinterpret_cast<uint64_t *>(&res->settled), static_cast<uint64_t>(painted));
+        }
+        return;
+    }
     constexpr int U = 8; // independent loads in flight per thread (a streaming pass: HBM latency x bandwidth)
     for (long long i0 = gthread; i0 < n; i0 += nthreads * U) {
         uint32_t dv[U];

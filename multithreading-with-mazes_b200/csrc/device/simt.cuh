@@ -76,6 +76,7 @@ LAB_DEV lab_u32x2 lab_ld_cg_x2(uint32_t const *base, uint32_t i) {
     return {t.x, t.y};
 }
 LAB_DEV void lab_st_x2(uint32_t *base, uint32_t i, uint32_t x, uint32_t y) { reinterpret_cast<uint2 *>(base)[i] = make_uint2(x, y); }
+LAB_DEV void lab_st_pair(uint32_t *p, uint32_t x, uint32_t y) { *reinterpret_cast<uint2 *>(p) = make_uint2(x, y); } // p on an 8-byte boundary
 LAB_DEV void lab_st_volatile(uint32_t *p, uint32_t v) { *reinterpret_cast<uint32_t volatile *>(p) = v; }
 
 LAB_DEV uint32_t lab_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }

@@ -57,7 +57,8 @@ struct Tree_ctl {
     // the lattice road (device/lattice.cuh), tried first on mazes carved on the lattice of odd squares
     uint32_t lat_err;        // why it gave up (1 not a lattice, 2 labels, 3 tour, 4 floods, 5 weights); nothing was written then
     uint32_t lat_on;         // tree_init_body: the counts allow a tree and the host found odd sizes and an (odd, odd) start
-    uint32_t lat_root_label; // the root component's label in the root's tile
+    uint32_t lat_root_label[2]; // the root components' labels in their tiles (two roots: a start on a passage square)
+    uint32_t lat_head_b;     // 1 + the arc the second root's tour begins with (0: it has none)
     uint32_t lat_flood_bad;
     uint32_t lat_ticket[4];  // dynamic tile counters: link, local ranking, flood, levels
     unsigned long long lat_settled;

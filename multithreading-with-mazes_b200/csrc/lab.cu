@@ -561,9 +561,10 @@ bool tree_may_run(lab_grid const *h, Run_desc const &d) {
     return !h->band_mode && d.nplanes == 1 && d.src_r[0] >= 0 && env_ll("LAB_TREE", 1) != 0;
 }
 
-// The lattice road (device/lattice.cuh) is tried where the maze can be one: odd sizes, the start on an (odd, odd) square.
+// The lattice road (device/lattice.cuh) is tried where the maze can be one: odd sizes, the start on a cell or a passage
+// (not on an (even, even) square: those are the lattice's pillars).
 bool lattice_may_run(lab_grid const *h, Run_desc const &d) {
-    return tree_may_run(h, d) && env_ll("LAB_LATTICE", 1) != 0 && (h->g.rows & 1) && (h->g.cols & 1) && (d.src_r[0] & 1) && (d.src_c[0] & 1);
+    return tree_may_run(h, d) && env_ll("LAB_LATTICE", 1) != 0 && (h->g.rows & 1) && (h->g.cols & 1) && ((d.src_r[0] | d.src_c[0]) & 1);
 }
 
 // Reset the workspace and pack the grid into tile bit masks (sources forced passable).

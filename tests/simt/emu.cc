@@ -51,7 +51,7 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
     tr.nslots = static_cast<uint32_t>(nt * SLOTS);
     tr.mark_bits = d.game == GAME_DISTANCE ? SQ_MEASURE : 0u;
     simt::launch(nwarps, [&](int wid, int lane) { tree_count_body(p, tr, wid, nwarps, lane); });
-    bool const lat_try = g_lattice_mode && (w.g.rows & 1) && (w.g.cols & 1) && (d.src_r[0] & 1) && (d.src_c[0] & 1);
+    bool const lat_try = g_lattice_mode && (w.g.rows & 1) && (w.g.cols & 1) && ((d.src_r[0] | d.src_c[0]) & 1);
     tr.lat_try = lat_try ? 1u : 0u;
     tree_init_body(p, tr);
     if (lat_try) { // the lattice road, orchestrated as run_lattice() in csrc/lab.cu does
@@ -198,7 +198,7 @@ int emu_distance(int rows, int cols, uint16_t *grid, int sr, int sc, uint32_t *d
     d.src_c[0] = sc;
     d.bound_mode = BOUND_NONE;
     // (as lab_distance_map: where the lattice road is tried, pack sets the measure bits in advance)
-    d.spec_mark = (g_tree_mode && g_lattice_mode && (rows & 1) && (cols & 1) && (sr & 1) && (sc & 1)) ? SQ_MEASURE : 0u;
+    d.spec_mark = (g_tree_mode && g_lattice_mode && (rows & 1) && (cols & 1) && ((sr | sc) & 1)) ? SQ_MEASURE : 0u;
     int rc = search(w, grid, rows, cols, d, SQ_PATH | SQ_MEASURE, SQ_PATH, nwarps, sched_seed);
     if (rc) return rc;
     Params p = make_params(w, 1);

@@ -258,6 +258,14 @@ LAB_DEV void lab_st_x2(uint32_t *base, uint32_t i, uint32_t x, uint32_t y) {
     base[2 * static_cast<size_t>(i)] = x;
     base[2 * static_cast<size_t>(i) + 1] = y;
 }
+LAB_DEV void lab_st_pair(uint32_t *p, uint32_t x, uint32_t y) {
+    if (reinterpret_cast<uintptr_t>(p) & 7u) {
+        std::fprintf(stderr, "simt: lab_st_pair to an address that is not on an 8-byte boundary\n");
+        std::abort();
+    }
+    p[0] = x;
+    p[1] = y;
+}
 LAB_DEV void lab_st_volatile(uint32_t *p, uint32_t v) { *p = v; }
 
 template <class T> LAB_DEV T lab_atomic_add(T *p, typename std::common_type<T>::type v) {

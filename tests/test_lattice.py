@@ -72,13 +72,46 @@ def test_emulated_any_odd_root(lab, O, emu, start):
     assert (d == d_ref).all() and mx == int(d_ref[reached].max()) and settled == int(reached.sum())
 
 
-def test_emulated_root_on_a_passage_takes_the_general_pipeline(lab, O, emu):
-    maze = lab.build_maze("kruskal", 129, 131, seed=6)
-    r, c = next((r, c) for r in range(61, 70, 2) for c in range(60, 70, 2) if maze[r, c] & lab.PATH_BIT)  # (odd, even): a passage
-    d_ref = O.bfs_levels(maze, r, c)
-    g, d, mx, settled, _ = emu.distance(maze, start=(r, c), nwarps=4, sched=1)
-    assert emu.lib.emu_last_tree_used() == GENERAL
-    assert (d == d_ref).all()
+def passage_squares(lab, maze):
+    """(odd, even) and (even, odd) path squares: next to tile borders, ON tile borders (column / row 64, 128), in corners."""
+    rows, cols = maze.shape
+    want = [(1, 2), (2, 1), (63, 64), (64, 63), (65, 64), (64, 65), (63, 62), (62, 63), (127, 128), (128, 127), (rows - 2, cols - 3), (rows - 3, cols - 2),
+            (33, 100), (100, 33)]
+    out = []
+    for r0, c0 in want:
+        # the nearest passable square with the same parities
+        for dr in range(0, rows, 2):
+            hit = [(r, c) for r in (r0 - dr, r0 + dr) for dc in range(0, 40, 2) for c in (c0 - dc, c0 + dc)
+                   if 0 < r < rows - 1 and 0 < c < cols - 1 and maze[r, c] & lab.PATH_BIT]
+            if hit:
+                out.append(hit[0])
+                break
+    return sorted(set(out))
+
+
+def test_emulated_roots_on_passages(lab, O, emu):
+    """The solvers start anywhere (solve_utilities.cc:275-285): a start on a passage square splits the lattice into two
+    trees whose tours are chained."""
+    maze = lab.build_maze("kruskal", 131, 195, seed=6)
+    starts = passage_squares(lab, maze)
+    assert len(starts) >= 10 and any(c % 64 == 0 for r, c in starts) and any(r % 64 == 0 for r, c in starts)
+    for k, (r, c) in enumerate(starts):
+        assert (r + c) % 2 == 1
+        d_ref = O.bfs_levels(maze, r, c)
+        g, d, mx, settled, _ = emu.distance(maze, start=(r, c), nwarps=4, sched=k)
+        assert emu.lib.emu_last_tree_used() == LATTICE, (r, c)
+        reached = d_ref != 0xFFFFFFFF
+        assert (d == d_ref).all() and mx == int(d_ref[reached].max()) and settled == int(reached.sum()), (r, c)
+        assert (((g & lab.MEASURE_BIT) != 0) == reached).all()
+
+
+def test_emulated_root_on_a_passage_inside_one_tile(lab, O, emu):
+    maze = lab.build_maze("wilson", 31, 41, seed=2)
+    for (r, c) in passage_squares(lab, maze)[:6]:
+        d_ref = O.bfs_levels(maze, r, c)
+        g, d, mx, settled, _ = emu.distance(maze, start=(r, c), nwarps=2, sched=1)
+        assert emu.lib.emu_last_tree_used() == LATTICE
+        assert (d == d_ref).all()
 
 
 def off_lattice_tree(lab, rows, cols, seed):
@@ -122,11 +155,10 @@ def test_emulated_games_on_the_lattice(lab, O, emu):
         placed, s, f = lab.place_hunt(maze, seed=seed)
         g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
         g, w, _, paths, _ = emu.solver(1, placed, [s], [f], 4, 1)
-        road = emu.lib.emu_last_tree_used()
-        assert road == (LATTICE if s[0] % 2 and s[1] % 2 else GENERAL)
-        seen.add(road)
+        assert emu.lib.emu_last_tree_used() == LATTICE
+        seen.add((s[0] % 2, s[1] % 2))
         assert (g == g_ref).all() and w == w_ref and paths_equal([paths[0]], [p_ref])
-    assert LATTICE in seen
+    assert len(seen) >= 2  # starts on cells and on passages
     for seed in range(60, 64):
         placed, s, fin = lab.place_gather(maze, seed=seed)
         g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
@@ -204,7 +236,7 @@ def test_gpu_games_on_the_lattice(lab, O):
             roads.add(g.stats()["tree_used"])
         g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
         assert (after == g_ref).all() and res.winner == w_ref and paths_equal(res.paths, [p_ref])
-    assert roads == {LATTICE, GENERAL}
+    assert roads == {LATTICE}
 
 
 @pytest.mark.gpu
