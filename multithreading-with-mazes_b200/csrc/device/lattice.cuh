@@ -44,15 +44,19 @@ constexpr uint32_t L_LINK = 0xFFFFFFFDu; // the first root's tour is over: the l
 constexpr int LST = 4;                                  // super-tile side, tiles
 constexpr uint32_t LB = 4u * LST * LC;                  // border slots of a super-tile
 constexpr uint32_t LSUP_SLOTS = LST * LST * LSLOTS;     // slots of a super-tile (8192: 13-bit local index)
-constexpr int L_LABEL_PLANES = 7, L_DEPTH_PLANES = 10;
+constexpr int L_LABEL_PLANES = 5, L_DEPTH_PLANES = 10;      // a cell's piece number inside its 8x8 board / its depth below its component's entry
+constexpr uint32_t L_LINK_SM = 768 + 512;               // words of shared memory per warp: lat_link_tile, lat_levels_tile
+constexpr bool L_PAIR_STORES = false;                   // 8-byte stores of the level rows (see lat_levels_tile)
 constexpr uint32_t L_CHUNK = 1024;                      // tour positions per scan chunk
 
 struct Lattice {
     uint32_t *mask;   // [ntiles][3][32]  cell boards in COLUMN layout (lane = cell column, bit = cell row): cells, W passage open, N passage open
     uint32_t *xmask;  // [ntiles][4]      open crossings per side (bit = index)
     uint32_t *next;   // [ntiles][128]    the arc the tour continues with after entering through this slot (global arc id), L_END, L_NONE
-    uint8_t *label;   // [ntiles][128]    component of the slot's cell
-    uint32_t *lplane; // [ntiles][7][32]  component label of every cell, bit-sliced
+    uint16_t *label;  // [ntiles][128]    component of the slot's cell (= the component's lowest piece id)
+    uint32_t *lplane; // [ntiles][5][32]  piece number of every cell inside its 8x8 board, bit-sliced (piece id = board * 32 + number)
+    uint16_t *cmap;   // [ntiles][512]    component of piece (number, board) at [number * 16 + board], numbers < nruns[tile]
+    uint32_t *nruns;  // [ntiles]
     uint64_t *xd;     // [ntiles][128]    after the local ranking: (dense border slot the chain leaves the super-tile to | hops to there << 32)
     uint64_t *gb;     // [nsuper][LB]     the border arcs' list: (next dense border slot | hops << 32), jumped in place
     uint32_t *R;      // [ntiles][128]    hops to the end of the tour (>= 1; larger = earlier)
@@ -186,7 +190,7 @@ LAB_DEV void lat_step(Lat_tile const &T, uint32_t &F, uint32_t &V) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 1 link.  Warp per tile.  sm: 128 words of shared memory per warp.
+// 1 link.  Warp per tile.  sm: L_LINK_SM words of shared memory per warp.
 LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int lane, uint32_t *sm, uint32_t &arcs) {
     Geom const &g = p.g;
     Tree_ctl *tc = lt.tc;
@@ -242,71 +246,82 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
     }
     arcs += lane == 0 ? static_cast<uint32_t>(lab_popc64(T.XN) + lab_popc64(T.XE) + lab_popc64(T.XS) + lab_popc64(T.XW)) : 0u;
 
-    // ---- components, one flood fill each, seeded from the crossing cells not reached yet ----
-    uint32_t U = ((T.XN >> lane) & 1u) | (((T.XS >> lane) & 1u) << 31) | (lane == 0 ? T.XW : 0u) | (lane == 31 ? T.XE : 0u);
-    uint32_t labs[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu}; // of slots (side, lane)
+    // ---- A: sixteen 8x8 BOARDS at once.  With the links between boards masked out a flood-fill step of the whole tile is
+    // sixteen independent steps, so every run floods one component PIECE per board (seeded from the board's first cell
+    // with a link out of the board that no earlier run reached).  All pieces of run r get the piece number r: a cell's
+    // piece id is  board * 32 + r  (sid), five bit planes for the whole tile. ----
+    uint32_t *parent = sm;                                                // [512] union-find over piece ids
+    uint16_t *rootof = reinterpret_cast<uint16_t *>(sm + 512);            // [512] component (= its lowest piece id) of a piece
+    uint8_t *first = reinterpret_cast<uint8_t *>(sm + 768);               // [4][512] see C
+    Lat_tile B = T;
+    B.mS &= 0xFEFEFEFEu;
+    B.mN &= 0x7F7F7F7Fu;
+    B.mE = (lane & 7) ? B.mE : 0u;
+    B.mW = ((lane & 7) != 7) ? B.mW : 0u;
+    uint32_t const right_wo = lab_shfl_down(T.Wo, 1);
+    uint32_t U = (T.No & 0x01010101u) | ((T.No >> 1) & 0x00808080u) | (((T.XS >> lane) & 1u) << 31) | ((lane & 7) == 0 ? T.Wo : 0u) |
+                 ((lane & 7) == 7 ? (lane == 31 ? T.XE : right_wo) : 0u);
+    U &= T.C;
     uint32_t L[L_LABEL_PLANES];
 #pragma unroll
     for (int q = 0; q < L_LABEL_PLANES; q++) {
         L[q] = 0;
     }
-    uint32_t k = 0, root_label[2] = {0xFFu, 0xFFu};
+    uint32_t runs = 0, root_sid[2] = {0xFFFFu, 0xFFFFu}, all = 0;
     bool root_pending[2] = {roots.n > 0 && roots.tile[0] == t, roots.n > 1 && roots.tile[1] == t};
     bool const root_tile = root_pending[0] || root_pending[1];
     for (;;) {
-        uint32_t const b = lab_ballot(U != 0);
-        uint32_t F;
-        if (b) {
-            int const l0 = lab_ffs32(b) - 1;
-            F = lane == l0 ? (U & (0u - U)) : 0u;
-        } else if (root_pending[0] || root_pending[1]) { // a root's component has no crossing (a maze inside one tile)
-            int const q = root_pending[0] ? 0 : 1;
-            F = lane == roots.col[q] ? (1u << roots.row[q]) : 0u;
-        } else {
-            break;
+        uint32_t F = 0;
+#pragma unroll
+        for (int bi = 0; bi < 4; bi++) {
+            uint32_t const byte = (U >> (8 * bi)) & 0xFFu;
+            uint32_t const grp = (lab_ballot(byte != 0) >> (lane & 24)) & 0xFFu; // which of the board's eight columns have a seed
+            if (byte && (lane & 7) == lab_ffs32(grp) - 1) {
+                F |= (byte & (0u - byte)) << (8 * bi);
+            }
         }
-        if (k >= LSLOTS - 1u) { // more components than crossings: cannot be
+        if (!lab_any(F != 0)) {
+            if (root_pending[0] || root_pending[1]) { // a root whose piece has no link out of its board (a maze inside one board)
+                int const q = root_pending[0] ? 0 : 1;
+                F = lane == roots.col[q] ? (1u << roots.row[q]) : 0u;
+            } else {
+                break;
+            }
+        }
+        if (runs >= 32u) { // more pieces in one board than it has border cells: cannot be
             if (lane == 0) lab_st_volatile(&tc->lat_err, 2u);
             return;
         }
         uint32_t M = F;
-        for (int it = 0; it < LC * LC / 4 + 1; it++) {
-            lat_step(T, F, M);
-            lat_step(T, F, M);
-            lat_step(T, F, M);
-            lat_step(T, F, M);
+        for (int it = 0; it < 64 / 2 + 1; it++) {
+            lat_step(B, F, M);
+            lat_step(B, F, M);
             if (!lab_any(F != 0)) {
                 break;
             }
         }
 #pragma unroll
         for (int q = 0; q < L_LABEL_PLANES; q++) {
-            if ((k >> q) & 1u) {
+            if ((runs >> q) & 1u) {
                 L[q] |= M;
             }
         }
-        uint32_t const west = lab_shfl(M, 0) & T.XW, east = lab_shfl(M, 31) & T.XE;
-        if (M & 1u & (T.XN >> lane)) labs[L_N] = k;
-        if ((M >> 31) & (T.XS >> lane) & 1u) labs[L_S] = k;
-        if ((west >> lane) & 1u) labs[L_W] = k;
-        if ((east >> lane) & 1u) labs[L_E] = k;
         if (root_tile) {
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 if (root_pending[q] && ((lab_shfl(M, roots.col[q]) >> roots.row[q]) & 1u)) {
-                    root_label[q] = k;
+                    root_sid[q] = static_cast<uint32_t>((roots.row[q] >> 3) * 4 + (roots.col[q] >> 3)) * 32u + runs;
                     root_pending[q] = false;
                 }
             }
         }
+        all |= M;
         U &= ~M;
-        k++;
+        runs++;
     }
-    if (root_tile && lane == 0) {
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            if (roots.n > q && roots.tile[q] == t) lab_st_volatile(&tc->lat_root_label[q], root_label[q]);
-        }
+    if (lab_any(all != T.C)) { // cells no run reached: a part of the maze without a way out of its board -- not one tree
+        if (lane == 0) lab_st_volatile(&tc->lat_err, 4u);
+        return;
     }
     {
         uint32_t *pl = lt.lplane + static_cast<long long>(t) * (L_LABEL_PLANES * 32);
@@ -315,23 +330,114 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
             pl[q * 32 + lane] = L[q];
         }
     }
-    // ---- the tour: from a slot to the next slot of the same component, clockwise (N ->, E down, S <-, W up) ----
-    // sm[side * 32 + (label / 4)] bytes: first slot index of the label on that side in clockwise order (0xFF: none)
-    uint8_t *first = reinterpret_cast<uint8_t *>(sm);
+    // ---- B: pieces joined through the open links between boards are one component: union-find over the piece ids (the
+    // larger root is hooked under the smaller, so roots only decrease and concurrent unions cannot form a cycle) ----
 #pragma unroll
-    for (int s = 0; s < 4; s++) {
-        sm[s * 32 + lane] = 0xFFFFFFFFu;
+    for (int k = 0; k < 16; k++) {
+        parent[k * 32 + lane] = static_cast<uint32_t>(k * 32 + lane);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        sm[768 + k * 128 + lane] = 0xFFFFFFFFu; // `first`
+        sm[768 + k * 128 + 32 + lane] = 0xFFFFFFFFu;
+        sm[768 + k * 128 + 64 + lane] = 0xFFFFFFFFu;
+        sm[768 + k * 128 + 96 + lane] = 0xFFFFFFFFu;
     }
     lab_syncwarp();
+    auto piece = [&](uint32_t const (&P)[L_LABEL_PLANES], int bit) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int q = 0; q < L_LABEL_PLANES; q++) {
+            r |= ((P[q] >> bit) & 1u) << q;
+        }
+        return r;
+    };
+    auto unite = [&](uint32_t a, uint32_t b) {
+        for (int guard = 0; guard < 1024; guard++) {
+            for (uint32_t pa; (pa = lab_ld_volatile(parent + a)) != a;) a = pa;
+            for (uint32_t pb; (pb = lab_ld_volatile(parent + b)) != b;) b = pb;
+            if (a == b) {
+                return;
+            }
+            uint32_t const hi = a > b ? a : b, lo = a > b ? b : a;
+            if (lab_atomic_cas(parent + hi, hi, lo) == hi) {
+                return;
+            }
+        }
+    };
+    // links between vertically adjacent boards: rows 8, 16, 24 of this lane's column
+#pragma unroll
+    for (int bi = 1; bi < 4; bi++) {
+        if ((T.No >> (8 * bi)) & 1u) {
+            unite(static_cast<uint32_t>(bi * 4 + (lane >> 3)) * 32u + piece(L, 8 * bi), static_cast<uint32_t>((bi - 1) * 4 + (lane >> 3)) * 32u + piece(L, 8 * bi - 1));
+        }
+    }
+    // links between horizontally adjacent boards: columns 8, 16, 24; lane = row
+#pragma unroll
+    for (int bj = 1; bj < 4; bj++) {
+        uint32_t PR[L_LABEL_PLANES], PL[L_LABEL_PLANES];
+#pragma unroll
+        for (int q = 0; q < L_LABEL_PLANES; q++) {
+            PR[q] = lab_shfl(L[q], 8 * bj);
+            PL[q] = lab_shfl(L[q], 8 * bj - 1);
+        }
+        uint32_t const wo = lab_shfl(T.Wo, 8 * bj);
+        if ((wo >> lane) & 1u) {
+            unite(static_cast<uint32_t>((lane >> 3) * 4 + bj) * 32u + piece(PR, lane), static_cast<uint32_t>((lane >> 3) * 4 + bj - 1) * 32u + piece(PL, lane));
+        }
+    }
+    lab_syncwarp();
+    {
+        uint16_t *cmap = lt.cmap + static_cast<long long>(t) * 512;
+        for (uint32_t idx = static_cast<uint32_t>(lane); idx < runs * 16u; idx += 32u) { // piece (run idx / 16) of board idx % 16
+            uint32_t const sid = (idx & 15u) * 32u + (idx >> 4);
+            uint32_t a = sid;
+            for (uint32_t pa; (pa = parent[a]) != a;) a = pa;
+            rootof[sid] = static_cast<uint16_t>(a);
+            cmap[idx] = static_cast<uint16_t>(a);
+        }
+        if (lane == 0) {
+            lt.nruns[t] = runs;
+        }
+    }
+    lab_syncwarp();
+    // ---- C: the tour: from a slot to the next slot of the same component, clockwise (N ->, E down, S <-, W up) ----
+    uint32_t labs[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu}; // component of slots (side, lane)
+    {
+        uint32_t PW[L_LABEL_PLANES], PE[L_LABEL_PLANES];
+#pragma unroll
+        for (int q = 0; q < L_LABEL_PLANES; q++) {
+            PW[q] = lab_shfl(L[q], 0);
+            PE[q] = lab_shfl(L[q], 31);
+        }
+        if ((T.XN >> lane) & 1u) labs[L_N] = rootof[static_cast<uint32_t>(lane >> 3) * 32u + piece(L, 0)];
+        if ((T.XS >> lane) & 1u) labs[L_S] = rootof[static_cast<uint32_t>(12 + (lane >> 3)) * 32u + piece(L, 31)];
+        if ((T.XW >> lane) & 1u) labs[L_W] = rootof[static_cast<uint32_t>((lane >> 3) * 4) * 32u + piece(PW, lane)];
+        if ((T.XE >> lane) & 1u) labs[L_E] = rootof[static_cast<uint32_t>((lane >> 3) * 4 + 3) * 32u + piece(PE, lane)];
+    }
+    uint32_t root_label[2] = {0xFFFFu, 0xFFFFu};
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        if (root_sid[q] != 0xFFFFu) {
+            root_label[q] = rootof[root_sid[q]];
+        }
+    }
+    if (root_tile && lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            if (roots.n > q && roots.tile[q] == t) lab_st_volatile(&tc->lat_root_label[q], root_label[q]);
+        }
+    }
+    // first[side][component]: the component's first slot on that side in clockwise order (0xFF: none)
     uint32_t peers[4];
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         peers[s] = lab_match_any(labs[s]);
-        if (labs[s] != 0xFFu) {
+        if (labs[s] != 0xFFFFu) {
             bool const ascending = s == L_N || s == L_E;
             int const lead = ascending ? lab_ffs32(peers[s]) - 1 : 31 - lab_clz32(peers[s]);
             if (lead == lane) {
-                first[s * 128 + labs[s]] = static_cast<uint8_t>(lane);
+                first[s * 512 + labs[s]] = static_cast<uint8_t>(lane);
             }
         }
     }
@@ -341,9 +447,9 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
     uint32_t root_first[2] = {L_NONE, L_NONE};
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-        if (root_label[q] != 0xFFu) {
+        if (root_label[q] != 0xFFFFu) {
             for (int s = 3; s >= 0; s--) {
-                uint32_t const f = first[s * 128 + root_label[q]];
+                uint32_t const f = first[s * 512 + root_label[q]];
                 if (f != 0xFFu) root_first[q] = static_cast<uint32_t>(s) * LC + f;
             }
         }
@@ -353,7 +459,7 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
     for (int s = 0; s < 4; s++) {
         uint32_t out = L_NONE;
         uint32_t const lab = labs[s];
-        if (lab != 0xFFu) {
+        if (lab != 0xFFFFu) {
             bool const ascending = s == L_N || s == L_E;
             uint32_t const rest = ascending ? (peers[s] & ~((2u << lane) - 1u)) : (peers[s] & ((1u << lane) - 1u));
             uint32_t nslot;
@@ -364,7 +470,7 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
 #pragma unroll
                 for (int d = 1; d <= 4; d++) {
                     int const s2 = (s + d) & 3;
-                    uint32_t const f = first[s2 * 128 + lab];
+                    uint32_t const f = first[s2 * 512 + lab];
                     if (nslot == L_NONE && f != 0xFFu) {
                         nslot = static_cast<uint32_t>(s2) * LC + f;
                     }
@@ -382,7 +488,7 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
             }
         }
         lt.next[static_cast<long long>(t) * LSLOTS + s * LC + lane] = out;
-        lt.label[static_cast<long long>(t) * LSLOTS + s * LC + lane] = static_cast<uint8_t>(lab);
+        lt.label[static_cast<long long>(t) * LSLOTS + s * LC + lane] = static_cast<uint16_t>(lab);
     }
     lab_syncwarp();
 }
@@ -785,61 +891,82 @@ LAB_DEV uint32_t lat_prefix_below(Lattice const &lt, uint32_t r) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 5 levels.  Warp per tile; sm: 128 words (entry depth per component label).
+// 5 levels.  Warp per tile; sm: L_LINK_SM words.
 LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int lane, uint32_t *sm, uint32_t &mx) {
     Geom const &g = p.g;
     Lat_tile const T = lat_load(lt, t, lane);
-    uint32_t const X[4] = {T.XN, T.XE, T.XS, T.XW};
     long long const base = static_cast<long long>(t) * LSLOTS;
     uint32_t em[4];
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         em[s] = lab_ld_cg(lt.emask + static_cast<long long>(t) * 4 + s);
     }
+    // shared memory: entry depth per component [512] | component of a piece [512 x 16 bit] | entry depth per piece [512]
+    uint32_t *ecomp = sm;
+    uint16_t *rootof = reinterpret_cast<uint16_t *>(sm + 512);
+    uint32_t *epiece = sm + 768;
     // entry depth of every component: minus the weights of the arcs later on the tour than its entry arc
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         if ((em[s] >> lane) & 1u) {
             uint32_t const lab = lab_ld_cg(lt.label + base + s * LC + lane);
-            sm[lab & 127u] = 0u - lat_prefix_below(lt, lab_ld_cg(lt.R + base + s * LC + lane));
+            ecomp[lab & 511u] = 0u - lat_prefix_below(lt, lab_ld_cg(lt.R + base + s * LC + lane));
         }
     }
     Lat_roots const roots = lat_roots(p);
     if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-            if (roots.n > q && roots.tile[q] == t) sm[lt.tc->lat_root_label[q] & 127u] = 0u;
+            if (roots.n > q && roots.tile[q] == t) ecomp[lt.tc->lat_root_label[q] & 511u] = 0u;
         }
     }
     uint32_t const off = roots.passage ? 1u : 0u; // a root on a passage: its two cells are at level 1
+    uint32_t const runs = lab_ld_cg(lt.nruns + t);
     lab_syncwarp();
-    uint32_t L[L_LABEL_PLANES], D[L_DEPTH_PLANES];
+    {
+        uint16_t const *cmap = lt.cmap + static_cast<long long>(t) * 512;
+        for (uint32_t idx = static_cast<uint32_t>(lane); idx < runs * 16u; idx += 32u) {
+            epiece[(idx & 15u) * 32u + (idx >> 4)] = ecomp[lab_ld_cg(cmap + idx) & 511u];
+        }
+    }
+    lab_syncwarp();
+    // Bit planes -> one word per cell: a 32 x 32 bit transpose in registers (rows 0-4 the piece number, 5-14 the depth)
+    uint32_t A[32];
     {
         uint32_t const *pl = lt.lplane + static_cast<long long>(t) * (L_LABEL_PLANES * 32);
         uint32_t const *pd = lt.dplane + static_cast<long long>(t) * (L_DEPTH_PLANES * 32);
 #pragma unroll
         for (int q = 0; q < L_LABEL_PLANES; q++) {
-            L[q] = lab_ld_cg(pl + q * 32 + lane);
+            A[q] = lab_ld_cg(pl + q * 32 + lane);
         }
 #pragma unroll
         for (int q = 0; q < L_DEPTH_PLANES; q++) {
-            D[q] = lab_ld_cg(pd + q * 32 + lane);
+            A[L_LABEL_PLANES + q] = lab_ld_cg(pd + q * 32 + lane);
+        }
+#pragma unroll
+        for (int q = L_LABEL_PLANES + L_DEPTH_PLANES; q < 32; q++) {
+            A[q] = 0;
+        }
+        uint32_t m = 0x0000FFFFu;
+#pragma unroll
+        for (int jj = 16; jj != 0; jj >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 32; k = (k + jj + 1) & ~jj) {
+                uint32_t const x = ((A[k] >> jj) ^ A[k + jj]) & m;
+                A[k] ^= x << jj;
+                A[k + jj] ^= x;
+            }
+            m ^= m << (jj >> 1);
         }
     }
     // lane = cell column j: its 32 cells' levels (INF: no cell)
     uint32_t lv[LC];
+    uint32_t const board_col = static_cast<uint32_t>(lane >> 3) * 32u;
 #pragma unroll
     for (int i = 0; i < LC; i++) {
-        uint32_t lab = 0, d = 0;
-#pragma unroll
-        for (int q = 0; q < L_LABEL_PLANES; q++) {
-            lab |= ((L[q] >> i) & 1u) << q;
-        }
-#pragma unroll
-        for (int q = 0; q < L_DEPTH_PLANES; q++) {
-            d |= ((D[q] >> i) & 1u) << q;
-        }
-        uint32_t const v = 2u * (sm[lab] + d) + off;
+        uint32_t const sid = static_cast<uint32_t>((i >> 3) * 4) * 32u + board_col + (A[i] & 31u);
+        uint32_t const d = (A[i] >> L_LABEL_PLANES) & 1023u;
+        uint32_t const v = 2u * (epiece[sid] + d) + off;
         lv[i] = ((T.C >> i) & 1u) ? v : INF;
         mx = ((T.C >> i) & 1u) && v > mx ? v : mx;
     }
@@ -851,7 +978,9 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
     bool const in0 = c0 < g.cols, in1 = c0 + 1 < g.cols;
     uint32_t *dist = p.plane[0].dist;
     bool const entryN = (em[L_N] >> lane) & 1u;
-    bool const pairs_ok = (reinterpret_cast<uintptr_t>(dist) & 7u) == 0; // (a caller's field may start anywhere)
+    // (measured on B200 at 32767^2: the 8-byte variant below is SLOWER than plain 4-byte stores, 1.78 ms against 1.50 ms;
+    // kept switchable for the profile's sake)
+    bool const pairs_ok = L_PAIR_STORES && (reinterpret_cast<uintptr_t>(dist) & 7u) == 0; // (a caller's field may start anywhere)
 #pragma unroll
     for (int i = 0; i < LC; i++) {
         long long const r0 = static_cast<long long>(ty) * TS + 2 * i;

@@ -48,6 +48,7 @@ LAB_DEV uint32_t lab_ld_ro(uint32_t const *p) { return __ldg(p); }
 LAB_DEV uint16_t lab_ld_ro(uint16_t const *p) { return __ldg(p); }
 LAB_DEV uint8_t lab_ld_ro(uint8_t const *p) { return __ldg(p); }
 LAB_DEV uint8_t lab_ld_cg(uint8_t const *p) { return __ldcg(p); }
+LAB_DEV uint16_t lab_ld_cg(uint16_t const *p) { return __ldcg(p); }
 LAB_DEV void lab_st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
 LAB_DEV void lab_st_cg(uint64_t *p, uint64_t v) {
     __stcg(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v));

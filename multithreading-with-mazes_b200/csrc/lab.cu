@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) k_tree_finish_jump(Params p, Tree tr) {
 }
 // ---- the lattice road (device/lattice.cuh) ----
 __global__ void __launch_bounds__(128) k_lat_link(Params p, Lattice lt) {
-    __shared__ uint32_t sm[4][LSLOTS];
+    __shared__ uint32_t sm[4][L_LINK_SM];
     lat_link_body(p, lt, lane_id(), sm[threadIdx.x >> 5]);
 }
 constexpr int LAT_RANK_WARPS = 4; // warps per block of the local ranking (LSUP_SLOTS words of shared memory each)
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) k_lat_flood(Params p, Lattice lt) { lat_f
 __global__ void __launch_bounds__(256) k_lat_scan_chunks(Lattice lt) { lat_scan_chunks_body(lt, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void k_lat_scan_tops(Lattice lt) { lat_scan_tops_body(lt, lane_id()); }
 __global__ void __launch_bounds__(128) k_lat_levels(Params p, Lattice lt) {
-    __shared__ uint32_t sm[4][LSLOTS];
+    __shared__ uint32_t sm[4][L_LINK_SM];
     lat_levels_body(p, lt, lane_id(), sm[threadIdx.x >> 5]);
 }
 __global__ void __launch_bounds__(256) k_tree_orient(Params p, Tree tr) { tree_orient_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
@@ -684,7 +684,9 @@ int ensure_lattice(lab_grid *h) {
     CU(cudaMalloc(&lt.mask, nt * 96 * sizeof(uint32_t)));
     CU(cudaMalloc(&lt.xmask, nt * 4 * sizeof(uint32_t)));
     CU(cudaMalloc(&lt.next, nt * LSLOTS * sizeof(uint32_t)));
-    CU(cudaMalloc(&lt.label, nt * LSLOTS));
+    CU(cudaMalloc(&lt.label, nt * LSLOTS * sizeof(uint16_t)));
+    CU(cudaMalloc(&lt.cmap, nt * 512 * sizeof(uint16_t)));
+    CU(cudaMalloc(&lt.nruns, nt * sizeof(uint32_t)));
     CU(cudaMalloc(&lt.lplane, nt * L_LABEL_PLANES * 32 * sizeof(uint32_t)));
     CU(cudaMalloc(&lt.xd, nt * LSLOTS * sizeof(uint64_t)));
     CU(cudaMalloc(&lt.gb, static_cast<size_t>(lt.nsuper) * LB * sizeof(uint64_t)));
@@ -950,6 +952,25 @@ int grid_blocks(lab_grid *h) { return h->sm_count * 8; }
 
 } // namespace
 
+// Every entry point that takes a grid runs on the grid's device whatever device is current in the calling thread
+// (one process driving several GPUs, or torch.cuda.set_device in between), and puts the caller's device back.
+struct Device_guard {
+    int prev = -1;
+    bool switched = false;
+    explicit Device_guard(lab_grid const *h) {
+        if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) {
+            switched = cudaSetDevice(h->device) == cudaSuccess;
+        }
+    }
+    ~Device_guard() {
+        if (switched) {
+            cudaSetDevice(prev);
+        }
+    }
+    Device_guard(Device_guard const &) = delete;
+    Device_guard &operator=(Device_guard const &) = delete;
+};
+
 // ----------------------------------------------------------------------------------------- ABI
 extern "C" {
 
@@ -1028,7 +1049,19 @@ int lab_grid_create_on_device(int rows, int cols, void *device_squares, lab_grid
     }
     h->squares = static_cast<uint16_t *>(device_squares);
     h->owns_squares = false;
+    // the grid lives on the device that owns the caller's Squares, whatever device is current
+    cudaPointerAttributes attr{};
+    int prev = -1;
+    bool switched = false;
+    if (cudaPointerGetAttributes(&attr, device_squares) == cudaSuccess && attr.type == cudaMemoryTypeDevice && cudaGetDevice(&prev) == cudaSuccess &&
+        prev != attr.device) {
+        switched = cudaSetDevice(attr.device) == cudaSuccess;
+    }
+    (void)cudaGetLastError();
     rc = grid_common_init(h);
+    if (switched) {
+        cudaSetDevice(prev);
+    }
     if (rc) {
         lab_grid_destroy(h);
         return rc;
@@ -1038,6 +1071,7 @@ int lab_grid_create_on_device(int rows, int cols, void *device_squares, lab_grid
 }
 
 int lab_grid_destroy(lab_grid *h) {
+    Device_guard const guard_(h);
     if (!h) {
         return LAB_OK;
     }
@@ -1074,7 +1108,7 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->tree.tc);
     if (h->lat_alloc) {
         Lattice &lt = h->lat;
-        void *const arrays[] = {lt.mask, lt.xmask, lt.next, lt.label, lt.lplane, lt.xd, lt.gb, lt.R, lt.dplane, lt.emask, lt.wsum, lt.chunk};
+        void *const arrays[] = {lt.mask, lt.xmask, lt.next, lt.label, lt.cmap, lt.nruns, lt.lplane, lt.xd, lt.gb, lt.R, lt.dplane, lt.emask, lt.wsum, lt.chunk};
         for (void *a : arrays) {
             cudaFree(a);
         }
@@ -1082,11 +1116,18 @@ int lab_grid_destroy(lab_grid *h) {
     for (auto &e : h->ev) {
         if (e) cudaEventDestroy(e);
     }
+    for (auto &e : h->tev) {
+        if (e) cudaEventDestroy(e);
+    }
+    for (auto &e : h->lev) {
+        if (e) cudaEventDestroy(e);
+    }
     delete h;
     return LAB_OK;
 }
 
 int lab_grid_set_stream(lab_grid *h, void *cuda_stream) {
+    Device_guard const guard_(h);
     if (!h) {
         return fail(LAB_ERR_ARG, "null grid");
     }
@@ -1099,6 +1140,7 @@ int lab_grid_rows(const lab_grid *h) { return h ? h->g.rows : 0; }
 int lab_grid_cols(const lab_grid *h) { return h ? h->g.cols : 0; }
 
 int lab_grid_upload(lab_grid *h, const uint16_t *host_squares) {
+    Device_guard const guard_(h);
     if (!h || !host_squares) {
         return fail(LAB_ERR_ARG, "null argument");
     }
@@ -1113,6 +1155,7 @@ int lab_grid_upload(lab_grid *h, const uint16_t *host_squares) {
 }
 
 int lab_grid_download(lab_grid *h, uint16_t *host_squares) {
+    Device_guard const guard_(h);
     if (!h || !host_squares) {
         return fail(LAB_ERR_ARG, "null argument");
     }
@@ -1127,6 +1170,7 @@ int lab_grid_download(lab_grid *h, uint16_t *host_squares) {
 }
 
 int lab_grid_or_bits(lab_grid *h, const lab_point *cells, const uint16_t *bits, int n) {
+    Device_guard const guard_(h);
     if (!h || !cells || !bits || n < 0 || n > 32) {
         return fail(LAB_ERR_ARG, "bad or_bits arguments");
     }
@@ -1151,6 +1195,7 @@ int lab_grid_or_bits(lab_grid *h, const lab_point *cells, const uint16_t *bits, 
 }
 
 int lab_grid_and_bits(lab_grid *h, uint16_t mask) {
+    Device_guard const guard_(h);
     if (!h) {
         return fail(LAB_ERR_ARG, "null grid");
     }
@@ -1166,10 +1211,12 @@ lab_point lab_distance_start(int rows, int cols) {
 }
 
 void *lab_levels_device(lab_grid *h, int plane) {
+    Device_guard const guard_(h);
     return (h && plane >= 0 && plane < MAX_PLANES) ? h->plane[plane].dist : nullptr;
 }
 
 int lab_levels_bind(lab_grid *h, int plane, void *device_levels) {
+    Device_guard const guard_(h);
     if (!h || plane < 0 || plane >= MAX_PLANES || !device_levels) {
         return fail(LAB_ERR_ARG, "bad levels_bind arguments");
     }
@@ -1178,16 +1225,21 @@ int lab_levels_bind(lab_grid *h, int plane, void *device_levels) {
     }
     h->plane[plane].dist = static_cast<uint32_t *>(device_levels);
     h->owns_dist[plane] = false;
+    if (plane == 0) {
+        h->have_map = false; // (plane 0 now points at memory no search of this grid has written)
+    }
     return LAB_OK;
 }
 
 int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t *max_out, uint64_t *settled_out) {
+    Device_guard const guard_(h);
     if (!h) {
         return fail(LAB_ERR_ARG, "null grid");
     }
     if (!in_grid(h, {sr, sc})) {
         return fail(LAB_ERR_ARG, "start (%d,%d) outside the maze", sr, sc);
     }
+    h->have_map = false; // (until this search has finished: a failed one leaves no map to paint)
     Run_desc d{};
     d.game = GAME_DISTANCE;
     d.nplanes = 1;
@@ -1235,6 +1287,7 @@ int lab_distance_map(lab_grid *h, int sr, int sc, uint32_t *dist_host, uint64_t 
 }
 
 int lab_distance_paint(lab_grid *h, int channel, uint32_t *pixels_host) {
+    Device_guard const guard_(h);
     if (!h) {
         return fail(LAB_ERR_ARG, "null grid");
     }
@@ -1263,6 +1316,7 @@ int lab_distance_paint(lab_grid *h, int channel, uint32_t *pixels_host) {
 void *lab_pixels_device(lab_grid *h) { return h ? h->pixels : nullptr; }
 
 int lab_pixels_bind(lab_grid *h, void *device_pixels) {
+    Device_guard const guard_(h);
     if (!h || !device_pixels) {
         return fail(LAB_ERR_ARG, "null grid or pixel buffer");
     }
@@ -1344,6 +1398,7 @@ static int copy_path(lab_grid *h, int slot, lab_point *dst, uint64_t cap, uint64
 
 int lab_bfs_hunt(lab_grid *h, lab_point start, lab_point finish, int32_t *winner, lab_point *path, uint64_t path_cap,
                  uint64_t *path_len) {
+    Device_guard const guard_(h);
     if (!h || !in_grid(h, start) || !in_grid(h, finish)) {
         return fail(LAB_ERR_ARG, "bad hunt arguments");
     }
@@ -1372,6 +1427,7 @@ int lab_bfs_hunt(lab_grid *h, lab_point start, lab_point finish, int32_t *winner
 
 int lab_bfs_gather(lab_grid *h, lab_point start, const lab_point finishes[4], int32_t claimed_by[4],
                    lab_point *const paths[4], uint64_t path_cap, uint64_t path_len[4]) {
+    Device_guard const guard_(h);
     if (!h || !finishes || !in_grid(h, start)) {
         return fail(LAB_ERR_ARG, "bad gather arguments");
     }
@@ -1413,6 +1469,7 @@ int lab_bfs_gather(lab_grid *h, lab_point start, const lab_point finishes[4], in
 
 int lab_bfs_corners(lab_grid *h, const lab_point starts[4], lab_point finish, int32_t *winner, lab_point *path,
                     uint64_t path_cap, uint64_t *path_len) {
+    Device_guard const guard_(h);
     if (!h || !starts || !in_grid(h, finish)) {
         return fail(LAB_ERR_ARG, "bad corners arguments");
     }
@@ -1447,6 +1504,10 @@ int lab_band_cols_padded(const lab_grid *h) { return h ? h->g.tiles_x * TS : 0; 
 int lab_band_begin(lab_grid *h, int src_r, int src_c) { return lab_band_begin_game(h, GAME_DISTANCE, src_r, src_c); }
 
 int lab_band_begin_game(lab_grid *h, int game, int src_r, int src_c) {
+    Device_guard const guard_(h);
+    if (h) {
+        h->have_map = false; // (a band's field is not a map lab_distance_paint could colour: its maximum is the band's)
+    }
     if (!h) {
         return fail(LAB_ERR_ARG, "null grid");
     }
@@ -1483,6 +1544,7 @@ int lab_band_begin_game(lab_grid *h, int game, int src_r, int src_c) {
 }
 
 int lab_band_path_rows(lab_grid *h, void *top_dev, void *bottom_dev) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open || !top_dev || !bottom_dev) {
         return fail(LAB_ERR_ARG, "lab_band_path_rows: bad arguments or no band search open");
     }
@@ -1495,6 +1557,7 @@ int lab_band_path_rows(lab_grid *h, void *top_dev, void *bottom_dev) {
 }
 
 int lab_band_set_neighbour_paths(lab_grid *h, const void *above_bottom_dev, const void *below_top_dev) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open) {
         return fail(LAB_ERR_ARG, "no band search open");
     }
@@ -1512,6 +1575,7 @@ int lab_band_set_neighbour_paths(lab_grid *h, const void *above_bottom_dev, cons
 }
 
 int lab_band_relax(lab_grid *h) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open) {
         return fail(LAB_ERR_ARG, "no band search open");
     }
@@ -1519,6 +1583,7 @@ int lab_band_relax(lab_grid *h) {
 }
 
 int lab_band_export_edges(lab_grid *h, void *top_levels_dev, void *bottom_levels_dev) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open || !top_levels_dev || !bottom_levels_dev) {
         return fail(LAB_ERR_ARG, "lab_band_export_edges: bad arguments");
     }
@@ -1532,6 +1597,7 @@ int lab_band_export_edges(lab_grid *h, void *top_levels_dev, void *bottom_levels
 }
 
 int lab_band_import_edges(lab_grid *h, const void *above_bottom_levels_dev, const void *below_top_levels_dev, uint32_t *activated) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open || !activated) {
         return fail(LAB_ERR_ARG, "lab_band_import_edges: bad arguments");
     }
@@ -1549,6 +1615,7 @@ int lab_band_import_edges(lab_grid *h, const void *above_bottom_levels_dev, cons
 }
 
 int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open) {
         return fail(LAB_ERR_ARG, "no band search open");
     }
@@ -1572,6 +1639,7 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
 int lab_band_tree_bind(lab_grid *h, uint32_t tile_base, uint32_t ntiles_global, void *succ0, void *sr0, void *sr1,
                        void *loc, void *inmask, void *alist, const void *border_list, uint32_t border_count, const void *layout,
                        int world, int me) {
+    Device_guard const guard_(h);
     if (!h || !succ0 || !sr0 || !sr1 || (reinterpret_cast<uintptr_t>(sr0) & 7u) || (reinterpret_cast<uintptr_t>(sr1) & 7u) || !loc || !inmask || !alist || !border_list || !layout || world < 1 || me < 0 || me >= world) {
         return fail(LAB_ERR_ARG, "lab_band_tree_bind: bad argument");
     }
@@ -1651,6 +1719,7 @@ extern "C++" template <int KIND> int band_tree_jump(lab_grid *h, Tree tr, Params
 }
 
 int lab_band_tree_chunk_words(const lab_grid *h, int stage) {
+    Device_guard const guard_(h);
     if (!h || stage < 1 || stage > 3) {
         return 0;
     }
@@ -1659,6 +1728,7 @@ int lab_band_tree_chunk_words(const lab_grid *h, int stage) {
 }
 
 int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs, uint32_t *crossings, int32_t box[4]) {
+    Device_guard const guard_(h);
     int rc = band_tree_ready(h, "lab_band_tree_count");
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -1688,6 +1758,7 @@ int lab_band_tree_count(lab_grid *h, uint64_t *squares, uint64_t *pairs, uint32_
 // The ranks' counts and boxes say that the whole maze is one open room (device/room.cuh): this band's part of it
 // [r0, r1] x [c0, c1] (empty if r0 > r1) and the source, all relative to the band; levels in one streaming pass.
 int lab_band_room(lab_grid *h, int r0, int r1, int c0, int c1, int src_r, int src_c) {
+    Device_guard const guard_(h);
     int rc = band_tree_ready(h, "lab_band_room");
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -1707,6 +1778,7 @@ int lab_band_room(lab_grid *h, int r0, int r1, int c0, int c1, int src_r, int sr
 
 // walk + the band's own part of the ranking -> chunk 1
 int lab_band_tree_rank_local(lab_grid *h, uint64_t squares_global, uint64_t pairs_global, void *chunk1) {
+    Device_guard const guard_(h);
     int rc = band_tree_ready(h, "lab_band_tree_rank_local");
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -1730,6 +1802,7 @@ int lab_band_tree_rank_local(lab_grid *h, uint64_t squares_global, uint64_t pair
 
 // all chunks 1 in: the short list's ranking, the band's final ranks, orientation, the flood -> chunk 2
 int lab_band_tree_flood(lab_grid *h, const void *all1, int root_rank, void *chunk2) {
+    Device_guard const guard_(h);
     int rc = band_tree_ready(h, "lab_band_tree_flood");
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -1754,6 +1827,7 @@ int lab_band_tree_flood(lab_grid *h, const void *all1, int root_rank, void *chun
 
 // all chunks 2 in: parents of the band's entries, the band's own part of the prefix sums -> chunk 3
 int lab_band_tree_prefix_local(lab_grid *h, const void *all2, void *chunk3) {
+    Device_guard const guard_(h);
     int rc = band_tree_ready(h, "lab_band_tree_prefix_local");
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -1774,6 +1848,7 @@ int lab_band_tree_prefix_local(lab_grid *h, const void *all2, void *chunk3) {
 // Every rank has read the same flags, so all reach the same verdict `used`: 1 = the band's field is final;
 // 0 = not one tree, the field is wiped (tree_gate_body) and the relax / exchange loop takes over.
 int lab_band_tree_levels(lab_grid *h, const void *all3, int32_t *used) {
+    Device_guard const guard_(h);
     int rc = band_tree_ready(h, "lab_band_tree_levels");
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -1800,6 +1875,7 @@ int lab_band_tree_levels(lab_grid *h, const void *all3, int32_t *used) {
 // ---- the solvers across row bands: compositions of the pieces below, driven by bands.py (sharded_hunt / sharded_gather).
 // The level field is the sharded spanning-tree pipeline's or the open room's (begin with lab_band_begin_game).
 int lab_band_level_at(lab_grid *h, int r, int c, uint32_t *level) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open || !level || !in_grid(h, {r, c})) {
         return fail(LAB_ERR_ARG, "lab_band_level_at: bad arguments");
     }
@@ -1810,6 +1886,7 @@ int lab_band_level_at(lab_grid *h, int r, int c, uint32_t *level) {
 
 // Paint rules (post.cuh Paint_rule, plane 0): OR bits[k] into the band's squares whose level is below below[k].
 int lab_band_paint(lab_grid *h, int n_rules, const uint32_t *below, const uint32_t *bits, uint64_t *painted) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open || n_rules < 1 || n_rules > 4 || !below || !bits) {
         return fail(LAB_ERR_ARG, "lab_band_paint: bad arguments");
     }
@@ -1838,6 +1915,7 @@ int lab_band_paint(lab_grid *h, int n_rules, const uint32_t *below, const uint32
 // square's index along the whole path, other bands' squares left alone).  state: {steps, row, col, level left}.
 int lab_band_walk(lab_grid *h, int r, int c, int include_first, int first_only, uint32_t repaint_bits, void *path_dev, uint64_t path_cap,
                   int64_t state[4]) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open || !state) {
         return fail(LAB_ERR_ARG, "lab_band_walk: bad arguments");
     }
@@ -1859,6 +1937,7 @@ int lab_band_walk(lab_grid *h, int r, int c, int include_first, int first_only, 
 
 // gather's path.front() recolour (bfs_threads.cc:355-364) of one square of this band: paint nibble := bits
 int lab_band_recolour(lab_grid *h, int r, int c, uint16_t paint_bits) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open || !in_grid(h, {r, c})) {
         return fail(LAB_ERR_ARG, "lab_band_recolour: bad arguments");
     }
@@ -1870,6 +1949,7 @@ int lab_band_recolour(lab_grid *h, int r, int c, uint16_t paint_bits) {
 
 // closes a sharded game (the distance map closes with lab_band_finish): statistics, errors
 int lab_band_finish_game(lab_grid *h) {
+    Device_guard const guard_(h);
     if (!h || !h->band_open) {
         return fail(LAB_ERR_ARG, "no band search open");
     }
@@ -1881,6 +1961,7 @@ int lab_band_finish_game(lab_grid *h) {
 uint64_t lab_last_painted(const lab_grid *h) { return h ? h->last.settled : 0; }
 
 int lab_last_timing(const lab_grid *h, lab_timing *out) {
+    Device_guard const guard_(h);
     if (!h || !out) {
         return fail(LAB_ERR_ARG, "null argument");
     }
@@ -1889,6 +1970,7 @@ int lab_last_timing(const lab_grid *h, lab_timing *out) {
 }
 
 int lab_last_stats(const lab_grid *h, lab_stats *out) {
+    Device_guard const guard_(h);
     if (!h || !out) {
         return fail(LAB_ERR_ARG, "null argument");
     }

@@ -62,9 +62,10 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
         lt.nslots = static_cast<uint32_t>(nt * LSLOTS);
         std::vector<uint32_t> mask(nt * 96, 0xDEADBEEFu), xmask(nt * 4), next(nt * LSLOTS, 0xDEADBEEFu), lplane(nt * L_LABEL_PLANES * 32), R(nt * LSLOTS, 0xDEADBEEFu),
             dplane(nt * L_DEPTH_PLANES * 32), emask(nt * 4), wsum(nt * LSLOTS + 2 + L_CHUNK, 0xDEADBEEFu), chunk(nt * LSLOTS / L_CHUNK + 2);
-        std::vector<uint8_t> label(nt * LSLOTS);
+        std::vector<uint16_t> label(nt * LSLOTS), cmap(nt * 512, 0xDEAD);
+        std::vector<uint32_t> nruns_v(nt);
         std::vector<uint64_t> xd(nt * LSLOTS, 0xDEADBEEFDEADBEEFull), gb(static_cast<size_t>(lt.nsuper) * LB, 0xDEADBEEFDEADBEEFull);
-        lt.mask = mask.data(); lt.xmask = xmask.data(); lt.next = next.data(); lt.label = label.data(); lt.lplane = lplane.data();
+        lt.mask = mask.data(); lt.xmask = xmask.data(); lt.next = next.data(); lt.label = label.data(); lt.cmap = cmap.data(); lt.nruns = nruns_v.data(); lt.lplane = lplane.data();
         lt.xd = xd.data(); lt.gb = gb.data(); lt.R = R.data(); lt.dplane = dplane.data(); lt.emask = emask.data(); lt.wsum = wsum.data();
         lt.chunk = chunk.data();
         lt.tc = &tc;
