@@ -354,8 +354,17 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
     };
     auto unite = [&](uint32_t a, uint32_t b) {
         for (int guard = 0; guard < 1024; guard++) {
-            for (uint32_t pa; (pa = lab_ld_volatile(parent + a)) != a;) a = pa;
-            for (uint32_t pb; (pb = lab_ld_volatile(parent + b)) != b;) b = pb;
+            // find with path halving (a stale grandparent is still an ancestor: roots only ever get hooked under smaller ids)
+            for (uint32_t pa; (pa = lab_ld_volatile(parent + a)) != a;) {
+                uint32_t const ga = lab_ld_volatile(parent + pa);
+                lab_st_volatile(parent + a, ga);
+                a = ga;
+            }
+            for (uint32_t pb; (pb = lab_ld_volatile(parent + b)) != b;) {
+                uint32_t const gb = lab_ld_volatile(parent + pb);
+                lab_st_volatile(parent + b, gb);
+                b = gb;
+            }
             if (a == b) {
                 return;
             }
