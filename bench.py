@@ -387,10 +387,13 @@ def ours_bands(args, lab, dist, torch, world, rank, local):
     game, builder, n, mod, stands_for = WORKLOADS[workload]
     t0 = time.time()
     strong = game == "distance+gather"  # the headline maze itself, cut into `world` bands (a taller one could not be built in minutes)
-    maze, spec = make_case(lab, workload, bands=1 if strong else world)  # same seed on every rank -> same maze (one rank builds, the others read the cache)
+    if rank == 0:  # one rank builds (and caches) the maze, the others read the file
+        make_case(lab, workload, bands=1 if strong else world)
+    dist.barrier()
+    maze, spec = make_case(lab, workload, bands=1 if strong else world)
     build_s = time.time() - t0
     rows, cols = maze.shape
-    r0, nloc = bands.split_rows(rows, world)[rank]
+    r0, nloc = bands.split_rows_super(rows, world)[rank]  # whole super-tile rows: the lattice road across bands takes them
     stream = torch.cuda.current_stream()
     pristine = torch.from_numpy(maze[r0:r0 + nloc].view(np.int16).copy()).cuda()
     work = torch.empty_like(pristine)
@@ -420,10 +423,12 @@ def ours_bands(args, lab, dist, torch, world, rank, local):
         sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     settled, rounds, search_ms, tree_steps, launches = 0, 0, 0.0, 0, 0
+    roads = set()
     for e in evs:
         res = step(e)
         settled += res["settled"]
         rounds += res["rounds"]
+        roads.add(res["road"])
         tree_steps += int(res.get("tree", False))
         search_ms += eng.grid.timing()["search_ms"]
         launches += int(eng.grid.stats()["launches"])
@@ -466,14 +471,18 @@ def ours_bands(args, lab, dist, torch, world, rank, local):
             "config": {"workload": workload, "stands_for": stands_for, "game": "distance" if strong else game, "builder": builder, "mod": mod, "rows": rows, "cols": cols,
                        "seed": SEED + 2, "cells_settled_per_step": settled // args.steps,
                        "parallelism": (f"{world} row bands of one {rows}x{cols} maze, one per GPU; " +
-                                       ("sharded spanning-tree pipeline: walk / flood / fix-up on the band's tiles, pointer jumping over all crossings on "
+                                       ("lattice road across the bands: link / local ranking / flood / levels on the band's tiles, the border-list "
+                                        "slices all-gathered and the arcs' weights all-reduced over NCCL (two exchanges per map)" if roads == {"lattice"} else
+                                        "sharded spanning-tree pipeline: walk / flood / fix-up on the band's tiles, pointer jumping over all crossings on "
                                         "every rank, NCCL all-gathers of the crossing arrays' slices + one-word all-reduces between the phases"
                                         if tree_steps == args.steps else
                                         "NCCL send/recv of one row of levels per neighbour + 1-word all-reduce between local searches")),
+                       "road": sorted(roads),
                        "exchange_rounds_per_step": rounds / args.steps, "l2": "256 MB flush buffer written between timed steps",
                        "maze_build_s_host": round(build_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
-                         "kernel": ("spanning-tree pipeline across the bands (k_tree_walk, k_tree_jump<rank>, k_tree_flood, k_tree_jump<prefix>, "
+                         "kernel": ("lattice road across the bands (k_lat_link, k_lat_rank_*, k_lat_flood, k_lat_scan_*, k_lat_levels; exchanges included)"
+                                    if roads == {"lattice"} else "spanning-tree pipeline across the bands (k_tree_walk, k_tree_jump<rank>, k_tree_flood, k_tree_jump<prefix>, "
                                     "k_tree_fixup; exchanges included)" if tree_steps == args.steps
                                     else "k_bfs_tiles (all launches of a step, exchanges included)"), "peak_source": peak_src + f" x {world} GPUs",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": search_ms_max / args.steps},

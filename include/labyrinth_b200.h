@@ -227,6 +227,37 @@ int lab_band_tree_flood(lab_grid *g, const void *all_chunks1, int root_rank, voi
 int lab_band_tree_prefix_local(lab_grid *g, const void *all_chunks2, void *chunk3);
 int lab_band_tree_levels(lab_grid *g, const void *all_chunks3, int32_t *used);
 
+/* The lattice road (csrc/device/lattice.cuh) across row bands: what the reference builders' perfect mazes take (cells on
+ * the odd squares: builders of kruskal.cc, wilson_path_carver.cc, recursive_backtracker.cc ...), tried BEFORE the general
+ * pipeline above.  Bands are whole SUPER-TILE rows (lab_band_lat_super_rows() x 64 rows), all of `super_rows_band`
+ * super-tile rows but the last, which may be shorter; the whole maze has odd sizes and the start lies on an
+ * (odd, odd) square.  Every rank holds three whole-maze arrays of lab_band_lat_words' sizes: the border list
+ * (uint64 entries), the weights (uint32 words) and the scan's chunk offsets (uint32).  After lab_band_begin(_game) and
+ * lab_band_set_neighbour_paths:
+ *     lab_band_lat_bind    the band's place (super-tile rows [base, base + band) of `global`) and the three arrays
+ *     lab_band_lat_link    counts, link, local ranking -> the band's slice of the border list (entries
+ *                          [rank * slice, (rank + 1) * slice), slice = entries / world) and its 8-word header
+ *                          -- the ranks all-gather both --
+ *     lab_band_lat_flood   the whole maze's counts from the headers (every rank reads the same ones: they agree without
+ *                          a host round trip), the ranking over the whole border list, the band's floods; its arcs'
+ *                          weights go to their tour positions in the weights array (zeroed first if zero_weights)
+ *                          -- the ranks sum the weights arrays (all-reduce over weight_words - 1024 words) --
+ *     lab_band_lat_levels  prefix sums over the whole tour, the band's final levels -> used: 1 = the field is final
+ *                          (lab_band_finish next); 0 = not one lattice tree: nothing was written, the pipeline above or
+ *                          the loop take over
+ * Two exchanges per map whatever its diameter.  lab_band_lat_set_peers (optional, after bind): the other ranks' border
+ * lists and weights arrays as device pointers valid on this device ([0] = this rank's own); the kernels then store a
+ * band's slice and weights into EVERY rank's arrays themselves (NVLink peer stores) and the two exchanges shrink to
+ * barriers (call lab_band_lat_flood with zero_weights = 0 and clear the last 8 weight words before lab_band_lat_link). */
+int lab_band_lat_super_rows(void);
+int lab_band_lat_words(int tiles_x, int super_rows_global, uint64_t *border_entries, uint64_t *weight_words, uint64_t *chunk_words);
+int lab_band_lat_bind(lab_grid *g, int super_row_base, int super_rows_band, int super_rows_global, void *border_list, void *weights,
+                      void *chunks);
+int lab_band_lat_set_peers(lab_grid *g, int n, void *const *border_lists, void *const *weights);
+int lab_band_lat_link(lab_grid *g, void *header_dev);
+int lab_band_lat_flood(lab_grid *g, const void *all_headers_dev, int world, int zero_weights);
+int lab_band_lat_levels(lab_grid *g, int32_t *used);
+
 int lab_last_timing(const lab_grid *g, lab_timing *out);
 int lab_last_stats(const lab_grid *g, lab_stats *out);
 const char *lab_last_error(void);

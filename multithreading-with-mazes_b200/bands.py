@@ -72,6 +72,21 @@ def split_rows(rows: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+LAT_SUPER_TILES = 4  # LST of csrc/device/lattice.cuh: bands of the lattice road are whole super-tile rows
+
+
+def split_rows_super(rows: int, world: int, super_tiles: int = LAT_SUPER_TILES) -> List[Tuple[int, int]]:
+    """Bands of whole SUPER-TILE rows (4 x 64 rows), all of the same height but the last: what the lattice road across
+    bands (``_sharded_lattice``) needs.  The other sharded roads take these bands too."""
+    unit = super_tiles * TS
+    sup_rows = (rows + unit - 1) // unit
+    per = (sup_rows + world - 1) // world
+    out = [(min(rows, r * per * unit), min(rows, (r + 1) * per * unit) - min(rows, r * per * unit)) for r in range(world)]
+    if any(n <= 0 for _, n in out):
+        raise ValueError(f"{rows} rows are too few for {world} bands of whole super-tile rows ({unit} rows each)")
+    return out
+
+
 class _BandEngine:
     """One band: ctypes over <prefix>band_* entry points that share one protocol (include/labyrinth_b200.h).
     Subclasses set self.L (the library), self.h (the band's handle), self.prefix, self.row_device."""
@@ -226,10 +241,46 @@ class _BandEngine:
         return used.value == 1
 
 
+    # -- the lattice road across bands (lab_band_lat_*) --
+    def lat_bind(self, rank: int, per: int, world: int):
+        """Whole-maze border list / weights / chunk arrays (allocated once per layout) and the band's place in them."""
+        torch = self.torch
+        key = (rank, per, world)
+        b = getattr(self, "_lat_bufs", None)
+        if b is None or b["key"] != key:
+            tiles_x = self.cols_padded // TS
+            n_b, n_w, n_c = c_uint64(), c_uint64(), c_uint64()
+            self._check(self._f("lat_words")(c_int(tiles_x), c_int(per * world), byref(n_b), byref(n_w), byref(n_c)))
+            dev = self.row_device
+            b = {"key": key, "gb": torch.empty(int(n_b.value), dtype=torch.int64, device=dev),
+                 "wsum": torch.zeros(int(n_w.value), dtype=torch.int32, device=dev), "chunk": torch.empty(int(n_c.value), dtype=torch.int32, device=dev),
+                 "hdr": torch.zeros(8, dtype=torch.int32, device=dev), "all_hdr": torch.zeros(8 * world, dtype=torch.int32, device=dev),
+                 "slice": int(n_b.value) // world, "reduce_words": int(n_w.value) - 1024}
+            self._check(self._f("lat_bind")(self.h, c_int(rank * per), c_int(per), c_int(per * world), self._ptr(b["gb"]), self._ptr(b["wsum"]),
+                                            self._ptr(b["chunk"])))
+            self._lat_bufs = b
+        return b
+
+    def lat_link(self, hdr):
+        self._check(self._f("lat_link")(self.h, self._ptr(hdr)))
+
+    def lat_flood(self, all_hdr, world: int, zero_weights: bool):
+        self._check(self._f("lat_flood")(self.h, self._ptr(all_hdr), c_int(world), c_int(1 if zero_weights else 0)))
+
+    def lat_levels(self) -> bool:
+        used = ctypes.c_int32()
+        self._check(self._f("lat_levels")(self.h, byref(used)))
+        return used.value == 1
+
+
 class GpuBandEngine(_BandEngine):
     """One band on one GPU: the lab_band_* entry points of liblabyrinth_b200; buffers are CUDA torch tensors."""
 
     prefix = "lab_band_"
+    supports_lattice = True
+
+    def grid_cols(self):
+        return self.grid.cols
 
     def __init__(self, lab, squares, device=None):
         import torch
@@ -268,7 +319,7 @@ def _exchange(dist, rank, world, up_payload, down_payload, engine, group):
 
 
 def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_local: int, group=None, max_rounds: int = 1 << 20,
-                         use_tree: bool = True):
+                         use_tree: bool = True, use_lattice: bool = True):
     """Run the sharded distance map on this rank's band.  Collective: every rank of `group` calls it.
 
     Returns {"max", "settled", "rounds"} (global values; the level field stays in the engine)."""
@@ -297,7 +348,10 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     tr.mark("cross")
     flag = torch.zeros(1, dtype=torch.int32, device=engine.row_device)
     rounds = 0
-    tree = use_tree and getattr(engine, "supports_tree", False) and _sharded_tree(engine, start_global, row0, rows_local, group, tr)
+    tree = False
+    if use_tree and getattr(engine, "supports_tree", False):
+        lattice = use_lattice and getattr(engine, "supports_lattice", False) and _sharded_lattice(engine, start_global, row0, rows_local, group, tr)
+        tree = "lattice" if lattice else _sharded_tree(engine, start_global, row0, rows_local, group, tr)
     while not tree:
         rounds += 1
         engine.relax()
@@ -306,8 +360,10 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
         activated = engine.import_edges(above_bottom, below_top)
         flag.fill_(1 if activated else 0)
         dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-        if int(flag.item()) == 0 or rounds >= max_rounds:
+        if int(flag.item()) == 0:
             break
+        if rounds >= max_rounds:
+            raise RuntimeError(f"sharded_distance_map: no fixpoint after {max_rounds} exchange rounds")
     tr.mark("search")
     mx, settled = engine.finish()
     tr.mark("finish")
@@ -317,7 +373,8 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     every = out.view(world, 2).tolist()
     tr.mark("results")
     tr.report(rank)
-    return {"max": max(int(e[0]) for e in every), "settled": sum(int(e[1]) for e in every), "rounds": rounds, "tree": tree is True, "road": "wave" if not tree else ("tree" if tree is True else "room")}
+    return {"max": max(int(e[0]) for e in every), "settled": sum(int(e[1]) for e in every), "rounds": rounds, "tree": tree is True or tree == "lattice",
+            "road": "wave" if not tree else ("tree" if tree is True else tree)}
 
 
 def _all_gather(dist, out, chunk, world, group):
@@ -338,6 +395,56 @@ def tree_layout(split, tiles_x: int):
     if any(r0 % TS for r0, _ in split) or any(bases[r] != sum(ntiles[:r]) for r in range(len(split))) or total * 256 + 2 >= 1 << 32:
         return None
     return {"split": list(split), "bases": bases, "ntiles": ntiles, "total": total, "tiles_x": tiles_x}
+
+
+def _sharded_lattice(engine, start_global, row0, rows_local, group, tr=None) -> bool:
+    """The lattice road (csrc/device/lattice.cuh) across the bands.  Collective.  Two exchanges per map: the bands' slices
+    of the border list (+ one header each) are all-gathered, every rank finishes the ranking over the whole list and
+    floods its own tiles; the arcs' weights, scattered by tour position into a whole-maze array, are summed over the
+    ranks; every rank scans them and writes its band's levels.  True: the bands' level fields are final; False: not
+    applicable (bands not whole super-tile rows, even sizes, start not on a cell) or not one lattice tree -- nothing has
+    been written and the general pipeline / the wave take over."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    dev = engine.row_device
+    mark = tr.mark if tr is not None else (lambda name: None)
+    cached = getattr(engine, "_lat_layout", None)
+    if cached is None or cached[0] != (row0, rows_local, world):
+        t = torch.tensor([row0, rows_local], dtype=torch.int64, device=dev)
+        out = torch.empty(2 * world, dtype=torch.int64, device=dev)
+        _all_gather(dist, out, t, world, group)
+        split = [(int(a), int(b)) for a, b in out.view(world, 2).tolist()]
+        unit = LAT_SUPER_TILES * TS
+        per = (split[0][1] + unit - 1) // unit
+        ok = all(r0 == r * per * unit for r, (r0, _) in enumerate(split)) and all(n == per * unit for _, n in split[:-1]) and 0 < split[-1][1] <= per * unit
+        cached = ((row0, rows_local, world), (per, sum(n for _, n in split)) if ok else None)
+        engine._lat_layout = cached
+    if cached[1] is None:
+        return False
+    per, rows_global = cached[1]
+    cols = int(engine.grid_cols())
+    sr, sc = start_global
+    if not (rows_global % 2 and cols % 2 and sr % 2 and sc % 2):
+        return False
+    b = engine.lat_bind(rank, per, world)
+    engine.lat_link(b["hdr"])
+    mark("lattice: link + local rank")
+    _all_gather(dist, b["all_hdr"], b["hdr"], world, group)
+    n = b["slice"]
+    mine = b["gb"][rank * n:(rank + 1) * n]
+    _all_gather(dist, b["gb"], mine if dist.get_backend(group) == "nccl" else mine.clone(), world, group)
+    mark("lattice: all-gather border list")
+    engine.lat_flood(b["all_hdr"], world, True)
+    mark("lattice: rank + flood")
+    if world > 1:
+        dist.all_reduce(b["wsum"][: b["reduce_words"]], op=dist.ReduceOp.SUM, group=group)
+    mark("lattice: all-reduce weights")
+    used = engine.lat_levels()
+    mark("lattice: scan + levels")
+    return used
 
 
 def _sharded_tree(engine, start_global, row0, rows_local, group, tr=None) -> bool:
@@ -436,7 +543,11 @@ def _sharded_field(engine, game, start_global, row0, rows_local, group):
     top, bottom = engine.path_rows()
     above_bottom, below_top = _exchange(dist, rank, world, top, bottom, engine, group)
     engine.set_neighbour_paths(above_bottom, below_top)
-    road = _sharded_tree(engine, start_global, row0, rows_local, group, tr)
+    road = False
+    if getattr(engine, "supports_lattice", False) and _sharded_lattice(engine, start_global, row0, rows_local, group, tr):
+        road = True  # (the lattice road leaves the same level field the general pipeline does)
+    if not road:
+        road = _sharded_tree(engine, start_global, row0, rows_local, group, tr)
     if not road:
         engine.finish_game()
         raise NotImplementedError("the solvers are sharded on perfect mazes and open rooms only (a general maze needs the bounded wave across bands)")

@@ -67,6 +67,19 @@ struct Lattice {
     Tree_ctl *tc;
     int sup_y, sup_x, nsuper;
     uint32_t nslots; // ntiles * 128
+    // Row bands (one band of a taller maze per GPU).  Bands are whole super-tile rows.  Arc ids, `R`, the
+    // dense border slots of `gb` and the tour positions of `wsum` are GLOBAL (the whole maze's); the per-tile arrays
+    // hold the band's tiles only: local tile t is global tile tile_base + t, local super-tile S is global sup_base + S.
+    // gb and wsum are whole-maze arrays on every rank: a rank fills in its own part -- into every peer's copy, by
+    // stores over NVLink from inside lat_rank_local_super / lat_flood_tile (peers > 1), or into its own copy alone,
+    // the copies then being joined by an all-gather / all-reduce (peers == 1) -- and reads the whole.
+    // Single GPU: tile_base = sup_base = 0, the *_global fields equal the local ones, peers = 1.
+    uint32_t tile_base, sup_base;
+    int nsuper_global;
+    uint32_t nslots_global;
+    int peers;                 // copies of gb / wsum this rank writes (its own is [0])
+    uint64_t *gb_peer[8];
+    uint32_t *wsum_peer[8];
 };
 
 LAB_DEV bool lat_live(Tree_ctl const *tc) { return tc->ok != 0 && tc->lat_on != 0 && tc->lat_err == 0; }
@@ -121,6 +134,10 @@ struct Lat_roots {
 LAB_DEV Lat_roots lat_roots(Params const &p) {
     Lat_roots r{};
     uint32_t const t0 = p.ctl->src_tile[0];
+    if (t0 == 0xFFFFFFFFu) { // row bands: the root is in another band (and on a cell: lab_band_lat_link)
+        r.ptile = t0;
+        return r;
+    }
     int const sr = static_cast<int>(p.ctl->src_rc[0] >> 8), sc = static_cast<int>(p.ctl->src_rc[0] & 0xFFu);
     int const i = sr >> 1, j = sc >> 1;
     r.ptile = t0;
@@ -463,7 +480,7 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
             }
         }
     }
-    uint32_t const gt = t;
+    uint32_t const gt = t + lt.tile_base; // the tile's id in the whole maze (row bands)
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         uint32_t out = L_NONE;
@@ -487,7 +504,7 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
             }
             uint32_t const me = static_cast<uint32_t>(s) * LC + static_cast<uint32_t>(lane);
             out = lat_twin(g, gt, nslot);
-            if (me == root_first[roots.n - 1]) { // the last root's tour ends here ...
+            if (roots.n > 0 && me == root_first[roots.n - 1]) { // the last root's tour ends here ...
                 if (roots.n == 2) {
                     lab_st_volatile(&tc->lat_head_b, out + 1u); // ... and would have begun with this arc
                 }
@@ -547,13 +564,18 @@ LAB_DEV uint32_t lat_next(Lattice const &lt, long long a) {
 }
 LAB_DEV void lat_rank_local_super(Params const &p, Lattice const &lt, uint32_t S, int lane, uint32_t *sm) {
     Geom const &g = p.g;
-    uint32_t const sy0 = (S / static_cast<uint32_t>(lt.sup_x)) * LST, sx0 = (S % static_cast<uint32_t>(lt.sup_x)) * LST;
+    // (sy0, sx0): the super-tile's first tile in the WHOLE maze; gy0: the band's first tile row there
+    uint32_t const SG = S + lt.sup_base, gy0 = lt.tile_base / static_cast<uint32_t>(g.tiles_x);
+    uint32_t const sy0 = (SG / static_cast<uint32_t>(lt.sup_x)) * LST, sx0 = (SG % static_cast<uint32_t>(lt.sup_x)) * LST;
+    auto local_arc = [&](uint32_t ty, uint32_t tx, uint32_t slot) { // (ty, tx) in the whole maze, a tile of this band
+        return (static_cast<long long>(ty - gy0) * g.tiles_x + tx) * LSLOTS + slot;
+    };
     for (uint32_t i = static_cast<uint32_t>(lane); i < LSUP_SLOTS; i += 32u) {
         uint32_t const lt_y = i / (LST * LSLOTS), lt_x = (i / LSLOTS) % LST, slot = i % LSLOTS;
         uint32_t const ty = sy0 + lt_y, tx = sx0 + lt_x;
         uint32_t e = LX_OUT | i;
-        if (ty < static_cast<uint32_t>(g.tiles_y) && tx < static_cast<uint32_t>(g.tiles_x)) {
-            uint32_t const nx = lat_next(lt, (static_cast<long long>(ty) * g.tiles_x + tx) * LSLOTS + slot);
+        if (ty - gy0 < static_cast<uint32_t>(g.tiles_y) && tx < static_cast<uint32_t>(g.tiles_x)) {
+            uint32_t const nx = lat_next(lt, local_arc(ty, tx, slot));
             if (nx < L_LINK) {
                 uint32_t const nt = nx / LSLOTS, ny = nt / static_cast<uint32_t>(g.tiles_x), nxx = nt % static_cast<uint32_t>(g.tiles_x);
                 if (ny - sy0 < static_cast<uint32_t>(LST) && nxx - sx0 < static_cast<uint32_t>(LST)) {
@@ -585,17 +607,17 @@ LAB_DEV void lat_rank_local_super(Params const &p, Lattice const &lt, uint32_t S
     for (uint32_t i = static_cast<uint32_t>(lane); i < LSUP_SLOTS; i += 32u) {
         uint32_t const lt_y = i / (LST * LSLOTS), lt_x = (i / LSLOTS) % LST, slot = i % LSLOTS, side = slot >> 5;
         uint32_t const ty = sy0 + lt_y, tx = sx0 + lt_x;
-        bool const present = ty < static_cast<uint32_t>(g.tiles_y) && tx < static_cast<uint32_t>(g.tiles_x);
+        bool const present = ty - gy0 < static_cast<uint32_t>(g.tiles_y) && tx < static_cast<uint32_t>(g.tiles_x);
         uint64_t pair = 0xFFFFFFFFull; // (no arc: the end, 0 hops)
         bool open = false;
         if (present) {
-            long long const a = (static_cast<long long>(ty) * g.tiles_x + tx) * LSLOTS + slot;
+            long long const a = local_arc(ty, tx, slot);
             open = lab_ld_cg(lt.next + a) != L_NONE;
             if (open) {
                 uint32_t const e = sm[i];
                 uint32_t const last = e & LX_IDX, hops = ((e & ~LX_OUT) >> 13) + 1u;
                 uint32_t const ly = last / (LST * LSLOTS), lx = (last / LSLOTS) % LST;
-                uint32_t const nx = lat_next(lt, (static_cast<long long>(sy0 + ly) * g.tiles_x + sx0 + lx) * LSLOTS + last % LSLOTS);
+                uint32_t const nx = lat_next(lt, local_arc(sy0 + ly, sx0 + lx, last % LSLOTS));
                 uint32_t const dense = (nx >= L_LINK || !(e & LX_OUT)) ? 0xFFFFFFFFu : lat_dense_border(lt, g, nx);
                 pair = static_cast<uint64_t>(dense) | (static_cast<uint64_t>(hops) << 32);
                 lab_st_cg(lt.xd + a, pair);
@@ -604,7 +626,10 @@ LAB_DEV void lat_rank_local_super(Params const &p, Lattice const &lt, uint32_t S
         bool const border = (side == L_N && lt_y == 0) || (side == L_S && lt_y == LST - 1) || (side == L_W && lt_x == 0) || (side == L_E && lt_x == LST - 1);
         if (border) {
             uint32_t const along = (side == L_N || side == L_S) ? lt_x : lt_y;
-            lab_st_cg(lt.gb + static_cast<long long>(S) * LB + side * (LST * LC) + along * LC + (slot & 31u), open ? pair : 0xFFFFFFFFull);
+            long long const at = static_cast<long long>(SG) * LB + side * (LST * LC) + along * LC + (slot & 31u);
+            for (int q = 0; q < lt.peers; q++) { // every rank's copy of the border list (stores over NVLink)
+                lab_st_cg(lt.gb_peer[q] + at, open ? pair : 0xFFFFFFFFull);
+            }
         }
     }
     lab_syncwarp();
@@ -633,8 +658,8 @@ LAB_DEV void lat_rank_global_body(Lattice const &lt, long long gthread, long lon
     if (!lat_live(tc)) {
         return;
     }
-    long long const n = static_cast<long long>(lt.nsuper) * LB;
-    uint32_t const limit = lt.nslots + 2u;
+    long long const n = static_cast<long long>(lt.nsuper_global) * LB;
+    uint32_t const limit = lt.nslots_global + 2u;
     for (int pass = 0; pass < (1 << 20); pass++) { // (a cycle ends through `limit`, not through the pass count)
         bool pending = false;
         for (long long i = gthread; i < n; i += nthreads) {
@@ -720,7 +745,13 @@ LAB_DEV void lat_flood_tile(Params const &p, Lattice const &lt, uint32_t t, int 
     for (int s = 0; s < 4; s++) {
         open[s] = (X[s] >> lane) & 1u;
         Ro[s] = open[s] ? lab_ld_cg(lt.R + base + s * LC + lane) : 0u;
-        Rt[s] = open[s] ? lab_ld_cg(lt.R + lat_twin(g, t, static_cast<uint32_t>(s * LC + lane))) : 0u;
+        Rt[s] = 0u;
+        if (open[s]) {
+            uint32_t const tw = lat_twin(g, t + lt.tile_base, static_cast<uint32_t>(s * LC + lane)); // (global arc id)
+            uint32_t const twl = tw - lt.tile_base * LSLOTS;
+            // a twin in another band is a border arc of its super-tile: its hops are in the (whole-maze) border list
+            Rt[s] = twl < lt.nslots ? lab_ld_cg(lt.R + twl) : static_cast<uint32_t>(lab_ld_cg(lt.gb + lat_dense_border(lt, g, tw)) >> 32);
+        }
         entry[s] = open[s] && Ro[s] > Rt[s];
         bad |= (open[s] && (Ro[s] == Rt[s] || Ro[s] == 0u || Rt[s] == 0u)) ? 1u : 0u;
     }
@@ -791,8 +822,10 @@ LAB_DEV void lat_flood_tile(Params const &p, Lattice const &lt, uint32_t t, int 
     for (int s = 0; s < 4; s++) {
         if (open[s] && !entry[s]) {
             uint32_t const w = ld[s] + 1u;
-            lt.wsum[Rt[s]] = w;
-            lt.wsum[Ro[s]] = 0u - w;
+            for (int q = 0; q < lt.peers; q++) { // every rank's copy of the weights (stores over NVLink)
+                lt.wsum_peer[q][Rt[s]] = w;
+                lt.wsum_peer[q][Ro[s]] = 0u - w;
+            }
         }
     }
 }
@@ -1057,6 +1090,81 @@ LAB_DEV void lat_levels_body(Params const &p, Lattice const &lt, int lane, uint3
     mx = lab_reduce_max(mx);
     if (lane == 0 && mx) {
         lab_atomic_max(&p.ctl->max_level, mx);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row bands: the glue between the phases.  A band runs count + link + local ranking on its own tiles,
+// the ranks put their border-list slices and one header each together (lat_band_header_body -> all-gather, or peer
+// stores), every rank checks the WHOLE maze's counts (lat_band_check_body), finishes the ranking over the whole
+// border list, floods its tiles and scatters its arcs' weights; the weights are joined (all-reduce or peer stores,
+// with each band's count of reached squares in the tail), and every rank scans them and writes its band's levels.
+// Two exchanges per map, whatever its diameter.  All single-thread bodies.
+constexpr uint32_t LAT_HDR = 8;   // words of a band's header
+constexpr uint32_t LAT_TAIL = 8;  // words after wsum[nslots_global + 2): reached squares (lo, hi), error flags
+LAB_DEV void lat_band_open_body(Lattice const &lt) { // before the link: whether the whole maze has a tree's counts is not known yet
+    lt.tc->ok = 1u;
+    lt.tc->lat_on = 1u;
+}
+LAB_DEV void lat_band_header_body(Lattice const &lt, uint32_t *hdr) {
+    Tree_ctl const *tc = lt.tc;
+    hdr[0] = static_cast<uint32_t>(tc->V);
+    hdr[1] = static_cast<uint32_t>(tc->V >> 32);
+    hdr[2] = static_cast<uint32_t>(tc->E);
+    hdr[3] = static_cast<uint32_t>(tc->E >> 32);
+    hdr[4] = tc->n_arcs;
+    hdr[5] = tc->lat_err;
+    hdr[6] = hdr[7] = 0u;
+}
+LAB_DEV void lat_band_check_body(Lattice const &lt, uint32_t const *all_hdr, int world) {
+    Tree_ctl *tc = lt.tc;
+    unsigned long long V = 0, E = 0, arcs = 0;
+    uint32_t err = 0;
+    for (int r = 0; r < world; r++) {
+        uint32_t const *h = all_hdr + static_cast<size_t>(r) * LAT_HDR;
+        V += static_cast<unsigned long long>(h[0]) | (static_cast<unsigned long long>(h[1]) << 32);
+        E += static_cast<unsigned long long>(h[2]) | (static_cast<unsigned long long>(h[3]) << 32);
+        arcs += h[4];
+        err = err ? err : h[5];
+    }
+    tc->V = V;
+    tc->E = E;
+    tc->n_arcs = static_cast<uint32_t>(arcs);
+    tc->ok = (V >= 2 && E + 1 == V && arcs <= lt.nslots_global) ? 1u : 0u; // every rank reads the same headers: they all agree
+    if (err && !tc->lat_err) {
+        tc->lat_err = err;
+    }
+}
+// after the flood: this band's reached squares and flags go where the all-reduce (or the peers' stores) join them
+LAB_DEV void lat_band_tail_body(Lattice const &lt) {
+    Tree_ctl const *tc = lt.tc;
+    uint32_t const at = lt.nslots_global + 2u;
+    for (int q = 0; q < lt.peers; q++) {
+        uint32_t *w = lt.wsum_peer[q] + at;
+        if (lt.peers == 1) { // (to be summed)
+            w[0] = static_cast<uint32_t>(tc->lat_settled); // (a maze has fewer than 2^32 squares: make_geom)
+            w[1] = 0u;
+            w[2] = (tc->lat_flood_bad || tc->lat_err) ? 1u : 0u;
+        } else { // (peer stores: everybody adds into everybody's tail)
+            lab_atomic_add(w, static_cast<uint32_t>(tc->lat_settled));
+            lab_atomic_add(w + 2, (tc->lat_flood_bad || tc->lat_err) ? 1u : 0u);
+        }
+    }
+}
+// before the gate: this control block belongs to the lattice road alone -- if it gave up, no pipeline made the field
+LAB_DEV void lat_band_close_body(Lattice const &lt) {
+    Tree_ctl *tc = lt.tc;
+    if (!(tc->ok != 0 && lat_made(tc))) {
+        tc->ok = 0u;
+    }
+}
+LAB_DEV void lat_band_settled_body(Lattice const &lt) {
+    Tree_ctl *tc = lt.tc;
+    uint32_t const *w = lt.wsum + lt.nslots_global + 2u;
+    tc->lat_settled = w[0];
+    tc->lat_flood_bad = w[2];
+    if (w[2] && !tc->lat_err) {
+        tc->lat_err = 4u;
     }
 }
 

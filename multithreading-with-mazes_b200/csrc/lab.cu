@@ -230,6 +230,12 @@ __global__ void __launch_bounds__(128) k_lat_levels(Params p, Lattice lt) {
     __shared__ uint32_t sm[4][L_LINK_SM];
     lat_levels_body(p, lt, lane_id(), sm[threadIdx.x >> 5]);
 }
+__global__ void k_lat_band_open(Lattice lt) { lat_band_open_body(lt); }
+__global__ void k_lat_band_header(Lattice lt, uint32_t *hdr) { lat_band_header_body(lt, hdr); }
+__global__ void k_lat_band_check(Lattice lt, uint32_t const *all_hdr, int world) { lat_band_check_body(lt, all_hdr, world); }
+__global__ void k_lat_band_tail(Lattice lt) { lat_band_tail_body(lt); }
+__global__ void k_lat_band_settled(Lattice lt) { lat_band_settled_body(lt); }
+__global__ void k_lat_band_close(Lattice lt) { lat_band_close_body(lt); }
 __global__ void __launch_bounds__(256) k_tree_orient(Params p, Tree tr) { tree_orient_body(p, tr, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void __launch_bounds__(128) k_tree_flood(Params p, Tree tr) {
     extern __shared__ __align__(16) uint64_t flood_sm[];
@@ -435,6 +441,9 @@ struct lab_grid {
     bool tree_tried = false;
     Lattice lat{}; // the lattice road's workspace (allocated on first use)
     bool lat_alloc = false;
+    Lattice band_lat{}; // ... across row bands (lab_band_lat_*): whole-maze geometry, the caller's whole-maze arrays
+    bool band_lat_bound = false;
+    Tree_ctl *band_lat_tc = nullptr;
     uint64_t launches = 0; // kernels launched by the last search (bench.py reports them)
     bool tree_cfg = false;
     // the pipeline across row bands (lab_band_tree_*): the caller's global arrays, this band's control block
@@ -696,6 +705,12 @@ int ensure_lattice(lab_grid *h) {
     CU(cudaMalloc(&lt.wsum, (nt * LSLOTS + 2 + L_CHUNK) * sizeof(uint32_t)));
     CU(cudaMalloc(&lt.chunk, (nt * LSLOTS / L_CHUNK + 2) * sizeof(uint32_t)));
     CU(cudaFuncSetAttribute(k_lat_rank_local, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(LAT_RANK_WARPS * LSUP_SLOTS * sizeof(uint32_t))));
+    lt.tile_base = lt.sup_base = 0;
+    lt.nsuper_global = lt.nsuper;
+    lt.nslots_global = lt.nslots;
+    lt.peers = 1;
+    lt.gb_peer[0] = lt.gb;
+    lt.wsum_peer[0] = lt.wsum;
     h->lat_alloc = true;
     return LAB_OK;
 }
@@ -1091,6 +1106,7 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->d_front_rc);
     cudaFree(h->d_paths);
     cudaFree(h->band_tree.tc);
+    cudaFree(h->band_lat_tc);
     if (h->owns_pixels) {
         cudaFree(h->pixels);
     }
@@ -1632,6 +1648,167 @@ int lab_band_finish(lab_grid *h, uint64_t *local_max, uint64_t *local_settled) {
     if (rc) return rc;
     if (local_max) *local_max = h->last.max_level;
     if (local_settled) *local_settled = h->last.settled;
+    return LAB_OK;
+}
+
+// ---- the lattice road across row bands (device/lattice.cuh; protocol in include/labyrinth_b200.h) ----
+int lab_band_lat_super_rows(void) { return LST; }
+int lab_band_lat_words(int tiles_x, int super_rows_global, uint64_t *border_entries, uint64_t *weight_words, uint64_t *chunk_words) {
+    if (tiles_x < 1 || super_rows_global < 1) {
+        return fail(LAB_ERR_ARG, "lab_band_lat_words: bad argument");
+    }
+    unsigned long long const sup_x = (static_cast<unsigned long long>(tiles_x) + LST - 1) / LST;
+    unsigned long long const nslots = static_cast<unsigned long long>(super_rows_global) * LST * tiles_x * LSLOTS;
+    if (nslots + 2 + LAT_TAIL >= (1ull << 32)) {
+        return fail(LAB_ERR_ARG, "lab_band_lat_words: maze too large");
+    }
+    if (border_entries) *border_entries = static_cast<unsigned long long>(super_rows_global) * sup_x * LB;
+    if (weight_words) *weight_words = nslots + 2 + LAT_TAIL + L_CHUNK;
+    if (chunk_words) *chunk_words = nslots / L_CHUNK + 2;
+    return LAB_OK;
+}
+
+int lab_band_lat_bind(lab_grid *h, int super_row_base, int super_rows_band, int super_rows_global, void *border_list, void *weights, void *chunks) {
+    Device_guard const guard_(h);
+    if (!h || !border_list || !weights || !chunks || super_row_base < 0 || super_rows_band < 1 || super_row_base + super_rows_band > super_rows_global ||
+        (reinterpret_cast<uintptr_t>(border_list) & 7u)) {
+        return fail(LAB_ERR_ARG, "lab_band_lat_bind: bad argument");
+    }
+    if (h->g.tiles_y > super_rows_band * LST) {
+        return fail(LAB_ERR_ARG, "lab_band_lat_bind: the band has %d tile rows, more than %d super-tile rows hold", h->g.tiles_y, super_rows_band);
+    }
+    int rc = ensure_lattice(h); // (the per-tile arrays; its own border list and weights stay unused here)
+    if (rc) return rc;
+    if (!h->band_lat_tc) {
+        CU(cudaMalloc(&h->band_lat_tc, sizeof(Tree_ctl)));
+    }
+    Lattice lt = h->lat;
+    lt.tc = h->band_lat_tc;
+    lt.sup_y = super_rows_band; // (the last band may have fewer tile rows than that: its missing tiles count as empty)
+    lt.nsuper = lt.sup_y * lt.sup_x;
+    lt.tile_base = static_cast<uint32_t>(super_row_base) * LST * static_cast<uint32_t>(h->g.tiles_x);
+    lt.sup_base = static_cast<uint32_t>(super_row_base) * static_cast<uint32_t>(lt.sup_x);
+    lt.nsuper_global = super_rows_global * lt.sup_x;
+    lt.nslots_global = static_cast<uint32_t>(static_cast<unsigned long long>(super_rows_global) * LST * h->g.tiles_x * LSLOTS);
+    lt.gb = static_cast<uint64_t *>(border_list);
+    lt.wsum = static_cast<uint32_t *>(weights);
+    lt.chunk = static_cast<uint32_t *>(chunks);
+    lt.peers = 1;
+    lt.gb_peer[0] = lt.gb;
+    lt.wsum_peer[0] = lt.wsum;
+    h->band_lat = lt;
+    h->band_lat_bound = true;
+    return LAB_OK;
+}
+
+// Peer mode: the border-list slices and the weights are stored straight into every rank's copy (over NVLink) from inside
+// the kernels that make them; [0] must be this rank's own arrays.
+int lab_band_lat_set_peers(lab_grid *h, int n, void *const *border_lists, void *const *weights) {
+    Device_guard const guard_(h);
+    if (!h || !h->band_lat_bound || n < 1 || n > 8 || !border_lists || !weights || border_lists[0] != h->band_lat.gb || weights[0] != h->band_lat.wsum) {
+        return fail(LAB_ERR_ARG, "lab_band_lat_set_peers: bad argument");
+    }
+    h->band_lat.peers = n;
+    for (int q = 0; q < n; q++) {
+        h->band_lat.gb_peer[q] = static_cast<uint64_t *>(border_lists[q]);
+        h->band_lat.wsum_peer[q] = static_cast<uint32_t *>(weights[q]);
+    }
+    return LAB_OK;
+}
+
+static int band_lat_ready(lab_grid *h, char const *who) {
+    if (!h || !h->band_open || !h->band_lat_bound) {
+        return fail(LAB_ERR_ARG, "%s: no band search open, or lab_band_lat_bind not called", who);
+    }
+    return LAB_OK;
+}
+
+// Phase 1 (after lab_band_set_neighbour_paths): counts, link, local ranking -> this band's slice of the border list (in
+// place, or in every peer's copy) and its header.  The root must be on a cell ((odd, odd) in the whole maze).
+int lab_band_lat_link(lab_grid *h, void *header_dev) {
+    Device_guard const guard_(h);
+    int rc = band_lat_ready(h, "lab_band_lat_link");
+    if (rc) return rc;
+    if (!header_dev) {
+        return fail(LAB_ERR_ARG, "lab_band_lat_link: null header");
+    }
+    cudaStream_t s = h->stream;
+    Lattice const lt = h->band_lat;
+    Params p = make_params(h, 1);
+    Tree tr{};
+    tr.tc = lt.tc;
+    tr.banded = 1;
+    CU(cudaMemsetAsync(lt.tc, 0, sizeof(Tree_ctl), s));
+    k_tree_count<<<std::min(blocks_for(h, h->g.ntiles, 256), h->sm_count * 8), 256, 0, s>>>(p, tr);
+    k_lat_band_open<<<1, 1, 0, s>>>(lt);
+    int const tile_blocks = static_cast<int>(std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 16));
+    k_lat_link<<<tile_blocks, 128, 0, s>>>(p, lt);
+    size_t const rank_smem = LAT_RANK_WARPS * LSUP_SLOTS * sizeof(uint32_t);
+    int const rank_blocks = std::min((lt.nsuper + LAT_RANK_WARPS - 1) / LAT_RANK_WARPS, h->sm_count * 6);
+    k_lat_rank_local<<<rank_blocks, 32 * LAT_RANK_WARPS, rank_smem, s>>>(p, lt);
+    k_lat_band_header<<<1, 1, 0, s>>>(lt, static_cast<uint32_t *>(header_dev));
+    h->launches += 5;
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+// Phase 2 (the border list and the headers of all ranks are in place): the whole maze's counts, the ranking over the whole
+// border list, this band's floods; its arcs' weights and its count of reached squares go into the weights array.
+// zero_weights: clear the array first (the copies are summed afterwards); 0 in peer mode, where every position is
+// written by the rank that owns it (the caller clears the tail words once per map).
+int lab_band_lat_flood(lab_grid *h, const void *all_headers_dev, int world, int zero_weights) {
+    Device_guard const guard_(h);
+    int rc = band_lat_ready(h, "lab_band_lat_flood");
+    if (rc) return rc;
+    if (!all_headers_dev || world < 1) {
+        return fail(LAB_ERR_ARG, "lab_band_lat_flood: bad argument");
+    }
+    cudaStream_t s = h->stream;
+    Lattice const lt = h->band_lat;
+    Params p = make_params(h, 1);
+    if (zero_weights) {
+        CU(cudaMemsetAsync(lt.wsum, 0, (static_cast<size_t>(lt.nslots_global) + 2 + LAT_TAIL) * sizeof(uint32_t), s));
+    }
+    k_lat_band_check<<<1, 1, 0, s>>>(lt, static_cast<uint32_t const *>(all_headers_dev), world);
+    long long const nb = static_cast<long long>(lt.nsuper_global) * LB;
+    k_lat_rank_global<<<static_cast<int>(std::min<long long>((nb + 255) / 256, static_cast<long long>(h->sm_count) * 8)), 256, 0, s>>>(lt);
+    k_lat_rank_expand<<<static_cast<int>(std::min<long long>((static_cast<long long>(lt.nslots) + 255) / 256, static_cast<long long>(h->sm_count) * 16)), 256, 0, s>>>(lt);
+    int const tile_blocks = static_cast<int>(std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 16));
+    k_lat_flood<<<tile_blocks, 128, 0, s>>>(p, lt);
+    k_lat_band_tail<<<1, 1, 0, s>>>(lt);
+    h->launches += 5;
+    CU(cudaGetLastError());
+    return LAB_OK;
+}
+
+// Phase 3 (the weights of all ranks are in place): prefix sums over the whole tour, this band's levels.  *used = 1: the
+// band's level field is final (lab_band_finish is left); 0: not one lattice tree, nothing was written.
+int lab_band_lat_levels(lab_grid *h, int32_t *used) {
+    Device_guard const guard_(h);
+    int rc = band_lat_ready(h, "lab_band_lat_levels");
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    Lattice const lt = h->band_lat;
+    Params p = make_params(h, 1);
+    k_lat_band_settled<<<1, 1, 0, s>>>(lt);
+    k_lat_scan_chunks<<<static_cast<int>(std::min<long long>((static_cast<long long>(lt.nslots_global) / L_CHUNK + 8) / 8, static_cast<long long>(h->sm_count) * 8)), 256, 0, s>>>(lt);
+    k_lat_scan_tops<<<1, 32, 0, s>>>(lt);
+    int const tile_blocks = static_cast<int>(std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 16));
+    k_lat_levels<<<tile_blocks, 128, 0, s>>>(p, lt);
+    k_lat_band_close<<<1, 1, 0, s>>>(lt);
+    Tree tr{};
+    tr.tc = lt.tc;
+    tr.banded = 1;
+    k_tree_gate<<<h->sm_count * 2, 256, 0, s>>>(p, tr);
+    h->launches += 6;
+    CU(cudaGetLastError());
+    Tree_ctl c{};
+    CU(cudaMemcpyAsync(&c, lt.tc, sizeof c, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    h->tree_last = c;
+    if (used) {
+        *used = c.used == 3u ? 1 : 0;
+    }
     return LAB_OK;
 }
 

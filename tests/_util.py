@@ -111,6 +111,10 @@ def emu_band_engine(squares: np.ndarray, nwarps: int = 4, sched: int = 0):
 
     class EmuBandEngine(bands._BandEngine):
         prefix = "emu_band_"
+        supports_lattice = True
+
+        def grid_cols(self):
+            return self.cols
 
         def __init__(self):
             self.torch = torch

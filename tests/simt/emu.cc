@@ -69,6 +69,11 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
         lt.xd = xd.data(); lt.gb = gb.data(); lt.R = R.data(); lt.dplane = dplane.data(); lt.emask = emask.data(); lt.wsum = wsum.data();
         lt.chunk = chunk.data();
         lt.tc = &tc;
+        lt.nsuper_global = lt.nsuper;
+        lt.nslots_global = lt.nslots;
+        lt.peers = 1;
+        lt.gb_peer[0] = lt.gb;
+        lt.wsum_peer[0] = lt.wsum;
         std::vector<uint32_t> lsm(static_cast<size_t>(nwarps) * LSUP_SLOTS);
         long long const nth = static_cast<long long>(nwarps) * 32;
         simt::launch(nwarps, [&](int wid, int lane) { lat_link_body(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS); }, sched_seed);
@@ -248,6 +253,12 @@ struct Emu_band {
     Band_layout const *layout = nullptr;
     int world = 1, me = 0;
     Tree_ctl tree_last{};
+    // the lattice road across bands (emu_band_lat_*)
+    Lattice lat{};
+    Tree_ctl lat_tc{};
+    std::vector<uint32_t> l_mask, l_xmask, l_next, l_lplane, l_R, l_dplane, l_emask, l_nruns, l_sm;
+    std::vector<uint16_t> l_label, l_cmap;
+    std::vector<uint64_t> l_xd;
 };
 
 void *emu_band_create(int rows, int cols, uint16_t *grid, int nwarps, unsigned sched_seed) {
@@ -580,6 +591,114 @@ int emu_band_tree_levels(void *h, uint32_t const *all3, int32_t *used) {
     simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, local, static_cast<long long>(wid) * 32 + lane, nthreads); });
     e->tree_last = e->tc;
     *used = static_cast<int32_t>(e->tree_last.used);
+    return 0;
+}
+
+// ---- the lattice road across bands: emu_band_lat_* mirror lab_band_lat_* (csrc/lab.cu) ----
+int emu_band_lat_super_rows(void) { return LST; }
+int emu_band_lat_words(int tiles_x, int super_rows_global, uint64_t *border_entries, uint64_t *weight_words, uint64_t *chunk_words) {
+    unsigned long long const sup_x = (static_cast<unsigned long long>(tiles_x) + LST - 1) / LST;
+    unsigned long long const nslots = static_cast<unsigned long long>(super_rows_global) * LST * tiles_x * LSLOTS;
+    *border_entries = static_cast<unsigned long long>(super_rows_global) * sup_x * LB;
+    *weight_words = nslots + 2 + LAT_TAIL + L_CHUNK;
+    *chunk_words = nslots / L_CHUNK + 2;
+    return 0;
+}
+int emu_band_lat_bind(void *h, int super_row_base, int super_rows_band, int super_rows_global, uint64_t *border_list, uint32_t *weights, uint32_t *chunks) {
+    auto *e = static_cast<Emu_band *>(h);
+    Geom const &g = e->w.g;
+    if (g.tiles_y > super_rows_band * LST) return -1;
+    size_t const nt = static_cast<size_t>(g.ntiles);
+    e->l_mask.assign(nt * 96, 0xDEADBEEFu);
+    e->l_xmask.assign(nt * 4, 0);
+    e->l_next.assign(nt * LSLOTS, 0xDEADBEEFu);
+    e->l_label.assign(nt * LSLOTS, 0);
+    e->l_cmap.assign(nt * 512, 0xDEAD);
+    e->l_nruns.assign(nt, 0);
+    e->l_lplane.assign(nt * L_LABEL_PLANES * 32, 0);
+    e->l_xd.assign(nt * LSLOTS, 0xDEADBEEFDEADBEEFull);
+    e->l_R.assign(nt * LSLOTS, 0xDEADBEEFu);
+    e->l_dplane.assign(nt * L_DEPTH_PLANES * 32, 0);
+    e->l_emask.assign(nt * 4, 0);
+    e->l_sm.assign(static_cast<size_t>(e->nwarps) * LSUP_SLOTS, 0);
+    Lattice &lt = e->lat;
+    lt = Lattice{};
+    lt.mask = e->l_mask.data(); lt.xmask = e->l_xmask.data(); lt.next = e->l_next.data(); lt.label = e->l_label.data(); lt.cmap = e->l_cmap.data();
+    lt.nruns = e->l_nruns.data(); lt.lplane = e->l_lplane.data(); lt.xd = e->l_xd.data(); lt.R = e->l_R.data(); lt.dplane = e->l_dplane.data();
+    lt.emask = e->l_emask.data();
+    lt.tc = &e->lat_tc;
+    lt.sup_x = (g.tiles_x + LST - 1) / LST;
+    lt.sup_y = super_rows_band;
+    lt.nsuper = lt.sup_y * lt.sup_x;
+    lt.nslots = static_cast<uint32_t>(nt * LSLOTS);
+    lt.tile_base = static_cast<uint32_t>(super_row_base) * LST * static_cast<uint32_t>(g.tiles_x);
+    lt.sup_base = static_cast<uint32_t>(super_row_base) * static_cast<uint32_t>(lt.sup_x);
+    lt.nsuper_global = super_rows_global * lt.sup_x;
+    lt.nslots_global = static_cast<uint32_t>(static_cast<unsigned long long>(super_rows_global) * LST * g.tiles_x * LSLOTS);
+    lt.gb = border_list;
+    lt.wsum = weights;
+    lt.chunk = chunks;
+    lt.peers = 1;
+    lt.gb_peer[0] = lt.gb;
+    lt.wsum_peer[0] = lt.wsum;
+    return 0;
+}
+int emu_band_lat_set_peers(void *h, int n, void *const *border_lists, void *const *weights) {
+    auto *e = static_cast<Emu_band *>(h);
+    e->lat.peers = n;
+    for (int q = 0; q < n; q++) {
+        e->lat.gb_peer[q] = static_cast<uint64_t *>(border_lists[q]);
+        e->lat.wsum_peer[q] = static_cast<uint32_t *>(weights[q]);
+    }
+    return 0;
+}
+int emu_band_lat_link(void *h, uint32_t *header) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    Lattice const lt = e->lat;
+    e->lat_tc = Tree_ctl{};
+    Tree tr{};
+    tr.tc = &e->lat_tc;
+    tr.banded = 1;
+    simt::launch(nw, [&](int wid, int lane) { tree_count_body(p, tr, wid, nw, lane); });
+    lat_band_open_body(lt);
+    simt::launch(nw, [&](int wid, int lane) { lat_link_body(p, lt, lane, e->l_sm.data() + static_cast<size_t>(wid) * LSUP_SLOTS); }, e->sched);
+    simt::launch(nw, [&](int wid, int lane) { lat_rank_local_body(p, lt, lane, e->l_sm.data() + static_cast<size_t>(wid) * LSUP_SLOTS); }, e->sched);
+    lat_band_header_body(lt, header);
+    return 0;
+}
+int emu_band_lat_flood(void *h, uint32_t const *all_headers, int world, int zero_weights) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    long long const nth = static_cast<long long>(nw) * 32;
+    Lattice const lt = e->lat;
+    if (zero_weights) std::memset(lt.wsum, 0, (static_cast<size_t>(lt.nslots_global) + 2 + LAT_TAIL) * sizeof(uint32_t));
+    lat_band_check_body(lt, all_headers, world);
+    simt::launch(nw, [&](int wid, int lane) { lat_rank_global_body(lt, static_cast<long long>(wid) * 32 + lane, nth); }, e->sched);
+    simt::launch(nw, [&](int wid, int lane) { lat_rank_expand_body(lt, static_cast<long long>(wid) * 32 + lane, nth); });
+    simt::launch(nw, [&](int wid, int lane) { lat_flood_body(p, lt, lane); }, e->sched);
+    lat_band_tail_body(lt);
+    return 0;
+}
+int emu_band_lat_levels(void *h, int32_t *used) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    int const nw = e->nwarps;
+    long long const nth = static_cast<long long>(nw) * 32;
+    Lattice const lt = e->lat;
+    lat_band_settled_body(lt);
+    simt::launch(nw, [&](int wid, int lane) { lat_scan_chunks_body(lt, wid, nw, lane); });
+    simt::launch(1, [&](int, int lane) { lat_scan_tops_body(lt, lane); });
+    simt::launch(nw, [&](int wid, int lane) { lat_levels_body(p, lt, lane, e->l_sm.data() + static_cast<size_t>(wid) * LSUP_SLOTS); }, e->sched);
+    lat_band_close_body(lt);
+    Tree tr{};
+    tr.tc = &e->lat_tc;
+    tr.banded = 1;
+    simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, tr, static_cast<long long>(wid) * 32 + lane, nth); });
+    e->tree_last = e->lat_tc;
+    *used = e->lat_tc.used == 3u ? 1 : 0;
     return 0;
 }
 

@@ -149,17 +149,77 @@ def _gloo_emu_worker(rank, world, port, maze_path, out_dir, use_tree):
     dist.destroy_process_group()
 
 
+def _gloo_emu_lattice_worker(rank, world, port, maze_path, out_dir, start):
+    """The lattice road across bands of whole super-tile rows (bands.split_rows_super), kernel bodies on the emulator."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    import __graft_entry__ as graft
+    from _util import emu_band_engine
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lab = graft.load_package()
+    from mazes_b200 import bands
+
+    maze = np.load(maze_path)
+    r0, n = bands.split_rows_super(maze.shape[0], world)[rank]
+    eng = emu_band_engine(maze[r0 : r0 + n].copy(), nwarps=3, sched=rank + 1)
+    res = bands.sharded_distance_map(eng, tuple(start) if start else lab.distance_start(*maze.shape), r0, n)
+    np.savez(os.path.join(out_dir, f"band{rank}.npz"), dist=eng.levels(), sq=eng.sq, r0=r0, mx=res["max"], settled=res["settled"],
+             rounds=res["rounds"], road=res["road"], used=eng.tree_used())
+    eng.close()
+    dist.destroy_process_group()
+
+
 def _check_bands(tmp_path, world, maze, O, road):
     g_ref, d_ref, mx_ref, settled_ref = O.distance_map(maze)
     for rank in range(world):
         z = np.load(tmp_path / f"band{rank}.npz")
         r0 = int(z["r0"])
         n = z["dist"].shape[0]
-        assert str(z["road"]) == road and int(z["used"]) == {"wave": 0, "tree": 1, "room": 2}[road], (rank, str(z["road"]), int(z["used"]))
+        assert str(z["road"]) == road and int(z["used"]) == {"wave": 0, "tree": 1, "room": 2, "lattice": 3}[road], (rank, str(z["road"]), int(z["used"]))
         assert (int(z["rounds"]) == 0) == (road != "wave")
         assert (z["dist"] == d_ref[r0 : r0 + n]).all(), (rank, int((z["dist"] != d_ref[r0 : r0 + n]).sum()))
         assert (z["sq"] == g_ref[r0 : r0 + n]).all()
         assert int(z["mx"]) == mx_ref and int(z["settled"]) == settled_ref
+
+
+@pytest.mark.parametrize("builder,rows,cols,world,start", [("kruskal", 511, 131, 2, None), ("wilson", 767, 67, 3, None), ("rdfs", 513, 129, 2, (511, 1)),
+                                                          ("kruskal", 767, 65, 3, (1, 63))])
+def test_sharded_lattice_road_on_gloo(lab, O, tmp_path, builder, rows, cols, world, start):
+    """Reference builders' mazes across 2-3 bands of whole super-tile rows: the lattice road, two exchanges per map,
+    bit-exact.  (513 rows over 2 ranks: the last band is ONE row; starts in the first / last band, next to a band border.)"""
+    import torch.multiprocessing as mp
+
+    maze = lab.build_maze(builder, rows, cols, seed=37)
+    path = str(tmp_path / "maze.npy")
+    np.save(path, maze)
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_emu_lattice_worker, args=(world, port, path, str(tmp_path), start), nprocs=world, join=True)
+    if start is None:
+        _check_bands(tmp_path, world, maze, O, "lattice")
+    else:
+        d_ref = O.bfs_levels(maze, *start)
+        for rank in range(world):
+            z = np.load(tmp_path / f"band{rank}.npz")
+            r0, n = int(z["r0"]), z["dist"].shape[0]
+            assert str(z["road"]) == "lattice" and int(z["used"]) == 3
+            assert (z["dist"] == d_ref[r0 : r0 + n]).all(), (rank, int((z["dist"] != d_ref[r0 : r0 + n]).sum()))
+
+
+def test_sharded_lattice_that_is_no_tree_falls_back_on_gloo(lab, O, tmp_path):
+    import torch.multiprocessing as mp
+
+    from test_tree_pipeline import tree_looking_non_tree
+
+    maze = tree_looking_non_tree(lab, 511, 67, 2)
+    path = str(tmp_path / "maze.npy")
+    np.save(path, maze)
+    port = 35800 + (os.getpid() % 2000)
+    mp.spawn(_gloo_emu_lattice_worker, args=(2, port, path, str(tmp_path), None), nprocs=2, join=True)
+    _check_bands(tmp_path, 2, maze, O, "wave")
 
 
 @pytest.mark.parametrize("builder,rows,cols,world", [("kruskal", 255, 131, 2), ("wilson", 193, 197, 3), ("rdfs", 257, 67, 2), ("kruskal", 447, 65, 3)])
