@@ -249,6 +249,8 @@ int lab_band_tree_levels(lab_grid *g, const void *all_chunks3, int32_t *used);
  * lists and weights arrays as device pointers valid on this device ([0] = this rank's own); the kernels then store a
  * band's slice and weights into EVERY rank's arrays themselves (NVLink peer stores) and the two exchanges shrink to
  * barriers (call lab_band_lat_flood with zero_weights = 0 and clear the last 8 weight words before lab_band_lat_link). */
+int lab_band_begin_lattice(lab_grid *g, int game, int src_r, int src_c, int lattice_next); /* lab_band_begin_game that leaves the field's reset and the
+                                                                                           * measure bits to the lattice road (lattice_next != 0) */
 int lab_band_lat_super_rows(void);
 int lab_band_lat_words(int tiles_x, int super_rows_global, uint64_t *border_entries, uint64_t *weight_words, uint64_t *chunk_words);
 int lab_band_lat_bind(lab_grid *g, int super_row_base, int super_rows_band, int super_rows_global, void *border_list, void *weights,

@@ -39,7 +39,7 @@ ABI_SYMBOLS = (
     "lab_band_export_edges", "lab_band_import_edges", "lab_band_finish",
     "lab_band_tree_bind", "lab_band_tree_chunk_words", "lab_band_tree_count", "lab_band_tree_rank_local", "lab_band_tree_flood",
     "lab_band_tree_prefix_local", "lab_band_tree_levels", "lab_band_room",
-    "lab_band_lat_super_rows", "lab_band_lat_words", "lab_band_lat_bind", "lab_band_lat_set_peers", "lab_band_lat_link", "lab_band_lat_flood",
+    "lab_band_begin_lattice", "lab_band_lat_super_rows", "lab_band_lat_words", "lab_band_lat_bind", "lab_band_lat_set_peers", "lab_band_lat_link", "lab_band_lat_flood",
     "lab_band_lat_levels",
     "lab_band_begin_game", "lab_band_level_at", "lab_band_paint", "lab_band_walk", "lab_band_recolour", "lab_band_finish_game",
 )

@@ -112,9 +112,9 @@ class _BandEngine:
     def _ptr(t):
         return c_void_p(t.data_ptr()) if t is not None else None
 
-    def begin(self, src_local: Optional[Tuple[int, int]]):
+    def begin(self, src_local: Optional[Tuple[int, int]], lattice_next: bool = False):
         r, c = src_local if src_local is not None else (-1, -1)
-        self._check(self._f("begin")(self.h, c_int(r), c_int(c)))
+        self._check(self._f("begin_lattice")(self.h, c_int(0), c_int(r), c_int(c), c_int(1 if lattice_next else 0)))
 
     def path_rows(self):
         self._check(self._f("path_rows")(self.h, self._ptr(self._u8[0]), self._ptr(self._u8[1])))
@@ -191,9 +191,9 @@ class _BandEngine:
         return (int(v.value), int(e.value), int(x.value)) + tuple(int(b) for b in box)
 
     # -- the solvers across bands (lab_band_begin_game, _level_at, _paint, _walk, _recolour, _finish_game) --
-    def begin_game(self, game: int, src_local: Optional[Tuple[int, int]]):
+    def begin_game(self, game: int, src_local: Optional[Tuple[int, int]], lattice_next: bool = False):
         r, c = src_local if src_local is not None else (-1, -1)
-        self._check(self._f("begin_game")(self.h, c_int(game), c_int(r), c_int(c)))
+        self._check(self._f("begin_lattice")(self.h, c_int(game), c_int(r), c_int(c), c_int(1 if lattice_next else 0)))
 
     def level_at(self, r: int, c: int) -> int:
         v = c_uint32()
@@ -331,7 +331,11 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     sr, sc = start_global
     src_local = (sr - row0, sc) if row0 <= sr < row0 + rows_local else None
     tr = _Trace(engine.row_device)
-    engine.begin(src_local)
+    lattice_layout = _lattice_layout(engine, start_global, row0, rows_local, group) if (use_tree and use_lattice) else None
+    if lattice_layout is not None:
+        engine.begin(src_local, lattice_next=True)
+    else:
+        engine.begin(src_local)
     tr.mark("begin")
     top, bottom = engine.path_rows()
     if world > 1 and dist.get_backend(group) == "nccl":  # one flat all-gather beats two send/recv pairs for rows this small
@@ -350,7 +354,7 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     rounds = 0
     tree = False
     if use_tree and getattr(engine, "supports_tree", False):
-        lattice = use_lattice and getattr(engine, "supports_lattice", False) and _sharded_lattice(engine, start_global, row0, rows_local, group, tr)
+        lattice = lattice_layout is not None and _sharded_lattice(engine, lattice_layout, group, tr)
         tree = "lattice" if lattice else _sharded_tree(engine, start_global, row0, rows_local, group, tr)
     while not tree:
         rounds += 1
@@ -397,20 +401,16 @@ def tree_layout(split, tiles_x: int):
     return {"split": list(split), "bases": bases, "ntiles": ntiles, "total": total, "tiles_x": tiles_x}
 
 
-def _sharded_lattice(engine, start_global, row0, rows_local, group, tr=None) -> bool:
-    """The lattice road (csrc/device/lattice.cuh) across the bands.  Collective.  Two exchanges per map: the bands' slices
-    of the border list (+ one header each) are all-gathered, every rank finishes the ranking over the whole list and
-    floods its own tiles; the arcs' weights, scattered by tour position into a whole-maze array, are summed over the
-    ranks; every rank scans them and writes its band's levels.  True: the bands' level fields are final; False: not
-    applicable (bands not whole super-tile rows, even sizes, start not on a cell) or not one lattice tree -- nothing has
-    been written and the general pipeline / the wave take over."""
+def _lattice_layout(engine, start_global, row0, rows_local, group):
+    """(super-tile rows per band, rows of the whole maze) if the lattice road across bands applies -- bands of whole
+    super-tile rows, all of one height but the last, odd sizes, the start on a cell -- else None.  Collective the first time."""
     import torch
     import torch.distributed as dist
 
-    rank = dist.get_rank(group)
+    if not getattr(engine, "supports_lattice", False):
+        return None
     world = dist.get_world_size(group)
     dev = engine.row_device
-    mark = tr.mark if tr is not None else (lambda name: None)
     cached = getattr(engine, "_lat_layout", None)
     if cached is None or cached[0] != (row0, rows_local, world):
         t = torch.tensor([row0, rows_local], dtype=torch.int64, device=dev)
@@ -423,12 +423,28 @@ def _sharded_lattice(engine, start_global, row0, rows_local, group, tr=None) -> 
         cached = ((row0, rows_local, world), (per, sum(n for _, n in split)) if ok else None)
         engine._lat_layout = cached
     if cached[1] is None:
-        return False
+        return None
     per, rows_global = cached[1]
-    cols = int(engine.grid_cols())
     sr, sc = start_global
-    if not (rows_global % 2 and cols % 2 and sr % 2 and sc % 2):
-        return False
+    if not (rows_global % 2 and int(engine.grid_cols()) % 2 and sr % 2 and sc % 2):
+        return None
+    return cached[1]
+
+
+def _sharded_lattice(engine, layout, group, tr=None) -> bool:
+    """The lattice road (csrc/device/lattice.cuh) across the bands.  Collective.  Two exchanges per map: the bands' slices
+    of the border list (+ one header each) are all-gathered, every rank finishes the ranking over the whole list and
+    floods its own tiles; the arcs' weights, scattered by tour position into a whole-maze array, are summed over the
+    ranks; every rank scans them and writes its band's levels.  True: the bands' level fields are final; False: not
+    applicable (bands not whole super-tile rows, even sizes, start not on a cell) or not one lattice tree -- nothing has
+    been written and the general pipeline / the wave take over."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    mark = tr.mark if tr is not None else (lambda name: None)
+    per, rows_global = layout
     b = engine.lat_bind(rank, per, world)
     engine.lat_link(b["hdr"])
     mark("lattice: link + local rank")
@@ -440,7 +456,11 @@ def _sharded_lattice(engine, start_global, row0, rows_local, group, tr=None) -> 
     engine.lat_flood(b["all_hdr"], world, True)
     mark("lattice: rank + flood")
     if world > 1:
-        dist.all_reduce(b["wsum"][: b["reduce_words"]], op=dist.ReduceOp.SUM, group=group)
+        # only the tour's positions (1 .. arcs of the whole maze) hold weights; the bands' counts sit in the array's tail
+        arcs = int(b["all_hdr"].view(world, 8)[:, 4].sum().item())
+        tail = b["reduce_words"] - 8
+        dist.all_reduce(b["wsum"][: min(arcs + 2, tail)], op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(b["wsum"][tail: tail + 8], op=dist.ReduceOp.SUM, group=group)
     mark("lattice: all-reduce weights")
     used = engine.lat_levels()
     mark("lattice: scan + levels")
@@ -539,12 +559,13 @@ def _sharded_field(engine, game, start_global, row0, rows_local, group):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     sr, sc = start_global
     tr = _Trace(engine.row_device)
-    engine.begin_game(game, (sr - row0, sc) if row0 <= sr < row0 + rows_local else None)
+    lattice_layout = _lattice_layout(engine, start_global, row0, rows_local, group)
+    engine.begin_game(game, (sr - row0, sc) if row0 <= sr < row0 + rows_local else None, lattice_next=lattice_layout is not None)
     top, bottom = engine.path_rows()
     above_bottom, below_top = _exchange(dist, rank, world, top, bottom, engine, group)
     engine.set_neighbour_paths(above_bottom, below_top)
     road = False
-    if getattr(engine, "supports_lattice", False) and _sharded_lattice(engine, start_global, row0, rows_local, group, tr):
+    if lattice_layout is not None and _sharded_lattice(engine, lattice_layout, group, tr):
         road = True  # (the lattice road leaves the same level field the general pipeline does)
     if not road:
         road = _sharded_tree(engine, start_global, row0, rows_local, group, tr)

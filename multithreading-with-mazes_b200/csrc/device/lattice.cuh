@@ -1161,6 +1161,7 @@ LAB_DEV void lat_band_close_body(Lattice const &lt) {
 LAB_DEV void lat_band_settled_body(Lattice const &lt) {
     Tree_ctl *tc = lt.tc;
     uint32_t const *w = lt.wsum + lt.nslots_global + 2u;
+    tc->lat_settled_band = tc->lat_settled;
     tc->lat_settled = w[0];
     tc->lat_flood_bad = w[2];
     if (w[2] && !tc->lat_err) {

@@ -62,6 +62,7 @@ struct Tree_ctl {
     uint32_t lat_flood_bad;
     uint32_t lat_ticket[4];  // dynamic tile counters: link, local ranking, flood, levels
     unsigned long long lat_settled;
+    unsigned long long lat_settled_band; // row bands: this band's share (lat_settled is the whole maze's after the exchange)
 };
 
 struct Tree {
@@ -1211,7 +1212,7 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
     }
     if (spec_final) {
         ctl->measured = 1u;
-        ctl->n_marked = tc->lat_settled;
+        ctl->n_marked = tr.banded ? tc->lat_settled_band : tc->lat_settled;
     }
     for (uint32_t j = 0; j < ctl->n_targets; j++) {
         ctl->target_val[j] = p.plane[0].dist[ctl->target_cell[j]];

@@ -434,6 +434,7 @@ struct lab_grid {
     Run_desc band_desc{};
     bool band_open = false;
     bool band_mode = false; // the search being prepared is one band of a sharded one
+    bool band_skip_field_reset = false; // ... whose level field the lattice road across bands will write or wipe
     // spanning-tree pipeline workspace (allocated on first use)
     Tree tree{};
     bool tree_alloc = false;
@@ -596,7 +597,7 @@ int search_prepare(lab_grid *h, Run_desc const &d, uint16_t pass_mask, uint16_t 
         CU(cudaMemsetAsync(pl.visited, 0, nt * TS * sizeof(uint64_t), s));
         CU(cudaMemsetAsync(pl.edges, 0xFF, (nt + 2 * static_cast<size_t>(g.tiles_x)) * 4 * TS * sizeof(uint32_t), s));
         CU(cudaMemsetAsync(pl.state, 0, nt * sizeof(uint32_t), s));
-        if (!tree_may_run(h, d)) { // (else the tree pipeline's fix-up or gate writes every square of the field)
+        if (!tree_may_run(h, d) && !(h->band_mode && h->band_skip_field_reset)) { // (else the pipeline's last kernel or the gate writes every square of the field)
             CU(cudaMemsetAsync(pl.dist, 0xFF, cells * sizeof(uint32_t), s));
         }
     }
@@ -1518,8 +1519,12 @@ int lab_bfs_corners(lab_grid *h, const lab_point starts[4], lab_point finish, in
 int lab_band_cols_padded(const lab_grid *h) { return h ? h->g.tiles_x * TS : 0; }
 
 int lab_band_begin(lab_grid *h, int src_r, int src_c) { return lab_band_begin_game(h, GAME_DISTANCE, src_r, src_c); }
+int lab_band_begin_game(lab_grid *h, int game, int src_r, int src_c) { return lab_band_begin_lattice(h, game, src_r, src_c, 0); }
 
-int lab_band_begin_game(lab_grid *h, int game, int src_r, int src_c) {
+// lattice_next != 0: the caller will run the lattice road across bands (lab_band_lat_link .. lab_band_lat_levels) next.  Its
+// last step writes every square of the band's level field, or wipes it if the maze is no lattice tree, so the field is
+// not cleared here; and for the distance map pack sets the measure bits on the way (see measure_body).
+int lab_band_begin_lattice(lab_grid *h, int game, int src_r, int src_c, int lattice_next) {
     Device_guard const guard_(h);
     if (h) {
         h->have_map = false; // (a band's field is not a map lab_distance_paint could colour: its maximum is the band's)
@@ -1544,7 +1549,9 @@ int lab_band_begin_game(lab_grid *h, int game, int src_r, int src_c) {
         d.src_c[0] = src_c;
     }
     d.bound_mode = BOUND_NONE;
+    d.spec_mark = (lattice_next && game == GAME_DISTANCE) ? SQ_MEASURE : 0u;
     h->band_desc = d;
+    h->band_skip_field_reset = lattice_next != 0;
     if (!h->ghost_n) {
         CU(cudaMalloc(&h->ghost_n, static_cast<size_t>(h->g.tiles_x) * sizeof(uint64_t)));
         CU(cudaMalloc(&h->ghost_s, static_cast<size_t>(h->g.tiles_x) * sizeof(uint64_t)));

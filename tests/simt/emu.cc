@@ -279,10 +279,11 @@ int emu_band_cols_padded(void *h) { return static_cast<Emu_band *>(h)->w.g.tiles
 uint32_t *emu_band_levels(void *h) { return static_cast<Emu_band *>(h)->w.dist[0].data(); }
 int emu_band_tree_used(void *h) { return static_cast<int>(static_cast<Emu_band *>(h)->tree_last.used); }
 
-int emu_band_begin_game(void *h, int game, int src_r, int src_c);
+int emu_band_begin_lattice(void *h, int game, int src_r, int src_c, int lattice_next);
+int emu_band_begin_game(void *h, int game, int src_r, int src_c) { return emu_band_begin_lattice(h, game, src_r, src_c, 0); }
 int emu_band_begin(void *h, int src_r, int src_c) { return emu_band_begin_game(h, GAME_DISTANCE, src_r, src_c); }
 
-int emu_band_begin_game(void *h, int game, int src_r, int src_c) {
+int emu_band_begin_lattice(void *h, int game, int src_r, int src_c, int lattice_next) {
     auto *e = static_cast<Emu_band *>(h);
     Workspace &w = e->w;
     Geom const &g = w.g;
@@ -294,13 +295,14 @@ int emu_band_begin_game(void *h, int game, int src_r, int src_c) {
         e->d.src_c[0] = src_c;
     }
     e->d.bound_mode = BOUND_NONE;
+    e->d.spec_mark = (lattice_next && game == GAME_DISTANCE) ? SQ_MEASURE : 0u;
     size_t const nt = static_cast<size_t>(g.ntiles), cells = static_cast<size_t>(g.rows) * g.cols;
     w.path.assign(nt * TS, 0);
     w.cross.assign(nt * 4, 0);
     w.visited[0].assign(nt * TS, 0);
     w.edges[0].assign((nt + 2 * static_cast<size_t>(g.tiles_x)) * 4 * TS, INF);
     w.state[0].assign(nt, 0);
-    w.dist[0].assign(cells, INF);
+    w.dist[0].assign(cells, lattice_next ? 0xABABABABu : INF); // (as lab_band_begin_lattice: the lattice road writes or wipes the field)
     std::memset(&w.ctl, 0, sizeof w.ctl);
     std::memset(&w.res, 0, sizeof w.res);
     size_t cap = 1024;
@@ -311,7 +313,7 @@ int emu_band_begin_game(void *h, int game, int src_r, int src_c) {
     e->tree_last = Tree_ctl{};
     int const nw = e->nwarps;
     uint16_t const mask = game == GAME_DISTANCE ? (SQ_PATH | SQ_MEASURE) : SQ_PATH;
-    simt::launch(nw, [&](int wid, int lane) { pack_body(g, w.grid_ptr, w.path.data(), mask, SQ_PATH, 0, wid, nw, lane); });
+    simt::launch(nw, [&](int wid, int lane) { pack_body(g, w.grid_ptr, w.path.data(), mask, SQ_PATH, static_cast<uint16_t>(e->d.spec_mark), wid, nw, lane); });
     force_sources_body(g, w.path.data(), e->d, w.grid_ptr);
     return 0;
 }

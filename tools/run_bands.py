@@ -12,6 +12,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--builder", default="kruskal"); ap.add_argument("--rows", type=int, default=4095); ap.add_argument("--cols", type=int, default=4095)
 ap.add_argument("--check", action="store_true"); ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--game", default="distance", choices=["distance", "hunt", "gather"])
+ap.add_argument("--super", action="store_true", help="bands of whole super-tile rows (the lattice road across bands)")
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -52,7 +53,7 @@ if a.game != "distance":
         print(f"rank {rank}: band rows [{r0},{r0 + n}) {'OK' if ok else 'MISMATCH'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0)
-r0, n = bands.split_rows(a.rows, world)[rank]
+r0, n = (bands.split_rows_super if a.super else bands.split_rows)(a.rows, world)[rank]
 pristine = torch.from_numpy(maze[r0:r0 + n].view(np.int16).copy()).cuda()
 sq = torch.empty_like(pristine)
 lv = torch.empty((n, a.cols), dtype=torch.int32, device="cuda")
