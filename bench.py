@@ -57,6 +57,8 @@ WORKLOADS = {
                 "north_star headline: BFS distance map AND bfs-gather on a 32767x32767 perfect maze, one GPU (value = distance map, `gather` = bfs-gather)"),
     "c2-distance-kruskal-4095": ("distance", "kruskal", 4095, None, "configs[1]"),
     "c3-gather-arena-16383": ("gather", "arena", 16383, None, "configs[2]"),
+    "c4-corners-grid-cross-32767": ("corners", "grid", 32767, "cross", "configs[3]: bfs-corners with -m cross on a 32767x32767 grid maze, one GPU"),
+    "c5-distance-wilson-65535": ("distance", "wilson", 65535, None, "configs[4]: BFS distance map on a 65535x65535 wilson perfect maze (row bands at N > 1: strong scaling)"),
     "c4-corners-grid-cross-4095": ("corners", "grid", 4095, "cross", "configs[3] at 4095 (host build time)"),
     "h-distance-arena-32767": ("distance", "arena", 32767, None, "north_star headline size, open maze"),
     "h-gather-arena-32767": ("gather", "arena", 32767, None, "north_star headline size, open maze"),
@@ -386,7 +388,7 @@ def ours_bands(args, lab, dist, torch, world, rank, local):
     workload = args.workload
     game, builder, n, mod, stands_for = WORKLOADS[workload]
     t0 = time.time()
-    strong = game == "distance+gather"  # the headline maze itself, cut into `world` bands (a taller one could not be built in minutes)
+    strong = n >= 32767  # the headline maze itself, cut into `world` bands (a taller one could not be built in minutes)
     if rank == 0:  # one rank builds (and caches) the maze, the others read the file
         make_case(lab, workload, bands=1 if strong else world)
     dist.barrier()

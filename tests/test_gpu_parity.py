@@ -116,3 +116,47 @@ def test_errors_are_loud(lab):
     with lab.Grid.empty(9, 9) as g:
         with pytest.raises(lab.LabError):
             g.distance_map(start=(99, 0))
+
+
+# ---- BASELINE.json's configs at their own sizes, bit-exact against the oracle's CPU restatement ----
+def test_config3_gather_arena_16383_bit_exact(lab, O):
+    """configs[2]: bfs-gather (4 thread colours) on a 16383 x 16383 arena -- grid, claims and path lengths."""
+    maze = lab.cached_maze("arena", 16383, 16383, seed=0xB2000002)
+    placed, s, fin = lab.place_gather(maze, seed=0xB2000003)
+    with lab.Grid.from_host(placed) as g:
+        res = g.gather(s, fin, want_paths=False)
+        after = g.download()
+    g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
+    assert (after == g_ref).all(), int((after != g_ref).sum())
+    assert (res.claimed_by == c_ref).all() and res.path_len == [len(p) for p in p_ref]
+
+
+def test_config4_corners_grid_cross_4095_bit_exact(lab, O):
+    """configs[3]'s game and builder (bfs-corners, grid -m cross) at 4095 x 4095: grid, winner, the winner's path."""
+    maze = lab.cached_maze("grid", 4095, 4095, seed=0xB2000002, mod="cross")
+    placed, st, f = lab.place_corners(maze, seed=0xB2000003)
+    with lab.Grid.from_host(placed) as g:
+        res = g.corners(st, f)
+        after = g.download()
+    g_ref, w_ref, p_ref = O.canon_corners(placed, st, f)
+    assert (after == g_ref).all(), int((after != g_ref).sum())
+    assert res.winner == w_ref and _paths_equal(res.paths, [p_ref])
+
+
+def test_config2_gather_and_hunt_kruskal_4095_bit_exact(lab, O):
+    """configs[1]'s maze with the solvers on it (starts on cells and on passages: both take the lattice road)."""
+    maze = lab.cached_maze("kruskal", 4095, 4095, seed=0xB2000002)
+    for k in range(3):
+        placed, s, fin = lab.place_gather(maze, seed=0xB2000003 + k)
+        with lab.Grid.from_host(placed) as g:
+            res = g.gather(s, fin, want_paths=False)
+            after = g.download()
+            assert g.stats()["tree_used"] == 3
+        g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
+        assert (after == g_ref).all() and (res.claimed_by == c_ref).all() and res.path_len == [len(p) for p in p_ref]
+        placed, s, f = lab.place_hunt(maze, seed=0xB2000013 + k)
+        with lab.Grid.from_host(placed) as g:
+            res = g.hunt(s, f)
+            after = g.download()
+        g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
+        assert (after == g_ref).all() and res.winner == w_ref and _paths_equal(res.paths, [p_ref])

@@ -154,3 +154,48 @@ def test_gpu_hunt_and_gather_invariants_at_scale(lab, builder, n):
     for k in range(4):
         j = int(np.nonzero(np.asarray(res.claimed_by) == k)[0][0])
         assert valid_shortest_path(placed, res.paths[k], s, fin[j], int(d[fin[j][0], fin[j][1]]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [8191])
+def test_gpu_corners_invariants_at_scale(lab, n):
+    """bfs-corners (solvers/bfs_threads.cc:420-453) beyond the oracle's sizes, on BASELINE configs[3]'s builder (grid, -m
+    cross): four fields, one per corner start.  With d_k the exact level field from corner k (each proven a BFS field by
+    the equations above, on the device), D = min_k d_k(finish): the winner is the lowest k with d_k(finish) == D, its
+    path a wall-respecting chain of exactly D squares from a neighbour of the finish to its corner, and colour k paints
+    exactly the squares with d_k < D; nothing else of a Square changes (static corners does not repaint the path)."""
+    import torch
+
+    from _util import valid_shortest_path
+
+    maze = lab.build_maze("grid", n, n, seed=0xB2000002, mod="cross")
+    placed, starts, f = lab.place_corners(maze, seed=0xB2000003)
+    fields = []
+    for k in range(4):
+        sq = torch.from_numpy(placed.view(np.int16).copy()).cuda()
+        lv = torch.empty((n, n), dtype=torch.int32, device="cuda")
+        g = lab.Grid.from_device_ptr(n, n, sq.data_ptr(), keepalive=sq)
+        try:
+            g.set_stream(torch.cuda.current_stream().cuda_stream)
+            g.bind_levels(0, lv.data_ptr())
+            res = g.distance_map(tuple(int(x) for x in starts[k]), want_dist=False)
+            torch.cuda.synchronize()
+            reached, mx = check_field(torch, lv, sq, tuple(int(x) for x in starts[k]), lab)
+            assert reached == res.settled and mx == res.max
+            fields.append(lv.cpu().numpy().view(np.uint32))
+        finally:
+            g.close()
+    Dk = [int(d[f[0], f[1]]) for d in fields]
+    D = min(Dk)
+    with lab.Grid.from_host(placed) as g:
+        res = g.corners(starts, f)
+        after = g.download()
+    assert res.winner == Dk.index(D) and res.path_len[0] == D
+    assert valid_shortest_path(placed, res.paths[0], tuple(int(x) for x in starts[res.winner]), f, D)
+    path = np.asarray(res.paths[0]).reshape(-1, 2)
+    assert (fields[res.winner][path[:, 0], path[:, 1]] == np.arange(D - 1, -1, -1)).all()
+    want = np.zeros((n, n), np.uint16)
+    for k in range(4):
+        want |= np.where(fields[k] < D, np.uint16(1 << (4 + k)), np.uint16(0))
+    assert ((after & lab.PAINT_MASK) == want).all()
+    assert ((after & ~np.uint16(lab.PAINT_MASK)) == (placed & ~np.uint16(lab.PAINT_MASK))).all()
