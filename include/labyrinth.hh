@@ -33,6 +33,10 @@
 #include <string_view>
 #include <vector>
 
+#include <optional>
+#include <thread>
+#include <chrono>
+#include <algorithm>
 #include "labyrinth_b200.h"
 
 namespace Speed {
@@ -212,6 +216,27 @@ inline void print_gather_solution_message() {
     for (int k = 0; k < 4; k++) print_color_block(1 << k);
     std::cout << " All threads found their finish squares!\n";
 }
+
+// Printer::set_cursor_position (printers/printers.cc:14-17) and Sutil::flush_cursor_path_coordinate (solve_utilities.cc:216-221)
+inline void set_cursor_position(Maze::Point p) { std::cout << "\033[" << p.row + 1 << ";" << p.col + 1 << "f"; }
+inline void flush_cursor_path_coordinate(Maze::Maze const &maze, Maze::Point p) {
+    set_cursor_position(p);
+    print_point(maze, p);
+    std::cout << std::flush;
+}
+inline constexpr std::array<int, 8> solver_speeds = {0, 20000, 10000, 5000, 2000, 1000, 500, 250}; // solve_utilities.cc:130-131
+inline constexpr int overlap_key_and_message_height = 9;                                           // solve_utilities.cc:129
+inline constexpr std::array<Maze::Point, 7> all_dirs = {{{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {0, -1}}}; // :127-128 (SW is missing upstream)
+// Sutil::deluminate_maze (solve_utilities.cc:227 ff.): the dark solvers start from a blank screen
+inline void deluminate_maze(Maze::Maze const &maze) {
+    for (int r = 0; r < maze.row_size(); r++) {
+        for (int c = 0; c < maze.col_size(); c++) {
+            set_cursor_position({r, c});
+            std::cout << " ";
+        }
+    }
+    std::cout << std::flush;
+}
 } // namespace Sutil
 
 // ------------------------------------------------------------------------------------- builders
@@ -334,48 +359,287 @@ inline void corners(Maze::Maze &maze) {
     std::cout << "\n";
 }
 
-inline void animate_hunt(Maze::Maze &maze, Speed::Speed) { hunt(maze); }
-inline void animate_gather(Maze::Maze &maze, Speed::Speed) { gather(maze); }
-inline void animate_corners(Maze::Maze &maze, Speed::Speed) { corners(maze); }
-
 } // namespace Bfs
 
-// ------------------------------------------------------------------------------------- painters
-namespace Distance {
-
-// painters/distance.cc:129-156: the BFS and the painter's colour arithmetic (distance.cc:45-70) both run on
-// the GPU (lab_distance_map, lab_distance_paint); what is left here is the reference's printing.
-inline void paint_distance_from_center(Maze::Maze &maze) {
-    int const rows = maze.row_size(), cols = maze.col_size();
-    std::vector<uint32_t> pixels;
-    uint64_t max = 0, settled = 0;
-    std::mt19937 rng(Lab::device_seed());
-    std::uniform_int_distribution<int> uid(0, 2);
-    int const choice = uid(rng); // (drawn whether or not anything is printed: the same RNG stream either way)
-    {
-        Lab::Device_maze d(maze);
-        lab_point const s = lab_distance_start(rows, cols);
-        Lab::check(lab_distance_map(d.g, s.row, s.col, nullptr, &max, &settled), "lab_distance_map");
-        if (!Lab::g_quiet) {
-            pixels.resize(static_cast<size_t>(rows) * cols);
-            Lab::check(lab_distance_paint(d.g, choice, pixels.data()), "lab_distance_paint");
+// ---------------------------------------------------------------------- animated solvers: replay
+// The reference's animated variants (solvers/bfs_threads.cc:282-331,371-418,455-514; dark ones: darkbfs_threads.cc:154-300)
+// draw every square the moment a thread paints it and sleep solver_speeds[speed] microseconds per square and thread.  Here
+// the search runs on the GPU first (the same entry points as the static variants: same grid afterwards); the frames are
+// then REPLAYED from its level fields: the painted squares in level order -- the order a lock-step schedule of the
+// reference's four threads reaches them --, each drawn with the colours it carries during the search, then the winner's
+// path square by square (hunt, corners) or the claimed finishes' fronts (gather), as the reference does after its join.
+namespace Lab {
+struct Replay {
+    std::vector<uint32_t> order;  // flat indices of the squares to draw, by the level at which they are painted
+    std::vector<uint16_t> paint;  // the paint bits a square shows while the search runs
+};
+// levels[k]: field of colour k (one shared field: pass it four times); limit[k]: colour k paints levels below limit[k]
+inline Replay make_replay(int rows, int cols, std::array<uint32_t const *, 4> levels, std::array<uint32_t, 4> limit) {
+    size_t const n = static_cast<size_t>(rows) * cols;
+    Replay out;
+    std::vector<std::pair<uint32_t, uint32_t>> keyed; // (first level at which some colour paints it, index)
+    out.paint.assign(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t first = 0xFFFFFFFFu;
+        uint16_t bits = 0;
+        for (int k = 0; k < 4; k++) {
+            uint32_t const d = levels[k][i];
+            if (d != 0xFFFFFFFFu && d < limit[k]) {
+                bits = static_cast<uint16_t>(bits | (1u << (Sutil::thread_paint_shift + k)));
+                first = d < first ? d : first;
+            }
         }
-        d.download();
+        if (bits) {
+            out.paint[i] = bits;
+            keyed.push_back({first, static_cast<uint32_t>(i)});
+        }
     }
-    if (Lab::g_quiet) return;
+    std::stable_sort(keyed.begin(), keyed.end(), [](auto const &a, auto const &b) { return a.first < b.first; });
+    out.order.reserve(keyed.size());
+    for (auto const &k : keyed) out.order.push_back(k.second);
+    return out;
+}
+inline void nap(int microseconds) {
+    if (microseconds > 0) std::this_thread::sleep_for(std::chrono::microseconds(microseconds));
+}
+// Manhattan levels of an open room (the searches of csrc/device/room.cuh write no field)
+inline std::vector<uint32_t> room_levels(Maze::Maze const &maze, lab_point s) {
+    int const rows = maze.row_size(), cols = maze.col_size();
+    std::vector<uint32_t> d(static_cast<size_t>(rows) * cols, 0xFFFFFFFFu);
     for (int r = 0; r < rows; r++) {
         for (int c = 0; c < cols; c++) {
-            std::cout << "\033[" << r + 1 << ";" << c + 1 << "f";
-            uint32_t const px = pixels[static_cast<size_t>(r) * cols + c];
-            if (px >> 24) {
-                std::cout << "\033[38;2;" << (px & 0xFF) << ";" << ((px >> 8) & 0xFF) << ";" << ((px >> 16) & 0xFF) << "m█\033[0m";
-            } else {
-                std::cout << Sutil::wall_styles.at(maze.style_index() * 16 + (maze[r][c].load() & Maze::wall_mask));
+            if (maze[r][c].load() & Maze::path_bit) d[static_cast<size_t>(r) * cols + c] = static_cast<uint32_t>(std::abs(r - s.row) + std::abs(c - s.col));
+        }
+    }
+    d[static_cast<size_t>(s.row) * cols + s.col] = 0;
+    return d;
+}
+inline std::vector<uint32_t> levels_of(lab_grid *g, int plane, Maze::Maze const &maze, lab_point start) {
+    std::vector<uint32_t> d(static_cast<size_t>(maze.row_size()) * maze.col_size());
+    lab_stats st{};
+    lab_last_stats(g, &st);
+    if (st.tree_used == 2) return room_levels(maze, start);
+    check(lab_levels_download(g, plane, d.data()), "lab_levels_download");
+    return d;
+}
+inline void draw_replay(Maze::Maze &shown, Replay const &rp, int step_us) {
+    int const cols = shown.col_size();
+    for (uint32_t i : rp.order) {
+        Maze::Point const p{static_cast<int>(i / static_cast<uint32_t>(cols)), static_cast<int>(i % static_cast<uint32_t>(cols))};
+        shown[p.row][p.col] |= rp.paint[i];
+        Sutil::flush_cursor_path_coordinate(shown, p);
+        nap(step_us);
+    }
+}
+
+inline void animate_hunt(Maze::Maze &maze, Speed::Speed speed, bool dark) {
+    int const rows = maze.row_size(), cols = maze.col_size();
+    int const us = Sutil::solver_speeds.at(static_cast<size_t>(speed));
+    lab_point start{}, finish{};
+    check(lab_place_hunt(rows, cols, maze.squares(), device_seed(), &start, &finish), "Bfs::animate_hunt placement");
+    g_next_seed += g_seeded ? 1 : 0;
+    Maze::Maze shown = maze; // what is on the screen: the placed maze, painted square by square below
+    int32_t winner = -1;
+    uint64_t path_len = 0;
+    std::vector<lab_point> path(static_cast<size_t>(rows) * cols / 2 + 2);
+    std::vector<uint32_t> levels;
+    {
+        Device_maze d(maze);
+        check(lab_bfs_hunt(d.g, start, finish, &winner, path.data(), path.size(), &path_len), "lab_bfs_hunt");
+        levels = levels_of(d.g, 0, maze, start);
+        d.download();
+    }
+    if (g_quiet) return;
+    Sutil::set_cursor_position({rows, 0});
+    Sutil::print_overlap_key();
+    if (dark) Sutil::deluminate_maze(shown);
+    Sutil::flush_cursor_path_coordinate(shown, {finish.row, finish.col});
+    nap(us);
+    uint32_t const D = levels[static_cast<size_t>(finish.row) * cols + finish.col];
+    // four threads share the start: every square closer than the finish carries all four colours while they search
+    draw_replay(shown, make_replay(rows, cols, {levels.data(), levels.data(), levels.data(), levels.data()}, {D, D, D, D}), us / 4);
+    if (winner >= 0) {
+        uint16_t const colour = static_cast<uint16_t>(1u << (Sutil::thread_paint_shift + winner));
+        for (uint64_t k = 0; k < path_len && k < path.size(); k++) {
+            Maze::Point const p{path[k].row, path[k].col};
+            shown[p.row][p.col] &= static_cast<uint16_t>(~Sutil::thread_paint_mask);
+            shown[p.row][p.col] |= colour;
+            Sutil::flush_cursor_path_coordinate(shown, p);
+            nap(us);
+        }
+    }
+    Sutil::set_cursor_position({rows + Sutil::overlap_key_and_message_height, 0});
+    Sutil::print_hunt_solution_message(winner < 0 ? Sutil::no_winner : static_cast<uint16_t>(winner));
+    std::cout << "\n";
+}
+
+inline void animate_gather(Maze::Maze &maze, Speed::Speed speed, bool dark) {
+    int const rows = maze.row_size(), cols = maze.col_size();
+    int const us = Sutil::solver_speeds.at(static_cast<size_t>(speed));
+    lab_point start{}, finishes[4]{};
+    check(lab_place_gather(rows, cols, maze.squares(), device_seed(), &start, finishes), "Bfs::animate_gather placement");
+    g_next_seed += g_seeded ? 4 : 0;
+    Maze::Maze shown = maze;
+    int32_t claimed[4];
+    uint64_t lens[4];
+    std::vector<uint32_t> levels;
+    {
+        Device_maze d(maze);
+        check(lab_bfs_gather(d.g, start, finishes, claimed, nullptr, 0, lens), "lab_bfs_gather");
+        levels = levels_of(d.g, 0, maze, start);
+        d.download();
+    }
+    if (g_quiet) return;
+    Sutil::set_cursor_position({rows, 0});
+    Sutil::print_overlap_key();
+    if (dark) Sutil::deluminate_maze(shown);
+    for (auto const &f : finishes) Sutil::flush_cursor_path_coordinate(shown, {f.row, f.col});
+    // colour k searches until it reaches the finish it claims
+    std::array<uint32_t, 4> limit{0, 0, 0, 0};
+    for (int j = 0; j < 4; j++) {
+        if (claimed[j] >= 0 && claimed[j] < 4) limit[static_cast<size_t>(claimed[j])] = levels[static_cast<size_t>(finishes[j].row) * cols + finishes[j].col];
+    }
+    draw_replay(shown, make_replay(rows, cols, {levels.data(), levels.data(), levels.data(), levels.data()}, limit), us / 4);
+    // what the reference does after the join (bfs_threads.cc:356-364): the final grid's recoloured fronts and claims
+    for (int r = 0; r < rows; r++) {
+        for (int c = 0; c < cols; c++) {
+            if (shown[r][c].load() != maze[r][c].load()) {
+                shown[r][c].store(maze[r][c].load());
+                Sutil::flush_cursor_path_coordinate(shown, {r, c});
             }
         }
     }
+    Sutil::set_cursor_position({rows + Sutil::overlap_key_and_message_height, 0});
+    Sutil::print_gather_solution_message();
+    std::cout << "\n";
+}
+
+inline void animate_corners(Maze::Maze &maze, Speed::Speed speed, bool dark) {
+    int const rows = maze.row_size(), cols = maze.col_size();
+    int const us = Sutil::solver_speeds.at(static_cast<size_t>(speed));
+    lab_point starts[4]{}, finish{};
+    check(lab_place_corners(rows, cols, maze.squares(), device_seed(), starts, &finish), "Bfs::animate_corners placement");
+    for (Maze::Point const &p : Sutil::all_dirs) { // the animated variant carves SEVEN neighbours of the centre (bfs_threads.cc:469-472; the static one four)
+        maze[finish.row + p.row][finish.col + p.col] |= Maze::path_bit;
+    }
+    Maze::Maze shown = maze;
+    int32_t winner = -1;
+    uint64_t path_len = 0;
+    std::vector<lab_point> path(static_cast<size_t>(rows) * cols / 2 + 2);
+    std::array<std::vector<uint32_t>, 4> levels;
+    {
+        Device_maze d(maze);
+        check(lab_bfs_corners(d.g, starts, finish, &winner, path.data(), path.size(), &path_len), "lab_bfs_corners");
+        for (int k = 0; k < 4; k++) levels[static_cast<size_t>(k)] = levels_of(d.g, k, maze, starts[k]);
+        d.download();
+    }
+    if (g_quiet) return;
+    Sutil::set_cursor_position({rows, 0});
+    Sutil::print_overlap_key();
+    if (dark) Sutil::deluminate_maze(shown);
+    Sutil::flush_cursor_path_coordinate(shown, {finish.row, finish.col});
+    uint32_t D = 0xFFFFFFFFu; // the game ends when the first colour is home
+    for (int k = 0; k < 4; k++) D = std::min(D, levels[static_cast<size_t>(k)][static_cast<size_t>(finish.row) * cols + finish.col]);
+    draw_replay(shown, make_replay(rows, cols, {levels[0].data(), levels[1].data(), levels[2].data(), levels[3].data()}, {D, D, D, D}), us / 4);
+    if (winner >= 0) { // (the animated corners repaints the winner's path: bfs_threads.cc:494-507)
+        uint16_t const colour = static_cast<uint16_t>(1u << (Sutil::thread_paint_shift + winner));
+        for (uint64_t k = 0; k < path_len && k < path.size(); k++) {
+            Maze::Point const p{path[k].row, path[k].col};
+            shown[p.row][p.col] &= static_cast<uint16_t>(~Sutil::thread_paint_mask);
+            shown[p.row][p.col] |= colour;
+            Sutil::flush_cursor_path_coordinate(shown, p);
+            nap(us);
+        }
+    }
+    Sutil::set_cursor_position({rows + Sutil::overlap_key_and_message_height, 0});
+    Sutil::print_hunt_solution_message(winner < 0 ? Sutil::no_winner : static_cast<uint16_t>(winner));
+    std::cout << "\n";
+}
+} // namespace Lab
+
+namespace Bfs {
+inline void animate_hunt(Maze::Maze &maze, Speed::Speed speed) { Lab::animate_hunt(maze, speed, false); }
+inline void animate_gather(Maze::Maze &maze, Speed::Speed speed) { Lab::animate_gather(maze, speed, false); }
+inline void animate_corners(Maze::Maze &maze, Speed::Speed speed) { Lab::animate_corners(maze, speed, false); }
+} // namespace Bfs
+
+// solvers/darkbfs_threads.cc:154-300: the same searches drawn on a dark screen (the static slots of run_maze's
+// darkbfs-* entries are Bfs::hunt / gather / corners upstream: run_maze.cc:113-115)
+namespace Dark_bfs {
+inline void animate_hunt(Maze::Maze &maze, Speed::Speed speed) { Lab::animate_hunt(maze, speed, true); }
+inline void animate_gather(Maze::Maze &maze, Speed::Speed speed) { Lab::animate_gather(maze, speed, true); }
+inline void animate_corners(Maze::Maze &maze, Speed::Speed speed) { Lab::animate_corners(maze, speed, true); }
+} // namespace Dark_bfs
+
+// ------------------------------------------------------------------------------------- painters
+namespace Lab {
+inline constexpr std::array<int, 8> painter_speeds = {0, 10000, 5000, 2000, 1000, 500, 250, 50}; // painters/rgb.cc:24-25
+// Rgb::print_rgb / print_wall for one square (painters/rgb.cc:51-66): a pixel of lab_distance_paint / lab_runs_paint or the wall glyph
+inline void print_heat_square(Maze::Maze const &maze, std::vector<uint32_t> const &pixels, int r, int c) {
+    std::cout << "\033[" << r + 1 << ";" << c + 1 << "f";
+    uint32_t const px = pixels[static_cast<size_t>(r) * maze.col_size() + c];
+    if (px >> 24) {
+        std::cout << "\033[38;2;" << (px & 0xFF) << ";" << ((px >> 8) & 0xFF) << ";" << ((px >> 16) & 0xFF) << "m█\033[0m";
+    } else {
+        std::cout << Sutil::wall_styles.at(maze.style_index() * 16 + (maze[r][c].load() & Maze::wall_mask));
+    }
+}
+// BFS and the painter's colour arithmetic on the GPU; `runs`: Runs::paint_runs instead of the distance map; speed: the
+// animated variant (distance.cc:158-204, runs.cc:163 ff.: four threads repaint the map outwards from the start) replayed
+// from the level field -- squares in level order, painter_speeds[speed] / 4 microseconds apart.
+inline void paint_map(Maze::Maze &maze, bool runs, std::optional<Speed::Speed> speed) {
+    int const rows = maze.row_size(), cols = maze.col_size();
+    std::vector<uint32_t> pixels, levels;
+    uint64_t max = 0, settled = 0;
+    std::mt19937 rng(device_seed());
+    std::uniform_int_distribution<int> uid(0, 2);
+    int const choice = uid(rng); // (drawn whether or not anything is printed: the same RNG stream either way)
+    {
+        Device_maze d(maze);
+        lab_point const s = lab_distance_start(rows, cols);
+        if (runs) {
+            check(lab_runs_map(d.g, s.row, s.col, nullptr, &max, &settled), "lab_runs_map");
+        } else {
+            check(lab_distance_map(d.g, s.row, s.col, nullptr, &max, &settled), "lab_distance_map");
+        }
+        if (!g_quiet) {
+            pixels.resize(static_cast<size_t>(rows) * cols);
+            check(runs ? lab_runs_paint(d.g, choice, pixels.data()) : lab_distance_paint(d.g, choice, pixels.data()), "painter");
+            if (speed) levels = levels_of(d.g, 0, maze, s);
+        }
+        d.download();
+    }
+    if (g_quiet) return;
+    if (!speed) {
+        for (int r = 0; r < rows; r++) {
+            for (int c = 0; c < cols; c++) print_heat_square(maze, pixels, r, c);
+        }
+    } else {
+        std::vector<std::pair<uint32_t, uint32_t>> keyed;
+        for (size_t i = 0; i < levels.size(); i++) {
+            if (levels[i] != 0xFFFFFFFFu) keyed.push_back({levels[i], static_cast<uint32_t>(i)});
+        }
+        std::stable_sort(keyed.begin(), keyed.end(), [](auto const &a, auto const &b) { return a.first < b.first; });
+        int const us = painter_speeds.at(static_cast<size_t>(*speed));
+        for (auto const &k : keyed) {
+            print_heat_square(maze, pixels, static_cast<int>(k.second / static_cast<uint32_t>(cols)), static_cast<int>(k.second % static_cast<uint32_t>(cols)));
+            std::cout << std::flush;
+            nap(us / 4);
+        }
+        Sutil::set_cursor_position({rows, 0});
+    }
     std::cout << "\n\n";
 }
-inline void animate_distance_from_center(Maze::Maze &maze, Speed::Speed) { paint_distance_from_center(maze); }
+} // namespace Lab
 
+namespace Distance {
+// painters/distance.cc:129-156 / :158-204
+inline void paint_distance_from_center(Maze::Maze &maze) { Lab::paint_map(maze, false, std::nullopt); }
+inline void animate_distance_from_center(Maze::Maze &maze, Speed::Speed speed) { Lab::paint_map(maze, false, speed); }
 } // namespace Distance
+
+namespace Runs {
+// painters/runs.cc:130-161 / :163 ff. -- on the GPU for mazes that are one tree (every builder without -m; lab_runs_map)
+inline void paint_runs(Maze::Maze &maze) { Lab::paint_map(maze, true, std::nullopt); }
+inline void animate_runs(Maze::Maze &maze, Speed::Speed speed) { Lab::paint_map(maze, true, speed); }
+} // namespace Runs

@@ -115,6 +115,11 @@ lab_point lab_distance_start(int rows, int cols);
  * beyond the end of the game at LAB_INF; in an open room -- csrc/device/room.cuh -- no field is written). */
 void *lab_levels_device(lab_grid *g, int plane);
 /* Use caller-owned device memory (rows*cols uint32) as plane k's level field from now on. */
+/* The level field the last search left in `plane` (hunt, gather, distance: plane 0 from the shared start; corners: plane k
+ * from corner k), copied to the host: rows*cols uint32, 0xFFFFFFFF = no level.  The animated variants of the reference
+ * (bfs_threads.cc:282-331,371-418,455-514; darkbfs_threads.cc:154-300; distance.cc:158-204) are replayed from it.
+ * LAB_ERR_ARG after a search that took the open-room road (no field is written there: levels are |dr| + |dc|). */
+int lab_levels_download(lab_grid *g, int plane, uint32_t *levels_host);
 int lab_levels_bind(lab_grid *g, int plane, void *device_levels);
 
 /* ---- Distance painter (painters/distance.cc:45-70, `painter`) -------------------------------- */
@@ -126,6 +131,15 @@ int lab_levels_bind(lab_grid *g, int plane, void *device_levels);
  * (no map entry).  pixels_host: NULL or rows*cols uint32 (copied D2H).  The pixels stay resident
  * (lab_pixels_device); lab_pixels_bind makes the painter write into caller-owned device memory. */
 int lab_distance_paint(lab_grid *g, int channel, uint32_t *pixels_host);
+
+/* Runs::paint_runs (painters/runs.cc:130-161) -- SURVEY.md 8(f) rank 2.  The same search as the distance map (start, FIFO
+ * order N,E,S,W, measure bit on every reached square); the map holds for every reached square the length of the straight
+ * run its tree path ends with: 0 at the start, `turn ? 1 : parent's + 1` (:148-151).  runs_host (may be NULL):
+ * rows*cols uint32, 0xFFFFFFFF = no entry.  On the GPU for mazes that are ONE TREE (all perfect mazes; the parent of a
+ * square is then its one neighbour a level lower); LAB_ERR_ARG for a maze with loops, where the reference's parent
+ * depends on its queue order.  lab_runs_paint: the painter's colours (:45-70), as lab_distance_paint. */
+int lab_runs_map(lab_grid *g, int start_row, int start_col, uint32_t *runs_host, uint64_t *max_out, uint64_t *settled_out);
+int lab_runs_paint(lab_grid *g, int channel, uint32_t *pixels_host);
 void *lab_pixels_device(lab_grid *g);
 int lab_pixels_bind(lab_grid *g, void *device_pixels);
 

@@ -30,8 +30,8 @@ PAINT_MASK, CACHE_MASK, MEASURE_BIT = 0x00F0, 0x0F00, 0x0200
 ABI_SYMBOLS = (
     "lab_grid_create", "lab_grid_create_on_device", "lab_grid_upload", "lab_grid_download", "lab_grid_destroy",
     "lab_grid_set_stream", "lab_grid_device_squares", "lab_grid_rows", "lab_grid_cols", "lab_grid_or_bits",
-    "lab_grid_and_bits", "lab_distance_map", "lab_distance_start", "lab_levels_device", "lab_levels_bind",
-    "lab_distance_paint", "lab_pixels_device", "lab_pixels_bind",
+    "lab_grid_and_bits", "lab_distance_map", "lab_distance_start", "lab_levels_device", "lab_levels_bind", "lab_levels_download",
+    "lab_distance_paint", "lab_pixels_device", "lab_pixels_bind", "lab_runs_map", "lab_runs_paint",
     "lab_bfs_hunt", "lab_bfs_gather", "lab_bfs_corners", "lab_last_painted", "lab_last_timing", "lab_last_stats",
     "lab_last_error", "lab_pick_random_point", "lab_set_corner_starts", "lab_place_hunt", "lab_place_gather",
     "lab_place_corners", "lab_build_maze", "lab_device_info", "lab_maze_write", "lab_maze_header", "lab_maze_read",
@@ -105,6 +105,8 @@ def lib():
         L.lab_levels_device.argtypes = [c_void_p, c_int]
         L.lab_levels_bind.argtypes = [c_void_p, c_int, c_void_p]
         L.lab_distance_paint.argtypes = [c_void_p, c_int, c_void_p]
+        L.lab_runs_map.argtypes = [c_void_p, c_int, c_int, c_void_p, POINTER(c_uint64), POINTER(c_uint64)]
+        L.lab_runs_paint.argtypes = [c_void_p, c_int, c_void_p]
         L.lab_pixels_device.argtypes = [c_void_p]
         L.lab_pixels_bind.argtypes = [c_void_p, c_void_p]
         L.lab_bfs_hunt.argtypes = [c_void_p, Point, Point, POINTER(c_int32), c_void_p, c_uint64, POINTER(c_uint64)]
@@ -373,6 +375,19 @@ class Grid:
             px = np.empty((self.rows, self.cols), np.uint32)
             ptr = _np_ptr(px)
         _check(lib().lab_distance_paint(self._h, channel, ptr))
+        return px
+
+    # -- Runs::paint_runs (painters/runs.cc:130-161): straight-run lengths along the search's tree paths (one tree only)
+    def runs_map(self, start: Optional[tuple] = None, want_runs: bool = True) -> DistanceResult:
+        sr, sc = start if start is not None else distance_start(self.rows, self.cols)
+        mx, st = c_uint64(), c_uint64()
+        runs = np.empty((self.rows, self.cols), np.uint32) if want_runs else None
+        _check(lib().lab_runs_map(self._h, sr, sc, _np_ptr(runs) if want_runs else None, byref(mx), byref(st)))
+        return DistanceResult(mx.value, st.value, runs)
+
+    def paint_runs(self, channel: int) -> np.ndarray:
+        px = np.empty((self.rows, self.cols), np.uint32)
+        _check(lib().lab_runs_paint(self._h, channel, _np_ptr(px)))
         return px
 
     def pixels_device(self) -> int:

@@ -1,6 +1,5 @@
-// measure -- the reference's painter CLI (measure/measure.cc) with "-p distance" dispatched to the
-// B200 library.  Flags are the reference's: -r -c -b -m -p -d -pa -ba -h ("runs" is the next row of
-// SURVEY.md §8(f) and not built yet: an argument error here).
+// measure -- the reference's painter CLI (measure/measure.cc) with "-p distance" and "-p runs" dispatched to the
+// B200 library.  Flags are the reference's: -r -c -b -m -p -d -pa -ba -h.
 #include "cli_common.hh"
 
 namespace {
@@ -10,9 +9,9 @@ void print_usage() {
                  "  -r rows   -c cols          odd sizes >= 7 (even values are bumped by one)\n"
                  "  -b rdfs|wilson|kruskal|grid|arena\n"
                  "  -m cross|x                 builder modification\n"
-                 "  -p distance                painter\n"
+                 "  -p distance|runs           painter (runs: perfect mazes, i.e. builders without -m)\n"
                  "  -d sharp|round|doubles|bold|contrast|spikes\n"
-                 "  -pa 0-7  -ba 0-7           animation speeds (this drop-in draws the finished frame)\n"
+                 "  -pa 0-7  -ba 0-7           animation speeds (frames replayed from the GPU search's level field)\n"
                  "  -h                         this message\n"
                  "  environment: LAB_SEED=n reproducible run, LAB_QUIET=1 no rendering, LAB_TIMING=1 device timings\n";
 }
@@ -25,6 +24,7 @@ int main(int argc, char **argv) {
     auto const styles = cli::style_table();
     std::unordered_map<std::string, cli::Call_function> const painters = {
         {"distance", {Distance::paint_distance_from_center, Distance::animate_distance_from_center}},
+        {"runs", {Runs::paint_runs, Runs::animate_runs}},
     };
     std::unordered_set<std::string> const flags = {"-r", "-c", "-b", "-p", "-h", "-d", "-m", "-pa", "-ba"};
     Maze::Maze_args margs;

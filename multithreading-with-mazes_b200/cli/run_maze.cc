@@ -14,7 +14,7 @@ void print_usage() {
                  "  -m cross|x                 builder modification\n"
                  "  -s bfs-hunt|bfs-gather|bfs-corners|darkbfs-hunt|darkbfs-gather|darkbfs-corners\n"
                  "  -d sharp|round|doubles|bold|contrast|spikes\n"
-                 "  -sa 0-7  -ba 0-7           animation speeds (this drop-in draws the finished frame)\n"
+                 "  -sa 0-7  -ba 0-7           animation speeds (frames replayed from the GPU search's level fields)\n"
                  "  -h                         this message\n"
                  "  environment: LAB_SEED=n reproducible run, LAB_QUIET=1 no rendering\n";
 }
@@ -39,9 +39,9 @@ int main(int argc, char **argv) {
         {"bfs-gather", {Bfs::gather, Bfs::animate_gather}},
         {"bfs-corners", {Bfs::corners, Bfs::animate_corners}},
         // run_maze.cc:113-115: the static slots of the dark variants are the plain Bfs functions
-        {"darkbfs-hunt", {Bfs::hunt, Bfs::animate_hunt}},
-        {"darkbfs-gather", {Bfs::gather, Bfs::animate_gather}},
-        {"darkbfs-corners", {Bfs::corners, Bfs::animate_corners}},
+        {"darkbfs-hunt", {Bfs::hunt, Dark_bfs::animate_hunt}},
+        {"darkbfs-gather", {Bfs::gather, Dark_bfs::animate_gather}},
+        {"darkbfs-corners", {Bfs::corners, Dark_bfs::animate_corners}},
     };
     std::unordered_set<std::string> const flags = {"-r", "-c", "-b", "-s", "-h", "-g", "-d", "-m", "-sa", "-ba"};
     Maze_runner runner;

@@ -276,63 +276,55 @@ LAB_DEV void paint_body(Params p, uint16_t *grid, Result *res, long long gthread
     }
     uint32_t painted = 0;
     bool const same_plane = nr <= 1 || (r[0].plane == r[1].plane && r[0].plane == r[2].plane && r[0].plane == r[3].plane);
-    // One field (hunt, gather), both arrays on 16-byte boundaries: eight squares per thread and step -- two 16-byte
-    // loads of levels, one 16-byte read-modify-write of Squares -- and a group whose levels are all at or beyond the
-    // largest threshold is not touched at all.
-    if (same_plane && nr >= 1 && (reinterpret_cast<uintptr_t>(grid) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p.plane[r[0].plane].dist) & 15u) == 0) {
-        uint32_t const *d = p.plane[r[0].plane].dist;
-        uint32_t top = 0;
-        for (uint32_t k = 0; k < nr; k++) {
-            top = r[k].below > top ? r[k].below : top;
-        }
+    // All arrays on 16-byte boundaries: eight squares per thread and step -- per field two 16-byte loads of levels (one field
+    // for hunt and gather, one per colour for corners), one 16-byte read-modify-write of Squares -- and a group whose levels
+    // are all at or beyond the thresholds is not touched at all.
+    bool vec_ok = nr >= 1 && (reinterpret_cast<uintptr_t>(grid) & 15u) == 0;
+    for (uint32_t k = 0; k < nr; k++) {
+        vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(p.plane[r[k].plane].dist) & 15u) == 0;
+    }
+    if (vec_ok) {
+        uint32_t const nfields = same_plane ? 1u : nr; // (same_plane: every rule looks at field r[0].plane)
         long long const groups = n / 8;
-        constexpr int V = 2;
-        for (long long g0 = gthread; g0 < groups; g0 += nthreads * V) {
-            lab_u32x4 a[V], b[V];
-            bool any[V];
-#pragma unroll
-            for (int u = 0; u < V; u++) {
-                long long const gi = g0 + u * nthreads;
-                if (gi < groups) {
-                    a[u] = lab_ld_stream_v4(d + gi * 8);
-                    b[u] = lab_ld_stream_v4(d + gi * 8 + 4);
-                } else {
-                    a[u] = b[u] = lab_u32x4{INF, INF, INF, INF};
-                }
-                uint32_t const lo = lab_umin(lab_umin(lab_umin(a[u].x, a[u].y), lab_umin(a[u].z, a[u].w)), lab_umin(lab_umin(b[u].x, b[u].y), lab_umin(b[u].z, b[u].w)));
-                any[u] = lo < top;
+        for (long long gi = gthread; gi < groups; gi += nthreads) {
+            uint32_t bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            lab_u32x4 a[4], b[4];
+            for (uint32_t f = 0; f < nfields; f++) { // (all the loads first: independent)
+                uint32_t const *d = p.plane[r[f].plane].dist;
+                a[f] = lab_ld_stream_v4(d + gi * 8);
+                b[f] = lab_ld_stream_v4(d + gi * 8 + 4);
             }
+            for (uint32_t f = 0; f < nfields; f++) {
+                uint32_t const lv[8] = {a[f].x, a[f].y, a[f].z, a[f].w, b[f].x, b[f].y, b[f].z, b[f].w};
+                for (uint32_t k = same_plane ? 0u : f; k < (same_plane ? nr : f + 1u); k++) {
 #pragma unroll
-            for (int u = 0; u < V; u++) {
-                if (!any[u]) {
-                    continue;
-                }
-                long long const gi = g0 + u * nthreads;
-                uint32_t const lv[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
-                uint32_t bits[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    bits[q] = 0;
-                    for (uint32_t k = 0; k < nr; k++) {
+                    for (int q = 0; q < 8; q++) {
                         bits[q] |= lv[q] < r[k].below ? r[k].bits : 0u;
                     }
-                    painted += bits[q] ? 1u : 0u;
                 }
-                lab_u32x4 sq = lab_ld_stream_v4(grid + gi * 8);
-                sq.x |= bits[0] | (bits[1] << 16);
-                sq.y |= bits[2] | (bits[3] << 16);
-                sq.z |= bits[4] | (bits[5] << 16);
-                sq.w |= bits[6] | (bits[7] << 16);
-                lab_st_v4(grid + gi * 8, sq);
             }
+            uint32_t const any = bits[0] | bits[1] | bits[2] | bits[3] | bits[4] | bits[5] | bits[6] | bits[7];
+            if (!any) {
+                continue;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                painted += bits[q] ? 1u : 0u;
+            }
+            lab_u32x4 sq = lab_ld_stream_v4(grid + gi * 8);
+            sq.x |= bits[0] | (bits[1] << 16);
+            sq.y |= bits[2] | (bits[3] << 16);
+            sq.z |= bits[4] | (bits[5] << 16);
+            sq.w |= bits[6] | (bits[7] << 16);
+            lab_st_v4(grid + gi * 8, sq);
         }
         for (long long i = groups * 8 + gthread; i < n; i += nthreads) { // the last few squares
-            uint32_t bits = 0;
+            uint32_t bits1 = 0;
             for (uint32_t k = 0; k < nr; k++) {
-                bits |= d[i] < r[k].below ? r[k].bits : 0u;
+                bits1 |= p.plane[r[k].plane].dist[i] < r[k].below ? r[k].bits : 0u;
             }
-            if (bits) {
-                grid[i] |= static_cast<uint16_t>(bits);
+            if (bits1) {
+                grid[i] |= static_cast<uint16_t>(bits1);
                 painted++;
             }
         }
@@ -685,6 +677,55 @@ LAB_DEV void heatmap_body(Geom g, uint32_t const *dist, Result const *res, int c
     }
     for (unsigned long long i = nvec * 4 + static_cast<unsigned long long>(gthread); i < n; i += stride) {
         pixels[i] = heat_pixel(dist[i], max, dmax, channel);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Runs::paint_runs (painters/runs.cc:130-161): the length of the straight run the search's tree path ends with at
+// every square -- `len = turn ? 1 : len(parent) + 1`, 0 at the start (:148-151).  On ONE TREE (every perfect maze) the
+// FIFO search's parent of a square is simply its one neighbour a level lower, so the runs follow from the level field:
+// walk back from the square while the parent lies in the same direction.  Runs in mazes are a few squares long, the
+// walk is a handful of loads.  (A maze with loops needs the FIFO order among equal levels to name a parent: not here.)
+// runs[i] = INF where the map has no entry; *max_out = the longest run.  One thread per square.
+LAB_DEV void runs_body(Geom g, uint32_t const *dist, uint32_t *runs, uint32_t *max_out, long long gthread, long long nthreads) {
+    long long const n = static_cast<long long>(g.rows) * g.cols;
+    long long const step[4] = {-static_cast<long long>(g.cols), 1, static_cast<long long>(g.cols), -1}; // N, E, S, W (maze.cc:213-218)
+    uint32_t mx = 0;
+    for (long long i = gthread; i < n; i += nthreads) {
+        uint32_t const d = dist[i];
+        uint32_t len = INF;
+        if (d == 0u) {
+            len = 0u;
+        } else if (d != INF) {
+            long long const r = i / g.cols, c = i % g.cols;
+            int dir = -1;
+            for (int k = 0; k < 4 && dir < 0; k++) {
+                bool const inside = k == 0 ? r > 0 : (k == 1 ? c + 1 < g.cols : (k == 2 ? r + 1 < g.rows : c > 0));
+                if (inside && dist[i + step[k]] == d - 1u) {
+                    dir = k;
+                }
+            }
+            len = 1u;
+            if (dir >= 0) {
+                long long p = i + step[dir]; // the parent; its own parent in the same direction continues the run
+                long long pr = r + (dir == 0 ? -1 : (dir == 2 ? 1 : 0)), pc = c + (dir == 1 ? 1 : (dir == 3 ? -1 : 0));
+                for (uint32_t dp = d - 1u; dp > 0u; dp--) {
+                    pr += dir == 0 ? -1 : (dir == 2 ? 1 : 0);
+                    pc += dir == 1 ? 1 : (dir == 3 ? -1 : 0);
+                    if (pr < 0 || pr >= g.rows || pc < 0 || pc >= g.cols || dist[p + step[dir]] != dp - 1u) {
+                        break;
+                    }
+                    p += step[dir];
+                    len++;
+                }
+            }
+            mx = len > mx ? len : mx;
+        }
+        runs[i] = len;
+    }
+    mx = lab_reduce_max(mx);
+    if ((gthread & 31) == 0 && mx) {
+        lab_atomic_max(max_out, mx);
     }
 }
 

@@ -261,6 +261,11 @@ __global__ void __launch_bounds__(256) k_heatmap(Geom g, uint32_t const *dist, R
                  static_cast<long long>(gridDim.x) * blockDim.x);
 }
 
+__global__ void __launch_bounds__(256) k_runs(Geom g, uint32_t const *dist, uint32_t *runs, Result *res) {
+    // (max_level is a 64-bit field holding a value below 2^32: its low word is what atomicMax sees)
+    runs_body(g, dist, runs, reinterpret_cast<uint32_t *>(&res->max_level), static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+              static_cast<long long>(gridDim.x) * blockDim.x);
+}
 __global__ void k_resolve(Params p, Run_desc d, Result *res, int32_t const *finish_rc) {
     resolve_body(p, d, res, finish_rc);
 }
@@ -417,6 +422,9 @@ struct lab_grid {
     uint32_t *pixels = nullptr; // heat map of the last distance map (lab_distance_paint), rows*cols
     bool owns_pixels = false;
     bool have_map = false;      // plane 0 holds a finished distance map
+    uint32_t *runs = nullptr;   // Runs::paint_runs: run lengths of the last lab_runs_map, rows*cols
+    Result *runs_res = nullptr; // ... and their maximum (max_level), where k_heatmap looks for it
+    bool have_runs = false;
     int32_t *d_cells = nullptr; // scratch for or_bits
     uint16_t *d_bits = nullptr;
     cudaStream_t stream = nullptr;
@@ -1108,6 +1116,8 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->d_paths);
     cudaFree(h->band_tree.tc);
     cudaFree(h->band_lat_tc);
+    cudaFree(h->runs);
+    cudaFree(h->runs_res);
     if (h->owns_pixels) {
         cudaFree(h->pixels);
     }
@@ -1232,6 +1242,21 @@ void *lab_levels_device(lab_grid *h, int plane) {
     return (h && plane >= 0 && plane < MAX_PLANES) ? h->plane[plane].dist : nullptr;
 }
 
+// The level field of the last search's plane, copied to the host (what the animated variants replay their frames from).
+// An open room (csrc/device/room.cuh) never materialises its field: LAB_ERR_ARG, the levels are Manhattan distances.
+int lab_levels_download(lab_grid *h, int plane, uint32_t *levels_host) {
+    Device_guard const guard_(h);
+    if (!h || plane < 0 || plane >= MAX_PLANES || !levels_host || !h->plane[plane].dist) {
+        return fail(LAB_ERR_ARG, "lab_levels_download: bad argument, or no such field");
+    }
+    if (h->tree_last.used == 2u) {
+        return fail(LAB_ERR_ARG, "lab_levels_download: the last search was an open room (levels are Manhattan distances from the start; no field was written)");
+    }
+    CU(cudaMemcpyAsync(levels_host, h->plane[plane].dist, static_cast<size_t>(h->g.rows) * h->g.cols * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LAB_OK;
+}
+
 int lab_levels_bind(lab_grid *h, int plane, void *device_levels) {
     Device_guard const guard_(h);
     if (!h || plane < 0 || plane >= MAX_PLANES || !device_levels) {
@@ -1321,6 +1346,73 @@ int lab_distance_paint(lab_grid *h, int channel, uint32_t *pixels_host) {
     }
     cudaStream_t s = h->stream;
     k_heatmap<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->res, channel, h->pixels);
+    TRACE("k_heatmap", s);
+    CU(cudaGetLastError());
+    if (pixels_host) {
+        CU(cudaMemcpyAsync(pixels_host, h->pixels, bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    return LAB_OK;
+}
+
+// Runs::paint_runs (painters/runs.cc:130-161): the search is the distance map's (same start, same measure bits: :139,152);
+// the run lengths follow from its level field on one tree.
+int lab_runs_map(lab_grid *h, int sr, int sc, uint32_t *runs_host, uint64_t *max_out, uint64_t *settled_out) {
+    Device_guard const guard_(h);
+    if (!h) {
+        return fail(LAB_ERR_ARG, "null grid");
+    }
+    h->have_runs = false;
+    uint64_t settled = 0;
+    int rc = lab_distance_map(h, sr, sc, nullptr, nullptr, &settled);
+    if (rc) {
+        return rc;
+    }
+    if (h->tree_last.used != 1u && h->tree_last.used != 3u) {
+        return fail(LAB_ERR_ARG, "lab_runs_map: the maze is not one tree (the run of a square needs its parent in the reference's FIFO search, "
+                                 "which only a tree's level field names)");
+    }
+    size_t const cells = static_cast<size_t>(h->g.rows) * h->g.cols;
+    if (!h->runs) {
+        CU(cudaMalloc(&h->runs, cells * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->runs_res, sizeof(Result)));
+    }
+    cudaStream_t s = h->stream;
+    CU(cudaMemsetAsync(h->runs_res, 0, sizeof(Result), s));
+    k_runs<<<grid_blocks(h), 256, 0, s>>>(h->g, h->plane[0].dist, h->runs, h->runs_res);
+    TRACE("k_runs", s);
+    CU(cudaGetLastError());
+    Result r{};
+    CU(cudaMemcpyAsync(&r, h->runs_res, sizeof r, cudaMemcpyDeviceToHost, s));
+    if (runs_host) {
+        CU(cudaMemcpyAsync(runs_host, h->runs, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    h->have_runs = true;
+    if (max_out) *max_out = r.max_level;
+    if (settled_out) *settled_out = settled;
+    return LAB_OK;
+}
+
+// The runs painter's colours (painters/runs.cc:45-70: the distance painter's arithmetic on run lengths).
+int lab_runs_paint(lab_grid *h, int channel, uint32_t *pixels_host) {
+    Device_guard const guard_(h);
+    if (!h) {
+        return fail(LAB_ERR_ARG, "null grid");
+    }
+    if (channel < 0 || channel > 2) {
+        return fail(LAB_ERR_ARG, "colour channel %d (0 red, 1 green, 2 blue)", channel);
+    }
+    if (!h->have_runs) {
+        return fail(LAB_ERR_ARG, "no run map to paint: call lab_runs_map first");
+    }
+    size_t const bytes = static_cast<size_t>(h->g.rows) * h->g.cols * sizeof(uint32_t);
+    if (!h->pixels) {
+        CU(cudaMalloc(&h->pixels, bytes));
+        h->owns_pixels = true;
+    }
+    cudaStream_t s = h->stream;
+    k_heatmap<<<grid_blocks(h), 256, 0, s>>>(h->g, h->runs, h->runs_res, channel, h->pixels);
     TRACE("k_heatmap", s);
     CU(cudaGetLastError());
     if (pixels_host) {

@@ -94,6 +94,40 @@ def ref_bfs():
     return _REF_BFS
 
 
+_REF_RUNS = None
+
+
+def ref_runs_lib():
+    global _REF_RUNS
+    if _REF_RUNS is None:
+        _REF_RUNS = _load(os.path.join(HERE, "_ref", "libref_runs.so"))
+    return _REF_RUNS
+
+
+def have_ref_runs() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_runs.so"))
+
+
+def ref_runs(grid: np.ndarray, seed: int = 0):
+    """The real Runs::paint_runs (painters/runs.cc:130-161) -> (grid_after, runs u64 (2^64-1 = absent), max)"""
+    rows, cols = grid.shape
+    g = np.ascontiguousarray(grid, np.uint16).copy()
+    r = np.zeros((rows, cols), np.uint64)
+    mx = c_uint64()
+    ref_runs_lib().ref_runs(c_int(rows), c_int(cols), _p(g), c_uint(seed), _p(r), byref(mx))
+    return g, r, mx.value
+
+
+def runs_map(grid: np.ndarray):
+    """painters/runs.cc:130-161 restated -> (grid_after, runs u32 (INF = absent), max, settled)"""
+    rows, cols = grid.shape
+    g = np.ascontiguousarray(grid, np.uint16).copy()
+    r = np.zeros((rows, cols), np.uint32)
+    mx, st = c_uint64(), c_uint64()
+    orc().orc_runs_map(c_int(rows), c_int(cols), _p(g), _p(r), byref(mx), byref(st))
+    return g, r, mx.value, st.value
+
+
 def ref_dist():
     global _REF_DIST
     if _REF_DIST is None:

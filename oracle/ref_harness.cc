@@ -58,10 +58,24 @@ template <class Map> static void oracle_capture_distance_map(uint64_t max, Map c
     }
 }
 #include "_ref/unity_dist.inc"
+#elif defined(REF_FAMILY_RUNS)
+namespace Maze { struct Point; }
+// filled by the capture hook the Makefile puts in front of runs.cc:158 `painter(maze, map);`
+static uint64_t g_captured_max = 0;
+static std::vector<std::pair<std::pair<int, int>, uint64_t>> g_captured;
+template <class Map> static void oracle_capture_run_map(uint64_t max, Map const &m) {
+    g_captured_max = max;
+    g_captured.clear();
+    g_captured.reserve(m.size());
+    for (auto const &kv : m) {
+        g_captured.push_back({{kv.first.row, kv.first.col}, kv.second});
+    }
+}
+#include "_ref/unity_runs.inc"
 #elif defined(REF_FAMILY_BFS)
 #include "_ref/unity_bfs.inc"
 #else
-#error "define REF_FAMILY_BFS or REF_FAMILY_DIST"
+#error "define REF_FAMILY_BFS, REF_FAMILY_DIST or REF_FAMILY_RUNS"
 #endif
 #undef random_device
 
@@ -220,6 +234,28 @@ int ref_distance(int rows, int cols, uint16_t *grid, unsigned seed, uint64_t *di
 }
 
 #endif // REF_FAMILY_DIST
+
+#if defined(REF_FAMILY_RUNS)
+// Runs the reference's Runs::paint_runs (painters/runs.cc:130-161) on the given squares.  grid is updated in place
+// (measure bit 9 on reached squares).  runs_out[r*cols+c] = captured map value, UINT64_MAX where the map has no entry.
+int ref_runs(int rows, int cols, uint16_t *grid, unsigned seed, uint64_t *runs_out, uint64_t *max_out) {
+    Null_buf nb;
+    {
+        Cout_redirect quiet(&nb);
+        ref_seed(seed);
+        Maze::Maze maze = make_maze(rows, cols, grid);
+        Runs::paint_runs(maze);
+        read_back(maze, grid);
+    }
+    size_t const n = static_cast<size_t>(rows) * cols;
+    std::fill(runs_out, runs_out + n, UINT64_MAX);
+    for (auto const &e : g_captured) {
+        runs_out[static_cast<size_t>(e.first.first) * cols + e.first.second] = e.second;
+    }
+    *max_out = g_captured_max;
+    return 0;
+}
+#endif // REF_FAMILY_RUNS
 
 #if defined(REF_FAMILY_BFS)
 

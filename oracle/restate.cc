@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <vector>
@@ -308,6 +309,48 @@ int orc_distance_map(int rows, int cols, uint16_t *grid, uint32_t *dist, uint64_
             dist[g.idx(nr, nc)] = d + 1;
             settled++;
             q.push_back(static_cast<int64_t>(g.idx(nr, nc)));
+        }
+    }
+    *max_out = max;
+    *settled_out = settled;
+    return 0;
+}
+
+// painters/runs.cc:130-161 (the BFS of Runs::paint_runs; its painter is orc_painter_rgb with runs for levels: :45-70).
+// runs[r*cols+c] = length of the straight run the FIFO search's tree path ends with at that square (0 at the start),
+// INF where the map has no entry.  grid gets Rgb::measure on reached squares.  Any maze (FIFO order, N,E,S,W).
+int orc_runs_map(int rows, int cols, uint16_t *grid, uint32_t *runs, uint64_t *max_out, uint64_t *settled_out) {
+    Grid const g{rows, cols, grid};
+    int const row_mid = rows / 2;
+    int const col_mid = cols / 2;
+    Point const start = {row_mid + 1 - (row_mid % 2), col_mid + 1 - (col_mid % 2)};
+    std::fill(runs, runs + static_cast<size_t>(rows) * cols, INF);
+    struct Run_point { // runs.cc:39-43
+        uint32_t len;
+        int64_t prev, cur;
+    };
+    uint64_t max = 0, settled = 1;
+    int64_t const s0 = static_cast<int64_t>(g.idx(start.row, start.col));
+    runs[s0] = 0; // Run_map map(start, 0)  :136
+    std::vector<Run_point> q;
+    q.push_back({0, s0, s0});
+    g.at(start.row, start.col) |= measure_bit;
+    for (size_t head = 0; head < q.size(); head++) {
+        Run_point const cur = q[head];
+        int const r = static_cast<int>(cur.cur / cols), c = static_cast<int>(cur.cur % cols);
+        int const pr = static_cast<int>(cur.prev / cols), pc = static_cast<int>(cur.prev % cols);
+        max = std::max<uint64_t>(max, cur.len);
+        for (Point const &p : dirs) {
+            int const nr = r + p.row, nc = c + p.col;
+            uint16_t const sq = g.at(nr, nc);
+            if (!(sq & path_bit) || (sq & measure_bit)) {
+                continue;
+            }
+            uint32_t const len = std::abs(nr - pr) == std::abs(nc - pc) ? 1u : cur.len + 1u; // a turn starts a new run  :148-151
+            g.at(nr, nc) |= measure_bit;
+            runs[g.idx(nr, nc)] = len;
+            settled++;
+            q.push_back({len, cur.cur, static_cast<int64_t>(g.idx(nr, nc))});
         }
     }
     *max_out = max;

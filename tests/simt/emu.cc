@@ -187,6 +187,16 @@ void stats_out(Workspace const &w, uint64_t *st) {
 
 extern "C" {
 
+// Runs::paint_runs' run lengths from a level field (post.cuh runs_body), as lab_runs_map launches it
+int emu_runs(int rows, int cols, uint32_t const *dist, uint32_t *runs, uint32_t *max_out, int nwarps) {
+    Geom g{};
+    g.rows = rows;
+    g.cols = cols;
+    *max_out = 0;
+    long long const nthreads = static_cast<long long>(nwarps) * 32;
+    simt::launch(nwarps, [&](int wid, int lane) { runs_body(g, dist, runs, max_out, static_cast<long long>(wid) * 32 + lane, nthreads); });
+    return 0;
+}
 void emu_set_tree(int mode) { g_tree_mode = mode; }
 void emu_set_lattice(int mode) { g_lattice_mode = mode; }
 int emu_last_lattice_error(void) { return static_cast<int>(g_tree_last.lat_err); }

@@ -29,7 +29,7 @@ def test_help_and_flag_errors(prog):
 
 def test_out_of_scope_solvers_are_argument_errors():
     assert run("run_maze", "-s", "dfs-hunt").returncode == 1
-    assert run("measure", "-p", "runs").returncode == 1
+    assert run("measure", "-p", "runs2").returncode == 1
 
 
 def read_dump(path):
