@@ -127,7 +127,8 @@ class ClockSampler:
 def make_case_for(lab, game, builder, n, mod, seed_offset, rows=None):
     rows = rows or n
     pillar = mod == "pillar"  # (bench only) one wall square in the arena: no longer an open room, the tile wave runs
-    maze = lab.cached_maze(builder, rows, n, seed=SEED + 2 + seed_offset, mod=None if pillar else mod)
+    # (very large mazes for the sharded distance map: map the cached file, every rank copies its own band only)
+    maze = lab.cached_maze(builder, rows, n, seed=SEED + 2 + seed_offset, mod=None if pillar else mod, mmap=game == "distance" and rows * n > (1 << 31))
     if pillar:
         maze = maze.copy()
         maze[rows // 4, n // 4] &= ~np.uint16(lab.PATH_BIT)

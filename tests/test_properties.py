@@ -13,13 +13,16 @@ import pytest
 INF = 0xFFFFFFFF
 
 
-def check_field(torch, levels, squares, start, lab, block=2048):
-    """levels: int32 CUDA tensor (bit pattern of uint32), squares: int16 CUDA tensor (after the map), start: (r, c)."""
+def check_field(torch, levels, squares, start, lab, block=2048, first_row=0, last_row=None):
+    """levels: int32 CUDA tensor (bit pattern of uint32), squares: int16 CUDA tensor (after the map), start: (r, c).
+    first_row / last_row: check these rows only (a row band with one halo row of its neighbours above and below:
+    tools/run_bands.py --check-property)."""
     rows, cols = levels.shape
+    last_row = rows if last_row is None else last_row
     big = 1 << 40
     reached_total, max_level = 0, 0
-    for r0 in range(0, rows, block):
-        r1 = min(rows, r0 + block)
+    for r0 in range(first_row, last_row, block):
+        r1 = min(last_row, r0 + block)
         lo, hi = max(0, r0 - 1), min(rows, r1 + 1)
         L = levels[lo:hi].to(torch.int64) & 0xFFFFFFFF
         L = torch.where(L == INF, torch.full_like(L, big), L)

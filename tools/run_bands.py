@@ -13,13 +13,23 @@ ap.add_argument("--builder", default="kruskal"); ap.add_argument("--rows", type=
 ap.add_argument("--check", action="store_true"); ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--game", default="distance", choices=["distance", "hunt", "gather"])
 ap.add_argument("--super", action="store_true", help="bands of whole super-tile rows (the lattice road across bands)")
+ap.add_argument("--check-property", action="store_true", help="verify every band on the device through the BFS equations (tests/test_properties.py), "
+                "with one halo row of levels from the neighbouring bands: for sizes beyond the oracle's reach")
+ap.add_argument("--seed", type=lambda x: int(x, 0), default=0xB2000005)
+ap.add_argument("--cached", action="store_true", help="build the maze once (rank 0), cache it as a raw maze file, map it on the other ranks")
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 lab = graft.load_package()
 from mazes_b200 import bands
-maze = lab.build_maze(a.builder, a.rows, a.cols, seed=0xB2000005)
+if a.cached:
+    if rank == 0:
+        lab.cached_maze(a.builder, a.rows, a.cols, seed=a.seed, mmap=True)
+    dist.barrier()
+    maze = lab.cached_maze(a.builder, a.rows, a.cols, seed=a.seed, mmap=True)
+else:
+    maze = lab.build_maze(a.builder, a.rows, a.cols, seed=a.seed)
 if a.game != "distance":
     # the sharded solvers: place the game on the host as the reference does, run it band by band, compare with the oracle
     if a.game == "hunt":
@@ -71,6 +81,34 @@ for rep in range(a.reps):
     if rank == 0:
         print(json.dumps({"builder": a.builder, "rows": a.rows, "cols": a.cols, "world": world, "rep": rep, "wall_ms": round(float(t.item()) * 1e3, 3),
                           "Gcells_per_s": round(res["settled"] / float(t.item()) / 1e9, 3), **res}), flush=True)
+if a.check_property:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_properties import check_field
+    # one halo row of levels and Squares from each neighbour, then the BFS equations on the band's own rows
+    up_lv, dn_lv = torch.full((1, a.cols), -1, dtype=torch.int32, device="cuda"), torch.full((1, a.cols), -1, dtype=torch.int32, device="cuda")
+    up_sq, dn_sq = torch.zeros((1, a.cols), dtype=torch.int16, device="cuda"), torch.zeros((1, a.cols), dtype=torch.int16, device="cuda")
+    ops = []
+    if rank > 0:
+        ops += [dist.P2POp(dist.isend, lv[:1].contiguous(), rank - 1), dist.P2POp(dist.irecv, up_lv, rank - 1),
+                dist.P2POp(dist.isend, sq[:1].contiguous(), rank - 1), dist.P2POp(dist.irecv, up_sq, rank - 1)]
+    if rank < world - 1:
+        ops += [dist.P2POp(dist.isend, lv[-1:].contiguous(), rank + 1), dist.P2POp(dist.irecv, dn_lv, rank + 1),
+                dist.P2POp(dist.isend, sq[-1:].contiguous(), rank + 1), dist.P2POp(dist.irecv, dn_sq, rank + 1)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    first, last = (1 if rank > 0 else 0), (1 if rank > 0 else 0) + n
+    ext_lv = torch.cat(([up_lv] if rank > 0 else []) + [lv] + ([dn_lv] if rank < world - 1 else []))
+    ext_sq = torch.cat(([up_sq] if rank > 0 else []) + [sq] + ([dn_sq] if rank < world - 1 else []))
+    s_ext = (start[0] - r0 + first, start[1]) if r0 <= start[0] < r0 + n else (-10, -10)
+    try:
+        reached, mx_band = check_field(torch, ext_lv, ext_sq, s_ext, lab, first_row=first, last_row=last)
+        tot = torch.tensor([reached], dtype=torch.int64, device="cuda"); dist.all_reduce(tot)
+        mxt = torch.tensor([mx_band], dtype=torch.int64, device="cuda"); dist.all_reduce(mxt, op=dist.ReduceOp.MAX)
+        ok = int(tot.item()) == res["settled"] and int(mxt.item()) == res["max"]
+        print(f"rank {rank}: band rows [{r0},{r0 + n}) BFS equations {'OK' if ok else 'COUNT/MAX MISMATCH'} (reached {reached}, band max {mx_band})", flush=True)
+    except AssertionError as e:
+        print(f"rank {rank}: band rows [{r0},{r0 + n}) BFS equations VIOLATED: {e}", flush=True)
 if a.check:
     O = graft.load_oracle()
     g_ref, d_ref, mx, settled = O.distance_map(maze)

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as graft
 lab = graft.load_package()
 what, builder, n, reps = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 2
-maze = lab.build_maze(builder, n, n, seed=0xB2000002)
+maze = lab.cached_maze(builder, n, n, seed=0xB2000002)
 if what == "gather":
     maze, start, fin = lab.place_gather(maze, seed=0xB2000003)
 if what == "hunt":
