@@ -86,14 +86,16 @@ if a.check_property:
     from test_properties import check_field
     # one halo row of levels and Squares from each neighbour, then the BFS equations on the band's own rows
     up_lv, dn_lv = torch.full((1, a.cols), -1, dtype=torch.int32, device="cuda"), torch.full((1, a.cols), -1, dtype=torch.int32, device="cuda")
+    # (NCCL has no 16-bit integer type: the Squares' rows travel as bytes)
     up_sq, dn_sq = torch.zeros((1, a.cols), dtype=torch.int16, device="cuda"), torch.zeros((1, a.cols), dtype=torch.int16, device="cuda")
+    sq_first, sq_last = sq[:1].contiguous().view(torch.uint8), sq[-1:].contiguous().view(torch.uint8)
     ops = []
     if rank > 0:
         ops += [dist.P2POp(dist.isend, lv[:1].contiguous(), rank - 1), dist.P2POp(dist.irecv, up_lv, rank - 1),
-                dist.P2POp(dist.isend, sq[:1].contiguous(), rank - 1), dist.P2POp(dist.irecv, up_sq, rank - 1)]
+                dist.P2POp(dist.isend, sq_first, rank - 1), dist.P2POp(dist.irecv, up_sq.view(torch.uint8), rank - 1)]
     if rank < world - 1:
         ops += [dist.P2POp(dist.isend, lv[-1:].contiguous(), rank + 1), dist.P2POp(dist.irecv, dn_lv, rank + 1),
-                dist.P2POp(dist.isend, sq[-1:].contiguous(), rank + 1), dist.P2POp(dist.irecv, dn_sq, rank + 1)]
+                dist.P2POp(dist.isend, sq_last, rank + 1), dist.P2POp(dist.irecv, dn_sq.view(torch.uint8), rank + 1)]
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
