@@ -594,6 +594,18 @@ inline void paint_map(Maze::Maze &maze, bool runs, std::optional<Speed::Speed> s
     std::mt19937 rng(device_seed());
     std::uniform_int_distribution<int> uid(0, 2);
     int const choice = uid(rng); // (drawn whether or not anything is printed: the same RNG stream either way)
+    // LAB_DEVICES=n (n > 1): the map is made on n GPUs of this process, the maze cut into row bands (lab_distance_map_sharded).
+    // (The painter's colours need the map on one device: with rendering on, one device makes it.)
+    if (char const *nd = std::getenv("LAB_DEVICES"); nd && std::atoi(nd) > 1 && !runs && g_quiet) {
+        int const n = std::min(std::atoi(nd), 8);
+        int devices[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+        lab_point const s = lab_distance_start(rows, cols);
+        if (lab_distance_map_sharded(n, devices, rows, cols, maze.squares(), s.row, s.col, nullptr, &max, &settled, nullptr) != LAB_OK) {
+            std::cerr << "lab_distance_map_sharded: " << lab_sharded_last_error() << "\n";
+            std::abort();
+        }
+        return;
+    }
     {
         Device_maze d(maze);
         lab_point const s = lab_distance_start(rows, cols);

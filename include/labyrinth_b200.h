@@ -274,6 +274,19 @@ int lab_band_lat_link(lab_grid *g, void *header_dev);
 int lab_band_lat_flood(lab_grid *g, const void *all_headers_dev, int world, int zero_weights);
 int lab_band_lat_levels(lab_grid *g, int32_t *used);
 
+/* ---- one process, several GPUs --------------------------------------------------------------- */
+/* The reference is one process with one Maze (run_maze/run_maze.cc:182); this lets its entry points use the whole box
+ * without a launcher (SURVEY.md 8(b)'s lab_set_devices): the distance map of the host Squares (rows*cols, updated in place
+ * as lab_distance_map + lab_grid_download do) cut into row bands over `ndev` devices of THIS process (devices[] = CUDA
+ * ordinals; they must be peers).  It is the lattice road across bands above in peer mode: no NCCL, the kernels store their
+ * slices of the border list and their weights into every device's copy over NVLink, the host only orders the three phases.
+ * A maze the sharded road does not apply to (even sizes, start not on a cell, fewer than two super-tile rows, not one
+ * lattice tree) is searched by devices[0] alone -- *devices_used says which it was.  dist_host, max_out, settled_out,
+ * devices_used may be NULL.  Errors: lab_sharded_last_error() (or lab_last_error() for the calls underneath). */
+int lab_distance_map_sharded(int ndev, const int *devices, int rows, int cols, uint16_t *squares, int start_row, int start_col,
+                             uint32_t *dist_host, uint64_t *max_out, uint64_t *settled_out, int *devices_used);
+const char *lab_sharded_last_error(void);
+
 int lab_last_timing(const lab_grid *g, lab_timing *out);
 int lab_last_stats(const lab_grid *g, lab_stats *out);
 const char *lab_last_error(void);

@@ -39,7 +39,7 @@ ABI_SYMBOLS = (
     "lab_band_export_edges", "lab_band_import_edges", "lab_band_finish",
     "lab_band_tree_bind", "lab_band_tree_chunk_words", "lab_band_tree_count", "lab_band_tree_rank_local", "lab_band_tree_flood",
     "lab_band_tree_prefix_local", "lab_band_tree_levels", "lab_band_room",
-    "lab_band_begin_lattice", "lab_band_lat_super_rows", "lab_band_lat_words", "lab_band_lat_bind", "lab_band_lat_set_peers", "lab_band_lat_link", "lab_band_lat_flood",
+    "lab_distance_map_sharded", "lab_sharded_last_error", "lab_band_begin_lattice", "lab_band_lat_super_rows", "lab_band_lat_words", "lab_band_lat_bind", "lab_band_lat_set_peers", "lab_band_lat_link", "lab_band_lat_flood",
     "lab_band_lat_levels",
     "lab_band_begin_game", "lab_band_level_at", "lab_band_paint", "lab_band_walk", "lab_band_recolour", "lab_band_finish_game",
 )
@@ -207,6 +207,23 @@ def cached_maze(builder: str, rows: int, cols: int, seed: int, mod: Optional[str
     except (OSError, LabError):
         pass  # a cache that cannot be written is only slower
     return g
+
+
+def distance_map_sharded(squares: np.ndarray, devices: Sequence[int], start: Optional[tuple] = None, want_dist: bool = True):
+    """lab_distance_map_sharded: one process, `devices` GPUs, row bands (peer stores over NVLink, no NCCL).
+    -> (squares after, DistanceResult, devices used)"""
+    g = np.ascontiguousarray(squares, np.uint16).copy()
+    rows, cols = g.shape
+    sr, sc = start if start is not None else distance_start(rows, cols)
+    dist = np.empty((rows, cols), np.uint32) if want_dist else None
+    mx, st, used = c_uint64(), c_uint64(), c_int()
+    dev = (c_int * len(devices))(*devices)
+    L = lib()
+    L.lab_sharded_last_error.restype = c_char_p
+    rc = L.lab_distance_map_sharded(len(devices), dev, rows, cols, _np_ptr(g), sr, sc, _np_ptr(dist) if want_dist else None, byref(mx), byref(st), byref(used))
+    if rc != 0:
+        raise LabError(rc, (L.lab_sharded_last_error() or L.lab_last_error()).decode(errors="replace"))
+    return g, DistanceResult(mx.value, st.value, dist), used.value
 
 
 def distance_start(rows: int, cols: int) -> tuple[int, int]:

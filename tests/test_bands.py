@@ -563,3 +563,74 @@ def test_gpu_sharded_games_single_rank(lab, O):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("builder,rows,cols,world", [("kruskal", 511, 131, 2), ("wilson", 1023, 67, 4), ("rdfs", 767, 129, 3)])
+def test_lattice_bands_peer_mode_one_process(lab, O, builder, rows, cols, world):
+    """lab_band_lat_set_peers: every band's kernels store its slice of the border list and its weights straight into EVERY
+    band's copy (what lab_distance_map_sharded does over NVLink between the devices of one process): no all-gather, no
+    all-reduce, the phases only have to be ordered.  Kernel bodies on the emulator, bands in lock step."""
+    import ctypes
+
+    import torch
+
+    from _util import emu_band_engine
+    from mazes_b200 import bands
+
+    maze = lab.build_maze(builder, rows, cols, seed=41)
+    split = bands.split_rows_super(rows, world)
+    start = lab.distance_start(rows, cols)
+    engs = [emu_band_engine(maze[r0:r0 + n].copy(), nwarps=3, sched=r + 1) for r, (r0, n) in enumerate(split)]
+    for e, (r0, n) in zip(engs, split):
+        e.begin((start[0] - r0, start[1]) if r0 <= start[0] < r0 + n else None, lattice_next=True)
+    rows_ = [e.path_rows() for e in engs]
+    tops, bots = [r[0].clone() for r in rows_], [r[1].clone() for r in rows_]
+    for r, e in enumerate(engs):
+        e.set_neighbour_paths(bots[r - 1] if r > 0 else None, tops[r + 1] if r < world - 1 else None)
+    per = (split[0][1] + 255) // 256
+    bufs = [e.lat_bind(r, per, world) for r, e in enumerate(engs)]
+    for r, e in enumerate(engs):
+        order = [r] + [q for q in range(world) if q != r]
+        gbs = (ctypes.c_void_p * world)(*[bufs[q]["gb"].data_ptr() for q in order])
+        ws = (ctypes.c_void_p * world)(*[bufs[q]["wsum"].data_ptr() for q in order])
+        assert e.L.emu_band_lat_set_peers(e.h, world, gbs, ws) == 0
+        bufs[r]["wsum"].fill_(0x5A5A5A5A)  # (peer mode does not clear the weights: every position is written by its owner)
+        tail = bufs[r]["reduce_words"] - 8
+        bufs[r]["wsum"][tail:tail + 8] = 0
+    for e, b in zip(engs, bufs):
+        e.lat_link(b["hdr"])
+    all_hdr = torch.cat([b["hdr"] for b in bufs])
+    for e, b in zip(engs, bufs):
+        b["all_hdr"].copy_(all_hdr)
+    for e, b in zip(engs, bufs):
+        e.lat_flood(b["all_hdr"], world, False)
+    assert all(e.lat_levels() for e in engs)
+    g_ref, d_ref, mx_ref, settled_ref = O.distance_map(maze)
+    mx, settled = 0, 0
+    for e, (r0, n) in zip(engs, split):
+        m, s = e.finish()
+        mx, settled = max(mx, m), settled + s
+        assert (e.levels() == d_ref[r0:r0 + n]).all() and (e.sq == g_ref[r0:r0 + n]).all()
+        e.close()
+    assert mx == mx_ref and settled == settled_ref
+
+
+@pytest.mark.gpu
+def test_gpu_distance_map_sharded_one_process(lab, O):
+    """lab_distance_map_sharded through the C ABI.  With one visible GPU both bands run on it (device list [0, 0]: the peer
+    stores are then ordinary stores); with two or more, on two devices over NVLink."""
+    import torch
+
+    ndev = torch.cuda.device_count()
+    devices = [0, 1] if ndev >= 2 else [0, 0]
+    for builder, rows, cols in [("kruskal", 1023, 515), ("wilson", 2047, 1025)]:
+        maze = lab.build_maze(builder, rows, cols, seed=43)
+        after, res, used = lab.distance_map_sharded(maze, devices)
+        g_ref, d_ref, mx_ref, settled_ref = O.distance_map(maze)
+        assert used == 2
+        assert (res.dist == d_ref).all() and (after == g_ref).all() and res.max == mx_ref and res.settled == settled_ref
+    # a maze the sharded road does not apply to: one device searches it
+    maze = lab.build_maze("grid", 1023, 515, seed=43, mod="cross")
+    after, res, used = lab.distance_map_sharded(maze, devices)
+    g_ref, d_ref, mx_ref, settled_ref = O.distance_map(maze)
+    assert used == 1 and (res.dist == d_ref).all() and (after == g_ref).all()
