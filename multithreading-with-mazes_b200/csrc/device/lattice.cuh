@@ -41,6 +41,7 @@ constexpr uint32_t LSLOTS = 128;   // crossing slots of a tile: side * 32 + inde
 enum Lside : uint32_t { L_N = 0, L_E = 1, L_S = 2, L_W = 3 }; // index = cell column (N, S) / cell row (E, W)
 constexpr uint32_t L_END = 0xFFFFFFFEu, L_NONE = 0xFFFFFFFFu;
 constexpr uint32_t L_LINK = 0xFFFFFFFDu; // the first root's tour is over: the list goes on with the second root's (Tree_ctl::lat_head_b)
+constexpr uint32_t LO_NONE = 0xFFu, LO_END = 0xFEu, LO_LINK = 0xFDu; // Lattice::outslot's markers (slots are 0 .. 127)
 constexpr int LST = 4;                                  // super-tile side, tiles
 constexpr uint32_t LB = 4u * LST * LC;                  // border slots of a super-tile
 constexpr uint32_t LSUP_SLOTS = LST * LST * LSLOTS;     // slots of a super-tile (8192: 13-bit local index)
@@ -52,7 +53,7 @@ constexpr uint32_t L_CHUNK = 1024;                      // tour positions per sc
 struct Lattice {
     uint32_t *mask;   // [ntiles][3][32]  cell boards in COLUMN layout (lane = cell column, bit = cell row): cells, W passage open, N passage open
     uint32_t *xmask;  // [ntiles][4]      open crossings per side (bit = index)
-    uint32_t *next;   // [ntiles][128]    the arc the tour continues with after entering through this slot (global arc id), L_END, L_NONE
+    uint8_t *outslot; // [ntiles][128]    the slot the tour LEAVES the tile through after entering through this one; LO_END, LO_LINK, LO_NONE
     uint16_t *label;  // [ntiles][128]    component of the slot's cell (= the component's lowest piece id)
     uint32_t *lplane; // [ntiles][5][32]  piece number of every cell inside its 8x8 board, bit-sliced (piece id = board * 32 + number)
     uint16_t *cmap;   // [ntiles][512]    component of piece (number, board) at [number * 16 + board], numbers < nruns[tile]
@@ -483,7 +484,7 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
     uint32_t const gt = t + lt.tile_base; // the tile's id in the whole maze (row bands)
 #pragma unroll
     for (int s = 0; s < 4; s++) {
-        uint32_t out = L_NONE;
+        uint32_t out = LO_NONE;
         uint32_t const lab = labs[s];
         if (lab != 0xFFFFu) {
             bool const ascending = s == L_N || s == L_E;
@@ -503,17 +504,17 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
                 }
             }
             uint32_t const me = static_cast<uint32_t>(s) * LC + static_cast<uint32_t>(lane);
-            out = lat_twin(g, gt, nslot);
+            out = nslot;
             if (roots.n > 0 && me == root_first[roots.n - 1]) { // the last root's tour ends here ...
                 if (roots.n == 2) {
-                    lab_st_volatile(&tc->lat_head_b, out + 1u); // ... and would have begun with this arc
+                    lab_st_volatile(&tc->lat_head_b, lat_twin(g, gt, nslot) + 1u); // ... and would have begun with this arc
                 }
-                out = L_END;
+                out = LO_END;
             } else if (roots.n == 2 && me == root_first[0]) {
-                out = L_LINK;
+                out = LO_LINK;
             }
         }
-        lt.next[static_cast<long long>(t) * LSLOTS + s * LC + lane] = out;
+        lt.outslot[static_cast<long long>(t) * LSLOTS + s * LC + lane] = static_cast<uint8_t>(out);
         lt.label[static_cast<long long>(t) * LSLOTS + s * LC + lane] = static_cast<uint16_t>(lab);
     }
     lab_syncwarp();
@@ -553,34 +554,50 @@ LAB_DEV uint32_t lat_dense_border(Lattice const &lt, Geom const &g, uint32_t arc
     uint32_t const along = (side == L_N || side == L_S) ? tx % LST : ty % LST;
     return S * LB + side * (LST * LC) + along * LC + idx;
 }
-// the arc after arc a; the end of the first root's tour continues with the second root's
-LAB_DEV uint32_t lat_next(Lattice const &lt, long long a) {
-    uint32_t nx = lab_ld_cg(lt.next + a);
-    if (nx == L_LINK) {
-        uint32_t const h = lab_ld_cg(&lt.tc->lat_head_b);
-        nx = h ? h - 1u : L_END;
-    }
-    return nx;
+// Where the tour goes after entering super-tile-local tile (lt_y, lt_x) through a slot whose out-slot is `o` (< 128):
+// the neighbouring tile on o's side, through the mirrored slot.  (dy, dx, slot there)
+LAB_DEV void lat_step_out(uint32_t o, int &dy, int &dx, uint32_t &slot) {
+    uint32_t const side = o >> 5, idx = o & 31u;
+    dy = side == L_N ? -1 : (side == L_S ? 1 : 0);
+    dx = side == L_W ? -1 : (side == L_E ? 1 : 0);
+    slot = ((side + 2u) & 3u) * LC + idx; // N <-> S, E <-> W
 }
 LAB_DEV void lat_rank_local_super(Params const &p, Lattice const &lt, uint32_t S, int lane, uint32_t *sm) {
     Geom const &g = p.g;
     // (sy0, sx0): the super-tile's first tile in the WHOLE maze; gy0: the band's first tile row there
     uint32_t const SG = S + lt.sup_base, gy0 = lt.tile_base / static_cast<uint32_t>(g.tiles_x);
-    uint32_t const sy0 = (SG / static_cast<uint32_t>(lt.sup_x)) * LST, sx0 = (SG % static_cast<uint32_t>(lt.sup_x)) * LST;
-    auto local_arc = [&](uint32_t ty, uint32_t tx, uint32_t slot) { // (ty, tx) in the whole maze, a tile of this band
-        return (static_cast<long long>(ty - gy0) * g.tiles_x + tx) * LSLOTS + slot;
+    uint32_t const sup_x = static_cast<uint32_t>(lt.sup_x);
+    uint32_t const sy0 = (SG / sup_x) * LST, sx0 = (SG % sup_x) * LST;
+    // (the second root's first arc, if the list is two tours chained: the one entry that is not a neighbour's slot)
+    uint32_t const head_b = lab_ld_cg(&lt.tc->lat_head_b);
+    auto local_arc = [&](uint32_t lt_y, uint32_t lt_x, uint32_t slot) { // a tile of this super-tile (and of this band)
+        return (static_cast<long long>(sy0 + lt_y - gy0) * g.tiles_x + sx0 + lt_x) * LSLOTS + slot;
+    };
+    // where the chain goes from entry i: -> (global tile row, column, slot), or none (the end of the list)
+    auto successor = [&](uint32_t lt_y, uint32_t lt_x, uint32_t o, uint32_t &ny, uint32_t &nx, uint32_t &nslot) {
+        if (o == LO_LINK) {
+            if (!head_b) return false;
+            uint32_t const a = head_b - 1u, t = a / LSLOTS;
+            ny = t / static_cast<uint32_t>(g.tiles_x);
+            nx = t % static_cast<uint32_t>(g.tiles_x);
+            nslot = a % LSLOTS;
+            return true;
+        }
+        if (o >= LO_LINK) return false; // END (or no crossing)
+        int dy, dx;
+        lat_step_out(o, dy, dx, nslot);
+        ny = sy0 + lt_y + static_cast<uint32_t>(dy);
+        nx = sx0 + lt_x + static_cast<uint32_t>(dx);
+        return true;
     };
     for (uint32_t i = static_cast<uint32_t>(lane); i < LSUP_SLOTS; i += 32u) {
         uint32_t const lt_y = i / (LST * LSLOTS), lt_x = (i / LSLOTS) % LST, slot = i % LSLOTS;
-        uint32_t const ty = sy0 + lt_y, tx = sx0 + lt_x;
         uint32_t e = LX_OUT | i;
-        if (ty - gy0 < static_cast<uint32_t>(g.tiles_y) && tx < static_cast<uint32_t>(g.tiles_x)) {
-            uint32_t const nx = lat_next(lt, local_arc(ty, tx, slot));
-            if (nx < L_LINK) {
-                uint32_t const nt = nx / LSLOTS, ny = nt / static_cast<uint32_t>(g.tiles_x), nxx = nt % static_cast<uint32_t>(g.tiles_x);
-                if (ny - sy0 < static_cast<uint32_t>(LST) && nxx - sx0 < static_cast<uint32_t>(LST)) {
-                    e = (((ny - sy0) * LST + (nxx - sx0)) * LSLOTS + nx % LSLOTS) | (1u << 13);
-                }
+        if (sy0 + lt_y - gy0 < static_cast<uint32_t>(g.tiles_y) && sx0 + lt_x < static_cast<uint32_t>(g.tiles_x)) {
+            uint32_t const o = lab_ld_cg(lt.outslot + local_arc(lt_y, lt_x, slot));
+            uint32_t ny, nx, nslot;
+            if (successor(lt_y, lt_x, o, ny, nx, nslot) && ny - sy0 < static_cast<uint32_t>(LST) && nx - sx0 < static_cast<uint32_t>(LST)) {
+                e = (((ny - sy0) * LST + (nx - sx0)) * LSLOTS + nslot) | (1u << 13);
             }
         }
         sm[i] = e;
@@ -606,19 +623,23 @@ LAB_DEV void lat_rank_local_super(Params const &p, Lattice const &lt, uint32_t S
     lab_syncwarp();
     for (uint32_t i = static_cast<uint32_t>(lane); i < LSUP_SLOTS; i += 32u) {
         uint32_t const lt_y = i / (LST * LSLOTS), lt_x = (i / LSLOTS) % LST, slot = i % LSLOTS, side = slot >> 5;
-        uint32_t const ty = sy0 + lt_y, tx = sx0 + lt_x;
-        bool const present = ty - gy0 < static_cast<uint32_t>(g.tiles_y) && tx < static_cast<uint32_t>(g.tiles_x);
+        bool const present = sy0 + lt_y - gy0 < static_cast<uint32_t>(g.tiles_y) && sx0 + lt_x < static_cast<uint32_t>(g.tiles_x);
         uint64_t pair = 0xFFFFFFFFull; // (no arc: the end, 0 hops)
         bool open = false;
         if (present) {
-            long long const a = local_arc(ty, tx, slot);
-            open = lab_ld_cg(lt.next + a) != L_NONE;
+            long long const a = local_arc(lt_y, lt_x, slot);
+            open = lab_ld_cg(lt.outslot + a) != LO_NONE;
             if (open) {
                 uint32_t const e = sm[i];
                 uint32_t const last = e & LX_IDX, hops = ((e & ~LX_OUT) >> 13) + 1u;
                 uint32_t const ly = last / (LST * LSLOTS), lx = (last / LSLOTS) % LST;
-                uint32_t const nx = lat_next(lt, local_arc(sy0 + ly, sx0 + lx, last % LSLOTS));
-                uint32_t const dense = (nx >= L_LINK || !(e & LX_OUT)) ? 0xFFFFFFFFu : lat_dense_border(lt, g, nx);
+                uint32_t const o = lab_ld_cg(lt.outslot + local_arc(ly, lx, last % LSLOTS));
+                uint32_t ny, nx, nslot, dense = 0xFFFFFFFFu;
+                if ((e & LX_OUT) && successor(ly, lx, o, ny, nx, nslot)) { // an inbound border slot of another super-tile
+                    uint32_t const nside = nslot >> 5;
+                    uint32_t const along = (nside == L_N || nside == L_S) ? nx % LST : ny % LST;
+                    dense = ((ny / LST) * sup_x + nx / LST) * LB + nside * (LST * LC) + along * LC + (nslot & 31u);
+                }
                 pair = static_cast<uint64_t>(dense) | (static_cast<uint64_t>(hops) << 32);
                 lab_st_cg(lt.xd + a, pair);
             }
@@ -699,7 +720,7 @@ LAB_DEV void lat_rank_expand_body(Lattice const &lt, long long gthread, long lon
     bool bad = false;
     for (long long a = gthread; a < static_cast<long long>(lt.nslots); a += nthreads) {
         uint32_t r = 0;
-        if (lab_ld_cg(lt.next + a) != L_NONE) {
+        if (lab_ld_cg(lt.outslot + a) != LO_NONE) {
             uint64_t const e = lab_ld_cg(lt.xd + a);
             uint32_t const x = static_cast<uint32_t>(e);
             r = static_cast<uint32_t>(e >> 32);

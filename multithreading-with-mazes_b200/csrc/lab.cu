@@ -701,7 +701,7 @@ int ensure_lattice(lab_grid *h) {
     lt.nslots = static_cast<uint32_t>(nt * LSLOTS);
     CU(cudaMalloc(&lt.mask, nt * 96 * sizeof(uint32_t)));
     CU(cudaMalloc(&lt.xmask, nt * 4 * sizeof(uint32_t)));
-    CU(cudaMalloc(&lt.next, nt * LSLOTS * sizeof(uint32_t)));
+    CU(cudaMalloc(&lt.outslot, nt * LSLOTS));
     CU(cudaMalloc(&lt.label, nt * LSLOTS * sizeof(uint16_t)));
     CU(cudaMalloc(&lt.cmap, nt * 512 * sizeof(uint16_t)));
     CU(cudaMalloc(&lt.nruns, nt * sizeof(uint32_t)));
@@ -1135,7 +1135,7 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->tree.tc);
     if (h->lat_alloc) {
         Lattice &lt = h->lat;
-        void *const arrays[] = {lt.mask, lt.xmask, lt.next, lt.label, lt.cmap, lt.nruns, lt.lplane, lt.xd, lt.gb, lt.R, lt.dplane, lt.emask, lt.wsum, lt.chunk};
+        void *const arrays[] = {lt.mask, lt.xmask, lt.outslot, lt.label, lt.cmap, lt.nruns, lt.lplane, lt.xd, lt.gb, lt.R, lt.dplane, lt.emask, lt.wsum, lt.chunk};
         for (void *a : arrays) {
             cudaFree(a);
         }
