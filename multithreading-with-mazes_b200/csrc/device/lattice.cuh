@@ -7,11 +7,11 @@
 // walks (12 of 32 lanes busy, profiles/r01b_*).  On the lattice a 64x64-square tile is a 32x32 CELL board that
 // fits one 32-bit word per lane, and everything a tile has to do becomes a few warp-wide bit operations:
 //
-//   1 link    components of a tile by bit-board flood fill (one step = 2 shifts, 2 shuffles, 6 logic ops for
-//             all 1024 cells).  The tree is planar, so the Euler tour that enters a component through one
-//             border crossing leaves it through the NEXT crossing of the same component clockwise around the
-//             tile: no wall following at all, the tour's successor pointers come from the labels of the <= 128
-//             crossing slots (match_any).
+//   1 link    components of a tile: the vertical runs of a cell column are bit operations on the column's word, the
+//             W passages join them through a union-find in shared memory (one union per passage).  The tree is
+//             planar, so the Euler tour that enters a component through one border crossing leaves it through the
+//             NEXT crossing of the same component clockwise around the tile: no wall following at all, the tour's
+//             successor pointers come from the labels of the <= 128 crossing slots (match_any).
 //   2 rank    hops to the end of the tour for every crossing arc, hierarchically: inside a super-tile of
 //             LST x LST tiles by in-place pointer jumping in shared memory (one warp, single-word (pointer,
 //             hops) entries, so any interleaving of reads and writes is valid and no barrier is needed), then
@@ -45,8 +45,8 @@ constexpr uint32_t LO_NONE = 0xFFu, LO_END = 0xFEu, LO_LINK = 0xFDu; // Lattice:
 constexpr int LST = 4;                                  // super-tile side, tiles
 constexpr uint32_t LB = 4u * LST * LC;                  // border slots of a super-tile
 constexpr uint32_t LSUP_SLOTS = LST * LST * LSLOTS;     // slots of a super-tile (8192: 13-bit local index)
-constexpr int L_LABEL_PLANES = 5, L_DEPTH_PLANES = 10;      // a cell's piece number inside its 8x8 board / its depth below its component's entry
-constexpr uint32_t L_LINK_SM = 768 + 512;               // words of shared memory per warp: lat_link_tile, lat_levels_tile
+constexpr int L_DEPTH_PLANES = 10;                          // a cell's depth below its component's entry, bit-sliced
+constexpr uint32_t L_LINK_SM = 1536;                    // words of shared memory per warp: lat_link_tile, lat_levels_tile
 constexpr bool L_PAIR_STORES = false;                   // 8-byte stores of the level rows (see lat_levels_tile)
 constexpr uint32_t L_CHUNK = 1024;                      // tour positions per scan chunk
 
@@ -55,9 +55,7 @@ struct Lattice {
     uint32_t *xmask;  // [ntiles][4]      open crossings per side (bit = index)
     uint8_t *outslot; // [ntiles][128]    the slot the tour LEAVES the tile through after entering through this one; LO_END, LO_LINK, LO_NONE
     uint16_t *label;  // [ntiles][128]    component of the slot's cell (= the component's lowest piece id)
-    uint32_t *lplane; // [ntiles][5][32]  piece number of every cell inside its 8x8 board, bit-sliced (piece id = board * 32 + number)
-    uint16_t *cmap;   // [ntiles][512]    component of piece (number, board) at [number * 16 + board], numbers < nruns[tile]
-    uint32_t *nruns;  // [ntiles]
+    uint16_t *cmap;   // [ntiles][1024]   component of the vertical run that begins at cell (row, column), at [row * 32 + column]
     uint64_t *xd;     // [ntiles][128]    after the local ranking: (dense border slot the chain leaves the super-tile to | hops to there << 32)
     uint64_t *gb;     // [nsuper][LB]     the border arcs' list: (next dense border slot | hops << 32), jumped in place
     uint32_t *R;      // [ntiles][128]    hops to the end of the tour (>= 1; larger = earlier)
@@ -264,195 +262,110 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
     }
     arcs += lane == 0 ? static_cast<uint32_t>(lab_popc64(T.XN) + lab_popc64(T.XE) + lab_popc64(T.XS) + lab_popc64(T.XW)) : 0u;
 
-    // ---- A: sixteen 8x8 BOARDS at once.  With the links between boards masked out a flood-fill step of the whole tile is
-    // sixteen independent steps, so every run floods one component PIECE per board (seeded from the board's first cell
-    // with a link out of the board that no earlier run reached).  All pieces of run r get the piece number r: a cell's
-    // piece id is  board * 32 + r  (sid), five bit planes for the whole tile. ----
-    uint32_t *parent = sm;                                                // [512] union-find over piece ids
-    uint16_t *rootof = reinterpret_cast<uint16_t *>(sm + 512);            // [512] component (= its lowest piece id) of a piece
-    uint8_t *first = reinterpret_cast<uint8_t *>(sm + 768);               // [4][512] see C
-    Lat_tile B = T;
-    B.mS &= 0xFEFEFEFEu;
-    B.mN &= 0x7F7F7F7Fu;
-    B.mE = (lane & 7) ? B.mE : 0u;
-    B.mW = ((lane & 7) != 7) ? B.mW : 0u;
-    uint32_t const right_wo = lab_shfl_down(T.Wo, 1);
-    uint32_t U = (T.No & 0x01010101u) | ((T.No >> 1) & 0x00808080u) | (((T.XS >> lane) & 1u) << 31) | ((lane & 7) == 0 ? T.Wo : 0u) |
-                 ((lane & 7) == 7 ? (lane == 31 ? T.XE : right_wo) : 0u);
-    U &= T.C;
-    uint32_t L[L_LABEL_PLANES];
-#pragma unroll
-    for (int q = 0; q < L_LABEL_PLANES; q++) {
-        L[q] = 0;
-    }
-    uint32_t runs = 0, root_sid[2] = {0xFFFFu, 0xFFFFu}, all = 0;
-    bool root_pending[2] = {roots.n > 0 && roots.tile[0] == t, roots.n > 1 && roots.tile[1] == t};
-    bool const root_tile = root_pending[0] || root_pending[1];
-    for (;;) {
-        uint32_t F = 0;
-#pragma unroll
-        for (int bi = 0; bi < 4; bi++) {
-            uint32_t const byte = (U >> (8 * bi)) & 0xFFu;
-            uint32_t const grp = (lab_ballot(byte != 0) >> (lane & 24)) & 0xFFu; // which of the board's eight columns have a seed
-            if (byte && (lane & 7) == lab_ffs32(grp) - 1) {
-                F |= (byte & (0u - byte)) << (8 * bi);
-            }
-        }
-        if (!lab_any(F != 0)) {
-            if (root_pending[0] || root_pending[1]) { // a root whose piece has no link out of its board (a maze inside one board)
-                int const q = root_pending[0] ? 0 : 1;
-                F = lane == roots.col[q] ? (1u << roots.row[q]) : 0u;
-            } else {
-                break;
-            }
-        }
-        if (runs >= 32u) { // more pieces in one board than it has border cells: cannot be
-            if (lane == 0) lab_st_volatile(&tc->lat_err, 2u);
-            return;
-        }
-        uint32_t M = F;
-        for (int it = 0; it < 64 / 2 + 1; it++) {
-            lat_step(B, F, M);
-            lat_step(B, F, M);
-            if (!lab_any(F != 0)) {
-                break;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < L_LABEL_PLANES; q++) {
-            if ((runs >> q) & 1u) {
-                L[q] |= M;
-            }
-        }
-        if (root_tile) {
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                if (root_pending[q] && ((lab_shfl(M, roots.col[q]) >> roots.row[q]) & 1u)) {
-                    root_sid[q] = static_cast<uint32_t>((roots.row[q] >> 3) * 4 + (roots.col[q] >> 3)) * 32u + runs;
-                    root_pending[q] = false;
-                }
-            }
-        }
-        all |= M;
-        U &= ~M;
-        runs++;
-    }
-    if (lab_any(all != T.C)) { // cells no run reached: a part of the maze without a way out of its board -- not one tree
-        if (lane == 0) lab_st_volatile(&tc->lat_err, 4u);
-        return;
-    }
-    {
-        uint32_t *pl = lt.lplane + static_cast<long long>(t) * (L_LABEL_PLANES * 32);
-#pragma unroll
-        for (int q = 0; q < L_LABEL_PLANES; q++) {
-            pl[q * 32 + lane] = L[q];
-        }
-    }
-    // ---- B: pieces joined through the open links between boards are one component: union-find over the piece ids (the
-    // larger root is hooked under the smaller, so roots only decrease and concurrent unions cannot form a cycle) ----
+    // ---- A: components.  A column's cells fall into vertical RUNS (cells joined through open N passages); bit i of
+    // `st`: cell (i, lane) begins one.  A run is named after its first cell, id = row * 32 + column, so the runs cost
+    // nothing; the open W passages join runs of neighbouring columns: a union-find over the ids in shared memory (the
+    // larger root is hooked under the smaller: pointers only ever lead to smaller ids, no cycle can form, and a
+    // component's name is its lowest run id).  One union per W passage, ~16 per lane. ----
+    uint16_t *parent = reinterpret_cast<uint16_t *>(sm);                 // [1024]
+    uint8_t *first = reinterpret_cast<uint8_t *>(sm + 512);              // [4][1024] see C; all 0xFF between tiles (lat_link_body)
+    uint32_t const st = T.C & ~(T.No & ~1u);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        parent[k * 32 + lane] = static_cast<uint32_t>(k * 32 + lane);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        sm[768 + k * 128 + lane] = 0xFFFFFFFFu; // `first`
-        sm[768 + k * 128 + 32 + lane] = 0xFFFFFFFFu;
-        sm[768 + k * 128 + 64 + lane] = 0xFFFFFFFFu;
-        sm[768 + k * 128 + 96 + lane] = 0xFFFFFFFFu;
+        int const w = k * 32 + lane; // ids 2w, 2w + 1
+        sm[w] = static_cast<uint32_t>(2 * w) | (static_cast<uint32_t>(2 * w + 1) << 16);
     }
     lab_syncwarp();
-    auto piece = [&](uint32_t const (&P)[L_LABEL_PLANES], int bit) {
-        uint32_t r = 0;
-#pragma unroll
-        for (int q = 0; q < L_LABEL_PLANES; q++) {
-            r |= ((P[q] >> bit) & 1u) << q;
+    auto run_of = [](uint32_t starts, int i) { return 31 - lab_clz32(starts & (0xFFFFFFFFu >> (31 - i))); }; // first row of cell i's run
+    auto find = [&](uint32_t a) {
+        // path halving (a stale grandparent is still an ancestor: roots only ever get hooked under smaller ids)
+        for (uint32_t pa; (pa = lab_ld_volatile(parent + a)) != a;) {
+            uint32_t const ga = lab_ld_volatile(parent + pa);
+            if (ga != pa) lab_st_volatile(parent + a, static_cast<uint16_t>(ga));
+            a = ga;
         }
-        return r;
+        return a;
     };
-    auto unite = [&](uint32_t a, uint32_t b) {
-        for (int guard = 0; guard < 1024; guard++) {
-            // find with path halving (a stale grandparent is still an ancestor: roots only ever get hooked under smaller ids)
-            for (uint32_t pa; (pa = lab_ld_volatile(parent + a)) != a;) {
-                uint32_t const ga = lab_ld_volatile(parent + pa);
-                lab_st_volatile(parent + a, ga);
-                a = ga;
-            }
-            for (uint32_t pb; (pb = lab_ld_volatile(parent + b)) != b;) {
-                uint32_t const gb = lab_ld_volatile(parent + pb);
-                lab_st_volatile(parent + b, gb);
-                b = gb;
-            }
-            if (a == b) {
-                return;
-            }
-            uint32_t const hi = a > b ? a : b, lo = a > b ? b : a;
-            if (lab_atomic_cas(parent + hi, hi, lo) == hi) {
-                return;
-            }
-        }
-    };
-    // links between vertically adjacent boards: rows 8, 16, 24 of this lane's column
-#pragma unroll
-    for (int bi = 1; bi < 4; bi++) {
-        if ((T.No >> (8 * bi)) & 1u) {
-            unite(static_cast<uint32_t>(bi * 4 + (lane >> 3)) * 32u + piece(L, 8 * bi), static_cast<uint32_t>((bi - 1) * 4 + (lane >> 3)) * 32u + piece(L, 8 * bi - 1));
-        }
-    }
-    // links between horizontally adjacent boards: columns 8, 16, 24; lane = row
-#pragma unroll
-    for (int bj = 1; bj < 4; bj++) {
-        uint32_t PR[L_LABEL_PLANES], PL[L_LABEL_PLANES];
-#pragma unroll
-        for (int q = 0; q < L_LABEL_PLANES; q++) {
-            PR[q] = lab_shfl(L[q], 8 * bj);
-            PL[q] = lab_shfl(L[q], 8 * bj - 1);
-        }
-        uint32_t const wo = lab_shfl(T.Wo, 8 * bj);
-        if ((wo >> lane) & 1u) {
-            unite(static_cast<uint32_t>((lane >> 3) * 4 + bj) * 32u + piece(PR, lane), static_cast<uint32_t>((lane >> 3) * 4 + bj - 1) * 32u + piece(PL, lane));
-        }
-    }
-    lab_syncwarp();
     {
-        uint16_t *cmap = lt.cmap + static_cast<long long>(t) * 512;
-        for (uint32_t idx = static_cast<uint32_t>(lane); idx < runs * 16u; idx += 32u) { // piece (run idx / 16) of board idx % 16
-            uint32_t const sid = (idx & 15u) * 32u + (idx >> 4);
-            uint32_t a = sid;
-            for (uint32_t pa; (pa = parent[a]) != a;) a = pa;
-            rootof[sid] = static_cast<uint16_t>(a);
-            cmap[idx] = static_cast<uint16_t>(a);
-        }
-        if (lane == 0) {
-            lt.nruns[t] = runs;
+        // Warp-synchronous rounds instead of atomics (a shared-memory CAS costs the LSU 2-4 cycles per LANE): every lane
+        // finds the two roots of its next passage; after a barrier all lanes hook at once with a plain store -- roots are
+        // only changed by hooks, so every lane still holds true roots; lanes hooking the SAME root collide, one store
+        // wins, the others see it after the next barrier and go round again.
+        uint32_t const st_left = lab_shfl_up(st, 1);
+        uint32_t w = lane ? T.Wo : 0u; // (lane 0's W passages are crossings)
+        uint32_t a = 0, b = 0;
+        bool busy = false;
+        for (int round = 0; round < 2048; round++) {
+            if (!busy && w) {
+                int const i = lab_ffs32(w) - 1;
+                w &= w - 1u;
+                a = static_cast<uint32_t>(run_of(st, i) * 32 + lane);
+                b = static_cast<uint32_t>(run_of(st_left, i) * 32 + lane - 1);
+                busy = true;
+            }
+            if (!lab_any(busy)) {
+                break;
+            }
+            uint32_t hi = 0, lo = 0;
+            if (busy) {
+                a = find(a);
+                b = find(b);
+                hi = a > b ? a : b;
+                lo = a > b ? b : a;
+                busy = a != b; // (equal: a cycle, not a tree; the counts or the tour will say so)
+            }
+            lab_syncwarp();
+            if (busy) {
+                lab_st_volatile(parent + hi, static_cast<uint16_t>(lo));
+            }
+            lab_syncwarp();
+            if (busy && lab_ld_volatile(parent + hi) == lo) {
+                busy = false;
+            }
         }
     }
     lab_syncwarp();
+    // every id's component, flat (parent[id] = root), by pointer doubling over all 1024 ids in step: 32 independent
+    // two-hop look-ups per lane and pass, no divergence (a walk to the root per run is a long tail of a few lanes).
+    // cmap: the flat array as it is, for lat_levels_tile (ids that begin no run hold themselves).
+    for (int pass = 0; pass < 12; pass++) {
+        bool changed = false;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            uint32_t const pa = parent[k * 32 + lane], ga = parent[pa];
+            if (ga != pa) {
+                parent[k * 32 + lane] = static_cast<uint16_t>(ga);
+                changed = true;
+            }
+        }
+        lab_syncwarp();
+        if (!lab_any(changed)) {
+            break;
+        }
+    }
+    {
+        uint32_t *cm = reinterpret_cast<uint32_t *>(lt.cmap + static_cast<long long>(t) * 1024);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            cm[k * 32 + lane] = sm[k * 32 + lane];
+        }
+    }
     // ---- C: the tour: from a slot to the next slot of the same component, clockwise (N ->, E down, S <-, W up) ----
     uint32_t labs[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu}; // component of slots (side, lane)
     {
-        uint32_t PW[L_LABEL_PLANES], PE[L_LABEL_PLANES];
-#pragma unroll
-        for (int q = 0; q < L_LABEL_PLANES; q++) {
-            PW[q] = lab_shfl(L[q], 0);
-            PE[q] = lab_shfl(L[q], 31);
-        }
-        if ((T.XN >> lane) & 1u) labs[L_N] = rootof[static_cast<uint32_t>(lane >> 3) * 32u + piece(L, 0)];
-        if ((T.XS >> lane) & 1u) labs[L_S] = rootof[static_cast<uint32_t>(12 + (lane >> 3)) * 32u + piece(L, 31)];
-        if ((T.XW >> lane) & 1u) labs[L_W] = rootof[static_cast<uint32_t>((lane >> 3) * 4) * 32u + piece(PW, lane)];
-        if ((T.XE >> lane) & 1u) labs[L_E] = rootof[static_cast<uint32_t>((lane >> 3) * 4 + 3) * 32u + piece(PE, lane)];
+        uint32_t const st_w = lab_shfl(st, 0), st_e = lab_shfl(st, 31); // W / E slots: lane = cell row, columns 0 / 31
+        if ((T.XN >> lane) & 1u) labs[L_N] = parent[lane];
+        if ((T.XS >> lane) & 1u) labs[L_S] = parent[run_of(st, 31) * 32 + lane];
+        if ((T.XW >> lane) & 1u) labs[L_W] = parent[run_of(st_w, lane) * 32];
+        if ((T.XE >> lane) & 1u) labs[L_E] = parent[run_of(st_e, lane) * 32 + 31];
     }
     uint32_t root_label[2] = {0xFFFFu, 0xFFFFu};
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-        if (root_sid[q] != 0xFFFFu) {
-            root_label[q] = rootof[root_sid[q]];
-        }
-    }
-    if (root_tile && lane == 0) {
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            if (roots.n > q && roots.tile[q] == t) lab_st_volatile(&tc->lat_root_label[q], root_label[q]);
+        if (roots.n > q && roots.tile[q] == t) { // (uniform)
+            uint32_t const st_r = lab_shfl(st, roots.col[q]);
+            root_label[q] = parent[run_of(st_r, roots.row[q]) * 32 + roots.col[q]];
+            if (lane == 0) lab_st_volatile(&tc->lat_root_label[q], root_label[q]);
         }
     }
     // first[side][component]: the component's first slot on that side in clockwise order (0xFF: none)
@@ -464,7 +377,7 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
             bool const ascending = s == L_N || s == L_E;
             int const lead = ascending ? lab_ffs32(peers[s]) - 1 : 31 - lab_clz32(peers[s]);
             if (lead == lane) {
-                first[s * 512 + labs[s]] = static_cast<uint8_t>(lane);
+                first[s * 1024 + labs[s]] = static_cast<uint8_t>(lane);
             }
         }
     }
@@ -476,7 +389,7 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
     for (int q = 0; q < 2; q++) {
         if (root_label[q] != 0xFFFFu) {
             for (int s = 3; s >= 0; s--) {
-                uint32_t const f = first[s * 512 + root_label[q]];
+                uint32_t const f = first[s * 1024 + root_label[q]];
                 if (f != 0xFFu) root_first[q] = static_cast<uint32_t>(s) * LC + f;
             }
         }
@@ -497,7 +410,7 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
 #pragma unroll
                 for (int d = 1; d <= 4; d++) {
                     int const s2 = (s + d) & 3;
-                    uint32_t const f = first[s2 * 512 + lab];
+                    uint32_t const f = first[s2 * 1024 + lab];
                     if (nslot == L_NONE && f != 0xFFu) {
                         nslot = static_cast<uint32_t>(s2) * LC + f;
                     }
@@ -518,6 +431,13 @@ LAB_DEV void lat_link_tile(Params const &p, Lattice const &lt, uint32_t t, int l
         lt.label[static_cast<long long>(t) * LSLOTS + s * LC + lane] = static_cast<uint16_t>(lab);
     }
     lab_syncwarp();
+#pragma unroll
+    for (int s = 0; s < 4; s++) { // `first` back to all 0xFF for the warp's next tile
+        if (labs[s] != 0xFFFFu) {
+            first[s * 1024 + labs[s]] = 0xFFu;
+        }
+    }
+    lab_syncwarp();
 }
 
 LAB_DEV void lat_link_body(Params const &p, Lattice const &lt, int lane, uint32_t *sm) {
@@ -525,6 +445,11 @@ LAB_DEV void lat_link_body(Params const &p, Lattice const &lt, int lane, uint32_
         return;
     }
     uint32_t arcs = 0;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        sm[512 + k * 32 + lane] = 0xFFFFFFFFu; // lat_link_tile's `first`
+    }
+    lab_syncwarp();
     for (;;) {
         uint32_t t = 0;
         if (lane == 0) {
@@ -964,50 +889,42 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
     for (int s = 0; s < 4; s++) {
         em[s] = lab_ld_cg(lt.emask + static_cast<long long>(t) * 4 + s);
     }
-    // shared memory: entry depth per component [512] | component of a piece [512 x 16 bit] | entry depth per piece [512]
+    // shared memory: entry depth per component [1024] | component of every run [1024 x 16 bit] (lat_link_tile's cmap)
     uint32_t *ecomp = sm;
-    uint16_t *rootof = reinterpret_cast<uint16_t *>(sm + 512);
-    uint32_t *epiece = sm + 768;
+    uint16_t *comp_of = reinterpret_cast<uint16_t *>(sm + 1024);
+    {
+        uint32_t const *cm = reinterpret_cast<uint32_t const *>(lt.cmap + static_cast<long long>(t) * 1024);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            sm[1024 + k * 32 + lane] = lab_ld_cg(cm + k * 32 + lane);
+        }
+    }
     // entry depth of every component: minus the weights of the arcs later on the tour than its entry arc
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         if ((em[s] >> lane) & 1u) {
             uint32_t const lab = lab_ld_cg(lt.label + base + s * LC + lane);
-            ecomp[lab & 511u] = 0u - lat_prefix_below(lt, lab_ld_cg(lt.R + base + s * LC + lane));
+            ecomp[lab & 1023u] = 0u - lat_prefix_below(lt, lab_ld_cg(lt.R + base + s * LC + lane));
         }
     }
     Lat_roots const roots = lat_roots(p);
     if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-            if (roots.n > q && roots.tile[q] == t) ecomp[lt.tc->lat_root_label[q] & 511u] = 0u;
+            if (roots.n > q && roots.tile[q] == t) ecomp[lt.tc->lat_root_label[q] & 1023u] = 0u;
         }
     }
     uint32_t const off = roots.passage ? 1u : 0u; // a root on a passage: its two cells are at level 1
-    uint32_t const runs = lab_ld_cg(lt.nruns + t);
-    lab_syncwarp();
-    {
-        uint16_t const *cmap = lt.cmap + static_cast<long long>(t) * 512;
-        for (uint32_t idx = static_cast<uint32_t>(lane); idx < runs * 16u; idx += 32u) {
-            epiece[(idx & 15u) * 32u + (idx >> 4)] = ecomp[lab_ld_cg(cmap + idx) & 511u];
-        }
-    }
-    lab_syncwarp();
-    // Bit planes -> one word per cell: a 32 x 32 bit transpose in registers (rows 0-4 the piece number, 5-14 the depth)
+    // Depth planes -> one word per cell: a 32 x 32 bit transpose in registers (rows 0-9 the depth)
     uint32_t A[32];
     {
-        uint32_t const *pl = lt.lplane + static_cast<long long>(t) * (L_LABEL_PLANES * 32);
         uint32_t const *pd = lt.dplane + static_cast<long long>(t) * (L_DEPTH_PLANES * 32);
 #pragma unroll
-        for (int q = 0; q < L_LABEL_PLANES; q++) {
-            A[q] = lab_ld_cg(pl + q * 32 + lane);
-        }
-#pragma unroll
         for (int q = 0; q < L_DEPTH_PLANES; q++) {
-            A[L_LABEL_PLANES + q] = lab_ld_cg(pd + q * 32 + lane);
+            A[q] = lab_ld_cg(pd + q * 32 + lane);
         }
 #pragma unroll
-        for (int q = L_LABEL_PLANES + L_DEPTH_PLANES; q < 32; q++) {
+        for (int q = L_DEPTH_PLANES; q < 32; q++) {
             A[q] = 0;
         }
         uint32_t m = 0x0000FFFFu;
@@ -1022,14 +939,18 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
             m ^= m << (jj >> 1);
         }
     }
-    // lane = cell column j: its 32 cells' levels (INF: no cell)
+    lab_syncwarp();
+    // lane = cell column j: its 32 cells' levels (INF: no cell).  The cells of a vertical run share their component:
+    // its entry depth is looked up where a run begins (bit i of st, as in lat_link_tile)
     uint32_t lv[LC];
-    uint32_t const board_col = static_cast<uint32_t>(lane >> 3) * 32u;
+    uint32_t const st = T.C & ~(T.No & ~1u);
+    uint32_t e = 0;
 #pragma unroll
     for (int i = 0; i < LC; i++) {
-        uint32_t const sid = static_cast<uint32_t>((i >> 3) * 4) * 32u + board_col + (A[i] & 31u);
-        uint32_t const d = (A[i] >> L_LABEL_PLANES) & 1023u;
-        uint32_t const v = 2u * (epiece[sid] + d) + off;
+        if ((st >> i) & 1u) {
+            e = ecomp[comp_of[i * 32 + lane] & 1023u];
+        }
+        uint32_t const v = 2u * (e + (A[i] & 1023u)) + off;
         lv[i] = ((T.C >> i) & 1u) ? v : INF;
         mx = ((T.C >> i) & 1u) && v > mx ? v : mx;
     }

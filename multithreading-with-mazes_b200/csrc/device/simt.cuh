@@ -40,6 +40,7 @@ LAB_DEV uint64_t lab_ld_cg(uint64_t const *p) {
 }
 LAB_DEV uint32_t lab_ld_volatile(uint32_t const *p) { return *reinterpret_cast<uint32_t const volatile *>(p); }
 LAB_DEV uint64_t lab_ld_volatile(uint64_t const *p) { return *reinterpret_cast<uint64_t const volatile *>(p); }
+LAB_DEV uint16_t lab_ld_volatile(uint16_t const *p) { return *reinterpret_cast<uint16_t const volatile *>(p); }
 // read-only data (path masks): non-coherent path is fine
 LAB_DEV uint64_t lab_ld_ro(uint64_t const *p) {
     return static_cast<uint64_t>(__ldg(reinterpret_cast<unsigned long long const *>(p)));
@@ -79,6 +80,7 @@ LAB_DEV lab_u32x2 lab_ld_cg_x2(uint32_t const *base, uint32_t i) {
 LAB_DEV void lab_st_x2(uint32_t *base, uint32_t i, uint32_t x, uint32_t y) { reinterpret_cast<uint2 *>(base)[i] = make_uint2(x, y); }
 LAB_DEV void lab_st_pair(uint32_t *p, uint32_t x, uint32_t y) { *reinterpret_cast<uint2 *>(p) = make_uint2(x, y); } // p on an 8-byte boundary
 LAB_DEV void lab_st_volatile(uint32_t *p, uint32_t v) { *reinterpret_cast<uint32_t volatile *>(p) = v; }
+LAB_DEV void lab_st_volatile(uint16_t *p, uint16_t v) { *reinterpret_cast<uint16_t volatile *>(p) = v; }
 
 LAB_DEV uint32_t lab_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 LAB_DEV uint64_t lab_atomic_add(uint64_t *p, uint64_t v) {

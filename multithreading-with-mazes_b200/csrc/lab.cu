@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) k_tree_finish_jump(Params p, Tree tr) {
     tree_finish_jump_body(p, tr, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
 }
 // ---- the lattice road (device/lattice.cuh) ----
-__global__ void __launch_bounds__(128) k_lat_link(Params p, Lattice lt) {
+__global__ void __launch_bounds__(128, 8) k_lat_link(Params p, Lattice lt) {
     __shared__ uint32_t sm[4][L_LINK_SM];
     lat_link_body(p, lt, lane_id(), sm[threadIdx.x >> 5]);
 }
@@ -703,9 +703,7 @@ int ensure_lattice(lab_grid *h) {
     CU(cudaMalloc(&lt.xmask, nt * 4 * sizeof(uint32_t)));
     CU(cudaMalloc(&lt.outslot, nt * LSLOTS));
     CU(cudaMalloc(&lt.label, nt * LSLOTS * sizeof(uint16_t)));
-    CU(cudaMalloc(&lt.cmap, nt * 512 * sizeof(uint16_t)));
-    CU(cudaMalloc(&lt.nruns, nt * sizeof(uint32_t)));
-    CU(cudaMalloc(&lt.lplane, nt * L_LABEL_PLANES * 32 * sizeof(uint32_t)));
+    CU(cudaMalloc(&lt.cmap, nt * 1024 * sizeof(uint16_t)));
     CU(cudaMalloc(&lt.xd, nt * LSLOTS * sizeof(uint64_t)));
     CU(cudaMalloc(&lt.gb, static_cast<size_t>(lt.nsuper) * LB * sizeof(uint64_t)));
     CU(cudaMalloc(&lt.R, nt * LSLOTS * sizeof(uint32_t)));
@@ -1135,7 +1133,7 @@ int lab_grid_destroy(lab_grid *h) {
     cudaFree(h->tree.tc);
     if (h->lat_alloc) {
         Lattice &lt = h->lat;
-        void *const arrays[] = {lt.mask, lt.xmask, lt.outslot, lt.label, lt.cmap, lt.nruns, lt.lplane, lt.xd, lt.gb, lt.R, lt.dplane, lt.emask, lt.wsum, lt.chunk};
+        void *const arrays[] = {lt.mask, lt.xmask, lt.outslot, lt.label, lt.cmap, lt.xd, lt.gb, lt.R, lt.dplane, lt.emask, lt.wsum, lt.chunk};
         for (void *a : arrays) {
             cudaFree(a);
         }

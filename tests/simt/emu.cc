@@ -60,13 +60,12 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
         lt.sup_x = (w.g.tiles_x + LST - 1) / LST;
         lt.nsuper = lt.sup_y * lt.sup_x;
         lt.nslots = static_cast<uint32_t>(nt * LSLOTS);
-        std::vector<uint32_t> mask(nt * 96, 0xDEADBEEFu), xmask(nt * 4), lplane(nt * L_LABEL_PLANES * 32), R(nt * LSLOTS, 0xDEADBEEFu),
+        std::vector<uint32_t> mask(nt * 96, 0xDEADBEEFu), xmask(nt * 4), R(nt * LSLOTS, 0xDEADBEEFu),
             dplane(nt * L_DEPTH_PLANES * 32), emask(nt * 4), wsum(nt * LSLOTS + 2 + L_CHUNK, 0xDEADBEEFu), chunk(nt * LSLOTS / L_CHUNK + 2);
-        std::vector<uint16_t> label(nt * LSLOTS), cmap(nt * 512, 0xDEAD);
+        std::vector<uint16_t> label(nt * LSLOTS), cmap(nt * 1024, 0xDEAD);
         std::vector<uint8_t> outslot(nt * LSLOTS, 0xAB);
-        std::vector<uint32_t> nruns_v(nt);
         std::vector<uint64_t> xd(nt * LSLOTS, 0xDEADBEEFDEADBEEFull), gb(static_cast<size_t>(lt.nsuper) * LB, 0xDEADBEEFDEADBEEFull);
-        lt.mask = mask.data(); lt.xmask = xmask.data(); lt.outslot = outslot.data(); lt.label = label.data(); lt.cmap = cmap.data(); lt.nruns = nruns_v.data(); lt.lplane = lplane.data();
+        lt.mask = mask.data(); lt.xmask = xmask.data(); lt.outslot = outslot.data(); lt.label = label.data(); lt.cmap = cmap.data();
         lt.xd = xd.data(); lt.gb = gb.data(); lt.R = R.data(); lt.dplane = dplane.data(); lt.emask = emask.data(); lt.wsum = wsum.data();
         lt.chunk = chunk.data();
         lt.tc = &tc;
@@ -268,7 +267,7 @@ struct Emu_band {
     Lattice lat{};
     Tree_ctl lat_tc{};
     std::vector<uint8_t> l_outslot;
-    std::vector<uint32_t> l_mask, l_xmask, l_lplane, l_R, l_dplane, l_emask, l_nruns, l_sm;
+    std::vector<uint32_t> l_mask, l_xmask, l_R, l_dplane, l_emask, l_sm;
     std::vector<uint16_t> l_label, l_cmap;
     std::vector<uint64_t> l_xd;
 };
@@ -627,9 +626,7 @@ int emu_band_lat_bind(void *h, int super_row_base, int super_rows_band, int supe
     e->l_xmask.assign(nt * 4, 0);
     e->l_outslot.assign(nt * LSLOTS, 0xAB);
     e->l_label.assign(nt * LSLOTS, 0);
-    e->l_cmap.assign(nt * 512, 0xDEAD);
-    e->l_nruns.assign(nt, 0);
-    e->l_lplane.assign(nt * L_LABEL_PLANES * 32, 0);
+    e->l_cmap.assign(nt * 1024, 0xDEAD);
     e->l_xd.assign(nt * LSLOTS, 0xDEADBEEFDEADBEEFull);
     e->l_R.assign(nt * LSLOTS, 0xDEADBEEFu);
     e->l_dplane.assign(nt * L_DEPTH_PLANES * 32, 0);
@@ -638,7 +635,7 @@ int emu_band_lat_bind(void *h, int super_row_base, int super_rows_band, int supe
     Lattice &lt = e->lat;
     lt = Lattice{};
     lt.mask = e->l_mask.data(); lt.xmask = e->l_xmask.data(); lt.outslot = e->l_outslot.data(); lt.label = e->l_label.data(); lt.cmap = e->l_cmap.data();
-    lt.nruns = e->l_nruns.data(); lt.lplane = e->l_lplane.data(); lt.xd = e->l_xd.data(); lt.R = e->l_R.data(); lt.dplane = e->l_dplane.data();
+    lt.xd = e->l_xd.data(); lt.R = e->l_R.data(); lt.dplane = e->l_dplane.data();
     lt.emask = e->l_emask.data();
     lt.tc = &e->lat_tc;
     lt.sup_x = (g.tiles_x + LST - 1) / LST;
