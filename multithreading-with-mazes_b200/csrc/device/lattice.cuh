@@ -32,6 +32,7 @@
 // nothing has been written to the level field and the general pipeline (tree.cuh), then the tile wave
 // (engine.cuh), take over.  Results are bit-identical on all three roads (tests/test_lattice.py).
 #pragma once
+#include "post.cuh"
 #include "tree.cuh"
 
 namespace lab {
@@ -47,7 +48,6 @@ constexpr uint32_t LB = 4u * LST * LC;                  // border slots of a sup
 constexpr uint32_t LSUP_SLOTS = LST * LST * LSLOTS;     // slots of a super-tile (8192: 13-bit local index)
 constexpr int L_DEPTH_PLANES = 10;                          // a cell's depth below its component's entry, bit-sliced
 constexpr uint32_t L_LINK_SM = 1536;                    // words of shared memory per warp: lat_link_tile, lat_levels_tile
-constexpr bool L_PAIR_STORES = false;                   // 8-byte stores of the level rows (see lat_levels_tile)
 constexpr uint32_t L_CHUNK = 1024;                      // tour positions per scan chunk
 
 struct Lattice {
@@ -450,14 +450,17 @@ LAB_DEV void lat_link_body(Params const &p, Lattice const &lt, int lane, uint32_
         sm[512 + k * 32 + lane] = 0xFFFFFFFFu; // lat_link_tile's `first`
     }
     lab_syncwarp();
+    uint32_t next = 0; // (the ticket after this one is asked for before the tile is worked on: its round trip is hidden)
+    if (lane == 0) {
+        next = lab_atomic_add(&lt.tc->lat_ticket[0], 1u);
+    }
     for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) {
-            t = lab_atomic_add(&lt.tc->lat_ticket[0], 1u);
-        }
-        t = lab_shfl(t, 0);
+        uint32_t const t = lab_shfl(next, 0);
         if (t >= static_cast<uint32_t>(p.g.ntiles)) {
             break;
+        }
+        if (lane == 0) {
+            next = lab_atomic_add(&lt.tc->lat_ticket[0], 1u);
         }
         lat_link_tile(p, lt, t, lane, sm, arcs);
     }
@@ -584,14 +587,17 @@ LAB_DEV void lat_rank_local_body(Params const &p, Lattice const &lt, int lane, u
     if (!lat_live(lt.tc)) {
         return;
     }
+    uint32_t next = 0; // (the ticket after this one is asked for before the tile is worked on: its round trip is hidden)
+    if (lane == 0) {
+        next = lab_atomic_add(&lt.tc->lat_ticket[1], 1u);
+    }
     for (;;) {
-        uint32_t S = 0;
-        if (lane == 0) {
-            S = lab_atomic_add(&lt.tc->lat_ticket[1], 1u);
-        }
-        S = lab_shfl(S, 0);
+        uint32_t const S = lab_shfl(next, 0);
         if (S >= static_cast<uint32_t>(lt.nsuper)) {
             break;
+        }
+        if (lane == 0) {
+            next = lab_atomic_add(&lt.tc->lat_ticket[1], 1u);
         }
         lat_rank_local_super(p, lt, S, lane, sm);
     }
@@ -782,14 +788,17 @@ LAB_DEV void lat_flood_body(Params const &p, Lattice const &lt, int lane) {
     }
     unsigned long long settled = 0;
     uint32_t bad = 0;
+    uint32_t next = 0; // (the ticket after this one is asked for before the tile is worked on: its round trip is hidden)
+    if (lane == 0) {
+        next = lab_atomic_add(&tc->lat_ticket[2], 1u);
+    }
     for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) {
-            t = lab_atomic_add(&tc->lat_ticket[2], 1u);
-        }
-        t = lab_shfl(t, 0);
+        uint32_t const t = lab_shfl(next, 0);
         if (t >= static_cast<uint32_t>(p.g.ntiles)) {
             break;
+        }
+        if (lane == 0) {
+            next = lab_atomic_add(&tc->lat_ticket[2], 1u);
         }
         lat_flood_tile(p, lt, t, lane, settled, bad);
     }
@@ -880,8 +889,115 @@ LAB_DEV uint32_t lat_prefix_below(Lattice const &lt, uint32_t r) {
 
 // ---------------------------------------------------------------------------------------------
 // 5 levels.  Warp per tile; sm: L_LINK_SM words.
-LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int lane, uint32_t *sm, uint32_t &mx) {
+// What lat_levels_tile does with a tile's levels: LAT_LEVELS writes them; LAT_PAINT also applies the solvers' paint rules
+// to the Squares on the way (the field is in registers: k_paint's second pass over it, 4 B read per square, is saved);
+// LAT_PROBE writes nothing and only takes the level of one square (the solvers' finishes: the paint rules come from them).
+enum Lat_mode : int { LAT_LEVELS = 0, LAT_PAINT = 1, LAT_PROBE = 2 };
+struct Lat_paint { // resolve_body's rules (post.cuh), all on field 0
+    uint32_t n;
+    uint32_t below[4], bits[4];
+    uint16_t *grid;
+};
+// rows of squares: row 2i = [pillar, N passage of cell (i, j)], row 2i+1 = [W passage of cell (i, j), cell (i, j)];
+// lane j has columns 2j, 2j+1.  A passage lies one below the deeper of its two cells; across the tile's border the
+// deeper one is this cell iff the crossing is its component's entry.  FULL: the tile lies inside the maze (no bounds
+// to check); the pair (pillar, N passage) of an even row starts on an 8-byte boundary (cols is odd): one 8-byte store.
+template <int MODE, bool FULL>
+LAB_DEV void lat_emit_rows(Geom const &g, Lat_tile const &T, uint32_t const (&lv)[LC], uint32_t emW, bool entryN, int lane, int ty, int tx, uint32_t *dist,
+                           Lat_paint const &pr, uint32_t &painted, int probe_r, int probe_c, uint32_t &probe_out) {
+    long long const c0 = static_cast<long long>(tx) * TS + 2 * lane, r_base = static_cast<long long>(ty) * TS;
+    bool const in0 = FULL || c0 < g.cols, in1 = FULL || c0 + 1 < g.cols;
+    long long at = r_base * g.cols + c0; // square (row 2i, column c0)
+    bool const pairs = FULL && (reinterpret_cast<uintptr_t>(dist) & 7u) == 0; // (a caller's field may start anywhere)
+    auto bits_of = [&](uint32_t v) {
+        uint32_t b = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            b |= (static_cast<uint32_t>(k) < pr.n && v < pr.below[k]) ? pr.bits[k] : 0u;
+        }
+        return b;
+    };
+    // LAT_PAINT: four cell rows at a time -- their levels are stored, then ALL their Squares that get paint are loaded, then
+    // all are stored (a load / store pair per square one after the other leaves one DRAM round trip per square on the
+    // warp's critical path: the compiler cannot move a load above the store before it)
+    constexpr int G = 4;
+#pragma unroll
+    for (int i0 = 0; i0 < LC; i0 += G) {
+        uint32_t pb[3 * G];
+        long long const at0 = at;
+#pragma unroll
+        for (int ii = 0; ii < G; ii++) {
+            int const i = i0 + ii;
+            uint32_t const me = lv[i];
+            uint32_t const left_in = lab_shfl_up(me, 1);
+            uint32_t const up = i ? lv[i ? i - 1 : 0] : (entryN ? me : me + 2u);
+            uint32_t const left = lane ? left_in : (((emW >> i) & 1u) ? me : me + 2u);
+            uint32_t const np = ((T.No >> i) & 1u) ? (me > up ? me : up) - 1u : INF;
+            uint32_t const wp = ((T.Wo >> i) & 1u) ? (me > left ? me : left) - 1u : INF;
+            if (MODE == LAT_PROBE) {
+                if (lane == (probe_c >> 1)) {
+                    if (probe_r == 2 * i) probe_out = (probe_c & 1) ? np : INF;
+                    if (probe_r == 2 * i + 1) probe_out = (probe_c & 1) ? me : wp;
+                }
+                continue;
+            }
+            bool const ok0 = FULL || r_base + 2 * i < g.rows, ok1 = FULL || r_base + 2 * i + 1 < g.rows;
+            if (ok0) {
+                if (pairs) {
+                    lab_st_pair(dist + at, INF, np);
+                } else {
+                    if (in0) dist[at] = INF;
+                    if (in1) dist[at + 1] = np;
+                }
+            }
+            if (ok1) {
+                long long const at1 = at + g.cols;
+                if (in0) dist[at1] = wp;
+                if (in1) dist[at1 + 1] = me;
+            }
+            if (MODE == LAT_PAINT) {
+                pb[3 * ii] = ok0 && in1 ? bits_of(np) : 0u;
+                pb[3 * ii + 1] = ok1 && in0 ? bits_of(wp) : 0u;
+                pb[3 * ii + 2] = ok1 && in1 ? bits_of(me) : 0u;
+            }
+            at += 2 * static_cast<long long>(g.cols);
+        }
+        if (MODE == LAT_PAINT) {
+            uint16_t pv[3 * G];
+#pragma unroll
+            for (int ii = 0; ii < G; ii++) {
+                long long const a0 = at0 + 2 * static_cast<long long>(g.cols) * ii, a1 = a0 + g.cols;
+                pv[3 * ii] = pb[3 * ii] ? pr.grid[a0 + 1] : static_cast<uint16_t>(0);
+                pv[3 * ii + 1] = pb[3 * ii + 1] ? pr.grid[a1] : static_cast<uint16_t>(0);
+                pv[3 * ii + 2] = pb[3 * ii + 2] ? pr.grid[a1 + 1] : static_cast<uint16_t>(0);
+            }
+#pragma unroll
+            for (int ii = 0; ii < G; ii++) {
+                long long const a0 = at0 + 2 * static_cast<long long>(g.cols) * ii, a1 = a0 + g.cols;
+                if (pb[3 * ii]) pr.grid[a0 + 1] = static_cast<uint16_t>(pv[3 * ii] | pb[3 * ii]);
+                if (pb[3 * ii + 1]) pr.grid[a1] = static_cast<uint16_t>(pv[3 * ii + 1] | pb[3 * ii + 1]);
+                if (pb[3 * ii + 2]) pr.grid[a1 + 1] = static_cast<uint16_t>(pv[3 * ii + 2] | pb[3 * ii + 2]);
+                painted += (pb[3 * ii] ? 1u : 0u) + (pb[3 * ii + 1] ? 1u : 0u) + (pb[3 * ii + 2] ? 1u : 0u);
+            }
+        }
+    }
+}
+template <int MODE>
+LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int lane, uint32_t *sm, uint32_t &mx, Lat_paint const &pr, uint32_t &painted,
+                             int probe_r, int probe_c, uint32_t &probe_out) {
     Geom const &g = p.g;
+    if (MODE == LAT_PAINT) { // the tile's Squares are read in a while: lane j asks for its two rows now (128 bytes each, on any boundary)
+        long long const c_first = static_cast<long long>(t % static_cast<uint32_t>(g.tiles_x)) * TS;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            long long const r = static_cast<long long>(t / static_cast<uint32_t>(g.tiles_x)) * TS + 2 * lane + q;
+            if (r < g.rows) {
+                uint16_t const *row = pr.grid + r * g.cols + c_first;
+                lab_prefetch_l2(row);
+                if (c_first + TS - 1 < g.cols) lab_prefetch_l2(row + TS - 1);
+            }
+        }
+    }
     Lat_tile const T = lat_load(lt, t, lane);
     long long const base = static_cast<long long>(t) * LSLOTS;
     uint32_t em[4];
@@ -954,84 +1070,93 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
         lv[i] = ((T.C >> i) & 1u) ? v : INF;
         mx = ((T.C >> i) & 1u) && v > mx ? v : mx;
     }
-    // rows of squares: row 2i = [pillar, N passage of cell (i, j)], row 2i+1 = [W passage of cell (i, j), cell (i, j)];
-    // lane j writes columns 2j, 2j+1.  A passage lies one below the deeper of its two cells; across the tile's
-    // border the deeper one is this cell iff the crossing is its component's entry.
     int const ty = static_cast<int>(t / static_cast<uint32_t>(g.tiles_x)), tx = static_cast<int>(t % static_cast<uint32_t>(g.tiles_x));
-    long long const c0 = static_cast<long long>(tx) * TS + 2 * lane;
-    bool const in0 = c0 < g.cols, in1 = c0 + 1 < g.cols;
     uint32_t *dist = p.plane[0].dist;
     bool const entryN = (em[L_N] >> lane) & 1u;
-    // (measured on B200 at 32767^2: the 8-byte variant below is SLOWER than plain 4-byte stores, 1.78 ms against 1.50 ms;
-    // kept switchable for the profile's sake)
-    bool const pairs_ok = L_PAIR_STORES && (reinterpret_cast<uintptr_t>(dist) & 7u) == 0; // (a caller's field may start anywhere)
-#pragma unroll
-    for (int i = 0; i < LC; i++) {
-        long long const r0 = static_cast<long long>(ty) * TS + 2 * i;
-        uint32_t const me = lv[i];
-        uint32_t const left = lab_shfl_up(me, 1);
-        uint32_t np = INF, wp = INF;
-        if ((T.No >> i) & 1u) {
-            np = i ? (me > lv[i ? i - 1 : 0] ? me : lv[i ? i - 1 : 0]) - 1u : (entryN ? me - 1u : me + 1u);
-        }
-        if ((T.Wo >> i) & 1u) {
-            wp = lane ? (me > left ? me : left) - 1u : (((em[L_W] >> i) & 1u) ? me - 1u : me + 1u);
-        }
-        // 8-byte stores: cols is odd, so in an even row the pair (c0, c0 + 1) starts on an 8-byte boundary and in an odd
-        // row the pair (c0 - 1, c0) does -- the cell of the lane to the left and this lane's W passage
-        if (r0 < g.rows) {
-            uint32_t *row = dist + r0 * g.cols + c0;
-            if (pairs_ok && in1) {
-                lab_st_pair(row, INF, np);
-            } else {
-                if (in0) row[0] = INF;
-                if (in1) row[1] = np;
-            }
-        }
-        if (r0 + 1 < g.rows) {
-            uint32_t *row = dist + (r0 + 1) * g.cols + c0;
-            if (pairs_ok) {
-                if (lane && in0) {
-                    lab_st_pair(row - 1, left, wp);
-                } else if (lane && c0 - 1 < g.cols) {
-                    row[-1] = left;
-                }
-                if (lane == 0 && in0) row[0] = wp;
-                if (lane == 31 && in1) row[1] = me;
-            } else {
-                if (in0) row[0] = wp;
-                if (in1) row[1] = me;
-            }
-        }
+    bool const full = static_cast<long long>(ty + 1) * TS <= g.rows && static_cast<long long>(tx + 1) * TS <= g.cols;
+    if (full) {
+        lat_emit_rows<MODE, true>(g, T, lv, em[L_W], entryN, lane, ty, tx, dist, pr, painted, probe_r, probe_c, probe_out);
+    } else {
+        lat_emit_rows<MODE, false>(g, T, lv, em[L_W], entryN, lane, ty, tx, dist, pr, painted, probe_r, probe_c, probe_out);
     }
     lab_syncwarp(); // (the rows' INF at the root passage was another lane's store)
-    if (roots.passage && roots.ptile == t && lane == roots.pj) {
-        long long const r = static_cast<long long>(ty) * TS + 2 * roots.pi + (roots.horizontal ? 1 : 0);
-        long long const c = static_cast<long long>(tx) * TS + 2 * roots.pj + (roots.horizontal ? 0 : 1);
-        dist[r * g.cols + c] = 0u;
+    if (roots.passage && roots.ptile == t && lane == roots.pj) { // the root passage itself: level 0
+        int const lr = 2 * roots.pi + (roots.horizontal ? 1 : 0), lc = 2 * roots.pj + (roots.horizontal ? 0 : 1);
+        long long const sq = (static_cast<long long>(ty) * TS + lr) * g.cols + static_cast<long long>(tx) * TS + lc;
+        if (MODE == LAT_PROBE) {
+            if (probe_r == lr && probe_c == lc) probe_out = 0u;
+        } else {
+            dist[sq] = 0u;
+            if (MODE == LAT_PAINT) {
+                uint32_t b = 0;
+                for (uint32_t k = 0; k < pr.n; k++) {
+                    b |= 0u < pr.below[k] ? pr.bits[k] : 0u;
+                }
+                if (b) {
+                    pr.grid[sq] = static_cast<uint16_t>(pr.grid[sq] | b);
+                    painted++;
+                }
+            }
+        }
     }
     lab_syncwarp();
 }
-LAB_DEV void lat_levels_body(Params const &p, Lattice const &lt, int lane, uint32_t *sm) {
+template <int MODE> LAB_DEV void lat_levels_body(Params const &p, Lattice const &lt, int lane, uint32_t *sm, Result *res, uint16_t *grid) {
     Tree_ctl *tc = lt.tc;
     if (!lat_live(tc)) {
         return;
     }
-    uint32_t mx = 0;
-    for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) {
-            t = lab_atomic_add(&tc->lat_ticket[3], 1u);
+    Lat_paint pr{};
+    if (MODE == LAT_PAINT) {
+        pr.n = res->n_rules;
+        for (int k = 0; k < 4; k++) {
+            pr.below[k] = res->rule[k].below;
+            pr.bits[k] = res->rule[k].bits;
         }
-        t = lab_shfl(t, 0);
+        pr.grid = grid;
+    }
+    uint32_t mx = 0, painted = 0, unused = 0;
+    uint32_t next = 0; // (the ticket after this one is asked for before the tile is worked on: its round trip is hidden)
+    if (lane == 0) {
+        next = lab_atomic_add(&tc->lat_ticket[3], 1u);
+    }
+    for (;;) {
+        uint32_t const t = lab_shfl(next, 0);
         if (t >= static_cast<uint32_t>(p.g.ntiles)) {
             break;
         }
-        lat_levels_tile(p, lt, t, lane, sm, mx);
+        if (lane == 0) {
+            next = lab_atomic_add(&tc->lat_ticket[3], 1u);
+        }
+        lat_levels_tile<MODE>(p, lt, t, lane, sm, mx, pr, painted, 0, 0, unused);
     }
     mx = lab_reduce_max(mx);
     if (lane == 0 && mx) {
         lab_atomic_max(&p.ctl->max_level, mx);
+    }
+    if (MODE == LAT_PAINT) {
+        painted = lab_reduce_add(painted);
+        if (lane == 0 && painted) {
+            lab_atomic_add(reinterpret_cast<uint64_t *>(&res->settled), static_cast<uint64_t>(painted));
+        }
+    }
+}
+// The solvers' finishes: warp j takes finish j's level out of its tile (nothing is written to the field), then one
+// thread runs resolve_body on them: the paint rules are known BEFORE the levels are written, so lat_levels_body<LAT_PAINT>
+// can apply them on the way (Control::painted tells paint_body that it has been done).
+LAB_DEV void lat_targets_body(Params const &p, Lattice const &lt, int warp, int lane, uint32_t *sm) {
+    Control *ctl = p.ctl;
+    if (!lat_live(lt.tc) || static_cast<uint32_t>(warp) >= ctl->n_targets) {
+        return;
+    }
+    unsigned long long const cell = ctl->target_cell[warp];
+    int const r = static_cast<int>(cell / static_cast<unsigned long long>(p.g.cols)), c = static_cast<int>(cell % static_cast<unsigned long long>(p.g.cols));
+    uint32_t const t = static_cast<uint32_t>((r / TS) * p.g.tiles_x + c / TS);
+    uint32_t mx = 0, painted = 0, out = INF;
+    Lat_paint const none{};
+    lat_levels_tile<LAT_PROBE>(p, lt, t, lane, sm, mx, none, painted, r % TS, c % TS, out);
+    if (lane == ((c % TS) >> 1)) {
+        ctl->target_val[warp] = out;
     }
 }
 

@@ -258,6 +258,9 @@ LAB_DEV void resolve_body(Params p, Run_desc d, Result *res, int32_t const *fini
 // Elementwise: OR each rule's bits into the squares whose level in the rule's field is below the
 // rule's threshold; counts the squares that received any bit into res->settled.
 LAB_DEV void paint_body(Params p, uint16_t *grid, Result *res, long long gthread, long long nthreads) {
+    if (p.ctl->painted) { // lat_levels_body<LAT_PAINT> applied the rules on its way
+        return;
+    }
     long long const n = static_cast<long long>(p.g.rows) * p.g.cols;
     uint32_t const nr = res->n_rules;
     Paint_rule r[4];

@@ -226,9 +226,19 @@ __global__ void __launch_bounds__(256) k_lat_rank_expand(Lattice lt) {
 __global__ void __launch_bounds__(128) k_lat_flood(Params p, Lattice lt) { lat_flood_body(p, lt, lane_id()); }
 __global__ void __launch_bounds__(256) k_lat_scan_chunks(Lattice lt) { lat_scan_chunks_body(lt, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void k_lat_scan_tops(Lattice lt) { lat_scan_tops_body(lt, lane_id()); }
-__global__ void __launch_bounds__(128) k_lat_levels(Params p, Lattice lt) {
+template <int MODE> __global__ void __launch_bounds__(128, MODE == LAT_PAINT ? 6 : 8) k_lat_levels(Params p, Lattice lt, Result *res, uint16_t *grid) {
     __shared__ uint32_t sm[4][L_LINK_SM];
-    lat_levels_body(p, lt, lane_id(), sm[threadIdx.x >> 5]);
+    lat_levels_body<MODE>(p, lt, lane_id(), sm[threadIdx.x >> 5], res, grid);
+}
+// hunt / gather on the lattice road: the finishes' levels and the paint rules BEFORE the field is written (lat_targets_body)
+__global__ void __launch_bounds__(128) k_lat_targets(Params p, Lattice lt, Run_desc d, Result *res, int32_t const *finish_rc) {
+    __shared__ uint32_t sm[4][L_LINK_SM];
+    lat_targets_body(p, lt, static_cast<int>(threadIdx.x >> 5), lane_id(), sm[threadIdx.x >> 5]);
+    __syncthreads();
+    if (threadIdx.x == 0 && lat_live(lt.tc)) {
+        resolve_body(p, d, res, finish_rc);
+        p.ctl->painted = 1u;
+    }
 }
 __global__ void k_lat_band_open(Lattice lt) { lat_band_open_body(lt); }
 __global__ void k_lat_band_header(Lattice lt, uint32_t *hdr) { lat_band_header_body(lt, hdr); }
@@ -725,7 +735,7 @@ int ensure_lattice(lab_grid *h) {
 // The lattice road (device/lattice.cuh), tried before the general pipeline on mazes that can be lattices: odd
 // sizes, the start on an (odd, odd) square.  Whether the maze IS one is decided on the device, kernel by kernel;
 // after a failure the remaining launches return at once and nothing has been written.
-int run_lattice(lab_grid *h, Params const &p) {
+int run_lattice(lab_grid *h, Params const &p, Run_desc const &d) {
     int const rc = ensure_lattice(h);
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -766,7 +776,16 @@ int run_lattice(lab_grid *h, Params const &p) {
     k_lat_scan_tops<<<1, 32, 0, s>>>(lt);
     TRACE("k_lat_scan_tops", s);
     mark();
-    k_lat_levels<<<tile_blocks, 128, 0, s>>>(p, lt);
+    // hunt / gather: the paint rules are applied while the levels are written (k_paint then returns at once)
+    bool const fuse_paint = (d.game == GAME_HUNT || d.game == GAME_GATHER) && env_ll("LAB_LAT_FUSE_PAINT", 1) != 0;
+    if (fuse_paint) {
+        k_lat_targets<<<1, 128, 0, s>>>(p, lt, d, h->res, h->d_finish_rc);
+        TRACE("k_lat_targets", s);
+        k_lat_levels<LAT_PAINT><<<tile_blocks, 128, 0, s>>>(p, lt, h->res, h->squares);
+        h->launches += 1;
+    } else {
+        k_lat_levels<LAT_LEVELS><<<tile_blocks, 128, 0, s>>>(p, lt, nullptr, nullptr);
+    }
     TRACE("k_lat_levels", s);
     mark();
     h->launches += 8;
@@ -817,7 +836,7 @@ int run_tree(lab_grid *h, Run_desc const &d) {
     mark();
     k_tree_init<<<1, 1, 0, s>>>(p, tr);
     if (lat_try) {
-        rc = run_lattice(h, p);
+        rc = run_lattice(h, p, d);
         if (rc) return rc;
     }
     int const walk_blocks = std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * h->tree_walk_per_sm);
@@ -1891,7 +1910,7 @@ int lab_band_lat_levels(lab_grid *h, int32_t *used) {
     k_lat_scan_chunks<<<static_cast<int>(std::min<long long>((static_cast<long long>(lt.nslots_global) / L_CHUNK + 8) / 8, static_cast<long long>(h->sm_count) * 8)), 256, 0, s>>>(lt);
     k_lat_scan_tops<<<1, 32, 0, s>>>(lt);
     int const tile_blocks = static_cast<int>(std::min<long long>((h->g.ntiles + 3) / 4, static_cast<long long>(h->sm_count) * 16));
-    k_lat_levels<<<tile_blocks, 128, 0, s>>>(p, lt);
+    k_lat_levels<LAT_LEVELS><<<tile_blocks, 128, 0, s>>>(p, lt, nullptr, nullptr);
     k_lat_band_close<<<1, 1, 0, s>>>(lt);
     Tree tr{};
     tr.tc = lt.tc;

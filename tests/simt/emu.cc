@@ -30,10 +30,12 @@ struct Workspace {
 int g_tree_mode = 1;      // 0: never, 1: when the counts allow it (as csrc/lab.cu does)
 int g_lattice_mode = 1;   // 0: the general pipeline only, 1: the lattice road first (as csrc/lab.cu does)
 Tree_ctl g_tree_last{};
+int g_paint_fused = 0; // the last search applied the solvers' paint rules inside lat_levels_body
 
 // The spanning-tree pipeline, orchestrated as run_tree() in csrc/lab.cu does.
 void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned sched_seed) {
     g_tree_last = Tree_ctl{};
+    g_paint_fused = 0;
     if (d.nplanes != 1 || d.src_r[0] < 0 || !g_tree_mode) return;
     size_t const nt = static_cast<size_t>(w.g.ntiles);
     size_t const n = nt * SLOTS + 2;
@@ -83,7 +85,23 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
         simt::launch(nwarps, [&](int wid, int lane) { lat_flood_body(p, lt, lane); }, sched_seed);
         simt::launch(nwarps, [&](int wid, int lane) { lat_scan_chunks_body(lt, wid, nwarps, lane); });
         simt::launch(1, [&](int, int lane) { lat_scan_tops_body(lt, lane); });
-        simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS); }, sched_seed);
+        if (d.game == GAME_HUNT || d.game == GAME_GATHER) { // as run_lattice(): k_lat_targets, then the levels with the paint fused
+            int32_t frc[8] = {0};
+            for (int j = 0; j < d.n_targets; j++) {
+                frc[2 * j] = d.tgt_r[j];
+                frc[2 * j + 1] = d.tgt_c[j];
+            }
+            std::vector<uint32_t> tsm(4 * static_cast<size_t>(L_LINK_SM));
+            simt::launch(4, [&](int wid, int lane) { lat_targets_body(p, lt, wid, lane, tsm.data() + static_cast<size_t>(wid) * L_LINK_SM); });
+            if (lat_live(lt.tc)) {
+                resolve_body(p, d, &w.res, frc);
+                p.ctl->painted = 1u;
+                g_paint_fused = 1;
+            }
+            simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body<LAT_PAINT>(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS, &w.res, w.grid_ptr); }, sched_seed);
+        } else {
+            simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body<LAT_LEVELS>(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS, nullptr, nullptr); }, sched_seed);
+        }
     }
     size_t const SM = FLOOD_U64 > WALK_U64 ? FLOOD_U64 : WALK_U64;
     std::vector<uint64_t> sm(static_cast<size_t>(nwarps) * SM);
@@ -202,6 +220,7 @@ void emu_set_lattice(int mode) { g_lattice_mode = mode; }
 int emu_last_lattice_error(void) { return static_cast<int>(g_tree_last.lat_err); }
 // 0: the tile wave made the field; 1: the tree pipeline did
 int emu_last_tree_used(void) { return static_cast<int>(g_tree_last.used); }
+int emu_last_paint_fused(void) { return g_paint_fused; }
 
 int emu_distance(int rows, int cols, uint16_t *grid, int sr, int sc, uint32_t *dist_out, uint64_t *max_out,
                  uint64_t *settled_out, int nwarps, unsigned sched_seed, uint64_t *stats) {
@@ -702,7 +721,7 @@ int emu_band_lat_levels(void *h, int32_t *used) {
     lat_band_settled_body(lt);
     simt::launch(nw, [&](int wid, int lane) { lat_scan_chunks_body(lt, wid, nw, lane); });
     simt::launch(1, [&](int, int lane) { lat_scan_tops_body(lt, lane); });
-    simt::launch(nw, [&](int wid, int lane) { lat_levels_body(p, lt, lane, e->l_sm.data() + static_cast<size_t>(wid) * LSUP_SLOTS); }, e->sched);
+    simt::launch(nw, [&](int wid, int lane) { lat_levels_body<LAT_LEVELS>(p, lt, lane, e->l_sm.data() + static_cast<size_t>(wid) * LSUP_SLOTS, nullptr, nullptr); }, e->sched);
     lat_band_close_body(lt);
     Tree tr{};
     tr.tc = &e->lat_tc;

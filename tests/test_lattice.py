@@ -155,7 +155,7 @@ def test_emulated_games_on_the_lattice(lab, O, emu):
         placed, s, f = lab.place_hunt(maze, seed=seed)
         g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
         g, w, _, paths, _ = emu.solver(1, placed, [s], [f], 4, 1)
-        assert emu.lib.emu_last_tree_used() == LATTICE
+        assert emu.lib.emu_last_tree_used() == LATTICE and emu.lib.emu_last_paint_fused() == 1  # (paint rules applied by the levels kernel)
         seen.add((s[0] % 2, s[1] % 2))
         assert (g == g_ref).all() and w == w_ref and paths_equal([paths[0]], [p_ref])
     assert len(seen) >= 2  # starts on cells and on passages
@@ -163,6 +163,7 @@ def test_emulated_games_on_the_lattice(lab, O, emu):
         placed, s, fin = lab.place_gather(maze, seed=seed)
         g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
         g, _, c, paths, _ = emu.solver(2, placed, [s], fin, 4, 1)
+        assert emu.lib.emu_last_paint_fused() == 1
         assert (g == g_ref).all() and (c == c_ref).all() and paths_equal(paths, p_ref)
 
 
