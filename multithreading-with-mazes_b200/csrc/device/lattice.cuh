@@ -450,17 +450,14 @@ LAB_DEV void lat_link_body(Params const &p, Lattice const &lt, int lane, uint32_
         sm[512 + k * 32 + lane] = 0xFFFFFFFFu; // lat_link_tile's `first`
     }
     lab_syncwarp();
-    uint32_t next = 0; // (the ticket after this one is asked for before the tile is worked on: its round trip is hidden)
-    if (lane == 0) {
-        next = lab_atomic_add(&lt.tc->lat_ticket[0], 1u);
-    }
     for (;;) {
-        uint32_t const t = lab_shfl(next, 0);
+        uint32_t t = 0;
+        if (lane == 0) {
+            t = lab_atomic_add(&lt.tc->lat_ticket[0], 1u);
+        }
+        t = lab_shfl(t, 0);
         if (t >= static_cast<uint32_t>(p.g.ntiles)) {
             break;
-        }
-        if (lane == 0) {
-            next = lab_atomic_add(&lt.tc->lat_ticket[0], 1u);
         }
         lat_link_tile(p, lt, t, lane, sm, arcs);
     }
@@ -587,17 +584,14 @@ LAB_DEV void lat_rank_local_body(Params const &p, Lattice const &lt, int lane, u
     if (!lat_live(lt.tc)) {
         return;
     }
-    uint32_t next = 0; // (the ticket after this one is asked for before the tile is worked on: its round trip is hidden)
-    if (lane == 0) {
-        next = lab_atomic_add(&lt.tc->lat_ticket[1], 1u);
-    }
     for (;;) {
-        uint32_t const S = lab_shfl(next, 0);
+        uint32_t S = 0;
+        if (lane == 0) {
+            S = lab_atomic_add(&lt.tc->lat_ticket[1], 1u);
+        }
+        S = lab_shfl(S, 0);
         if (S >= static_cast<uint32_t>(lt.nsuper)) {
             break;
-        }
-        if (lane == 0) {
-            next = lab_atomic_add(&lt.tc->lat_ticket[1], 1u);
         }
         lat_rank_local_super(p, lt, S, lane, sm);
     }
@@ -788,17 +782,14 @@ LAB_DEV void lat_flood_body(Params const &p, Lattice const &lt, int lane) {
     }
     unsigned long long settled = 0;
     uint32_t bad = 0;
-    uint32_t next = 0; // (the ticket after this one is asked for before the tile is worked on: its round trip is hidden)
-    if (lane == 0) {
-        next = lab_atomic_add(&tc->lat_ticket[2], 1u);
-    }
     for (;;) {
-        uint32_t const t = lab_shfl(next, 0);
+        uint32_t t = 0;
+        if (lane == 0) {
+            t = lab_atomic_add(&tc->lat_ticket[2], 1u);
+        }
+        t = lab_shfl(t, 0);
         if (t >= static_cast<uint32_t>(p.g.ntiles)) {
             break;
-        }
-        if (lane == 0) {
-            next = lab_atomic_add(&tc->lat_ticket[2], 1u);
         }
         lat_flood_tile(p, lt, t, lane, settled, bad);
     }
@@ -986,18 +977,6 @@ template <int MODE>
 LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int lane, uint32_t *sm, uint32_t &mx, Lat_paint const &pr, uint32_t &painted,
                              int probe_r, int probe_c, uint32_t &probe_out) {
     Geom const &g = p.g;
-    if (MODE == LAT_PAINT) { // the tile's Squares are read in a while: lane j asks for its two rows now (128 bytes each, on any boundary)
-        long long const c_first = static_cast<long long>(t % static_cast<uint32_t>(g.tiles_x)) * TS;
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            long long const r = static_cast<long long>(t / static_cast<uint32_t>(g.tiles_x)) * TS + 2 * lane + q;
-            if (r < g.rows) {
-                uint16_t const *row = pr.grid + r * g.cols + c_first;
-                lab_prefetch_l2(row);
-                if (c_first + TS - 1 < g.cols) lab_prefetch_l2(row + TS - 1);
-            }
-        }
-    }
     Lat_tile const T = lat_load(lt, t, lane);
     long long const base = static_cast<long long>(t) * LSLOTS;
     uint32_t em[4];
@@ -1116,17 +1095,14 @@ template <int MODE> LAB_DEV void lat_levels_body(Params const &p, Lattice const 
         pr.grid = grid;
     }
     uint32_t mx = 0, painted = 0, unused = 0;
-    uint32_t next = 0; // (the ticket after this one is asked for before the tile is worked on: its round trip is hidden)
-    if (lane == 0) {
-        next = lab_atomic_add(&tc->lat_ticket[3], 1u);
-    }
     for (;;) {
-        uint32_t const t = lab_shfl(next, 0);
+        uint32_t t = 0;
+        if (lane == 0) {
+            t = lab_atomic_add(&tc->lat_ticket[3], 1u);
+        }
+        t = lab_shfl(t, 0);
         if (t >= static_cast<uint32_t>(p.g.ntiles)) {
             break;
-        }
-        if (lane == 0) {
-            next = lab_atomic_add(&tc->lat_ticket[3], 1u);
         }
         lat_levels_tile<MODE>(p, lt, t, lane, sm, mx, pr, painted, 0, 0, unused);
     }

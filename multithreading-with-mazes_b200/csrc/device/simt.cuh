@@ -97,8 +97,6 @@ LAB_DEV uint32_t lab_atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v
 LAB_DEV uint32_t lab_atomic_cas(uint32_t *p, uint32_t expect, uint32_t v) { return atomicCAS(p, expect, v); }
 LAB_DEV uint32_t lab_atomic_exch(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
 
-// a hint: bring the 128-byte line at p into L2 (a later load then finds it there)
-LAB_DEV void lab_prefetch_l2(void const *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 LAB_DEV void lab_threadfence() { __threadfence(); }
 LAB_DEV void lab_nanosleep(unsigned ns) { __nanosleep(ns); }
 LAB_DEV uint64_t lab_cycles() { return static_cast<uint64_t>(clock64()); }

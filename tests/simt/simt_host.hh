@@ -268,7 +268,6 @@ LAB_DEV void lab_st_pair(uint32_t *p, uint32_t x, uint32_t y) {
 }
 LAB_DEV void lab_st_volatile(uint32_t *p, uint32_t v) { *p = v; }
 LAB_DEV void lab_st_volatile(uint16_t *p, uint16_t v) { *p = v; }
-LAB_DEV void lab_prefetch_l2(void const *) {}
 
 template <class T> LAB_DEV T lab_atomic_add(T *p, typename std::common_type<T>::type v) {
     T const o = *p;
