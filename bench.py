@@ -346,6 +346,8 @@ def ours(args):
     game, builder, n, mod, stands_for = WORKLOADS[workload]
     if world > 1 and game in ("distance", "distance+gather") and args.sharding == "bands":
         return ours_bands(args, lab, dist, torch, world, rank, local)
+    if world > 1 and game == "corners" and args.sharding == "bands":
+        return ours_corner_bands(args, lab, dist, torch, world, rank, local)
 
     # ---- synthetic input: one seeded maze per rank (independent mazes: no data-path collective) ----
     t0 = time.time()
@@ -548,6 +550,84 @@ def ours_bands(args, lab, dist, torch, world, rank, local):
             "e2e": {"value": e_settled / (e_ms_max * 1e-3) / 1e9, "unit": "Gcells/s", "h2d_bytes_per_step": cells * 2,
                     "d2h_bytes_per_step": cells * 6, "ms_per_step": e_ms_max / e_steps, "steps": e_steps},
             "gpu_launches": launches, "clocks": clocks,
+        }))
+    dist.destroy_process_group()
+
+
+def ours_corner_bands(args, lab, dist, torch, world, rank, local):
+    """N > 1, bfs-corners (BASELINE configs[3]): the workload's maze cut into N row bands (strong scaling), four fields
+    searched at once by the tile wave band by band (bands.sharded_corners): four rows of levels to each neighbour and a
+    one-word all-reduce per exchange round.  value = squares that received a paint bit / s."""
+    from mazes_b200 import bands
+
+    workload = args.workload
+    game, builder, n, mod, stands_for = WORKLOADS[workload]
+    t0 = time.time()
+    if rank == 0:  # one rank builds (and caches) the maze, the others read the file
+        make_case(lab, workload)
+    dist.barrier()
+    maze, spec = make_case(lab, workload)
+    build_s = time.time() - t0
+    rows, cols = maze.shape
+    r0, nloc = bands.split_rows(rows, world)[rank]
+    stream = torch.cuda.current_stream()
+    pristine = torch.from_numpy(maze[r0:r0 + nloc].view(np.int16).copy()).cuda()
+    work = torch.empty_like(pristine)
+    levels = [torch.empty((nloc, cols), dtype=torch.int32, device="cuda") for _ in range(4)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    eng = bands.GpuBandEngine(lab, work)
+    for k, lv in enumerate(levels):
+        eng.grid.bind_levels(k, lv.data_ptr())
+
+    def step(ev=None):
+        work.copy_(pristine)
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if ev:
+            ev[0].record(stream)
+        res = bands.sharded_corners(eng, spec["starts"], spec["finish"], r0, nloc)
+        if ev:
+            ev[1].record(stream)
+        return res
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    painted, rounds, launches = 0, 0, 0
+    for e in evs:
+        res = step(e)
+        painted += res["painted"]
+        rounds += res["rounds"]
+        launches += int(eng.grid.stats()["launches"])
+    torch.cuda.synchronize()
+    step_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+    vec = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+    step_ms_max = float(vec.item())
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = ALG_BYTES_PER_CELL["corners"] * rows * cols
+        achieved = alg_bytes / (step_ms_max / args.steps * 1e-3) / 1e9
+        emit_line(json.dumps({
+            "metric": "cells settled/sec (G/s) for BFS distance map & bfs-gather; % of HBM roofline",
+            "value": painted / (step_ms_max * 1e-3) / 1e9, "unit": "Gcells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": workload, "stands_for": stands_for, "game": game, "builder": builder, "mod": mod, "rows": rows, "cols": cols, "seed": SEED + 2,
+                       "cells_settled_per_step": painted // args.steps, "winner": res["winner"], "finish_level": res["level"],
+                       "parallelism": f"{world} row bands of one {rows}x{cols} maze, one per GPU; four fields by the tile wave, band by band: "
+                                      "NCCL send/recv of four rows of levels per neighbour + a 1-word all-reduce per exchange round",
+                       "exchange_rounds_per_step": rounds / args.steps, "l2": "256 MB flush buffer written between timed steps", "maze_build_s_host": round(build_s, 2)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
+                         "kernel": "k_bfs_tiles x 4 fields (all launches of a step, exchanges and host round trips included)", "peak_source": peak_src + f" x {world} GPUs",
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": step_ms_max / args.steps},
+            "e2e": None, "gpu_launches": launches, "clocks": clocks,
         }))
     dist.destroy_process_group()
 

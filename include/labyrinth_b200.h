@@ -189,8 +189,20 @@ int lab_band_finish(lab_grid *g, uint64_t *local_max, uint64_t *local_settled);
  *                             state = {squares walked, row, col where it stopped, level left (0: at the start)}
  *     lab_band_recolour       paint nibble of one square := bits (gather's path.front(), bfs_threads.cc:355-364)
  *     lab_band_finish_game    closes the game
- * multithreading-with-mazes_b200/bands.py (sharded_hunt, sharded_gather) is the driver. */
+ * multithreading-with-mazes_b200/bands.py (sharded_hunt, sharded_gather) is the driver.  On any other maze (loops:
+ * grid, -m cross, -m x) the field comes from the relax / exchange loop above run to its fixpoint after lab_band_begin_game.
+ *
+ * Bfs::corners across row bands (solvers/bfs_threads.cc:420-453; bands.sharded_corners): FOUR fields at once,
+ *     lab_band_begin_corners  src_rc = colour k's start (row, col) in band rows, (-1, -1) if it lies in another band
+ *     lab_band_planes         fields of the open band search (1; 4 after lab_band_begin_corners): lab_band_export_edges /
+ *                             _import_edges then move lab_band_planes() x lab_band_cols_padded() levels per row buffer,
+ *                             field k's at [k * cols_padded, (k + 1) * cols_padded)
+ *     lab_band_level_at_plane / lab_band_paint_planes   as above, naming the field (colour k paints from its own) */
 int lab_band_begin_game(lab_grid *g, int game, int src_r_local, int src_c);
+int lab_band_begin_corners(lab_grid *g, const int32_t src_rc[8]);
+int lab_band_planes(const lab_grid *g);
+int lab_band_level_at_plane(lab_grid *g, int plane, int r, int c, uint32_t *level);
+int lab_band_paint_planes(lab_grid *g, int n_rules, const uint32_t *plane, const uint32_t *below, const uint32_t *bits, uint64_t *painted);
 int lab_band_level_at(lab_grid *g, int r, int c, uint32_t *level);
 int lab_band_paint(lab_grid *g, int n_rules, const uint32_t *below, const uint32_t *bits, uint64_t *painted);
 int lab_band_walk(lab_grid *g, int r, int c, int include_first, int first_only, uint32_t repaint_bits, void *path_dev,

@@ -42,6 +42,7 @@ ABI_SYMBOLS = (
     "lab_distance_map_sharded", "lab_sharded_last_error", "lab_band_begin_lattice", "lab_band_lat_super_rows", "lab_band_lat_words", "lab_band_lat_bind", "lab_band_lat_set_peers", "lab_band_lat_link", "lab_band_lat_flood",
     "lab_band_lat_levels",
     "lab_band_begin_game", "lab_band_level_at", "lab_band_paint", "lab_band_walk", "lab_band_recolour", "lab_band_finish_game",
+    "lab_band_begin_corners", "lab_band_planes", "lab_band_level_at_plane", "lab_band_paint_planes",
 )
 
 

@@ -99,6 +99,8 @@ class _BandEngine:
         dev = self.row_device
         self._u8 = [torch.empty(self.cols_padded, dtype=torch.uint8, device=dev) for _ in range(2)]
         self._u32 = [torch.empty(self.cols_padded, dtype=torch.int32, device=dev) for _ in range(2)]
+        self._u32x4 = None  # corners: four fields' rows per buffer (allocated by begin_corners)
+        self.nplanes = 1
         self._tree_bufs = None
 
     def _f(self, name):
@@ -114,7 +116,18 @@ class _BandEngine:
 
     def begin(self, src_local: Optional[Tuple[int, int]], lattice_next: bool = False):
         r, c = src_local if src_local is not None else (-1, -1)
+        self.nplanes = 1
         self._check(self._f("begin_lattice")(self.h, c_int(0), c_int(r), c_int(c), c_int(1 if lattice_next else 0)))
+
+    def begin_corners(self, srcs_local):
+        """Bfs::corners: four fields at once; srcs_local[k] = colour k's start in band rows, or None (another band's)."""
+        flat = []
+        for s_ in srcs_local:
+            flat += list(s_) if s_ is not None else [-1, -1]
+        self.nplanes = 4
+        if self._u32x4 is None:
+            self._u32x4 = [self.torch.empty(4 * self.cols_padded, dtype=self.torch.int32, device=self.row_device) for _ in range(2)]
+        self._check(self._f("begin_corners")(self.h, (ctypes.c_int32 * 8)(*flat)))
 
     def path_rows(self):
         self._check(self._f("path_rows")(self.h, self._ptr(self._u8[0]), self._ptr(self._u8[1])))
@@ -127,8 +140,9 @@ class _BandEngine:
         self._check(self._f("relax")(self.h))
 
     def export_edges(self):
-        self._check(self._f("export_edges")(self.h, self._ptr(self._u32[0]), self._ptr(self._u32[1])))
-        return self._u32[0], self._u32[1]
+        bufs = self._u32 if self.nplanes == 1 else self._u32x4  # (field k's row at [k * cols_padded, (k + 1) * cols_padded))
+        self._check(self._f("export_edges")(self.h, self._ptr(bufs[0]), self._ptr(bufs[1])))
+        return bufs[0], bufs[1]
 
     def import_edges(self, above_bottom, below_top) -> int:
         n = c_uint32()
@@ -193,20 +207,22 @@ class _BandEngine:
     # -- the solvers across bands (lab_band_begin_game, _level_at, _paint, _walk, _recolour, _finish_game) --
     def begin_game(self, game: int, src_local: Optional[Tuple[int, int]], lattice_next: bool = False):
         r, c = src_local if src_local is not None else (-1, -1)
+        self.nplanes = 1
         self._check(self._f("begin_lattice")(self.h, c_int(game), c_int(r), c_int(c), c_int(1 if lattice_next else 0)))
 
-    def level_at(self, r: int, c: int) -> int:
+    def level_at(self, r: int, c: int, plane: int = 0) -> int:
         v = c_uint32()
-        self._check(self._f("level_at")(self.h, c_int(r), c_int(c), byref(v)))
+        self._check(self._f("level_at_plane")(self.h, c_int(plane), c_int(r), c_int(c), byref(v)))
         return int(v.value)
 
     def paint(self, rules) -> int:
-        """rules: [(below, bits)], at most 4 -> squares of this band that received a bit"""
+        """rules: [(below, bits)] or [(below, bits, field)], at most 4 -> squares of this band that received a bit"""
         n = len(rules)
         below = (c_uint32 * 4)(*[r[0] for r in rules] + [0] * (4 - n))
         bits = (c_uint32 * 4)(*[r[1] for r in rules] + [0] * (4 - n))
+        plane = (c_uint32 * 4)(*[(r[2] if len(r) > 2 else 0) for r in rules] + [0] * (4 - n))
         painted = c_uint64()
-        self._check(self._f("paint")(self.h, c_int(n), below, bits, byref(painted)))
+        self._check(self._f("paint_planes")(self.h, c_int(n), plane, below, bits, byref(painted)))
         return int(painted.value)
 
     def walk(self, r: int, c: int, include_first: bool, first_only: bool, repaint_bits: int, path_buf=None):
@@ -356,18 +372,8 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     if use_tree and getattr(engine, "supports_tree", False):
         lattice = lattice_layout is not None and _sharded_lattice(engine, lattice_layout, group, tr)
         tree = "lattice" if lattice else _sharded_tree(engine, start_global, row0, rows_local, group, tr)
-    while not tree:
-        rounds += 1
-        engine.relax()
-        top, bottom = engine.export_edges()
-        above_bottom, below_top = _exchange(dist, rank, world, top, bottom, engine, group)
-        activated = engine.import_edges(above_bottom, below_top)
-        flag.fill_(1 if activated else 0)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-        if int(flag.item()) == 0:
-            break
-        if rounds >= max_rounds:
-            raise RuntimeError(f"sharded_distance_map: no fixpoint after {max_rounds} exchange rounds")
+    if not tree:
+        rounds = _wave_to_fixpoint(engine, group, max_rounds)
     tr.mark("search")
     mx, settled = engine.finish()
     tr.mark("finish")
@@ -379,6 +385,29 @@ def sharded_distance_map(engine, start_global: Tuple[int, int], row0: int, rows_
     tr.report(rank)
     return {"max": max(int(e[0]) for e in every), "settled": sum(int(e[1]) for e in every), "rounds": rounds, "tree": tree is True or tree == "lattice",
             "road": "wave" if not tree else ("tree" if tree is True else tree)}
+
+
+def _wave_to_fixpoint(engine, group, max_rounds: int = 1 << 20) -> int:
+    """The tile wave, band by band (general mazes): local search to the band's fixpoint, one row of levels per open field
+    to each neighbour, a one-word all-reduce; until no rank's border tiles were re-activated.  -> exchange rounds"""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    flag = torch.zeros(1, dtype=torch.int32, device=engine.row_device)
+    rounds = 0
+    while True:
+        rounds += 1
+        engine.relax()
+        top, bottom = engine.export_edges()
+        above_bottom, below_top = _exchange(dist, rank, world, top, bottom, engine, group)
+        activated = engine.import_edges(above_bottom, below_top)
+        flag.fill_(1 if activated else 0)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()) == 0:
+            return rounds
+        if rounds >= max_rounds:
+            raise RuntimeError(f"no fixpoint after {max_rounds} exchange rounds")
 
 
 def _all_gather(dist, out, chunk, world, group):
@@ -570,9 +599,23 @@ def _sharded_field(engine, game, start_global, row0, rows_local, group):
     if not road:
         road = _sharded_tree(engine, start_global, row0, rows_local, group, tr)
     if not road:
-        engine.finish_game()
-        raise NotImplementedError("the solvers are sharded on perfect mazes and open rooms only (a general maze needs the bounded wave across bands)")
+        # a general maze (loops: grid, -m cross, -m x): the tile wave across bands, to the field's fixpoint.  The canonical
+        # model paints {d < D}: the whole field with the thresholds applied afterwards gives the same grid a bounded search does.
+        _wave_to_fixpoint(engine, group)
+        return "wave"
     return "tree" if road is True else "room"
+
+
+def _band_split(engine, row0, rows_local, group):
+    """[(first row, rows)] of every rank's band (all-gathered once per layout, kept on the engine)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    cached = getattr(engine, "_split", None)
+    if cached is None or cached[0] != (row0, rows_local, world):
+        cached = ((row0, rows_local, world), [tuple(x) for x in _gather_ints(engine, [row0, rows_local], group)])
+        engine._split = cached
+    return cached[1]
 
 
 def _level_of(engine, road, square, start_global, row0, rows_local, group):
@@ -617,7 +660,7 @@ def _walk_path(engine, road, finish, start_global, level, repaint_bits, want_pat
                 if left <= 0:
                     break
                 # the walk stopped at its band's border: its next square is across it (one level lower, in the neighbour's band)
-                owner_r0, owner_n = next((a, n) for a, n in engine._tree_layout[1]["split"] if a <= r < a + n)
+                owner_r0, owner_n = next((a, n) for a, n in _band_split(engine, row0, rows_local, group) if a <= r < a + n)
                 cur = (r - 1, c) if r == owner_r0 else (r + 1, c)
                 if not (r == owner_r0 or r == owner_r0 + owner_n - 1) or steps == 0 and include_first:
                     raise RuntimeError(f"path walk lost at ({r},{c}) with {left} levels to go")
@@ -694,3 +737,33 @@ def sharded_gather(engine, start_global, finishes_global, row0: int, rows_local:
     engine.finish_game()
     painted = sum(v[0] for v in _gather_ints(engine, [painted], group))
     return {"claimed_by": claimed_by, "path_len": path_len, "paths": paths, "painted": painted, "road": road}
+
+
+def sharded_corners(engine, starts_global, finish_global, row0: int, rows_local: int, group=None):
+    """Bfs::corners (solvers/bfs_threads.cc:420-453) on this rank's band: four colours, each from its own corner, one finish
+    (the caller placed the bits and carved the finish's cross as Bfs::corners does, e.g. with lab.place_corners).  Collective.
+    Four fields are searched at once by the tile wave, band by band, to their fixpoint; the canonical model then paints
+    colour k on {d_k < D}, D = the lowest level at which any colour reaches the finish (winner: the lowest such colour) --
+    post.cuh resolve_body's rules.  The static game never repaints; the winner's path is not returned.
+    -> {"winner", "level", "painted", "rounds", "road"}"""
+    starts = [tuple(int(x) for x in s_) for s_ in starts_global]
+    fr, fc = (int(x) for x in finish_global)
+    here = lambda r: row0 <= r < row0 + rows_local
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    engine.begin_corners([(r - row0, c) if here(r) else None for r, c in starts])
+    top, bottom = engine.path_rows()
+    above_bottom, below_top = _exchange(dist, rank, world, top, bottom, engine, group)
+    engine.set_neighbour_paths(above_bottom, below_top)
+    rounds = _wave_to_fixpoint(engine, group)
+    mine = [engine.level_at(fr - row0, fc, k) if here(fr) else -1 for k in range(4)]
+    mine = [-1 if v == INF else v for v in mine]
+    levels = [max(v[k] for v in _gather_ints(engine, mine, group)) for k in range(4)]
+    reached = [v for v in levels if v >= 0]
+    level = min(reached) if reached else INF
+    winner = next((k for k in range(4) if levels[k] == level), -1) if reached else -1
+    painted = engine.paint([(level, (1 << k) << PAINT_SHIFT, k) for k in range(4)])
+    engine.finish_game()
+    painted = sum(v[0] for v in _gather_ints(engine, [painted], group))
+    return {"winner": winner, "level": level if reached else -1, "painted": painted, "rounds": rounds, "road": "wave"}

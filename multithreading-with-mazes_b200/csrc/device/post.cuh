@@ -450,6 +450,18 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
         }
         return;
     }
+    // Row bands: the squares just above / below the band are the neighbouring bands' border rows; where the tile wave made
+    // the field their levels are in the ghost tile rows of the edge arrays (band_import_edges_body).  The canonical step
+    // (first of N, E, S, W one level lower) must see them: on a maze with loops a square of the border row can have a lower
+    // neighbour across the border AND one inside the band.  (Anywhere else the ghosts hold INF and change nothing.)
+    uint32_t const *edges = p.plane[plane].edges;
+    auto halo = [&](long long rr, long long cc) -> uint32_t {
+        if (!edges || cc < 0 || cc >= g.cols) return INF;
+        if (rr == -1) return lab_ld_cg(edges + (cc >> 6) * (4 * TS) + SIDE_S * TS + (cc & 63));
+        if (rr == g.rows) return lab_ld_cg(edges + (static_cast<long long>(g.ntiles) + g.tiles_x + (cc >> 6)) * (4 * TS) + SIDE_N * TS + (cc & 63));
+        return INF;
+    };
+    bool handover = false; // the canonical step leads into the neighbouring band: the walk stops here (walk_left = d)
     // N, E, S, W (maze/maze.cc:213-218) without a table in local memory: k -> (k odd ? 0 : k - 1, k odd ? 2 - k : 0)
     bool const voter = lane < 4;
     int const my_dr = (lane & 1) ? 0 : (lane & 3) - 1, my_dc = (lane & 1) ? 2 - (lane & 3) : 0;
@@ -505,6 +517,8 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
                 int const nr = r + my_dr, nc = c + my_dc;
                 if (nr >= 0 && nr < g.rows && nc >= 0 && nc < g.cols) {
                     hit = dist[static_cast<long long>(nr) * g.cols + nc] == d - 1;
+                } else {
+                    hit = halo(nr, nc) == d - 1;
                 }
             }
             uint32_t const mk = lab_ballot(hit);
@@ -512,6 +526,10 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
                 break; // cannot happen on a converged field
             }
             int const k = lab_ffs32(mk) - 1;
+            if (r + ((k & 1) ? 0 : k - 1) < 0 || r + ((k & 1) ? 0 : k - 1) >= g.rows) {
+                handover = true;
+                break;
+            }
             r += (k & 1) ? 0 : k - 1;
             c += (k & 1) ? 2 - k : 0;
             d--;
@@ -534,7 +552,7 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
         // step's instruction count IS the walk's speed); stepping onto the ring makes that square's tile the next one.
         int const my_off = voter ? my_dr * WALK_W + my_dc : 0; // lanes 0..3 look N, E, S, W of the walker; the others at it
         bool lost = false;
-        while (d > 0 && !lost) {
+        while (d > 0 && !lost && !handover) {
             int const cty = r >> 6, ctx = c >> 6;
             lab_syncwarp(); // (everybody is done with the old tile)
             {
@@ -556,7 +574,7 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
                     long long const rr = k < 4 ? row0 + ((k & 2) ? TS : -1) : row0 + q;
                     long long const cc = k < 4 ? col0 + q : col0 + ((k & 2) ? TS : -1);
                     bool const ok = rr >= 0 && rr < g.rows && cc >= 0 && cc < g.cols;
-                    h[k] = ok ? lab_ld_ro(dist + rr * g.cols + cc) : INF;
+                    h[k] = ok ? lab_ld_ro(dist + rr * g.cols + cc) : halo(rr, cc);
                 }
 #pragma unroll
                 for (int k = 0; k < K; k++) {
@@ -581,6 +599,10 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
                     break;
                 }
                 int const k = lab_ffs32(mk) - 1; // first of N, E, S, W one level lower
+                if ((cty << 6) + lr + ((k & 1) ? 0 : k - 1) < 0 || (cty << 6) + lr + ((k & 1) ? 0 : k - 1) >= g.rows) {
+                    handover = true; // (into the neighbouring band)
+                    break;
+                }
                 idx = static_cast<int>(lab_shfl(static_cast<uint32_t>(cand), k));
                 lr += (k & 1) ? 0 : k - 1;
                 lc += (k & 1) ? 2 - k : 0;
@@ -776,10 +798,10 @@ LAB_DEV void band_export_edges_body(Geom g, uint32_t const *edges, uint32_t *top
 // Take the neighbours' border levels into the ghost tile rows; a border tile whose ghost improved
 // where the border can be crossed becomes active and is queued.  One warp per tile column.
 // (Runs between two launches of the search kernel: every tile is idle, the queue is empty.)
-LAB_DEV void band_import_edges_body(Params p, uint32_t const *above_bottom, uint32_t const *below_top, uint32_t *activated,
+LAB_DEV void band_import_edges_body(Params p, int plane, uint32_t const *above_bottom, uint32_t const *below_top, uint32_t *activated,
                                     long long gwarp, long long nwarps, int lane) {
     Geom const &g = p.g;
-    Plane const &pl = p.plane[0];
+    Plane const &pl = p.plane[plane];
     for (long long tx = gwarp; tx < g.tiles_x; tx += nwarps) {
         for (int side = 0; side < 2; side++) {
             uint32_t const *src = side == 0 ? above_bottom : below_top;
@@ -802,7 +824,7 @@ LAB_DEV void band_import_edges_body(Params p, uint32_t const *above_bottom, uint
             if (lab_any(improved) && lane == 0) {
                 if (lab_atomic_or(&pl.state[t], ST_ACTIVE) == 0u) {
                     lab_atomic_add(&p.ctl->pending, 1u);
-                    queue_push(p, static_cast<uint32_t>(t));
+                    queue_push(p, static_cast<uint32_t>(plane) * static_cast<uint32_t>(g.ntiles) + static_cast<uint32_t>(t)); // (as init_run_body queues a source)
                     lab_atomic_add(activated, 1u);
                 }
             }

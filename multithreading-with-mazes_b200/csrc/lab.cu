@@ -354,9 +354,9 @@ __global__ void __launch_bounds__(256) k_band_ghost_words(Geom g, uint8_t const 
 __global__ void __launch_bounds__(256) k_band_export_edges(Geom g, uint32_t const *edges, uint32_t *top, uint32_t *bottom) {
     band_export_edges_body(g, edges, top, bottom, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x);
 }
-__global__ void __launch_bounds__(256) k_band_import_edges(Params p, uint32_t const *above_bottom, uint32_t const *below_top,
+__global__ void __launch_bounds__(256) k_band_import_edges(Params p, int plane, uint32_t const *above_bottom, uint32_t const *below_top,
                                                            uint32_t *activated) {
-    band_import_edges_body(p, above_bottom, below_top, activated, gwarp_id(), nwarps_total(), lane_id());
+    band_import_edges_body(p, plane, above_bottom, below_top, activated, gwarp_id(), nwarps_total(), lane_id());
 }
 __global__ void k_band_rearm(Params p, unsigned long long budget_ns) { band_rearm_body(p, budget_ns); }
 
@@ -1633,16 +1633,31 @@ int lab_band_begin_game(lab_grid *h, int game, int src_r, int src_c) { return la
 // lattice_next != 0: the caller will run the lattice road across bands (lab_band_lat_link .. lab_band_lat_levels) next.  Its
 // last step writes every square of the band's level field, or wipes it if the maze is no lattice tree, so the field is
 // not cleared here; and for the distance map pack sets the measure bits on the way (see measure_body).
+static int band_begin_common(lab_grid *h, Run_desc const &d, int lattice_next) {
+    h->have_map = false; // (a band's field is not a map lab_distance_paint could colour: its maximum is the band's)
+    h->band_desc = d;
+    h->band_skip_field_reset = lattice_next != 0;
+    if (!h->ghost_n) {
+        CU(cudaMalloc(&h->ghost_n, static_cast<size_t>(h->g.tiles_x) * sizeof(uint64_t)));
+        CU(cudaMalloc(&h->ghost_s, static_cast<size_t>(h->g.tiles_x) * sizeof(uint64_t)));
+        CU(cudaMalloc(&h->d_activated, sizeof(uint32_t)));
+    }
+    h->band_mode = true;
+    h->tree_last = Tree_ctl{};
+    h->tree_tried = false;
+    // passable: the distance map skips measured squares (distance.cc:145-148), the solvers look at path_bit alone
+    int const rc = d.game == GAME_DISTANCE ? search_prepare(h, d, SQ_PATH | SQ_MEASURE, SQ_PATH) : search_prepare(h, d, SQ_PATH, SQ_PATH);
+    h->band_open = rc == LAB_OK;
+    return rc;
+}
+
 int lab_band_begin_lattice(lab_grid *h, int game, int src_r, int src_c, int lattice_next) {
     Device_guard const guard_(h);
-    if (h) {
-        h->have_map = false; // (a band's field is not a map lab_distance_paint could colour: its maximum is the band's)
-    }
     if (!h) {
         return fail(LAB_ERR_ARG, "null grid");
     }
     if (game != GAME_DISTANCE && game != GAME_HUNT && game != GAME_GATHER) {
-        return fail(LAB_ERR_ARG, "sharded game %d (0 distance, 1 hunt, 2 gather)", game);
+        return fail(LAB_ERR_ARG, "sharded game %d (0 distance, 1 hunt, 2 gather; corners: lab_band_begin_corners)", game);
     }
     if (src_r >= 0 && !in_grid(h, {src_r, src_c})) {
         return fail(LAB_ERR_ARG, "source (%d,%d) outside the band", src_r, src_c);
@@ -1659,21 +1674,38 @@ int lab_band_begin_lattice(lab_grid *h, int game, int src_r, int src_c, int latt
     }
     d.bound_mode = BOUND_NONE;
     d.spec_mark = (lattice_next && game == GAME_DISTANCE) ? SQ_MEASURE : 0u;
-    h->band_desc = d;
-    h->band_skip_field_reset = lattice_next != 0;
-    if (!h->ghost_n) {
-        CU(cudaMalloc(&h->ghost_n, static_cast<size_t>(h->g.tiles_x) * sizeof(uint64_t)));
-        CU(cudaMalloc(&h->ghost_s, static_cast<size_t>(h->g.tiles_x) * sizeof(uint64_t)));
-        CU(cudaMalloc(&h->d_activated, sizeof(uint32_t)));
-    }
-    h->band_mode = true;
-    h->tree_last = Tree_ctl{};
-    h->tree_tried = false;
-    // passable: the distance map skips measured squares (distance.cc:145-148), the solvers look at path_bit alone
-    int const rc = game == GAME_DISTANCE ? search_prepare(h, d, SQ_PATH | SQ_MEASURE, SQ_PATH) : search_prepare(h, d, SQ_PATH, SQ_PATH);
-    h->band_open = rc == LAB_OK;
-    return rc;
+    return band_begin_common(h, d, lattice_next);
 }
+
+// Bfs::corners across row bands (bfs_threads.cc:420-453): FOUR fields searched at once, colour k from its own corner.
+// src_rc: (row, col) of colour k's start in band rows, (-1, -1) for a start in another band.  The fields are searched to
+// their fixpoint (no bound): the canonical model paints {d_k < D}, D = the lowest level any colour reaches the finish at
+// (resolve_body), which the caller takes from lab_band_level_at_plane once the bands have converged.
+int lab_band_begin_corners(lab_grid *h, const int32_t *src_rc) {
+    Device_guard const guard_(h);
+    if (!h || !src_rc) {
+        return fail(LAB_ERR_ARG, "lab_band_begin_corners: null argument");
+    }
+    Run_desc d{};
+    d.game = GAME_CORNERS;
+    d.nplanes = 4;
+    for (int k = 0; k < MAX_PLANES; k++) {
+        d.src_r[k] = d.src_c[k] = -1;
+    }
+    for (int k = 0; k < 4; k++) {
+        if (src_rc[2 * k] >= 0) {
+            if (!in_grid(h, {src_rc[2 * k], src_rc[2 * k + 1]})) {
+                return fail(LAB_ERR_ARG, "corner start %d (%d,%d) outside the band", k, src_rc[2 * k], src_rc[2 * k + 1]);
+            }
+            d.src_r[k] = src_rc[2 * k];
+            d.src_c[k] = src_rc[2 * k + 1];
+        }
+    }
+    d.bound_mode = BOUND_NONE;
+    return band_begin_common(h, d, 0);
+}
+
+int lab_band_planes(const lab_grid *h) { return (h && h->band_open) ? h->band_desc.nplanes : 0; }
 
 int lab_band_path_rows(lab_grid *h, void *top_dev, void *bottom_dev) {
     Device_guard const guard_(h);
@@ -1711,7 +1743,7 @@ int lab_band_relax(lab_grid *h) {
     if (!h || !h->band_open) {
         return fail(LAB_ERR_ARG, "no band search open");
     }
-    return search_launch(h, 1);
+    return search_launch(h, h->band_desc.nplanes);
 }
 
 int lab_band_export_edges(lab_grid *h, void *top_levels_dev, void *bottom_levels_dev) {
@@ -1720,10 +1752,12 @@ int lab_band_export_edges(lab_grid *h, void *top_levels_dev, void *bottom_levels
         return fail(LAB_ERR_ARG, "lab_band_export_edges: bad arguments");
     }
     int const n = h->g.tiles_x * TS;
-    k_band_export_edges<<<(n + 255) / 256, 256, 0, h->stream>>>(h->g, h->plane[0].edges, static_cast<uint32_t *>(top_levels_dev),
-                                                               static_cast<uint32_t *>(bottom_levels_dev));
-    TRACE("k_band_export_edges", h->stream);
-    h->launches += 1;
+    for (int k = 0; k < h->band_desc.nplanes; k++) { // (field k's rows at [k * n, (k + 1) * n))
+        k_band_export_edges<<<(n + 255) / 256, 256, 0, h->stream>>>(h->g, h->plane[k].edges, static_cast<uint32_t *>(top_levels_dev) + static_cast<size_t>(k) * n,
+                                                                   static_cast<uint32_t *>(bottom_levels_dev) + static_cast<size_t>(k) * n);
+        TRACE("k_band_export_edges", h->stream);
+        h->launches += 1;
+    }
     CU(cudaGetLastError());
     return LAB_OK;
 }
@@ -1734,13 +1768,17 @@ int lab_band_import_edges(lab_grid *h, const void *above_bottom_levels_dev, cons
         return fail(LAB_ERR_ARG, "lab_band_import_edges: bad arguments");
     }
     cudaStream_t s = h->stream;
-    Params p = make_params(h, 1);
+    int const planes = h->band_desc.nplanes;
+    size_t const n = static_cast<size_t>(h->g.tiles_x) * TS;
+    Params p = make_params(h, planes);
     CU(cudaMemsetAsync(h->d_activated, 0, sizeof(uint32_t), s));
     k_band_rearm<<<1, 1, 0, s>>>(p, budget_ns());
-    k_band_import_edges<<<blocks_for(h, h->g.tiles_x, 256), 256, 0, s>>>(p, static_cast<uint32_t const *>(above_bottom_levels_dev),
-                                                                         static_cast<uint32_t const *>(below_top_levels_dev), h->d_activated);
-    TRACE("k_band_import_edges", s);
-    h->launches += 2;
+    for (int k = 0; k < planes; k++) {
+        uint32_t const *above = static_cast<uint32_t const *>(above_bottom_levels_dev), *below = static_cast<uint32_t const *>(below_top_levels_dev);
+        k_band_import_edges<<<blocks_for(h, h->g.tiles_x, 256), 256, 0, s>>>(p, k, above ? above + k * n : nullptr, below ? below + k * n : nullptr, h->d_activated);
+        TRACE("k_band_import_edges", s);
+    }
+    h->launches += 1 + planes;
     CU(cudaMemcpyAsync(activated, h->d_activated, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return LAB_OK;
@@ -2167,20 +2205,26 @@ int lab_band_tree_levels(lab_grid *h, const void *all3, int32_t *used) {
 
 // ---- the solvers across row bands: compositions of the pieces below, driven by bands.py (sharded_hunt / sharded_gather).
 // The level field is the sharded spanning-tree pipeline's or the open room's (begin with lab_band_begin_game).
-int lab_band_level_at(lab_grid *h, int r, int c, uint32_t *level) {
+int lab_band_level_at_plane(lab_grid *h, int plane, int r, int c, uint32_t *level) {
     Device_guard const guard_(h);
-    if (!h || !h->band_open || !level || !in_grid(h, {r, c})) {
+    if (!h || !h->band_open || !level || !in_grid(h, {r, c}) || plane < 0 || plane >= h->band_desc.nplanes) {
         return fail(LAB_ERR_ARG, "lab_band_level_at: bad arguments");
     }
-    CU(cudaMemcpyAsync(level, h->plane[0].dist + static_cast<size_t>(r) * h->g.cols + c, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(level, h->plane[plane].dist + static_cast<size_t>(r) * h->g.cols + c, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return LAB_OK;
 }
+int lab_band_level_at(lab_grid *h, int r, int c, uint32_t *level) { return lab_band_level_at_plane(h, 0, r, c, level); }
 
 // Paint rules (post.cuh Paint_rule, plane 0): OR bits[k] into the band's squares whose level is below below[k].
 int lab_band_paint(lab_grid *h, int n_rules, const uint32_t *below, const uint32_t *bits, uint64_t *painted) {
+    uint32_t const plane0[4] = {0u, 0u, 0u, 0u};
+    return lab_band_paint_planes(h, n_rules, plane0, below, bits, painted);
+}
+// ... rule k looks at field plane[k] (corners: colour k's own field)
+int lab_band_paint_planes(lab_grid *h, int n_rules, const uint32_t *plane, const uint32_t *below, const uint32_t *bits, uint64_t *painted) {
     Device_guard const guard_(h);
-    if (!h || !h->band_open || n_rules < 1 || n_rules > 4 || !below || !bits) {
+    if (!h || !h->band_open || n_rules < 1 || n_rules > 4 || !plane || !below || !bits) {
         return fail(LAB_ERR_ARG, "lab_band_paint: bad arguments");
     }
     cudaStream_t s = h->stream;
@@ -2188,10 +2232,13 @@ int lab_band_paint(lab_grid *h, int n_rules, const uint32_t *below, const uint32
     r.winner = -1;
     r.n_rules = static_cast<uint32_t>(n_rules);
     for (int k = 0; k < n_rules; k++) {
-        r.rule[k] = {0u, below[k], bits[k], 0u};
+        if (plane[k] >= static_cast<uint32_t>(h->band_desc.nplanes)) {
+            return fail(LAB_ERR_ARG, "lab_band_paint: rule %d names field %u of %d", k, plane[k], h->band_desc.nplanes);
+        }
+        r.rule[k] = {plane[k], below[k], bits[k], 0u};
     }
     CU(cudaMemcpyAsync(h->res, &r, sizeof r, cudaMemcpyHostToDevice, s));
-    Params p = make_params(h, 1);
+    Params p = make_params(h, h->band_desc.nplanes);
     k_paint<<<grid_blocks(h), 256, 0, s>>>(p, h->squares, h->res);
     TRACE("k_paint", s);
     h->launches += 1;
@@ -2211,6 +2258,9 @@ int lab_band_walk(lab_grid *h, int r, int c, int include_first, int first_only, 
     Device_guard const guard_(h);
     if (!h || !h->band_open || !state) {
         return fail(LAB_ERR_ARG, "lab_band_walk: bad arguments");
+    }
+    if (h->tree_last.used != 2u && !in_grid(h, {r, c})) { // (only an open room's closed form takes a finish outside the band)
+        return fail(LAB_ERR_ARG, "lab_band_walk: (%d,%d) outside the band", r, c);
     }
     cudaStream_t s = h->stream;
     Params p = make_params(h, 1);

@@ -307,36 +307,30 @@ void *emu_band_create(int rows, int cols, uint16_t *grid, int nwarps, unsigned s
 void emu_band_destroy(void *h) { delete static_cast<Emu_band *>(h); }
 int emu_band_cols_padded(void *h) { return static_cast<Emu_band *>(h)->w.g.tiles_x * TS; }
 uint32_t *emu_band_levels(void *h) { return static_cast<Emu_band *>(h)->w.dist[0].data(); }
+uint32_t *emu_band_levels_plane(void *h, int k) { return static_cast<Emu_band *>(h)->w.dist[k].data(); }
 int emu_band_tree_used(void *h) { return static_cast<int>(static_cast<Emu_band *>(h)->tree_last.used); }
 
 int emu_band_begin_lattice(void *h, int game, int src_r, int src_c, int lattice_next);
 int emu_band_begin_game(void *h, int game, int src_r, int src_c) { return emu_band_begin_lattice(h, game, src_r, src_c, 0); }
 int emu_band_begin(void *h, int src_r, int src_c) { return emu_band_begin_game(h, GAME_DISTANCE, src_r, src_c); }
 
-int emu_band_begin_lattice(void *h, int game, int src_r, int src_c, int lattice_next) {
-    auto *e = static_cast<Emu_band *>(h);
+static int emu_band_begin_common(Emu_band *e, int lattice_next) {
     Workspace &w = e->w;
     Geom const &g = w.g;
-    fill_desc(e->d);
-    e->d.game = game;
-    e->d.nplanes = 1;
-    if (src_r >= 0) {
-        e->d.src_r[0] = src_r;
-        e->d.src_c[0] = src_c;
-    }
-    e->d.bound_mode = BOUND_NONE;
-    e->d.spec_mark = (lattice_next && game == GAME_DISTANCE) ? SQ_MEASURE : 0u;
+    int const game = e->d.game;
     size_t const nt = static_cast<size_t>(g.ntiles), cells = static_cast<size_t>(g.rows) * g.cols;
     w.path.assign(nt * TS, 0);
     w.cross.assign(nt * 4, 0);
-    w.visited[0].assign(nt * TS, 0);
-    w.edges[0].assign((nt + 2 * static_cast<size_t>(g.tiles_x)) * 4 * TS, INF);
-    w.state[0].assign(nt, 0);
-    w.dist[0].assign(cells, lattice_next ? 0xABABABABu : INF); // (as lab_band_begin_lattice: the lattice road writes or wipes the field)
+    for (int k = 0; k < e->d.nplanes; k++) {
+        w.visited[k].assign(nt * TS, 0);
+        w.edges[k].assign((nt + 2 * static_cast<size_t>(g.tiles_x)) * 4 * TS, INF);
+        w.state[k].assign(nt, 0);
+        w.dist[k].assign(cells, lattice_next ? 0xABABABABu : INF); // (as lab_band_begin_lattice: the lattice road writes or wipes the field)
+    }
     std::memset(&w.ctl, 0, sizeof w.ctl);
     std::memset(&w.res, 0, sizeof w.res);
     size_t cap = 1024;
-    while (cap < 2 * (nt + static_cast<size_t>(e->nwarps) + 64)) cap <<= 1;
+    while (cap < 2 * (static_cast<size_t>(e->d.nplanes) * nt + static_cast<size_t>(e->nwarps) + 64)) cap <<= 1;
     w.queue.assign(cap, Q_EMPTY);
     e->ghost_n.assign(g.tiles_x, 0);
     e->ghost_s.assign(g.tiles_x, 0);
@@ -347,23 +341,57 @@ int emu_band_begin_lattice(void *h, int game, int src_r, int src_c, int lattice_
     force_sources_body(g, w.path.data(), e->d, w.grid_ptr);
     return 0;
 }
-
-int emu_band_level_at(void *h, int r, int c, uint32_t *level) {
+int emu_band_begin_lattice(void *h, int game, int src_r, int src_c, int lattice_next) {
     auto *e = static_cast<Emu_band *>(h);
-    *level = e->w.dist[0][static_cast<size_t>(r) * e->w.g.cols + c];
+    fill_desc(e->d);
+    e->d.game = game;
+    e->d.nplanes = 1;
+    if (src_r >= 0) {
+        e->d.src_r[0] = src_r;
+        e->d.src_c[0] = src_c;
+    }
+    e->d.bound_mode = BOUND_NONE;
+    e->d.spec_mark = (lattice_next && game == GAME_DISTANCE) ? SQ_MEASURE : 0u;
+    return emu_band_begin_common(e, lattice_next);
+}
+int emu_band_begin_corners(void *h, int32_t const *src_rc) { // mirrors lab_band_begin_corners
+    auto *e = static_cast<Emu_band *>(h);
+    fill_desc(e->d);
+    e->d.game = GAME_CORNERS;
+    e->d.nplanes = 4;
+    for (int k = 0; k < 4; k++) {
+        if (src_rc[2 * k] >= 0) {
+            e->d.src_r[k] = src_rc[2 * k];
+            e->d.src_c[k] = src_rc[2 * k + 1];
+        }
+    }
+    e->d.bound_mode = BOUND_NONE;
+    return emu_band_begin_common(e, 0);
+}
+int emu_band_planes(void *h) { return static_cast<Emu_band *>(h)->d.nplanes; }
+
+int emu_band_level_at_plane(void *h, int plane, int r, int c, uint32_t *level) {
+    auto *e = static_cast<Emu_band *>(h);
+    *level = e->w.dist[plane][static_cast<size_t>(r) * e->w.g.cols + c];
     return 0;
 }
+int emu_band_level_at(void *h, int r, int c, uint32_t *level) { return emu_band_level_at_plane(h, 0, r, c, level); }
 
+int emu_band_paint_planes(void *h, int n_rules, uint32_t const *plane, uint32_t const *below, uint32_t const *bits, uint64_t *painted);
 int emu_band_paint(void *h, int n_rules, uint32_t const *below, uint32_t const *bits, uint64_t *painted) {
+    uint32_t const plane0[4] = {0u, 0u, 0u, 0u};
+    return emu_band_paint_planes(h, n_rules, plane0, below, bits, painted);
+}
+int emu_band_paint_planes(void *h, int n_rules, uint32_t const *plane, uint32_t const *below, uint32_t const *bits, uint64_t *painted) {
     auto *e = static_cast<Emu_band *>(h);
     Workspace &w = e->w;
-    Params p = make_params(w, 1);
+    Params p = make_params(w, e->d.nplanes);
     int const nw = e->nwarps;
     long long const nthreads = static_cast<long long>(nw) * 32;
     w.res = Result{};
     w.res.winner = -1;
     w.res.n_rules = static_cast<uint32_t>(n_rules);
-    for (int k = 0; k < n_rules; k++) w.res.rule[k] = {0u, below[k], bits[k], 0u};
+    for (int k = 0; k < n_rules; k++) w.res.rule[k] = {plane[k], below[k], bits[k], 0u};
     simt::launch(nw, [&](int wid, int lane) { paint_body(p, w.grid_ptr, &w.res, static_cast<long long>(wid) * 32 + lane, nthreads); });
     *painted = w.res.settled;
     return 0;
@@ -411,14 +439,14 @@ int emu_band_set_neighbour_paths(void *h, uint8_t const *above_bottom, uint8_t c
     int const nw = e->nwarps;
     simt::launch(nw, [&](int wid, int lane) { band_ghost_words_body(w.g, above_bottom, below_top, e->ghost_n.data(), e->ghost_s.data(), wid, nw, lane); });
     simt::launch(nw, [&](int wid, int lane) { cross_body(w.g, w.path.data(), w.cross.data(), e->ghost_n.data(), e->ghost_s.data(), wid, nw, lane); });
-    Params p = make_params(w, 1);
+    Params p = make_params(w, e->d.nplanes);
     init_run_body(p, e->d, 60ull * 1000000000ull);
     return 0;
 }
 
 int emu_band_relax(void *h) {
     auto *e = static_cast<Emu_band *>(h);
-    Params p = make_params(e->w, 1);
+    Params p = make_params(e->w, e->d.nplanes);
     int const nw = e->nwarps;
     e->stages.assign(static_cast<size_t>(nw) * STAGE_U64, 0);
     simt::launch(nw, [&](int wid, int lane) { bfs_worker_body(p, lane, e->stages.data() + static_cast<size_t>(wid) * STAGE_U64); }, e->sched);
@@ -428,19 +456,27 @@ int emu_band_relax(void *h) {
 
 int emu_band_export_edges(void *h, uint32_t *top, uint32_t *bottom) {
     auto *e = static_cast<Emu_band *>(h);
-    for (long long i = 0; i < static_cast<long long>(e->w.g.tiles_x) * TS; i++) {
-        band_export_edges_body(e->w.g, e->w.edges[0].data(), top, bottom, i);
+    long long const n = static_cast<long long>(e->w.g.tiles_x) * TS;
+    for (int k = 0; k < e->d.nplanes; k++) {
+        for (long long i = 0; i < n; i++) {
+            band_export_edges_body(e->w.g, e->w.edges[k].data(), top + k * n, bottom + k * n, i);
+        }
     }
     return 0;
 }
 
 int emu_band_import_edges(void *h, uint32_t const *above_bottom, uint32_t const *below_top, uint32_t *activated) {
     auto *e = static_cast<Emu_band *>(h);
-    Params p = make_params(e->w, 1);
+    Params p = make_params(e->w, e->d.nplanes);
     int const nw = e->nwarps;
+    long long const n = static_cast<long long>(e->w.g.tiles_x) * TS;
     *activated = 0;
     band_rearm_body(p, 60ull * 1000000000ull);
-    simt::launch(nw, [&](int wid, int lane) { band_import_edges_body(p, above_bottom, below_top, activated, wid, nw, lane); });
+    for (int k = 0; k < e->d.nplanes; k++) {
+        simt::launch(nw, [&](int wid, int lane) {
+            band_import_edges_body(p, k, above_bottom ? above_bottom + k * n : nullptr, below_top ? below_top + k * n : nullptr, activated, wid, nw, lane);
+        });
+    }
     return 0;
 }
 

@@ -307,6 +307,9 @@ def _gloo_game_worker(rank, world, port, maze_path, out_dir, game, spec):
     if game == "hunt":
         res = bands.sharded_hunt(eng, spec["start"], spec["finish"], r0, n)
         extra = dict(winner=res["winner"], path=res["path"], path_len=res["path_len"])
+    elif game == "corners":
+        res = bands.sharded_corners(eng, spec["starts"], spec["finish"], r0, n)
+        extra = dict(winner=res["winner"], level=res["level"], rounds=res["rounds"])
     else:
         res = bands.sharded_gather(eng, spec["start"], spec["finishes"], r0, n)
         extra = dict(claimed_by=np.asarray(res["claimed_by"]), path_len=np.asarray(res["path_len"]),
@@ -352,6 +355,66 @@ def test_sharded_hunt_and_gather_on_gloo(lab, O, tmp_path, builder, rows, cols, 
             assert (b["claimed_by"] == c_ref).all()
             for k in range(4):
                 assert (b[f"path{k}"] == np.asarray(p_ref[k]).reshape(-1, 2)).all()
+
+
+def _hunt_and_gather_checks(lab, O, tmp_path, maze, world, road, seed=7):
+    import torch.multiprocessing as mp
+
+    placed, s, f = lab.place_hunt(maze, seed=seed)
+    path = str(tmp_path / "maze.npy")
+    np.save(path, placed)
+    spec = {"start": tuple(int(x) for x in s), "finish": tuple(int(x) for x in f)}
+    mp.spawn(_gloo_game_worker, args=(world, _free_port(), path, str(tmp_path), "hunt", spec), nprocs=world, join=True)
+    g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
+    z = [np.load(tmp_path / f"band{r}.npz") for r in range(world)]
+    assert all(str(b["road"]) == road for b in z)
+    assert (np.concatenate([b["sq"] for b in z]) == g_ref).all()
+    for b in z:
+        assert int(b["winner"]) == w_ref and (b["path"] == np.asarray(p_ref)).all() and int(b["path_len"]) == len(p_ref)
+    placed, s, fin = lab.place_gather(maze, seed=seed + 20)
+    np.save(path, placed)
+    spec = {"start": tuple(int(x) for x in s), "finishes": [tuple(int(x) for x in q) for q in fin]}
+    mp.spawn(_gloo_game_worker, args=(world, _free_port(), path, str(tmp_path), "gather", spec), nprocs=world, join=True)
+    g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
+    z = [np.load(tmp_path / f"band{r}.npz") for r in range(world)]
+    got = np.concatenate([b["sq"] for b in z])
+    assert all(str(b["road"]) == road for b in z)
+    assert (got == g_ref).all(), int((got != g_ref).sum())
+    for b in z:
+        assert (b["claimed_by"] == c_ref).all()
+        for k in range(4):
+            assert (b[f"path{k}"] == np.asarray(p_ref[k]).reshape(-1, 2)).all()
+
+
+@pytest.mark.parametrize("builder,mod,rows,cols,world", [("grid", "cross", 191, 131, 2), ("kruskal", "x", 193, 133, 3)])
+def test_sharded_hunt_and_gather_on_general_mazes_on_gloo(lab, O, tmp_path, builder, mod, rows, cols, world):
+    """Mazes with loops (-m cross, -m x: bfs_threads.cc:35-85,144-185 on anything the builders make) across 2-3 bands: the
+    field comes from the tile wave run band by band to its fixpoint, the games' thresholds are applied to it afterwards --
+    grids, claims and canonical paths equal the single-maze canonical model's."""
+    maze = lab.build_maze(builder, rows, cols, seed=43, mod=mod)
+    _hunt_and_gather_checks(lab, O, tmp_path, maze, world, "wave")
+
+
+@pytest.mark.parametrize("builder,mod,rows,cols,world", [("grid", "cross", 191, 131, 2), ("grid", "cross", 257, 67, 3), ("kruskal", None, 193, 131, 3),
+                                                         ("arena", None, 129, 131, 2)])
+def test_sharded_corners_on_gloo(lab, O, tmp_path, builder, mod, rows, cols, world):
+    """Bfs::corners (bfs_threads.cc:420-453; BASELINE configs[3] is grid + cross) across 2-3 bands: four fields searched at
+    once by the wave, four rows of levels per exchange; grid and winner equal the single-maze canonical model's."""
+    import torch.multiprocessing as mp
+
+    maze = lab.build_maze(builder, rows, cols, seed=47, mod=mod)
+    placed, starts, finish = lab.place_corners(maze, seed=5)
+    path = str(tmp_path / "maze.npy")
+    np.save(path, placed)
+    spec = {"starts": [tuple(int(x) for x in q) for q in starts], "finish": tuple(int(x) for x in finish)}
+    mp.spawn(_gloo_game_worker, args=(world, _free_port(), path, str(tmp_path), "corners", spec), nprocs=world, join=True)
+    g_ref, w_ref, p_ref = O.canon_corners(placed, starts, finish)
+    z = [np.load(tmp_path / f"band{r}.npz") for r in range(world)]
+    got = np.concatenate([b["sq"] for b in z])
+    assert (got == g_ref).all(), int((got != g_ref).sum())
+    for b in z:
+        assert int(b["winner"]) == w_ref and int(b["level"]) == len(p_ref)
+    assert int(z[0]["painted"]) == int(((g_ref & 0x00F0) != 0).sum())
 
 
 def test_split_rows(lab):
@@ -400,6 +463,55 @@ def test_band_entry_points_one_process(lab, O, builder, rows, cols, nb):
     got_g = np.concatenate([s.cpu().numpy().view(np.uint16) for s in sq])
     assert (got_d == d_ref).all() and (got_g == g_ref).all()
     assert max(r[0] for r in res) == mx_ref and sum(r[1] for r in res) == settled_ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("builder,mod,rows,cols,nb", [("grid", "cross", 511, 387, 2), ("grid", "cross", 1023, 643, 4), ("kruskal", "x", 447, 259, 3),
+                                                     ("arena", None, 383, 321, 3)])
+def test_gpu_corners_across_bands_one_process(lab, O, builder, mod, rows, cols, nb):
+    """Bfs::corners across 2-4 bands on the CUDA band engine (lab_band_begin_corners, four rows of levels per exchange),
+    several bands driven in lock step by one process: grid and winner equal the canonical model's."""
+    import torch
+
+    from mazes_b200 import bands
+
+    maze = lab.build_maze(builder, rows, cols, seed=53, mod=mod)
+    placed, starts, finish = lab.place_corners(maze, seed=9)
+    split = bands.split_rows(rows, nb)
+    sq = [torch.from_numpy(placed[r0 : r0 + n].view(np.int16).copy()).cuda() for r0, n in split]
+    eng = [bands.GpuBandEngine(lab, s) for s in sq]
+    for e, (r0, n) in zip(eng, split):
+        e.begin_corners([(int(r) - r0, int(c)) if r0 <= r < r0 + n else None for r, c in starts])
+        assert e.L.lab_band_planes(e.h) == 4
+    rows_p = [tuple(t.clone() for t in e.path_rows()) for e in eng]
+    for i, e in enumerate(eng):
+        e.set_neighbour_paths(rows_p[i - 1][1] if i > 0 else None, rows_p[i + 1][0] if i < nb - 1 else None)
+    rounds = 0
+    while True:
+        rounds += 1
+        for e in eng:
+            e.relax()
+        edges = [tuple(t.clone() for t in e.export_edges()) for e in eng]
+        act = [e.import_edges(edges[i - 1][1] if i > 0 else None, edges[i + 1][0] if i < nb - 1 else None) for i, e in enumerate(eng)]
+        if not any(act):
+            break
+        assert rounds < 100000
+    fr, fc = int(finish[0]), int(finish[1])
+    owner = next(i for i, (r0, n) in enumerate(split) if r0 <= fr < r0 + n)
+    levels = [eng[owner].level_at(fr - split[owner][0], fc, k) for k in range(4)]
+    level = min(levels)
+    winner = levels.index(level) if level != bands.INF else -1
+    painted = sum(e.paint([(level, (1 << k) << bands.PAINT_SHIFT, k) for k in range(4)]) for e in eng)
+    for e in eng:
+        e.finish_game()
+    g_ref, w_ref, p_ref = O.canon_corners(placed, starts, finish)
+    got = np.concatenate([s.cpu().numpy().view(np.uint16) for s in sq])
+    assert (got == g_ref).all(), int((got != g_ref).sum())
+    assert winner == w_ref and level == len(p_ref) and painted == int(((g_ref & 0x00F0) != 0).sum())
+    # ... and equal to the one-GPU game on the whole maze
+    with lab.Grid.from_host(placed) as g:
+        res = g.corners(starts, finish, want_path=False)
+        assert (g.download() == g_ref).all() and res.winner == w_ref
 
 
 def _lockstep_tree(eng, split, start, cols):

@@ -11,7 +11,8 @@ import __graft_entry__ as graft
 ap = argparse.ArgumentParser()
 ap.add_argument("--builder", default="kruskal"); ap.add_argument("--rows", type=int, default=4095); ap.add_argument("--cols", type=int, default=4095)
 ap.add_argument("--check", action="store_true"); ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--game", default="distance", choices=["distance", "hunt", "gather"])
+ap.add_argument("--game", default="distance", choices=["distance", "hunt", "gather", "corners"])
+ap.add_argument("--mod", default=None, choices=[None, "cross", "x"], help="-m modification of the maze (loops: the tile wave across bands)")
 ap.add_argument("--super", action="store_true", help="bands of whole super-tile rows (the lattice road across bands)")
 ap.add_argument("--check-property", action="store_true", help="verify every band on the device through the BFS equations (tests/test_properties.py), "
                 "with one halo row of levels from the neighbouring bands: for sizes beyond the oracle's reach")
@@ -29,11 +30,13 @@ if a.cached:
     dist.barrier()
     maze = lab.cached_maze(a.builder, a.rows, a.cols, seed=a.seed, mmap=True)
 else:
-    maze = lab.build_maze(a.builder, a.rows, a.cols, seed=a.seed)
+    maze = lab.build_maze(a.builder, a.rows, a.cols, seed=a.seed, mod=a.mod)
 if a.game != "distance":
     # the sharded solvers: place the game on the host as the reference does, run it band by band, compare with the oracle
     if a.game == "hunt":
         placed, s, f = lab.place_hunt(maze, seed=0xB2000006)
+    elif a.game == "corners":
+        placed, s, f = lab.place_corners(maze, seed=0xB2000008)
     else:
         placed, s, f = lab.place_gather(maze, seed=0xB2000007)
     r0, n = bands.split_rows(a.rows, world)[rank]
@@ -44,16 +47,23 @@ if a.game != "distance":
         t0 = time.perf_counter()
         if a.game == "hunt":
             res = bands.sharded_hunt(eng, tuple(int(x) for x in s), tuple(int(x) for x in f), r0, n)
+        elif a.game == "corners":
+            res = bands.sharded_corners(eng, [tuple(int(x) for x in q) for q in s], tuple(int(x) for x in f), r0, n)
+            res["path_len"] = res["level"]
         else:
             res = bands.sharded_gather(eng, tuple(int(x) for x in s), [tuple(int(x) for x in q) for q in f], r0, n)
         torch.cuda.synchronize()
         t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
             print(json.dumps({"game": a.game, "builder": a.builder, "rows": a.rows, "cols": a.cols, "world": world, "rep": rep,
-                              "wall_ms": round(float(t.item()) * 1e3, 3), "path_len": res["path_len"], "painted": res["painted"], "road": res["road"]}), flush=True)
+                              "wall_ms": round(float(t.item()) * 1e3, 3), "path_len": res["path_len"], "painted": res["painted"], "road": res["road"],
+                              "rounds": res.get("rounds")}), flush=True)
     if a.check:
         O = graft.load_oracle()
-        if a.game == "hunt":
+        if a.game == "corners":
+            g_ref, w_ref, p_ref = O.canon_corners(placed, s, f)
+            ok = bool((sq.cpu().numpy().view(np.uint16) == g_ref[r0:r0 + n]).all() and res["winner"] == w_ref and res["level"] == len(p_ref))
+        elif a.game == "hunt":
             g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
             ok = bool((sq.cpu().numpy().view(np.uint16) == g_ref[r0:r0 + n]).all() and res["winner"] == w_ref and (res["path"] == np.asarray(p_ref)).all())
         else:
