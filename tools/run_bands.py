@@ -68,6 +68,12 @@ if a.game != "distance":
             ok = bool((sq.cpu().numpy().view(np.uint16) == g_ref[r0:r0 + n]).all() and res["winner"] == w_ref and (res["path"] == np.asarray(p_ref)).all())
         else:
             g_ref, c_ref, p_ref = O.canon_gather(placed, s, f)
+            got = sq.cpu().numpy().view(np.uint16)
+            print(f"rank {rank}: grid diffs {int((got != g_ref[r0:r0 + n]).sum())} claimed {list(res['claimed_by'])} vs {list(c_ref)} paths "
+                  f"{[bool(res['paths'][k].shape == np.asarray(p_ref[k]).reshape(-1, 2).shape and (res['paths'][k] == np.asarray(p_ref[k]).reshape(-1, 2)).all()) for k in range(4)]}", flush=True)
+            if (got != g_ref[r0:r0 + n]).any():
+                rr, cc = np.nonzero(got != g_ref[r0:r0 + n])
+                print(f"rank {rank}: first diffs {[(int(a) + r0, int(b), hex(int(got[a, b])), hex(int(g_ref[a + r0, b]))) for a, b in list(zip(rr, cc))[:6]]}", flush=True)
             ok = bool((sq.cpu().numpy().view(np.uint16) == g_ref[r0:r0 + n]).all() and (np.asarray(res["claimed_by"]) == c_ref).all()
                       and all((res["paths"][k] == np.asarray(p_ref[k]).reshape(-1, 2)).all() for k in range(4)))
         print(f"rank {rank}: band rows [{r0},{r0 + n}) {'OK' if ok else 'MISMATCH'}", flush=True)
