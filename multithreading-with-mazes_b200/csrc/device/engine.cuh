@@ -102,6 +102,7 @@ struct Control {
     uint32_t room;
     int32_t room_r0, room_r1, room_c0, room_c1, room_sr, room_sc; // (row bands: relative to the band, see room.cuh)
     uint32_t painted; // the lattice road has applied the paint rules while writing the levels (lattice.cuh): paint_body has nothing to do
+    uint32_t walked;  // ... and has marked the winner's path from the tour's ranks (lat_path_*): hunt's walk has nothing to do
 };
 
 struct Params {

@@ -1137,6 +1137,136 @@ LAB_DEV void lat_targets_body(Params const &p, Lattice const &lt, int warp, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// hunt: the winner's path WITHOUT the walk.  The canonical path (from the finish to the first neighbour one level lower,
+// post.cuh walk_body) is one dependent chain, 10^5-10^6 squares long on the reference's mazes at the headline sizes -- tens
+// of milliseconds for one warp, ten times the search.  On a tree it is the finish's ancestors, and the tour's ranks name
+// them: a component of a tile lies on the path iff the subtree behind one of its crossings holds the finish's component,
+// i.e. iff the rank R_F of that component's entry arc lies between the ranks of the crossing's two arcs (down: the
+// twin's, earlier on the tour, larger R; up: this slot's).  So every tile finds its own SEGMENTS of the path (first
+// squares: the crossing passage if it lies in the tile -- N and W sides -- else the cell at the crossing), and every
+// segment is walked on its own, inside its tile (walk_body, confine): a few hundred steps each, all at once.  Squares are
+// written at their index along the path (finish level - 1 - own level).
+// lat_path_begin_body: one warp.  seg: room for the segments' first squares (flat indices).
+LAB_DEV void lat_path_begin_body(Params const &p, Lattice const &lt, Result *res, int32_t const *finish_rc, uint16_t *grid, int32_t *out,
+                                 unsigned long long max_out, uint32_t *seg, int lane) {
+    Tree_ctl *tc = lt.tc;
+    Control *ctl = p.ctl;
+    Geom const &g = p.g;
+    if (lane == 0) {
+        tc->lat_path_on = 0u;
+        tc->lat_path_nseg = 0u;
+    }
+    if (!lat_live(tc) || !ctl->painted || res->winner < 0) {
+        return;
+    }
+    int const fr = finish_rc[0], fc = finish_rc[1];
+    uint32_t const *dist = p.plane[0].dist;
+    uint32_t const D = dist[static_cast<long long>(fr) * g.cols + fc];
+    if (D == INF || ((fr | fc) & 1) == 0) {
+        return; // (the one-warp walk says what there is to say)
+    }
+    // the finish's component: of the cell that owns the square (a passage is its cell's N or W passage)
+    uint32_t const t = static_cast<uint32_t>((fr / TS) * g.tiles_x + fc / TS);
+    int const i = (fr % TS) >> 1, j = (fc % TS) >> 1;
+    uint32_t const *m = lt.mask + static_cast<long long>(t) * 96;
+    uint32_t const st = lab_ld_cg(m + j) & ~(lab_ld_cg(m + 64 + j) & ~1u);
+    uint32_t const run = static_cast<uint32_t>(31 - lab_clz32(st & (0xFFFFFFFFu >> (31 - i))));
+    uint32_t const comp = lab_ld_cg(lt.cmap + static_cast<long long>(t) * 1024 + run * 32u + static_cast<uint32_t>(j));
+    uint32_t rank = 0; // the entry arc of that component (none: a root's component, nobody's descendant)
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        long long const a = static_cast<long long>(t) * LSLOTS + s * LC + lane;
+        if (((lab_ld_cg(lt.emask + static_cast<long long>(t) * 4 + s) >> lane) & 1u) && lab_ld_cg(lt.label + a) == comp) {
+            rank = lab_ld_cg(lt.R + a);
+        }
+    }
+    rank = lab_reduce_max(rank);
+    if (lane != 0) {
+        return;
+    }
+    uint32_t const repaint = (1u << res->winner) << SQ_PAINT_SHIFT;
+    // the first square of the path, if it lies in the finish's tile: that tile's own segment begins there
+    int const dr[4] = {-1, 0, 1, 0}, dc[4] = {0, 1, 0, -1};
+    for (int k = 0; k < 4 && D > 0; k++) {
+        int const r = fr + dr[k], c = fc + dc[k];
+        if (r >= 0 && r < g.rows && c >= 0 && c < g.cols && dist[static_cast<long long>(r) * g.cols + c] == D - 1u) {
+            if (r / TS == fr / TS && c / TS == fc / TS) {
+                seg[tc->lat_path_nseg++] = static_cast<uint32_t>(r) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(c);
+            }
+            break;
+        }
+    }
+    // the last square is the start (a start on a passage square is in no component)
+    if (D > 0) {
+        uint32_t const t0 = ctl->src_tile[0];
+        long long const sr = static_cast<long long>(t0 / static_cast<uint32_t>(g.tiles_x)) * TS + (ctl->src_rc[0] >> 8);
+        long long const sc = static_cast<long long>(t0 % static_cast<uint32_t>(g.tiles_x)) * TS + (ctl->src_rc[0] & 0xFFu);
+        long long const at = sr * g.cols + sc;
+        grid[at] = static_cast<uint16_t>((grid[at] & ~SQ_PAINT_MASK) | repaint);
+        if (out && D - 1u < max_out) {
+            out[2ull * (D - 1u)] = static_cast<int32_t>(sr);
+            out[2ull * (D - 1u) + 1] = static_cast<int32_t>(sc);
+        }
+        res->walk_r[0] = static_cast<int32_t>(sr);
+        res->walk_c[0] = static_cast<int32_t>(sc);
+    } else {
+        res->walk_r[0] = fr;
+        res->walk_c[0] = fc;
+    }
+    res->path_len[0] = D;
+    res->walk_left[0] = 0;
+    tc->lat_path_rank = rank;
+    tc->lat_path_level = D;
+    tc->lat_path_on = 1u;
+    ctl->walked = 1u;
+}
+// warp per tile: the crossings the path comes up through
+LAB_DEV void lat_path_find_body(Params const &p, Lattice const &lt, uint32_t *seg, uint32_t seg_cap, long long gwarp, long long nwarps, int lane) {
+    Tree_ctl *tc = lt.tc;
+    Geom const &g = p.g;
+    if (!tc->lat_path_on || tc->lat_path_rank == 0u) {
+        return;
+    }
+    uint32_t const RF = tc->lat_path_rank;
+    for (long long t = gwarp; t < g.ntiles; t += nwarps) {
+        long long const base = t * LSLOTS;
+        uint32_t const ty = static_cast<uint32_t>(t / g.tiles_x), tx = static_cast<uint32_t>(t % g.tiles_x);
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            uint32_t const x = lab_ld_cg(lt.xmask + t * 4 + s), e = lab_ld_cg(lt.emask + t * 4 + s);
+            if (((x & ~e) >> lane) & 1u) {
+                uint32_t const up = lab_ld_cg(lt.R + base + s * LC + lane);
+                uint32_t const down = lab_ld_cg(lt.R + lat_twin(g, static_cast<uint32_t>(t), static_cast<uint32_t>(s * LC + lane)));
+                if (up < RF && RF <= down) {
+                    uint32_t const r = ty * TS + (s == L_N ? 0u : (s == L_S ? TS - 1u : 2u * lane + 1u));
+                    uint32_t const c = tx * TS + (s == L_W ? 0u : (s == L_E ? TS - 1u : 2u * lane + 1u));
+                    uint32_t const at = lab_atomic_add(&tc->lat_path_nseg, 1u);
+                    if (at < seg_cap) {
+                        seg[at] = r * static_cast<uint32_t>(g.cols) + c;
+                    }
+                }
+            }
+        }
+    }
+}
+// warp per segment (wid of nw warps; sm: WALK_SM_U32 words)
+LAB_DEV void lat_path_walk_body(Params const &p, Lattice const &lt, Result *res, uint16_t *grid, int32_t *out, unsigned long long max_out,
+                                uint32_t const *seg, uint32_t seg_cap, long long wid, long long nw, int lane, uint32_t *sm) {
+    Tree_ctl const *tc = lt.tc;
+    if (!tc->lat_path_on) {
+        return;
+    }
+    uint32_t const n = tc->lat_path_nseg < seg_cap ? tc->lat_path_nseg : seg_cap, D = tc->lat_path_level;
+    uint32_t const repaint = (1u << res->winner) << SQ_PAINT_SHIFT;
+    for (long long i = wid; i < n; i += nw) {
+        uint32_t const sq = lab_ld_cg(seg + i);
+        int const r = static_cast<int>(sq / static_cast<uint32_t>(p.g.cols)), c = static_cast<int>(sq % static_cast<uint32_t>(p.g.cols));
+        uint32_t const d = p.plane[0].dist[sq];
+        walk_body(p, 0, r, c, grid, out, max_out, repaint, 0, res, 0, lane, sm, 1, D - 1u - d, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row bands: the glue between the phases.  A band runs count + link + local ranking on its own tiles,
 // the ranks put their border-list slices and one header each together (lat_band_header_body -> all-gather, or peer
 // stores), every rank checks the WHOLE maze's counts (lat_band_check_body), finishes the ranking over the whole

@@ -427,9 +427,11 @@ LAB_DEV void walk_flush(Geom const &g, uint32_t const *batch, uint32_t nb, unsig
 }
 
 // include_first: (fr, fc) is itself a square of the path (a walk taken over from the neighbouring band), not the finish.
+// confine: ONE SEGMENT of a path (lattice.cuh, the winner's path without the walk): the walk stays inside the 64x64 tile of
+// (fr, fc) and stops where its next step would leave it; its squares go to out[out_base ...]; `res` is not touched.
 LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int32_t *out,
                        unsigned long long max_out, uint32_t repaint_bits, int first_only, Result *res, int slot,
-                       int lane, uint32_t *sm, int include_first = 0) {
+                       int lane, uint32_t *sm, int include_first = 0, unsigned long long out_base = 0, int confine = 0) {
     Geom const &g = p.g;
     uint32_t const *dist = p.plane[plane].dist;
     bool const room = p.ctl->room != 0; // (single-field games only: the levels are room_level, no field exists)
@@ -439,10 +441,10 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
     // (in a room the finish may lie in another band, outside this one's rows: the closed form does not care)
     uint32_t const d0 = room ? room_absdiff(r, m.sr) + room_absdiff(c, m.sc) : dist[static_cast<long long>(r) * g.cols + c];
     uint32_t d = d0;
-    unsigned long long flushed = 0;
+    unsigned long long flushed = out_base;
     uint32_t nb = 0;
     if (d == INF) {
-        if (lane == 0) {
+        if (lane == 0 && !confine) {
             res->path_len[slot] = 0;
             res->walk_r[slot] = r;
             res->walk_c[slot] = c;
@@ -603,6 +605,10 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
                     handover = true; // (into the neighbouring band)
                     break;
                 }
+                if (confine && (static_cast<unsigned>(lr + ((k & 1) ? 0 : k - 1)) >= 64u || static_cast<unsigned>(lc + ((k & 1) ? 2 - k : 0)) >= 64u)) {
+                    handover = true; // (the segment ends at its tile's border)
+                    break;
+                }
                 idx = static_cast<int>(lab_shfl(static_cast<uint32_t>(cand), k));
                 lr += (k & 1) ? 0 : k - 1;
                 lc += (k & 1) ? 2 - k : 0;
@@ -623,7 +629,7 @@ LAB_DEV void walk_body(Params p, int plane, int fr, int fc, uint16_t *grid, int3
     }
     unsigned long long const n = flushed + nb; // squares walked
     walk_flush(g, batch, nb, flushed, grid, out, max_out, repaint_bits, lane);
-    if (lane == 0) {
+    if (lane == 0 && !confine) {
         res->path_len[slot] = first_only ? static_cast<unsigned long long>(d0) : n;
         res->walk_r[slot] = r;
         res->walk_c[slot] = c;

@@ -230,6 +230,19 @@ template <int MODE> __global__ void __launch_bounds__(128, MODE == LAT_PAINT ? 6
     __shared__ uint32_t sm[4][L_LINK_SM];
     lat_levels_body<MODE>(p, lt, lane_id(), sm[threadIdx.x >> 5], res, grid);
 }
+// hunt on the lattice road: the winner's path from the tour's ranks (lat_path_*), every segment walked on its own
+__global__ void k_lat_path_begin(Params p, Lattice lt, Result *res, int32_t const *finish_rc, uint16_t *grid, int32_t *out, unsigned long long max_out,
+                                 uint32_t *seg) {
+    lat_path_begin_body(p, lt, res, finish_rc, grid, out, max_out, seg, lane_id());
+}
+__global__ void __launch_bounds__(256) k_lat_path_find(Params p, Lattice lt, uint32_t *seg, uint32_t seg_cap) {
+    lat_path_find_body(p, lt, seg, seg_cap, gwarp_id(), nwarps_total(), lane_id());
+}
+__global__ void k_lat_path_walk(Params p, Lattice lt, Result *res, uint16_t *grid, int32_t *out, unsigned long long max_out, uint32_t const *seg,
+                                uint32_t seg_cap) {
+    __shared__ uint32_t sm[WALK_SM_U32]; // one warp per block
+    lat_path_walk_body(p, lt, res, grid, out, max_out, seg, seg_cap, blockIdx.x, gridDim.x, lane_id(), sm);
+}
 // hunt / gather on the lattice road: the finishes' levels and the paint rules BEFORE the field is written (lat_targets_body)
 __global__ void __launch_bounds__(128) k_lat_targets(Params p, Lattice lt, Run_desc d, Result *res, int32_t const *finish_rc) {
     __shared__ uint32_t sm[4][L_LINK_SM];
@@ -298,6 +311,10 @@ __global__ void k_walk(Params p, int game, uint16_t *grid, Result *res, int32_t 
     int const slot = static_cast<int>(blockIdx.x);
     int plane = 0, fj = 0;
     uint32_t repaint = 0;
+    if (game == GAME_HUNT && p.ctl->walked) { // lat_path_*: the path is marked and written already; its length is the finish's level
+        if (lane_id() == 0) res->path_len[slot] = res->game_level[0];
+        return;
+    }
     if (game == GAME_HUNT) {
         if (res->winner < 0) {
             if (lane_id() == 0) res->path_len[slot] = 0;
@@ -458,6 +475,8 @@ struct lab_grid {
     bool tree_alloc = false;
     Tree_ctl tree_last{};
     bool tree_tried = false;
+    int32_t *hunt_out = nullptr; // where hunt's winner path goes (solver_common sets both before the search; null: not wanted)
+    unsigned long long hunt_out_cap = 0;
     Lattice lat{}; // the lattice road's workspace (allocated on first use)
     bool lat_alloc = false;
     Lattice band_lat{}; // ... across row bands (lab_band_lat_*): whole-maze geometry, the caller's whole-maze arrays
@@ -783,6 +802,17 @@ int run_lattice(lab_grid *h, Params const &p, Run_desc const &d) {
         TRACE("k_lat_targets", s);
         k_lat_levels<LAT_PAINT><<<tile_blocks, 128, 0, s>>>(p, lt, h->res, h->squares);
         h->launches += 1;
+        if (d.game == GAME_HUNT && env_ll("LAB_LAT_PATH", 1) != 0) {
+            // the winner's path, painted over the colours just applied (k_walk then returns at once).  The segments' list
+            // borrows the local ranking's pair array, which nobody reads after k_lat_rank_expand.
+            uint32_t *seg = reinterpret_cast<uint32_t *>(lt.xd);
+            uint32_t const seg_cap = lt.nslots;
+            k_lat_path_begin<<<1, 32, 0, s>>>(p, lt, h->res, h->d_finish_rc, h->squares, h->hunt_out, h->hunt_out_cap, seg);
+            k_lat_path_find<<<blocks_for(h, nt, 256), 256, 0, s>>>(p, lt, seg, seg_cap);
+            k_lat_path_walk<<<h->sm_count * 8, 32, 0, s>>>(p, lt, h->res, h->squares, h->hunt_out, h->hunt_out_cap, seg, seg_cap);
+            TRACE("k_lat_path_walk", s);
+            h->launches += 3;
+        }
     } else {
         k_lat_levels<LAT_LEVELS><<<tile_blocks, 128, 0, s>>>(p, lt, nullptr, nullptr);
     }
@@ -1464,7 +1494,18 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
     }
     cudaStream_t s = h->stream;
     CU(cudaMemcpyAsync(h->d_finish_rc, frc, sizeof frc, cudaMemcpyHostToDevice, s));
-    int rc = run_search(h, d, SQ_PATH, SQ_PATH); // passable <=> path_bit (bfs_threads.cc:71-72)
+    int rc = LAB_OK;
+    h->hunt_out = nullptr;
+    h->hunt_out_cap = 0;
+    if (d.game == GAME_HUNT && want_paths) { // (the lattice road writes the winner's path itself: it needs the buffer before the search)
+        rc = ensure_paths(h, path_cap);
+        if (rc) {
+            return rc;
+        }
+        h->hunt_out = h->d_paths;
+        h->hunt_out_cap = path_cap;
+    }
+    rc = run_search(h, d, SQ_PATH, SQ_PATH); // passable <=> path_bit (bfs_threads.cc:71-72)
     if (rc) {
         return rc;
     }

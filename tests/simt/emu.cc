@@ -31,11 +31,15 @@ int g_tree_mode = 1;      // 0: never, 1: when the counts allow it (as csrc/lab.
 int g_lattice_mode = 1;   // 0: the general pipeline only, 1: the lattice road first (as csrc/lab.cu does)
 Tree_ctl g_tree_last{};
 int g_paint_fused = 0; // the last search applied the solvers' paint rules inside lat_levels_body
+int g_path_segments = -1; // ... and marked hunt's winner path from the tour's ranks: segments walked (-1: it did not)
+int32_t *g_hunt_out = nullptr; // where hunt's path goes (set by emu_solver before the search, as solver_common does)
+unsigned long long g_hunt_out_cap = 0;
 
 // The spanning-tree pipeline, orchestrated as run_tree() in csrc/lab.cu does.
 void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned sched_seed) {
     g_tree_last = Tree_ctl{};
     g_paint_fused = 0;
+    g_path_segments = -1;
     if (d.nplanes != 1 || d.src_r[0] < 0 || !g_tree_mode) return;
     size_t const nt = static_cast<size_t>(w.g.ntiles);
     size_t const n = nt * SLOTS + 2;
@@ -99,6 +103,17 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
                 g_paint_fused = 1;
             }
             simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body<LAT_PAINT>(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS, &w.res, w.grid_ptr); }, sched_seed);
+            if (d.game == GAME_HUNT) { // the winner's path from the tour's ranks, as run_lattice() launches it
+                uint32_t *seg = reinterpret_cast<uint32_t *>(xd.data());
+                uint32_t const seg_cap = lt.nslots;
+                simt::launch(1, [&](int, int lane) { lat_path_begin_body(p, lt, &w.res, frc, w.grid_ptr, g_hunt_out, g_hunt_out_cap, seg, lane); });
+                simt::launch(nwarps, [&](int wid, int lane) { lat_path_find_body(p, lt, seg, seg_cap, wid, nwarps, lane); });
+                std::vector<uint32_t> wsm(static_cast<size_t>(nwarps) * WALK_SM_U32);
+                simt::launch(nwarps, [&](int wid, int lane) {
+                    lat_path_walk_body(p, lt, &w.res, w.grid_ptr, g_hunt_out, g_hunt_out_cap, seg, seg_cap, wid, nwarps, lane, wsm.data() + static_cast<size_t>(wid) * WALK_SM_U32);
+                });
+                if (tc.lat_path_on) g_path_segments = static_cast<int>(tc.lat_path_nseg);
+            }
         } else {
             simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body<LAT_LEVELS>(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS, nullptr, nullptr); }, sched_seed);
         }
@@ -221,6 +236,7 @@ int emu_last_lattice_error(void) { return static_cast<int>(g_tree_last.lat_err);
 // 0: the tile wave made the field; 1: the tree pipeline did
 int emu_last_tree_used(void) { return static_cast<int>(g_tree_last.used); }
 int emu_last_paint_fused(void) { return g_paint_fused; }
+int emu_last_path_segments(void) { return g_path_segments; }
 
 int emu_distance(int rows, int cols, uint16_t *grid, int sr, int sc, uint32_t *dist_out, uint64_t *max_out,
                  uint64_t *settled_out, int nwarps, unsigned sched_seed, uint64_t *stats) {
@@ -814,7 +830,10 @@ int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *star
         frc[0] = finishes[0];
         frc[1] = finishes[1];
     }
+    g_hunt_out = game == GAME_HUNT ? paths_out : nullptr;
+    g_hunt_out_cap = game == GAME_HUNT ? static_cast<unsigned long long>(max_path) : 0ull;
     int rc = search(w, grid, rows, cols, d, SQ_PATH, SQ_PATH, nwarps, sched_seed);
+    g_hunt_out = nullptr;
     if (rc) return rc;
     Params p = make_params(w, d.nplanes);
     resolve_body(p, d, &w.res, frc);
@@ -825,6 +844,10 @@ int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *star
     auto walk = [&](int slot, int32_t *out, unsigned long long max_out, int first_only) {
         int plane = 0, fj = 0;
         uint32_t repaint = 0;
+        if (game == GAME_HUNT && w.ctl.walked) { // (k_walk: lat_path_* has marked and written the path)
+            w.res.path_len[slot] = w.res.game_level[0];
+            return;
+        }
         if (game == GAME_HUNT) {
             if (w.res.winner < 0) return;
             repaint = (1u << w.res.winner) << SQ_PAINT_SHIFT;

@@ -156,6 +156,7 @@ def test_emulated_games_on_the_lattice(lab, O, emu):
         g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
         g, w, _, paths, _ = emu.solver(1, placed, [s], [f], 4, 1)
         assert emu.lib.emu_last_tree_used() == LATTICE and emu.lib.emu_last_paint_fused() == 1  # (paint rules applied by the levels kernel)
+        assert emu.lib.emu_last_path_segments() >= 1 or len(p_ref) <= 1  # (the winner's path came from the tour's ranks, in segments)
         seen.add((s[0] % 2, s[1] % 2))
         assert (g == g_ref).all() and w == w_ref and paths_equal([paths[0]], [p_ref])
     assert len(seen) >= 2  # starts on cells and on passages
