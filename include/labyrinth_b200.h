@@ -285,6 +285,15 @@ int lab_band_lat_set_peers(lab_grid *g, int n, void *const *border_lists, void *
 int lab_band_lat_link(lab_grid *g, void *header_dev);
 int lab_band_lat_flood(lab_grid *g, const void *all_headers_dev, int world, int zero_weights);
 int lab_band_lat_levels(lab_grid *g, int32_t *used);
+/* hunt's winner path on the lattice road across bands WITHOUT hand-overs (the tour's ranks are the whole maze's: every band finds
+ * and walks the path's segments in its own rows; csrc/device/lattice.cuh lat_path_*; replaces the walk of
+ * solvers/bfs_threads.cc:263-274's repaint).  _rank: the band that holds the finish -> rank of the entry arc of the finish's
+ * component (0: a root's component) and the finish's level; the caller tells every band.  _mark: (fin_r, fin_c) / (start_r,
+ * start_c) in band rows, -1 if in another band; path_dev: NULL or path_cap (row, col) pairs written at the squares' indices
+ * along the whole path (band rows); repaint_bits != 0: the paint nibble of the path's squares := bits. */
+int lab_band_lat_path_rank(lab_grid *g, int r, int c, uint32_t *rank, uint32_t *level);
+int lab_band_lat_path_mark(lab_grid *g, uint32_t rank, uint32_t level, int fin_r, int fin_c, int start_r, int start_c, uint32_t repaint_bits,
+                           void *path_dev, uint64_t path_cap, uint64_t *segments);
 
 /* ---- one process, several GPUs --------------------------------------------------------------- */
 /* The reference is one process with one Maze (run_maze/run_maze.cc:182); this lets its entry points use the whole box

@@ -43,6 +43,7 @@ ABI_SYMBOLS = (
     "lab_band_lat_levels",
     "lab_band_begin_game", "lab_band_level_at", "lab_band_paint", "lab_band_walk", "lab_band_recolour", "lab_band_finish_game",
     "lab_band_begin_corners", "lab_band_planes", "lab_band_level_at_plane", "lab_band_paint_planes",
+    "lab_band_lat_path_rank", "lab_band_lat_path_mark",
 )
 
 

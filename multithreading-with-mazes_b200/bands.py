@@ -283,6 +283,22 @@ class _BandEngine:
     def lat_flood(self, all_hdr, world: int, zero_weights: bool):
         self._check(self._f("lat_flood")(self.h, self._ptr(all_hdr), c_int(world), c_int(1 if zero_weights else 0)))
 
+    def lat_path_rank(self, r: int, c: int) -> Tuple[int, int]:
+        """(rank of the entry arc of the component that holds band square (r, c), the square's level)"""
+        rank, level = c_uint32(), c_uint32()
+        self._check(self._f("lat_path_rank")(self.h, c_int(r), c_int(c), byref(rank), byref(level)))
+        return int(rank.value), int(level.value)
+
+    def lat_path_mark(self, rank: int, level: int, fin_local, start_local, repaint_bits: int, path_buf=None) -> int:
+        """Marks this band's squares of the finish -> start path (no hand-over between bands) -> segments walked here"""
+        fr, fc = fin_local if fin_local is not None else (-1, -1)
+        sr, sc = start_local if start_local is not None else (-1, -1)
+        n = c_uint64()
+        cap = int(path_buf.shape[0]) if path_buf is not None else 0
+        self._check(self._f("lat_path_mark")(self.h, c_uint32(rank), c_uint32(level), c_int(fr), c_int(fc), c_int(sr), c_int(sc), c_uint32(repaint_bits),
+                                             self._ptr(path_buf), c_uint64(cap), byref(n)))
+        return int(n.value)
+
     def lat_levels(self) -> bool:
         used = ctypes.c_int32()
         self._check(self._f("lat_levels")(self.h, byref(used)))
@@ -595,7 +611,7 @@ def _sharded_field(engine, game, start_global, row0, rows_local, group):
     engine.set_neighbour_paths(above_bottom, below_top)
     road = False
     if lattice_layout is not None and _sharded_lattice(engine, lattice_layout, group, tr):
-        road = True  # (the lattice road leaves the same level field the general pipeline does)
+        return "lattice"  # (the same level field the general pipeline leaves; the tour's ranks stay for lat_path_*)
     if not road:
         road = _sharded_tree(engine, start_global, row0, rows_local, group, tr)
     if not road:
@@ -676,6 +692,31 @@ def _walk_path(engine, road, finish, start_global, level, repaint_bits, want_pat
     return full[:level].cpu().numpy()
 
 
+def _lattice_path(engine, finish, start_global, level, repaint_bits, want_path, row0, rows_local, group):
+    """The finish -> start path on the lattice road, no hand-over: the band that holds the finish reads the rank of the entry
+    arc of the finish's component (one all-gather of two ints), then every band marks the path's segments in its own rows
+    from the whole-maze tour ranks it already holds, at their indices along the path."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    here = lambda sq: row0 <= sq[0] < row0 + rows_local
+    mine = list(engine.lat_path_rank(finish[0] - row0, finish[1])) + [1] if here(finish) else [0, 0, 0]
+    rank_f, level_f, _ = next(v for v in _gather_ints(engine, mine, group) if v[2] == 1)
+    assert level_f == level
+    full = torch.full((level, 2), -1, dtype=torch.int32, device=engine.row_device) if want_path else None
+    engine.lat_path_mark(rank_f, level, (finish[0] - row0, finish[1]) if here(finish) else None,
+                         (start_global[0] - row0, start_global[1]) if here(start_global) else None, repaint_bits, full)
+    if not want_path:
+        return None
+    full[:, 0] = torch.where(full[:, 0] >= 0, full[:, 0] + row0, full[:, 0])
+    if world > 1:
+        every = torch.empty((world,) + tuple(full.shape), dtype=torch.int32, device=engine.row_device)
+        _all_gather(dist, every.view(-1), full.view(-1), world, group)
+        full = every.max(dim=0).values
+    return full.cpu().numpy()
+
+
 def sharded_hunt(engine, start_global, finish_global, row0: int, rows_local: int, group=None, want_path: bool = True):
     """Bfs::hunt on this rank's band (the caller placed start_bit / finish_bit).  Collective.
     -> {"winner", "path_len", "path" (global (row, col) pairs or None), "painted", "road"}"""
@@ -685,7 +726,10 @@ def sharded_hunt(engine, start_global, finish_global, row0: int, rows_local: int
         engine.finish_game()
         return {"winner": -1, "path_len": 0, "path": None, "painted": 0, "road": road}
     painted = engine.paint([(level, PAINT_MASK)])
-    path = _walk_path(engine, road, finish_global, start_global, level, 1 << PAINT_SHIFT, want_path, row0, rows_local, group)
+    if road == "lattice" and level > 0:
+        path = _lattice_path(engine, finish_global, start_global, level, 1 << PAINT_SHIFT, want_path, row0, rows_local, group)
+    else:
+        path = _walk_path(engine, road, finish_global, start_global, level, 1 << PAINT_SHIFT, want_path, row0, rows_local, group)
     engine.finish_game()
     painted = sum(v[0] for v in _gather_ints(engine, [painted], group))
     return {"winner": 0, "path_len": level, "path": path, "painted": painted, "road": road}

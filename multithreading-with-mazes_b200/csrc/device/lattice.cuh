@@ -1146,7 +1146,63 @@ LAB_DEV void lat_targets_body(Params const &p, Lattice const &lt, int warp, int 
 // squares: the crossing passage if it lies in the tile -- N and W sides -- else the cell at the crossing), and every
 // segment is walked on its own, inside its tile (walk_body, confine): a few hundred steps each, all at once.  Squares are
 // written at their index along the path (finish level - 1 - own level).
-// lat_path_begin_body: one warp.  seg: room for the segments' first squares (flat indices).
+// Row bands: the ranks are the whole maze's, so every band finds and walks the segments in its own rows with no hand-over
+// at all; the band that holds the finish tells the others R_F and the finish's level (lat_path_rank_body), every band
+// then runs lat_path_setup_body + find + walk (lab_band_lat_path_*).
+// rank of the entry arc of the component that holds square (fr, fc) of this band (0: a root's component).  One warp.
+LAB_DEV uint32_t lat_path_rank_body(Params const &p, Lattice const &lt, int fr, int fc, int lane) {
+    Geom const &g = p.g;
+    // the component of the cell that owns the square (a passage is its cell's N or W passage)
+    uint32_t const t = static_cast<uint32_t>((fr / TS) * g.tiles_x + fc / TS);
+    int const i = (fr % TS) >> 1, j = (fc % TS) >> 1;
+    uint32_t const *m = lt.mask + static_cast<long long>(t) * 96;
+    uint32_t const st = lab_ld_cg(m + j) & ~(lab_ld_cg(m + 64 + j) & ~1u);
+    uint32_t const run = static_cast<uint32_t>(31 - lab_clz32(st & (0xFFFFFFFFu >> (31 - i))));
+    uint32_t const comp = lab_ld_cg(lt.cmap + static_cast<long long>(t) * 1024 + run * 32u + static_cast<uint32_t>(j));
+    uint32_t rank = 0;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        long long const a = static_cast<long long>(t) * LSLOTS + s * LC + lane;
+        if (((lab_ld_cg(lt.emask + static_cast<long long>(t) * 4 + s) >> lane) & 1u) && lab_ld_cg(lt.label + a) == comp) {
+            rank = lab_ld_cg(lt.R + a);
+        }
+    }
+    return lab_reduce_max(rank);
+}
+// One thread.  (fr, fc) / (sr, sc): the finish / the start in this grid's rows, fr < 0 / sr < 0: in another band.
+LAB_DEV void lat_path_setup_body(Params const &p, Lattice const &lt, uint32_t rank, uint32_t D, int fr, int fc, int sr, int sc, uint32_t repaint,
+                                 uint16_t *grid, int32_t *out, unsigned long long max_out, uint32_t *seg) {
+    Tree_ctl *tc = lt.tc;
+    Geom const &g = p.g;
+    uint32_t const *dist = p.plane[0].dist;
+    tc->lat_path_nseg = 0u;
+    // the first square of the path, if it lies in the finish's tile: that tile's own segment begins there
+    int const dr[4] = {-1, 0, 1, 0}, dc[4] = {0, 1, 0, -1};
+    for (int k = 0; k < 4 && D > 0 && fr >= 0; k++) {
+        int const r = fr + dr[k], c = fc + dc[k];
+        if (r >= 0 && r < g.rows && c >= 0 && c < g.cols && dist[static_cast<long long>(r) * g.cols + c] == D - 1u) {
+            if (r / TS == fr / TS && c / TS == fc / TS) {
+                seg[tc->lat_path_nseg++] = static_cast<uint32_t>(r) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(c);
+            }
+            break;
+        }
+    }
+    // the last square is the start (a start on a passage square is in no component)
+    if (D > 0 && sr >= 0) {
+        long long const at = static_cast<long long>(sr) * g.cols + sc;
+        if (repaint) {
+            grid[at] = static_cast<uint16_t>((grid[at] & ~SQ_PAINT_MASK) | repaint);
+        }
+        if (out && D - 1u < max_out) {
+            out[2ull * (D - 1u)] = sr;
+            out[2ull * (D - 1u) + 1] = sc;
+        }
+    }
+    tc->lat_path_rank = rank;
+    tc->lat_path_level = D;
+    tc->lat_path_on = 1u;
+}
+// lat_path_begin_body: one warp, one GPU.  seg: room for the segments' first squares (flat indices).
 LAB_DEV void lat_path_begin_body(Params const &p, Lattice const &lt, Result *res, int32_t const *finish_rc, uint16_t *grid, int32_t *out,
                                  unsigned long long max_out, uint32_t *seg, int lane) {
     Tree_ctl *tc = lt.tc;
@@ -1160,64 +1216,22 @@ LAB_DEV void lat_path_begin_body(Params const &p, Lattice const &lt, Result *res
         return;
     }
     int const fr = finish_rc[0], fc = finish_rc[1];
-    uint32_t const *dist = p.plane[0].dist;
-    uint32_t const D = dist[static_cast<long long>(fr) * g.cols + fc];
+    uint32_t const D = p.plane[0].dist[static_cast<long long>(fr) * g.cols + fc];
     if (D == INF || ((fr | fc) & 1) == 0) {
         return; // (the one-warp walk says what there is to say)
     }
-    // the finish's component: of the cell that owns the square (a passage is its cell's N or W passage)
-    uint32_t const t = static_cast<uint32_t>((fr / TS) * g.tiles_x + fc / TS);
-    int const i = (fr % TS) >> 1, j = (fc % TS) >> 1;
-    uint32_t const *m = lt.mask + static_cast<long long>(t) * 96;
-    uint32_t const st = lab_ld_cg(m + j) & ~(lab_ld_cg(m + 64 + j) & ~1u);
-    uint32_t const run = static_cast<uint32_t>(31 - lab_clz32(st & (0xFFFFFFFFu >> (31 - i))));
-    uint32_t const comp = lab_ld_cg(lt.cmap + static_cast<long long>(t) * 1024 + run * 32u + static_cast<uint32_t>(j));
-    uint32_t rank = 0; // the entry arc of that component (none: a root's component, nobody's descendant)
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-        long long const a = static_cast<long long>(t) * LSLOTS + s * LC + lane;
-        if (((lab_ld_cg(lt.emask + static_cast<long long>(t) * 4 + s) >> lane) & 1u) && lab_ld_cg(lt.label + a) == comp) {
-            rank = lab_ld_cg(lt.R + a);
-        }
-    }
-    rank = lab_reduce_max(rank);
+    uint32_t const rank = lat_path_rank_body(p, lt, fr, fc, lane);
     if (lane != 0) {
         return;
     }
-    uint32_t const repaint = (1u << res->winner) << SQ_PAINT_SHIFT;
-    // the first square of the path, if it lies in the finish's tile: that tile's own segment begins there
-    int const dr[4] = {-1, 0, 1, 0}, dc[4] = {0, 1, 0, -1};
-    for (int k = 0; k < 4 && D > 0; k++) {
-        int const r = fr + dr[k], c = fc + dc[k];
-        if (r >= 0 && r < g.rows && c >= 0 && c < g.cols && dist[static_cast<long long>(r) * g.cols + c] == D - 1u) {
-            if (r / TS == fr / TS && c / TS == fc / TS) {
-                seg[tc->lat_path_nseg++] = static_cast<uint32_t>(r) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(c);
-            }
-            break;
-        }
-    }
-    // the last square is the start (a start on a passage square is in no component)
-    if (D > 0) {
-        uint32_t const t0 = ctl->src_tile[0];
-        long long const sr = static_cast<long long>(t0 / static_cast<uint32_t>(g.tiles_x)) * TS + (ctl->src_rc[0] >> 8);
-        long long const sc = static_cast<long long>(t0 % static_cast<uint32_t>(g.tiles_x)) * TS + (ctl->src_rc[0] & 0xFFu);
-        long long const at = sr * g.cols + sc;
-        grid[at] = static_cast<uint16_t>((grid[at] & ~SQ_PAINT_MASK) | repaint);
-        if (out && D - 1u < max_out) {
-            out[2ull * (D - 1u)] = static_cast<int32_t>(sr);
-            out[2ull * (D - 1u) + 1] = static_cast<int32_t>(sc);
-        }
-        res->walk_r[0] = static_cast<int32_t>(sr);
-        res->walk_c[0] = static_cast<int32_t>(sc);
-    } else {
-        res->walk_r[0] = fr;
-        res->walk_c[0] = fc;
-    }
+    uint32_t const t0 = ctl->src_tile[0];
+    int const sr = static_cast<int>(t0 / static_cast<uint32_t>(g.tiles_x)) * TS + static_cast<int>(ctl->src_rc[0] >> 8);
+    int const sc = static_cast<int>(t0 % static_cast<uint32_t>(g.tiles_x)) * TS + static_cast<int>(ctl->src_rc[0] & 0xFFu);
+    lat_path_setup_body(p, lt, rank, D, fr, fc, sr, sc, (1u << res->winner) << SQ_PAINT_SHIFT, grid, out, max_out, seg);
+    res->walk_r[0] = D > 0 ? sr : fr;
+    res->walk_c[0] = D > 0 ? sc : fc;
     res->path_len[0] = D;
     res->walk_left[0] = 0;
-    tc->lat_path_rank = rank;
-    tc->lat_path_level = D;
-    tc->lat_path_on = 1u;
     ctl->walked = 1u;
 }
 // warp per tile: the crossings the path comes up through
@@ -1236,7 +1250,10 @@ LAB_DEV void lat_path_find_body(Params const &p, Lattice const &lt, uint32_t *se
             uint32_t const x = lab_ld_cg(lt.xmask + t * 4 + s), e = lab_ld_cg(lt.emask + t * 4 + s);
             if (((x & ~e) >> lane) & 1u) {
                 uint32_t const up = lab_ld_cg(lt.R + base + s * LC + lane);
-                uint32_t const down = lab_ld_cg(lt.R + lat_twin(g, static_cast<uint32_t>(t), static_cast<uint32_t>(s * LC + lane)));
+                uint32_t const tw = lat_twin(g, static_cast<uint32_t>(t) + lt.tile_base, static_cast<uint32_t>(s * LC + lane)); // (global arc id)
+                uint32_t const twl = tw - lt.tile_base * LSLOTS;
+                // (a twin in another band is a border arc of its super-tile: its hops are in the whole-maze border list)
+                uint32_t const down = twl < lt.nslots ? lab_ld_cg(lt.R + twl) : static_cast<uint32_t>(lab_ld_cg(lt.gb + lat_dense_border(lt, g, tw)) >> 32);
                 if (up < RF && RF <= down) {
                     uint32_t const r = ty * TS + (s == L_N ? 0u : (s == L_S ? TS - 1u : 2u * lane + 1u));
                     uint32_t const c = tx * TS + (s == L_W ? 0u : (s == L_E ? TS - 1u : 2u * lane + 1u));
@@ -1250,14 +1267,13 @@ LAB_DEV void lat_path_find_body(Params const &p, Lattice const &lt, uint32_t *se
     }
 }
 // warp per segment (wid of nw warps; sm: WALK_SM_U32 words)
-LAB_DEV void lat_path_walk_body(Params const &p, Lattice const &lt, Result *res, uint16_t *grid, int32_t *out, unsigned long long max_out,
+LAB_DEV void lat_path_walk_body(Params const &p, Lattice const &lt, Result *res, uint32_t repaint, uint16_t *grid, int32_t *out, unsigned long long max_out,
                                 uint32_t const *seg, uint32_t seg_cap, long long wid, long long nw, int lane, uint32_t *sm) {
     Tree_ctl const *tc = lt.tc;
     if (!tc->lat_path_on) {
         return;
     }
     uint32_t const n = tc->lat_path_nseg < seg_cap ? tc->lat_path_nseg : seg_cap, D = tc->lat_path_level;
-    uint32_t const repaint = (1u << res->winner) << SQ_PAINT_SHIFT;
     for (long long i = wid; i < n; i += nw) {
         uint32_t const sq = lab_ld_cg(seg + i);
         int const r = static_cast<int>(sq / static_cast<uint32_t>(p.g.cols)), c = static_cast<int>(sq % static_cast<uint32_t>(p.g.cols));

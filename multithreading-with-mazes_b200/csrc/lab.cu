@@ -238,10 +238,27 @@ __global__ void k_lat_path_begin(Params p, Lattice lt, Result *res, int32_t cons
 __global__ void __launch_bounds__(256) k_lat_path_find(Params p, Lattice lt, uint32_t *seg, uint32_t seg_cap) {
     lat_path_find_body(p, lt, seg, seg_cap, gwarp_id(), nwarps_total(), lane_id());
 }
-__global__ void k_lat_path_walk(Params p, Lattice lt, Result *res, uint16_t *grid, int32_t *out, unsigned long long max_out, uint32_t const *seg,
-                                uint32_t seg_cap) {
+// repaint_bits == 0xFFFFFFFF: the winner's colour (Result::winner, known on the device only)
+__global__ void k_lat_path_walk(Params p, Lattice lt, Result *res, uint32_t repaint_bits, uint16_t *grid, int32_t *out, unsigned long long max_out,
+                                uint32_t const *seg, uint32_t seg_cap) {
     __shared__ uint32_t sm[WALK_SM_U32]; // one warp per block
-    lat_path_walk_body(p, lt, res, grid, out, max_out, seg, seg_cap, blockIdx.x, gridDim.x, lane_id(), sm);
+    if (!lt.tc->lat_path_on) {
+        return;
+    }
+    uint32_t const repaint = repaint_bits == 0xFFFFFFFFu ? (1u << res->winner) << SQ_PAINT_SHIFT : repaint_bits;
+    lat_path_walk_body(p, lt, res, repaint, grid, out, max_out, seg, seg_cap, blockIdx.x, gridDim.x, lane_id(), sm);
+}
+// row bands (lab_band_lat_path_*)
+__global__ void k_lat_path_rank(Params p, Lattice lt, int r, int c, uint32_t *out2) {
+    uint32_t const rank = lat_path_rank_body(p, lt, r, c, lane_id());
+    if (lane_id() == 0) {
+        out2[0] = rank;
+        out2[1] = p.plane[0].dist[static_cast<long long>(r) * p.g.cols + c];
+    }
+}
+__global__ void k_lat_path_setup(Params p, Lattice lt, uint32_t rank, uint32_t level, int fr, int fc, int sr, int sc, uint32_t repaint, uint16_t *grid,
+                                 int32_t *out, unsigned long long max_out, uint32_t *seg) {
+    lat_path_setup_body(p, lt, rank, level, fr, fc, sr, sc, repaint, grid, out, max_out, seg);
 }
 // hunt / gather on the lattice road: the finishes' levels and the paint rules BEFORE the field is written (lat_targets_body)
 __global__ void __launch_bounds__(128) k_lat_targets(Params p, Lattice lt, Run_desc d, Result *res, int32_t const *finish_rc) {
@@ -809,7 +826,7 @@ int run_lattice(lab_grid *h, Params const &p, Run_desc const &d) {
             uint32_t const seg_cap = lt.nslots;
             k_lat_path_begin<<<1, 32, 0, s>>>(p, lt, h->res, h->d_finish_rc, h->squares, h->hunt_out, h->hunt_out_cap, seg);
             k_lat_path_find<<<blocks_for(h, nt, 256), 256, 0, s>>>(p, lt, seg, seg_cap);
-            k_lat_path_walk<<<h->sm_count * 8, 32, 0, s>>>(p, lt, h->res, h->squares, h->hunt_out, h->hunt_out_cap, seg, seg_cap);
+            k_lat_path_walk<<<h->sm_count * 8, 32, 0, s>>>(p, lt, h->res, 0xFFFFFFFFu, h->squares, h->hunt_out, h->hunt_out_cap, seg, seg_cap);
             TRACE("k_lat_path_walk", s);
             h->launches += 3;
         }
@@ -2004,6 +2021,57 @@ int lab_band_lat_levels(lab_grid *h, int32_t *used) {
     if (used) {
         *used = c.used == 3u ? 1 : 0;
     }
+    return LAB_OK;
+}
+
+// hunt's winner path on the lattice road across bands, no hand-over (bands.sharded_hunt; lattice.cuh lat_path_*): the band
+// that holds the finish reads the rank of the entry arc of the finish's component and the finish's level ...
+int lab_band_lat_path_rank(lab_grid *h, int r, int c, uint32_t *rank, uint32_t *level) {
+    Device_guard const guard_(h);
+    int rc = band_lat_ready(h, "lab_band_lat_path_rank");
+    if (rc) return rc;
+    if (!rank || !level || !in_grid(h, {r, c}) || ((r | c) & 1) == 0) {
+        return fail(LAB_ERR_ARG, "lab_band_lat_path_rank: bad argument");
+    }
+    cudaStream_t s = h->stream;
+    Params p = make_params(h, 1);
+    uint32_t *d2 = reinterpret_cast<uint32_t *>(h->band_lat.xd); // (the local ranking's pairs: nobody reads them any more)
+    k_lat_path_rank<<<1, 32, 0, s>>>(p, h->band_lat, r, c, d2);
+    h->launches += 1;
+    uint32_t out2[2] = {0, 0};
+    CU(cudaMemcpyAsync(out2, d2, sizeof out2, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *rank = out2[0];
+    *level = out2[1];
+    return LAB_OK;
+}
+// ... every band then marks the path's squares in its own rows: (fin_r, fin_c) / (start_r, start_c) in band rows, -1: in another
+// band.  path_dev: NULL or room for path_cap (row, col) pairs, written at the squares' indices along the WHOLE path (band
+// rows; other bands' squares left alone).  repaint_bits != 0 replaces the paint nibble (the winner's colour).
+int lab_band_lat_path_mark(lab_grid *h, uint32_t rank, uint32_t level, int fin_r, int fin_c, int start_r, int start_c, uint32_t repaint_bits, void *path_dev,
+                           uint64_t path_cap, uint64_t *segments) {
+    Device_guard const guard_(h);
+    int rc = band_lat_ready(h, "lab_band_lat_path_mark");
+    if (rc) return rc;
+    if ((fin_r >= 0 && !in_grid(h, {fin_r, fin_c})) || (start_r >= 0 && !in_grid(h, {start_r, start_c})) || level == INF) {
+        return fail(LAB_ERR_ARG, "lab_band_lat_path_mark: bad argument");
+    }
+    cudaStream_t s = h->stream;
+    Params p = make_params(h, 1);
+    Lattice const lt = h->band_lat;
+    uint32_t *seg = reinterpret_cast<uint32_t *>(lt.xd);
+    uint32_t const seg_cap = lt.nslots;
+    int32_t *out = static_cast<int32_t *>(path_dev);
+    k_lat_path_setup<<<1, 1, 0, s>>>(p, lt, rank, level, fin_r, fin_c, start_r, start_c, repaint_bits, h->squares, out, path_cap, seg);
+    k_lat_path_find<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, lt, seg, seg_cap);
+    k_lat_path_walk<<<h->sm_count * 8, 32, 0, s>>>(p, lt, h->res, repaint_bits, h->squares, out, path_cap, seg, seg_cap);
+    TRACE("k_lat_path_walk", s);
+    h->launches += 3;
+    CU(cudaGetLastError());
+    uint32_t n = 0;
+    CU(cudaMemcpyAsync(&n, &lt.tc->lat_path_nseg, sizeof n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (segments) *segments = n;
     return LAB_OK;
 }
 

@@ -110,7 +110,7 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
                 simt::launch(nwarps, [&](int wid, int lane) { lat_path_find_body(p, lt, seg, seg_cap, wid, nwarps, lane); });
                 std::vector<uint32_t> wsm(static_cast<size_t>(nwarps) * WALK_SM_U32);
                 simt::launch(nwarps, [&](int wid, int lane) {
-                    lat_path_walk_body(p, lt, &w.res, w.grid_ptr, g_hunt_out, g_hunt_out_cap, seg, seg_cap, wid, nwarps, lane, wsm.data() + static_cast<size_t>(wid) * WALK_SM_U32);
+                    if (tc.lat_path_on) lat_path_walk_body(p, lt, &w.res, (1u << w.res.winner) << SQ_PAINT_SHIFT, w.grid_ptr, g_hunt_out, g_hunt_out_cap, seg, seg_cap, wid, nwarps, lane, wsm.data() + static_cast<size_t>(wid) * WALK_SM_U32);
                 });
                 if (tc.lat_path_on) g_path_segments = static_cast<int>(tc.lat_path_nseg);
             }
@@ -781,6 +781,38 @@ int emu_band_lat_levels(void *h, int32_t *used) {
     simt::launch(nw, [&](int wid, int lane) { tree_gate_body(p, tr, static_cast<long long>(wid) * 32 + lane, nth); });
     e->tree_last = e->lat_tc;
     *used = e->lat_tc.used == 3u ? 1 : 0;
+    return 0;
+}
+
+// mirrors lab_band_lat_path_rank / _mark (csrc/lab.cu)
+int emu_band_lat_path_rank(void *h, int r, int c, uint32_t *rank, uint32_t *level) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    Lattice const lt = e->lat;
+    uint32_t out = 0;
+    simt::launch(1, [&](int, int lane) {
+        uint32_t const v = lat_path_rank_body(p, lt, r, c, lane);
+        if (lane == 0) out = v;
+    });
+    *rank = out;
+    *level = e->w.dist[0][static_cast<size_t>(r) * e->w.g.cols + c];
+    return 0;
+}
+int emu_band_lat_path_mark(void *h, uint32_t rank, uint32_t level, int fin_r, int fin_c, int start_r, int start_c, uint32_t repaint_bits, int32_t *path,
+                           uint64_t path_cap, uint64_t *segments) {
+    auto *e = static_cast<Emu_band *>(h);
+    Params p = make_params(e->w, 1);
+    Lattice const lt = e->lat;
+    int const nw = e->nwarps;
+    uint32_t *seg = reinterpret_cast<uint32_t *>(e->l_xd.data());
+    uint32_t const seg_cap = lt.nslots;
+    lat_path_setup_body(p, lt, rank, level, fin_r, fin_c, start_r, start_c, repaint_bits, e->w.grid_ptr, path, path_cap, seg);
+    simt::launch(nw, [&](int wid, int lane) { lat_path_find_body(p, lt, seg, seg_cap, wid, nw, lane); });
+    std::vector<uint32_t> wsm(static_cast<size_t>(nw) * WALK_SM_U32);
+    simt::launch(nw, [&](int wid, int lane) {
+        lat_path_walk_body(p, lt, &e->w.res, repaint_bits, e->w.grid_ptr, path, path_cap, seg, seg_cap, wid, nw, lane, wsm.data() + static_cast<size_t>(wid) * WALK_SM_U32);
+    });
+    if (segments) *segments = e->lat_tc.lat_path_nseg;
     return 0;
 }
 

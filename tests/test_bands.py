@@ -302,7 +302,7 @@ def _gloo_game_worker(rank, world, port, maze_path, out_dir, game, spec):
     from mazes_b200 import bands
 
     maze = np.load(maze_path)
-    r0, n = bands.split_rows(maze.shape[0], world)[rank]
+    r0, n = (bands.split_rows_super if spec.get("super") else bands.split_rows)(maze.shape[0], world)[rank]
     eng = emu_band_engine(maze[r0 : r0 + n].copy(), nwarps=3, sched=rank + 1)
     if game == "hunt":
         res = bands.sharded_hunt(eng, spec["start"], spec["finish"], r0, n)
@@ -355,6 +355,36 @@ def test_sharded_hunt_and_gather_on_gloo(lab, O, tmp_path, builder, rows, cols, 
             assert (b["claimed_by"] == c_ref).all()
             for k in range(4):
                 assert (b[f"path{k}"] == np.asarray(p_ref[k]).reshape(-1, 2)).all()
+
+
+@pytest.mark.parametrize("builder,rows,cols,world", [("kruskal", 767, 131, 3), ("wilson", 513, 195, 2), ("rdfs", 1023, 67, 2)])
+def test_sharded_hunt_on_the_lattice_road_on_gloo(lab, O, tmp_path, builder, rows, cols, world):
+    """Bfs::hunt across bands of whole super-tile rows: the lattice road's level field, and the winner's path WITHOUT any
+    hand-over between the bands -- every band marks the segments in its own rows from the whole-maze tour ranks
+    (lab_band_lat_path_rank / _mark).  Grid, winner and the canonical path equal the single-maze model's."""
+    import torch.multiprocessing as mp
+
+    maze = lab.build_maze(builder, rows, cols, seed=59)
+    done = 0
+    for seed in range(40):
+        placed, s, f = lab.place_hunt(maze, seed=seed)
+        if not (s[0] % 2 == 1 and s[1] % 2 == 1):
+            continue  # (the lattice road across bands wants the start on a cell; other starts take the general pipeline)
+        path = str(tmp_path / "maze.npy")
+        np.save(path, placed)
+        spec = {"start": tuple(int(x) for x in s), "finish": tuple(int(x) for x in f), "super": True}
+        mp.spawn(_gloo_game_worker, args=(world, _free_port(), path, str(tmp_path), "hunt", spec), nprocs=world, join=True)
+        g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
+        z = [np.load(tmp_path / f"band{r}.npz") for r in range(world)]
+        assert all(str(b["road"]) == "lattice" for b in z)
+        got = np.concatenate([b["sq"] for b in z])
+        assert (got == g_ref).all(), int((got != g_ref).sum())
+        for b in z:
+            assert int(b["winner"]) == w_ref and int(b["path_len"]) == len(p_ref) and (b["path"] == np.asarray(p_ref)).all()
+        done += 1
+        if done == 2:
+            break
+    assert done == 2
 
 
 def _hunt_and_gather_checks(lab, O, tmp_path, maze, world, road, seed=7):
@@ -685,6 +715,15 @@ def test_gpu_sharded_games_single_rank(lab, O):
             res = bands.sharded_hunt(eng, tuple(int(x) for x in s), tuple(int(x) for x in f), 0, rows)
             g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
             assert (sq.cpu().numpy().view(np.uint16) == g_ref).all() and res["winner"] == w_ref and (res["path"] == np.asarray(p_ref)).all()
+            if builder != "arena":  # a start on a cell: the lattice road, the winner's path from the tour's ranks (lab_band_lat_path_*)
+                seed = next(q for q in range(100) if all(int(x) % 2 == 1 for x in lab.place_hunt(maze, seed=q)[1]))
+                placed, s, f = lab.place_hunt(maze, seed=seed)
+                sq = torch.from_numpy(placed.view(np.int16).copy()).cuda()
+                eng = bands.GpuBandEngine(lab, sq)
+                res = bands.sharded_hunt(eng, tuple(int(x) for x in s), tuple(int(x) for x in f), 0, rows)
+                g_ref, w_ref, p_ref = O.canon_hunt(placed, s, f)
+                assert res["road"] == "lattice"
+                assert (sq.cpu().numpy().view(np.uint16) == g_ref).all() and res["winner"] == w_ref and (res["path"] == np.asarray(p_ref)).all()
             placed, s, fin = lab.place_gather(maze, seed=12)
             sq = torch.from_numpy(placed.view(np.int16).copy()).cuda()
             eng = bands.GpuBandEngine(lab, sq)

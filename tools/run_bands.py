@@ -39,7 +39,7 @@ if a.game != "distance":
         placed, s, f = lab.place_corners(maze, seed=0xB2000008)
     else:
         placed, s, f = lab.place_gather(maze, seed=0xB2000007)
-    r0, n = bands.split_rows(a.rows, world)[rank]
+    r0, n = (bands.split_rows_super if a.super else bands.split_rows)(a.rows, world)[rank]
     for rep in range(a.reps):
         sq = torch.from_numpy(placed[r0:r0 + n].view(np.int16).copy()).cuda()
         eng = bands.GpuBandEngine(lab, sq)
