@@ -461,8 +461,9 @@ struct lab_grid {
     Result *res = nullptr;
     int32_t *d_finish_rc = nullptr; // 4 (r,c)
     int32_t *d_front_rc = nullptr;  // 4 (r,c)
-    int32_t *d_paths = nullptr;     // 4 * path_cap (r,c)
+    int32_t *d_paths = nullptr;     // path_slots * path_cap (r,c)
     unsigned long long path_cap = 0;
+    int path_slots = 0;
     uint32_t *pixels = nullptr; // heat map of the last distance map (lab_distance_paint), rows*cols
     bool owns_pixels = false;
     bool have_map = false;      // plane 0 holds a finished distance map
@@ -1024,14 +1025,20 @@ int finish_run(lab_grid *h) {
 
 bool in_grid(lab_grid const *h, lab_point p) { return p.row >= 0 && p.row < h->g.rows && p.col >= 0 && p.col < h->g.cols; }
 
-int ensure_paths(lab_grid *h, unsigned long long cap) {
-    if (cap > h->path_cap) {
+// room for `slots` paths of `cap` squares each (gather: four, hunt and corners: the winner's alone)
+int ensure_paths(lab_grid *h, unsigned long long cap, int slots) {
+    if (cap > h->path_cap || slots > h->path_slots) {
         if (h->d_paths) {
             CU(cudaFree(h->d_paths));
             h->d_paths = nullptr;
         }
-        CU(cudaMalloc(&h->d_paths, static_cast<size_t>(cap) * 4 * 2 * sizeof(int32_t)));
+        cap = std::max(cap, h->path_cap);
+        slots = std::max(slots, h->path_slots);
+        h->path_cap = 0;
+        h->path_slots = 0;
+        CU(cudaMalloc(&h->d_paths, static_cast<size_t>(cap) * slots * 2 * sizeof(int32_t)));
         h->path_cap = cap;
+        h->path_slots = slots;
     }
     return LAB_OK;
 }
@@ -1515,7 +1522,7 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
     h->hunt_out = nullptr;
     h->hunt_out_cap = 0;
     if (d.game == GAME_HUNT && want_paths) { // (the lattice road writes the winner's path itself: it needs the buffer before the search)
-        rc = ensure_paths(h, path_cap);
+        rc = ensure_paths(h, path_cap, 1);
         if (rc) {
             return rc;
         }
@@ -1539,7 +1546,7 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
         k_gather_fixup<<<1, 1, 0, s>>>(h->g, h->squares, h->res, h->d_finish_rc, h->d_front_rc);
         TRACE("k_gather_fixup", s);
         if (want_paths) {
-            rc = ensure_paths(h, path_cap);
+            rc = ensure_paths(h, path_cap, 4);
             if (rc) {
                 return rc;
             }
@@ -1551,7 +1558,7 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
         // corners walks only when the caller wants the path (static corners never repaints)
         if (d.game == GAME_HUNT || want_paths) {
             if (want_paths) {
-                rc = ensure_paths(h, path_cap);
+                rc = ensure_paths(h, path_cap, 1);
                 if (rc) {
                     return rc;
                 }

@@ -51,3 +51,22 @@ def ref(O):
     if not O.have_ref():
         pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
     return O
+
+
+# libtorch's exit handlers crash now and then (SIGSEGV in c10::Dispatcher::cleanup -> free) once gloo process groups have
+# been used in a process -- seen at interpreter exit of spawned workers and, 1 run in 6, of the pytest process itself, after
+# every test had passed.  The session's own verdict is what the run exits with: once the summary is printed and every other
+# plugin has unconfigured, leave without the handlers.
+_session_status = [None]
+
+
+def pytest_sessionfinish(session, exitstatus):
+    _session_status[0] = int(exitstatus)
+
+
+@pytest.hookimpl(trylast=True)
+def pytest_unconfigure(config):
+    if _session_status[0] is not None and "torch.distributed" in sys.modules:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(_session_status[0])
