@@ -182,6 +182,9 @@ def bench_game(lab, torch, maze, spec, args, flush, e2e_steps):
     levels = [torch.empty((rows, cols), dtype=torch.int32, device="cuda") for _ in range(4 if game == "corners" else 1)]
     grid = lab.Grid.from_device_ptr(rows, cols, work.data_ptr(), keepalive=work)
     grid.set_stream(stream.cuda_stream)
+    # the static games show the grid alone (Bfs::gather, bfs_threads.cc:333-369): as include/labyrinth.hh does, gather does not ask for
+    # its level field to be kept (4 bytes per square, the Squares read and written)
+    grid.set_option(lab.OPT_SOLVER_LEVELS, 0)
     for k, lv in enumerate(levels):
         grid.bind_levels(k, lv.data_ptr())
 
@@ -237,6 +240,7 @@ def e2e_leg(lab, torch, maze, spec, flush, steps, lanes=2):
         lv = torch.empty((rows, cols), dtype=torch.int32, device="cuda") if game != "corners" else None
         g = lab.Grid.from_device_ptr(rows, cols, sq.data_ptr(), keepalive=sq)
         g.set_stream(st.cuda_stream)
+        g.set_option(lab.OPT_SOLVER_LEVELS, 0)
         if lv is not None:
             g.bind_levels(0, lv.data_ptr())
         ctx.append({"stream": st, "grid": g, "lv": lv, "out": torch.empty_like(host_in).pin_memory(),

@@ -331,6 +331,7 @@ inline void gather(Maze::Maze &maze) {
     uint64_t lens[4];
     {
         Lab::Device_maze d(maze);
+        lab_grid_set_option(d.g, LAB_OPT_SOLVER_LEVELS, 0); // (the static game shows the grid alone: no level field to keep)
         Lab::check(lab_bfs_gather(d.g, start, finishes, claimed, nullptr, 0, lens), "lab_bfs_gather");
         d.download();
     }

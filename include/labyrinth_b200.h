@@ -91,6 +91,12 @@ int lab_grid_upload(lab_grid *g, const uint16_t *host_squares);
 int lab_grid_download(lab_grid *g, uint16_t *host_squares);
 int lab_grid_destroy(lab_grid *g);
 /* All later work of this grid is enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream). */
+/* Options of a grid.  LAB_OPT_SOLVER_LEVELS (default 1): hunt / gather / corners leave their level field(s) behind for
+ * lab_levels_download (the animated variants replay from them).  0: a solver may skip writing a field it does not need itself --
+ * bfs-gather without paths on the reference builders' perfect mazes then only reads and writes the Squares (4 bytes
+ * per square); lab_levels_download afterwards returns LAB_ERR_ARG.  The grid's contents are the same either way. */
+enum { LAB_OPT_SOLVER_LEVELS = 1 };
+int lab_grid_set_option(lab_grid *g, int option, int value);
 int lab_grid_set_stream(lab_grid *g, void *cuda_stream);
 void *lab_grid_device_squares(lab_grid *g);
 int lab_grid_rows(const lab_grid *g);

@@ -43,8 +43,11 @@ ABI_SYMBOLS = (
     "lab_band_lat_levels",
     "lab_band_begin_game", "lab_band_level_at", "lab_band_paint", "lab_band_walk", "lab_band_recolour", "lab_band_finish_game",
     "lab_band_begin_corners", "lab_band_planes", "lab_band_level_at_plane", "lab_band_paint_planes",
-    "lab_band_lat_path_rank", "lab_band_lat_path_mark",
+    "lab_band_lat_path_rank", "lab_band_lat_path_mark", "lab_grid_set_option",
 )
+
+
+OPT_SOLVER_LEVELS = 1  # lab_grid_set_option
 
 
 class LabError(RuntimeError):
@@ -356,6 +359,12 @@ class Grid:
     def device_squares(self) -> int:
         return int(lib().lab_grid_device_squares(self._h) or 0)
 
+    def levels(self, plane: int = 0) -> np.ndarray:
+        """The level field of the last search (lab_levels_download); LabError if that search left none."""
+        out = np.empty((self.rows, self.cols), np.uint32)
+        _check(lib().lab_levels_download(self._h, c_int(plane), _np_ptr(out)))
+        return out
+
     def levels_device(self, plane: int = 0) -> int:
         return int(lib().lab_levels_device(self._h, plane) or 0)
 
@@ -416,6 +425,10 @@ class Grid:
         _check(lib().lab_pixels_bind(self._h, c_void_p(ptr)))
 
     # -- Bfs::hunt / gather / corners, thread part
+    def set_option(self, option: int, value: int):
+        """lab_grid_set_option (OPT_SOLVER_LEVELS = 1: keep the solvers' level fields, the default; 0: gather without paths may skip its field)"""
+        _check(lib().lab_grid_set_option(self._h, c_int(option), c_int(value)))
+
     def hunt(self, start, finish, want_path: bool = True) -> SolveResult:
         cap = self.rows * self.cols if want_path else 0
         path = np.empty((cap, 2), np.int32) if want_path else None

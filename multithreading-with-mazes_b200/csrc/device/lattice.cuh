@@ -883,7 +883,7 @@ LAB_DEV uint32_t lat_prefix_below(Lattice const &lt, uint32_t r) {
 // What lat_levels_tile does with a tile's levels: LAT_LEVELS writes them; LAT_PAINT also applies the solvers' paint rules
 // to the Squares on the way (the field is in registers: k_paint's second pass over it, 4 B read per square, is saved);
 // LAT_PROBE writes nothing and only takes the level of one square (the solvers' finishes: the paint rules come from them).
-enum Lat_mode : int { LAT_LEVELS = 0, LAT_PAINT = 1, LAT_PROBE = 2 };
+enum Lat_mode : int { LAT_LEVELS = 0, LAT_PAINT = 1, LAT_PROBE = 2, LAT_PAINT_ONLY = 3 }; // (PAINT_ONLY: the rules applied, the field itself NOT written -- see lat_targets_body)
 struct Lat_paint { // resolve_body's rules (post.cuh), all on field 0
     uint32_t n;
     uint32_t below[4], bits[4];
@@ -896,6 +896,7 @@ struct Lat_paint { // resolve_body's rules (post.cuh), all on field 0
 template <int MODE, bool FULL>
 LAB_DEV void lat_emit_rows(Geom const &g, Lat_tile const &T, uint32_t const (&lv)[LC], uint32_t emW, bool entryN, int lane, int ty, int tx, uint32_t *dist,
                            Lat_paint const &pr, uint32_t &painted, int probe_r, int probe_c, uint32_t &probe_out) {
+    constexpr bool PAINTS = MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY, STORES = MODE == LAT_LEVELS || MODE == LAT_PAINT;
     long long const c0 = static_cast<long long>(tx) * TS + 2 * lane, r_base = static_cast<long long>(ty) * TS;
     bool const in0 = FULL || c0 < g.cols, in1 = FULL || c0 + 1 < g.cols;
     long long at = r_base * g.cols + c0; // square (row 2i, column c0)
@@ -933,7 +934,7 @@ LAB_DEV void lat_emit_rows(Geom const &g, Lat_tile const &T, uint32_t const (&lv
                 continue;
             }
             bool const ok0 = FULL || r_base + 2 * i < g.rows, ok1 = FULL || r_base + 2 * i + 1 < g.rows;
-            if (ok0) {
+            if (STORES && ok0) {
                 if (pairs) {
                     lab_st_pair(dist + at, INF, np);
                 } else {
@@ -941,19 +942,19 @@ LAB_DEV void lat_emit_rows(Geom const &g, Lat_tile const &T, uint32_t const (&lv
                     if (in1) dist[at + 1] = np;
                 }
             }
-            if (ok1) {
+            if (STORES && ok1) {
                 long long const at1 = at + g.cols;
                 if (in0) dist[at1] = wp;
                 if (in1) dist[at1 + 1] = me;
             }
-            if (MODE == LAT_PAINT) {
+            if (PAINTS) {
                 pb[3 * ii] = ok0 && in1 ? bits_of(np) : 0u;
                 pb[3 * ii + 1] = ok1 && in0 ? bits_of(wp) : 0u;
                 pb[3 * ii + 2] = ok1 && in1 ? bits_of(me) : 0u;
             }
             at += 2 * static_cast<long long>(g.cols);
         }
-        if (MODE == LAT_PAINT) {
+        if (PAINTS) {
             uint16_t pv[3 * G];
 #pragma unroll
             for (int ii = 0; ii < G; ii++) {
@@ -1065,8 +1066,8 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
         if (MODE == LAT_PROBE) {
             if (probe_r == lr && probe_c == lc) probe_out = 0u;
         } else {
-            dist[sq] = 0u;
-            if (MODE == LAT_PAINT) {
+            if (MODE != LAT_PAINT_ONLY) dist[sq] = 0u;
+            if (MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY) {
                 uint32_t b = 0;
                 for (uint32_t k = 0; k < pr.n; k++) {
                     b |= 0u < pr.below[k] ? pr.bits[k] : 0u;
@@ -1086,7 +1087,7 @@ template <int MODE> LAB_DEV void lat_levels_body(Params const &p, Lattice const 
         return;
     }
     Lat_paint pr{};
-    if (MODE == LAT_PAINT) {
+    if (MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY) {
         pr.n = res->n_rules;
         for (int k = 0; k < 4; k++) {
             pr.below[k] = res->rule[k].below;
@@ -1110,7 +1111,7 @@ template <int MODE> LAB_DEV void lat_levels_body(Params const &p, Lattice const 
     if (lane == 0 && mx) {
         lab_atomic_max(&p.ctl->max_level, mx);
     }
-    if (MODE == LAT_PAINT) {
+    if (MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY) {
         painted = lab_reduce_add(painted);
         if (lane == 0 && painted) {
             lab_atomic_add(reinterpret_cast<uint64_t *>(&res->settled), static_cast<uint64_t>(painted));
@@ -1133,6 +1134,41 @@ LAB_DEV void lat_targets_body(Params const &p, Lattice const &lt, int warp, int 
     lat_levels_tile<LAT_PROBE>(p, lt, t, lane, sm, mx, none, painted, r % TS, c % TS, out);
     if (lane == ((c % TS) >> 1)) {
         ctl->target_val[warp] = out;
+    }
+}
+
+// gather without paths, the field not wanted (LAT_PAINT_ONLY): the one thing besides the paint that reads levels is
+// path.front() of every colour (bfs_threads.cc:355-364) -- the first of the finish's N, E, S, W neighbours one level lower.
+// Warp k probes the four neighbours of the finish colour k claims (after resolve_body); front_rc[2k], [2k+1] as k_walk leaves them.
+LAB_DEV void lat_fronts_body(Params const &p, Lattice const &lt, Result const *res, int32_t const *finish_rc, int32_t *front_rc, int warp, int lane, uint32_t *sm) {
+    if (!lat_live(lt.tc) || warp >= 4) {
+        return;
+    }
+    int const fj = res->finish_of[warp];
+    uint32_t const D = res->game_level[warp];
+    if (fj < 0 || D == INF || D == 0u) {
+        return; // (front_rc stays -1)
+    }
+    int const fr = finish_rc[2 * fj], fc = finish_rc[2 * fj + 1];
+    int const dr[4] = {-1, 0, 1, 0}, dc[4] = {0, 1, 0, -1};
+    bool found = false;
+    for (int k = 0; k < 4; k++) {
+        int const r = fr + dr[k], c = fc + dc[k];
+        if (found || r < 0 || r >= p.g.rows || c < 0 || c >= p.g.cols) {
+            continue; // (uniform)
+        }
+        uint32_t const t = static_cast<uint32_t>((r / TS) * p.g.tiles_x + c / TS);
+        uint32_t mx = 0, painted = 0, out = INF;
+        Lat_paint const none{};
+        lat_levels_tile<LAT_PROBE>(p, lt, t, lane, sm, mx, none, painted, r % TS, c % TS, out);
+        out = lab_shfl(out, (c % TS) >> 1);
+        if (out == D - 1u) {
+            found = true;
+            if (lane == 0) {
+                front_rc[2 * warp] = r;
+                front_rc[2 * warp + 1] = c;
+            }
+        }
     }
 }
 

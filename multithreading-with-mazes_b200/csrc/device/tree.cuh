@@ -1217,7 +1217,7 @@ LAB_DEV void tree_gate_body(Params const &p, Tree const &tr, long long gthread, 
         ctl->measured = 1u;
         ctl->n_marked = tr.banded ? tc->lat_settled_band : tc->lat_settled;
     }
-    for (uint32_t j = 0; j < ctl->n_targets; j++) {
+    for (uint32_t j = 0; j < ctl->n_targets && !ctl->painted; j++) { // (painted: lat_targets_body has taken them; the field may not exist)
         ctl->target_val[j] = p.plane[0].dist[ctl->target_cell[j]];
     }
     for (unsigned long long q = 0; q < ctl->tail; q++) {

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) k_lat_rank_expand(Lattice lt) {
 __global__ void __launch_bounds__(128) k_lat_flood(Params p, Lattice lt) { lat_flood_body(p, lt, lane_id()); }
 __global__ void __launch_bounds__(256) k_lat_scan_chunks(Lattice lt) { lat_scan_chunks_body(lt, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void k_lat_scan_tops(Lattice lt) { lat_scan_tops_body(lt, lane_id()); }
-template <int MODE> __global__ void __launch_bounds__(128, MODE == LAT_PAINT ? 6 : 8) k_lat_levels(Params p, Lattice lt, Result *res, uint16_t *grid) {
+template <int MODE> __global__ void __launch_bounds__(128, (MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY) ? 6 : 8) k_lat_levels(Params p, Lattice lt, Result *res, uint16_t *grid) {
     __shared__ uint32_t sm[4][L_LINK_SM];
     lat_levels_body<MODE>(p, lt, lane_id(), sm[threadIdx.x >> 5], res, grid);
 }
@@ -261,13 +261,19 @@ __global__ void k_lat_path_setup(Params p, Lattice lt, uint32_t rank, uint32_t l
     lat_path_setup_body(p, lt, rank, level, fr, fc, sr, sc, repaint, grid, out, max_out, seg);
 }
 // hunt / gather on the lattice road: the finishes' levels and the paint rules BEFORE the field is written (lat_targets_body)
-__global__ void __launch_bounds__(128) k_lat_targets(Params p, Lattice lt, Run_desc d, Result *res, int32_t const *finish_rc) {
+// front_rc != null (gather, no paths, the field not wanted): every colour's path.front() by probing too (lat_fronts_body)
+__global__ void __launch_bounds__(128) k_lat_targets(Params p, Lattice lt, Run_desc d, Result *res, int32_t const *finish_rc, int32_t *front_rc) {
     __shared__ uint32_t sm[4][L_LINK_SM];
     lat_targets_body(p, lt, static_cast<int>(threadIdx.x >> 5), lane_id(), sm[threadIdx.x >> 5]);
     __syncthreads();
     if (threadIdx.x == 0 && lat_live(lt.tc)) {
         resolve_body(p, d, res, finish_rc);
         p.ctl->painted = 1u;
+        if (front_rc) p.ctl->fronts_done = 1u;
+    }
+    __syncthreads();
+    if (front_rc) {
+        lat_fronts_body(p, lt, res, finish_rc, front_rc, static_cast<int>(threadIdx.x >> 5), lane_id(), sm[threadIdx.x >> 5]);
     }
 }
 __global__ void k_lat_band_open(Lattice lt) { lat_band_open_body(lt); }
@@ -330,6 +336,10 @@ __global__ void k_walk(Params p, int game, uint16_t *grid, Result *res, int32_t 
     uint32_t repaint = 0;
     if (game == GAME_HUNT && p.ctl->walked) { // lat_path_*: the path is marked and written already; its length is the finish's level
         if (lane_id() == 0) res->path_len[slot] = res->game_level[0];
+        return;
+    }
+    if (game == GAME_GATHER && first_only && p.ctl->fronts_done) { // lat_fronts_body: path.front() is known (and no field exists to step on)
+        if (lane_id() == 0) res->path_len[slot] = res->finish_of[slot] >= 0 ? res->game_level[slot] : 0;
         return;
     }
     if (game == GAME_HUNT) {
@@ -493,6 +503,9 @@ struct lab_grid {
     bool tree_alloc = false;
     Tree_ctl tree_last{};
     bool tree_tried = false;
+    bool opt_solver_levels = true; // lab_grid_set_option(LAB_OPT_SOLVER_LEVELS)
+    bool skip_field_now = false;   // this solver call may leave its level field unwritten (gather, no paths, the option off)
+    bool field_skipped = false;    // ... and the road that ran did (lab_levels_download says so)
     int32_t *hunt_out = nullptr; // where hunt's winner path goes (solver_common sets both before the search; null: not wanted)
     unsigned long long hunt_out_cap = 0;
     Lattice lat{}; // the lattice road's workspace (allocated on first use)
@@ -816,9 +829,14 @@ int run_lattice(lab_grid *h, Params const &p, Run_desc const &d) {
     // hunt / gather: the paint rules are applied while the levels are written (k_paint then returns at once)
     bool const fuse_paint = (d.game == GAME_HUNT || d.game == GAME_GATHER) && env_ll("LAB_LAT_FUSE_PAINT", 1) != 0;
     if (fuse_paint) {
-        k_lat_targets<<<1, 128, 0, s>>>(p, lt, d, h->res, h->d_finish_rc);
+        bool const skip_field = h->skip_field_now; // (gather without paths, LAB_OPT_SOLVER_LEVELS off: nobody reads the field)
+        k_lat_targets<<<1, 128, 0, s>>>(p, lt, d, h->res, h->d_finish_rc, skip_field ? h->d_front_rc : nullptr);
         TRACE("k_lat_targets", s);
-        k_lat_levels<LAT_PAINT><<<tile_blocks, 128, 0, s>>>(p, lt, h->res, h->squares);
+        if (skip_field) {
+            k_lat_levels<LAT_PAINT_ONLY><<<tile_blocks, 128, 0, s>>>(p, lt, h->res, h->squares);
+        } else {
+            k_lat_levels<LAT_PAINT><<<tile_blocks, 128, 0, s>>>(p, lt, h->res, h->squares);
+        }
         h->launches += 1;
         if (d.game == GAME_HUNT && env_ll("LAB_LAT_PATH", 1) != 0) {
             // the winner's path, painted over the colours just applied (k_walk then returns at once).  The segments' list
@@ -1233,6 +1251,17 @@ int lab_grid_set_stream(lab_grid *h, void *cuda_stream) {
     return LAB_OK;
 }
 
+int lab_grid_set_option(lab_grid *h, int option, int value) {
+    if (!h) {
+        return fail(LAB_ERR_ARG, "null grid");
+    }
+    if (option == LAB_OPT_SOLVER_LEVELS) {
+        h->opt_solver_levels = value != 0;
+        return LAB_OK;
+    }
+    return fail(LAB_ERR_ARG, "lab_grid_set_option: unknown option %d", option);
+}
+
 void *lab_grid_device_squares(lab_grid *h) { return h ? h->squares : nullptr; }
 int lab_grid_rows(const lab_grid *h) { return h ? h->g.rows : 0; }
 int lab_grid_cols(const lab_grid *h) { return h ? h->g.cols : 0; }
@@ -1322,6 +1351,9 @@ int lab_levels_download(lab_grid *h, int plane, uint32_t *levels_host) {
     }
     if (h->tree_last.used == 2u) {
         return fail(LAB_ERR_ARG, "lab_levels_download: the last search was an open room (levels are Manhattan distances from the start; no field was written)");
+    }
+    if (h->field_skipped) {
+        return fail(LAB_ERR_ARG, "lab_levels_download: the last game left no field (bfs-gather without paths with LAB_OPT_SOLVER_LEVELS off)");
     }
     CU(cudaMemcpyAsync(levels_host, h->plane[plane].dist, static_cast<size_t>(h->g.rows) * h->g.cols * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -1521,6 +1553,11 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
     int rc = LAB_OK;
     h->hunt_out = nullptr;
     h->hunt_out_cap = 0;
+    h->skip_field_now = d.game == GAME_GATHER && !want_paths && !h->opt_solver_levels;
+    h->field_skipped = false;
+    if (d.game == GAME_GATHER) {
+        CU(cudaMemsetAsync(h->d_front_rc, 0xFF, 8 * sizeof(int32_t), s)); // (before the search: the lattice road may fill it in)
+    }
     if (d.game == GAME_HUNT && want_paths) { // (the lattice road writes the winner's path itself: it needs the buffer before the search)
         rc = ensure_paths(h, path_cap, 1);
         if (rc) {
@@ -1540,7 +1577,6 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
     TRACE("k_paint", s);
     h->launches += 2 + (d.game == GAME_GATHER ? (want_paths ? 3 : 2) : 1);
     if (d.game == GAME_GATHER) {
-        CU(cudaMemsetAsync(h->d_front_rc, 0xFF, 8 * sizeof(int32_t), s));
         k_walk<<<4, 32, 0, s>>>(p, d.game, h->squares, h->res, h->d_finish_rc, h->d_front_rc, 1, 1, 1);
         TRACE("k_walk", s);
         k_gather_fixup<<<1, 1, 0, s>>>(h->g, h->squares, h->res, h->d_finish_rc, h->d_front_rc);
@@ -1572,7 +1608,9 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
         }
     }
     CU(cudaGetLastError());
-    return finish_run(h);
+    rc = finish_run(h);
+    h->field_skipped = rc == LAB_OK && h->skip_field_now && h->tree_last.used == 3u && env_ll("LAB_LAT_FUSE_PAINT", 1) != 0;
+    return rc;
 }
 
 static int copy_path(lab_grid *h, int slot, lab_point *dst, uint64_t cap, uint64_t len) {

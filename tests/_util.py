@@ -76,10 +76,10 @@ class Emu:
         assert rc == 0, f"emulated search failed: {rc}"
         return g, d, mx.value, st.value, stats
 
-    def solver(self, game, grid, starts, finishes, nwarps=4, sched=0):
+    def solver(self, game, grid, starts, finishes, nwarps=4, sched=0, want_paths=True):
         rows, cols = grid.shape
         g = np.ascontiguousarray(grid, np.uint16).copy()
-        mp = rows * cols
+        mp = rows * cols if want_paths else 0
         st = np.zeros((4, 2), np.int32)
         s = np.asarray(starts, np.int32).reshape(-1, 2)
         st[: len(s)] = s
@@ -88,14 +88,14 @@ class Emu:
         fi[: len(f)] = f
         win = ctypes.c_int32()
         claimed = np.zeros(4, np.int32)
-        paths = np.zeros((4, mp, 2), np.int32)
+        paths = np.zeros((4, max(mp, 1), 2), np.int32)
         lens = np.zeros(4, np.int64)
         painted = ctypes.c_uint64()
         stats = np.zeros(8, np.uint64)
         rc = self.lib.emu_solver(game, rows, cols, self._p(g), self._p(st), self._p(fi), ctypes.byref(win), self._p(claimed),
                                  self._p(paths), ctypes.c_longlong(mp), self._p(lens), ctypes.byref(painted), nwarps, sched, self._p(stats))
         assert rc == 0, f"emulated search failed: {rc}"
-        return g, win.value, claimed, [paths[k, : lens[k]].copy() for k in range(4)], painted.value
+        return g, win.value, claimed, [paths[k, : lens[k] if want_paths else 0].copy() for k in range(4)], painted.value
 
 
 def emu_band_engine(squares: np.ndarray, nwarps: int = 4, sched: int = 0):

@@ -32,6 +32,9 @@ int g_lattice_mode = 1;   // 0: the general pipeline only, 1: the lattice road f
 Tree_ctl g_tree_last{};
 int g_paint_fused = 0; // the last search applied the solvers' paint rules inside lat_levels_body
 int g_path_segments = -1; // ... and marked hunt's winner path from the tour's ranks: segments walked (-1: it did not)
+int g_opt_solver_levels = 1; // lab_grid_set_option(LAB_OPT_SOLVER_LEVELS)
+int g_skip_field = 0;        // this solver call may leave its field unwritten (gather without paths, the option off)
+int32_t *g_front_rc = nullptr;
 int32_t *g_hunt_out = nullptr; // where hunt's path goes (set by emu_solver before the search, as solver_common does)
 unsigned long long g_hunt_out_cap = 0;
 
@@ -97,11 +100,17 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
             }
             std::vector<uint32_t> tsm(4 * static_cast<size_t>(L_LINK_SM));
             simt::launch(4, [&](int wid, int lane) { lat_targets_body(p, lt, wid, lane, tsm.data() + static_cast<size_t>(wid) * L_LINK_SM); });
+            bool const skip_field = g_skip_field && d.game == GAME_GATHER;
             if (lat_live(lt.tc)) {
                 resolve_body(p, d, &w.res, frc);
                 p.ctl->painted = 1u;
-                g_paint_fused = 1;
+                if (skip_field) p.ctl->fronts_done = 1u;
+                g_paint_fused = skip_field ? 2 : 1;
             }
+            if (skip_field) {
+                simt::launch(4, [&](int wid, int lane) { lat_fronts_body(p, lt, &w.res, frc, g_front_rc, wid, lane, tsm.data() + static_cast<size_t>(wid) * L_LINK_SM); });
+                simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body<LAT_PAINT_ONLY>(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS, &w.res, w.grid_ptr); }, sched_seed);
+            } else
             simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body<LAT_PAINT>(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS, &w.res, w.grid_ptr); }, sched_seed);
             if (d.game == GAME_HUNT) { // the winner's path from the tour's ranks, as run_lattice() launches it
                 uint32_t *seg = reinterpret_cast<uint32_t *>(xd.data());
@@ -231,6 +240,7 @@ int emu_runs(int rows, int cols, uint32_t const *dist, uint32_t *runs, uint32_t 
     return 0;
 }
 void emu_set_tree(int mode) { g_tree_mode = mode; }
+void emu_set_option_solver_levels(int v) { g_opt_solver_levels = v; }
 void emu_set_lattice(int mode) { g_lattice_mode = mode; }
 int emu_last_lattice_error(void) { return static_cast<int>(g_tree_last.lat_err); }
 // 0: the tile wave made the field; 1: the tree pipeline did
@@ -864,15 +874,19 @@ int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *star
     }
     g_hunt_out = game == GAME_HUNT ? paths_out : nullptr;
     g_hunt_out_cap = game == GAME_HUNT ? static_cast<unsigned long long>(max_path) : 0ull;
+    int32_t front[8];
+    for (auto &x : front) x = -1;
+    g_front_rc = front;
+    g_skip_field = game == GAME_GATHER && max_path == 0 && !g_opt_solver_levels; // (as solver_common: gather, no paths, the option off)
     int rc = search(w, grid, rows, cols, d, SQ_PATH, SQ_PATH, nwarps, sched_seed);
     g_hunt_out = nullptr;
+    g_front_rc = nullptr;
+    g_skip_field = 0;
     if (rc) return rc;
     Params p = make_params(w, d.nplanes);
     resolve_body(p, d, &w.res, frc);
     long long const nthreads = static_cast<long long>(nwarps) * 32;
     simt::launch(nwarps, [&](int wid, int lane) { paint_body(p, grid, &w.res, static_cast<long long>(wid) * 32 + lane, nthreads); });
-    int32_t front[8];
-    for (auto &x : front) x = -1;
     auto walk = [&](int slot, int32_t *out, unsigned long long max_out, int first_only) {
         int plane = 0, fj = 0;
         uint32_t repaint = 0;
@@ -887,6 +901,7 @@ int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *star
             if (w.res.winner < 0) return;
             plane = w.res.winner;
         } else {
+            if (first_only && w.ctl.fronts_done) return; // (k_walk: lat_fronts_body has found path.front())
             fj = w.res.finish_of[slot];
             if (fj < 0) return;
         }
@@ -898,7 +913,7 @@ int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *star
     if (game == GAME_GATHER) {
         for (int k = 0; k < 4; k++) walk(k, front + 2 * k, 1, 1);
         gather_fixup_body(w.g, grid, &w.res, frc, front);
-        for (int k = 0; k < 4; k++) walk(k, paths_out + static_cast<size_t>(k) * max_path * 2, static_cast<unsigned long long>(max_path), 0);
+        for (int k = 0; k < 4 && max_path > 0; k++) walk(k, paths_out + static_cast<size_t>(k) * max_path * 2, static_cast<unsigned long long>(max_path), 0);
     } else {
         walk(0, paths_out, static_cast<unsigned long long>(max_path), 0);
     }

@@ -168,7 +168,44 @@ def test_emulated_games_on_the_lattice(lab, O, emu):
         assert (g == g_ref).all() and (c == c_ref).all() and paths_equal(paths, p_ref)
 
 
+def test_emulated_gather_without_its_field(lab, O, emu):
+    """LAB_OPT_SOLVER_LEVELS off, no paths wanted: bfs-gather on the lattice road applies its paint rules WITHOUT writing the
+    level field (SURVEY 8(d)'s 4 bytes per square); path.front() of every colour comes from probing the finishes'
+    neighbours.  The grid is the canonical model's all the same."""
+    maze = lab.build_maze("kruskal", 131, 197, seed=9)
+    emu.lib.emu_set_option_solver_levels(0)
+    try:
+        for seed in range(60, 70):
+            placed, s, fin = lab.place_gather(maze, seed=seed)
+            g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
+            g, _, c, _, painted = emu.solver(2, placed, [s], fin, 4, 1, want_paths=False)
+            assert emu.lib.emu_last_tree_used() == LATTICE and emu.lib.emu_last_paint_fused() == 2  # (2: painted, field skipped)
+            assert (g == g_ref).all() and (c == c_ref).all() and painted > 0
+    finally:
+        emu.lib.emu_set_option_solver_levels(1)
+
+
 # ------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_gpu_gather_without_its_field(lab, O):
+    """lab_grid_set_option(LAB_OPT_SOLVER_LEVELS, 0): the same grid and claims, no field (lab_levels_download says so)."""
+    maze = lab.build_maze("wilson", 1023, 1535, seed=4)
+    for seed in range(4):
+        placed, s, fin = lab.place_gather(maze, seed=0xB2000203 + seed)
+        g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
+        with lab.Grid.from_host(placed) as g:
+            g.set_option(lab.OPT_SOLVER_LEVELS, 0)
+            res = g.gather(s, fin, want_paths=False)
+            assert g.stats()["tree_used"] == LATTICE
+            assert (g.download() == g_ref).all() and (res.claimed_by == c_ref).all() and list(res.path_len) == [len(p) for p in p_ref]
+            with pytest.raises(lab.LabError):
+                g.levels(0)
+            # with paths the field is needed and written whatever the option says
+            g.upload(placed)
+            res = g.gather(s, fin, want_paths=True)
+            assert (g.download() == g_ref).all() and paths_equal(res.paths, p_ref)
+            g.levels(0)
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("builder,n", [("kruskal", 1023), ("wilson", 2047), ("rdfs", 1535), ("kruskal", 4095), ("wilson", 4095)])
 def test_gpu_lattice_road_is_used_and_exact(lab, O, builder, n):
