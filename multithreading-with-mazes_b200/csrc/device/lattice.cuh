@@ -893,15 +893,20 @@ struct Lat_paint { // resolve_body's rules (post.cuh), all on field 0
 // lane j has columns 2j, 2j+1.  A passage lies one below the deeper of its two cells; across the tile's border the
 // deeper one is this cell iff the crossing is its component's entry.  FULL: the tile lies inside the maze (no bounds
 // to check); the pair (pillar, N passage) of an even row starts on an 8-byte boundary (cols is odd): one 8-byte store.
-template <int MODE, bool FULL>
+// UNIFORM (paint modes): no threshold of the rules falls among this tile's levels -- every passable square of the tile gets
+// the same bits `ubits` (rules whose threshold lies above all of them), so a square's bits are one test instead of four.
+template <int MODE, bool FULL, bool UNIFORM = false>
 LAB_DEV void lat_emit_rows(Geom const &g, Lat_tile const &T, uint32_t const (&lv)[LC], uint32_t emW, bool entryN, int lane, int ty, int tx, uint32_t *dist,
-                           Lat_paint const &pr, uint32_t &painted, int probe_r, int probe_c, uint32_t &probe_out) {
+                           Lat_paint const &pr, uint32_t &painted, int probe_r, int probe_c, uint32_t &probe_out, uint32_t ubits = 0) {
     constexpr bool PAINTS = MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY, STORES = MODE == LAT_LEVELS || MODE == LAT_PAINT;
     long long const c0 = static_cast<long long>(tx) * TS + 2 * lane, r_base = static_cast<long long>(ty) * TS;
     bool const in0 = FULL || c0 < g.cols, in1 = FULL || c0 + 1 < g.cols;
     long long at = r_base * g.cols + c0; // square (row 2i, column c0)
     bool const pairs = FULL && (reinterpret_cast<uintptr_t>(dist) & 7u) == 0; // (a caller's field may start anywhere)
     auto bits_of = [&](uint32_t v) {
+        if (UNIFORM) {
+            return v != INF ? ubits : 0u;
+        }
         uint32_t b = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -1040,7 +1045,7 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
     // its entry depth is looked up where a run begins (bit i of st, as in lat_link_tile)
     uint32_t lv[LC];
     uint32_t const st = T.C & ~(T.No & ~1u);
-    uint32_t e = 0;
+    uint32_t e = 0, tmin = INF, tmax = 0; // (paint modes: the tile's cells' levels lie in [tmin, tmax])
 #pragma unroll
     for (int i = 0; i < LC; i++) {
         if ((st >> i) & 1u) {
@@ -1049,12 +1054,46 @@ LAB_DEV void lat_levels_tile(Params const &p, Lattice const &lt, uint32_t t, int
         uint32_t const v = 2u * (e + (A[i] & 1023u)) + off;
         lv[i] = ((T.C >> i) & 1u) ? v : INF;
         mx = ((T.C >> i) & 1u) && v > mx ? v : mx;
+        if (MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY) {
+            tmin = ((T.C >> i) & 1u) && v < tmin ? v : tmin;
+            tmax = ((T.C >> i) & 1u) && v > tmax ? v : tmax;
+        }
     }
     int const ty = static_cast<int>(t / static_cast<uint32_t>(g.tiles_x)), tx = static_cast<int>(t % static_cast<uint32_t>(g.tiles_x));
     uint32_t *dist = p.plane[0].dist;
     bool const entryN = (em[L_N] >> lane) & 1u;
     bool const full = static_cast<long long>(ty + 1) * TS <= g.rows && static_cast<long long>(tx + 1) * TS <= g.cols;
-    if (full) {
+    // paint modes: a passage lies one below the deeper of its two cells, a crossing passage one below or above its cell -- every
+    // square of the tile has its level in [tmin - 1, tmax + 1].  A rule whose threshold lies above that paints all of them, one
+    // whose threshold lies at or below it none; if every rule is one or the other the tile's paint is uniform (the common case:
+    // four thresholds among 10^5-10^6 levels), and a tile nobody paints is not read at all.
+    bool uniform = false;
+    uint32_t ubits = 0;
+    if (MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY) {
+        tmin = lab_reduce_min(tmin);
+        tmax = lab_reduce_max(tmax);
+        uniform = tmin != INF && tmax < INF - 2u;
+        for (uint32_t k = 0; k < pr.n; k++) {
+            bool const all = tmax + 1u < pr.below[k], none = pr.below[k] == 0u || (tmin > 0u && tmin - 1u >= pr.below[k]);
+            uniform = uniform && (all || none);
+            ubits |= all ? pr.bits[k] : 0u;
+        }
+    }
+    if (MODE == LAT_PAINT_ONLY && uniform && ubits == 0u) {
+        // nothing to write in this tile
+    } else if (MODE == LAT_PAINT && uniform && ubits == 0u) {
+        if (full) {
+            lat_emit_rows<LAT_LEVELS, true>(g, T, lv, em[L_W], entryN, lane, ty, tx, dist, pr, painted, probe_r, probe_c, probe_out);
+        } else {
+            lat_emit_rows<LAT_LEVELS, false>(g, T, lv, em[L_W], entryN, lane, ty, tx, dist, pr, painted, probe_r, probe_c, probe_out);
+        }
+    } else if ((MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY) && uniform) {
+        if (full) {
+            lat_emit_rows<MODE, true, true>(g, T, lv, em[L_W], entryN, lane, ty, tx, dist, pr, painted, probe_r, probe_c, probe_out, ubits);
+        } else {
+            lat_emit_rows<MODE, false, true>(g, T, lv, em[L_W], entryN, lane, ty, tx, dist, pr, painted, probe_r, probe_c, probe_out, ubits);
+        }
+    } else if (full) {
         lat_emit_rows<MODE, true>(g, T, lv, em[L_W], entryN, lane, ty, tx, dist, pr, painted, probe_r, probe_c, probe_out);
     } else {
         lat_emit_rows<MODE, false>(g, T, lv, em[L_W], entryN, lane, ty, tx, dist, pr, painted, probe_r, probe_c, probe_out);

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) k_lat_rank_expand(Lattice lt) {
 __global__ void __launch_bounds__(128) k_lat_flood(Params p, Lattice lt) { lat_flood_body(p, lt, lane_id()); }
 __global__ void __launch_bounds__(256) k_lat_scan_chunks(Lattice lt) { lat_scan_chunks_body(lt, gwarp_id(), nwarps_total(), lane_id()); }
 __global__ void k_lat_scan_tops(Lattice lt) { lat_scan_tops_body(lt, lane_id()); }
-template <int MODE> __global__ void __launch_bounds__(128, (MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY) ? 6 : 8) k_lat_levels(Params p, Lattice lt, Result *res, uint16_t *grid) {
+template <int MODE> __global__ void __launch_bounds__(128, (MODE == LAT_PAINT || MODE == LAT_PAINT_ONLY) ? 5 : 8) k_lat_levels(Params p, Lattice lt, Result *res, uint16_t *grid) {
     __shared__ uint32_t sm[4][L_LINK_SM];
     lat_levels_body<MODE>(p, lt, lane_id(), sm[threadIdx.x >> 5], res, grid);
 }
