@@ -103,6 +103,7 @@ struct Control {
     int32_t room_r0, room_r1, room_c0, room_c1, room_sr, room_sc; // (row bands: relative to the band, see room.cuh)
     uint32_t painted; // the lattice road has applied the paint rules while writing the levels (lattice.cuh): paint_body has nothing to do
     uint32_t walked;  // ... and has marked the winner's path from the tour's ranks (lat_path_*): hunt's walk has nothing to do
+    uint32_t walk_fallback; // lat_path_begin_body met a finish it leaves to the one-warp walk (unreachable, or on a pillar): `walked` is not set
     uint32_t fronts_done; // ... and has found every colour's path.front() by probing (lat_fronts_body; the field was not written): gather's one-step walks have nothing to do
 };
 

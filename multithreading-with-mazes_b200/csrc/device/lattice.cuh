@@ -1245,19 +1245,20 @@ LAB_DEV uint32_t lat_path_rank_body(Params const &p, Lattice const &lt, int fr, 
     return lab_reduce_max(rank);
 }
 // One thread.  (fr, fc) / (sr, sc): the finish / the start in this grid's rows, fr < 0 / sr < 0: in another band.
-LAB_DEV void lat_path_setup_body(Params const &p, Lattice const &lt, uint32_t rank, uint32_t D, int fr, int fc, int sr, int sc, uint32_t repaint,
+// q: which path (hunt: 0; gather: colour q's); seg: path q's region of the segment list; out: path q's buffer
+LAB_DEV void lat_path_setup_body(Params const &p, Lattice const &lt, int q, uint32_t rank, uint32_t D, int fr, int fc, int sr, int sc, uint32_t repaint,
                                  uint16_t *grid, int32_t *out, unsigned long long max_out, uint32_t *seg) {
     Tree_ctl *tc = lt.tc;
     Geom const &g = p.g;
     uint32_t const *dist = p.plane[0].dist;
-    tc->lat_path_nseg = 0u;
+    uint32_t nseg = 0;
     // the first square of the path, if it lies in the finish's tile: that tile's own segment begins there
     int const dr[4] = {-1, 0, 1, 0}, dc[4] = {0, 1, 0, -1};
     for (int k = 0; k < 4 && D > 0 && fr >= 0; k++) {
         int const r = fr + dr[k], c = fc + dc[k];
         if (r >= 0 && r < g.rows && c >= 0 && c < g.cols && dist[static_cast<long long>(r) * g.cols + c] == D - 1u) {
             if (r / TS == fr / TS && c / TS == fc / TS) {
-                seg[tc->lat_path_nseg++] = static_cast<uint32_t>(r) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(c);
+                seg[nseg++] = static_cast<uint32_t>(r) * static_cast<uint32_t>(g.cols) + static_cast<uint32_t>(c);
             }
             break;
         }
@@ -1273,27 +1274,40 @@ LAB_DEV void lat_path_setup_body(Params const &p, Lattice const &lt, uint32_t ra
             out[2ull * (D - 1u) + 1] = sc;
         }
     }
-    tc->lat_path_rank = rank;
-    tc->lat_path_level = D;
-    tc->lat_path_on = 1u;
+    tc->lat_path_rank[q] = rank;
+    tc->lat_path_level[q] = D;
+    tc->lat_path_nseg[q] = nseg;
+    lab_atomic_or(&tc->lat_path_on, 1u << q);
 }
-// lat_path_begin_body: one warp, one GPU.  seg: room for the segments' first squares (flat indices).
-LAB_DEV void lat_path_begin_body(Params const &p, Lattice const &lt, Result *res, int32_t const *finish_rc, uint16_t *grid, int32_t *out,
-                                 unsigned long long max_out, uint32_t *seg, int lane) {
+// lat_path_begin_body: one GPU; warp q of four (after lat_path_on and the counts were cleared).  hunt: warp 0 alone, the winner's
+// path, repainted in its colour; gather (paths wanted): warp q = colour q's path to the finish it claims, nothing repainted.
+// seg: room for the segments' first squares (flat indices), a quarter per path; out: the paths' buffers, out_stride pairs apart.
+LAB_DEV void lat_path_begin_body(Params const &p, Lattice const &lt, int game, Result *res, int32_t const *finish_rc, uint16_t *grid, int32_t *out,
+                                 unsigned long long out_stride, unsigned long long max_out, uint32_t *seg, uint32_t seg_cap, int q, int lane) {
     Tree_ctl *tc = lt.tc;
     Control *ctl = p.ctl;
     Geom const &g = p.g;
-    if (lane == 0) {
-        tc->lat_path_on = 0u;
-        tc->lat_path_nseg = 0u;
-    }
-    if (!lat_live(tc) || !ctl->painted || res->winner < 0) {
+    if (!lat_live(tc) || !ctl->painted || ctl->fronts_done) { // (fronts_done: the field was not written)
         return;
     }
-    int const fr = finish_rc[0], fc = finish_rc[1];
+    int fj = 0;
+    if (game == GAME_HUNT) {
+        if (q != 0 || res->winner < 0) return;
+    } else {
+        fj = res->finish_of[q];
+        if (fj < 0) { // (as k_walk leaves an unclaimed colour)
+            if (lane == 0) {
+                res->path_len[q] = 0;
+                if (out) out[static_cast<unsigned long long>(q) * out_stride * 2] = -1;
+            }
+            return;
+        }
+    }
+    int const fr = finish_rc[2 * fj], fc = finish_rc[2 * fj + 1];
     uint32_t const D = p.plane[0].dist[static_cast<long long>(fr) * g.cols + fc];
     if (D == INF || ((fr | fc) & 1) == 0) {
-        return; // (the one-warp walk says what there is to say)
+        if (lane == 0) ctl->walk_fallback = 1u; // (the one-warp walk says what there is to say)
+        return;
     }
     uint32_t const rank = lat_path_rank_body(p, lt, fr, fc, lane);
     if (lane != 0) {
@@ -1302,21 +1316,28 @@ LAB_DEV void lat_path_begin_body(Params const &p, Lattice const &lt, Result *res
     uint32_t const t0 = ctl->src_tile[0];
     int const sr = static_cast<int>(t0 / static_cast<uint32_t>(g.tiles_x)) * TS + static_cast<int>(ctl->src_rc[0] >> 8);
     int const sc = static_cast<int>(t0 % static_cast<uint32_t>(g.tiles_x)) * TS + static_cast<int>(ctl->src_rc[0] & 0xFFu);
-    lat_path_setup_body(p, lt, rank, D, fr, fc, sr, sc, (1u << res->winner) << SQ_PAINT_SHIFT, grid, out, max_out, seg);
-    res->walk_r[0] = D > 0 ? sr : fr;
-    res->walk_c[0] = D > 0 ? sc : fc;
-    res->path_len[0] = D;
-    res->walk_left[0] = 0;
-    ctl->walked = 1u;
+    uint32_t const repaint = game == GAME_HUNT ? (1u << res->winner) << SQ_PAINT_SHIFT : 0u;
+    lat_path_setup_body(p, lt, q, rank, D, fr, fc, sr, sc, repaint, grid, out ? out + static_cast<unsigned long long>(q) * out_stride * 2 : nullptr, max_out,
+                        seg + static_cast<size_t>(q) * (seg_cap / 4));
+    res->walk_r[q] = D > 0 ? sr : fr;
+    res->walk_c[q] = D > 0 ? sc : fc;
+    res->path_len[q] = D;
+    res->walk_left[q] = 0;
 }
 // warp per tile: the crossings the path comes up through
 LAB_DEV void lat_path_find_body(Params const &p, Lattice const &lt, uint32_t *seg, uint32_t seg_cap, long long gwarp, long long nwarps, int lane) {
     Tree_ctl *tc = lt.tc;
     Geom const &g = p.g;
-    if (!tc->lat_path_on || tc->lat_path_rank == 0u) {
+    uint32_t const on = tc->lat_path_on;
+    uint32_t RF[4];
+    bool any = false;
+    for (int q = 0; q < 4; q++) {
+        RF[q] = ((on >> q) & 1u) ? tc->lat_path_rank[q] : 0u; // (0: no such path, or its finish lies in a root's component: nobody's descendant)
+        any = any || RF[q] != 0u;
+    }
+    if (!any) {
         return;
     }
-    uint32_t const RF = tc->lat_path_rank;
     for (long long t = gwarp; t < g.ntiles; t += nwarps) {
         long long const base = t * LSLOTS;
         uint32_t const ty = static_cast<uint32_t>(t / g.tiles_x), tx = static_cast<uint32_t>(t % g.tiles_x);
@@ -1329,12 +1350,15 @@ LAB_DEV void lat_path_find_body(Params const &p, Lattice const &lt, uint32_t *se
                 uint32_t const twl = tw - lt.tile_base * LSLOTS;
                 // (a twin in another band is a border arc of its super-tile: its hops are in the whole-maze border list)
                 uint32_t const down = twl < lt.nslots ? lab_ld_cg(lt.R + twl) : static_cast<uint32_t>(lab_ld_cg(lt.gb + lat_dense_border(lt, g, tw)) >> 32);
-                if (up < RF && RF <= down) {
-                    uint32_t const r = ty * TS + (s == L_N ? 0u : (s == L_S ? TS - 1u : 2u * lane + 1u));
-                    uint32_t const c = tx * TS + (s == L_W ? 0u : (s == L_E ? TS - 1u : 2u * lane + 1u));
-                    uint32_t const at = lab_atomic_add(&tc->lat_path_nseg, 1u);
-                    if (at < seg_cap) {
-                        seg[at] = r * static_cast<uint32_t>(g.cols) + c;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (RF[q] != 0u && up < RF[q] && RF[q] <= down) {
+                        uint32_t const r = ty * TS + (s == L_N ? 0u : (s == L_S ? TS - 1u : 2u * lane + 1u));
+                        uint32_t const c = tx * TS + (s == L_W ? 0u : (s == L_E ? TS - 1u : 2u * lane + 1u));
+                        uint32_t const at = lab_atomic_add(&tc->lat_path_nseg[q], 1u);
+                        if (at < seg_cap / 4) {
+                            seg[static_cast<size_t>(q) * (seg_cap / 4) + at] = r * static_cast<uint32_t>(g.cols) + c;
+                        }
                     }
                 }
             }
@@ -1342,18 +1366,23 @@ LAB_DEV void lat_path_find_body(Params const &p, Lattice const &lt, uint32_t *se
     }
 }
 // warp per segment (wid of nw warps; sm: WALK_SM_U32 words)
-LAB_DEV void lat_path_walk_body(Params const &p, Lattice const &lt, Result *res, uint32_t repaint, uint16_t *grid, int32_t *out, unsigned long long max_out,
-                                uint32_t const *seg, uint32_t seg_cap, long long wid, long long nw, int lane, uint32_t *sm) {
+LAB_DEV void lat_path_walk_body(Params const &p, Lattice const &lt, Result *res, uint32_t repaint, uint16_t *grid, int32_t *out, unsigned long long out_stride,
+                                unsigned long long max_out, uint32_t const *seg, uint32_t seg_cap, long long wid, long long nw, int lane, uint32_t *sm) {
     Tree_ctl const *tc = lt.tc;
-    if (!tc->lat_path_on) {
-        return;
-    }
-    uint32_t const n = tc->lat_path_nseg < seg_cap ? tc->lat_path_nseg : seg_cap, D = tc->lat_path_level;
-    for (long long i = wid; i < n; i += nw) {
-        uint32_t const sq = lab_ld_cg(seg + i);
-        int const r = static_cast<int>(sq / static_cast<uint32_t>(p.g.cols)), c = static_cast<int>(sq % static_cast<uint32_t>(p.g.cols));
-        uint32_t const d = p.plane[0].dist[sq];
-        walk_body(p, 0, r, c, grid, out, max_out, repaint, 0, res, 0, lane, sm, 1, D - 1u - d, 1);
+    uint32_t const on = tc->lat_path_on;
+    for (int q = 0; q < 4; q++) {
+        if (!((on >> q) & 1u)) {
+            continue;
+        }
+        uint32_t const n = tc->lat_path_nseg[q] < seg_cap / 4 ? tc->lat_path_nseg[q] : seg_cap / 4, D = tc->lat_path_level[q];
+        uint32_t const *list = seg + static_cast<size_t>(q) * (seg_cap / 4);
+        int32_t *out_q = out ? out + static_cast<unsigned long long>(q) * out_stride * 2 : nullptr;
+        for (long long i = wid; i < n; i += nw) {
+            uint32_t const sq = lab_ld_cg(list + i);
+            int const r = static_cast<int>(sq / static_cast<uint32_t>(p.g.cols)), c = static_cast<int>(sq % static_cast<uint32_t>(p.g.cols));
+            uint32_t const d = p.plane[0].dist[sq];
+            walk_body(p, 0, r, c, grid, out_q, max_out, repaint, 0, res, 0, lane, sm, 1, D - 1u - d, 1);
+        }
     }
 }
 

@@ -63,9 +63,9 @@ struct Tree_ctl {
     uint32_t lat_ticket[4];  // dynamic tile counters: link, local ranking, flood, levels
     unsigned long long lat_settled;
     unsigned long long lat_settled_band; // row bands: this band's share (lat_settled is the whole maze's after the exchange)
-    // the winner's path from the tour's ranks (lat_path_*): rank of the entry arc of the finish's component (0: a root's
+    // paths from the tour's ranks (lat_path_*): rank of the entry arc of the finish's component (0: a root's
     // component), the finish's level, segments found
-    uint32_t lat_path_rank, lat_path_level, lat_path_nseg, lat_path_on;
+    uint32_t lat_path_rank[4], lat_path_level[4], lat_path_nseg[4], lat_path_on; // (per path: hunt has one, gather four; _on: a bit per path)
 };
 
 struct Tree {

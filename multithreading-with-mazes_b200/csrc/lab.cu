@@ -230,23 +230,34 @@ template <int MODE> __global__ void __launch_bounds__(128, (MODE == LAT_PAINT ||
     __shared__ uint32_t sm[4][L_LINK_SM];
     lat_levels_body<MODE>(p, lt, lane_id(), sm[threadIdx.x >> 5], res, grid);
 }
-// hunt on the lattice road: the winner's path from the tour's ranks (lat_path_*), every segment walked on its own
-__global__ void k_lat_path_begin(Params p, Lattice lt, Result *res, int32_t const *finish_rc, uint16_t *grid, int32_t *out, unsigned long long max_out,
-                                 uint32_t *seg) {
-    lat_path_begin_body(p, lt, res, finish_rc, grid, out, max_out, seg, lane_id());
+// hunt (the winner's path) and gather with paths (every colour's) on the lattice road: paths from the tour's ranks (lat_path_*),
+// every segment walked on its own
+__global__ void __launch_bounds__(128) k_lat_path_begin(Params p, Lattice lt, int game, Result *res, int32_t const *finish_rc, uint16_t *grid, int32_t *out,
+                                                        unsigned long long out_stride, unsigned long long max_out, uint32_t *seg, uint32_t seg_cap) {
+    Tree_ctl *tc = lt.tc;
+    if (threadIdx.x == 0) {
+        tc->lat_path_on = 0u;
+        for (int q = 0; q < 4; q++) tc->lat_path_nseg[q] = 0u;
+    }
+    __syncthreads();
+    lat_path_begin_body(p, lt, game, res, finish_rc, grid, out, out_stride, max_out, seg, seg_cap, static_cast<int>(threadIdx.x >> 5), lane_id());
+    __syncthreads();
+    if (threadIdx.x == 0 && lat_live(tc) && p.ctl->painted && !p.ctl->fronts_done && !p.ctl->walk_fallback && (game != GAME_HUNT || res->winner >= 0)) {
+        p.ctl->walked = 1u; // (k_walk: nothing left to do)
+    }
 }
 __global__ void __launch_bounds__(256) k_lat_path_find(Params p, Lattice lt, uint32_t *seg, uint32_t seg_cap) {
     lat_path_find_body(p, lt, seg, seg_cap, gwarp_id(), nwarps_total(), lane_id());
 }
 // repaint_bits == 0xFFFFFFFF: the winner's colour (Result::winner, known on the device only)
-__global__ void k_lat_path_walk(Params p, Lattice lt, Result *res, uint32_t repaint_bits, uint16_t *grid, int32_t *out, unsigned long long max_out,
-                                uint32_t const *seg, uint32_t seg_cap) {
+__global__ void k_lat_path_walk(Params p, Lattice lt, Result *res, uint32_t repaint_bits, uint16_t *grid, int32_t *out, unsigned long long out_stride,
+                                unsigned long long max_out, uint32_t const *seg, uint32_t seg_cap) {
     __shared__ uint32_t sm[WALK_SM_U32]; // one warp per block
     if (!lt.tc->lat_path_on) {
         return;
     }
     uint32_t const repaint = repaint_bits == 0xFFFFFFFFu ? (1u << res->winner) << SQ_PAINT_SHIFT : repaint_bits;
-    lat_path_walk_body(p, lt, res, repaint, grid, out, max_out, seg, seg_cap, blockIdx.x, gridDim.x, lane_id(), sm);
+    lat_path_walk_body(p, lt, res, repaint, grid, out, out_stride, max_out, seg, seg_cap, blockIdx.x, gridDim.x, lane_id(), sm);
 }
 // row bands (lab_band_lat_path_*)
 __global__ void k_lat_path_rank(Params p, Lattice lt, int r, int c, uint32_t *out2) {
@@ -258,7 +269,9 @@ __global__ void k_lat_path_rank(Params p, Lattice lt, int r, int c, uint32_t *ou
 }
 __global__ void k_lat_path_setup(Params p, Lattice lt, uint32_t rank, uint32_t level, int fr, int fc, int sr, int sc, uint32_t repaint, uint16_t *grid,
                                  int32_t *out, unsigned long long max_out, uint32_t *seg) {
-    lat_path_setup_body(p, lt, rank, level, fr, fc, sr, sc, repaint, grid, out, max_out, seg);
+    lt.tc->lat_path_on = 0u;
+    for (int q = 0; q < 4; q++) lt.tc->lat_path_nseg[q] = 0u;
+    lat_path_setup_body(p, lt, 0, rank, level, fr, fc, sr, sc, repaint, grid, out, max_out, seg);
 }
 // hunt / gather on the lattice road: the finishes' levels and the paint rules BEFORE the field is written (lat_targets_body)
 // front_rc != null (gather, no paths, the field not wanted): every colour's path.front() by probing too (lat_fronts_body)
@@ -336,6 +349,10 @@ __global__ void k_walk(Params p, int game, uint16_t *grid, Result *res, int32_t 
     uint32_t repaint = 0;
     if (game == GAME_HUNT && p.ctl->walked) { // lat_path_*: the path is marked and written already; its length is the finish's level
         if (lane_id() == 0) res->path_len[slot] = res->game_level[0];
+        return;
+    }
+    if (game == GAME_GATHER && !first_only && p.ctl->walked) { // lat_path_*: every colour's path is written already
+        if (lane_id() == 0) res->path_len[slot] = res->finish_of[slot] >= 0 ? res->game_level[slot] : 0;
         return;
     }
     if (game == GAME_GATHER && first_only && p.ctl->fronts_done) { // lat_fronts_body: path.front() is known (and no field exists to step on)
@@ -838,14 +855,16 @@ int run_lattice(lab_grid *h, Params const &p, Run_desc const &d) {
             k_lat_levels<LAT_PAINT><<<tile_blocks, 128, 0, s>>>(p, lt, h->res, h->squares);
         }
         h->launches += 1;
-        if (d.game == GAME_HUNT && env_ll("LAB_LAT_PATH", 1) != 0) {
-            // the winner's path, painted over the colours just applied (k_walk then returns at once).  The segments' list
-            // borrows the local ranking's pair array, which nobody reads after k_lat_rank_expand.
+        if ((d.game == GAME_HUNT || (d.game == GAME_GATHER && h->hunt_out)) && !skip_field && env_ll("LAB_LAT_PATH", 1) != 0) {
+            // hunt: the winner's path, painted over the colours just applied; gather with paths: every colour's path written
+            // out (k_walk then returns at once).  The segments' list borrows the local ranking's pair array, which nobody
+            // reads after k_lat_rank_expand.
             uint32_t *seg = reinterpret_cast<uint32_t *>(lt.xd);
             uint32_t const seg_cap = lt.nslots;
-            k_lat_path_begin<<<1, 32, 0, s>>>(p, lt, h->res, h->d_finish_rc, h->squares, h->hunt_out, h->hunt_out_cap, seg);
+            k_lat_path_begin<<<1, 128, 0, s>>>(p, lt, d.game, h->res, h->d_finish_rc, h->squares, h->hunt_out, h->path_cap, h->hunt_out_cap, seg, seg_cap);
             k_lat_path_find<<<blocks_for(h, nt, 256), 256, 0, s>>>(p, lt, seg, seg_cap);
-            k_lat_path_walk<<<h->sm_count * 8, 32, 0, s>>>(p, lt, h->res, 0xFFFFFFFFu, h->squares, h->hunt_out, h->hunt_out_cap, seg, seg_cap);
+            k_lat_path_walk<<<h->sm_count * 8, 32, 0, s>>>(p, lt, h->res, d.game == GAME_HUNT ? 0xFFFFFFFFu : 0u, h->squares, h->hunt_out, h->path_cap,
+                                                           h->hunt_out_cap, seg, seg_cap);
             TRACE("k_lat_path_walk", s);
             h->launches += 3;
         }
@@ -1558,8 +1577,8 @@ static int solver_common(lab_grid *h, Run_desc const &d, lab_point const *finish
     if (d.game == GAME_GATHER) {
         CU(cudaMemsetAsync(h->d_front_rc, 0xFF, 8 * sizeof(int32_t), s)); // (before the search: the lattice road may fill it in)
     }
-    if (d.game == GAME_HUNT && want_paths) { // (the lattice road writes the winner's path itself: it needs the buffer before the search)
-        rc = ensure_paths(h, path_cap, 1);
+    if ((d.game == GAME_HUNT || d.game == GAME_GATHER) && want_paths) { // (the lattice road writes the paths itself: it needs the buffer before the search)
+        rc = ensure_paths(h, path_cap, d.game == GAME_GATHER ? 4 : 1);
         if (rc) {
             return rc;
         }
@@ -2109,12 +2128,12 @@ int lab_band_lat_path_mark(lab_grid *h, uint32_t rank, uint32_t level, int fin_r
     int32_t *out = static_cast<int32_t *>(path_dev);
     k_lat_path_setup<<<1, 1, 0, s>>>(p, lt, rank, level, fin_r, fin_c, start_r, start_c, repaint_bits, h->squares, out, path_cap, seg);
     k_lat_path_find<<<blocks_for(h, h->g.ntiles, 256), 256, 0, s>>>(p, lt, seg, seg_cap);
-    k_lat_path_walk<<<h->sm_count * 8, 32, 0, s>>>(p, lt, h->res, repaint_bits, h->squares, out, path_cap, seg, seg_cap);
+    k_lat_path_walk<<<h->sm_count * 8, 32, 0, s>>>(p, lt, h->res, repaint_bits, h->squares, out, 0, path_cap, seg, seg_cap);
     TRACE("k_lat_path_walk", s);
     h->launches += 3;
     CU(cudaGetLastError());
     uint32_t n = 0;
-    CU(cudaMemcpyAsync(&n, &lt.tc->lat_path_nseg, sizeof n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&n, &lt.tc->lat_path_nseg[0], sizeof n, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (segments) *segments = n;
     return LAB_OK;

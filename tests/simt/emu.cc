@@ -112,16 +112,27 @@ void run_tree(Workspace &w, Params &p, Run_desc const &d, int nwarps, unsigned s
                 simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body<LAT_PAINT_ONLY>(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS, &w.res, w.grid_ptr); }, sched_seed);
             } else
             simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body<LAT_PAINT>(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS, &w.res, w.grid_ptr); }, sched_seed);
-            if (d.game == GAME_HUNT) { // the winner's path from the tour's ranks, as run_lattice() launches it
+            if ((d.game == GAME_HUNT || (d.game == GAME_GATHER && g_hunt_out)) && !skip_field) { // paths from the tour's ranks, as run_lattice() launches them
                 uint32_t *seg = reinterpret_cast<uint32_t *>(xd.data());
                 uint32_t const seg_cap = lt.nslots;
-                simt::launch(1, [&](int, int lane) { lat_path_begin_body(p, lt, &w.res, frc, w.grid_ptr, g_hunt_out, g_hunt_out_cap, seg, lane); });
+                tc.lat_path_on = 0u;
+                for (int q = 0; q < 4; q++) tc.lat_path_nseg[q] = 0u;
+                simt::launch(4, [&](int wid, int lane) {
+                    lat_path_begin_body(p, lt, d.game, &w.res, frc, w.grid_ptr, g_hunt_out, g_hunt_out_cap, g_hunt_out_cap, seg, seg_cap, wid, lane);
+                });
+                if (lat_live(lt.tc) && p.ctl->painted && !p.ctl->fronts_done && !p.ctl->walk_fallback && (d.game != GAME_HUNT || w.res.winner >= 0)) {
+                    p.ctl->walked = 1u;
+                }
                 simt::launch(nwarps, [&](int wid, int lane) { lat_path_find_body(p, lt, seg, seg_cap, wid, nwarps, lane); });
                 std::vector<uint32_t> wsm(static_cast<size_t>(nwarps) * WALK_SM_U32);
+                uint32_t const repaint = d.game == GAME_HUNT && w.res.winner >= 0 ? (1u << w.res.winner) << SQ_PAINT_SHIFT : 0u;
                 simt::launch(nwarps, [&](int wid, int lane) {
-                    if (tc.lat_path_on) lat_path_walk_body(p, lt, &w.res, (1u << w.res.winner) << SQ_PAINT_SHIFT, w.grid_ptr, g_hunt_out, g_hunt_out_cap, seg, seg_cap, wid, nwarps, lane, wsm.data() + static_cast<size_t>(wid) * WALK_SM_U32);
+                    if (tc.lat_path_on) lat_path_walk_body(p, lt, &w.res, repaint, w.grid_ptr, g_hunt_out, g_hunt_out_cap, g_hunt_out_cap, seg, seg_cap, wid, nwarps, lane, wsm.data() + static_cast<size_t>(wid) * WALK_SM_U32);
                 });
-                if (tc.lat_path_on) g_path_segments = static_cast<int>(tc.lat_path_nseg);
+                if (tc.lat_path_on) {
+                    g_path_segments = 0;
+                    for (int q = 0; q < 4; q++) g_path_segments += static_cast<int>(tc.lat_path_nseg[q]);
+                }
             }
         } else {
             simt::launch(nwarps, [&](int wid, int lane) { lat_levels_body<LAT_LEVELS>(p, lt, lane, lsm.data() + static_cast<size_t>(wid) * LSUP_SLOTS, nullptr, nullptr); }, sched_seed);
@@ -816,13 +827,15 @@ int emu_band_lat_path_mark(void *h, uint32_t rank, uint32_t level, int fin_r, in
     int const nw = e->nwarps;
     uint32_t *seg = reinterpret_cast<uint32_t *>(e->l_xd.data());
     uint32_t const seg_cap = lt.nslots;
-    lat_path_setup_body(p, lt, rank, level, fin_r, fin_c, start_r, start_c, repaint_bits, e->w.grid_ptr, path, path_cap, seg);
+    e->lat_tc.lat_path_on = 0u;
+    for (int q = 0; q < 4; q++) e->lat_tc.lat_path_nseg[q] = 0u;
+    lat_path_setup_body(p, lt, 0, rank, level, fin_r, fin_c, start_r, start_c, repaint_bits, e->w.grid_ptr, path, path_cap, seg);
     simt::launch(nw, [&](int wid, int lane) { lat_path_find_body(p, lt, seg, seg_cap, wid, nw, lane); });
     std::vector<uint32_t> wsm(static_cast<size_t>(nw) * WALK_SM_U32);
     simt::launch(nw, [&](int wid, int lane) {
-        lat_path_walk_body(p, lt, &e->w.res, repaint_bits, e->w.grid_ptr, path, path_cap, seg, seg_cap, wid, nw, lane, wsm.data() + static_cast<size_t>(wid) * WALK_SM_U32);
+        lat_path_walk_body(p, lt, &e->w.res, repaint_bits, e->w.grid_ptr, path, 0, path_cap, seg, seg_cap, wid, nw, lane, wsm.data() + static_cast<size_t>(wid) * WALK_SM_U32);
     });
-    if (segments) *segments = e->lat_tc.lat_path_nseg;
+    if (segments) *segments = e->lat_tc.lat_path_nseg[0];
     return 0;
 }
 
@@ -872,8 +885,8 @@ int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *star
         frc[0] = finishes[0];
         frc[1] = finishes[1];
     }
-    g_hunt_out = game == GAME_HUNT ? paths_out : nullptr;
-    g_hunt_out_cap = game == GAME_HUNT ? static_cast<unsigned long long>(max_path) : 0ull;
+    g_hunt_out = ((game == GAME_HUNT || game == GAME_GATHER) && max_path > 0) ? paths_out : nullptr; // (gather: four buffers, max_path pairs apart)
+    g_hunt_out_cap = g_hunt_out ? static_cast<unsigned long long>(max_path) : 0ull;
     int32_t front[8];
     for (auto &x : front) x = -1;
     g_front_rc = front;
@@ -902,6 +915,10 @@ int emu_solver(int game, int rows, int cols, uint16_t *grid, int32_t const *star
             plane = w.res.winner;
         } else {
             if (first_only && w.ctl.fronts_done) return; // (k_walk: lat_fronts_body has found path.front())
+            if (!first_only && w.ctl.walked) {           // (k_walk: lat_path_* has written every colour's path)
+                w.res.path_len[slot] = w.res.finish_of[slot] >= 0 ? w.res.game_level[slot] : 0;
+                return;
+            }
             fj = w.res.finish_of[slot];
             if (fj < 0) return;
         }

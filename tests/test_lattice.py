@@ -164,7 +164,7 @@ def test_emulated_games_on_the_lattice(lab, O, emu):
         placed, s, fin = lab.place_gather(maze, seed=seed)
         g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
         g, _, c, paths, _ = emu.solver(2, placed, [s], fin, 4, 1)
-        assert emu.lib.emu_last_paint_fused() == 1
+        assert emu.lib.emu_last_paint_fused() == 1 and emu.lib.emu_last_path_segments() >= 4  # (all four paths from the tour's ranks, in segments)
         assert (g == g_ref).all() and (c == c_ref).all() and paths_equal(paths, p_ref)
 
 
