@@ -387,6 +387,29 @@ def test_sharded_hunt_on_the_lattice_road_on_gloo(lab, O, tmp_path, builder, row
     assert done == 2
 
 
+def test_sharded_gather_on_the_lattice_road_on_gloo(lab, O, tmp_path):
+    """Bfs::gather across bands of whole super-tile rows: the lattice road's field, claims and path.front() recolours by the
+    owning bands, the four paths walked band by band on that field."""
+    import torch.multiprocessing as mp
+
+    maze = lab.build_maze("kruskal", 767, 131, seed=61)
+    seed = next(q for q in range(100) if all(int(x) % 2 == 1 for x in lab.place_gather(maze, seed=q)[1]))
+    placed, s, fin = lab.place_gather(maze, seed=seed)
+    path = str(tmp_path / "maze.npy")
+    np.save(path, placed)
+    spec = {"start": tuple(int(x) for x in s), "finishes": [tuple(int(x) for x in q) for q in fin], "super": True}
+    mp.spawn(_gloo_game_worker, args=(3, _free_port(), path, str(tmp_path), "gather", spec), nprocs=3, join=True)
+    g_ref, c_ref, p_ref = O.canon_gather(placed, s, fin)
+    z = [np.load(tmp_path / f"band{r}.npz") for r in range(3)]
+    assert all(str(b["road"]) == "lattice" for b in z)
+    got = np.concatenate([b["sq"] for b in z])
+    assert (got == g_ref).all(), int((got != g_ref).sum())
+    for b in z:
+        assert (b["claimed_by"] == c_ref).all()
+        for k in range(4):
+            assert (b[f"path{k}"] == np.asarray(p_ref[k]).reshape(-1, 2)).all()
+
+
 def _hunt_and_gather_checks(lab, O, tmp_path, maze, world, road, seed=7):
     import torch.multiprocessing as mp
 
