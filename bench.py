@@ -14,8 +14,11 @@ Default workload ``h-32767`` = BASELINE.json's north_star headline: the BFS dist
 to the reference builder's output for that seed; cached as a raw maze file under /dev/shm so that a box pays the
 host build once).  ``value`` / ``roofline`` / ``e2e`` are the distance map's, the ``gather`` object holds the same
 three for bfs-gather.  BASELINE configs[1..3] and the other sizes are ``--workload`` names.
-N > 1 (torchrun): the headline maze cut into N row bands, one per GPU (strong scaling; bands.py); other distance
-workloads run ONE maze N times taller (weak); the other games run one maze per GPU.
+The games run as the reference's static entry points do (Bfs::gather shows the grid alone): LAB_OPT_SOLVER_LEVELS is off, so
+bfs-gather does not keep a level field nobody reads (4 bytes per square, the Squares read and written).
+N > 1 (torchrun): the headline maze cut into N row bands, one per GPU (strong scaling; bands.py); the corners workloads
+likewise (bands.sharded_corners); other distance workloads run ONE maze N times taller (weak); the other games run one
+maze per GPU.
 
   value      cells settled / second (G/s) with the maze already resident in HBM: K steps, each timed
              with CUDA events on the launching stream (the Square grid is restored from a pristine
