@@ -3,7 +3,7 @@
 // These produce the packed Square grids the solvers/painters consume.  They are linear-time
 // restatements on a flat uint16_t array of the reference generators that BASELINE.json's
 // configs name, and -- given the same seed for the RNG the reference seeds from
-// std::random_device -- they emit byte-identical grids (tests/test_builders.py checks this
+// std::random_device -- they emit byte-identical grids (tests/test_oracle_vs_reference.py checks this
 // against the real reference text on a size/seed ladder; tests/golden/ pins it on the GPU box).
 //
 //   arena    builders/arena.cc:17-26
