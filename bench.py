@@ -218,7 +218,7 @@ def bench_game(lab, torch, maze, spec, args, flush, e2e_steps):
     del pristine, work, levels
     torch.cuda.empty_cache()
     e_ms, e_settled, e_lanes = e2e_leg(lab, torch, maze, spec, flush, e2e_steps)
-    return {"game": game, "cells": cells, "step_ms": step_ms, "settled": settled, "t": t, "stats": stats, "e_ms": e_ms,
+    return {"game": game, "cells": cells, "rows": rows, "cols": cols, "step_ms": step_ms, "settled": settled, "t": t, "stats": stats, "e_ms": e_ms,
             "e_settled": e_settled, "e_steps": e2e_steps, "e_lanes": e_lanes, "h2d": cells * 2,
             "d2h": cells * 2 + (cells * 4 if game == "distance" else 0)}
 
@@ -302,6 +302,12 @@ ROADS = {0: "tile wave (k_bfs_tiles, csrc/device/engine.cuh)",
          3: "lattice road (k_lat_link, k_lat_rank_local/global/expand, k_lat_flood, k_lat_scan_*, k_lat_levels; csrc/device/lattice.cuh)"}
 
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one search phase, from the ncu launch list of the default command
+# with this code (profiles/r02b_launches_h-32767.md: the kernels between k_pack and the epilogue, one headline-size search);
+# keyed by (rows, cols, game, road).  Other workloads: null.
+NCU_TRAFFIC = {(32767, 32767, "distance", 3): 8.95e9, (32767, 32767, "gather", 3): 7.27e9}
+
+
 def game_record(m, args, world, reduce_max, reduce_sum):
     """One game's measurements -> the JSON fields (value, roofline, e2e ...), max over ranks / whole-job sums."""
     step_ms, e_ms, search_ms, post_ms, total_ms = reduce_max([m["step_ms"], m["e_ms"], m["t"]["search_ms"], m["t"]["post_ms"], m["t"]["total_ms"]])
@@ -319,7 +325,9 @@ def game_record(m, args, world, reduce_max, reduce_sum):
     return {
         "value": settled / (step_ms * 1e-3) / 1e9, "unit": "Gcells/s", "ms_per_step": step_ms / args.steps,
         "cells_settled_per_step": m["settled"] // args.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_TRAFFIC.get((m["rows"], m["cols"], game, road)),
+                     "traffic_source": "profiles/r02b_launches_h-32767.md (ncu launch list, search-phase kernels of one search)" if (m["rows"], m["cols"], game, road) in NCU_TRAFFIC else None,
                      "kernel": "search phase = " + ROADS.get(road, "?"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms_sum / step_ms,
                      "whole_step": {"achieved": whole, "frac": whole / peak,
